@@ -1,0 +1,259 @@
+/* ====================================================================================================
+ *  sphb200.h — C ABI of libsphb200.so: the B200-native (sm_100a) weakly-compressible SPH hot path.
+ *
+ *  This is the drop-in boundary for what SPHinXsys reaches today through `execution::par_device`
+ *  (SYCL).  Generic lambdas cannot cross a C ABI, so the seam sits one level up, at the `exec()` of each
+ *  dynamics class: every entry point below replaces the device launches one reference `exec()` makes.
+ *  Citations are `path:line` relative to /root/reference/src/shared unless a longer path is given.
+ *
+ *  Conventions
+ *    - every function returns int: 0 = OK, < 0 = SPHB200_E_* below, > 0 = a cudaError_t value;
+ *      nothing throws or exits; sphb200_last_error_string() describes the last failure of a context.
+ *    - all pointers inside *_view_t / *_args_t are DEVICE pointers unless the field says "host";
+ *      the library never owns particle data, only its own scratch (sort buffers, histograms).
+ *    - `stream` is a cudaStream_t passed as void*; calls are asynchronous on it except where a value is
+ *      returned to the host (scan total, reductions, required capacities), exactly where the reference
+ *      synchronises too (particle_iterators_sycl.h:80-105, algorithm_primitive_sycl.h:96-122).
+ *    - Vecd variables live on the device as float4 (x, y, z, w); `w` is padding unless stated. Host
+ *      `Vecd*` arrays (packed 3 floats) are converted with sphb200_vec3_to_vec4 / sphb200_vec4_to_vec3.
+ *      2-D cases use the same kernels with z == 0 and one cell layer in z.
+ *    - Real = float, UnsignedInt = uint32_t (base_data_type.h:50-60 under SPHINXSYS_USE_SYCL).
+ * ==================================================================================================== */
+#ifndef SPHB200_H
+#define SPHB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SPHB200_VERSION 100
+
+enum
+{
+    SPHB200_OK = 0,
+    SPHB200_E_INVALID = -1,     /* bad argument (null pointer, unsupported enum, n too large) */
+    SPHB200_E_CAPACITY = -2,    /* output buffer smaller than required; required size is returned */
+    SPHB200_E_UNSUPPORTED = -3, /* type tuple outside the closed set listed in DESIGN.md */
+    SPHB200_E_NOMEM = -4
+};
+
+typedef struct sphb200_context sphb200_context_t; /* opaque; one per GPU, one driving host thread */
+
+typedef struct { float x, y, z, w; } sphb200_vec4_t;
+
+/* Mesh POD; ref: meshes/base_mesh.h, base_mesh.cpp:6-16 (computed by the host in Real precision). */
+typedef struct
+{
+    float lower[3];   /* mesh_lower_bound_ */
+    float spacing;    /* grid_spacing_ */
+    int32_t cells[3]; /* all_cells_ = all_grid_points_ - 1 ; cells[2] == 1 in 2-D */
+} sphb200_mesh_t;
+
+/* KernelTabulatedCK + Neighbor<SPHAdaptation,SPHAdaptation>::SmoothingKernel scalars;
+ * ref: shared_ck/smoothing_kernel/kernel_tabulated_ck.h:37-72, shared_ck/body_relation/neighbor_method.hpp:18-142 */
+typedef struct
+{
+    int32_t dim;            /* 2 | 3 */
+    int32_t kind;           /* 0 Wendland C2, 1 Laguerre-Gauss (informational; the table defines the kernel) */
+    float h;                /* max(src_h, tar_h): inv_h_ = 1/h */
+    float src_h;            /* source smoothing length: W0 uses src_inv_h_ */
+    float kernel_size;      /* 2.0 */
+    float dimension_factor; /* Kernel::DimensionFactor{2,3}D(), base_kernel.h:91-93 */
+    float w[24];            /* w_1d[k]  = W_1D((k-1) dq), dq = kernel_size/20 */
+    float dw[24];           /* dw_1d[k] = dW_1D((k-1) dq) */
+} sphb200_kernel_t;
+
+/* WeaklyCompressibleFluid::EosKernel + RiemannSolver::ComputingKernel selection;
+ * ref: materials/weakly_compressible_fluid.h:40-70, shared_ck/.../riemann_solver/riemann_solver_ck.h:46-173 */
+typedef struct
+{
+    float rho0, c0;
+    int32_t riemann;       /* 0 NoRiemannSolverCK, 1 AcousticRiemannSolverCK, 2 DissipativeRiemannSolverCK */
+    int32_t correction;    /* 0 NoKernelCorrectionCK, 1 LinearCorrectionCK (needs fluid.B) */
+    float limiter_coeff;   /* 3.0 (riemann_solver_ck.h:97) */
+    int32_t free_surface;  /* DensityRegularization flow type: 1 FreeSurface, 0 Internal */
+} sphb200_fluid_t;
+
+/* Device views of one fluid body (the DiscreteVariables the acoustic steps register,
+ * acoustic_step_1st_half.hpp:13-39, density_regularization.hpp:14-27, fluid_time_step_ck.cpp:34-49). */
+typedef struct
+{
+    uint32_t n;                   /* TotalRealParticles */
+    sphb200_vec4_t *pos;          /* Position */
+    sphb200_vec4_t *vel;          /* Velocity */
+    sphb200_vec4_t *dpos;         /* Displacement */
+    sphb200_vec4_t *force;        /* Force */
+    sphb200_vec4_t *force_prior;  /* ForcePrior */
+    float *vol;                   /* VolumetricMeasure */
+    float *mass;                  /* Mass */
+    float *rho;                   /* Density */
+    float *p;                     /* Pressure */
+    float *compression;           /* Compression */
+    float *compression_rate;      /* CompressionRate */
+    float *vol_ref;               /* VolumetricMeasureRef */
+    float *compression_sum;       /* CompressionSummation */
+    float *B;                     /* LinearCorrectionMatrix, 9 floats row-major per particle, or NULL */
+    sphb200_vec4_t *posvol;       /* derived gather record (x, y, z, Vol): refresh with sphb200_pack_posvol
+                                     whenever Position or VolumetricMeasure changed */
+} sphb200_fluid_view_t;
+
+/* Device views of one wall (contact) body; ref: interaction_ck.hpp:79-91 (Interaction<Wall>). */
+typedef struct
+{
+    uint32_t n;
+    const sphb200_vec4_t *pos;      /* Position */
+    const sphb200_vec4_t *posvol;   /* (x, y, z, Vol) */
+    const sphb200_vec4_t *vel_ave;  /* AverageVelocity, or NULL == 0 */
+    const sphb200_vec4_t *acc_ave;  /* AverageAcceleration, or NULL == 0 */
+    const sphb200_vec4_t *normal;   /* NormalDirection */
+    const float *vol_ref;           /* VolumetricMeasureRef */
+} sphb200_wall_view_t;
+
+/* CellLinkedList<SPHAdaptation> storage; ref: meshes/cell_linked_list.cpp:167-175 */
+typedef struct
+{
+    uint32_t *cell_offset;    /* [total_cells + 1] */
+    uint32_t *particle_index; /* [max(n, 1)] ; inside a cell, ascending particle index (deterministic) */
+} sphb200_cell_list_t;
+
+/* Relation<...>::NeighborList in the library's coalesced layout ("SELL-32"): particles are grouped in
+ * slices of 32; entry k of particle i is index[slice_offset[i/32] + 32*k + (i%32)], k < count[i].
+ * Row order = reference search order (cells x->y->z, then in-cell order), so sums are reproducible.
+ * sphb200_relation_export_csr() converts to the reference's particle_offset_/neighbor_index_ form
+ * (shared_ck/body_relation/relation_ck.h:89-102). */
+typedef struct
+{
+    uint32_t *count;        /* [n + 1] neighbours of particle i (entry n is scratch for the CSR export scan) */
+    uint32_t *slice_offset; /* [ceil(n/32) + 1] */
+    uint32_t *index;        /* [capacity] */
+    uint64_t capacity;      /* entries allocated for `index` */
+} sphb200_relation_t;
+
+/* ---------------------------------------------------------------------------------------------------
+ * context, diagnostics, memory  (replaces implementation_sycl.h:43-160 ExecutionInstance + USM helpers)
+ * ------------------------------------------------------------------------------------------------- */
+int sphb200_version(void);
+int sphb200_context_create(int device, sphb200_context_t **out);
+int sphb200_context_destroy(sphb200_context_t *ctx);
+const char *sphb200_last_error_string(const sphb200_context_t *ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+uint64_t sphb200_launch_count(const sphb200_context_t *ctx);
+
+int sphb200_malloc_device(void **ptr, size_t bytes);                 /* allocateDeviceOnly, implementation_sycl.h:99-105 */
+int sphb200_malloc_host(void **ptr, size_t bytes);                   /* allocateHostStaging (pinned) */
+int sphb200_free_device(void *ptr);
+int sphb200_free_host(void *ptr);
+int sphb200_copy_h2d(void *dst, const void *src, size_t bytes, void *stream); /* copyToDevice   :117-127 */
+int sphb200_copy_d2h(void *dst, const void *src, size_t bytes, void *stream); /* copyFromDevice :129-139 */
+int sphb200_stream_sync(void *stream);
+int sphb200_fill_u32(sphb200_context_t *ctx, uint32_t *dst, uint32_t value, uint64_t n, void *stream);
+int sphb200_fill_f32(sphb200_context_t *ctx, float *dst, float value, uint64_t n, void *stream);
+/* Vecd layout conversion (device to device): packed 3-float AoS <-> float4 */
+int sphb200_vec3_to_vec4(sphb200_context_t *ctx, sphb200_vec4_t *dst, const float *src3, uint32_t n, void *stream);
+int sphb200_vec4_to_vec3(sphb200_context_t *ctx, float *dst3, const sphb200_vec4_t *src, uint32_t n, void *stream);
+int sphb200_pack_posvol(sphb200_context_t *ctx, sphb200_vec4_t *posvol, const sphb200_vec4_t *pos, const float *vol,
+                        uint32_t n, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * primitives  (replaces algorithm_primitive_sycl.h:44-137)
+ * ------------------------------------------------------------------------------------------------- */
+/* exclusive_scan(policy, first, d_first, n, plus): out[0]=0, out[i]=sum_{k<i} in[k]; the last input is not
+ * read into the result; returns out[n-1] through *last_host when non-NULL (synchronises the stream).
+ * ref: common/algorithm_primitive.h:244-279, src_sycl/.../algorithm_primitive_sycl.h:96-122 */
+int sphb200_exclusive_scan_u32(sphb200_context_t *ctx, const uint32_t *in, uint32_t *out, uint64_t n,
+                               uint32_t *last_host, void *stream);
+/* RadixSort<...>::sort_by_key: stable ascending LSD radix sort of (key, value) pairs, in place.
+ * ref: src_sycl/.../algorithm_primitive_sycl.hpp:90-238 */
+int sphb200_sort_pairs_u32(sphb200_context_t *ctx, uint32_t *keys, uint32_t *values, uint64_t n, int key_bits,
+                           void *stream);
+/* UpdateSortableVariables: dst[i] = src[perm[i]] for `count` arrays in one launch; elem_bytes[k] in {4, 16, 36}.
+ * ref: shared_ck/.../base_configuration_dynamics.h:74-128 (the reference copies then gathers, per variable) */
+int sphb200_gather_multi(sphb200_context_t *ctx, int count, void *const *dst, const void *const *src,
+                         const uint32_t *elem_bytes, const uint32_t *perm, uint32_t n, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * configuration dynamics
+ * ------------------------------------------------------------------------------------------------- */
+/* ParticleSortCK::prepareSequence: key = Morton(cell(pos)), perm[i] = i; ref: particle_sort_ck.hpp:61-67,
+ * meshes/base_mesh.hxx:9-15,85-99.  `cell_id` (linear cell index, base_mesh.hxx:73-78) optional. */
+int sphb200_morton_keys(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, const sphb200_vec4_t *pos, uint32_t n,
+                        uint32_t *keys, uint32_t *perm, uint32_t *cell_id, void *stream);
+/* ParticleSortCK::updateSortedID: sorted_id[original_id[i]] = i; ref: particle_sort_ck.hpp:69-74 */
+int sphb200_update_sorted_id(sphb200_context_t *ctx, const uint32_t *original_id, uint32_t *sorted_id, uint32_t n,
+                             void *stream);
+/* UpdateCellLinkedList::exec: count -> scan -> fill (+ in-cell ordering); ref: update_cell_linked_list.hpp:40-106 */
+int sphb200_cell_list_build(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, const sphb200_vec4_t *pos, uint32_t n,
+                            sphb200_cell_list_t list, void *stream);
+/* UpdateRelation<Inner<>>::exec and <Contact<>>::exec, split as the reference splits them so the host can
+ * grow `index` between the two phases (update_body_relation.hpp:117-164, 240-288):
+ *   *_count : fills rel.count and rel.slice_offset, returns the required capacity (entries) in *required_host
+ *   *_fill  : fills rel.index (returns SPHB200_E_CAPACITY if rel.capacity is too small)
+ * Neighbour criterion: |inv_h (x_i - x_j)|^2 < kernel_size^2, strict, ops rounded separately
+ * (neighbor_method.hpp:152-156); inner additionally j != i.  `tar_*` describe the searched body. */
+int sphb200_relation_count(sphb200_context_t *ctx, const sphb200_mesh_t *tar_mesh, const sphb200_kernel_t *kernel,
+                           const sphb200_vec4_t *src_pos, uint32_t n_src, const sphb200_vec4_t *tar_pos,
+                           sphb200_cell_list_t tar_list, int is_inner, int search_depth, sphb200_relation_t rel,
+                           uint64_t *required_host, void *stream);
+int sphb200_relation_fill(sphb200_context_t *ctx, const sphb200_mesh_t *tar_mesh, const sphb200_kernel_t *kernel,
+                          const sphb200_vec4_t *src_pos, uint32_t n_src, const sphb200_vec4_t *tar_pos,
+                          sphb200_cell_list_t tar_list, int is_inner, int search_depth, sphb200_relation_t rel,
+                          void *stream);
+/* SELL-32 -> reference CSR (particle_offset_[n+1], neighbor_index_[total]) */
+int sphb200_relation_export_csr(sphb200_context_t *ctx, sphb200_relation_t rel, uint32_t n, uint32_t *particle_offset,
+                                uint32_t *neighbor_index, uint64_t index_capacity, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * fluid dynamics
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct
+{
+    sphb200_fluid_view_t fluid;
+    sphb200_wall_view_t wall;       /* wall.n == 0: no contact body */
+    sphb200_relation_t inner;
+    sphb200_relation_t contact;
+    sphb200_kernel_t kernel;
+    sphb200_fluid_t material;
+} sphb200_fluid_args_t;
+
+/* GravityForceCK<Gravity>::update (+ForcePriorCK::update); ref: general_dynamics/force_prior_ck.hpp:38-44 */
+int sphb200_gravity_force(sphb200_context_t *ctx, const sphb200_fluid_view_t *fluid, const float gravity[3],
+                          sphb200_vec4_t *previous_force, void *stream);
+/* InteractionDynamicsCK<CompressionSummation<Inner<>,Contact<>>>::exec, optionally followed in the same launch
+ * by DensityRegularization::update (regularize != 0).  ref: fluid_dynamics/density_regularization.hpp:40-118 */
+int sphb200_compression_summation(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, int regularize, void *stream);
+int sphb200_density_regularization(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, void *stream);
+/* StateDynamics<AdvectionStepSetup>, <UpdateParticlePosition>; ref: fluid_time_step_ck.h:139-180 */
+int sphb200_advection_setup(sphb200_context_t *ctx, const sphb200_fluid_view_t *fluid, void *stream);
+int sphb200_update_position(sphb200_context_t *ctx, const sphb200_fluid_view_t *fluid, void *stream);
+/* ReduceDynamicsCK<AdvectionTimeStepCK>, <AcousticTimeStepCK>: return the REDUCED value (max) and the
+ * finished dt, as FinishDynamics::Result does.  ref: fluid_time_step_ck.hpp:31-57, fluid_time_step_ck.cpp:12-27 */
+int sphb200_advection_time_step(sphb200_context_t *ctx, const sphb200_fluid_view_t *fluid, float h_min, float u_ref,
+                                float cfl, float *reduced_host, float *dt_host, void *stream);
+int sphb200_acoustic_time_step(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, float h_min, float cfl,
+                               float *reduced_host, float *dt_host, void *stream);
+/* InteractionDynamicsCK<AcousticStep1stHalf<Inner<OneLevel,..>,Contact<Wall,..>>>::exec(dt):
+ * initialize -> interact(inner) -> interact(wall) -> update, ref: acoustic_step_1st_half.hpp:66-180,
+ * interaction_algorithms_ck.cpp:29-34.  Two launches (initialize; fused interact+update). */
+int sphb200_acoustic_1st_half(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, float dt, void *stream);
+/* ...AcousticStep2ndHalf...::exec(dt), one fused launch; ref: acoustic_step_2nd_half.hpp:33-137.
+ * When next_reduced_dev != NULL the launch also leaves max_i AcousticTimeStepCK::reduce(i) of the NEW state
+ * in *next_reduced_dev (device float, must be zeroed by the caller) so the next step needs no extra pass. */
+int sphb200_acoustic_2nd_half(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, float dt, float h_min,
+                              float *next_reduced_dev, void *stream);
+/* phase-granular entry points (parity tests against the reference's per-phase kernels) */
+int sphb200_acoustic_1st_half_initialize(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, float dt, void *stream);
+int sphb200_acoustic_1st_half_interact(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, float dt, int do_update,
+                                       void *stream);
+/* LinearCorrectionMatrix<Inner<WithUpdate>,Contact<>>; ref: general_dynamics/kernel_correction_ck.hpp:40-95 */
+int sphb200_linear_correction_matrix(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, float alpha, void *stream);
+/* ReduceDynamicsCK<TotalMechanicalEnergyCK>; ref: general_dynamics/general_reduce_ck.h:52-88 */
+int sphb200_total_mechanical_energy(sphb200_context_t *ctx, const sphb200_fluid_view_t *fluid, const float gravity[3],
+                                    double *energy_host, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SPHB200_H */

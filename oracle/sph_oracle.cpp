@@ -1,0 +1,1329 @@
+// =====================================================================================
+//  sph_oracle.cpp — CPU ORACLE (TEST INFRASTRUCTURE, NOT PRODUCT CODE)
+//
+//  A plain C++17/OpenMP restatement of the SPHinXsys weakly-compressible SPH fluid hot
+//  path (neighbour machinery + density summation + acoustic 1st/2nd half with wall,
+//  Riemann), written from the algorithm description of the reference sources cited on
+//  each function ("ref:" comments; paths relative to /root/reference/src/shared).
+//
+//  Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference
+//  legs may load this library. The product path (libsphb200.so) never links or calls it.
+//
+//  The reference itself cannot be compiled in this image (needs Eigen, oneTBB, Boost,
+//  Simbody, spdlog, DPC++), so this restatement is pinned instead by the reference's own
+//  known-answer vectors and regression series (see tests/test_oracle_*.py).
+//
+//  Canonical conventions:
+//    * compiled with -ffp-contract=off: every fp op in index/criterion expressions is
+//      rounded separately;
+//    * cell lists hold particles in ascending index order inside a cell; CSR neighbour
+//      rows follow the reference search order (cells x -> y -> z, then in-cell order),
+//      so results are deterministic (the reference's atomics make its order arbitrary);
+//    * 2-D runs through the same code with z == 0 and one cell layer in z (bit-identical
+//      to the 2-D formulas: the extra terms are exact zeros).
+// =====================================================================================
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef uint32_t u32;
+
+namespace
+{
+// ------------------------------------------------------------------------------------
+// small helpers; ref: common/scalar_functions.h:40-43,70-73,128-131
+// ------------------------------------------------------------------------------------
+template <class R> inline R SMAX(R a, R b) { return a >= b ? a : b; }
+template <class R> inline R SMIN(R a, R b) { return a <= b ? a : b; }
+template <class R> inline R SGN(R x) { return x < R(0) ? R(-1) : (x > R(0) ? R(1) : R(0)); }
+
+template <class R> struct V3
+{
+    R x, y, z;
+    V3() : x(0), y(0), z(0) {}
+    V3(R a, R b, R c) : x(a), y(b), z(c) {}
+    V3 operator+(const V3 &o) const { return V3(x + o.x, y + o.y, z + o.z); }
+    V3 operator-(const V3 &o) const { return V3(x - o.x, y - o.y, z - o.z); }
+    V3 operator-() const { return V3(-x, -y, -z); }
+    V3 operator*(R s) const { return V3(x * s, y * s, z * s); }
+    V3 operator/(R s) const { return V3(x / s, y / s, z / s); }
+    V3 &operator+=(const V3 &o) { x += o.x; y += o.y; z += o.z; return *this; }
+    V3 &operator-=(const V3 &o) { x -= o.x; y -= o.y; z -= o.z; return *this; }
+    R dot(const V3 &o) const { return (x * o.x + y * o.y) + z * o.z; }
+    R squaredNorm() const { return (x * x + y * y) + z * z; }
+    R norm() const { return std::sqrt(squaredNorm()); }
+    // Eigen normalized(): z = squaredNorm(); z > 0 ? v / sqrt(z) : v
+    V3 normalized() const { R s = squaredNorm(); return s > R(0) ? (*this) / std::sqrt(s) : *this; }
+};
+template <class R> inline V3<R> operator*(R s, const V3<R> &v) { return v * s; }
+
+template <class R> struct M3 // row-major 3x3
+{
+    R m[9];
+    static M3 Zero() { M3 a; for (R &v : a.m) v = 0; return a; }
+    static M3 Identity() { M3 a = Zero(); a.m[0] = a.m[4] = a.m[8] = 1; return a; }
+    M3 operator*(R s) const { M3 a; for (int k = 0; k < 9; ++k) a.m[k] = m[k] * s; return a; }
+    M3 operator+(const M3 &o) const { M3 a; for (int k = 0; k < 9; ++k) a.m[k] = m[k] + o.m[k]; return a; }
+    V3<R> operator*(const V3<R> &v) const
+    {
+        return V3<R>((m[0] * v.x + m[1] * v.y) + m[2] * v.z, (m[3] * v.x + m[4] * v.y) + m[5] * v.z,
+                     (m[6] * v.x + m[7] * v.y) + m[8] * v.z);
+    }
+    M3 operator*(const M3 &o) const
+    {
+        M3 a;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c)
+                a.m[3 * r + c] = (m[3 * r] * o.m[c] + m[3 * r + 1] * o.m[3 + c]) + m[3 * r + 2] * o.m[6 + c];
+        return a;
+    }
+    M3 transpose() const
+    {
+        M3 a;
+        for (int r = 0; r < 3; ++r)
+            for (int c = 0; c < 3; ++c) a.m[3 * r + c] = m[3 * c + r];
+        return a;
+    }
+    R determinant() const
+    {
+        return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) +
+               m[2] * (m[3] * m[7] - m[4] * m[6]);
+    }
+    M3 inverse() const
+    {
+        R d = determinant();
+        M3 a;
+        a.m[0] = (m[4] * m[8] - m[5] * m[7]) / d;
+        a.m[1] = (m[2] * m[7] - m[1] * m[8]) / d;
+        a.m[2] = (m[1] * m[5] - m[2] * m[4]) / d;
+        a.m[3] = (m[5] * m[6] - m[3] * m[8]) / d;
+        a.m[4] = (m[0] * m[8] - m[2] * m[6]) / d;
+        a.m[5] = (m[2] * m[3] - m[0] * m[5]) / d;
+        a.m[6] = (m[3] * m[7] - m[4] * m[6]) / d;
+        a.m[7] = (m[1] * m[6] - m[0] * m[7]) / d;
+        a.m[8] = (m[0] * m[4] - m[1] * m[3]) / d;
+        return a;
+    }
+};
+
+// ------------------------------------------------------------------------------------
+// Mesh; ref: meshes/base_mesh.cpp:6-16 (geometry is computed by the caller in Real
+// precision and handed in), meshes/base_mesh.hxx:9-26,73-99
+// ------------------------------------------------------------------------------------
+struct MeshPOD
+{
+    double lower[3];
+    double spacing;
+    int cells[3];
+};
+
+template <class R> struct Mesh
+{
+    R lower[3];
+    R spacing;
+    int cells[3];
+    u32 total() const { return u32(cells[0]) * u32(cells[1]) * u32(cells[2]); }
+    void set(const MeshPOD &p)
+    {
+        for (int d = 0; d < 3; ++d) { lower[d] = R(p.lower[d]); cells[d] = p.cells[d]; }
+        spacing = R(p.spacing);
+    }
+    // ref: base_mesh.hxx:9-15 — floor((x - lower) / spacing), clamp to [0, all_grid_points - 2]
+    inline void cellIndex(const R *x, int *c) const
+    {
+        for (int d = 0; d < 3; ++d)
+        {
+            R t = x[d] - lower[d];
+            R u = t / spacing;
+            int k = (int)std::floor(u);
+            k = k < 0 ? 0 : k;
+            k = k > cells[d] - 1 ? cells[d] - 1 : k;
+            c[d] = k;
+        }
+    }
+    // ref: base_mesh.hxx:73-78 (z fastest)
+    inline u32 linear(const int *c) const
+    {
+        return u32(c[0]) * u32(cells[1]) * u32(cells[2]) + u32(c[1]) * u32(cells[2]) + u32(c[2]);
+    }
+};
+
+// ref: base_mesh.hxx:85-99
+inline u32 mortonSpread(u32 i)
+{
+    u32 x = i;
+    x &= 0x3ff;
+    x = (x | x << 16) & 0x30000ff;
+    x = (x | x << 8) & 0x300f00f;
+    x = (x | x << 4) & 0x30c30c3;
+    x = (x | x << 2) & 0x9249249;
+    return x;
+}
+inline u32 mortonKey(const int *c) { return mortonSpread(c[0]) | (mortonSpread(c[1]) << 1) | (mortonSpread(c[2]) << 2); }
+
+// ------------------------------------------------------------------------------------
+// Tabulated kernel; ref: shared_ck/smoothing_kernel/kernel_tabulated_ck.h:37-72, .cpp:6-25,
+// shared_ck/body_relation/neighbor_method.hpp:18-142. Table values are produced by the
+// caller from the analytic W_1D/dW_1D (kernels/kernel_wendland_c2.cpp:8-50,
+// kernels/kernel_laguerre_gauss.cpp:8-50) in Real precision.
+// ------------------------------------------------------------------------------------
+struct KernelPOD
+{
+    int dim;          // 2 or 3
+    int kind;         // 0 Wendland C2, 1 Laguerre-Gauss (only used by the analytic legacy form)
+    double h;         // reference smoothing length
+    double kernel_size; // 2.0
+    double dimension_factor; // factor_W_dim * h^dim  (base_kernel.h:87-93)
+    double w[24], dw[24];
+};
+
+template <class R> struct Kernel
+{
+    int dim, kind;
+    R h, inv_h, kernel_size, kernel_size_sq;
+    R dimension_factor;
+    R dq, delta0, delta1, delta2, delta3;
+    R w[24], dw[24];
+    R inv_h_pow_dim, inv_h_pow_dim1; // inv_h^dim and inv_h^(dim+1)
+    // legacy analytic factors (base_kernel.cpp:21-29)
+    R factor_W, factor_dW, rc_ref_sqr;
+
+    void set(const KernelPOD &p)
+    {
+        dim = p.dim; kind = p.kind;
+        h = R(p.h);
+        inv_h = R(1.0) / h;
+        kernel_size = R(p.kernel_size);
+        kernel_size_sq = kernel_size * kernel_size;
+        dimension_factor = R(p.dimension_factor);
+        dq = kernel_size / R(20);
+        delta0 = (R(-1.0) * dq) * (R(-2.0) * dq) * (R(-3.0) * dq);
+        delta1 = dq * (R(-1.0) * dq) * (R(-2.0) * dq);
+        delta2 = (R(2.0) * dq) * dq * (R(-1.0) * dq);
+        delta3 = (R(3.0) * dq) * (R(2.0) * dq) * dq;
+        for (int k = 0; k < 24; ++k) { w[k] = R(p.w[k]); dw[k] = R(p.dw[k]); }
+        R ih2 = inv_h * inv_h, ih3 = ih2 * inv_h, ih4 = ih3 * inv_h;
+        inv_h_pow_dim = dim == 2 ? ih2 : ih3;
+        inv_h_pow_dim1 = dim == 2 ? ih3 : ih4;
+        // legacy: factor_W_dim = inv_h^dim * sigma_dim ; sigma_dim = dimension_factor (up to rounding)
+        factor_W = inv_h_pow_dim * dimension_factor;
+        factor_dW = inv_h * factor_W;
+        R rc = kernel_size * h;
+        rc_ref_sqr = rc * rc;
+    }
+    // ref: kernel_tabulated_ck.h:45-58
+    inline R interpolateCubic(const R *data, R q) const
+    {
+        int location = (int)std::floor(q / dq);
+        int i = location + 1;
+        R f1 = q - R(location) * dq;
+        R f0 = f1 + dq;
+        R f2 = f1 - dq;
+        R f3 = f1 - 2 * dq;
+        return (f1 * f2 * f3) / delta0 * data[i - 1] + (f0 * f2 * f3) / delta1 * data[i] +
+               (f0 * f1 * f3) / delta2 * data[i + 1] + (f0 * f1 * f2) / delta3 * data[i + 2];
+    }
+    // ref: neighbor_method.hpp:24-52,103-130
+    inline R W(const V3<R> &disp) const { return inv_h_pow_dim * dimension_factor * interpolateCubic(w, disp.norm() * inv_h); }
+    inline R dW(const V3<R> &disp) const { return inv_h_pow_dim1 * dimension_factor * interpolateCubic(dw, disp.norm() * inv_h); }
+    inline R W0() const { return inv_h_pow_dim * dimension_factor * interpolateCubic(w, R(0)); }
+    // ref: neighbor_method.hpp:152-156
+    inline bool criterion(const R *xi, const R *xj) const
+    {
+        R sx = inv_h * (xi[0] - xj[0]);
+        R sy = inv_h * (xi[1] - xj[1]);
+        R sz = inv_h * (xi[2] - xj[2]);
+        R r2 = (sx * sx + sy * sy) + sz * sz;
+        return r2 < kernel_size_sq;
+    }
+    // legacy analytic forms; ref: kernels/base_kernel.cpp:44-61, kernel_wendland_c2.cpp, kernel_laguerre_gauss.cpp
+    inline R W1D(R q) const
+    {
+        if (kind == 0) return R(std::pow(1.0 - 0.5 * q, 4) * (1.0 + 2.0 * q));
+        return R((1.0 - std::pow(double(q), 2) + std::pow(double(q), 4) / 6.0) * std::exp(-std::pow(double(q), 2)));
+    }
+    inline R dW1D(R q) const
+    {
+        if (kind == 0) return R(0.625 * std::pow(q - 2.0, 3) * q);
+        double Q = q;
+        return R((-std::pow(Q, 5) / 3.0 + 8.0 * std::pow(Q, 3) / 3.0 - 4.0 * Q) * std::exp(-Q * Q));
+    }
+    inline R W_analytic(R r) const { return factor_W * W1D(r * inv_h); }
+    inline R dW_analytic(R r) const { return factor_dW * dW1D(r * inv_h); }
+};
+
+// ------------------------------------------------------------------------------------
+// Primitives; ref: common/algorithm_primitive.h:244-250 (scan)
+// ------------------------------------------------------------------------------------
+u32 exclusiveScan(const u32 *in, u32 *out, u32 n)
+{
+    // out[0] = 0; out[i] = sum_{k<i} in[k]; the last input entry is unused. returns out[n-1].
+    u32 acc = 0;
+    for (u32 i = 0; i < n; ++i)
+    {
+        u32 v = in[i];
+        out[i] = acc;
+        acc += v;
+    }
+    return n ? out[n - 1] : 0;
+}
+
+struct CSR
+{
+    std::vector<u32> offset, index;
+};
+
+template <class R> struct CellList
+{
+    Mesh<R> mesh;
+    std::vector<u32> cell_offset, particle_index;
+};
+
+// ref: shared_ck/.../update_cell_linked_list.hpp:40-106 (count -> scan -> fill)
+template <class R> void buildCellList(CellList<R> &cl, const R *pos, u32 n)
+{
+    u32 cells = cl.mesh.total();
+    std::vector<u32> count(cells + 1, 0), cell_of(n);
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < (long)n; ++i)
+    {
+        int c[3];
+        cl.mesh.cellIndex(pos + 3 * i, c);
+        cell_of[i] = cl.mesh.linear(c);
+    }
+    for (u32 i = 0; i < n; ++i) count[cell_of[i]]++;
+    cl.cell_offset.assign(cells + 1, 0);
+    exclusiveScan(count.data(), cl.cell_offset.data(), cells + 1);
+    cl.particle_index.assign(std::max<u32>(n, 1), 0);
+    std::vector<u32> cursor(cl.cell_offset.begin(), cl.cell_offset.end() - 1);
+    for (u32 i = 0; i < n; ++i) cl.particle_index[cursor[cell_of[i]]++] = i; // ascending i inside a cell
+}
+
+// ref: meshes/cell_linked_list.hpp:120-160 + for_3D_build/meshes/mesh_iterators.hpp:18-27
+template <class R, class F> inline void searchBox(const CellList<R> &cl, const R *x, int depth, const F &f)
+{
+    int c[3];
+    cl.mesh.cellIndex(x, c);
+    int lo[3], hi[3];
+    for (int d = 0; d < 3; ++d)
+    {
+        lo[d] = std::max(0, c[d] - depth);
+        hi[d] = std::min(cl.mesh.cells[d], c[d] + depth + 1);
+    }
+    int cc[3];
+    for (cc[0] = lo[0]; cc[0] < hi[0]; ++cc[0])
+        for (cc[1] = lo[1]; cc[1] < hi[1]; ++cc[1])
+            for (cc[2] = lo[2]; cc[2] < hi[2]; ++cc[2])
+            {
+                u32 lin = cl.mesh.linear(cc);
+                for (u32 n = cl.cell_offset[lin]; n < cl.cell_offset[lin + 1]; ++n) f(cl.particle_index[n]);
+            }
+}
+
+// ref: shared_ck/.../update_body_relation.hpp:62-164 — the reference builds the symmetric
+// inner list by a one-sided (i<j) search with atomics; the resulting neighbour SET of i is
+// { j != i : criterion(i,j) } over the 3^d cell box, which is what is enumerated here.
+template <class R, class Crit>
+void buildInner(CSR &csr, const CellList<R> &cl, const R *pos, u32 n, const Crit &crit)
+{
+    std::vector<u32> count(n + 1, 0);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long i = 0; i < (long)n; ++i)
+    {
+        u32 c = 0;
+        searchBox(cl, pos + 3 * i, 1, [&](u32 j) { if (j != (u32)i && crit(pos + 3 * i, pos + 3 * j)) ++c; });
+        count[i] = c;
+    }
+    csr.offset.assign(n + 1, 0);
+    exclusiveScan(count.data(), csr.offset.data(), n + 1);
+    csr.index.assign(std::max<u32>(csr.offset[n], 1), 0);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long i = 0; i < (long)n; ++i)
+    {
+        u32 k = csr.offset[i];
+        searchBox(cl, pos + 3 * i, 1, [&](u32 j) { if (j != (u32)i && crit(pos + 3 * i, pos + 3 * j)) csr.index[k++] = j; });
+    }
+}
+
+// ref: update_body_relation.hpp:199-288 (full search, deterministic order)
+template <class R, class Crit>
+void buildContact(CSR &csr, const CellList<R> &tar_cl, const R *src_pos, u32 n_src, const R *tar_pos, int depth,
+                  const Crit &crit)
+{
+    std::vector<u32> count(n_src + 1, 0);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long i = 0; i < (long)n_src; ++i)
+    {
+        u32 c = 0;
+        searchBox(tar_cl, src_pos + 3 * i, depth, [&](u32 j) { if (crit(src_pos + 3 * i, tar_pos + 3 * j)) ++c; });
+        count[i] = c;
+    }
+    csr.offset.assign(n_src + 1, 0);
+    exclusiveScan(count.data(), csr.offset.data(), n_src + 1);
+    csr.index.assign(std::max<u32>(csr.offset[n_src], 1), 0);
+#pragma omp parallel for schedule(dynamic, 256)
+    for (long i = 0; i < (long)n_src; ++i)
+    {
+        u32 k = csr.offset[i];
+        searchBox(tar_cl, src_pos + 3 * i, depth,
+                  [&](u32 j) { if (crit(src_pos + 3 * i, tar_pos + 3 * j)) csr.index[k++] = j; });
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// Parameters handed in by the caller
+// ------------------------------------------------------------------------------------
+struct ParamsPOD
+{
+    int dim;                // 2 | 3
+    int riemann;            // 0 NoRiemann, 1 Acoustic (TruncatedLinear 3.0), 2 Dissipative (NoLimiter)
+    int correction;         // 0 none, 1 LinearCorrection (B matrix)
+    int free_surface;       // density regularisation: 1 FreeSurface (max(sigma,1)), 0 Internal
+    double rho0, c0;
+    double gravity[3];
+    double U_ref;
+    double h_min;           // = h_ref
+    double acoustic_cfl;    // 0.6
+    double advection_cfl;   // 0.25
+    double correction_alpha; // 0.5
+    double sigma0;          // legacy: lattice number density (adaptation.cpp:26-60)
+    double wall_rho0;       // legacy: Solid reference density (1.0)
+    int contact_depth;      // search depth in the wall mesh (cell_linked_list.hpp:161-167)
+    int threads;            // 0 = leave OpenMP default
+};
+
+template <class R> struct Body
+{
+    u32 n = 0;
+    std::map<std::string, std::vector<R>> real;   // scalars (n), vectors (3n), matrices (9n)
+    std::map<std::string, std::vector<u32>> uint; // ids
+    std::vector<R> &r(const std::string &k, size_t width = 1, R init = R(0))
+    {
+        auto it = real.find(k);
+        if (it == real.end()) it = real.emplace(k, std::vector<R>(size_t(n) * width, init)).first;
+        return it->second;
+    }
+};
+
+template <class R> struct Sim
+{
+    ParamsPOD P;
+    Kernel<R> K;
+    Body<R> fluid, wall;
+    CellList<R> fluid_cl, wall_cl;
+    CSR inner, contact;
+    // legacy per-pair storage (AoS Neighborhood restated in CSR order; neighborhood.h:49-66)
+    std::vector<R> in_W, in_dW, in_r, in_e, ct_W, ct_dW, ct_r, ct_e;
+    // riemann constants; ref: riemann_solver_ck.hpp:58-69
+    R rho0, c0, p0, Z, inv_Z_sum, inv_Z_ave, Z_geo, inv_c_ave, limiter;
+    double physical_time = 0;
+    long acoustic_steps = 0, outer_steps = 0;
+    std::vector<double> energy_series, time_series;
+
+    void init(const ParamsPOD &p, const KernelPOD &k, const MeshPOD &fm, const MeshPOD &wm)
+    {
+        P = p;
+        K.set(k);
+        fluid_cl.mesh.set(fm);
+        wall_cl.mesh.set(wm);
+        rho0 = R(p.rho0); c0 = R(p.c0);
+        p0 = rho0 * c0 * c0; // weakly_compressible_fluid.cpp:8-9
+        Z = rho0 * c0;
+        inv_Z_sum = R(1.0) / (Z + Z);
+        inv_Z_ave = (Z + Z) / (Z * Z + Z * Z);
+        Z_geo = R(2.0) * Z * Z * inv_Z_sum;
+        inv_c_ave = R(0.5) * (rho0 + rho0) * inv_Z_ave;
+        limiter = R(3.0);
+#ifdef _OPENMP
+        if (p.threads > 0) omp_set_num_threads(p.threads);
+#endif
+    }
+
+    // ---- riemann; ref: riemann_solver_ck.hpp:17-56, common/common_functors.h:82-94 ----
+    inline R AverageP(R p_i, R p_j) const { return inv_Z_sum * (p_i * Z + p_j * Z); }
+    inline V3<R> AverageV(const V3<R> &vi, const V3<R> &vj) const { return (vi * Z + vj * Z) * inv_Z_sum; }
+    inline R PJump(R u) const
+    {
+        if (P.riemann == 0) return R(0);
+        R lim = P.riemann == 1 ? SMIN(limiter * (inv_c_ave * SMAX(u, R(0))), R(1)) : R(1);
+        return Z_geo * u * lim;
+    }
+    inline R UJump(R dp) const { return P.riemann == 0 ? R(0) : dp * inv_Z_ave; }
+
+    inline V3<R> vec(const std::vector<R> &a, u32 i) const { return V3<R>(a[3 * i], a[3 * i + 1], a[3 * i + 2]); }
+    inline void setv(std::vector<R> &a, u32 i, const V3<R> &v) { a[3 * i] = v.x; a[3 * i + 1] = v.y; a[3 * i + 2] = v.z; }
+    inline M3<R> mat(const std::vector<R> &a, u32 i) const { M3<R> m; std::memcpy(m.m, &a[9 * i], 9 * sizeof(R)); return m; }
+
+    void ensureFluidState()
+    {
+        u32 n = fluid.n;
+        fluid.r("Position", 3); fluid.r("Velocity", 3); fluid.r("Displacement", 3);
+        fluid.r("Force", 3); fluid.r("ForcePrior", 3); fluid.r("PreviousGravityForceCK", 3);
+        fluid.r("VolumetricMeasure"); fluid.r("Mass"); fluid.r("Density", 1, rho0); fluid.r("Pressure");
+        fluid.r("Compression", 1, R(1)); fluid.r("CompressionRate"); fluid.r("VolumetricMeasureRef");
+        fluid.r("CompressionSummation", 1, R(1)); fluid.r("DensityChangeRate"); fluid.r("DensitySummation");
+        if (fluid.real.find("LinearCorrectionMatrix") == fluid.real.end())
+        {
+            auto &B = fluid.r("LinearCorrectionMatrix", 9);
+            for (u32 i = 0; i < n; ++i) B[9 * i] = B[9 * i + 4] = B[9 * i + 8] = R(1);
+        }
+        if (fluid.uint.find("OriginalID") == fluid.uint.end())
+        {
+            auto &o = fluid.uint["OriginalID"]; o.resize(n); std::iota(o.begin(), o.end(), 0u);
+            auto &s = fluid.uint["SortedID"]; s.resize(n); std::iota(s.begin(), s.end(), 0u);
+        }
+        wall.r("Position", 3); wall.r("VolumetricMeasure"); wall.r("VolumetricMeasureRef"); wall.r("Mass");
+        wall.r("Velocity", 3); wall.r("Acceleration", 3); wall.r("NormalDirection", 3);
+    }
+
+    // =================================================================================
+    // configuration dynamics
+    // =================================================================================
+    void cellListFluid() { buildCellList(fluid_cl, fluid.r("Position", 3).data(), fluid.n); }
+    void cellListWall() { buildCellList(wall_cl, wall.r("Position", 3).data(), wall.n); }
+
+    void relationsCK()
+    {
+        const Kernel<R> &k = K;
+        auto crit = [&k](const R *a, const R *b) { return k.criterion(a, b); };
+        buildInner(inner, fluid_cl, fluid.r("Position", 3).data(), fluid.n, crit);
+        buildContact(contact, wall_cl, fluid.r("Position", 3).data(), fluid.n, wall.r("Position", 3).data(),
+                     P.contact_depth, crit);
+    }
+    // legacy criterion: displacement.squaredNorm() < rc_ref_sqr ; ref: kernels/base_kernel.h:105-114,
+    // particle_neighborhood/neighborhood.cpp:26-35,84-99,147-160
+    void relationsLegacy()
+    {
+        const R rc2 = K.rc_ref_sqr;
+        auto crit = [rc2](const R *a, const R *b) {
+            R dx = a[0] - b[0], dy = a[1] - b[1], dz = a[2] - b[2];
+            return (dx * dx + dy * dy) + dz * dz < rc2;
+        };
+        const std::vector<R> &pos = fluid.r("Position", 3), &wpos = wall.r("Position", 3);
+        buildInner(inner, fluid_cl, pos.data(), fluid.n, crit);
+        buildContact(contact, wall_cl, pos.data(), fluid.n, wpos.data(), P.contact_depth, crit);
+        auto fill = [&](const CSR &csr, const std::vector<R> &tpos, std::vector<R> &W, std::vector<R> &dW,
+                        std::vector<R> &rr, std::vector<R> &e) {
+            size_t m = csr.offset[fluid.n];
+            W.resize(m); dW.resize(m); rr.resize(m); e.resize(3 * m);
+#pragma omp parallel for schedule(static)
+            for (long i = 0; i < (long)fluid.n; ++i)
+                for (u32 n = csr.offset[i]; n < csr.offset[i + 1]; ++n)
+                {
+                    u32 j = csr.index[n];
+                    V3<R> d = vec(pos, i) - vec(tpos, j);
+                    R dist = std::sqrt(d.squaredNorm());
+                    W[n] = K.W_analytic(dist);
+                    dW[n] = K.dW_analytic(dist);
+                    rr[n] = dist;
+                    V3<R> ee = d / (dist + R(2.71051e-20)); // base_kernel.h:99-100
+                    e[3 * n] = ee.x; e[3 * n + 1] = ee.y; e[3 * n + 2] = ee.z;
+                }
+        };
+        fill(inner, pos, in_W, in_dW, in_r, in_e);
+        fill(contact, wpos, ct_W, ct_dW, ct_r, ct_e);
+    }
+
+    // ref: shared_ck/.../particle_sort_ck.hpp:61-104, base_configuration_dynamics.h:101-125.
+    // The reference host sort is an unstable quicksort; any permutation with sorted keys is valid.
+    // The oracle uses a stable sort (ties keep ascending index), as the device radix sort does.
+    // `with_force`: the reference does NOT list "Force" among the CK evolving variables
+    // (acoustic_step_1st_half.hpp:30-34) so it is left unpermuted unless asked.
+    void sortParticles(bool legacy)
+    {
+        u32 n = fluid.n;
+        std::vector<u32> keys(n), perm(n);
+        const std::vector<R> &pos = fluid.r("Position", 3);
+        for (u32 i = 0; i < n; ++i)
+        {
+            int c[3];
+            fluid_cl.mesh.cellIndex(&pos[3 * i], c);
+            keys[i] = mortonKey(c);
+            perm[i] = i;
+        }
+        std::stable_sort(perm.begin(), perm.end(), [&](u32 a, u32 b) { return keys[a] < keys[b]; });
+        fluid.uint["SortKeys"] = keys;
+        fluid.uint["Permutation"] = perm;
+        std::vector<std::string> names;
+        if (legacy)
+            names = {"Position", "VolumetricMeasure", "Velocity", "Mass", "ForcePrior", "Force", "DensityChangeRate",
+                     "Density", "Pressure"};
+        else
+            names = {"Position", "VolumetricMeasure", "Velocity", "Mass", "ForcePrior", "Compression", "CompressionRate",
+                     "VolumetricMeasureRef", "PreviousGravityForceCK"};
+        for (const std::string &nm : names)
+        {
+            std::vector<R> &a = fluid.real[nm];
+            size_t w = a.size() / n;
+            std::vector<R> tmp(a);
+            for (u32 i = 0; i < n; ++i)
+                for (size_t e = 0; e < w; ++e) a[w * i + e] = tmp[w * perm[i] + e];
+        }
+        std::vector<u32> &oid = fluid.uint["OriginalID"], &sid = fluid.uint["SortedID"];
+        std::vector<u32> tmp(oid);
+        for (u32 i = 0; i < n; ++i) oid[i] = tmp[perm[i]];
+        for (u32 i = 0; i < n; ++i) sid[oid[i]] = i;
+    }
+
+    // =================================================================================
+    // CK fluid dynamics
+    // =================================================================================
+    // ref: general_dynamics/force_prior_ck.hpp:38-44, force_prior_ck.h:53-57
+    void gravityForce()
+    {
+        std::vector<R> &fp = fluid.r("ForcePrior", 3), &prev = fluid.r("PreviousGravityForceCK", 3);
+        const std::vector<R> &m = fluid.r("Mass");
+        V3<R> g(R(P.gravity[0]), R(P.gravity[1]), R(P.gravity[2]));
+        for (u32 i = 0; i < fluid.n; ++i)
+        {
+            V3<R> cur = m[i] * g;
+            setv(fp, i, vec(fp, i) + (cur - vec(prev, i)));
+            setv(prev, i, cur);
+        }
+    }
+
+    // ref: fluid_dynamics/density_regularization.hpp:40-50 (inner), :74-83 (contact)
+    void compressionSummation()
+    {
+        const std::vector<R> &pos = fluid.r("Position", 3), &Vref = fluid.r("VolumetricMeasureRef");
+        const std::vector<R> &wpos = wall.r("Position", 3), &wVref = wall.r("VolumetricMeasureRef");
+        std::vector<R> &sum = fluid.r("CompressionSummation");
+        R W0 = K.W0();
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long i = 0; i < (long)fluid.n; ++i)
+        {
+            R s = W0 * Vref[i];
+            for (u32 n = inner.offset[i]; n < inner.offset[i + 1]; ++n)
+            {
+                u32 j = inner.index[n];
+                s += K.W(vec(pos, i) - vec(pos, j)) * Vref[j];
+            }
+            for (u32 n = contact.offset[i]; n < contact.offset[i + 1]; ++n)
+            {
+                u32 j = contact.index[n];
+                s += K.W(vec(pos, i) - vec(wpos, j)) * wVref[j];
+            }
+            sum[i] = s;
+        }
+    }
+    // ref: density_regularization.hpp:109-118, density_regularization.h:145-184
+    void densityRegularization()
+    {
+        const std::vector<R> &sum = fluid.r("CompressionSummation");
+        std::vector<R> &C = fluid.r("Compression"), &rho = fluid.r("Density");
+        for (u32 i = 0; i < fluid.n; ++i)
+        {
+            C[i] = P.free_surface ? SMAX(sum[i], R(1)) : sum[i];
+            rho[i] = C[i] * rho0;
+        }
+    }
+    // ref: fluid_time_step_ck.h:139-180
+    void advectionSetup()
+    {
+        std::vector<R> &Vol = fluid.r("VolumetricMeasure"), &dpos = fluid.r("Displacement", 3);
+        const std::vector<R> &m = fluid.r("Mass"), &rho = fluid.r("Density");
+        for (u32 i = 0; i < fluid.n; ++i)
+        {
+            Vol[i] = m[i] / rho[i];
+            dpos[3 * i] = dpos[3 * i + 1] = dpos[3 * i + 2] = R(0);
+        }
+    }
+    void updatePosition()
+    {
+        std::vector<R> &pos = fluid.r("Position", 3);
+        const std::vector<R> &dpos = fluid.r("Displacement", 3);
+        for (size_t k = 0; k < size_t(3) * fluid.n; ++k) pos[k] += dpos[k];
+    }
+    // ref: fluid_time_step_ck.h:106-109, fluid_time_step_ck.cpp:24-27; TinyReal base_data_type.h:207
+    double advectionDtReduced()
+    {
+        const std::vector<R> &vel = fluid.r("Velocity", 3);
+        R red = std::numeric_limits<R>::lowest();
+        for (u32 i = 0; i < fluid.n; ++i) red = SMAX(red, vec(vel, i).squaredNorm());
+        return double(red);
+    }
+    double advectionDt()
+    {
+        R red = R(advectionDtReduced());
+        return double(R(P.advection_cfl) * R(P.h_min) / (SMAX(R(std::sqrt(red)), R(P.U_ref)) + R(2.71051e-20)));
+    }
+    // ref: fluid_time_step_ck.hpp:51-57, :31-36
+    double acousticDtReduced()
+    {
+        const std::vector<R> &vel = fluid.r("Velocity", 3), &F = fluid.r("Force", 3), &Fp = fluid.r("ForcePrior", 3),
+                             &m = fluid.r("Mass");
+        R hmin = R(P.h_min);
+        R red = std::numeric_limits<R>::lowest();
+        for (u32 i = 0; i < fluid.n; ++i)
+        {
+            R fn = (vec(F, i) + vec(Fp, i)).norm();
+            R acc = std::sqrt(R(4.0) * hmin * fn / m[i]);
+            red = SMAX(red, SMAX(c0 + vec(vel, i).norm(), acc));
+        }
+        return double(red);
+    }
+    double acousticDt()
+    {
+        R red = R(acousticDtReduced());
+        return double(R(P.acoustic_cfl) * R(P.h_min) / (red + R(2.71051e-20)));
+    }
+
+    // ---- 1st half; ref: fluid_dynamics/acoustic_step_1st_half.hpp:66-74,89-111,122-127,157-180 ----
+    void a1Init(R dt)
+    {
+        std::vector<R> &C = fluid.r("Compression"), &rho = fluid.r("Density"), &p = fluid.r("Pressure"),
+                       &dpos = fluid.r("Displacement", 3);
+        const std::vector<R> &Cd = fluid.r("CompressionRate"), &vel = fluid.r("Velocity", 3);
+        for (u32 i = 0; i < fluid.n; ++i)
+        {
+            C[i] += R(0.5) * dt * Cd[i];
+            rho[i] = C[i] * rho0;
+            p[i] = p0 * (rho[i] / rho0 - R(1.0));
+            setv(dpos, i, vec(dpos, i) + vec(vel, i) * dt * R(0.5));
+        }
+    }
+    void a1Inner()
+    {
+        const std::vector<R> &pos = fluid.r("Position", 3), &Vol = fluid.r("VolumetricMeasure"), &p = fluid.r("Pressure"),
+                             &C = fluid.r("Compression"), &B = fluid.r("LinearCorrectionMatrix", 9);
+        std::vector<R> &F = fluid.r("Force", 3), &Cd = fluid.r("CompressionRate");
+        const bool corr = P.correction != 0;
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long i = 0; i < (long)fluid.n; ++i)
+        {
+            V3<R> fs;
+            R diss(0);
+            for (u32 n = inner.offset[i]; n < inner.offset[i + 1]; ++n)
+            {
+                u32 j = inner.index[n];
+                V3<R> d = vec(pos, i) - vec(pos, j);
+                R dWV = K.dW(d) * Vol[j];
+                V3<R> e = d.normalized();
+                if (corr)
+                {
+                    // AverageP on matrices: inv_sum * (B_j p_i Z + B_i p_j Z)
+                    M3<R> Pm = (mat(B, j) * p[i] * Z + mat(B, i) * p[j] * Z) * inv_Z_sum;
+                    fs -= (Pm * R(2.0) * dWV) * e;
+                }
+                else
+                    fs -= AverageP(p[i], p[j]) * R(2.0) * dWV * e;
+                diss += UJump(p[i] - p[j]) * dWV;
+            }
+            setv(F, i, vec(F, i) + fs * Vol[i]);
+            Cd[i] = diss * C[i];
+        }
+    }
+    void a1Wall()
+    {
+        const std::vector<R> &pos = fluid.r("Position", 3), &Vol = fluid.r("VolumetricMeasure"), &p = fluid.r("Pressure"),
+                             &C = fluid.r("Compression"), &rho = fluid.r("Density"), &m = fluid.r("Mass"),
+                             &Fp = fluid.r("ForcePrior", 3), &B = fluid.r("LinearCorrectionMatrix", 9);
+        const std::vector<R> &wpos = wall.r("Position", 3), &wVol = wall.r("VolumetricMeasure"),
+                             &wacc = wall.r("Acceleration", 3);
+        std::vector<R> &F = fluid.r("Force", 3), &Cd = fluid.r("CompressionRate");
+        const bool corr = P.correction != 0;
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long i = 0; i < (long)fluid.n; ++i)
+        {
+            V3<R> fs;
+            R diss(0);
+            for (u32 n = contact.offset[i]; n < contact.offset[i + 1]; ++n)
+            {
+                u32 j = contact.index[n];
+                V3<R> d = vec(pos, i) - vec(wpos, j);
+                R dWV = K.dW(d) * wVol[j];
+                V3<R> e = d.normalized();
+                R r_ij = d.norm();
+                R face_acc = (vec(Fp, i) / m[i] - vec(wacc, j)).dot(-e);
+                R p_w = p[i] + rho[i] * r_ij * SMAX(R(0), face_acc);
+                if (corr)
+                    fs -= (mat(B, i) * (p[i] + p_w) * dWV) * e;
+                else
+                    fs -= (p[i] + p_w) * dWV * e;
+                diss += UJump(p[i] - p_w) * dWV;
+            }
+            setv(F, i, vec(F, i) + fs * Vol[i]);
+            Cd[i] += diss * C[i];
+        }
+    }
+    void a1Update(R dt)
+    {
+        std::vector<R> &vel = fluid.r("Velocity", 3);
+        const std::vector<R> &F = fluid.r("Force", 3), &Fp = fluid.r("ForcePrior", 3), &m = fluid.r("Mass");
+        for (u32 i = 0; i < fluid.n; ++i) setv(vel, i, vec(vel, i) + (vec(Fp, i) + vec(F, i)) / m[i] * dt);
+    }
+    // ---- 2nd half; ref: fluid_dynamics/acoustic_step_2nd_half.hpp:33-38,53-73,83-89,117-137 ----
+    void a2Init(R dt)
+    {
+        std::vector<R> &dpos = fluid.r("Displacement", 3);
+        const std::vector<R> &vel = fluid.r("Velocity", 3);
+        for (u32 i = 0; i < fluid.n; ++i) setv(dpos, i, vec(dpos, i) + vec(vel, i) * dt * R(0.5));
+    }
+    void a2Inner()
+    {
+        const std::vector<R> &pos = fluid.r("Position", 3), &Vol = fluid.r("VolumetricMeasure"), &vel = fluid.r("Velocity", 3),
+                             &C = fluid.r("Compression"), &B = fluid.r("LinearCorrectionMatrix", 9);
+        std::vector<R> &F = fluid.r("Force", 3), &Cd = fluid.r("CompressionRate");
+        const bool corr = P.correction != 0;
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long i = 0; i < (long)fluid.n; ++i)
+        {
+            R div(0);
+            V3<R> pd;
+            V3<R> vi = vec(vel, i);
+            for (u32 n = inner.offset[i]; n < inner.offset[i + 1]; ++n)
+            {
+                u32 j = inner.index[n];
+                V3<R> d = vec(pos, i) - vec(pos, j);
+                R dWV = K.dW(d) * Vol[j];
+                V3<R> e = d.normalized();
+                V3<R> vj = vec(vel, j);
+                V3<R> vave = AverageV(vi, vj);
+                V3<R> ce = corr ? mat(B, i) * e : e;
+                div += R(2.0) * (vi - vave).dot(ce) * dWV;
+                R u = (vi - vj).dot(e);
+                pd += PJump(u) * dWV * e;
+            }
+            Cd[i] += div * C[i];
+            setv(F, i, pd * Vol[i]);
+        }
+    }
+    void a2Wall()
+    {
+        const std::vector<R> &pos = fluid.r("Position", 3), &Vol = fluid.r("VolumetricMeasure"), &vel = fluid.r("Velocity", 3),
+                             &C = fluid.r("Compression"), &B = fluid.r("LinearCorrectionMatrix", 9);
+        const std::vector<R> &wpos = wall.r("Position", 3), &wVol = wall.r("VolumetricMeasure"),
+                             &wvel = wall.r("Velocity", 3), &wn = wall.r("NormalDirection", 3);
+        std::vector<R> &F = fluid.r("Force", 3), &Cd = fluid.r("CompressionRate");
+        const bool corr = P.correction != 0;
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long i = 0; i < (long)fluid.n; ++i)
+        {
+            R div(0);
+            V3<R> pd;
+            V3<R> vi = vec(vel, i);
+            for (u32 n = contact.offset[i]; n < contact.offset[i + 1]; ++n)
+            {
+                u32 j = contact.index[n];
+                V3<R> d = vec(pos, i) - vec(wpos, j);
+                R dWV = K.dW(d) * wVol[j];
+                V3<R> e = d.normalized();
+                V3<R> vdiff = R(2.0) * (vi - vec(wvel, j));
+                V3<R> ce = corr ? mat(B, i) * e : e;
+                div += vdiff.dot(ce) * dWV;
+                V3<R> nj = vec(wn, j);
+                V3<R> nf = SGN(e.dot(nj)) * nj;
+                R u = vdiff.dot(nf);
+                pd += PJump(u) * dWV * nf;
+            }
+            Cd[i] += div * C[i];
+            setv(F, i, vec(F, i) + pd * Vol[i]);
+        }
+    }
+    void a2Update(R dt)
+    {
+        std::vector<R> &C = fluid.r("Compression"), &rho = fluid.r("Density");
+        const std::vector<R> &Cd = fluid.r("CompressionRate");
+        for (u32 i = 0; i < fluid.n; ++i)
+        {
+            C[i] += R(0.5) * dt * Cd[i];
+            rho[i] = C[i] * rho0;
+        }
+    }
+    // ref: interaction_algorithms_ck.cpp:29-34 (init -> inner -> contact -> update)
+    void acoustic1(R dt) { a1Init(dt); a1Inner(); a1Wall(); a1Update(dt); }
+    void acoustic2(R dt) { a2Init(dt); a2Inner(); a2Wall(); a2Update(dt); }
+
+    // ref: general_dynamics/kernel_correction_ck.hpp:40-95; inverse with Tikhonov regularisation
+    // (common/vector_functions: inverseTikhonov(B, eps) = (B^T B + eps I)^-1 B^T)
+    void linearCorrection()
+    {
+        const std::vector<R> &pos = fluid.r("Position", 3), &Vol = fluid.r("VolumetricMeasure");
+        const std::vector<R> &wpos = wall.r("Position", 3), &wVol = wall.r("VolumetricMeasure");
+        std::vector<R> &B = fluid.r("LinearCorrectionMatrix", 9);
+        R alpha = R(P.correction_alpha);
+        const int dim = P.dim;
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long i = 0; i < (long)fluid.n; ++i)
+        {
+            M3<R> b = M3<R>::Zero();
+            auto acc = [&](const V3<R> &d, R vol) {
+                V3<R> g = (K.dW(d) * d.normalized()) * vol; // nablaW_ij * V_j
+                R rr[3] = {d.x, d.y, d.z}, gg[3] = {g.x, g.y, g.z};
+                for (int r = 0; r < 3; ++r)
+                    for (int c = 0; c < 3; ++c) b.m[3 * r + c] -= rr[r] * gg[c];
+            };
+            for (u32 n = inner.offset[i]; n < inner.offset[i + 1]; ++n)
+            {
+                u32 j = inner.index[n];
+                acc(vec(pos, i) - vec(pos, j), Vol[j]);
+            }
+            for (u32 n = contact.offset[i]; n < contact.offset[i + 1]; ++n)
+            {
+                u32 j = contact.index[n];
+                acc(vec(pos, i) - vec(wpos, j), wVol[j]);
+            }
+            if (dim == 2) b.m[8] = R(1); // embed the 2x2 block so determinant/inverse act on it alone
+            R det = b.determinant();
+            R det_sqr = SMAX(alpha - det, R(0));
+            M3<R> bt = b.transpose();
+            M3<R> btb = bt * b;
+            R eps = R(1.0e-8);
+            btb.m[0] += eps; btb.m[4] += eps; btb.m[8] += eps;
+            M3<R> inv = btb.inverse() * bt;
+            R wgt = det / (det + det_sqr);
+            M3<R> out = inv * wgt + M3<R>::Identity() * (R(1.0) - wgt);
+            std::memcpy(&B[9 * i], out.m, 9 * sizeof(R));
+        }
+    }
+
+    // ref: general_dynamics/general_reduce_ck.h:52-88, external_force.h:53-56
+    double mechanicalEnergy()
+    {
+        const std::vector<R> &pos = fluid.r("Position", 3), &vel = fluid.r("Velocity", 3), &m = fluid.r("Mass");
+        V3<R> g(R(P.gravity[0]), R(P.gravity[1]), R(P.gravity[2]));
+        R s(0);
+        for (u32 i = 0; i < fluid.n; ++i)
+            s += R(0.5) * m[i] * vec(vel, i).squaredNorm() + m[i] * g.dot(V3<R>() - vec(pos, i));
+        return double(s);
+    }
+
+    // =================================================================================
+    // legacy formulation (Integration1stHalf/2ndHalf, DensitySummation); state rho/drho_dt/pos
+    // =================================================================================
+    // ref: particle_dynamics/fluid_dynamics/density_summation.cpp:8-22,58-78, .hpp:28-32
+    void legacyDensitySummation()
+    {
+        std::vector<R> &rho = fluid.r("Density"), &rsum = fluid.r("DensitySummation");
+        const std::vector<R> &m = fluid.r("Mass"), &wm = wall.r("Mass");
+        R W0 = K.factor_W; // Kernel::W0 = factor_W_dim (base_kernel.h:134-136)
+        R inv_sigma0 = R(1.0) / R(P.sigma0);
+        R inv_rho0_k = R(1.0) / R(P.wall_rho0);
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long i = 0; i < (long)fluid.n; ++i)
+        {
+            R sigma = W0;
+            for (u32 n = inner.offset[i]; n < inner.offset[i + 1]; ++n) sigma += in_W[n];
+            R rs = sigma * rho0 * inv_sigma0;
+            R sc(0);
+            for (u32 n = contact.offset[i]; n < contact.offset[i + 1]; ++n) sc += ct_W[n] * inv_rho0_k * wm[contact.index[n]];
+            rs += sc * rho0 * rho0 * inv_sigma0 / m[i];
+            rsum[i] = rs;
+            rho[i] = P.free_surface ? SMAX(rs, rho0) : rs;
+        }
+        if (!P.free_surface)
+        {
+            std::vector<R> &Vol = fluid.r("VolumetricMeasure");
+            for (u32 i = 0; i < fluid.n; ++i) Vol[i] = m[i] / rho[i];
+        }
+    }
+    // ref: particle_dynamics/fluid_dynamics/fluid_integration.hpp:49-113
+    void legacy1(R dt)
+    {
+        std::vector<R> &rho = fluid.r("Density"), &p = fluid.r("Pressure"), &pos = fluid.r("Position", 3),
+                       &drho = fluid.r("DensityChangeRate"), &F = fluid.r("Force", 3), &vel = fluid.r("Velocity", 3);
+        const std::vector<R> &Vol = fluid.r("VolumetricMeasure"), &m = fluid.r("Mass"), &Fp = fluid.r("ForcePrior", 3);
+        const std::vector<R> &wVol = wall.r("VolumetricMeasure"), &wacc = wall.r("Acceleration", 3);
+        for (u32 i = 0; i < fluid.n; ++i)
+        {
+            rho[i] += drho[i] * dt * R(0.5);
+            p[i] = p0 * (rho[i] / rho0 - R(1.0));
+            setv(pos, i, vec(pos, i) + vec(vel, i) * dt * R(0.5));
+        }
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long i = 0; i < (long)fluid.n; ++i)
+        {
+            V3<R> f;
+            R diss(0);
+            for (u32 n = inner.offset[i]; n < inner.offset[i + 1]; ++n)
+            {
+                u32 j = inner.index[n];
+                R dWV = in_dW[n] * Vol[j];
+                V3<R> e(in_e[3 * n], in_e[3 * n + 1], in_e[3 * n + 2]);
+                f -= (p[i] + p[j]) * dWV * e;
+                diss += UJump(p[i] - p[j]) * dWV;
+            }
+            V3<R> fw;
+            R dissw(0);
+            for (u32 n = contact.offset[i]; n < contact.offset[i + 1]; ++n)
+            {
+                u32 j = contact.index[n];
+                V3<R> e(ct_e[3 * n], ct_e[3 * n + 1], ct_e[3 * n + 2]);
+                R dWV = ct_dW[n] * wVol[j];
+                R face_acc = (vec(Fp, i) / m[i] - vec(wacc, j)).dot(-e);
+                R p_w = p[i] + rho[i] * ct_r[n] * SMAX(R(0), face_acc);
+                fw -= (p[i] + p_w) * dWV * e;
+                dissw += UJump(p[i] - p_w) * dWV;
+            }
+            V3<R> Fi = vec(F, i) + f * Vol[i];
+            R dr = diss * rho[i];
+            Fi = Fi + fw * Vol[i];
+            dr += dissw * rho[i];
+            setv(F, i, Fi);
+            drho[i] = dr;
+        }
+        for (u32 i = 0; i < fluid.n; ++i) setv(vel, i, vec(vel, i) + (vec(Fp, i) + vec(F, i)) / m[i] * dt);
+    }
+    // ref: fluid_integration.hpp:159-231
+    void legacy2(R dt)
+    {
+        std::vector<R> &rho = fluid.r("Density"), &pos = fluid.r("Position", 3), &drho = fluid.r("DensityChangeRate"),
+                       &F = fluid.r("Force", 3);
+        const std::vector<R> &Vol = fluid.r("VolumetricMeasure"), &vel = fluid.r("Velocity", 3);
+        const std::vector<R> &wVol = wall.r("VolumetricMeasure"), &wvel = wall.r("Velocity", 3),
+                             &wn = wall.r("NormalDirection", 3);
+        for (u32 i = 0; i < fluid.n; ++i) setv(pos, i, vec(pos, i) + vec(vel, i) * dt * R(0.5));
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long i = 0; i < (long)fluid.n; ++i)
+        {
+            V3<R> vi = vec(vel, i);
+            R dcr(0);
+            V3<R> pd;
+            for (u32 n = inner.offset[i]; n < inner.offset[i + 1]; ++n)
+            {
+                u32 j = inner.index[n];
+                V3<R> e(in_e[3 * n], in_e[3 * n + 1], in_e[3 * n + 2]);
+                R dWV = in_dW[n] * Vol[j];
+                R u = (vi - vec(vel, j)).dot(e);
+                dcr += u * dWV;
+                pd += PJump(u) * dWV * e;
+            }
+            R dcrw(0);
+            V3<R> pdw;
+            for (u32 n = contact.offset[i]; n < contact.offset[i + 1]; ++n)
+            {
+                u32 j = contact.index[n];
+                V3<R> e(ct_e[3 * n], ct_e[3 * n + 1], ct_e[3 * n + 2]);
+                R dWV = ct_dW[n] * wVol[j];
+                V3<R> nj = vec(wn, j);
+                V3<R> nf = SGN(e.dot(nj)) * nj;
+                V3<R> v_in_wall = R(2.0) * vec(wvel, j) - vi;
+                dcrw += (vi - v_in_wall).dot(e) * dWV;
+                R u = R(2.0) * (vi - vec(wvel, j)).dot(nf);
+                pdw += PJump(u) * dWV * nf;
+            }
+            drho[i] += dcr * rho[i];
+            drho[i] += dcrw * rho[i];
+            setv(F, i, pd * Vol[i] + pdw * Vol[i]);
+        }
+        for (u32 i = 0; i < fluid.n; ++i) rho[i] += drho[i] * dt * R(0.5);
+    }
+    // ref: particle_dynamics/fluid_dynamics/fluid_time_step.cpp:21-59
+    double legacyAcousticDt()
+    {
+        const std::vector<R> &vel = fluid.r("Velocity", 3);
+        R red = std::numeric_limits<R>::lowest();
+        for (u32 i = 0; i < fluid.n; ++i) red = SMAX(red, c0 + vec(vel, i).norm());
+        return double(R(P.acoustic_cfl) * R(P.h_min) / (red + R(2.71051e-20)));
+    }
+    double legacyAdvectionDt()
+    {
+        const std::vector<R> &vel = fluid.r("Velocity", 3), &F = fluid.r("Force", 3), &Fp = fluid.r("ForcePrior", 3),
+                             &m = fluid.r("Mass");
+        R red = std::numeric_limits<R>::lowest();
+        for (u32 i = 0; i < fluid.n; ++i)
+        {
+            R acc = R(4.0) * R(P.h_min) * (vec(F, i) + vec(Fp, i)).norm() / m[i];
+            red = SMAX(red, SMAX(vec(vel, i).squaredNorm(), acc));
+        }
+        R speed_max = std::sqrt(red);
+        return double(R(P.advection_cfl) * R(P.h_min) / (SMAX(speed_max, R(P.U_ref)) + R(2.71051e-20)));
+    }
+
+    // =================================================================================
+    // time loops (host sequencing restated from the case files)
+    // =================================================================================
+    // ref: tests/tests_sycl/3d_examples/test_3d_dambreak_sycl/dambreak.cpp:152-225.
+    // Runs until `end_time` or `max_outer` outer steps (whichever first); records total mechanical
+    // energy at t=0 and every `record_interval` of physical time (as writeToFile does).
+    void prepareCK()
+    {
+        ensureFluidState();
+        gravityForce();
+        cellListFluid();
+        cellListWall();
+        relationsCK();
+        energy_series.clear(); time_series.clear();
+        energy_series.push_back(mechanicalEnergy()); time_series.push_back(physical_time);
+    }
+    long runCK(double end_time, long max_outer, double record_interval, int sort_interval)
+    {
+        long done = 0;
+        while (physical_time < end_time && done < max_outer)
+        {
+            double integration_time = 0;
+            while (integration_time < record_interval && done < max_outer)
+            {
+                compressionSummation();
+                densityRegularization();
+                advectionSetup();
+                double adv_dt = advectionDt();
+                if (P.correction) linearCorrection();
+                double relax = 0;
+                while (relax < adv_dt)
+                {
+                    double dt = acousticDt();
+                    acoustic1(R(dt));
+                    acoustic2(R(dt));
+                    relax += dt; integration_time += dt; physical_time += dt;
+                    ++acoustic_steps;
+                }
+                updatePosition();
+                ++outer_steps; ++done;
+                if (sort_interval > 0 && outer_steps % sort_interval == 0 && outer_steps != 1) sortParticles(false);
+                cellListFluid();
+                relationsCK();
+            }
+            if (integration_time >= record_interval)
+            {
+                energy_series.push_back(mechanicalEnergy()); time_series.push_back(physical_time);
+            }
+        }
+        return done;
+    }
+    // ref: tests/2d_examples/test_2d_dambreak/Dambreak.cpp:118-220 and
+    // tests/3d_examples/test_3d_dambreak/dambreak.cpp:108-194 (same sequencing).
+    // Energy is recorded at iteration 0 and every `observe_every` outer iterations (2-D case file),
+    // or at every output interval when observe_every == 0 (3-D case file).
+    void prepareLegacy()
+    {
+        ensureFluidState();
+        gravityForce(); // GravityForce: force_prior = m g  (same increment form)
+        cellListFluid();
+        cellListWall();
+        relationsLegacy();
+        energy_series.clear(); time_series.clear();
+        energy_series.push_back(mechanicalEnergy()); time_series.push_back(physical_time);
+    }
+    long runLegacy(double end_time, long max_outer, double output_interval, int observe_every, int sort_interval)
+    {
+        long done = 0;
+        while (physical_time < end_time && done < max_outer)
+        {
+            double integration_time = 0;
+            while (integration_time < output_interval && done < max_outer)
+            {
+                double adv_dt = legacyAdvectionDt();
+                legacyDensitySummation();
+                double relax = 0;
+                while (relax < adv_dt)
+                {
+                    double dt = legacyAcousticDt();
+                    legacy1(R(dt));
+                    legacy2(R(dt));
+                    relax += dt; integration_time += dt; physical_time += dt;
+                    ++acoustic_steps;
+                }
+                if (observe_every > 0 && outer_steps % 100 == 0 && outer_steps % observe_every == 0 && outer_steps != 0)
+                {
+                    energy_series.push_back(mechanicalEnergy()); time_series.push_back(physical_time);
+                }
+                ++outer_steps; ++done;
+                if (sort_interval > 0 && outer_steps % sort_interval == 0 && outer_steps != 1) sortParticles(true);
+                cellListFluid();
+                relationsLegacy();
+            }
+            if (observe_every == 0 && integration_time >= output_interval)
+            {
+                energy_series.push_back(mechanicalEnergy()); time_series.push_back(physical_time);
+            }
+        }
+        return done;
+    }
+};
+
+// type-erased handle
+struct Handle
+{
+    int f64;
+    Sim<float> *f;
+    Sim<double> *d;
+};
+
+template <class R>
+double execOp(Sim<R> &s, const std::string &op, double a0, double a1, double a2, double a3)
+{
+    s.ensureFluidState();
+    if (op == "gravity") s.gravityForce();
+    else if (op == "cell_list_fluid") s.cellListFluid();
+    else if (op == "cell_list_wall") s.cellListWall();
+    else if (op == "relations") s.relationsCK();
+    else if (op == "relations_legacy") s.relationsLegacy();
+    else if (op == "sort") s.sortParticles(false);
+    else if (op == "sort_legacy") s.sortParticles(true);
+    else if (op == "compression_summation") s.compressionSummation();
+    else if (op == "density_regularization") s.densityRegularization();
+    else if (op == "advection_setup") s.advectionSetup();
+    else if (op == "update_position") s.updatePosition();
+    else if (op == "advection_dt") return s.advectionDt();
+    else if (op == "advection_dt_reduced") return s.advectionDtReduced();
+    else if (op == "acoustic_dt") return s.acousticDt();
+    else if (op == "acoustic_dt_reduced") return s.acousticDtReduced();
+    else if (op == "acoustic1") s.acoustic1(R(a0));
+    else if (op == "acoustic2") s.acoustic2(R(a0));
+    else if (op == "acoustic1_init") s.a1Init(R(a0));
+    else if (op == "acoustic1_inner") s.a1Inner();
+    else if (op == "acoustic1_wall") s.a1Wall();
+    else if (op == "acoustic1_update") s.a1Update(R(a0));
+    else if (op == "acoustic2_init") s.a2Init(R(a0));
+    else if (op == "acoustic2_inner") s.a2Inner();
+    else if (op == "acoustic2_wall") s.a2Wall();
+    else if (op == "acoustic2_update") s.a2Update(R(a0));
+    else if (op == "linear_correction") s.linearCorrection();
+    else if (op == "energy") return s.mechanicalEnergy();
+    else if (op == "legacy_density_summation") s.legacyDensitySummation();
+    else if (op == "legacy1") s.legacy1(R(a0));
+    else if (op == "legacy2") s.legacy2(R(a0));
+    else if (op == "legacy_acoustic_dt") return s.legacyAcousticDt();
+    else if (op == "legacy_advection_dt") return s.legacyAdvectionDt();
+    else if (op == "prepare_ck") s.prepareCK();
+    else if (op == "prepare_legacy") s.prepareLegacy();
+    else if (op == "run_ck") return (double)s.runCK(a0, (long)a1, a2, (int)a3);
+    else if (op == "run_legacy") return (double)s.runLegacy(a0, (long)a1, a2, (int)a3, 100);
+    else if (op == "physical_time") return s.physical_time;
+    else if (op == "acoustic_steps") return (double)s.acoustic_steps;
+    else if (op == "outer_steps") return (double)s.outer_steps;
+    else return -12345.0; // unknown op
+    return 0.0;
+}
+} // namespace
+
+// =====================================================================================
+// C interface (ctypes)
+// =====================================================================================
+extern "C"
+{
+    void *orc_create(int f64, const ParamsPOD *p, const KernelPOD *k, const MeshPOD *fluid_mesh, const MeshPOD *wall_mesh,
+                     u32 n_fluid, u32 n_wall)
+    {
+        Handle *h = new Handle{f64, nullptr, nullptr};
+        if (f64)
+        {
+            h->d = new Sim<double>();
+            h->d->init(*p, *k, *fluid_mesh, *wall_mesh);
+            h->d->fluid.n = n_fluid; h->d->wall.n = n_wall;
+        }
+        else
+        {
+            h->f = new Sim<float>();
+            h->f->init(*p, *k, *fluid_mesh, *wall_mesh);
+            h->f->fluid.n = n_fluid; h->f->wall.n = n_wall;
+        }
+        return h;
+    }
+    void orc_destroy(void *hp)
+    {
+        Handle *h = (Handle *)hp;
+        delete h->f; delete h->d; delete h;
+    }
+    // returns pointer to the named real array of body (0 fluid, 1 wall); creates it (zero) with `width` if absent
+    void *orc_real(void *hp, int body, const char *name, int width, uint64_t *len)
+    {
+        Handle *h = (Handle *)hp;
+        if (h->f64)
+        {
+            auto &b = body ? h->d->wall : h->d->fluid;
+            auto &v = b.r(name, width);
+            *len = v.size();
+            return v.data();
+        }
+        auto &b = body ? h->f->wall : h->f->fluid;
+        auto &v = b.r(name, width);
+        *len = v.size();
+        return v.data();
+    }
+    // named u32 arrays: fluid ids ("OriginalID","SortedID","SortKeys","Permutation") and structures
+    // "fluid_cell_offset","fluid_particle_index","wall_cell_offset","wall_particle_index",
+    // "inner_offset","inner_index","contact_offset","contact_index"
+    void *orc_uint(void *hp, const char *name, uint64_t *len)
+    {
+        Handle *h = (Handle *)hp;
+        std::string k(name);
+        std::vector<u32> *v = nullptr;
+#define PICK(S)                                                                                                       \
+    if (k == "fluid_cell_offset") v = &S->fluid_cl.cell_offset;                                                      \
+    else if (k == "fluid_particle_index") v = &S->fluid_cl.particle_index;                                           \
+    else if (k == "wall_cell_offset") v = &S->wall_cl.cell_offset;                                                   \
+    else if (k == "wall_particle_index") v = &S->wall_cl.particle_index;                                             \
+    else if (k == "inner_offset") v = &S->inner.offset;                                                              \
+    else if (k == "inner_index") v = &S->inner.index;                                                                \
+    else if (k == "contact_offset") v = &S->contact.offset;                                                          \
+    else if (k == "contact_index") v = &S->contact.index;                                                            \
+    else { S->ensureFluidState(); v = &S->fluid.uint[k]; }
+        if (h->f64) { PICK(h->d) } else { PICK(h->f) }
+#undef PICK
+        *len = v->size();
+        return v->data();
+    }
+    double orc_exec(void *hp, const char *op, double a0, double a1, double a2, double a3)
+    {
+        Handle *h = (Handle *)hp;
+        return h->f64 ? execOp(*h->d, op, a0, a1, a2, a3) : execOp(*h->f, op, a0, a1, a2, a3);
+    }
+    // recorded energy series of the last run_* call
+    uint64_t orc_series(void *hp, double *times, double *energy, uint64_t cap)
+    {
+        Handle *h = (Handle *)hp;
+        const std::vector<double> &e = h->f64 ? h->d->energy_series : h->f->energy_series;
+        const std::vector<double> &t = h->f64 ? h->d->time_series : h->f->time_series;
+        uint64_t m = std::min<uint64_t>(cap, e.size());
+        for (uint64_t i = 0; i < m; ++i) { times[i] = t[i]; energy[i] = e[i]; }
+        return e.size();
+    }
+
+    // ---- stand-alone primitives (no Sim) ----
+    // ref: common/algorithm_primitive.h:244-250; known answer
+    // tests/unit_tests_src/.../test_exclusive_scan/test_exclusive_scan.cpp:9-27
+    u32 orc_exclusive_scan_u32(const u32 *in, u32 *out, u32 n) { return exclusiveScan(in, out, n); }
+    // cell ids (linear) and Morton keys of positions (packed 3 per particle), f32 or f64
+    void orc_cell_keys(int f64, const void *pos, u32 n, const MeshPOD *mp, u32 *cell, u32 *key)
+    {
+        if (f64)
+        {
+            Mesh<double> m; m.set(*mp);
+            const double *x = (const double *)pos;
+            for (u32 i = 0; i < n; ++i) { int c[3]; m.cellIndex(x + 3 * i, c); cell[i] = m.linear(c); key[i] = mortonKey(c); }
+        }
+        else
+        {
+            Mesh<float> m; m.set(*mp);
+            const float *x = (const float *)pos;
+            for (u32 i = 0; i < n; ++i) { int c[3]; m.cellIndex(x + 3 * i, c); cell[i] = m.linear(c); key[i] = mortonKey(c); }
+        }
+    }
+    // stable sort of (key, value) pairs ascending by key
+    void orc_sort_pairs_u32(u32 *keys, u32 *vals, u32 n)
+    {
+        std::vector<u32> idx(n);
+        std::iota(idx.begin(), idx.end(), 0u);
+        std::stable_sort(idx.begin(), idx.end(), [&](u32 a, u32 b) { return keys[a] < keys[b]; });
+        std::vector<u32> k(n), v(n);
+        for (u32 i = 0; i < n; ++i) { k[i] = keys[idx[i]]; v[i] = vals[idx[i]]; }
+        std::memcpy(keys, k.data(), n * sizeof(u32));
+        std::memcpy(vals, v.data(), n * sizeof(u32));
+    }
+    // tabulated kernel evaluation (for the closed-form pin); which: 0 W, 1 dW ; returns normalized value
+    double orc_kernel_eval(int f64, const KernelPOD *kp, int which, double q)
+    {
+        if (f64) { Kernel<double> k; k.set(*kp); return k.interpolateCubic(which ? k.dw : k.w, q); }
+        Kernel<float> k; k.set(*kp);
+        return k.interpolateCubic(which ? k.dw : k.w, float(q));
+    }
+    int orc_max_threads()
+    {
+#ifdef _OPENMP
+        return omp_get_max_threads();
+#else
+        return 1;
+#endif
+    }
+}

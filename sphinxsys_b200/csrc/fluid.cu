@@ -1,0 +1,834 @@
+// fluid.cu — weakly-compressible SPH fluid dynamics on sm_100a: density (compression) summation,
+// acoustic 1st/2nd half with wall + Riemann dissipation, time-step reductions, advection set-up.
+//
+// Replaces the device launches of (paths relative to /root/reference/src/shared/shared_ck/particle_dynamics):
+//   fluid_dynamics/density_regularization.hpp:40-118     CompressionSummation<Inner/Contact>, DensityRegularization
+//   fluid_dynamics/acoustic_step_1st_half.hpp:66-180     initialize / interact(inner) / interact(wall) / update
+//   fluid_dynamics/acoustic_step_2nd_half.hpp:33-137     initialize / interact(inner) / interact(wall) / update
+//   fluid_dynamics/fluid_time_step_ck.{h,hpp,cpp}        AcousticTimeStepCK, AdvectionTimeStepCK, AdvectionStepSetup,
+//                                                        UpdateParticlePosition
+//   general_dynamics/force_prior_ck.hpp:38-44            GravityForceCK
+//   general_dynamics/kernel_correction_ck.hpp:40-95      LinearCorrectionMatrix<Inner<WithUpdate>,Contact<>>
+//   general_dynamics/general_reduce_ck.h:52-88           TotalMechanicalEnergyCK
+//
+// Design: one thread per fluid particle; neighbour rows are read from the SELL-32 relation
+// (one coalesced 128-byte load per warp and neighbour slot); neighbour state is gathered as float4 records
+// (x, y, z, Vol) / (vx, vy, vz, -) through L1; the tabulated smoothing kernel (4-point Lagrange on a 24-entry
+// table, kernel_tabulated_ck.h:45-58) is evaluated from per-interval cubic coefficients staged in shared
+// memory (one LDS.128 + 3 FMA instead of 4 table loads, 4 divisions and ~25 flops); the reference's four
+// launches per half step are fused wherever no neighbour reads the value being written.
+#include "common.cuh"
+
+constexpr int FL_THREADS = 128;
+constexpr int KT_INTERVALS = 21;
+
+struct KTab
+{
+    float4 c[KT_INTERVALS];
+};
+
+struct FArgs
+{
+    // fluid
+    u32 n;
+    float4 *pos, *vel, *dpos, *force, *force_prior, *posvol;
+    float *vol, *mass, *rho, *p, *C, *Cdot, *vol_ref, *Csum, *B;
+    // wall
+    u32 n_wall;
+    const float4 *w_pos, *w_posvol, *w_vel, *w_acc, *w_n;
+    const float *w_vol_ref;
+    // relations
+    const u32 *in_count, *in_slice, *in_index;
+    const u32 *ct_count, *ct_slice, *ct_index;
+    // constants
+    float inv_h, inv_dq, W0;
+    float rho0, c0, p0, Z, inv_Z_sum, inv_Z_ave, Z_geo, inv_c_ave, limiter;
+    int free_surface, dim;
+};
+
+// per-interval cubic coefficients of the 4-point Lagrange interpolant, in t = q/dq - location (t in [0,1)),
+// pre-multiplied by `scale` (inv_h^dim * dimension_factor for W, inv_h^(dim+1) * dimension_factor for dW)
+static void build_tab(const float *data, double scale, KTab *out)
+{
+    for (int loc = 0; loc < KT_INTERVALS; ++loc)
+    {
+        double d0 = data[loc], d1 = data[loc + 1], d2 = data[loc + 2], d3 = data[loc + 3];
+        double a0 = d1;
+        double a1 = -d0 / 3.0 - d1 / 2.0 + d2 - d3 / 6.0;
+        double a2 = d0 / 2.0 - d1 + d2 / 2.0;
+        double a3 = -d0 / 6.0 + d1 / 2.0 - d2 / 2.0 + d3 / 6.0;
+        out->c[loc] = make_float4((float)(a0 * scale), (float)(a1 * scale), (float)(a2 * scale), (float)(a3 * scale));
+    }
+}
+
+static int make_fargs(sphb200_context *ctx, const sphb200_fluid_args_t *s, FArgs *a, KTab *wtab, KTab *dwtab)
+{
+    const sphb200_fluid_view_t &f = s->fluid;
+    a->n = f.n;
+    a->pos = (float4 *)f.pos; a->vel = (float4 *)f.vel; a->dpos = (float4 *)f.dpos;
+    a->force = (float4 *)f.force; a->force_prior = (float4 *)f.force_prior; a->posvol = (float4 *)f.posvol;
+    a->vol = f.vol; a->mass = f.mass; a->rho = f.rho; a->p = f.p; a->C = f.compression; a->Cdot = f.compression_rate;
+    a->vol_ref = f.vol_ref; a->Csum = f.compression_sum; a->B = f.B;
+    const sphb200_wall_view_t &w = s->wall;
+    a->n_wall = w.n;
+    a->w_pos = (const float4 *)w.pos; a->w_posvol = (const float4 *)w.posvol; a->w_vel = (const float4 *)w.vel_ave;
+    a->w_acc = (const float4 *)w.acc_ave; a->w_n = (const float4 *)w.normal; a->w_vol_ref = w.vol_ref;
+    a->in_count = s->inner.count; a->in_slice = s->inner.slice_offset; a->in_index = s->inner.index;
+    a->ct_count = w.n ? s->contact.count : nullptr;
+    a->ct_slice = w.n ? s->contact.slice_offset : nullptr;
+    a->ct_index = w.n ? s->contact.index : nullptr;
+    const sphb200_kernel_t &k = s->kernel;
+    if (k.dim != 2 && k.dim != 3)
+    {
+        snprintf(ctx->err, sizeof(ctx->err), "kernel.dim must be 2 or 3");
+        return SPHB200_E_UNSUPPORTED;
+    }
+    float inv_h = 1.0f / k.h, src_inv_h = 1.0f / k.src_h;
+    double ih = inv_h, sih = src_inv_h;
+    double w_scale = (k.dim == 2 ? ih * ih : ih * ih * ih) * k.dimension_factor;
+    double dw_scale = w_scale * ih;
+    if (wtab) build_tab(k.w, w_scale, wtab);
+    if (dwtab) build_tab(k.dw, dw_scale, dwtab);
+    a->inv_h = inv_h;
+    a->inv_dq = 20.0f / k.kernel_size;
+    a->W0 = (float)((k.dim == 2 ? sih * sih : sih * sih * sih) * k.dimension_factor * k.w[1]);
+    const sphb200_fluid_t &m = s->material;
+    if (m.riemann < 0 || m.riemann > 2 || m.correction < 0 || m.correction > 1)
+    {
+        snprintf(ctx->err, sizeof(ctx->err), "unsupported riemann/correction kind");
+        return SPHB200_E_UNSUPPORTED;
+    }
+    // ImpedanceModel, riemann_solver_ck.hpp:58-69 (same fluid on both sides), evaluated in Real
+    a->rho0 = m.rho0; a->c0 = m.c0;
+    a->p0 = m.rho0 * m.c0 * m.c0;
+    a->Z = m.rho0 * m.c0;
+    a->inv_Z_sum = 1.0f / (a->Z + a->Z);
+    a->inv_Z_ave = (a->Z + a->Z) / (a->Z * a->Z + a->Z * a->Z);
+    a->Z_geo = 2.0f * a->Z * a->Z * a->inv_Z_sum;
+    a->inv_c_ave = 0.5f * (m.rho0 + m.rho0) * a->inv_Z_ave;
+    a->limiter = m.limiter_coeff;
+    a->free_surface = m.free_surface;
+    a->dim = k.dim;
+    return 0;
+}
+
+__device__ __forceinline__ void stage_tab(const KTab &src, float4 *dst)
+{
+    if (threadIdx.x < KT_INTERVALS) dst[threadIdx.x] = src.c[threadIdx.x];
+    __syncthreads();
+}
+
+// tabulated-kernel value at q (already scaled): one LDS.128 + 3 FMA
+__device__ __forceinline__ float eval_tab(const float4 *tab, float q, float inv_dq)
+{
+    float tq = q * inv_dq;
+    float lf = fminf(floorf(tq), (float)(KT_INTERVALS - 1));
+    float t = tq - lf;
+    float4 c = tab[(int)lf];
+    return fmaf(fmaf(fmaf(c.w, t, c.z), t, c.y), t, c.x);
+}
+
+__device__ __forceinline__ float3 mat_vec(const float *B, float3 v)
+{
+    return make_float3(B[0] * v.x + B[1] * v.y + B[2] * v.z, B[3] * v.x + B[4] * v.y + B[5] * v.z,
+                       B[6] * v.x + B[7] * v.y + B[8] * v.z);
+}
+__device__ __forceinline__ void load_mat(const float *B, u32 i, float *out)
+{
+#pragma unroll
+    for (int k = 0; k < 9; ++k) out[k] = B[9ull * i + k];
+}
+
+// RiemannSolver<...>::ComputingKernel::DissipativePJump, riemann_solver_ck.hpp:44-49
+template <int RIEMANN> __device__ __forceinline__ float pjump(const FArgs &a, float u)
+{
+    if (RIEMANN == 0) return 0.f;
+    float lim = RIEMANN == 1 ? fminf(a.limiter * (a.inv_c_ave * fmaxf(u, 0.f)), 1.f) : 1.f;
+    return a.Z_geo * u * lim;
+}
+
+// =====================================================================================================
+// simple per-particle dynamics
+// =====================================================================================================
+__global__ void __launch_bounds__(256)
+    k_gravity(u32 n, const float *__restrict__ mass, float4 *__restrict__ force_prior, float4 *__restrict__ prev, float gx,
+              float gy, float gz)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float m = mass[i];
+    float4 cur = make_float4(m * gx, m * gy, m * gz, 0.f);
+    float4 fp = force_prior[i], pv = prev[i];
+    fp.x += cur.x - pv.x; fp.y += cur.y - pv.y; fp.z += cur.z - pv.z;
+    force_prior[i] = fp;
+    prev[i] = cur;
+}
+extern "C" int sphb200_gravity_force(sphb200_context_t *ctx, const sphb200_fluid_view_t *f, const float g[3],
+                                     sphb200_vec4_t *previous_force, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && f && g && previous_force && f->mass && f->force_prior, "null pointer");
+    if (f->n)
+        SPH_LAUNCH(ctx, k_gravity, sph_blocks(f->n, 256), 256, 0, stream, f->n, f->mass, (float4 *)f->force_prior,
+                   (float4 *)previous_force, g[0], g[1], g[2]);
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+    k_advection_setup(u32 n, const float *__restrict__ mass, const float *__restrict__ rho, float *__restrict__ vol,
+                      float4 *__restrict__ dpos)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    vol[i] = __fdiv_rn(mass[i], rho[i]);
+    dpos[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+}
+extern "C" int sphb200_advection_setup(sphb200_context_t *ctx, const sphb200_fluid_view_t *f, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && f && f->mass && f->rho && f->vol && f->dpos, "null pointer");
+    if (f->n)
+        SPH_LAUNCH(ctx, k_advection_setup, sph_blocks(f->n, 256), 256, 0, stream, f->n, f->mass, f->rho, f->vol,
+                   (float4 *)f->dpos);
+    return 0;
+}
+
+__global__ void __launch_bounds__(256) k_update_position(u32 n, float4 *__restrict__ pos, const float4 *__restrict__ dpos)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 x = pos[i], d = dpos[i];
+    x.x = __fadd_rn(x.x, d.x); x.y = __fadd_rn(x.y, d.y); x.z = __fadd_rn(x.z, d.z);
+    pos[i] = x;
+}
+extern "C" int sphb200_update_position(sphb200_context_t *ctx, const sphb200_fluid_view_t *f, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && f && f->pos && f->dpos, "null pointer");
+    if (f->n)
+        SPH_LAUNCH(ctx, k_update_position, sph_blocks(f->n, 256), 256, 0, stream, f->n, (float4 *)f->pos,
+                   (const float4 *)f->dpos);
+    return 0;
+}
+
+// =====================================================================================================
+// reductions
+// =====================================================================================================
+__device__ __forceinline__ float norm2_rn(float x, float y, float z)
+{
+    return __fadd_rn(__fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y)), __fmul_rn(z, z));
+}
+__device__ __forceinline__ void block_max_to_global(float v, float *out)
+{
+    __shared__ float ws[32];
+    v = warp_max(v);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        float t = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.f;
+        t = warp_max(t);
+        // all reduced quantities are >= 0, for which the unsigned bit pattern is order preserving
+        if (threadIdx.x == 0) atomicMax((unsigned *)out, __float_as_uint(t));
+    }
+}
+
+// AdvectionTimeStepCK::ReduceKernel::reduce = |v|^2, fluid_time_step_ck.h:106-109
+__global__ void __launch_bounds__(256) k_reduce_advection(u32 n, const float4 *__restrict__ vel, float *out)
+{
+    float v = 0.f;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        float4 u = vel[i];
+        v = fmaxf(v, norm2_rn(u.x, u.y, u.z));
+    }
+    block_max_to_global(v, out);
+}
+// AcousticTimeStepCK::ReduceKernel::reduce, fluid_time_step_ck.hpp:51-57
+__device__ __forceinline__ float acoustic_measure(float4 v, float4 F, float4 Fp, float m, float c0, float h_min)
+{
+    float fn = sqrtf(norm2_rn(__fadd_rn(F.x, Fp.x), __fadd_rn(F.y, Fp.y), __fadd_rn(F.z, Fp.z)));
+    float acc = sqrtf(__fdiv_rn(__fmul_rn(__fmul_rn(4.0f, h_min), fn), m));
+    float sp = __fadd_rn(c0, sqrtf(norm2_rn(v.x, v.y, v.z)));
+    return fmaxf(sp, acc);
+}
+__global__ void __launch_bounds__(256)
+    k_reduce_acoustic(u32 n, const float4 *__restrict__ vel, const float4 *__restrict__ force,
+                      const float4 *__restrict__ force_prior, const float *__restrict__ mass, float c0, float h_min, float *out)
+{
+    float v = 0.f;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        v = fmaxf(v, acoustic_measure(vel[i], force[i], force_prior[i], mass[i], c0, h_min));
+    block_max_to_global(v, out);
+}
+
+static int read_scalar(sphb200_context *ctx, float *host, cudaStream_t st)
+{
+    SPH_CUDA(ctx, cudaMemcpyAsync(ctx->host_pinned, ctx->dev_scalars, sizeof(float), cudaMemcpyDeviceToHost, st));
+    SPH_CUDA(ctx, cudaStreamSynchronize(st));
+    *host = *(float *)ctx->host_pinned;
+    return 0;
+}
+
+extern "C" int sphb200_advection_time_step(sphb200_context_t *ctx, const sphb200_fluid_view_t *f, float h_min, float u_ref,
+                                           float cfl, float *reduced_host, float *dt_host, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && f && f->vel, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    SPH_CUDA(ctx, cudaMemsetAsync(ctx->dev_scalars, 0, sizeof(float), st));
+    if (f->n)
+        SPH_LAUNCH(ctx, k_reduce_advection, min(sph_blocks(f->n, 256), 148u * 8u), 256, 0, st, f->n, (const float4 *)f->vel,
+                   (float *)ctx->dev_scalars);
+    float red;
+    int rc = read_scalar(ctx, &red, st);
+    if (rc) return rc;
+    if (reduced_host) *reduced_host = red;
+    // FinishDynamics::Result, fluid_time_step_ck.cpp:24-27
+    if (dt_host) *dt_host = cfl * h_min / (fmaxf(sqrtf(red), u_ref) + 2.71051e-20f);
+    return 0;
+}
+
+extern "C" int sphb200_acoustic_time_step(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, float h_min, float cfl,
+                                          float *reduced_host, float *dt_host, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && s && s->fluid.vel && s->fluid.force && s->fluid.force_prior && s->fluid.mass, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const sphb200_fluid_view_t &f = s->fluid;
+    SPH_CUDA(ctx, cudaMemsetAsync(ctx->dev_scalars, 0, sizeof(float), st));
+    if (f.n)
+        SPH_LAUNCH(ctx, k_reduce_acoustic, min(sph_blocks(f.n, 256), 148u * 8u), 256, 0, st, f.n, (const float4 *)f.vel,
+                   (const float4 *)f.force, (const float4 *)f.force_prior, f.mass, s->material.c0, h_min,
+                   (float *)ctx->dev_scalars);
+    float red;
+    int rc = read_scalar(ctx, &red, st);
+    if (rc) return rc;
+    if (reduced_host) *reduced_host = red;
+    // FinishDynamics::Result, fluid_time_step_ck.hpp:31-36
+    if (dt_host) *dt_host = cfl * h_min / (red + 2.71051e-20f);
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+    k_energy(u32 n, const float4 *__restrict__ pos, const float4 *__restrict__ vel, const float *__restrict__ mass, float gx,
+             float gy, float gz, double *out)
+{
+    double s = 0.0;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        float4 x = pos[i], v = vel[i];
+        float m = mass[i];
+        // 0.5 m |v|^2 + m g.(0 - x); general_reduce_ck.h:52-88, external_force.h:53-56
+        float ke = 0.5f * m * (v.x * v.x + v.y * v.y + v.z * v.z);
+        float pe = m * (gx * (0.f - x.x) + gy * (0.f - x.y) + gz * (0.f - x.z));
+        s += (double)ke + (double)pe;
+    }
+    __shared__ double ws[32];
+    s = warp_sum_f64(s);
+    if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x < 32)
+    {
+        double t = threadIdx.x < (blockDim.x >> 5) ? ws[threadIdx.x] : 0.0;
+        t = warp_sum_f64(t);
+        if (threadIdx.x == 0) atomicAdd(out, t);
+    }
+}
+extern "C" int sphb200_total_mechanical_energy(sphb200_context_t *ctx, const sphb200_fluid_view_t *f, const float g[3],
+                                               double *energy_host, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && f && g && energy_host && f->pos && f->vel && f->mass, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    SPH_CUDA(ctx, cudaMemsetAsync(ctx->dev_scalars, 0, sizeof(double), st));
+    if (f->n)
+        SPH_LAUNCH(ctx, k_energy, min(sph_blocks(f->n, 256), 148u * 4u), 256, 0, st, f->n, (const float4 *)f->pos,
+                   (const float4 *)f->vel, f->mass, g[0], g[1], g[2], (double *)ctx->dev_scalars);
+    SPH_CUDA(ctx, cudaMemcpyAsync(ctx->host_pinned, ctx->dev_scalars, sizeof(double), cudaMemcpyDeviceToHost, st));
+    SPH_CUDA(ctx, cudaStreamSynchronize(st));
+    *energy_host = *(double *)ctx->host_pinned;
+    return 0;
+}
+
+// =====================================================================================================
+// compression (density) summation + regularisation
+// =====================================================================================================
+__global__ void __launch_bounds__(FL_THREADS) k_compression_summation(FArgs a, KTab wtab, int regularize)
+{
+    __shared__ float4 tab[KT_INTERVALS];
+    stage_tab(wtab, tab);
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    float4 xi = a.pos[i];
+    float s = a.W0 * a.vol_ref[i];
+    {
+        u32 cnt = a.in_count[i];
+        const u32 *idx = a.in_index + (u64)a.in_slice[i >> 5] + (i & 31u);
+        for (u32 k = 0; k < cnt; ++k)
+        {
+            u32 j = idx[32ull * k];
+            float4 xj = a.pos[j];
+            float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+            float r = sqrtf(dx * dx + dy * dy + dz * dz);
+            s += eval_tab(tab, r * a.inv_h, a.inv_dq) * a.vol_ref[j];
+        }
+    }
+    if (a.n_wall)
+    {
+        u32 cnt = a.ct_count[i];
+        const u32 *idx = a.ct_index + (u64)a.ct_slice[i >> 5] + (i & 31u);
+        for (u32 k = 0; k < cnt; ++k)
+        {
+            u32 j = idx[32ull * k];
+            float4 xj = a.w_pos[j];
+            float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+            float r = sqrtf(dx * dx + dy * dy + dz * dz);
+            s += eval_tab(tab, r * a.inv_h, a.inv_dq) * a.w_vol_ref[j];
+        }
+    }
+    a.Csum[i] = s;
+    if (regularize)
+    {
+        float C = a.free_surface ? fmaxf(s, 1.0f) : s; // Regularization<FreeSurface>, density_regularization.h:163-181
+        a.C[i] = C;
+        a.rho[i] = C * a.rho0;
+    }
+}
+
+extern "C" int sphb200_compression_summation(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, int regularize, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && s, "null pointer");
+    FArgs a;
+    KTab wtab;
+    int rc = make_fargs(ctx, s, &a, &wtab, nullptr);
+    if (rc) return rc;
+    SPH_CHECK_ARG(ctx, a.n == 0 || (a.pos && a.vol_ref && a.Csum && a.in_count && a.in_slice && a.in_index), "null fluid array");
+    SPH_CHECK_ARG(ctx, !regularize || (a.C && a.rho), "null fluid array");
+    SPH_CHECK_ARG(ctx, a.n_wall == 0 || (a.w_pos && a.w_vol_ref && a.ct_count && a.ct_slice && a.ct_index), "null wall array");
+    if (a.n) SPH_LAUNCH(ctx, k_compression_summation, sph_blocks(a.n, FL_THREADS), FL_THREADS, 0, stream, a, wtab, regularize);
+    return 0;
+}
+
+__global__ void __launch_bounds__(256)
+    k_density_regularization(u32 n, const float *__restrict__ Csum, float *__restrict__ C, float *__restrict__ rho, float rho0,
+                             int free_surface)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float s = Csum[i];
+    float c = free_surface ? fmaxf(s, 1.0f) : s;
+    C[i] = c;
+    rho[i] = c * rho0;
+}
+extern "C" int sphb200_density_regularization(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && s && s->fluid.compression_sum && s->fluid.compression && s->fluid.rho, "null pointer");
+    const sphb200_fluid_view_t &f = s->fluid;
+    if (f.n)
+        SPH_LAUNCH(ctx, k_density_regularization, sph_blocks(f.n, 256), 256, 0, stream, f.n, f.compression_sum, f.compression,
+                   f.rho, s->material.rho0, s->material.free_surface);
+    return 0;
+}
+
+// =====================================================================================================
+// acoustic step, 1st half
+// =====================================================================================================
+// InitializeKernel::initialize, acoustic_step_1st_half.hpp:66-74. Separate launch: interact reads p_j of
+// neighbours, which must all be post-initialize.
+__global__ void __launch_bounds__(256) k_a1_init(FArgs a, float dt)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    float C = a.C[i] + 0.5f * dt * a.Cdot[i];
+    float rho = C * a.rho0;
+    a.C[i] = C;
+    a.rho[i] = rho;
+    a.p[i] = a.p0 * (rho / a.rho0 - 1.0f);
+    float4 d = a.dpos[i], v = a.vel[i];
+    d.x += v.x * dt * 0.5f; d.y += v.y * dt * 0.5f; d.z += v.z * dt * 0.5f;
+    a.dpos[i] = d;
+}
+
+// InteractKernel::interact (inner, :89-111; wall, :157-180) + UpdateKernel::update (:122-127), one launch:
+// update touches only particle i's own velocity, which no neighbour reads in this half step.
+template <int RIEMANN, bool CORR>
+__global__ void __launch_bounds__(FL_THREADS) k_a1_interact(FArgs a, KTab dwtab, float dt, int do_update)
+{
+    __shared__ float4 tab[KT_INTERVALS];
+    stage_tab(dwtab, tab);
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const float4 xi = a.posvol[i];
+    const float p_i = a.p[i];
+    float Bi[9];
+    if (CORR) load_mat(a.B, i, Bi);
+
+    float fx = 0.f, fy = 0.f, fz = 0.f, diss = 0.f;
+    {
+        u32 cnt = a.in_count[i];
+        const u32 *idx = a.in_index + (u64)a.in_slice[i >> 5] + (i & 31u);
+        for (u32 k = 0; k < cnt; ++k)
+        {
+            u32 j = idx[32ull * k];
+            float4 xj = a.posvol[j];
+            float p_j = a.p[j];
+            float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+            float r2 = dx * dx + dy * dy + dz * dz;
+            float inv_r = r2 > 0.f ? rsqrtf(r2) : 0.f; // normalized(): zero vector stays zero
+            float r = r2 * inv_r;
+            float dWV = eval_tab(tab, r * a.inv_h, a.inv_dq) * xj.w;
+            if (CORR)
+            {
+                float Bj[9];
+                load_mat(a.B, j, Bj);
+                float3 e = make_float3(dx * inv_r, dy * inv_r, dz * inv_r);
+                float3 bje = mat_vec(Bj, e), bie = mat_vec(Bi, e);
+                // AverageP(B_j p_i, B_i p_j) * 2 dWV * e
+                float c = 2.0f * dWV * a.inv_Z_sum * a.Z;
+                fx -= c * (p_i * bje.x + p_j * bie.x);
+                fy -= c * (p_i * bje.y + p_j * bie.y);
+                fz -= c * (p_i * bje.z + p_j * bie.z);
+            }
+            else
+            {
+                float pave = a.inv_Z_sum * (p_i * a.Z + p_j * a.Z); // AverageP, riemann_solver_ck.hpp:19-24
+                float c = pave * 2.0f * dWV * inv_r;
+                fx -= c * dx; fy -= c * dy; fz -= c * dz;
+            }
+            if (RIEMANN) diss += (p_i - p_j) * a.inv_Z_ave * dWV; // DissipativeUJump, :51-56
+        }
+    }
+    float wx = 0.f, wy = 0.f, wz = 0.f, wdiss = 0.f;
+    const float vol_i = xi.w;
+    float4 Fp = a.force_prior[i];
+    const float m_i = a.mass[i];
+    if (a.n_wall)
+    {
+        u32 cnt = a.ct_count[i];
+        if (cnt)
+        {
+            const float rho_i = a.rho[i];
+            const float ax = Fp.x / m_i, ay = Fp.y / m_i, az = Fp.z / m_i;
+            const u32 *idx = a.ct_index + (u64)a.ct_slice[i >> 5] + (i & 31u);
+            for (u32 k = 0; k < cnt; ++k)
+            {
+                u32 j = idx[32ull * k];
+                float4 xj = a.w_posvol[j];
+                float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                float r2 = dx * dx + dy * dy + dz * dz;
+                float inv_r = r2 > 0.f ? rsqrtf(r2) : 0.f;
+                float r = r2 * inv_r;
+                float dWV = eval_tab(tab, r * a.inv_h, a.inv_dq) * xj.w;
+                float ex = dx * inv_r, ey = dy * inv_r, ez = dz * inv_r;
+                float rx = ax, ry = ay, rz = az;
+                if (a.w_acc)
+                {
+                    float4 wa = a.w_acc[j];
+                    rx -= wa.x; ry -= wa.y; rz -= wa.z;
+                }
+                float face_acc = -(rx * ex + ry * ey + rz * ez);
+                float p_w = p_i + rho_i * r * fmaxf(0.f, face_acc);
+                float c = (p_i + p_w) * dWV;
+                if (CORR)
+                {
+                    float3 be = mat_vec(Bi, make_float3(ex, ey, ez));
+                    wx -= c * be.x; wy -= c * be.y; wz -= c * be.z;
+                }
+                else
+                {
+                    wx -= c * ex; wy -= c * ey; wz -= c * ez;
+                }
+                if (RIEMANN) wdiss += (p_i - p_w) * a.inv_Z_ave * dWV;
+            }
+        }
+    }
+    float4 F = a.force[i];
+    F.x += fx * vol_i; F.y += fy * vol_i; F.z += fz * vol_i;
+    F.x += wx * vol_i; F.y += wy * vol_i; F.z += wz * vol_i;
+    a.force[i] = F;
+    const float C_i = a.C[i];
+    float cd = diss * C_i;
+    cd += wdiss * C_i;
+    a.Cdot[i] = cd;
+    if (do_update)
+    {
+        float4 v = a.vel[i];
+        v.x += (Fp.x + F.x) / m_i * dt;
+        v.y += (Fp.y + F.y) / m_i * dt;
+        v.z += (Fp.z + F.z) / m_i * dt;
+        a.vel[i] = v;
+    }
+}
+
+static int check_acoustic_args(sphb200_context *ctx, const FArgs &a, bool second)
+{
+    SPH_CHECK_ARG(ctx, a.n == 0 || (a.posvol && a.vel && a.dpos && a.force && a.force_prior && a.mass && a.rho && a.p && a.C &&
+                                    a.Cdot && a.in_count && a.in_slice && a.in_index),
+                  "null fluid array");
+    SPH_CHECK_ARG(ctx, a.n_wall == 0 || (a.w_posvol && a.ct_count && a.ct_slice && a.ct_index), "null wall array");
+    SPH_CHECK_ARG(ctx, !second || a.n_wall == 0 || a.w_n, "null wall normal");
+    return 0;
+}
+
+extern "C" int sphb200_acoustic_1st_half_initialize(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, float dt, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && s, "null pointer");
+    FArgs a;
+    int rc = make_fargs(ctx, s, &a, nullptr, nullptr);
+    if (rc) return rc;
+    rc = check_acoustic_args(ctx, a, false);
+    if (rc) return rc;
+    if (a.n) SPH_LAUNCH(ctx, k_a1_init, sph_blocks(a.n, 256), 256, 0, stream, a, dt);
+    return 0;
+}
+
+template <bool CORR> static int launch_a1(sphb200_context *ctx, const FArgs &a, const KTab &t, int riemann, float dt, int upd, void *stream)
+{
+    unsigned g = sph_blocks(a.n, FL_THREADS);
+    switch (riemann)
+    {
+    case 0: SPH_LAUNCH(ctx, (k_a1_interact<0, CORR>), g, FL_THREADS, 0, stream, a, t, dt, upd); break;
+    case 1: SPH_LAUNCH(ctx, (k_a1_interact<1, CORR>), g, FL_THREADS, 0, stream, a, t, dt, upd); break;
+    default: SPH_LAUNCH(ctx, (k_a1_interact<2, CORR>), g, FL_THREADS, 0, stream, a, t, dt, upd); break;
+    }
+    return 0;
+}
+
+extern "C" int sphb200_acoustic_1st_half_interact(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, float dt, int do_update,
+                                                  void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && s, "null pointer");
+    FArgs a;
+    KTab dwtab;
+    int rc = make_fargs(ctx, s, &a, nullptr, &dwtab);
+    if (rc) return rc;
+    rc = check_acoustic_args(ctx, a, false);
+    if (rc) return rc;
+    SPH_CHECK_ARG(ctx, !s->material.correction || a.B, "LinearCorrectionCK needs fluid.B");
+    if (a.n == 0) return 0;
+    return s->material.correction ? launch_a1<true>(ctx, a, dwtab, s->material.riemann, dt, do_update, stream)
+                                  : launch_a1<false>(ctx, a, dwtab, s->material.riemann, dt, do_update, stream);
+}
+
+extern "C" int sphb200_acoustic_1st_half(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, float dt, void *stream)
+{
+    int rc = sphb200_acoustic_1st_half_initialize(ctx, s, dt, stream);
+    if (rc) return rc;
+    return sphb200_acoustic_1st_half_interact(ctx, s, dt, 1, stream);
+}
+
+// =====================================================================================================
+// acoustic step, 2nd half — initialize + interact(inner) + interact(wall) + update in ONE launch: neighbours
+// only read Position/Vol/Velocity here, none of which this half step writes.
+// =====================================================================================================
+template <int RIEMANN, bool CORR>
+__global__ void __launch_bounds__(FL_THREADS) k_a2(FArgs a, KTab dwtab, float dt, float h_min, float *next_reduced)
+{
+    __shared__ float4 tab[KT_INTERVALS];
+    stage_tab(dwtab, tab);
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    float measure = 0.f;
+    if (i < a.n)
+    {
+        const float4 xi = a.posvol[i];
+        const float4 vi = a.vel[i];
+        // InitializeKernel::initialize, acoustic_step_2nd_half.hpp:33-38
+        {
+            float4 d = a.dpos[i];
+            d.x += vi.x * dt * 0.5f; d.y += vi.y * dt * 0.5f; d.z += vi.z * dt * 0.5f;
+            a.dpos[i] = d;
+        }
+        float Bi[9];
+        if (CORR) load_mat(a.B, i, Bi);
+        float div = 0.f, px = 0.f, py = 0.f, pz = 0.f;
+        {
+            u32 cnt = a.in_count[i];
+            const u32 *idx = a.in_index + (u64)a.in_slice[i >> 5] + (i & 31u);
+            for (u32 k = 0; k < cnt; ++k)
+            {
+                u32 j = idx[32ull * k];
+                float4 xj = a.posvol[j];
+                float4 vj = a.vel[j];
+                float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                float r2 = dx * dx + dy * dy + dz * dz;
+                float inv_r = r2 > 0.f ? rsqrtf(r2) : 0.f;
+                float r = r2 * inv_r;
+                float dWV = eval_tab(tab, r * a.inv_h, a.inv_dq) * xj.w;
+                float ex = dx * inv_r, ey = dy * inv_r, ez = dz * inv_r;
+                // AverageV, riemann_solver_ck.hpp:26-31
+                float avx = (vi.x * a.Z + vj.x * a.Z) * a.inv_Z_sum;
+                float avy = (vi.y * a.Z + vj.y * a.Z) * a.inv_Z_sum;
+                float avz = (vi.z * a.Z + vj.z * a.Z) * a.inv_Z_sum;
+                float3 ce = CORR ? mat_vec(Bi, make_float3(ex, ey, ez)) : make_float3(ex, ey, ez);
+                div += 2.0f * ((vi.x - avx) * ce.x + (vi.y - avy) * ce.y + (vi.z - avz) * ce.z) * dWV;
+                float u = (vi.x - vj.x) * ex + (vi.y - vj.y) * ey + (vi.z - vj.z) * ez;
+                float c = pjump<RIEMANN>(a, u) * dWV;
+                px += c * ex; py += c * ey; pz += c * ez;
+            }
+        }
+        float wdiv = 0.f, wx = 0.f, wy = 0.f, wz = 0.f;
+        if (a.n_wall)
+        {
+            u32 cnt = a.ct_count[i];
+            const u32 *idx = a.ct_index + (u64)a.ct_slice[i >> 5] + (i & 31u);
+            for (u32 k = 0; k < cnt; ++k)
+            {
+                u32 j = idx[32ull * k];
+                float4 xj = a.w_posvol[j];
+                float4 nj = a.w_n[j];
+                float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                float r2 = dx * dx + dy * dy + dz * dz;
+                float inv_r = r2 > 0.f ? rsqrtf(r2) : 0.f;
+                float r = r2 * inv_r;
+                float dWV = eval_tab(tab, r * a.inv_h, a.inv_dq) * xj.w;
+                float ex = dx * inv_r, ey = dy * inv_r, ez = dz * inv_r;
+                float vx = vi.x, vy = vi.y, vz = vi.z;
+                if (a.w_vel)
+                {
+                    float4 wv = a.w_vel[j];
+                    vx -= wv.x; vy -= wv.y; vz -= wv.z;
+                }
+                vx *= 2.0f; vy *= 2.0f; vz *= 2.0f; // vel_diff = 2 (v_i - v_wall)
+                float3 ce = CORR ? mat_vec(Bi, make_float3(ex, ey, ez)) : make_float3(ex, ey, ez);
+                wdiv += (vx * ce.x + vy * ce.y + vz * ce.z) * dWV;
+                float en = ex * nj.x + ey * nj.y + ez * nj.z;
+                float sg = en < 0.f ? -1.f : (en > 0.f ? 1.f : 0.f); // SGN, scalar_functions.h:128-131
+                float nx = sg * nj.x, ny = sg * nj.y, nz = sg * nj.z;
+                float u = vx * nx + vy * ny + vz * nz;
+                float c = pjump<RIEMANN>(a, u) * dWV;
+                wx += c * nx; wy += c * ny; wz += c * nz;
+            }
+        }
+        const float vol_i = xi.w;
+        float C = a.C[i];
+        float cd = a.Cdot[i];
+        cd += div * C;
+        cd += wdiv * C;
+        a.Cdot[i] = cd;
+        float4 F = make_float4(px * vol_i, py * vol_i, pz * vol_i, 0.f);
+        F.x += wx * vol_i; F.y += wy * vol_i; F.z += wz * vol_i;
+        a.force[i] = F;
+        // UpdateKernel::update, acoustic_step_2nd_half.hpp:83-89
+        C += 0.5f * dt * cd;
+        a.C[i] = C;
+        a.rho[i] = C * a.rho0;
+        if (next_reduced) measure = acoustic_measure(vi, F, a.force_prior[i], a.mass[i], a.c0, h_min);
+    }
+    if (next_reduced) block_max_to_global(measure, next_reduced);
+}
+
+template <bool CORR>
+static int launch_a2(sphb200_context *ctx, const FArgs &a, const KTab &t, int riemann, float dt, float h_min, float *nr, void *stream)
+{
+    unsigned g = sph_blocks(a.n, FL_THREADS);
+    switch (riemann)
+    {
+    case 0: SPH_LAUNCH(ctx, (k_a2<0, CORR>), g, FL_THREADS, 0, stream, a, t, dt, h_min, nr); break;
+    case 1: SPH_LAUNCH(ctx, (k_a2<1, CORR>), g, FL_THREADS, 0, stream, a, t, dt, h_min, nr); break;
+    default: SPH_LAUNCH(ctx, (k_a2<2, CORR>), g, FL_THREADS, 0, stream, a, t, dt, h_min, nr); break;
+    }
+    return 0;
+}
+
+extern "C" int sphb200_acoustic_2nd_half(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, float dt, float h_min,
+                                         float *next_reduced_dev, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && s, "null pointer");
+    FArgs a;
+    KTab dwtab;
+    int rc = make_fargs(ctx, s, &a, nullptr, &dwtab);
+    if (rc) return rc;
+    rc = check_acoustic_args(ctx, a, true);
+    if (rc) return rc;
+    SPH_CHECK_ARG(ctx, !s->material.correction || a.B, "LinearCorrectionCK needs fluid.B");
+    if (a.n == 0) return 0;
+    return s->material.correction ? launch_a2<true>(ctx, a, dwtab, s->material.riemann, dt, h_min, next_reduced_dev, stream)
+                                  : launch_a2<false>(ctx, a, dwtab, s->material.riemann, dt, h_min, next_reduced_dev, stream);
+}
+
+// =====================================================================================================
+// linear correction matrix: B_i = -(sum_j r_ij (x) nablaW_ij V_j), then the Tikhonov-regularised,
+// determinant-weighted inverse; kernel_correction_ck.hpp:40-95, common/vector_functions.h:199-203
+// =====================================================================================================
+__device__ __forceinline__ float det3(const float *m)
+{
+    return m[0] * (m[4] * m[8] - m[5] * m[7]) - m[1] * (m[3] * m[8] - m[5] * m[6]) + m[2] * (m[3] * m[7] - m[4] * m[6]);
+}
+__device__ __forceinline__ void inv3(const float *m, float *o)
+{
+    float d = det3(m);
+    o[0] = (m[4] * m[8] - m[5] * m[7]) / d; o[1] = (m[2] * m[7] - m[1] * m[8]) / d; o[2] = (m[1] * m[5] - m[2] * m[4]) / d;
+    o[3] = (m[5] * m[6] - m[3] * m[8]) / d; o[4] = (m[0] * m[8] - m[2] * m[6]) / d; o[5] = (m[2] * m[3] - m[0] * m[5]) / d;
+    o[6] = (m[3] * m[7] - m[4] * m[6]) / d; o[7] = (m[1] * m[6] - m[0] * m[7]) / d; o[8] = (m[0] * m[4] - m[1] * m[3]) / d;
+}
+
+__global__ void __launch_bounds__(FL_THREADS) k_linear_correction(FArgs a, KTab dwtab, float alpha)
+{
+    __shared__ float4 tab[KT_INTERVALS];
+    stage_tab(dwtab, tab);
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const float4 xi = a.posvol[i];
+    float b[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) b[k] = 0.f;
+    auto accumulate = [&](float4 xj) {
+        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+        float r2 = dx * dx + dy * dy + dz * dz;
+        float inv_r = r2 > 0.f ? rsqrtf(r2) : 0.f;
+        float r = r2 * inv_r;
+        float g = eval_tab(tab, r * a.inv_h, a.inv_dq) * inv_r * xj.w; // dW/r * V_j : nablaW V = g * d
+        float gx = g * dx, gy = g * dy, gz = g * dz;
+        b[0] -= dx * gx; b[1] -= dx * gy; b[2] -= dx * gz;
+        b[3] -= dy * gx; b[4] -= dy * gy; b[5] -= dy * gz;
+        b[6] -= dz * gx; b[7] -= dz * gy; b[8] -= dz * gz;
+    };
+    {
+        u32 cnt = a.in_count[i];
+        const u32 *idx = a.in_index + (u64)a.in_slice[i >> 5] + (i & 31u);
+        for (u32 k = 0; k < cnt; ++k) accumulate(a.posvol[idx[32ull * k]]);
+    }
+    if (a.n_wall)
+    {
+        u32 cnt = a.ct_count[i];
+        const u32 *idx = a.ct_index + (u64)a.ct_slice[i >> 5] + (i & 31u);
+        for (u32 k = 0; k < cnt; ++k) accumulate(a.w_posvol[idx[32ull * k]]);
+    }
+    if (a.dim == 2) b[8] = 1.0f;
+    float det = det3(b);
+    float det_sqr = fmaxf(alpha - det, 0.f);
+    float btb[9], bt[9];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c) bt[3 * r + c] = b[3 * c + r];
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            btb[3 * r + c] = bt[3 * r] * b[c] + bt[3 * r + 1] * b[3 + c] + bt[3 * r + 2] * b[6 + c];
+    const float eps = 1.0e-8f; // SqrtEps, base_data_type.h:206
+    btb[0] += eps; btb[4] += eps; btb[8] += eps;
+    float ib[9], inv[9];
+    inv3(btb, ib);
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+        for (int c = 0; c < 3; ++c)
+            inv[3 * r + c] = ib[3 * r] * bt[c] + ib[3 * r + 1] * bt[3 + c] + ib[3 * r + 2] * bt[6 + c];
+    float wgt = det / (det + det_sqr);
+#pragma unroll
+    for (int k = 0; k < 9; ++k)
+    {
+        float id = (k == 0 || k == 4 || k == 8) ? 1.0f : 0.f;
+        a.B[9ull * i + k] = wgt * inv[k] + (1.0f - wgt) * id;
+    }
+}
+
+extern "C" int sphb200_linear_correction_matrix(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, float alpha, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && s, "null pointer");
+    FArgs a;
+    KTab dwtab;
+    int rc = make_fargs(ctx, s, &a, nullptr, &dwtab);
+    if (rc) return rc;
+    SPH_CHECK_ARG(ctx, a.n == 0 || (a.posvol && a.B && a.in_count && a.in_slice && a.in_index), "null fluid array");
+    SPH_CHECK_ARG(ctx, a.n_wall == 0 || (a.w_posvol && a.ct_count && a.ct_slice && a.ct_index), "null wall array");
+    if (a.n) SPH_LAUNCH(ctx, k_linear_correction, sph_blocks(a.n, FL_THREADS), FL_THREADS, 0, stream, a, dwtab, alpha);
+    return 0;
+}
