@@ -1,0 +1,339 @@
+"""GPU parity tests: the CUDA path (through the C ABI of libsphb200.so) against the CPU oracle on identical inputs.
+
+Bar (BASELINE.json north_star): bit-exact for cell indices, keys, sort permutations, cell lists and neighbour
+sets; floating-point fields within the tolerances written next to each assertion.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+from helpers import gpu_field, make_gpu, make_oracle, oracle_field, perturb_state, rel_err  # noqa: E402
+
+REPORT = {}
+
+
+def _report(key, value):
+    REPORT[key] = value
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        json.dump(REPORT, open(os.path.join(out, "parity_report.json"), "w"), indent=1, default=float)
+    except OSError:
+        pass
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from sphinxsys_b200 import capi
+    assert torch.cuda.is_available(), "these tests need a GPU"
+    c = capi.Context(0)
+    yield c
+    c.close()
+
+
+def _dev(a, dtype=torch.int32):
+    return torch.from_numpy(np.ascontiguousarray(a)).to("cuda").view(dtype)
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr())
+
+
+def _s():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+# ------------------------------------------------------------------------------------------------------
+# primitives
+# ------------------------------------------------------------------------------------------------------
+def test_exclusive_scan_known_answer(ctx, oracle_lib):
+    # tests/unit_tests_src/.../test_exclusive_scan/test_exclusive_scan.cpp:9-27 (last input entry unused)
+    v = np.array([3, 2, 3, 5, 0, 1, 3, 2, 5, 1, 0], dtype=np.uint32)
+    d_in = _dev(v.view(np.int32))
+    d_out = torch.zeros_like(d_in)
+    last = C.c_uint32(0)
+    ctx.call("sphb200_exclusive_scan_u32", _p(d_in), _p(d_out), v.size, C.byref(last), _s())
+    assert d_out.cpu().numpy().view(np.uint32).tolist() == [0, 3, 5, 8, 13, 13, 14, 17, 19, 24, 25]
+    assert last.value == 25
+
+
+@pytest.mark.parametrize("n", [0, 1, 2, 31, 4095, 4096, 4097, 100_000, 1_873_455, 16_777_217 + 5])
+def test_exclusive_scan_sizes(ctx, oracle_lib, n):
+    rng = np.random.default_rng(n)
+    v = rng.integers(0, 40, size=n, dtype=np.uint32)
+    ref, ref_last = oracle_lib.exclusive_scan(v) if n else (v, 0)
+    d_in = _dev(v.view(np.int32)) if n else torch.zeros(1, dtype=torch.int32, device="cuda")
+    d_out = torch.zeros_like(d_in)
+    last = C.c_uint32(123)
+    ctx.call("sphb200_exclusive_scan_u32", _p(d_in), _p(d_out), n, C.byref(last), _s())
+    if n:
+        assert np.array_equal(d_out.cpu().numpy().view(np.uint32), ref)
+    assert last.value == ref_last
+    # in-place form
+    if n:
+        ctx.call("sphb200_exclusive_scan_u32", _p(d_in), _p(d_in), n, None, _s())
+        assert np.array_equal(d_in.cpu().numpy().view(np.uint32), ref)
+
+
+@pytest.mark.parametrize("n,bits", [(1, 30), (2, 30), (257, 8), (4096, 30), (4097, 30), (1_000_003, 30), (300_000, 32), (50_000, 3)])
+def test_sort_pairs_stable(ctx, oracle_lib, n, bits):
+    rng = np.random.default_rng(n + bits)
+    hi = (1 << bits) - 1
+    keys = rng.integers(0, hi + 1, size=n, dtype=np.uint64).astype(np.uint32)
+    if n > 10:
+        keys[: n // 3] = keys[n // 3: 2 * (n // 3)]  # many ties: stability matters
+    vals = np.arange(n, dtype=np.uint32)
+    rk, rv = oracle_lib.sort_pairs(keys, vals)
+    dk, dv = _dev(keys.view(np.int32)), _dev(vals.view(np.int32))
+    ctx.call("sphb200_sort_pairs_u32", _p(dk), _p(dv), n, bits, _s())
+    assert np.array_equal(dk.cpu().numpy().view(np.uint32), rk)
+    assert np.array_equal(dv.cpu().numpy().view(np.uint32), rv)  # stable: identical permutation
+
+
+def test_gather_multi(ctx):
+    n = 100_003
+    rng = np.random.default_rng(5)
+    perm = rng.permutation(n).astype(np.int32)
+    a4 = rng.standard_normal((n, 4)).astype(np.float32)
+    a1 = rng.standard_normal(n).astype(np.float32)
+    a9 = rng.standard_normal((n, 9)).astype(np.float32)
+    u1 = rng.integers(0, 1 << 31, size=n).astype(np.int32)
+    srcs = [torch.from_numpy(x).cuda() for x in (a4, a1, a9, u1)]
+    dsts = [torch.empty_like(t) for t in srcs]
+    k = len(srcs)
+    dp = (C.c_void_p * k)(*[t.data_ptr() for t in dsts])
+    sp = (C.c_void_p * k)(*[t.data_ptr() for t in srcs])
+    nb = (C.c_uint32 * k)(16, 4, 36, 4)
+    ctx.call("sphb200_gather_multi", k, dp, sp, nb, _p(torch.from_numpy(perm).cuda()), n, _s())
+    for d, s in zip(dsts, (a4, a1, a9, u1)):
+        assert np.array_equal(d.cpu().numpy(), s[perm])
+
+
+def test_vec_layout_roundtrip(ctx):
+    n = 12_345
+    a = np.random.default_rng(1).standard_normal((n, 3)).astype(np.float32)
+    src = torch.from_numpy(a).cuda()
+    v4 = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+    back = torch.zeros((n, 3), dtype=torch.float32, device="cuda")
+    ctx.call("sphb200_vec3_to_vec4", _p(v4), _p(src), n, _s())
+    ctx.call("sphb200_vec4_to_vec3", _p(back), _p(v4), n, _s())
+    assert np.array_equal(back.cpu().numpy(), a)
+    assert np.array_equal(v4.cpu().numpy()[:, :3], a)
+
+
+# ------------------------------------------------------------------------------------------------------
+# neighbour machinery: bit-exact
+# ------------------------------------------------------------------------------------------------------
+def _random_positions(case, n, seed):
+    rng = np.random.default_rng(seed)
+    lo = np.array(case.mesh.lower)
+    ext = np.array(case.mesh.cells) * case.mesh.spacing
+    pos = lo + rng.uniform(-0.05, 1.05, size=(n, 3)) * ext  # some outside the mesh: clamping path
+    if case.dim == 2:
+        pos[:, 2] = 0.0
+    return pos.astype(np.float32)
+
+
+@pytest.mark.parametrize("dim,dp", [(3, 0.05), (2, 0.025)])
+def test_cell_index_and_morton_keys_bit_exact(ctx, oracle_lib, dim, dp):
+    from sphinxsys_b200 import capi, cases
+    case = cases.dam_break(dim=dim, dp=dp)
+    pos = np.concatenate([case.fluid_pos, _random_positions(case, 50_000, 3)])
+    n = pos.shape[0]
+    ref_cell, ref_key = oracle_lib.cell_keys(pos, case.mesh)
+    p4 = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+    p4[:, :3] = torch.from_numpy(pos).cuda()
+    keys = torch.zeros(n, dtype=torch.int32, device="cuda")
+    perm = torch.zeros(n, dtype=torch.int32, device="cuda")
+    cell = torch.zeros(n, dtype=torch.int32, device="cuda")
+    m = capi.mesh_t(case.mesh)
+    ctx.call("sphb200_morton_keys", C.byref(m), _p(p4), n, _p(keys), _p(perm), _p(cell), _s())
+    assert np.array_equal(cell.cpu().numpy().view(np.uint32), ref_cell)
+    assert np.array_equal(keys.cpu().numpy().view(np.uint32), ref_key)
+    assert np.array_equal(perm.cpu().numpy(), np.arange(n, dtype=np.int32))
+
+
+@pytest.fixture(scope="module")
+def pair3d():
+    """Default 3-D dam break (8,000 fluid + 56,560 wall), perturbed so the state is not a trivial lattice."""
+    from sphinxsys_b200 import cases
+    case = cases.dam_break(dim=3, dp=0.05)
+    pos, vel = perturb_state(case)
+    case.fluid_pos = pos
+    gpu = make_gpu(case, fused_time_step=False)
+    gpu.upload_state()
+    gpu.water_block.particles.upload("Velocity", vel)
+    gpu.initialize(upload=False)
+    o32 = make_oracle(case, f64=False)
+    o64 = make_oracle(case, f64=True)
+    for o in (o32, o64):
+        o.real("Velocity", 3)[:] = vel.reshape(-1)
+        o.exec("prepare_ck")
+    return case, gpu, o32, o64
+
+
+def test_cell_list_bit_exact(pair3d):
+    case, gpu, o32, _ = pair3d
+    cells = case.mesh.total_cells
+    for body, prefix in ((gpu.water_block, "fluid"), (gpu.wall_boundary, "wall")):
+        cll = body.getCellLinkedList()
+        off = cll.cell_offset[: cells + 1].cpu().numpy().view(np.uint32)
+        idx = cll.particle_index[: body.n].cpu().numpy().view(np.uint32)
+        assert np.array_equal(off, o32.uint(f"{prefix}_cell_offset"))
+        assert np.array_equal(idx, o32.uint(f"{prefix}_particle_index")[: body.n])
+
+
+def test_neighbour_lists_bit_exact(pair3d):
+    case, gpu, o32, _ = pair3d
+    for rel, name in ((gpu.water_block_inner, "inner"), (gpu.water_wall_contact, "contact")):
+        off, idx = rel.export_csr()
+        ref_off, ref_idx = o32.uint(f"{name}_offset"), o32.uint(f"{name}_index")
+        assert np.array_equal(off, ref_off)
+        total = int(ref_off[-1])
+        assert rel.total >= total
+        assert np.array_equal(idx[:total], ref_idx[:total])  # same sets AND same (reference search) order
+    _report("neighbours_3d", {"inner_total": int(o32.uint("inner_offset")[-1]), "contact_total": int(o32.uint("contact_offset")[-1])})
+
+
+def _compare(gpu, o32, o64, names_real, names_vec, tag, tol):
+    """|gpu - oracle64| must be within `tol` (field-norm relative) and comparable to the oracle's own fp32 error."""
+    rep = {}
+    for nm in names_real + names_vec:
+        w = 3 if nm in names_vec else 1
+        g = gpu_field(gpu, nm)
+        r32 = oracle_field(o32, nm, w)
+        r64 = oracle_field(o64, nm, w)
+        e_gpu = rel_err(g, r64)
+        e_o32 = rel_err(r32, r64)
+        e_gpu32 = rel_err(g, r32)
+        rep[nm] = {"gpu_vs_f64": e_gpu, "oracle32_vs_f64": e_o32, "gpu_vs_oracle32": e_gpu32}
+        bound = max(tol.get(nm, tol["default"]), 4.0 * e_o32)  # never demand more than the CPU fp32 path delivers
+        assert e_gpu <= bound, f"{tag}:{nm}: gpu vs oracle64 {e_gpu:.3e} (oracle32 vs 64 {e_o32:.3e})"
+    _report(tag, rep)
+    return rep
+
+
+def test_per_dynamics_parity_3d(pair3d):
+    """Each dynamics of one acoustic step, in the order of dambreak.cpp:188-205, compared field by field.
+    Tolerance: 1e-5 of the field's max norm (fp32, BASELINE.json), except Pressure whose fp32 granularity is
+    p0 * ulp(1) = 400 * 1.2e-7 (p = p0 (rho/rho0 - 1)): 2e-4 of max|p| on this case."""
+    case, gpu, o32, o64 = pair3d
+    tol = {"default": 1e-5, "Pressure": 3e-4, "CompressionRate": 5e-5, "Force": 5e-5}
+    # density summation + regularisation
+    gpu.fluid_density_summation.exec()
+    for o in (o32, o64):
+        o.exec("compression_summation")
+        o.exec("density_regularization")
+    _compare(gpu, o32, o64, ["CompressionSummation", "Compression", "Density"], [], "density_summation", tol)
+    gpu.water_advection_step_setup.exec()
+    for o in (o32, o64):
+        o.exec("advection_setup")
+    _compare(gpu, o32, o64, ["VolumetricMeasure"], ["Displacement"], "advection_setup", tol)
+    # time steps
+    adv = gpu.fluid_advection_time_step.exec()
+    ac = gpu.fluid_acoustic_time_step.exec()
+    assert abs(adv - o32.exec("advection_dt")) <= 1e-6 * adv
+    assert abs(ac - o32.exec("acoustic_dt")) <= 1e-6 * ac
+    assert np.float32(gpu.fluid_advection_time_step.last_reduced) == np.float32(o32.exec("advection_dt_reduced"))  # exact max
+    dt = float(np.float32(ac))
+    # 1st half, phase by phase
+    a = gpu.system.args()
+    gpu.system.prepare()
+    gpu.ctx.call("sphb200_acoustic_1st_half_initialize", C.byref(a), dt, _s())
+    for o in (o32, o64):
+        o.exec("acoustic1_init", dt)
+    _compare(gpu, o32, o64, ["Compression", "Density", "Pressure"], ["Displacement"], "a1_init", tol)
+    gpu.ctx.call("sphb200_acoustic_1st_half_interact", C.byref(a), dt, 1, _s())
+    for o in (o32, o64):
+        o.exec("acoustic1_inner")
+        o.exec("acoustic1_wall")
+        o.exec("acoustic1_update", dt)
+    _compare(gpu, o32, o64, ["CompressionRate"], ["Force", "Velocity"], "a1_interact_update", tol)
+    # 2nd half (single fused launch)
+    gpu.fluid_acoustic_step_2nd_half.exec(dt)
+    for o in (o32, o64):
+        o.exec("acoustic2", dt)
+    _compare(gpu, o32, o64, ["CompressionRate", "Compression", "Density"], ["Force", "Displacement"], "a2", tol)
+    # energy reduction
+    e = gpu.energy()
+    assert abs(e - o64.exec("energy")) <= 1e-5 * abs(e)
+
+
+def test_fused_time_step_equals_standalone(pair3d):
+    """The max folded into the 2nd-half launch must equal the stand-alone AcousticTimeStepCK reduction bit for bit."""
+    case, gpu, o32, o64 = pair3d
+    nr = gpu.fluid_acoustic_step_2nd_half.enable_fused_time_step()
+    dt = 1e-4
+    gpu.fluid_acoustic_step_1st_half.exec(dt)
+    gpu.fluid_acoustic_step_2nd_half.exec(dt)
+    fused = float(nr.item())
+    gpu.fluid_acoustic_time_step.exec()
+    assert np.float32(fused) == np.float32(gpu.fluid_acoustic_time_step.last_reduced)
+    gpu.fluid_acoustic_step_2nd_half.next_reduced = None
+    for o in (o32, o64):
+        o.exec("acoustic1", dt)
+        o.exec("acoustic2", dt)
+
+
+@pytest.mark.parametrize("dim,dp,correction,n_outer", [(3, 0.05, False, 12), (3, 0.05, True, 6), (2, 0.025, False, 30)])
+def test_multi_step_drift(dim, dp, correction, n_outer):
+    """Run the case-file loop on both sides from the true initial condition; compare after n_outer advection steps.
+    Bounds: fields within 2e-4 (positions 5e-6, i.e. a few ulp of the tank length) of the oracle in max-norm after n_outer*~5 acoustic steps;
+    total mechanical energy within 1e-5 relative; free-surface front position (max x) within 1e-5."""
+    from sphinxsys_b200 import cases
+    case = cases.dam_break(dim=dim, dp=dp)
+    gpu = make_gpu(case, correction=correction, fused_time_step=True, sort_interval=5)
+    gpu.initialize()
+    o32 = make_oracle(case, f64=False, correction=int(correction))
+    o32.exec("prepare_ck")
+    n_ac = 0
+    for _ in range(n_outer):
+        n_ac += gpu.step_outer()
+    o32.exec("run_ck", 1e9, n_outer, 1e9, 5)
+    assert int(o32.exec("acoustic_steps")) == n_ac, "both sides must take the same number of acoustic sub-steps"
+    assert abs(gpu.physical_time - o32.exec("physical_time")) <= 1e-5 * gpu.physical_time
+    rep = {}
+    # both sides sorted with the same stable permutation: compare in storage order
+    assert np.array_equal(gpu_field(gpu, "OriginalID"), o32.uint("OriginalID"))
+    for nm, w, tol in (("Position", 3, 5e-6), ("Velocity", 3, 2e-4), ("Density", 1, 1e-6), ("Compression", 1, 1e-6)):
+        e = rel_err(gpu_field(gpu, nm), oracle_field(o32, nm, w))
+        rep[nm] = e
+        assert e <= tol, f"{nm}: {e:.3e} after {n_outer} outer / {n_ac} acoustic steps"
+    e_gpu, e_ref = gpu.energy(), o32.exec("energy")
+    rep["energy"] = [e_gpu, e_ref]
+    assert abs(e_gpu - e_ref) <= 1e-5 * abs(e_ref)
+    front_gpu = float(gpu_field(gpu, "Position")[:, 0].max())
+    front_ref = float(oracle_field(o32, "Position", 3)[:, 0].max())
+    assert abs(front_gpu - front_ref) <= 1e-5 * abs(front_ref)
+    _report(f"drift_{dim}d_corr{int(correction)}", rep)
+
+
+def test_sort_permutation_properties_full_size(ctx):
+    """Size-independent properties at BASELINE config-2 scale (4,096,000 particles): keys[perm] sorted, perm a
+    bijection, stable (ties keep ascending original index)."""
+    from sphinxsys_b200 import capi, cases
+    case = cases.dam_break(dim=3, dp=0.00625)
+    n = case.n_fluid
+    assert n == 4_096_000
+    p4 = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+    p4[:, :3] = torch.from_numpy(case.fluid_pos).cuda()
+    keys = torch.zeros(n, dtype=torch.int32, device="cuda")
+    perm = torch.zeros(n, dtype=torch.int32, device="cuda")
+    m = capi.mesh_t(case.mesh)
+    ctx.call("sphb200_morton_keys", C.byref(m), _p(p4), n, _p(keys), _p(perm), None, _s())
+    keys0 = keys.clone()
+    ctx.call("sphb200_sort_pairs_u32", _p(keys), _p(perm), n, 30, _s())
+    k = keys.cpu().numpy().view(np.uint32).astype(np.int64)
+    p = perm.cpu().numpy().astype(np.int64)
+    assert np.all(np.diff(k) >= 0)
+    assert np.array_equal(np.sort(p), np.arange(n))
+    assert np.array_equal(keys0.cpu().numpy().view(np.uint32)[p], k.astype(np.uint32))
+    ties = np.diff(k) == 0
+    assert np.all(np.diff(p)[ties] > 0)
