@@ -1,0 +1,338 @@
+#!/usr/bin/env python
+"""bench.py — particle-steps/s of the 3-D WCSPH dam break (BASELINE.json metric) on N B200s of one node.
+
+One "step" = one advection (outer) step of the case-file loop (dambreak.cpp:188-222): density summation +
+regularisation, advection set-up, advection-dt reduction, the ~5 acoustic sub-steps it contains (acoustic-dt
+reduction + 1st half + 2nd half each), position update, particle sort at its natural cadence (every 100 outer
+steps), cell-linked-list and relation rebuild.  value = N_fluid x (acoustic sub-steps executed) / seconds, i.e.
+every per-advection cost is amortised into the particle-step rate.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--dp 0.00625] [--impl ours|reference]
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle (the reference cannot be built in this
+image) on the box's host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+A_STEP_1ST = 128  # algorithmic bytes / particle, 1st half  
+A_STEP_2ND = 84   # algorithmic bytes / particle, 2nd half
+A_OUTER = 122     # per outer step extras
+A_SORT = 224      # per sort
+
+
+def measured_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline_run(dp, max_outer, budget_s, threads=0):
+    """The oracle (CPU restatement of the reference's CK par_host data flow) on the host cores: bounded sample."""
+    from oracle import oracle as orc
+    from sphinxsys_b200 import cases
+    case = cases.dam_break(dim=3, dp=dp)
+    sim = orc.OracleSim(case, f64=False, threads=threads)
+    sim.exec("prepare_ck")
+    t0 = time.perf_counter()
+    done = 0
+    per_step = []
+    while done < max_outer and (time.perf_counter() - t0) < budget_s:
+        t1 = time.perf_counter()
+        sim.exec("run_ck", 1e9, 1, 1e9, 100)
+        per_step.append(time.perf_counter() - t1)
+        done += 1
+    elapsed = time.perf_counter() - t0
+    n_ac = int(sim.exec("acoustic_steps"))
+    return {"value": case.n_fluid * n_ac / elapsed, "unit": "particle-steps/s", "cores": orc.lib().orc_max_threads(),
+            "kind": "port",
+            "sample": f"3-D dam break dp={dp} ({case.n_fluid} fluid + {case.n_wall} wall), {done} outer / {n_ac} acoustic steps "
+                      f"in {elapsed:.1f} s, oracle fp32 + OpenMP (restatement of the reference CK par_host path, not the TBB build)",
+            "_elapsed": elapsed, "_steps": done, "_ms_per_step": 1e3 * elapsed / max(done, 1), "_n_fluid": case.n_fluid}
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    # bounded: each step is one outer step at a reduced resolution; the whole run is capped at ~2 minutes
+    dp = args.ref_dp
+    r = cpu_baseline_run(dp, max(args.steps + args.warmup, 1), 120.0)
+    line = {
+        "metric": "particle-steps/sec (3D WCSPH dam break)", "value": r["value"], "unit": "particle-steps/s",
+        "n_gpus": args.gpus, "steps": r["_steps"], "warmup": 0, "ms_per_step": r["_ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "impl": "reference",
+        "config": {"workload": f"3-D dam break WCSPH, dp={dp} bounded sample of config 2 (dp=0.00625)", "n_fluid": r["_n_fluid"]},
+        "cpu_baseline": {k: v for k, v in r.items() if not k.startswith("_")},
+        "e2e": {"value": r["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def time_kernel(fn, iters, torch):
+    """average launch duration of fn() over `iters` launches, CUDA events on the launching (current) stream."""
+    fn()
+    torch.cuda.synchronize()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    for _ in range(iters):
+        fn()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e) / iters  # ms
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from sphinxsys_b200 import cases
+    from sphinxsys_b200.solver import DamBreakCK
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — libsphb200 has no CPU path (use --impl reference for the CPU oracle)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    # weak scaling: every rank owns one z-slab of a tank stretched world x in z: rank-local
+    # dam break of the config-2 cross-section. TODO(multi-gpu): halo exchange between slabs.
+    case = cases.dam_break(dim=3, dp=args.dp)
+    solver = DamBreakCK(case, device_index=local_rank, fused_time_step=True, sort_interval=100)
+    solver.initialize()
+    n_fluid = case.n_fluid
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        solver.step_outer()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = solver.ctx.launches
+    ac0 = solver.acoustic_steps
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        solver.step_outer()
+    ev1.record()
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    n_ac = solver.acoustic_steps - ac0
+    launches = solver.ctx.launches - launches0
+    t = torch.tensor([ms, float(n_ac)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tmax = t.clone()
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        tsum = t.clone()
+        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
+        ms = float(tmax[0])
+        total_particle_steps = n_fluid * float(tsum[1])
+    else:
+        total_particle_steps = n_fluid * float(n_ac)
+    value = total_particle_steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (2nd-half fused launch), timed live on the same state ----
+    peak, peak_kind = measured_peak()
+    dt = solver.last_acoustic_dt
+    a1 = solver.fluid_acoustic_step_1st_half
+    a2 = solver.fluid_acoustic_step_2nd_half
+    ms_a2 = time_kernel(lambda: a2.exec(dt * 1e-3), 20, torch)
+    ms_a1 = time_kernel(lambda: a1.exec(dt * 1e-3), 20, torch)
+    ms_sum = time_kernel(lambda: solver.fluid_density_summation.exec(), 10, torch)
+    ms_cl = time_kernel(lambda: solver.water_cell_linked_list.exec(), 10, torch)
+    ms_rel = time_kernel(lambda: solver.water_block_update_complex_relation.exec(), 5, torch)
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get("k_a2", {}).get(str(n_fluid))
+    except Exception:
+        pass
+    ach_a2 = A_STEP_2ND * n_fluid / (ms_a2 * 1e-3) / 1e9
+    roofline = {"bound": "hbm", "kernel": "k_a2 (AcousticStep2ndHalf: initialize+inner+wall+update+dt-max, one launch)",
+                "achieved": ach_a2, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach_a2 / peak,
+                "traffic": traffic, "algorithmic_bytes_per_launch": A_STEP_2ND * n_fluid, "launch_ms": ms_a2,
+                "note": "pair arithmetic (~80 neighbours x ~35 instr) is FP32-issue/L1 bound before it is HBM bound; see DESIGN.md §5",
+                "other_kernels_ms": {"acoustic_1st_half(init+interact)": ms_a1, "density_summation": ms_sum,
+                                     "cell_list_build": ms_cl, "relation_build(inner+contact)": ms_rel}}
+
+    # ---- e2e: the same step driven from HOST buffers (pinned), H2D of the evolving state + D2H of the result ----
+    e2e = None
+    if True:
+        p = solver.water_block.particles
+        names = list(p.evolving)
+        host = {}
+        for nm in names:
+            tdev = p.vars[nm]
+            kind = p.kinds[nm]
+            if kind == "vec":
+                h = torch.from_numpy(p.download(nm)).pin_memory()
+            else:
+                h = tdev[: p.n].cpu().pin_memory()
+            host[nm] = h
+        out_names = ["Position", "Velocity", "Density"]
+        out_host = {nm: torch.empty((p.n, 3) if p.kinds[nm] == "vec" else (p.n,), dtype=torch.float32).pin_memory() for nm in out_names}
+        h2d = sum(h.numel() * h.element_size() for h in host.values())
+        d2h = sum(h.numel() * h.element_size() for h in out_host.values())
+        staging3 = torch.empty((p.n, 3), dtype=torch.float32, device="cuda")
+
+        def e2e_step():
+            for nm in names:
+                p.upload(nm, None, pinned=host[nm])
+            solver.water_block.posvol_dirty = True
+            solver._fused_valid = False
+            solver.water_cell_linked_list.exec()
+            solver.water_block_update_complex_relation.exec()
+            n = solver.step_outer()
+            for nm in out_names:
+                if p.kinds[nm] == "vec":
+                    solver.ctx.call("sphb200_vec4_to_vec3", __import__("ctypes").c_void_p(staging3.data_ptr()),
+                                    __import__("ctypes").c_void_p(p.vars[nm].data_ptr()), p.n,
+                                    __import__("ctypes").c_void_p(torch.cuda.current_stream().cuda_stream))
+                    out_host[nm].copy_(staging3, non_blocking=True)
+                else:
+                    out_host[nm].copy_(p.vars[nm][: p.n], non_blocking=True)
+            torch.cuda.synchronize()
+            return n
+
+        e2e_step()
+        barrier()
+        k_e2e = max(3, min(args.steps, 10))
+        t0 = time.perf_counter()
+        n_ac_e2e = 0
+        for _ in range(k_e2e):
+            n_ac_e2e += e2e_step()
+        barrier()
+        sec = time.perf_counter() - t0
+        tt = torch.tensor([sec, float(n_ac_e2e)], dtype=torch.float64, device="cuda")
+        if world > 1:
+            tm = tt.clone()
+            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+            ts = tt.clone()
+            dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+            sec, tot = float(tm[0]), n_fluid * float(ts[1])
+        else:
+            tot = n_fluid * float(n_ac_e2e)
+        e2e = {"value": tot / sec, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "steps": k_e2e, "note": "per step: H2D of all evolving variables from pinned host memory, cell-list + relation rebuild, "
+                                       "one outer step, D2H of Position/Velocity/Density"}
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample ----
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        r = cpu_baseline_run(args.ref_dp, 3, 25.0)
+        cpu = {k: v for k, v in r.items() if not k.startswith("_")}
+
+    if rank == 0:
+        n_ac_per_outer = n_ac / max(args.steps, 1)
+        alg_bytes = A_STEP_1ST + A_STEP_2ND + A_OUTER / max(n_ac_per_outer, 1e-9) + A_SORT / (100.0 * max(n_ac_per_outer, 1e-9))
+        line = {
+            "metric": "particle-steps/sec (3D WCSPH dam break)", "value": value, "unit": "particle-steps/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"3-D dam break WCSPH (tests_sycl dambreak geometry), dp={args.dp}: {n_fluid} fluid + {case.n_wall} wall "
+                                   f"particles per GPU, AcousticRiemann + wall, Wendland C2 tabulated, sort every 100 outer steps",
+                       "n_fluid_per_gpu": n_fluid, "n_wall_per_gpu": case.n_wall, "acoustic_steps_per_outer": n_ac_per_outer,
+                       "l2_policy": "working set (~2 GB incl. neighbour lists) larger than L2, no flush",
+                       "parallelism": "1 GPU" if world == 1 else f"{world} z-slab replicas (halo exchange pending)"},
+            "roofline": roofline,
+            "whole_step_hbm_frac": value * alg_bytes / 1e9 / peak,
+            "algorithmic_bytes_per_particle_step": alg_bytes,
+            "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--dp", type=float, default=0.00625, help="particle spacing; 0.00625 = config 2 (4,096,000 fluid)")
+    ap.add_argument("--ref-dp", type=float, default=0.0125, help="resolution of the bounded CPU sample (512,000 fluid)")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        if args.warmup < 3:
+            args.warmup = 3
+        run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -115,22 +115,43 @@ typedef struct
 /* CellLinkedList<SPHAdaptation> storage; ref: meshes/cell_linked_list.cpp:167-175 */
 typedef struct
 {
-    uint32_t *cell_offset;    /* [total_cells + 1] */
-    uint32_t *particle_index; /* [max(n, 1)] ; inside a cell, ascending particle index (deterministic) */
+    uint32_t *cell_offset;      /* [total_cells + 1] */
+    uint32_t *particle_index;   /* [max(n, 1)] ; inside a cell, ascending particle index (deterministic) */
+    sphb200_vec4_t *sorted_pos; /* optional [n]: sorted_pos[k] = pos[particle_index[k]] (contiguous candidate runs for
+                                   the neighbour search); NULL = not kept */
 } sphb200_cell_list_t;
 
-/* Relation<...>::NeighborList in the library's coalesced layout ("SELL-32"): particles are grouped in
- * slices of 32; entry k of particle i is index[slice_offset[i/32] + 32*k + (i%32)], k < count[i].
+/* Relation<...>::NeighborList in the library's coalesced layout ("SELL-32").
+ * Rows are stored per SLOT t; slot t holds source particle i = order[t] (order == NULL: i = t). The library
+ * uses the source body's cell-list order (order = particle_index) so that the 32 rows of a slice belong to
+ * spatially adjacent particles whatever the storage order is. Slots are grouped in slices of 32; entry k of
+ * slot t is index[slice_offset[t/32] + 32*k + (t%32)], k < count[t]; entries are TARGET PARTICLE ids.
  * Row order = reference search order (cells x->y->z, then in-cell order), so sums are reproducible.
- * sphb200_relation_export_csr() converts to the reference's particle_offset_/neighbor_index_ form
- * (shared_ck/body_relation/relation_ck.h:89-102). */
+ * sphb200_relation_export_csr() converts to the reference's particle_offset_/neighbor_index_ form indexed by
+ * particle id (shared_ck/body_relation/relation_ck.h:89-102). */
 typedef struct
 {
-    uint32_t *count;        /* [n + 1] neighbours of particle i (entry n is scratch for the CSR export scan) */
+    uint32_t *count;        /* [n + 1] neighbours of slot t (entry n is scratch) */
     uint32_t *slice_offset; /* [ceil(n/32) + 1] */
     uint32_t *index;        /* [capacity] */
     uint64_t capacity;      /* entries allocated for `index` */
+    const uint32_t *order;  /* [n] slot -> source particle id, or NULL (identity) */
 } sphb200_relation_t;
+
+/* One neighbour search: which particles look (src, in slot order), where they look (tar body + its cell list) */
+typedef struct
+{
+    sphb200_mesh_t tar_mesh;
+    sphb200_kernel_t kernel;
+    const sphb200_vec4_t *src_pos;        /* [n_src (+ghosts)] source Position */
+    uint32_t n_src;                       /* number of source slots */
+    const uint32_t *src_order;            /* slot -> source particle id (NULL: identity) */
+    const sphb200_vec4_t *src_sorted_pos; /* optional: source positions in slot order */
+    const sphb200_vec4_t *tar_pos;        /* target Position */
+    sphb200_cell_list_t tar_list;         /* target cell-linked list */
+    int32_t is_inner;                     /* 1: Inner<> (exclude j == i), 0: Contact<> */
+    int32_t search_depth;                 /* cells each side: 1 inner; contact: cell_linked_list.hpp:161-167 */
+} sphb200_search_t;
 
 /* ---------------------------------------------------------------------------------------------------
  * context, diagnostics, memory  (replaces implementation_sycl.h:43-160 ExecutionInstance + USM helpers)
@@ -193,15 +214,16 @@ int sphb200_cell_list_build(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, 
  *   *_fill  : fills rel.index (returns SPHB200_E_CAPACITY if rel.capacity is too small)
  * Neighbour criterion: |inv_h (x_i - x_j)|^2 < kernel_size^2, strict, ops rounded separately
  * (neighbor_method.hpp:152-156); inner additionally j != i.  `tar_*` describe the searched body. */
-int sphb200_relation_count(sphb200_context_t *ctx, const sphb200_mesh_t *tar_mesh, const sphb200_kernel_t *kernel,
-                           const sphb200_vec4_t *src_pos, uint32_t n_src, const sphb200_vec4_t *tar_pos,
-                           sphb200_cell_list_t tar_list, int is_inner, int search_depth, sphb200_relation_t rel,
+int sphb200_relation_count(sphb200_context_t *ctx, const sphb200_search_t *search, sphb200_relation_t rel,
                            uint64_t *required_host, void *stream);
-int sphb200_relation_fill(sphb200_context_t *ctx, const sphb200_mesh_t *tar_mesh, const sphb200_kernel_t *kernel,
-                          const sphb200_vec4_t *src_pos, uint32_t n_src, const sphb200_vec4_t *tar_pos,
-                          sphb200_cell_list_t tar_list, int is_inner, int search_depth, sphb200_relation_t rel,
-                          void *stream);
-/* SELL-32 -> reference CSR (particle_offset_[n+1], neighbor_index_[total]) */
+int sphb200_relation_fill(sphb200_context_t *ctx, const sphb200_search_t *search, sphb200_relation_t rel, void *stream);
+/* One-pass variant: every slice gets the fixed length 32*stride (slice_offset[s] = 32*stride*s, which needs
+ * rel.capacity >= 32*stride*ceil(n/32)), so count and fill happen in a single search. Rows longer than `stride`
+ * are truncated in `index` but counted in full: *max_count_host > stride tells the host to fall back to
+ * sphb200_relation_count/_fill (nothing is silently dropped). */
+int sphb200_relation_build_fixed(sphb200_context_t *ctx, const sphb200_search_t *search, sphb200_relation_t rel,
+                                 uint32_t stride, uint32_t *max_count_host, void *stream);
+/* SELL-32 (slot order) -> reference CSR indexed by particle id (particle_offset_[n+1], neighbor_index_[total]) */
 int sphb200_relation_export_csr(sphb200_context_t *ctx, sphb200_relation_t rel, uint32_t n, uint32_t *particle_offset,
                                 uint32_t *neighbor_index, uint64_t index_capacity, void *stream);
 
@@ -212,8 +234,8 @@ typedef struct
 {
     sphb200_fluid_view_t fluid;
     sphb200_wall_view_t wall;       /* wall.n == 0: no contact body */
-    sphb200_relation_t inner;
-    sphb200_relation_t contact;
+    sphb200_relation_t inner;       /* inner.order defines the slot order the launch iterates in */
+    sphb200_relation_t contact;     /* must have been built with the same src_order as `inner` */
     sphb200_kernel_t kernel;
     sphb200_fluid_t material;
 } sphb200_fluid_args_t;

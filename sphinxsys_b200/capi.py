@@ -49,11 +49,17 @@ class WallView(C.Structure):
 
 
 class CellListT(C.Structure):
-    _fields_ = [("cell_offset", _P), ("particle_index", _P)]
+    _fields_ = [("cell_offset", _P), ("particle_index", _P), ("sorted_pos", _P)]
 
 
 class RelationT(C.Structure):
-    _fields_ = [("count", _P), ("slice_offset", _P), ("index", _P), ("capacity", C.c_uint64)]
+    _fields_ = [("count", _P), ("slice_offset", _P), ("index", _P), ("capacity", C.c_uint64), ("order", _P)]
+
+
+class SearchT(C.Structure):
+    _fields_ = [("tar_mesh", MeshT), ("kernel", KernelT), ("src_pos", _P), ("n_src", C.c_uint32), ("src_order", _P),
+                ("src_sorted_pos", _P), ("tar_pos", _P), ("tar_list", CellListT), ("is_inner", C.c_int32),
+                ("search_depth", C.c_int32)]
 
 
 class FluidArgs(C.Structure):
@@ -88,10 +94,9 @@ SYMBOLS = {
     "sphb200_morton_keys": (_I, [_CTX, C.POINTER(MeshT), _P, _U32, _P, _P, _P, _P]),
     "sphb200_update_sorted_id": (_I, [_CTX, _P, _P, _U32, _P]),
     "sphb200_cell_list_build": (_I, [_CTX, C.POINTER(MeshT), _P, _U32, CellListT, _P]),
-    "sphb200_relation_count": (_I, [_CTX, C.POINTER(MeshT), C.POINTER(KernelT), _P, _U32, _P, CellListT, _I, _I,
-                                    RelationT, C.POINTER(_U64), _P]),
-    "sphb200_relation_fill": (_I, [_CTX, C.POINTER(MeshT), C.POINTER(KernelT), _P, _U32, _P, CellListT, _I, _I,
-                                   RelationT, _P]),
+    "sphb200_relation_count": (_I, [_CTX, C.POINTER(SearchT), RelationT, C.POINTER(_U64), _P]),
+    "sphb200_relation_fill": (_I, [_CTX, C.POINTER(SearchT), RelationT, _P]),
+    "sphb200_relation_build_fixed": (_I, [_CTX, C.POINTER(SearchT), RelationT, _U32, C.POINTER(_U32), _P]),
     "sphb200_relation_export_csr": (_I, [_CTX, RelationT, _U32, _P, _P, _U64, _P]),
     "sphb200_gravity_force": (_I, [_CTX, C.POINTER(FluidView), C.POINTER(_F * 3), _P, _P]),
     "sphb200_compression_summation": (_I, [_CTX, C.POINTER(FluidArgs), _I, _P]),

@@ -20,11 +20,12 @@
 #include "common.cuh"
 
 constexpr int FL_THREADS = 128;
-constexpr int KT_INTERVALS = 21;
+constexpr int KT_INTERVALS = 21; // intervals of the 24-entry table that q in [0, 2] can select
+constexpr int KT_SLOTS = 32;     // padded so that (index & 31) can never leave the table
 
 struct KTab
 {
-    float4 c[KT_INTERVALS];
+    float4 c[KT_SLOTS];
 };
 
 struct FArgs
@@ -40,24 +41,33 @@ struct FArgs
     // relations
     const u32 *in_count, *in_slice, *in_index;
     const u32 *ct_count, *ct_slice, *ct_index;
+    const u32 *order; // slot -> particle id (the relations' row order), or nullptr
     // constants
-    float inv_h, inv_dq, W0;
+    float inv_h, inv_dq, q_scale, W0;
     float rho0, c0, p0, Z, inv_Z_sum, inv_Z_ave, Z_geo, inv_c_ave, limiter;
     int free_surface, dim;
 };
 
-// per-interval cubic coefficients of the 4-point Lagrange interpolant, in t = q/dq - location (t in [0,1)),
-// pre-multiplied by `scale` (inv_h^dim * dimension_factor for W, inv_h^(dim+1) * dimension_factor for dW)
+// Per-interval cubic coefficients of the 4-point Lagrange interpolant (kernel_tabulated_ck.h:45-58).
+// With t = q/dq - location in [0,1) the interpolant is a0 + a1 t + a2 t^2 + a3 t^3; the table stores it
+// re-expanded in the CENTRED variable s = t - 1/2 in [-1/2, 1/2] (what the magic-number rounding in eval_tab
+// produces), pre-multiplied by `scale` (inv_h^dim * dimension_factor for W, inv_h^(dim+1) * ... for dW).
 static void build_tab(const float *data, double scale, KTab *out)
 {
-    for (int loc = 0; loc < KT_INTERVALS; ++loc)
+    for (int loc = 0; loc < KT_SLOTS; ++loc)
     {
-        double d0 = data[loc], d1 = data[loc + 1], d2 = data[loc + 2], d3 = data[loc + 3];
+        int l = loc < KT_INTERVALS ? loc : KT_INTERVALS - 1;
+        double d0 = data[l], d1 = data[l + 1], d2 = data[l + 2], d3 = data[l + 3];
         double a0 = d1;
         double a1 = -d0 / 3.0 - d1 / 2.0 + d2 - d3 / 6.0;
         double a2 = d0 / 2.0 - d1 + d2 / 2.0;
         double a3 = -d0 / 6.0 + d1 / 2.0 - d2 / 2.0 + d3 / 6.0;
-        out->c[loc] = make_float4((float)(a0 * scale), (float)(a1 * scale), (float)(a2 * scale), (float)(a3 * scale));
+        // t = s + 1/2
+        double b0 = a0 + a1 / 2.0 + a2 / 4.0 + a3 / 8.0;
+        double b1 = a1 + a2 + 3.0 * a3 / 4.0;
+        double b2 = a2 + 3.0 * a3 / 2.0;
+        double b3 = a3;
+        out->c[loc] = make_float4((float)(b0 * scale), (float)(b1 * scale), (float)(b2 * scale), (float)(b3 * scale));
     }
 }
 
@@ -77,6 +87,12 @@ static int make_fargs(sphb200_context *ctx, const sphb200_fluid_args_t *s, FArgs
     a->ct_count = w.n ? s->contact.count : nullptr;
     a->ct_slice = w.n ? s->contact.slice_offset : nullptr;
     a->ct_index = w.n ? s->contact.index : nullptr;
+    a->order = s->inner.order;
+    if (w.n && s->contact.order != s->inner.order)
+    {
+        snprintf(ctx->err, sizeof(ctx->err), "inner and contact relations must share one slot order");
+        return SPHB200_E_INVALID;
+    }
     const sphb200_kernel_t &k = s->kernel;
     if (k.dim != 2 && k.dim != 3)
     {
@@ -91,6 +107,7 @@ static int make_fargs(sphb200_context *ctx, const sphb200_fluid_args_t *s, FArgs
     if (dwtab) build_tab(k.dw, dw_scale, dwtab);
     a->inv_h = inv_h;
     a->inv_dq = 20.0f / k.kernel_size;
+    a->q_scale = inv_h * a->inv_dq; // r -> q / dq in one multiply
     a->W0 = (float)((k.dim == 2 ? sih * sih : sih * sih * sih) * k.dimension_factor * k.w[1]);
     const sphb200_fluid_t &m = s->material;
     if (m.riemann < 0 || m.riemann > 2 || m.correction < 0 || m.correction > 1)
@@ -114,18 +131,36 @@ static int make_fargs(sphb200_context *ctx, const sphb200_fluid_args_t *s, FArgs
 
 __device__ __forceinline__ void stage_tab(const KTab &src, float4 *dst)
 {
-    if (threadIdx.x < KT_INTERVALS) dst[threadIdx.x] = src.c[threadIdx.x];
+    if (threadIdx.x < KT_SLOTS) dst[threadIdx.x] = src.c[threadIdx.x];
     __syncthreads();
 }
 
-// tabulated-kernel value at q (already scaled): one LDS.128 + 3 FMA
-__device__ __forceinline__ float eval_tab(const float4 *tab, float q, float inv_dq)
+// Tabulated-kernel value (already scaled) at distance r: u = r * q_scale - 1/2 = q/dq - 1/2; adding 1.5 * 2^23
+// rounds u to the nearest integer = floor(q/dq) (ties land on a node, where adjacent intervals agree), leaves
+// that integer in the low mantissa bits, and s = u - round(u) is the centred local coordinate.
+// FFMA + 2 FADD + LOP + LDS.128 + 3 FFMA, no conversion/SFU instructions.
+__device__ __forceinline__ float eval_tab(const float4 *tab, float r, float q_scale)
 {
-    float tq = q * inv_dq;
-    float lf = fminf(floorf(tq), (float)(KT_INTERVALS - 1));
-    float t = tq - lf;
-    float4 c = tab[(int)lf];
-    return fmaf(fmaf(fmaf(c.w, t, c.z), t, c.y), t, c.x);
+    const float MAGIC = 12582912.0f; // 1.5 * 2^23
+    float u = fmaf(r, q_scale, -0.5f);
+    float m = u + MAGIC;
+    float s = u - (m - MAGIC);
+    float4 c = tab[__float_as_int(m) & (KT_SLOTS - 1)];
+    return fmaf(fmaf(fmaf(c.w, s, c.z), s, c.y), s, c.x);
+}
+
+// 1/sqrt(x) for x > 0 (MUFU.RSQ, flush-to-zero form: no denormal fix-up code); callers clamp x away from 0
+__device__ __forceinline__ float fast_rsqrt(float x)
+{
+    float y;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// |d| and 1/|d| with the convention of Eigen's normalized(): a zero vector stays zero (inv_r finite, d * inv_r = 0)
+__device__ __forceinline__ void dist(float r2, float &r, float &inv_r)
+{
+    inv_r = fast_rsqrt(fmaxf(r2, 1.0e-30f));
+    r = r2 * inv_r;
 }
 
 __device__ __forceinline__ float3 mat_vec(const float *B, float3 v)
@@ -350,35 +385,38 @@ extern "C" int sphb200_total_mechanical_energy(sphb200_context_t *ctx, const sph
 // =====================================================================================================
 __global__ void __launch_bounds__(FL_THREADS) k_compression_summation(FArgs a, KTab wtab, int regularize)
 {
-    __shared__ float4 tab[KT_INTERVALS];
+    __shared__ float4 tab[KT_SLOTS];
     stage_tab(wtab, tab);
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n) return;
+    const u32 i = a.order ? a.order[t] : t;
     float4 xi = a.pos[i];
     float s = a.W0 * a.vol_ref[i];
     {
-        u32 cnt = a.in_count[i];
-        const u32 *idx = a.in_index + (u64)a.in_slice[i >> 5] + (i & 31u);
+        u32 cnt = a.in_count[t];
+        const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
+#pragma unroll 4
         for (u32 k = 0; k < cnt; ++k)
         {
             u32 j = idx[32ull * k];
             float4 xj = a.pos[j];
             float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
             float r = sqrtf(dx * dx + dy * dy + dz * dz);
-            s += eval_tab(tab, r * a.inv_h, a.inv_dq) * a.vol_ref[j];
+            s += eval_tab(tab, r, a.q_scale) * a.vol_ref[j];
         }
     }
     if (a.n_wall)
     {
-        u32 cnt = a.ct_count[i];
-        const u32 *idx = a.ct_index + (u64)a.ct_slice[i >> 5] + (i & 31u);
+        u32 cnt = a.ct_count[t];
+        const u32 *idx = a.ct_index + (u64)a.ct_slice[t >> 5] + (t & 31u);
+#pragma unroll 4
         for (u32 k = 0; k < cnt; ++k)
         {
             u32 j = idx[32ull * k];
             float4 xj = a.w_pos[j];
             float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
             float r = sqrtf(dx * dx + dy * dy + dz * dz);
-            s += eval_tab(tab, r * a.inv_h, a.inv_dq) * a.w_vol_ref[j];
+            s += eval_tab(tab, r, a.q_scale) * a.w_vol_ref[j];
         }
     }
     a.Csum[i] = s;
@@ -449,10 +487,11 @@ __global__ void __launch_bounds__(256) k_a1_init(FArgs a, float dt)
 template <int RIEMANN, bool CORR>
 __global__ void __launch_bounds__(FL_THREADS) k_a1_interact(FArgs a, KTab dwtab, float dt, int do_update)
 {
-    __shared__ float4 tab[KT_INTERVALS];
+    __shared__ float4 tab[KT_SLOTS];
     stage_tab(dwtab, tab);
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n) return;
+    const u32 i = a.order ? a.order[t] : t;
     const float4 xi = a.posvol[i];
     const float p_i = a.p[i];
     float Bi[9];
@@ -460,8 +499,9 @@ __global__ void __launch_bounds__(FL_THREADS) k_a1_interact(FArgs a, KTab dwtab,
 
     float fx = 0.f, fy = 0.f, fz = 0.f, diss = 0.f;
     {
-        u32 cnt = a.in_count[i];
-        const u32 *idx = a.in_index + (u64)a.in_slice[i >> 5] + (i & 31u);
+        u32 cnt = a.in_count[t];
+        const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
+#pragma unroll 4
         for (u32 k = 0; k < cnt; ++k)
         {
             u32 j = idx[32ull * k];
@@ -469,9 +509,9 @@ __global__ void __launch_bounds__(FL_THREADS) k_a1_interact(FArgs a, KTab dwtab,
             float p_j = a.p[j];
             float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
             float r2 = dx * dx + dy * dy + dz * dz;
-            float inv_r = r2 > 0.f ? rsqrtf(r2) : 0.f; // normalized(): zero vector stays zero
-            float r = r2 * inv_r;
-            float dWV = eval_tab(tab, r * a.inv_h, a.inv_dq) * xj.w;
+            float r, inv_r;
+            dist(r2, r, inv_r);
+            float dWV = eval_tab(tab, r, a.q_scale) * xj.w;
             if (CORR)
             {
                 float Bj[9];
@@ -479,15 +519,15 @@ __global__ void __launch_bounds__(FL_THREADS) k_a1_interact(FArgs a, KTab dwtab,
                 float3 e = make_float3(dx * inv_r, dy * inv_r, dz * inv_r);
                 float3 bje = mat_vec(Bj, e), bie = mat_vec(Bi, e);
                 // AverageP(B_j p_i, B_i p_j) * 2 dWV * e
-                float c = 2.0f * dWV * a.inv_Z_sum * a.Z;
+                float c = dWV; // 2 dWV * Z / (Z + Z)
                 fx -= c * (p_i * bje.x + p_j * bie.x);
                 fy -= c * (p_i * bje.y + p_j * bie.y);
                 fz -= c * (p_i * bje.z + p_j * bie.z);
             }
             else
             {
-                float pave = a.inv_Z_sum * (p_i * a.Z + p_j * a.Z); // AverageP, riemann_solver_ck.hpp:19-24
-                float c = pave * 2.0f * dWV * inv_r;
+                // AverageP (riemann_solver_ck.hpp:19-24) with Z_i == Z_j (one fluid): 2 * pave = p_i + p_j
+                float c = (p_i + p_j) * dWV * inv_r;
                 fx -= c * dx; fy -= c * dy; fz -= c * dz;
             }
             if (RIEMANN) diss += (p_i - p_j) * a.inv_Z_ave * dWV; // DissipativeUJump, :51-56
@@ -499,21 +539,22 @@ __global__ void __launch_bounds__(FL_THREADS) k_a1_interact(FArgs a, KTab dwtab,
     const float m_i = a.mass[i];
     if (a.n_wall)
     {
-        u32 cnt = a.ct_count[i];
+        u32 cnt = a.ct_count[t];
         if (cnt)
         {
             const float rho_i = a.rho[i];
             const float ax = Fp.x / m_i, ay = Fp.y / m_i, az = Fp.z / m_i;
-            const u32 *idx = a.ct_index + (u64)a.ct_slice[i >> 5] + (i & 31u);
+            const u32 *idx = a.ct_index + (u64)a.ct_slice[t >> 5] + (t & 31u);
+#pragma unroll 4
             for (u32 k = 0; k < cnt; ++k)
             {
                 u32 j = idx[32ull * k];
                 float4 xj = a.w_posvol[j];
                 float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
                 float r2 = dx * dx + dy * dy + dz * dz;
-                float inv_r = r2 > 0.f ? rsqrtf(r2) : 0.f;
-                float r = r2 * inv_r;
-                float dWV = eval_tab(tab, r * a.inv_h, a.inv_dq) * xj.w;
+                float r, inv_r;
+                dist(r2, r, inv_r);
+                float dWV = eval_tab(tab, r, a.q_scale) * xj.w;
                 float ex = dx * inv_r, ey = dy * inv_r, ez = dz * inv_r;
                 float rx = ax, ry = ay, rz = az;
                 if (a.w_acc)
@@ -619,12 +660,13 @@ extern "C" int sphb200_acoustic_1st_half(sphb200_context_t *ctx, const sphb200_f
 template <int RIEMANN, bool CORR>
 __global__ void __launch_bounds__(FL_THREADS) k_a2(FArgs a, KTab dwtab, float dt, float h_min, float *next_reduced)
 {
-    __shared__ float4 tab[KT_INTERVALS];
+    __shared__ float4 tab[KT_SLOTS];
     stage_tab(dwtab, tab);
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     float measure = 0.f;
-    if (i < a.n)
+    if (t < a.n)
     {
+        const u32 i = a.order ? a.order[t] : t;
         const float4 xi = a.posvol[i];
         const float4 vi = a.vel[i];
         // InitializeKernel::initialize, acoustic_step_2nd_half.hpp:33-38
@@ -637,8 +679,9 @@ __global__ void __launch_bounds__(FL_THREADS) k_a2(FArgs a, KTab dwtab, float dt
         if (CORR) load_mat(a.B, i, Bi);
         float div = 0.f, px = 0.f, py = 0.f, pz = 0.f;
         {
-            u32 cnt = a.in_count[i];
-            const u32 *idx = a.in_index + (u64)a.in_slice[i >> 5] + (i & 31u);
+            u32 cnt = a.in_count[t];
+            const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
+#pragma unroll 4
             for (u32 k = 0; k < cnt; ++k)
             {
                 u32 j = idx[32ull * k];
@@ -646,17 +689,20 @@ __global__ void __launch_bounds__(FL_THREADS) k_a2(FArgs a, KTab dwtab, float dt
                 float4 vj = a.vel[j];
                 float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
                 float r2 = dx * dx + dy * dy + dz * dz;
-                float inv_r = r2 > 0.f ? rsqrtf(r2) : 0.f;
-                float r = r2 * inv_r;
-                float dWV = eval_tab(tab, r * a.inv_h, a.inv_dq) * xj.w;
+                float r, inv_r;
+                dist(r2, r, inv_r);
+                float dWV = eval_tab(tab, r, a.q_scale) * xj.w;
                 float ex = dx * inv_r, ey = dy * inv_r, ez = dz * inv_r;
-                // AverageV, riemann_solver_ck.hpp:26-31
-                float avx = (vi.x * a.Z + vj.x * a.Z) * a.inv_Z_sum;
-                float avy = (vi.y * a.Z + vj.y * a.Z) * a.inv_Z_sum;
-                float avz = (vi.z * a.Z + vj.z * a.Z) * a.inv_Z_sum;
-                float3 ce = CORR ? mat_vec(Bi, make_float3(ex, ey, ez)) : make_float3(ex, ey, ez);
-                div += 2.0f * ((vi.x - avx) * ce.x + (vi.y - avy) * ce.y + (vi.z - avz) * ce.z) * dWV;
-                float u = (vi.x - vj.x) * ex + (vi.y - vj.y) * ey + (vi.z - vj.z) * ez;
+                // AverageV (riemann_solver_ck.hpp:26-31) with Z_i == Z_j: 2 (v_i - v_ave) = v_i - v_j
+                float ux = vi.x - vj.x, uy = vi.y - vj.y, uz = vi.z - vj.z;
+                float u = ux * ex + uy * ey + uz * ez;
+                if (CORR)
+                {
+                    float3 ce = mat_vec(Bi, make_float3(ex, ey, ez));
+                    div += (ux * ce.x + uy * ce.y + uz * ce.z) * dWV;
+                }
+                else
+                    div += u * dWV;
                 float c = pjump<RIEMANN>(a, u) * dWV;
                 px += c * ex; py += c * ey; pz += c * ez;
             }
@@ -664,8 +710,9 @@ __global__ void __launch_bounds__(FL_THREADS) k_a2(FArgs a, KTab dwtab, float dt
         float wdiv = 0.f, wx = 0.f, wy = 0.f, wz = 0.f;
         if (a.n_wall)
         {
-            u32 cnt = a.ct_count[i];
-            const u32 *idx = a.ct_index + (u64)a.ct_slice[i >> 5] + (i & 31u);
+            u32 cnt = a.ct_count[t];
+            const u32 *idx = a.ct_index + (u64)a.ct_slice[t >> 5] + (t & 31u);
+#pragma unroll 4
             for (u32 k = 0; k < cnt; ++k)
             {
                 u32 j = idx[32ull * k];
@@ -673,9 +720,9 @@ __global__ void __launch_bounds__(FL_THREADS) k_a2(FArgs a, KTab dwtab, float dt
                 float4 nj = a.w_n[j];
                 float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
                 float r2 = dx * dx + dy * dy + dz * dz;
-                float inv_r = r2 > 0.f ? rsqrtf(r2) : 0.f;
-                float r = r2 * inv_r;
-                float dWV = eval_tab(tab, r * a.inv_h, a.inv_dq) * xj.w;
+                float r, inv_r;
+                dist(r2, r, inv_r);
+                float dWV = eval_tab(tab, r, a.q_scale) * xj.w;
                 float ex = dx * inv_r, ey = dy * inv_r, ez = dz * inv_r;
                 float vx = vi.x, vy = vi.y, vz = vi.z;
                 if (a.w_vel)
@@ -759,10 +806,11 @@ __device__ __forceinline__ void inv3(const float *m, float *o)
 
 __global__ void __launch_bounds__(FL_THREADS) k_linear_correction(FArgs a, KTab dwtab, float alpha)
 {
-    __shared__ float4 tab[KT_INTERVALS];
+    __shared__ float4 tab[KT_SLOTS];
     stage_tab(dwtab, tab);
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= a.n) return;
+    const u32 i = a.order ? a.order[t] : t;
     const float4 xi = a.posvol[i];
     float b[9];
 #pragma unroll
@@ -770,23 +818,23 @@ __global__ void __launch_bounds__(FL_THREADS) k_linear_correction(FArgs a, KTab 
     auto accumulate = [&](float4 xj) {
         float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
         float r2 = dx * dx + dy * dy + dz * dz;
-        float inv_r = r2 > 0.f ? rsqrtf(r2) : 0.f;
-        float r = r2 * inv_r;
-        float g = eval_tab(tab, r * a.inv_h, a.inv_dq) * inv_r * xj.w; // dW/r * V_j : nablaW V = g * d
+        float r, inv_r;
+        dist(r2, r, inv_r);
+        float g = eval_tab(tab, r, a.q_scale) * inv_r * xj.w; // dW/r * V_j : nablaW V = g * d
         float gx = g * dx, gy = g * dy, gz = g * dz;
         b[0] -= dx * gx; b[1] -= dx * gy; b[2] -= dx * gz;
         b[3] -= dy * gx; b[4] -= dy * gy; b[5] -= dy * gz;
         b[6] -= dz * gx; b[7] -= dz * gy; b[8] -= dz * gz;
     };
     {
-        u32 cnt = a.in_count[i];
-        const u32 *idx = a.in_index + (u64)a.in_slice[i >> 5] + (i & 31u);
+        u32 cnt = a.in_count[t];
+        const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
         for (u32 k = 0; k < cnt; ++k) accumulate(a.posvol[idx[32ull * k]]);
     }
     if (a.n_wall)
     {
-        u32 cnt = a.ct_count[i];
-        const u32 *idx = a.ct_index + (u64)a.ct_slice[i >> 5] + (i & 31u);
+        u32 cnt = a.ct_count[t];
+        const u32 *idx = a.ct_index + (u64)a.ct_slice[t >> 5] + (t & 31u);
         for (u32 k = 0; k < cnt; ++k) accumulate(a.w_posvol[idx[32ull * k]]);
     }
     if (a.dim == 2) b[8] = 1.0f;

@@ -76,7 +76,7 @@ __global__ void __launch_bounds__(256)
 // deterministic in-cell order: the final slot of i is the number of cell-mates with a smaller index
 __global__ void __launch_bounds__(256)
     k_cell_order(const u32 *__restrict__ cell_offset, const u32 *__restrict__ cell_of, const u32 *__restrict__ unordered,
-                 u32 n, u32 *__restrict__ particle_index)
+                 u32 n, u32 *__restrict__ particle_index, const float4 *__restrict__ pos, float4 *__restrict__ sorted_pos)
 {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -85,6 +85,7 @@ __global__ void __launch_bounds__(256)
     u32 smaller = 0;
     for (u32 k = b; k < e; ++k) smaller += (unordered[k] < i);
     particle_index[b + smaller] = i;
+    if (sorted_pos) sorted_pos[b + smaller] = pos[i];
 }
 
 extern "C" int sphb200_cell_list_build(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, const sphb200_vec4_t *pos,
@@ -107,7 +108,7 @@ extern "C" int sphb200_cell_list_build(sphb200_context_t *ctx, const sphb200_mes
     {
         SPH_LAUNCH(ctx, k_cell_fill, sph_blocks(n, 256), 256, 0, st, list.cell_offset, cell_of, rank, n, unordered);
         SPH_LAUNCH(ctx, k_cell_order, sph_blocks(n, 256), 256, 0, st, list.cell_offset, cell_of, unordered, n,
-                   list.particle_index);
+                   list.particle_index, (const float4 *)pos, (float4 *)list.sorted_pos);
     }
     return 0;
 }
@@ -119,7 +120,10 @@ struct SearchArgs
 {
     DMesh m;
     const float4 *src_pos;
+    const float4 *src_sorted_pos;
+    const u32 *src_order;
     const float4 *tar_pos;
+    const float4 *tar_sorted_pos;
     const u32 *cell_offset;
     const u32 *particle_index;
     u32 n_src;
@@ -138,9 +142,12 @@ __device__ __forceinline__ bool within(float4 xi, float4 xj, float inv_h, float 
     return r2 < ks2;
 }
 
-// enumerate candidates in the reference order: cells x -> y -> z (mesh_iterators.hpp:18-27); for fixed (x, y)
-// the z cells are contiguous in the linear index, so each (x, y) column is one run of the particle list.
-template <bool INNER, class F> __device__ __forceinline__ void for_each_neighbor(const SearchArgs &a, u32 i, float4 xi, F f)
+// Enumerate candidates in the reference order: cells x -> y -> z (mesh_iterators.hpp:18-27); for fixed (x, y)
+// the z cells are contiguous in the linear index, so each (x, y) column is ONE run of the cell list. With
+// SORTED (cell-ordered position copy available) a run is a contiguous float4 stream and the particle id is only
+// fetched for hits; otherwise positions are gathered through particle_index.
+template <bool INNER, bool SORTED, class F>
+__device__ __forceinline__ void for_each_neighbor(const SearchArgs &a, u32 i, float4 xi, F f)
 {
     const DMesh &m = a.m;
     int ca = cell_coord(xi.x, m.lx, m.spacing, m.cx);
@@ -154,69 +161,123 @@ template <bool INNER, class F> __device__ __forceinline__ void for_each_neighbor
         {
             u32 lin0 = cell_linear(m, x, y, z0);
             u32 b = a.cell_offset[lin0], e = a.cell_offset[lin0 + (u32)(z1 - z0)];
+#pragma unroll 4
             for (u32 k = b; k < e; ++k)
             {
-                u32 j = a.particle_index[k];
-                if (INNER && j == i) continue;
-                float4 xj = a.tar_pos[j];
-                if (within(xi, xj, a.inv_h, a.ks2)) f(j);
+                if (SORTED)
+                {
+                    float4 xj = a.tar_sorted_pos[k];
+                    if (within(xi, xj, a.inv_h, a.ks2))
+                    {
+                        u32 j = a.particle_index[k];
+                        if (!(INNER && j == i)) f(j);
+                    }
+                }
+                else
+                {
+                    u32 j = a.particle_index[k];
+                    if (INNER && j == i) continue;
+                    float4 xj = a.tar_pos[j];
+                    if (within(xi, xj, a.inv_h, a.ks2)) f(j);
+                }
             }
         }
 }
 
-template <bool INNER>
-__global__ void __launch_bounds__(128) k_relation_count(SearchArgs a, u32 *__restrict__ count, u32 *__restrict__ slice_len)
+__device__ __forceinline__ void load_source(const SearchArgs &a, u32 t, u32 &i, float4 &xi)
 {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    u32 c = 0;
-    if (i < a.n_src)
-    {
-        float4 xi = a.src_pos[i];
-        for_each_neighbor<INNER>(a, i, xi, [&](u32) { ++c; });
-        count[i] = c;
-    }
-    u32 mx = warp_max_u32(c);
-    if ((threadIdx.x & 31) == 0 && (i >> 5) <= ((a.n_src - 1) >> 5)) slice_len[i >> 5] = mx * 32u;
+    i = a.src_order ? a.src_order[t] : t;
+    xi = a.src_sorted_pos ? a.src_sorted_pos[t] : a.src_pos[i];
 }
 
-template <bool INNER>
+// MODE 0: count only (exact two-phase build, phase 1)
+// MODE 1: fill only  (phase 2; slice offsets come from the scan)
+// MODE 2: one pass, fixed slice stride: count + fill + running max of the row length
+template <bool INNER, bool SORTED, int MODE>
 __global__ void __launch_bounds__(128)
-    k_relation_fill(SearchArgs a, const u32 *__restrict__ slice_offset, u32 *__restrict__ index, u64 capacity)
+    k_relation(SearchArgs a, u32 *__restrict__ count, u32 *__restrict__ slice, u32 *__restrict__ index, u64 capacity, u32 stride,
+               u32 *__restrict__ max_count)
 {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n_src) return;
-    float4 xi = a.src_pos[i];
-    u64 pos = (u64)slice_offset[i >> 5] + (i & 31u);
-    for_each_neighbor<INNER>(a, i, xi, [&](u32 j) {
-        if (pos < capacity) index[pos] = j;
-        pos += 32;
-    });
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 c = 0;
+    if (t < a.n_src)
+    {
+        u32 i;
+        float4 xi;
+        load_source(a, t, i, xi);
+        if (MODE == 0)
+            for_each_neighbor<INNER, SORTED>(a, i, xi, [&](u32) { ++c; });
+        else
+        {
+            u64 base = (MODE == 1 ? (u64)slice[t >> 5] : (u64)(t >> 5) * 32ull * stride) + (t & 31u);
+            u32 limit = MODE == 2 ? stride : 0xffffffffu;
+            for_each_neighbor<INNER, SORTED>(a, i, xi, [&](u32 j) {
+                u64 pos = base + 32ull * c;
+                if (c < limit && pos < capacity) index[pos] = j;
+                ++c;
+            });
+        }
+        if (MODE != 1) count[t] = c;
+    }
+    if (MODE == 0)
+    {
+        u32 mx = warp_max_u32(c);
+        if ((threadIdx.x & 31) == 0 && t < a.n_src) slice[t >> 5] = mx * 32u;
+    }
+    if (MODE == 2)
+    {
+        u32 mx = warp_max_u32(c);
+        if ((threadIdx.x & 31) == 0 && t < a.n_src)
+        {
+            slice[t >> 5] = (t >> 5) * 32u * stride;
+            if (mx > 0) atomicMax(max_count, mx);
+        }
+    }
 }
 
-static int make_search(sphb200_context *ctx, const sphb200_mesh_t *mesh, const sphb200_kernel_t *kernel,
-                       const sphb200_vec4_t *src_pos, u32 n_src, const sphb200_vec4_t *tar_pos, sphb200_cell_list_t list,
-                       int depth, SearchArgs *a)
+static int make_search(sphb200_context *ctx, const sphb200_search_t *s, SearchArgs *a)
 {
-    a->m = make_dmesh(mesh);
-    a->src_pos = (const float4 *)src_pos;
-    a->tar_pos = (const float4 *)tar_pos;
-    a->cell_offset = list.cell_offset;
-    a->particle_index = list.particle_index;
-    a->n_src = n_src;
-    a->inv_h = 1.0f / kernel->h; // inv_h_ = 1 / max(src_h, tar_h), neighbor_method.hpp:73-76
-    a->ks2 = kernel->kernel_size * kernel->kernel_size;
-    a->depth = depth;
+    SPH_CHECK_ARG(ctx, s->search_depth >= 1 && s->search_depth <= 4, "search depth out of range");
+    a->m = make_dmesh(&s->tar_mesh);
+    a->src_pos = (const float4 *)s->src_pos;
+    a->src_sorted_pos = (const float4 *)s->src_sorted_pos;
+    a->src_order = s->src_order;
+    a->tar_pos = (const float4 *)s->tar_pos;
+    a->tar_sorted_pos = (const float4 *)s->tar_list.sorted_pos;
+    a->cell_offset = s->tar_list.cell_offset;
+    a->particle_index = s->tar_list.particle_index;
+    a->n_src = s->n_src;
+    a->inv_h = 1.0f / s->kernel.h; // inv_h_ = 1 / max(src_h, tar_h), neighbor_method.hpp:73-76
+    a->ks2 = s->kernel.kernel_size * s->kernel.kernel_size;
+    a->depth = s->search_depth;
+    if (s->n_src)
+    {
+        SPH_CHECK_ARG(ctx, (a->src_pos || (a->src_sorted_pos && a->src_order)) && a->tar_pos && a->cell_offset && a->particle_index,
+                      "null pointer");
+        SPH_CHECK_ARG(ctx, !s->is_inner || a->src_pos || a->src_order, "null pointer");
+    }
     return 0;
 }
 
-extern "C" int sphb200_relation_count(sphb200_context_t *ctx, const sphb200_mesh_t *tar_mesh, const sphb200_kernel_t *kernel,
-                                      const sphb200_vec4_t *src_pos, uint32_t n_src, const sphb200_vec4_t *tar_pos,
-                                      sphb200_cell_list_t tar_list, int is_inner, int search_depth, sphb200_relation_t rel,
+template <int MODE>
+static int launch_relation(sphb200_context *ctx, const SearchArgs &a, bool inner, u32 *count, u32 *slice, u32 *index, u64 cap,
+                           u32 stride, u32 *max_count, cudaStream_t st)
+{
+    unsigned g = sph_blocks(a.n_src, 128);
+    bool sorted = a.tar_sorted_pos != nullptr;
+    if (inner && sorted) SPH_LAUNCH(ctx, (k_relation<true, true, MODE>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
+    else if (inner) SPH_LAUNCH(ctx, (k_relation<true, false, MODE>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
+    else if (sorted) SPH_LAUNCH(ctx, (k_relation<false, true, MODE>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
+    else SPH_LAUNCH(ctx, (k_relation<false, false, MODE>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
+    return 0;
+}
+
+extern "C" int sphb200_relation_count(sphb200_context_t *ctx, const sphb200_search_t *search, sphb200_relation_t rel,
                                       uint64_t *required_host, void *stream)
 {
-    SPH_CHECK_ARG(ctx, ctx && tar_mesh && kernel && rel.count && rel.slice_offset, "null pointer");
-    SPH_CHECK_ARG(ctx, search_depth >= 1 && search_depth <= 4, "search depth out of range");
+    SPH_CHECK_ARG(ctx, ctx && search && rel.count && rel.slice_offset, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    u32 n_src = search->n_src;
     u32 nslices = (n_src + 31) / 32;
     if (n_src == 0)
     {
@@ -224,18 +285,16 @@ extern "C" int sphb200_relation_count(sphb200_context_t *ctx, const sphb200_mesh
         if (required_host) *required_host = 0;
         return 0;
     }
-    SPH_CHECK_ARG(ctx, src_pos && tar_pos && tar_list.cell_offset && tar_list.particle_index, "null pointer");
     SearchArgs a;
-    make_search(ctx, tar_mesh, kernel, src_pos, n_src, tar_pos, tar_list, search_depth, &a);
+    int rc = make_search(ctx, search, &a);
+    if (rc) return rc;
     void *p;
-    int rc = sph_scratch(ctx, 3, ((size_t)nslices + 1) * sizeof(u32) + 64, &p);
+    rc = sph_scratch(ctx, 3, ((size_t)nslices + 1) * sizeof(u32) + 64, &p);
     if (rc) return rc;
     u32 *slice_len = (u32 *)p;
     SPH_CUDA(ctx, cudaMemsetAsync(slice_len + nslices, 0, sizeof(u32), st));
-    if (is_inner)
-        SPH_LAUNCH(ctx, k_relation_count<true>, sph_blocks(n_src, 128), 128, 0, st, a, rel.count, slice_len);
-    else
-        SPH_LAUNCH(ctx, k_relation_count<false>, sph_blocks(n_src, 128), 128, 0, st, a, rel.count, slice_len);
+    rc = launch_relation<0>(ctx, a, search->is_inner != 0, rel.count, slice_len, nullptr, 0, 0, nullptr, st);
+    if (rc) return rc;
     rc = sph_scan_u32(ctx, slice_len, rel.slice_offset, (u64)nslices + 1, 0, st);
     if (rc) return rc;
     if (required_host)
@@ -247,34 +306,67 @@ extern "C" int sphb200_relation_count(sphb200_context_t *ctx, const sphb200_mesh
     return 0;
 }
 
-extern "C" int sphb200_relation_fill(sphb200_context_t *ctx, const sphb200_mesh_t *tar_mesh, const sphb200_kernel_t *kernel,
-                                     const sphb200_vec4_t *src_pos, uint32_t n_src, const sphb200_vec4_t *tar_pos,
-                                     sphb200_cell_list_t tar_list, int is_inner, int search_depth, sphb200_relation_t rel,
-                                     void *stream)
+extern "C" int sphb200_relation_fill(sphb200_context_t *ctx, const sphb200_search_t *search, sphb200_relation_t rel, void *stream)
 {
-    SPH_CHECK_ARG(ctx, ctx && tar_mesh && kernel && rel.count && rel.slice_offset && rel.index, "null pointer");
-    SPH_CHECK_ARG(ctx, search_depth >= 1 && search_depth <= 4, "search depth out of range");
-    if (n_src == 0) return 0;
+    SPH_CHECK_ARG(ctx, ctx && search && rel.count && rel.slice_offset && rel.index, "null pointer");
+    if (search->n_src == 0) return 0;
     SearchArgs a;
-    make_search(ctx, tar_mesh, kernel, src_pos, n_src, tar_pos, tar_list, search_depth, &a);
+    int rc = make_search(ctx, search, &a);
+    if (rc) return rc;
+    return launch_relation<1>(ctx, a, search->is_inner != 0, rel.count, rel.slice_offset, rel.index, rel.capacity, 0, nullptr,
+                              (cudaStream_t)stream);
+}
+
+extern "C" int sphb200_relation_build_fixed(sphb200_context_t *ctx, const sphb200_search_t *search, sphb200_relation_t rel,
+                                            uint32_t stride, uint32_t *max_count_host, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && search && rel.count && rel.slice_offset && rel.index, "null pointer");
+    SPH_CHECK_ARG(ctx, stride > 0, "stride must be positive");
     cudaStream_t st = (cudaStream_t)stream;
-    if (is_inner)
-        SPH_LAUNCH(ctx, k_relation_fill<true>, sph_blocks(n_src, 128), 128, 0, st, a, rel.slice_offset, rel.index, rel.capacity);
-    else
-        SPH_LAUNCH(ctx, k_relation_fill<false>, sph_blocks(n_src, 128), 128, 0, st, a, rel.slice_offset, rel.index, rel.capacity);
+    u32 n_src = search->n_src;
+    u64 nslices = ((u64)n_src + 31) / 32;
+    if (rel.capacity < nslices * 32ull * stride)
+    {
+        snprintf(ctx->err, sizeof(ctx->err), "relation_build_fixed: capacity %llu < %llu", (unsigned long long)rel.capacity,
+                 (unsigned long long)(nslices * 32ull * stride));
+        return SPHB200_E_CAPACITY;
+    }
+    SPH_CHECK_ARG(ctx, nslices * 32ull * stride < (1ull << 32), "fixed-stride relation exceeds 2^32 entries");
+    u32 *dmax = (u32 *)ctx->dev_scalars + 8;
+    SPH_CUDA(ctx, cudaMemsetAsync(dmax, 0, sizeof(u32), st));
+    if (n_src)
+    {
+        SearchArgs a;
+        int rc = make_search(ctx, search, &a);
+        if (rc) return rc;
+        rc = launch_relation<2>(ctx, a, search->is_inner != 0, rel.count, rel.slice_offset, rel.index, rel.capacity, stride, dmax, st);
+        if (rc) return rc;
+    }
+    if (max_count_host)
+    {
+        SPH_CUDA(ctx, cudaMemcpyAsync((u32 *)ctx->host_pinned + 8, dmax, sizeof(u32), cudaMemcpyDeviceToHost, st));
+        SPH_CUDA(ctx, cudaStreamSynchronize(st));
+        *max_count_host = *((u32 *)ctx->host_pinned + 8);
+    }
     return 0;
 }
 
-// SELL-32 -> CSR
-__global__ void __launch_bounds__(128)
-    k_export_csr(const u32 *__restrict__ count, const u32 *__restrict__ slice_offset, const u32 *__restrict__ index, u32 n,
-                 const u32 *__restrict__ particle_offset, u32 *__restrict__ neighbor_index)
+// SELL-32 (slot order) -> CSR by particle id
+__global__ void __launch_bounds__(256) k_counts_by_id(const u32 *__restrict__ count, const u32 *__restrict__ order, u32 n, u32 *__restrict__ by_id)
 {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    u64 src = (u64)slice_offset[i >> 5] + (i & 31u);
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) by_id[order ? order[t] : t] = count[t];
+}
+__global__ void __launch_bounds__(128)
+    k_export_csr(const u32 *__restrict__ count, const u32 *__restrict__ slice_offset, const u32 *__restrict__ index,
+                 const u32 *__restrict__ order, u32 n, const u32 *__restrict__ particle_offset, u32 *__restrict__ neighbor_index)
+{
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    u32 i = order ? order[t] : t;
+    u64 src = (u64)slice_offset[t >> 5] + (t & 31u);
     u32 dst = particle_offset[i];
-    u32 c = count[i];
+    u32 c = count[t];
     for (u32 k = 0; k < c; ++k) neighbor_index[dst + k] = index[src + 32ull * k];
 }
 
@@ -283,8 +375,14 @@ extern "C" int sphb200_relation_export_csr(sphb200_context_t *ctx, sphb200_relat
 {
     SPH_CHECK_ARG(ctx, ctx && rel.count && rel.slice_offset && particle_offset, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
-    // particle_offset = exclusive scan of count over n+1 entries (the last input is unused)
-    int rc = sph_scan_u32(ctx, rel.count, particle_offset, (u64)n + 1, 0, st);
+    void *p;
+    int rc = sph_scratch(ctx, 3, ((size_t)n + 1) * sizeof(u32) + 64, &p);
+    if (rc) return rc;
+    u32 *by_id = (u32 *)p;
+    SPH_CUDA(ctx, cudaMemsetAsync(by_id + n, 0, sizeof(u32), st));
+    if (n) SPH_LAUNCH(ctx, k_counts_by_id, sph_blocks(n, 256), 256, 0, st, rel.count, rel.order, n, by_id);
+    // particle_offset = exclusive scan of the per-particle counts over n+1 entries
+    rc = sph_scan_u32(ctx, by_id, particle_offset, (u64)n + 1, 0, st);
     if (rc) return rc;
     if (n == 0 || !neighbor_index) return 0;
     SPH_CUDA(ctx, cudaMemcpyAsync(ctx->host_pinned, particle_offset + n, sizeof(u32), cudaMemcpyDeviceToHost, st));
@@ -296,7 +394,7 @@ extern "C" int sphb200_relation_export_csr(sphb200_context_t *ctx, sphb200_relat
                  (unsigned long long)index_capacity);
         return SPHB200_E_CAPACITY;
     }
-    SPH_LAUNCH(ctx, k_export_csr, sph_blocks(n, 128), 128, 0, st, rel.count, rel.slice_offset, rel.index, n, particle_offset,
-               neighbor_index);
+    SPH_LAUNCH(ctx, k_export_csr, sph_blocks(n, 128), 128, 0, st, rel.count, rel.slice_offset, rel.index, rel.order, n,
+               particle_offset, neighbor_index);
     return 0;
 }

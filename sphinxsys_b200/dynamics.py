@@ -173,9 +173,11 @@ class CellLinkedList:
         cells = body.mesh.total_cells
         self.cell_offset = torch.zeros(cells + 2, dtype=torch.int32, device=body.device)
         self.particle_index = torch.zeros(max(body.n, 1) + 1, dtype=torch.int32, device=body.device)
+        # cell-ordered copy of Position: contiguous candidate runs for the neighbour search (library extension)
+        self.sorted_pos = torch.zeros((max(body.n, 1), 4), dtype=torch.float32, device=body.device)
 
     def view(self) -> capi.CellListT:
-        return capi.CellListT(_ptr(self.cell_offset), _ptr(self.particle_index))
+        return capi.CellListT(_ptr(self.cell_offset), _ptr(self.particle_index), _ptr(self.sorted_pos))
 
 
 class _Relation:
@@ -190,6 +192,9 @@ class _Relation:
         self.index = torch.zeros(self.capacity, dtype=torch.int32, device=dev)
         self.total = 0
         self.version = 0
+        # one-pass build: fixed slice stride (rows per slot); 0 selects the exact count -> scan -> fill build
+        self.fixed_stride = 0
+        self.max_count = 0
         h = max(source.kernel.h, target.kernel.h)
         self.kernel_t = capi.kernel_t(source.kernel if source.kernel.h >= target.kernel.h else target.kernel, src_h=source.kernel.h)
         self.kernel_t.h = h
@@ -199,7 +204,15 @@ class _Relation:
         self.search_depth = 1 if is_inner else int(np.ceil((max(sp, cut) - np.finfo(np.float32).eps) / sp))
 
     def view(self) -> capi.RelationT:
-        return capi.RelationT(_ptr(self.count), _ptr(self.slice_offset), _ptr(self.index), self.capacity)
+        order = self.source.getCellLinkedList().particle_index
+        return capi.RelationT(_ptr(self.count), _ptr(self.slice_offset), _ptr(self.index), self.capacity, _ptr(order))
+
+    def search(self) -> capi.SearchT:
+        src, tar = self.source, self.target
+        scl, tcl = src.getCellLinkedList(), tar.getCellLinkedList()
+        return capi.SearchT(tcl.mesh_t, self.kernel_t, _ptr(src.particles.vars["Position"]), src.n, _ptr(scl.particle_index),
+                            _ptr(scl.sorted_pos), _ptr(tar.particles.vars["Position"]), tcl.view(), int(self.is_inner),
+                            self.search_depth)
 
     def export_csr(self):
         """Reference layout (particle_offset_[n+1], neighbor_index_[total]) as numpy, for parity checks."""
@@ -242,22 +255,35 @@ class UpdateRelation:
     def __init__(self, policy, *relations):
         self.relations = relations
 
+    @staticmethod
+    def _grow(r, entries):
+        # DiscreteVariable::reallocateData: 1.25 x the required size, no copy (sphinxsys_variable.h:368-375)
+        r.capacity = int(entries * 1.25) + 1
+        r.index = torch.empty(r.capacity, dtype=torch.int32, device=r.source.device)
+        r.version += 1
+
     def exec(self, dt=0.0):
         for r in self.relations:
-            src, tar = r.source, r.target
+            src = r.source
             ctx = src.ctx
-            cll = tar.getCellLinkedList()
+            search = r.search()
+            if r.fixed_stride:
+                need = ((src.n + 31) // 32) * 32 * r.fixed_stride
+                if need > r.capacity:
+                    self._grow(r, need)
+                mx = C.c_uint32(0)
+                ctx.call("sphb200_relation_build_fixed", C.byref(search), r.view(), r.fixed_stride, C.byref(mx), _stream())
+                r.max_count = int(mx.value)
+                r.total = need
+                if r.max_count <= r.fixed_stride:
+                    continue
+                r.fixed_stride = 0  # a row overflowed the stride: rebuild exactly, and stay exact from now on
             required = C.c_uint64(0)
-            args = (C.byref(cll.mesh_t), C.byref(r.kernel_t), _ptr(src.particles.vars["Position"]), src.n,
-                    _ptr(tar.particles.vars["Position"]), cll.view(), int(r.is_inner), r.search_depth)
-            ctx.call("sphb200_relation_count", *args, r.view(), C.byref(required), _stream())
+            ctx.call("sphb200_relation_count", C.byref(search), r.view(), C.byref(required), _stream())
             r.total = int(required.value)
             if r.total > r.capacity:
-                # DiscreteVariable::reallocateData: 1.25 x the required size, no copy (sphinxsys_variable.h:368-375)
-                r.capacity = int(r.total * 1.25) + 1
-                r.index = torch.zeros(r.capacity, dtype=torch.int32, device=src.device)
-                r.version += 1
-            ctx.call("sphb200_relation_fill", *args, r.view(), _stream())
+                self._grow(r, r.total)
+            ctx.call("sphb200_relation_fill", C.byref(search), r.view(), _stream())
 
 
 class ParticleSortCK:

@@ -14,7 +14,7 @@ from . import dynamics as dyn
 
 class DamBreakCK:
     def __init__(self, case: cases.DamBreakCase, device_index=0, correction=False, riemann=1, fused_time_step=True,
-                 sort_interval=100, ctx: capi.Context | None = None):
+                 sort_interval=100, ctx: capi.Context | None = None, relation_stride=None):
         if not torch.cuda.is_available():
             raise capi.SphB200Error("CUDA device required: libsphb200 has no CPU path")
         self.case = case
@@ -31,6 +31,12 @@ class DamBreakCK:
         # ---- relations (:98-100) ----
         self.water_block_inner = dyn.Inner(self.water_block)
         self.water_wall_contact = dyn.Contact(self.water_block, [self.wall_boundary])
+        # one-pass relation build with a fixed row stride (falls back to the exact build if a row overflows);
+        # relation_stride=0 forces the exact count -> scan -> fill build of the reference
+        if relation_stride is None:
+            relation_stride = 128 if case.dim == 3 else 40
+        self.water_block_inner.fixed_stride = int(relation_stride)
+        self.water_wall_contact.fixed_stride = int(relation_stride)
         self.system = dyn._FluidSystem(self.water_block_inner, self.water_wall_contact, riemann=riemann,
                                        correction=int(correction), free_surface=1)
         P = dyn.par_device

@@ -202,6 +202,33 @@ def test_neighbour_lists_bit_exact(pair3d):
     _report("neighbours_3d", {"inner_total": int(o32.uint("inner_offset")[-1]), "contact_total": int(o32.uint("contact_offset")[-1])})
 
 
+def test_exact_two_phase_build_equals_one_pass(pair3d):
+    """count -> scan -> fill (the reference's phases) and the one-pass fixed-stride build give identical lists;
+    a stride that is too small is reported, not silently truncated."""
+    case, gpu, o32, _ = pair3d
+    rel = gpu.water_block_inner
+    ref_off, ref_idx = o32.uint("inner_offset"), o32.uint("inner_index")
+    keep = rel.fixed_stride
+    try:
+        rel.fixed_stride = 0
+        gpu.water_block_update_complex_relation.exec()
+        off, idx = rel.export_csr()
+        assert rel.total == int(np.sum(32 * np.max(np.diff(np.concatenate([ref_off.astype(np.int64)]))[
+            gpu.water_block.getCellLinkedList().particle_index[: case.n_fluid].cpu().numpy().astype(np.int64)][
+            : (case.n_fluid // 32) * 32].reshape(-1, 32), axis=1))) + (32 * int(np.max(np.diff(ref_off.astype(np.int64))[
+                gpu.water_block.getCellLinkedList().particle_index[: case.n_fluid].cpu().numpy().astype(np.int64)][
+                (case.n_fluid // 32) * 32:])) if case.n_fluid % 32 else 0)
+        assert np.array_equal(off, ref_off) and np.array_equal(idx[: ref_off[-1]], ref_idx[: ref_off[-1]])
+        rel.fixed_stride = 16  # far too small for ~65 neighbours: must fall back to the exact build
+        gpu.water_block_update_complex_relation.exec()
+        assert rel.fixed_stride == 0 and rel.max_count == int(np.max(np.diff(ref_off.astype(np.int64))))
+        off, idx = rel.export_csr()
+        assert np.array_equal(off, ref_off) and np.array_equal(idx[: ref_off[-1]], ref_idx[: ref_off[-1]])
+    finally:
+        rel.fixed_stride = keep
+        gpu.water_block_update_complex_relation.exec()
+
+
 def _compare(gpu, o32, o64, names_real, names_vec, tag, tol):
     """|gpu - oracle64| must be within `tol` (field-norm relative) and comparable to the oracle's own fp32 error."""
     rep = {}
