@@ -73,23 +73,31 @@ __global__ void __launch_bounds__(256)
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) list[cell_offset[cell_of[i]] + rank[i]] = i;
 }
-// deterministic in-cell order: the final slot of i is the number of cell-mates with a smaller index
+// deterministic in-cell order: the final slot of i is the number of cell-mates with a smaller sort key
+// (sort_key == nullptr: the particle index itself). Keys must be unique within a cell.
 __global__ void __launch_bounds__(256)
     k_cell_order(const u32 *__restrict__ cell_offset, const u32 *__restrict__ cell_of, const u32 *__restrict__ unordered,
-                 u32 n, u32 *__restrict__ particle_index, const float4 *__restrict__ pos, float4 *__restrict__ sorted_pos)
+                 const u32 *__restrict__ sort_key, u32 n, u32 *__restrict__ particle_index, const float4 *__restrict__ pos,
+                 float4 *__restrict__ sorted_pos)
 {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     u32 c = cell_of[i];
     u32 b = cell_offset[c], e = cell_offset[c + 1];
     u32 smaller = 0;
-    for (u32 k = b; k < e; ++k) smaller += (unordered[k] < i);
+    if (sort_key)
+    {
+        u32 ki = sort_key[i];
+        for (u32 k = b; k < e; ++k) smaller += (sort_key[unordered[k]] < ki);
+    }
+    else
+        for (u32 k = b; k < e; ++k) smaller += (unordered[k] < i);
     particle_index[b + smaller] = i;
     if (sorted_pos) sorted_pos[b + smaller] = pos[i];
 }
 
-extern "C" int sphb200_cell_list_build(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, const sphb200_vec4_t *pos,
-                                       uint32_t n, sphb200_cell_list_t list, void *stream)
+static int cell_list_build(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, const sphb200_vec4_t *pos, uint32_t n,
+                           const uint32_t *sort_key, sphb200_cell_list_t list, void *stream)
 {
     SPH_CHECK_ARG(ctx, ctx && mesh && list.cell_offset && list.particle_index && (pos || n == 0), "null pointer");
     u64 cells = (u64)mesh->cells[0] * mesh->cells[1] * mesh->cells[2];
@@ -107,10 +115,33 @@ extern "C" int sphb200_cell_list_build(sphb200_context_t *ctx, const sphb200_mes
     if (n)
     {
         SPH_LAUNCH(ctx, k_cell_fill, sph_blocks(n, 256), 256, 0, st, list.cell_offset, cell_of, rank, n, unordered);
-        SPH_LAUNCH(ctx, k_cell_order, sph_blocks(n, 256), 256, 0, st, list.cell_offset, cell_of, unordered, n,
+        SPH_LAUNCH(ctx, k_cell_order, sph_blocks(n, 256), 256, 0, st, list.cell_offset, cell_of, unordered, sort_key, n,
                    list.particle_index, (const float4 *)pos, (float4 *)list.sorted_pos);
     }
     return 0;
+}
+
+extern "C" int sphb200_cell_list_build(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, const sphb200_vec4_t *pos,
+                                       uint32_t n, sphb200_cell_list_t list, void *stream)
+{
+    return cell_list_build(ctx, mesh, pos, n, nullptr, list, stream);
+}
+
+// UpdateCellLinkedList for a body whose STORAGE follows the cell order: builds the list from the
+// current positions, gathers every listed variable into its shadow buffer by the resulting permutation
+// (dst_k[slot] = src_k[particle_index[slot]]) and leaves particle_index = identity. In-cell order = ascending
+// sort_key (the reference particle id), so lists and sums do not depend on the storage history.
+extern "C" int sphb200_cell_list_build_reorder(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, const sphb200_vec4_t *pos,
+                                               uint32_t n, const uint32_t *sort_key, sphb200_cell_list_t list, int count,
+                                               void *const *dst, const void *const *src, const uint32_t *elem_bytes,
+                                               void *stream)
+{
+    int rc = cell_list_build(ctx, mesh, pos, n, sort_key, list, stream);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    rc = sphb200_gather_multi(ctx, count, dst, src, elem_bytes, list.particle_index, n, stream);
+    if (rc) return rc;
+    return sphb200_iota_u32(ctx, list.particle_index, n, stream);
 }
 
 // =====================================================================================================
@@ -129,6 +160,7 @@ struct SearchArgs
     u32 n_src;
     float inv_h, ks2;
     int depth;
+    int cell_ordered;
 };
 
 // Neighbor<SPHAdaptation,SPHAdaptation>::NeighborCriterion, neighbor_method.hpp:152-156; every op rounded
@@ -235,6 +267,96 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// -----------------------------------------------------------------------------------------------------
+// Warp-uniform search for CELL-ORDERED storage (slot == particle id on both sides).
+// The 32 lanes of a warp are storage neighbours, i.e. they sit in the same (x, y) cell column and in a few
+// consecutive z cells. Lanes of one column form a group; for each of the (2d+1)^2 neighbouring columns the group
+// walks ONE contiguous run of target slots (cells z_min-d .. z_max+d), so control flow is uniform and every
+// candidate load is a broadcast. A lane accepts candidate k only inside its own clamped cell window
+// [lo, hi) — exactly the cells the reference visits (cell_linked_list.hpp:113-167) — and rows come out in the
+// reference order (cells x -> y -> z, then in-cell order).
+// The criterion is decided by a fused-arithmetic estimate when it is more than 1e-4 away from the threshold and
+// by the separately rounded reference expression (within()) otherwise, so set membership stays bit-identical.
+// -----------------------------------------------------------------------------------------------------
+template <bool INNER, int MODE>
+__global__ void __launch_bounds__(128)
+    k_relation_ordered(SearchArgs a, u32 *__restrict__ count, u32 *__restrict__ slice, u32 *__restrict__ index, u64 capacity,
+                       u32 stride, u32 *__restrict__ max_count)
+{
+    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = t < a.n_src;
+    const DMesh &m = a.m;
+    float4 xi = active ? a.src_pos[t] : make_float4(0.f, 0.f, 0.f, 0.f);
+    const int ca = cell_coord(xi.x, m.lx, m.spacing, m.cx);
+    const int cb = cell_coord(xi.y, m.ly, m.spacing, m.cy);
+    const int cc = cell_coord(xi.z, m.lz, m.spacing, m.cz);
+    const int d = a.depth;
+    const float inv_h2 = a.inv_h * a.inv_h;
+    const float sure_in = a.ks2 * (1.0f - 1.0e-4f), sure_out = a.ks2 * (1.0f + 1.0e-4f);
+    const u64 base = (MODE == 1 ? (u64)(active ? slice[t >> 5] : 0u) : (u64)(t >> 5) * 32ull * stride) + (t & 31u);
+    const u32 limit = MODE == 2 ? stride : 0xffffffffu;
+    u32 c = 0;
+    u32 todo = __ballot_sync(0xffffffffu, active);
+    while (todo)
+    {
+        const int leader = __ffs(todo) - 1;
+        const int la = __shfl_sync(0xffffffffu, ca, leader), lb = __shfl_sync(0xffffffffu, cb, leader);
+        const bool in = active && ca == la && cb == lb;
+        const u32 g = __ballot_sync(0xffffffffu, in);
+        todo &= ~g;
+        if (in)
+        {
+            const int zmin = __reduce_min_sync(g, cc), zmax = __reduce_max_sync(g, cc);
+            const int x0 = max(0, la - d), x1 = min(m.cx, la + d + 1);
+            const int y0 = max(0, lb - d), y1 = min(m.cy, lb + d + 1);
+            const int z0 = max(0, zmin - d), z1 = min(m.cz, zmax + d + 1);
+            const int wz0 = max(0, cc - d), wz1 = min(m.cz, cc + d + 1);
+            for (int x = x0; x < x1; ++x)
+                for (int y = y0; y < y1; ++y)
+                {
+                    const u32 col = cell_linear(m, x, y, 0);
+                    const u32 rb = a.cell_offset[col + z0], re = a.cell_offset[col + z1];
+                    const u32 lo = a.cell_offset[col + wz0];
+                    const u32 win = a.cell_offset[col + wz1] - lo;
+#pragma unroll 4
+                    for (u32 k = rb; k < re; ++k)
+                    {
+                        const float4 xj = a.tar_pos[k];
+                        const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                        const float r2 = inv_h2 * fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                        bool hit = r2 < sure_in;
+                        if (!hit && r2 < sure_out) hit = within(xi, xj, a.inv_h, a.ks2);
+                        hit = hit && (k - lo) < win && !(INNER && k == t);
+                        if (hit)
+                        {
+                            if (MODE != 0)
+                            {
+                                const u64 pos = base + 32ull * c;
+                                if (c < limit && pos < capacity) index[pos] = k;
+                            }
+                            ++c;
+                        }
+                    }
+                }
+        }
+    }
+    if (MODE != 1 && active) count[t] = c;
+    if (MODE == 0)
+    {
+        u32 mx = warp_max_u32(c);
+        if ((threadIdx.x & 31) == 0 && active) slice[t >> 5] = mx * 32u;
+    }
+    if (MODE == 2)
+    {
+        u32 mx = warp_max_u32(c);
+        if ((threadIdx.x & 31) == 0 && active)
+        {
+            slice[t >> 5] = (t >> 5) * 32u * stride;
+            if (mx > 0) atomicMax(max_count, mx);
+        }
+    }
+}
+
 static int make_search(sphb200_context *ctx, const sphb200_search_t *s, SearchArgs *a)
 {
     SPH_CHECK_ARG(ctx, s->search_depth >= 1 && s->search_depth <= 4, "search depth out of range");
@@ -250,6 +372,12 @@ static int make_search(sphb200_context *ctx, const sphb200_search_t *s, SearchAr
     a->inv_h = 1.0f / s->kernel.h; // inv_h_ = 1 / max(src_h, tar_h), neighbor_method.hpp:73-76
     a->ks2 = s->kernel.kernel_size * s->kernel.kernel_size;
     a->depth = s->search_depth;
+    a->cell_ordered = s->cell_ordered;
+    if (s->cell_ordered && s->n_src)
+    {
+        SPH_CHECK_ARG(ctx, a->src_pos && a->tar_pos && a->cell_offset && !a->src_order, "cell_ordered search needs src_pos, tar_pos, cell_offset and no src_order");
+        return 0;
+    }
     if (s->n_src)
     {
         SPH_CHECK_ARG(ctx, (a->src_pos || (a->src_sorted_pos && a->src_order)) && a->tar_pos && a->cell_offset && a->particle_index,
@@ -265,6 +393,12 @@ static int launch_relation(sphb200_context *ctx, const SearchArgs &a, bool inner
 {
     unsigned g = sph_blocks(a.n_src, 128);
     bool sorted = a.tar_sorted_pos != nullptr;
+    if (a.cell_ordered)
+    {
+        if (inner) SPH_LAUNCH(ctx, (k_relation_ordered<true, MODE>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
+        else SPH_LAUNCH(ctx, (k_relation_ordered<false, MODE>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
+        return 0;
+    }
     if (inner && sorted) SPH_LAUNCH(ctx, (k_relation<true, true, MODE>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
     else if (inner) SPH_LAUNCH(ctx, (k_relation<true, false, MODE>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
     else if (sorted) SPH_LAUNCH(ctx, (k_relation<false, true, MODE>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
