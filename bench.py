@@ -146,10 +146,12 @@ def time_kernel(fn, iters, torch):
 
 
 def run_ours(args, rank, world, local_rank):
+    import ctypes as C
+
     import torch
     import torch.distributed as dist
-    from sphinxsys_b200 import cases
-    from sphinxsys_b200.solver import DamBreakCK
+    from sphinxsys_b200 import host
+    from sphinxsys_b200.host import DamBreakCK
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — libsphb200 has no CPU path (use --impl reference for the CPU oracle)")
@@ -157,37 +159,35 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    # weak scaling: every rank owns one z-slab of a tank stretched world x in z: rank-local
-    # dam break of the config-2 cross-section. TODO(multi-gpu): halo exchange between slabs.
-    case = cases.dam_break(dim=3, dp=args.dp)
-    solver = DamBreakCK(case, device_index=local_rank, fused_time_step=True, sort_interval=100)
+    # The C++ host layer builds the case itself (lattice generator + shape normals, include/sphinxsys_ck/dambreak_case.h)
+    # and runs the case-file loop; Python only times it. Weak scaling: every rank runs the config-2 cross-section
+    # (one z-slab of a tank stretched world x in z).
+    solver = DamBreakCK(None, dim=3, dp=args.dp, device_index=local_rank, fused_time_step=True, sort_interval=100, generate=True)
     solver.initialize()
-    n_fluid = case.n_fluid
+    n_fluid, n_wall = solver.n_fluid, solver.n_wall
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(args.warmup):
-        solver.step_outer()
+    solver.run_outer(args.warmup)
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = solver.ctx.launches
+    launches0 = solver.launches
     ac0 = solver.acoustic_steps
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     ev0.record()
-    for _ in range(args.steps):
-        solver.step_outer()
+    solver.run_outer(args.steps)  # K outer steps inside the C++ host loop (library work runs on the default stream)
     ev1.record()
     barrier()
     ms = ev0.elapsed_time(ev1)
     clocks = sampler.stop() if rank == 0 else None
     n_ac = solver.acoustic_steps - ac0
-    launches = solver.ctx.launches - launches0
+    launches = solver.launches - launches0
     t = torch.tensor([ms, float(n_ac)], dtype=torch.float64, device="cuda")
     if world > 1:
         tmax = t.clone()
@@ -203,13 +203,12 @@ def run_ours(args, rank, world, local_rank):
     # ---- roofline of the dominant kernel (2nd-half fused launch), timed live on the same state ----
     peak, peak_kind = measured_peak()
     dt = solver.last_acoustic_dt
-    a1 = solver.fluid_acoustic_step_1st_half
-    a2 = solver.fluid_acoustic_step_2nd_half
-    ms_a2 = time_kernel(lambda: a2.exec(dt * 1e-3), 20, torch)
-    ms_a1 = time_kernel(lambda: a1.exec(dt * 1e-3), 20, torch)
-    ms_sum = time_kernel(lambda: solver.fluid_density_summation.exec(), 10, torch)
-    ms_cl = time_kernel(lambda: solver.water_cell_linked_list.exec(), 10, torch)
-    ms_rel = time_kernel(lambda: solver.water_block_update_complex_relation.exec(), 5, torch)
+    ms_a2 = time_kernel(lambda: solver.exec("acoustic2", dt * 1e-3), 20, torch)
+    ms_a1 = time_kernel(lambda: solver.exec("acoustic1", dt * 1e-3), 20, torch)
+    ms_sum = time_kernel(lambda: solver.exec("density_summation"), 10, torch)
+    ms_cl = time_kernel(lambda: solver.exec("cell_list_fluid"), 10, torch)
+    ms_rel = time_kernel(lambda: solver.exec("relations"), 5, torch)
+    solver.exec("acoustic_dt_unprime")
     traffic = None
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
@@ -220,70 +219,58 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "hbm", "kernel": "k_a2 (AcousticStep2ndHalf: initialize+inner+wall+update+dt-max, one launch)",
                 "achieved": ach_a2, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach_a2 / peak,
                 "traffic": traffic, "algorithmic_bytes_per_launch": A_STEP_2ND * n_fluid, "launch_ms": ms_a2,
-                "note": "pair arithmetic (~80 neighbours x ~35 instr) is FP32-issue/L1 bound before it is HBM bound; see DESIGN.md §5",
+                "note": "pair arithmetic (~80 neighbours x ~40 instr) is FP32-issue/L1 bound before it is HBM bound; see DESIGN.md §5",
                 "other_kernels_ms": {"acoustic_1st_half(init+interact)": ms_a1, "density_summation": ms_sum,
-                                     "cell_list_build": ms_cl, "relation_build(inner+contact)": ms_rel}}
+                                     "cell_list_build+reorder": ms_cl, "relation_build(inner+contact)": ms_rel}}
 
     # ---- e2e: the same step driven from HOST buffers (pinned), H2D of the evolving state + D2H of the result ----
-    e2e = None
-    if True:
-        p = solver.water_block.particles
-        names = list(p.evolving)
-        host = {}
-        for nm in names:
-            tdev = p.vars[nm]
-            kind = p.kinds[nm]
-            if kind == "vec":
-                h = torch.from_numpy(p.download(nm)).pin_memory()
-            else:
-                h = tdev[: p.n].cpu().pin_memory()
-            host[nm] = h
-        out_names = ["Position", "Velocity", "Density"]
-        out_host = {nm: torch.empty((p.n, 3) if p.kinds[nm] == "vec" else (p.n,), dtype=torch.float32).pin_memory() for nm in out_names}
-        h2d = sum(h.numel() * h.element_size() for h in host.values())
-        d2h = sum(h.numel() * h.element_size() for h in out_host.values())
-        staging3 = torch.empty((p.n, 3), dtype=torch.float32, device="cuda")
+    in_names = ["Position", "VolumetricMeasure", "Velocity", "Mass", "ForcePrior", "Compression", "CompressionRate",
+                "VolumetricMeasureRef", "PreviousGravityForceCK"]
+    out_names = ["Position", "Velocity", "Density"]
 
-        def e2e_step():
-            for nm in names:
-                p.upload(nm, None, pinned=host[nm])
-            solver.water_block.posvol_dirty = True
-            solver._fused_valid = False
-            solver.water_cell_linked_list.exec()
-            solver.water_block_update_complex_relation.exec()
-            n = solver.step_outer()
-            for nm in out_names:
-                if p.kinds[nm] == "vec":
-                    solver.ctx.call("sphb200_vec4_to_vec3", __import__("ctypes").c_void_p(staging3.data_ptr()),
-                                    __import__("ctypes").c_void_p(p.vars[nm].data_ptr()), p.n,
-                                    __import__("ctypes").c_void_p(torch.cuda.current_stream().cuda_stream))
-                    out_host[nm].copy_(staging3, non_blocking=True)
-                else:
-                    out_host[nm].copy_(p.vars[nm][: p.n], non_blocking=True)
-            torch.cuda.synchronize()
-            return n
+    def pinned_like(name):
+        w = 3 if name in host.VEC_NAMES else 1
+        tns = torch.empty((n_fluid, w) if w == 3 else (n_fluid,), dtype=torch.float32).pin_memory()
+        return tns, tns.numpy()
 
-        e2e_step()
-        barrier()
-        k_e2e = max(3, min(args.steps, 10))
-        t0 = time.perf_counter()
-        n_ac_e2e = 0
-        for _ in range(k_e2e):
-            n_ac_e2e += e2e_step()
-        barrier()
-        sec = time.perf_counter() - t0
-        tt = torch.tensor([sec, float(n_ac_e2e)], dtype=torch.float64, device="cuda")
-        if world > 1:
-            tm = tt.clone()
-            dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-            ts = tt.clone()
-            dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-            sec, tot = float(tm[0]), n_fluid * float(ts[1])
-        else:
-            tot = n_fluid * float(n_ac_e2e)
-        e2e = {"value": tot / sec, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-               "steps": k_e2e, "note": "per step: H2D of all evolving variables from pinned host memory, cell-list + relation rebuild, "
-                                       "one outer step, D2H of Position/Velocity/Density"}
+    host_in = {nm: pinned_like(nm) for nm in in_names}
+    host_out = {nm: pinned_like(nm) for nm in out_names}
+    for nm in in_names:
+        solver.download(nm, out=host_in[nm][1])
+    h2d = sum(tn.numel() * 4 for tn, _ in host_in.values())
+    d2h = sum(tn.numel() * 4 for tn, _ in host_out.values())
+
+    def e2e_step():
+        for nm in in_names:
+            solver.upload(nm, host_in[nm][1])           # DiscreteVariable::synchronizeToDevice (reference order)
+        solver.exec("cell_list_fluid")
+        solver.exec("relations")
+        n = solver.step_outer()
+        for nm in out_names:
+            solver.download(nm, out=host_out[nm][1])    # DiscreteVariable::synchronizeWithDevice
+        return n
+
+    e2e_step()
+    barrier()
+    k_e2e = max(3, min(args.steps, 10))
+    t0 = time.perf_counter()
+    n_ac_e2e = 0
+    for _ in range(k_e2e):
+        n_ac_e2e += e2e_step()
+    barrier()
+    sec = time.perf_counter() - t0
+    tt = torch.tensor([sec, float(n_ac_e2e)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        tm = tt.clone()
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        ts = tt.clone()
+        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
+        sec, tot = float(tm[0]), n_fluid * float(ts[1])
+    else:
+        tot = n_fluid * float(n_ac_e2e)
+    e2e = {"value": tot / sec, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+           "steps": k_e2e, "note": "per step: H2D of all evolving variables from pinned host memory (reference particle order), "
+                                   "cell-list + relation rebuild, one outer step, D2H of Position/Velocity/Density"}
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample ----
     cpu = None
@@ -298,9 +285,9 @@ def run_ours(args, rank, world, local_rank):
             "metric": "particle-steps/sec (3D WCSPH dam break)", "value": value, "unit": "particle-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"3-D dam break WCSPH (tests_sycl dambreak geometry), dp={args.dp}: {n_fluid} fluid + {case.n_wall} wall "
+            "config": {"workload": f"3-D dam break WCSPH (tests_sycl dambreak geometry), dp={args.dp}: {n_fluid} fluid + {n_wall} wall "
                                    f"particles per GPU, AcousticRiemann + wall, Wendland C2 tabulated, sort every 100 outer steps",
-                       "n_fluid_per_gpu": n_fluid, "n_wall_per_gpu": case.n_wall, "acoustic_steps_per_outer": n_ac_per_outer,
+                       "n_fluid_per_gpu": n_fluid, "n_wall_per_gpu": n_wall, "acoustic_steps_per_outer": n_ac_per_outer,
                        "l2_policy": "working set (~2 GB incl. neighbour lists) larger than L2, no flush",
                        "parallelism": "1 GPU" if world == 1 else f"{world} z-slab replicas (halo exchange pending)"},
             "roofline": roofline,

@@ -151,6 +151,9 @@ typedef struct
     sphb200_cell_list_t tar_list;         /* target cell-linked list */
     int32_t is_inner;                     /* 1: Inner<> (exclude j == i), 0: Contact<> */
     int32_t search_depth;                 /* cells each side: 1 inner; contact: cell_linked_list.hpp:161-167 */
+    int32_t cell_ordered;                 /* 1: src_pos and tar_pos are STORED in the cell order of their own lists
+                                             (slot == particle id, particle_index == identity, src_order == NULL; see
+                                             sphb200_cell_list_build_reorder): selects the warp-uniform search */
 } sphb200_search_t;
 
 /* ---------------------------------------------------------------------------------------------------
@@ -169,9 +172,11 @@ int sphb200_free_device(void *ptr);
 int sphb200_free_host(void *ptr);
 int sphb200_copy_h2d(void *dst, const void *src, size_t bytes, void *stream); /* copyToDevice   :117-127 */
 int sphb200_copy_d2h(void *dst, const void *src, size_t bytes, void *stream); /* copyFromDevice :129-139 */
+int sphb200_copy_d2d(void *dst, const void *src, size_t bytes, void *stream);
 int sphb200_stream_sync(void *stream);
 int sphb200_fill_u32(sphb200_context_t *ctx, uint32_t *dst, uint32_t value, uint64_t n, void *stream);
 int sphb200_fill_f32(sphb200_context_t *ctx, float *dst, float value, uint64_t n, void *stream);
+int sphb200_iota_u32(sphb200_context_t *ctx, uint32_t *dst, uint64_t n, void *stream); /* dst[i] = i */
 /* Vecd layout conversion (device to device): packed 3-float AoS <-> float4 */
 int sphb200_vec3_to_vec4(sphb200_context_t *ctx, sphb200_vec4_t *dst, const float *src3, uint32_t n, void *stream);
 int sphb200_vec4_to_vec3(sphb200_context_t *ctx, float *dst3, const sphb200_vec4_t *src, uint32_t n, void *stream);
@@ -208,6 +213,15 @@ int sphb200_update_sorted_id(sphb200_context_t *ctx, const uint32_t *original_id
 /* UpdateCellLinkedList::exec: count -> scan -> fill (+ in-cell ordering); ref: update_cell_linked_list.hpp:40-106 */
 int sphb200_cell_list_build(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, const sphb200_vec4_t *pos, uint32_t n,
                             sphb200_cell_list_t list, void *stream);
+/* UpdateCellLinkedList::exec for a body whose storage FOLLOWS the cell order: builds the list from `pos`, then
+ * gathers `count` variables into their shadow buffers by the new permutation (dst_k[slot] = src_k[old index],
+ * elem_bytes as in sphb200_gather_multi; `pos` must be among them) and leaves particle_index == identity.
+ * Inside a cell particles are ordered by ascending sort_key[i] (unique keys, e.g. the reference particle id;
+ * NULL = the old index), so lists and summation order do not depend on the storage history. The caller swaps
+ * each variable with its shadow afterwards. */
+int sphb200_cell_list_build_reorder(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, const sphb200_vec4_t *pos,
+                                    uint32_t n, const uint32_t *sort_key, sphb200_cell_list_t list, int count,
+                                    void *const *dst, const void *const *src, const uint32_t *elem_bytes, void *stream);
 /* UpdateRelation<Inner<>>::exec and <Contact<>>::exec, split as the reference splits them so the host can
  * grow `index` between the two phases (update_body_relation.hpp:117-164, 240-288):
  *   *_count : fills rel.count and rel.slice_offset, returns the required capacity (entries) in *required_host
@@ -223,9 +237,12 @@ int sphb200_relation_fill(sphb200_context_t *ctx, const sphb200_search_t *search
  * sphb200_relation_count/_fill (nothing is silently dropped). */
 int sphb200_relation_build_fixed(sphb200_context_t *ctx, const sphb200_search_t *search, sphb200_relation_t rel,
                                  uint32_t stride, uint32_t *max_count_host, void *stream);
-/* SELL-32 (slot order) -> reference CSR indexed by particle id (particle_offset_[n+1], neighbor_index_[total]) */
-int sphb200_relation_export_csr(sphb200_context_t *ctx, sphb200_relation_t rel, uint32_t n, uint32_t *particle_offset,
-                                uint32_t *neighbor_index, uint64_t index_capacity, void *stream);
+/* SELL-32 (slot order) -> reference CSR indexed by particle id (particle_offset_[n+1], neighbor_index_[total]).
+ * src_ids: slot -> id of the source particle (NULL: rel.order, else identity); tar_ids: stored target index -> id
+ * (NULL: identity). Row order is preserved. */
+int sphb200_relation_export_csr(sphb200_context_t *ctx, sphb200_relation_t rel, uint32_t n, const uint32_t *src_ids,
+                                const uint32_t *tar_ids, uint32_t *particle_offset, uint32_t *neighbor_index,
+                                uint64_t index_capacity, void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * fluid dynamics

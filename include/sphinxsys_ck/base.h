@@ -1,0 +1,150 @@
+// sphinxsys_ck/base.h — data types, execution policies and the device execution instance of the C++ host layer.
+//
+// This header set keeps the spellings of the SPHinXsys "CK" API for the weakly-compressible SPH hot path so that a
+// case file written against the reference compiles against it with `par_device` mapped to the B200 library:
+// every `exec()` below ends in calls to the C ABI of libsphb200.so (include/sphb200.h). There is no host/TBB
+// implementation and no SYCL: instantiating an algorithm with another policy is a compile-time error.
+//
+// Reference (paths relative to /root/reference/src/shared):
+//   Real/Vecd/UnsignedInt ........ common/base_data_type.h:50-84,204-209
+//   execution policies ........... shared_ck/.../execution_policy.h:37-83
+//   ExecutionInstance ............ src_sycl/.../implementation_sycl.h:43-94 (one queue, global singleton)
+//   error convention ............. common/sphinxsys_variable.h:252-257 (message to std::cout, then exit(1))
+#ifndef SPHINXSYS_CK_BASE_H
+#define SPHINXSYS_CK_BASE_H
+
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <type_traits>
+#include <vector>
+
+#include "../sphb200.h"
+
+namespace SPH
+{
+using Real = float;           // base_data_type.h:50-53 (SPHINXSYS_USE_FLOAT, as the SYCL build sets)
+using UnsignedInt = uint32_t; // base_data_type.h:58-60
+constexpr Real TinyReal = 2.71051e-20f; // base_data_type.h:207
+constexpr Real Pi = Real(3.14159265358979323846);
+
+// Vecd: always three components; 2-D cases keep z == 0 (the device kernels are dimension-agnostic that way).
+struct Vecd
+{
+    Real x = 0, y = 0, z = 0;
+    Vecd() = default;
+    Vecd(Real a, Real b, Real c = 0) : x(a), y(b), z(c) {}
+    Real &operator[](int d) { return d == 0 ? x : (d == 1 ? y : z); }
+    Real operator[](int d) const { return d == 0 ? x : (d == 1 ? y : z); }
+    Vecd operator+(const Vecd &o) const { return Vecd(x + o.x, y + o.y, z + o.z); }
+    Vecd operator-(const Vecd &o) const { return Vecd(x - o.x, y - o.y, z - o.z); }
+    Vecd operator*(Real s) const { return Vecd(x * s, y * s, z * s); }
+    static Vecd Zero() { return Vecd(); }
+};
+using Vec3d = Vecd;
+using Vec2d = Vecd;
+inline Vecd operator*(Real s, const Vecd &v) { return v * s; }
+
+struct Matd // row-major 3x3
+{
+    Real m[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    static Matd Identity() { return Matd(); }
+};
+
+struct BoundingBoxd
+{
+    Vecd lower_, upper_;
+    BoundingBoxd() = default;
+    BoundingBoxd(const Vecd &lo, const Vecd &up) : lower_(lo), upper_(up) {}
+};
+
+// ---- execution policies: only ParallelDevicePolicy is implemented ----
+namespace execution
+{
+struct SequencedPolicy {};
+struct ParallelPolicy {};
+struct ParallelDevicePolicy {};
+inline constexpr SequencedPolicy seq{};
+inline constexpr ParallelPolicy par_host{};
+inline constexpr ParallelDevicePolicy par_device{};
+template <class Policy> constexpr void require_device_policy()
+{
+    static_assert(std::is_same<Policy, ParallelDevicePolicy>::value,
+                  "sphinxsys_ck on libsphb200 implements execution::ParallelDevicePolicy only (no CPU fallback)");
+}
+} // namespace execution
+using MainExecutionPolicy = execution::ParallelDevicePolicy;
+
+// ---- errors: the reference prints and exits; here the message is thrown so harnesses can report it ----
+class SphError : public std::runtime_error
+{
+  public:
+    explicit SphError(const std::string &what) : std::runtime_error(what) {}
+};
+
+// ---- one library context + stream per process and device (ExecutionInstance of the SYCL build) ----
+class ExecutionInstance
+{
+    sphb200_context_t *ctx_ = nullptr;
+    int device_ = 0;
+    void *stream_ = nullptr; // default stream: ordered with every other user of the default stream
+
+    ExecutionInstance() = default;
+
+  public:
+    ~ExecutionInstance()
+    {
+        if (ctx_) sphb200_context_destroy(ctx_);
+    }
+    static ExecutionInstance &get()
+    {
+        static ExecutionInstance instance;
+        return instance;
+    }
+    void setDevice(int device)
+    {
+        if (ctx_ && device != device_) throw SphError("ExecutionInstance: device already selected");
+        device_ = device;
+    }
+    sphb200_context_t *ctx()
+    {
+        if (!ctx_)
+        {
+            int rc = sphb200_context_create(device_, &ctx_);
+            if (rc != 0)
+                throw SphError("sphb200_context_create(device=" + std::to_string(device_) + ") failed with code " +
+                               std::to_string(rc) + ": a CUDA device is required (libsphb200 has no CPU path)");
+        }
+        return ctx_;
+    }
+    void *stream() const { return stream_; }
+    int device() const { return device_; }
+    void check(int rc, const char *what)
+    {
+        if (rc == 0) return;
+        std::string msg = std::string(what) + " failed: code " + std::to_string(rc) + ": " +
+                          (ctx_ ? sphb200_last_error_string(ctx_) : "");
+        std::cout << "\n Error: " << msg << std::endl; // reference style: report on std::cout ...
+        throw SphError(msg);                           // ... and stop (exception instead of exit(1))
+    }
+    void synchronize() { check(sphb200_stream_sync(stream_), "sphb200_stream_sync"); }
+    uint64_t launches() { return ctx_ ? sphb200_launch_count(ctx_) : 0; }
+};
+inline ExecutionInstance &execution_instance() { return ExecutionInstance::get(); }
+
+#define SPHCK_CALL(fn, ...) ::SPH::execution_instance().check(fn(::SPH::execution_instance().ctx(), __VA_ARGS__), #fn)
+
+// BaseDynamics<ReturnType>: base_dynamics.h (exec(dt) interface)
+template <class ReturnType = void> class BaseDynamics
+{
+  public:
+    virtual ~BaseDynamics() {}
+    virtual ReturnType exec(Real dt = 0.0) = 0;
+};
+} // namespace SPH
+#endif

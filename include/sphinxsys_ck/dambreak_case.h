@@ -1,0 +1,204 @@
+// sphinxsys_ck/dambreak_case.h — the 3-D (and 2-D) dam-break case assembled from the host-layer classes, sequenced
+// exactly like the reference case file tests/tests_sycl/3d_examples/test_3d_dambreak_sycl/dambreak.cpp:69-225
+// (definitions :98-136, preparation :152-160, main loop :183-225). examples/dambreak_ck.cpp drives it from main();
+// the Python test/bench harness drives the same object through sphinxsys_b200/csrc/host_api.cpp.
+#ifndef SPHINXSYS_CK_DAMBREAK_CASE_H
+#define SPHINXSYS_CK_DAMBREAK_CASE_H
+
+#include "sphinxsys_ck.h"
+
+namespace SPH
+{
+struct DamBreakParameters
+{
+    int dim = 3;
+    double dp = 0.05;          // global_resolution (dambreak.cpp:19)
+    double DL = 5.366, DH = 2.0, DW = 0.5, LL = 2.0, LH = 1.0, LW = 0.5; // dambreak.cpp:13-18
+    double rho0_f = 1.0, gravity_g = 1.0;                                // :22-23
+    bool correction = false;   // LinearCorrectionCK variants (the reference case file uses them; the hot path is without)
+    bool fused_time_step = true;
+    bool fused_regularization = true;
+    int sort_interval = 100;   // :217-220
+    static DamBreakParameters twoDimensional(double dp = 0.025)
+    {
+        DamBreakParameters p;
+        p.dim = 2; p.dp = dp; p.DH = 5.366; p.DW = 0; p.LW = 0; // tests/2d_examples/test_2d_dambreak/Dambreak.cpp:13-18
+        return p;
+    }
+};
+
+class WaterBlock : public ComplexShape
+{
+  public:
+    WaterBlock(const std::string &name, const DamBreakParameters &q) : ComplexShape(name)
+    {
+        double half[3] = {0.5 * q.LL, 0.5 * q.LH, 0.5 * q.LW};
+        add<GeometricShapeBox>(half, half);
+    }
+};
+class WallBoundary : public ComplexShape
+{
+  public:
+    WallBoundary(const std::string &name, const DamBreakParameters &q) : ComplexShape(name)
+    {
+        double BW = 4.0 * q.dp;
+        double half_in[3] = {0.5 * q.DL, 0.5 * q.DH, 0.5 * q.DW};
+        double half_out[3] = {0.5 * q.DL + BW, 0.5 * q.DH + BW, q.dim == 3 ? 0.5 * q.DW + BW : 0.0};
+        add<GeometricShapeBox>(half_in, half_out);
+        subtract<GeometricShapeBox>(half_in, half_in);
+    }
+};
+
+class DamBreakCK
+{
+  public:
+    using P = MainExecutionPolicy;
+    DamBreakParameters q_;
+    Real U_f_, c_f_;
+    SPHSystem sph_system;
+    FluidBody water_block;
+    SolidBody wall_boundary;
+    std::unique_ptr<Inner<>> water_block_inner;
+    std::unique_ptr<Contact<>> water_wall_contact;
+    std::unique_ptr<UpdateCellLinkedList<P, RealBody>> water_cell_linked_list, wall_cell_linked_list;
+    std::unique_ptr<UpdateRelation<P, Inner<>, Contact<>>> water_block_update_complex_relation;
+    std::unique_ptr<ParticleSortCK<P>> particle_sort;
+    Gravity gravity;
+    std::unique_ptr<StateDynamics<P, GravityForceCK<Gravity>>> constant_gravity;
+    std::unique_ptr<StateDynamics<P, fluid_dynamics::AdvectionStepSetup>> water_advection_step_setup;
+    std::unique_ptr<StateDynamics<P, fluid_dynamics::UpdateParticlePosition>> water_update_particle_position;
+    std::unique_ptr<InteractionDynamicsCK<P, LinearCorrectionMatrixComplex>> fluid_linear_correction_matrix;
+    std::unique_ptr<InteractionDynamicsBase> fluid_acoustic_step_1st_half, fluid_acoustic_step_2nd_half;
+    std::unique_ptr<InteractionDynamicsCK<P, fluid_dynamics::CompressionSummation<Inner<>, Contact<>>>> fluid_density_summation;
+    std::unique_ptr<StateDynamics<P, fluid_dynamics::DensityRegularization<SPHBody, WeaklyCompressibleFluid, FreeSurface>>> fluid_density_regularization;
+    std::unique_ptr<ReduceDynamicsCK<P, fluid_dynamics::AdvectionTimeStepCK>> fluid_advection_time_step;
+    std::unique_ptr<ReduceDynamicsCK<P, fluid_dynamics::AcousticTimeStepCK<WeaklyCompressibleFluid>>> fluid_acoustic_time_step;
+    std::unique_ptr<ReduceDynamicsCK<P, TotalMechanicalEnergyCK>> record_water_mechanical_energy;
+    SingleVariable<Real> *sv_physical_time = nullptr;
+    size_t number_of_iterations = 0, acoustic_steps = 0;
+    double physical_time = 0; // accumulated in double for reporting; the SingleVariable keeps the Real copy
+    Real last_acoustic_dt = 0, last_advection_dt = 0;
+
+    static BoundingBoxd caseBounds(const DamBreakParameters &q)
+    {
+        double BW = 4.0 * q.dp;
+        return BoundingBoxd(Vecd(Real(-BW), Real(-BW), q.dim == 3 ? Real(-BW) : Real(0)),
+                            Vecd(Real(q.DL + BW), Real(q.DH + BW), q.dim == 3 ? Real(q.DW + BW) : Real(0)));
+    }
+
+    // positions == nullptr: generate the lattice here (generateParticles<BaseParticles, Lattice>()); otherwise use the
+    // arrays handed over (packed xyz, reference order), e.g. produced by the same rule on the harness side.
+    explicit DamBreakCK(const DamBreakParameters &q, const std::vector<Vecd> *fluid_positions = nullptr,
+                        const std::vector<Vecd> *wall_positions = nullptr, const std::vector<Vecd> *wall_normals = nullptr,
+                        const BoundingBoxd *exact_system_bounds = nullptr)
+        : q_(q), U_f_(Real(2.0 * std::sqrt(q.gravity_g * q.LH))), c_f_(Real(10.0) * U_f_),
+          sph_system(caseBounds(q), Real(q.dp), q.dim),
+          water_block(sph_system, makeShared<WaterBlock>("WaterBody", q)),
+          wall_boundary(sph_system, makeShared<WallBoundary>("WallBoundary", q)),
+          gravity(Vecd(0, Real(-q.gravity_g), 0))
+    {
+        {
+            // system bounds = case bounds + 4 dp (sph_system.cpp:39), evaluated in double from the case file's double
+            // literals and rounded once to Real
+            double BW = 4.0 * q.dp, ext[3] = {q.DL, q.DH, q.DW};
+            BoundingBoxd sb;
+            for (int d = 0; d < q.dim; ++d)
+            {
+                sb.lower_[d] = Real(-BW - 4.0 * q.dp);
+                sb.upper_[d] = Real(ext[d] + BW + 4.0 * q.dp);
+            }
+            sph_system.setSystemDomainBoundsExact(exact_system_bounds ? *exact_system_bounds : sb);
+        }
+        Real vol = Real(std::pow(Real(q.dp), Real(q.dim)));
+        water_block.defineMatterMaterial<WeaklyCompressibleFluid>(Real(q.rho0_f), c_f_);
+        if (fluid_positions) water_block.generateParticlesFromPositions(*fluid_positions, vol);
+        else water_block.generateParticles<BaseParticles, Lattice>();
+        wall_boundary.defineMatterMaterial<Solid>();
+        if (wall_positions) wall_boundary.generateParticlesFromPositions(*wall_positions, vol);
+        else wall_boundary.generateParticles<BaseParticles, Lattice>();
+        if (wall_normals) wall_boundary.registerWallVariables(wall_normals);
+        else wall_boundary.computeNormalFromBodyShape(); // NormalFromBodyShapeCK, run on the host (dambreak.cpp:119,153)
+
+        water_block_inner.reset(new Inner<>(water_block));
+        water_wall_contact.reset(new Contact<>(water_block, {&wall_boundary}));
+        water_cell_linked_list.reset(new UpdateCellLinkedList<P, RealBody>(water_block));
+        wall_cell_linked_list.reset(new UpdateCellLinkedList<P, RealBody>(wall_boundary));
+        water_block_update_complex_relation.reset(new UpdateRelation<P, Inner<>, Contact<>>(*water_block_inner, *water_wall_contact));
+        particle_sort.reset(new ParticleSortCK<P>(water_block));
+        constant_gravity.reset(new StateDynamics<P, GravityForceCK<Gravity>>(water_block, gravity));
+        water_advection_step_setup.reset(new StateDynamics<P, fluid_dynamics::AdvectionStepSetup>(water_block));
+        water_update_particle_position.reset(new StateDynamics<P, fluid_dynamics::UpdateParticlePosition>(water_block));
+        using namespace fluid_dynamics;
+        if (q.correction)
+        {
+            fluid_linear_correction_matrix.reset(new InteractionDynamicsCK<P, LinearCorrectionMatrixComplex>(
+                DynamicsArgs(*water_block_inner, 0.5), *water_wall_contact));
+            fluid_acoustic_step_1st_half.reset(new InteractionDynamicsCK<P, AcousticStep1stHalfWithWallRiemannCorrectionCK>(*water_block_inner, *water_wall_contact));
+            auto *a2 = new InteractionDynamicsCK<P, AcousticStep2ndHalfWithWallRiemannCorrectionCK>(*water_block_inner, *water_wall_contact);
+            fluid_acoustic_step_2nd_half.reset(a2);
+            fluid_acoustic_time_step.reset(new ReduceDynamicsCK<P, AcousticTimeStepCK<WeaklyCompressibleFluid>>(water_block));
+            if (q.fused_time_step) a2->fuseTimeStepReduction(*fluid_acoustic_time_step);
+        }
+        else
+        {
+            fluid_acoustic_step_1st_half.reset(new InteractionDynamicsCK<P, AcousticStep1stHalfWithWallRiemannCK>(*water_block_inner, *water_wall_contact));
+            auto *a2 = new InteractionDynamicsCK<P, AcousticStep2ndHalfWithWallRiemannCK>(*water_block_inner, *water_wall_contact);
+            fluid_acoustic_step_2nd_half.reset(a2);
+            fluid_acoustic_time_step.reset(new ReduceDynamicsCK<P, AcousticTimeStepCK<WeaklyCompressibleFluid>>(water_block));
+            if (q.fused_time_step) a2->fuseTimeStepReduction(*fluid_acoustic_time_step);
+        }
+        fluid_density_summation.reset(new InteractionDynamicsCK<P, CompressionSummation<Inner<>, Contact<>>>(*water_block_inner, *water_wall_contact));
+        fluid_density_regularization.reset(new StateDynamics<P, DensityRegularization<SPHBody, WeaklyCompressibleFluid, FreeSurface>>(water_block));
+        if (q.fused_regularization) fluid_density_summation->addPostStateDynamics(*fluid_density_regularization);
+        fluid_advection_time_step.reset(new ReduceDynamicsCK<P, AdvectionTimeStepCK>(water_block, U_f_));
+        record_water_mechanical_energy.reset(new ReduceDynamicsCK<P, TotalMechanicalEnergyCK>(water_block, gravity));
+        sv_physical_time = sph_system.getSystemVariableByName<Real>("PhysicalTime");
+    }
+
+    // dambreak.cpp:152-160
+    void initialize()
+    {
+        constant_gravity->exec();
+        water_cell_linked_list->exec();
+        wall_cell_linked_list->exec();
+        water_block_update_complex_relation->exec();
+        fluid_acoustic_time_step->setPrimed(false);
+    }
+
+    // one advection step, dambreak.cpp:188-222; returns the number of acoustic sub-steps taken
+    int stepOuter()
+    {
+        fluid_density_summation->exec();
+        if (!q_.fused_regularization) fluid_density_regularization->exec();
+        water_advection_step_setup->exec();
+        Real advection_dt = fluid_advection_time_step->exec();
+        if (q_.correction) fluid_linear_correction_matrix->exec();
+        Real relaxation_time = 0, acoustic_dt = 0;
+        int n_inner = 0;
+        while (relaxation_time < advection_dt)
+        {
+            acoustic_dt = fluid_acoustic_time_step->exec();
+            fluid_acoustic_step_1st_half->exec(acoustic_dt);
+            fluid_acoustic_step_2nd_half->exec(acoustic_dt);
+            relaxation_time += acoustic_dt;
+            physical_time += acoustic_dt;
+            sv_physical_time->incrementValue(acoustic_dt);
+            ++n_inner;
+        }
+        acoustic_steps += n_inner;
+        water_update_particle_position->exec();
+        number_of_iterations++;
+        if (q_.sort_interval > 0 && number_of_iterations % q_.sort_interval == 0 && number_of_iterations != 1)
+        {
+            particle_sort->exec();
+            fluid_acoustic_time_step->setPrimed(false); // Force/ForcePrior pairing changed (see ParticleSortCK)
+        }
+        water_cell_linked_list->exec();
+        water_block_update_complex_relation->exec();
+        last_acoustic_dt = acoustic_dt;
+        last_advection_dt = advection_dt;
+        return n_inner;
+    }
+};
+} // namespace SPH
+#endif

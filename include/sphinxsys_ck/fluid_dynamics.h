@@ -1,0 +1,539 @@
+// sphinxsys_ck/fluid_dynamics.h — the algorithm drivers (StateDynamics / ReduceDynamicsCK / InteractionDynamicsCK)
+// and the local dynamics of the weakly-compressible fluid hot path, each ending in one C-ABI call.
+//
+// Reference (relative to /root/reference/src/shared/shared_ck/particle_dynamics unless noted):
+//   StateDynamics, ReduceDynamicsCK ......... simple_algorithms_ck.h:41-121
+//   InteractionDynamicsCK ................... interaction_algorithms_ck.{h,hpp,cpp} (init -> pre -> interact -> post -> update)
+//   GravityForceCK .......................... general_dynamics/force_prior_ck.{h,hpp}
+//   AdvectionStepSetup, UpdateParticlePosition, AdvectionTimeStepCK, AcousticTimeStepCK
+//                                             fluid_dynamics/fluid_time_step_ck.{h,hpp,cpp}
+//   CompressionSummation, DensityRegularization  fluid_dynamics/density_regularization.{h,hpp}
+//   AcousticStep1stHalf / 2ndHalf + aliases .... fluid_dynamics/acoustic_step_1st_half.{h,hpp}, acoustic_step_2nd_half.{h,hpp}
+//   Riemann solvers ......................... fluid_dynamics/riemann_solver/riemann_solver_ck.h:46-173
+//   LinearCorrectionMatrix .................. general_dynamics/kernel_correction_ck.{h,hpp}
+//   TotalMechanicalEnergyCK ................. general_dynamics/general_reduce_ck.h:41-96
+//
+// The closed set of supported type tuples is SURVEY.md §8a: Inner<OneLevel, Riemann, Correction> x Contact<Wall, same, same>.
+#ifndef SPHINXSYS_CK_FLUID_DYNAMICS_H
+#define SPHINXSYS_CK_FLUID_DYNAMICS_H
+
+#include "configuration.h"
+
+namespace SPH
+{
+// ---- type tags (spelled as in the reference) ----
+struct Base {};
+struct WithUpdate {};
+struct WithInitialization {};
+struct OneLevel {};
+struct Wall {};
+struct FreeSurface {};
+struct Internal {};
+struct NoKernelCorrectionCK { static constexpr int kind = 0; };
+struct LinearCorrectionCK { static constexpr int kind = 1; };
+namespace fluid_dynamics
+{
+struct NoRiemannSolverCK { static constexpr int kind = 0; };
+struct AcousticRiemannSolverCK { static constexpr int kind = 1; };
+struct DissipativeRiemannSolverCK { static constexpr int kind = 2; };
+} // namespace fluid_dynamics
+
+class Gravity
+{
+    Vecd g_;
+
+  public:
+    explicit Gravity(const Vecd &g, const Vecd &reference_position = Vecd()) : g_(g) { (void)reference_position; }
+    const Vecd &InducedAcceleration() const { return g_; }
+    void toArray(float out[3]) const { out[0] = g_.x; out[1] = g_.y; out[2] = g_.z; }
+};
+
+// DynamicsArgs(identifier, args...): interaction_algorithms_ck / base_local_dynamics.h
+template <class Identifier, typename... Args> struct DynamicsArgsT
+{
+    Identifier &identifier_;
+    std::tuple<Args...> others_;
+};
+template <class Identifier, typename... Args> DynamicsArgsT<Identifier, Args...> DynamicsArgs(Identifier &id, Args... args)
+{
+    return DynamicsArgsT<Identifier, Args...>{id, std::make_tuple(args...)};
+}
+
+// =========================================================================================================
+// algorithm drivers
+// =========================================================================================================
+template <class ExecutionPolicy, class UpdateType> class StateDynamics : public UpdateType, public BaseDynamics<void>
+{
+  public:
+    template <typename... Args> explicit StateDynamics(Args &&...args) : UpdateType(std::forward<Args>(args)...)
+    {
+        execution::require_device_policy<ExecutionPolicy>();
+    }
+    void exec(Real dt = 0.0) override { this->deviceUpdate(dt); }
+};
+
+template <class ExecutionPolicy, class ReduceType>
+class ReduceDynamicsCK : public ReduceType, public BaseDynamics<typename ReduceType::OutputType>
+{
+  public:
+    using OutputType = typename ReduceType::OutputType;
+    template <typename... Args> explicit ReduceDynamicsCK(Args &&...args) : ReduceType(std::forward<Args>(args)...)
+    {
+        execution::require_device_policy<ExecutionPolicy>();
+    }
+    OutputType exec(Real dt = 0.0) override { return this->deviceReduce(dt); }
+};
+
+class InteractionDynamicsBase : public BaseDynamics<void>
+{
+  protected:
+    std::vector<BaseDynamics<void> *> pre_processes_, post_processes_;
+
+  public:
+    // interaction_algorithms_ck.h: addPre/PostContactInteraction, addPostStateDynamics (by reference form)
+    InteractionDynamicsBase &addPreContactInteraction(BaseDynamics<void> &d) { pre_processes_.push_back(&d); return *this; }
+    InteractionDynamicsBase &addPostContactInteraction(BaseDynamics<void> &d) { post_processes_.push_back(&d); return *this; }
+    InteractionDynamicsBase &addPostStateDynamics(BaseDynamics<void> &d) { post_processes_.push_back(&d); return *this; }
+};
+
+template <class ExecutionPolicy, class InteractionType>
+class InteractionDynamicsCK : public InteractionType, public InteractionDynamicsBase
+{
+  public:
+    template <typename... Args> explicit InteractionDynamicsCK(Args &&...args) : InteractionType(std::forward<Args>(args)...)
+    {
+        execution::require_device_policy<ExecutionPolicy>();
+    }
+    // runAllSteps (interaction_algorithms_ck.cpp:6-34): [initialize] -> pre -> interact(inner, contacts) -> post -> [update].
+    // initialize/interact/update of one dynamics are fused inside the library wherever no neighbour reads the value
+    // being written; a post process the library can fold into the same launch is handed to deviceInteract().
+    void exec(Real dt = 0.0) override
+    {
+        for (auto *d : pre_processes_) d->exec(dt);
+        std::vector<BaseDynamics<void> *> remaining = this->deviceInteract(dt, post_processes_);
+        for (auto *d : remaining) d->exec(dt);
+    }
+};
+
+// =========================================================================================================
+// shared plumbing: the argument block of one fluid body (+ wall)
+// =========================================================================================================
+namespace fluid_dynamics
+{
+class FluidDynamicsBase
+{
+  protected:
+    SPHBody &sph_body_;
+    BaseParticles &particles_;
+    RelationBase *inner_ = nullptr, *contact_ = nullptr;
+    int riemann_ = 1, correction_ = 0, free_surface_ = 1;
+
+  public:
+    explicit FluidDynamicsBase(SPHBody &body) : sph_body_(body), particles_(body.getBaseParticles()) {}
+    FluidDynamicsBase(RelationBase &inner, RelationBase *contact)
+        : sph_body_(inner.source_), particles_(inner.source_.getBaseParticles()), inner_(&inner), contact_(contact) {}
+    SPHBody &getSPHBody() { return sph_body_; }
+
+  protected:
+    // AcousticStep constructor: acoustic_step_1st_half.hpp:13-39
+    void registerAcousticVariables()
+    {
+        BaseParticles &p = particles_;
+        p.registerStateVariable<Real>("Pressure");
+        p.registerStateVariable<Real>("Compression", Real(1));
+        p.registerStateVariable<Real>("CompressionRate");
+        p.registerStateVariable<Vecd>("Velocity");
+        p.registerStateVariable<Vecd>("Displacement");
+        p.registerStateVariable<Vecd>("Force");
+        p.registerStateVariable<Vecd>("ForcePrior");
+        p.addEvolvingVariable<Vecd>("Velocity");
+        p.addEvolvingVariable<Real>("Mass");
+        p.addEvolvingVariable<Vecd>("ForcePrior");
+        p.addEvolvingVariable<Real>("Compression");
+        p.addEvolvingVariable<Real>("CompressionRate");
+    }
+    // CompressionSummation constructor: density_regularization.hpp:14-27
+    void registerSummationVariables()
+    {
+        BaseParticles &p = particles_;
+        bool fresh = !p.hasVariable("VolumetricMeasureRef");
+        auto *ref = p.registerStateVariable<Real>("VolumetricMeasureRef");
+        if (fresh)
+        {
+            ExecutionInstance &ex = execution_instance();
+            ex.check(sphb200_copy_d2d(ref->deviceAddress(), p.deviceData<Real>("VolumetricMeasure"),
+                                      p.TotalRealParticles() * sizeof(Real), ex.stream()), "sphb200_copy_d2d");
+        }
+        p.registerStateVariable<Real>("CompressionSummation", Real(1));
+        p.registerStateVariable<Real>("Compression", Real(1));
+        p.addEvolvingVariable<Real>("VolumetricMeasureRef");
+    }
+    sphb200_fluid_view_t fluidView()
+    {
+        BaseParticles &p = particles_;
+        sphb200_fluid_view_t f;
+        std::memset(&f, 0, sizeof(f));
+        f.n = (uint32_t)p.TotalRealParticles();
+        f.pos = (sphb200_vec4_t *)p.deviceDataOrNull<Vecd>("Position");
+        f.vel = (sphb200_vec4_t *)p.deviceDataOrNull<Vecd>("Velocity");
+        f.dpos = (sphb200_vec4_t *)p.deviceDataOrNull<Vecd>("Displacement");
+        f.force = (sphb200_vec4_t *)p.deviceDataOrNull<Vecd>("Force");
+        f.force_prior = (sphb200_vec4_t *)p.deviceDataOrNull<Vecd>("ForcePrior");
+        f.vol = (float *)p.deviceDataOrNull<Real>("VolumetricMeasure");
+        f.mass = (float *)p.deviceDataOrNull<Real>("Mass");
+        f.rho = (float *)p.deviceDataOrNull<Real>("Density");
+        f.p = (float *)p.deviceDataOrNull<Real>("Pressure");
+        f.compression = (float *)p.deviceDataOrNull<Real>("Compression");
+        f.compression_rate = (float *)p.deviceDataOrNull<Real>("CompressionRate");
+        f.vol_ref = (float *)p.deviceDataOrNull<Real>("VolumetricMeasureRef");
+        f.compression_sum = (float *)p.deviceDataOrNull<Real>("CompressionSummation");
+        f.B = (float *)p.deviceDataOrNull<Matd>("LinearCorrectionMatrix");
+        f.posvol = (sphb200_vec4_t *)p.deviceDataOrNull<Vecd>("PosVol");
+        return f;
+    }
+    sphb200_fluid_t material()
+    {
+        WeaklyCompressibleFluid &fl = dynamic_cast<WeaklyCompressibleFluid &>(sph_body_.getBaseMaterial());
+        sphb200_fluid_t m;
+        m.rho0 = fl.rho0_;
+        m.c0 = fl.c0_;
+        m.riemann = riemann_;
+        m.correction = correction_;
+        m.limiter_coeff = Real(3.0); // riemann_solver_ck.h:97
+        m.free_surface = free_surface_;
+        return m;
+    }
+    sphb200_fluid_args_t fluidArgs()
+    {
+        sphb200_fluid_args_t a;
+        std::memset(&a, 0, sizeof(a));
+        sph_body_.refreshPosVol();
+        a.fluid = fluidView();
+        a.material = material();
+        if (inner_)
+        {
+            a.inner = inner_->view();
+            a.kernel = inner_->kernel_;
+        }
+        else
+            a.kernel = sph_body_.getSPHAdaptation().kernel_;
+        if (contact_ && contact_->target_.TotalRealParticles())
+        {
+            SPHBody &w = contact_->target_;
+            w.refreshPosVol();
+            BaseParticles &wp = w.getBaseParticles();
+            a.wall.n = (uint32_t)wp.TotalRealParticles();
+            a.wall.pos = (const sphb200_vec4_t *)wp.deviceData<Vecd>("Position");
+            a.wall.posvol = (const sphb200_vec4_t *)wp.deviceData<Vecd>("PosVol");
+            a.wall.vel_ave = (const sphb200_vec4_t *)wp.deviceDataOrNull<Vecd>("AverageVelocity");
+            a.wall.acc_ave = (const sphb200_vec4_t *)wp.deviceDataOrNull<Vecd>("AverageAcceleration");
+            a.wall.normal = (const sphb200_vec4_t *)wp.deviceDataOrNull<Vecd>("NormalDirection");
+            a.wall.vol_ref = (const float *)wp.deviceDataOrNull<Real>("VolumetricMeasureRef");
+            a.contact = contact_->view();
+        }
+        return a;
+    }
+};
+
+// ---- StateDynamics local dynamics ----
+class AdvectionStepSetup : public FluidDynamicsBase
+{
+  public:
+    explicit AdvectionStepSetup(SPHBody &body) : FluidDynamicsBase(body) { particles_.registerStateVariable<Vecd>("Displacement"); }
+    void deviceUpdate(Real)
+    {
+        sphb200_fluid_view_t f = fluidView();
+        SPHCK_CALL(sphb200_advection_setup, &f, execution_instance().stream());
+        sph_body_.setPosVolDirty();
+    }
+};
+class UpdateParticlePosition : public FluidDynamicsBase
+{
+  public:
+    explicit UpdateParticlePosition(SPHBody &body) : FluidDynamicsBase(body) { particles_.registerStateVariable<Vecd>("Displacement"); }
+    void deviceUpdate(Real)
+    {
+        sphb200_fluid_view_t f = fluidView();
+        SPHCK_CALL(sphb200_update_position, &f, execution_instance().stream());
+        sph_body_.setPosVolDirty();
+    }
+};
+class DensityRegularizationBase : public FluidDynamicsBase
+{
+  public:
+    using FluidDynamicsBase::FluidDynamicsBase;
+    int flowType() const { return free_surface_; }
+    void deviceUpdate(Real)
+    {
+        sphb200_fluid_args_t a = fluidArgs();
+        SPHCK_CALL(sphb200_density_regularization, &a, execution_instance().stream());
+    }
+};
+template <class BodyType, class FluidType, class FlowType> class DensityRegularization : public DensityRegularizationBase
+{
+  public:
+    explicit DensityRegularization(SPHBody &body) : DensityRegularizationBase(body)
+    {
+        free_surface_ = std::is_same<FlowType, FreeSurface>::value ? 1 : 0;
+        registerSummationVariables();
+    }
+};
+
+// ---- ReduceDynamicsCK local dynamics ----
+class AdvectionTimeStepCK : public FluidDynamicsBase
+{
+    Real u_ref_, cfl_, h_min_, reduced_ = 0;
+
+  public:
+    using OutputType = Real;
+    AdvectionTimeStepCK(SPHBody &body, Real U_ref, Real advectionCFL = Real(0.25))
+        : FluidDynamicsBase(body), u_ref_(U_ref), cfl_(advectionCFL), h_min_(body.getSPHAdaptation().MinimumSmoothingLength())
+    {
+        particles_.registerStateVariable<Vecd>("Velocity");
+    }
+    Real ReducedValue() const { return reduced_; }
+    Real deviceReduce(Real)
+    {
+        sphb200_fluid_view_t f = fluidView();
+        float dt = 0;
+        SPHCK_CALL(sphb200_advection_time_step, &f, h_min_, u_ref_, cfl_, &reduced_, &dt, execution_instance().stream());
+        return dt;
+    }
+};
+
+class AcousticTimeStepBase : public FluidDynamicsBase
+{
+  protected:
+    Real cfl_, h_min_, reduced_ = 0;
+    DeviceBuffer fused_slot_; // device float written by the fused 2nd-half launch
+    bool primed_ = false;
+
+  public:
+    using OutputType = Real;
+    AcousticTimeStepBase(SPHBody &body, Real acousticCFL) : FluidDynamicsBase(body), cfl_(acousticCFL), h_min_(body.getSPHAdaptation().MinimumSmoothingLength())
+    {
+        registerAcousticVariables();
+    }
+    Real ReducedValue() const { return reduced_; }
+    Real minimumSmoothingLength() const { return h_min_; }
+    // hooks used by AcousticStep2ndHalf when the reduction is folded into its launch
+    float *fusedSlot()
+    {
+        fused_slot_.ensure(64);
+        return fused_slot_.get<float>();
+    }
+    void setPrimed(bool v) { primed_ = v; }
+    Real deviceReduce(Real)
+    {
+        ExecutionInstance &ex = execution_instance();
+        if (primed_)
+        {
+            // same 4-byte device->host read the stand-alone reduction ends with (particle_iterators_sycl.h:80-105)
+            primed_ = false;
+            ex.check(sphb200_copy_d2h(&reduced_, fused_slot_.get(), sizeof(float), ex.stream()), "sphb200_copy_d2h");
+            ex.synchronize();
+            return cfl_ * h_min_ / (reduced_ + TinyReal); // FinishDynamics::Result, fluid_time_step_ck.hpp:31-36
+        }
+        sphb200_fluid_args_t a = fluidArgs();
+        float dt = 0;
+        SPHCK_CALL(sphb200_acoustic_time_step, &a, h_min_, cfl_, &reduced_, &dt, ex.stream());
+        return dt;
+    }
+};
+template <class FluidType = WeaklyCompressibleFluid> class AcousticTimeStepCK : public AcousticTimeStepBase
+{
+  public:
+    explicit AcousticTimeStepCK(SPHBody &body, Real acousticCFL = Real(0.6)) : AcousticTimeStepBase(body, acousticCFL) {}
+};
+
+// ---- InteractionDynamicsCK local dynamics ----
+template <typename... T> class CompressionSummation;
+template <> class CompressionSummation<Inner<>, Contact<>> : public FluidDynamicsBase
+{
+  public:
+    CompressionSummation(Inner<> &inner, Contact<> &contact) : FluidDynamicsBase(inner, &contact) { registerSummationVariables(); }
+    std::vector<BaseDynamics<void> *> deviceInteract(Real, const std::vector<BaseDynamics<void> *> &post)
+    {
+        // a DensityRegularization of the same body queued as post process is folded into the summation launch
+        int regularize = 0;
+        std::vector<BaseDynamics<void> *> remaining;
+        for (auto *d : post)
+        {
+            auto *reg = dynamic_cast<DensityRegularizationBase *>(d);
+            if (reg && &reg->getSPHBody() == &sph_body_ && !regularize)
+            {
+                regularize = 1;
+                free_surface_ = reg->flowType();
+            }
+            else
+                remaining.push_back(d);
+        }
+        sphb200_fluid_args_t a = fluidArgs();
+        SPHCK_CALL(sphb200_compression_summation, &a, regularize, execution_instance().stream());
+        return remaining;
+    }
+};
+template <> class CompressionSummation<Inner<>> : public FluidDynamicsBase
+{
+  public:
+    explicit CompressionSummation(Inner<> &inner) : FluidDynamicsBase(inner, nullptr) { registerSummationVariables(); }
+    std::vector<BaseDynamics<void> *> deviceInteract(Real, const std::vector<BaseDynamics<void> *> &post)
+    {
+        sphb200_fluid_args_t a = fluidArgs();
+        SPHCK_CALL(sphb200_compression_summation, &a, 0, execution_instance().stream());
+        return post;
+    }
+};
+
+// phase-granular access (initialize | interact + update), used by parity tests against the reference's phases
+class AcousticStep1stHalfPhases
+{
+  public:
+    virtual ~AcousticStep1stHalfPhases() {}
+    virtual void deviceInitialize(Real dt) = 0;
+    virtual void deviceInteractAndUpdate(Real dt) = 0;
+};
+
+template <class RiemannType, class CorrectionType>
+class AcousticStep1stHalfWithWall : public FluidDynamicsBase, public AcousticStep1stHalfPhases
+{
+  public:
+    AcousticStep1stHalfWithWall(Inner<> &inner, Contact<> &contact) : FluidDynamicsBase(inner, &contact)
+    {
+        riemann_ = RiemannType::kind;
+        correction_ = CorrectionType::kind;
+        registerAcousticVariables();
+        if (correction_) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity());
+    }
+    std::vector<BaseDynamics<void> *> deviceInteract(Real dt, const std::vector<BaseDynamics<void> *> &post)
+    {
+        sphb200_fluid_args_t a = fluidArgs();
+        SPHCK_CALL(sphb200_acoustic_1st_half, &a, dt, execution_instance().stream());
+        return post;
+    }
+    void deviceInitialize(Real dt) override
+    {
+        sphb200_fluid_args_t a = fluidArgs();
+        SPHCK_CALL(sphb200_acoustic_1st_half_initialize, &a, dt, execution_instance().stream());
+    }
+    void deviceInteractAndUpdate(Real dt) override
+    {
+        sphb200_fluid_args_t a = fluidArgs();
+        SPHCK_CALL(sphb200_acoustic_1st_half_interact, &a, dt, 1, execution_instance().stream());
+    }
+};
+
+template <class RiemannType, class CorrectionType> class AcousticStep2ndHalfWithWall : public FluidDynamicsBase
+{
+    AcousticTimeStepBase *fused_time_step_ = nullptr;
+
+  public:
+    AcousticStep2ndHalfWithWall(Inner<> &inner, Contact<> &contact) : FluidDynamicsBase(inner, &contact)
+    {
+        riemann_ = RiemannType::kind;
+        correction_ = CorrectionType::kind;
+        registerAcousticVariables();
+        if (correction_) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity());
+    }
+    // Fold the next AcousticTimeStepCK reduction into this launch (library extension: removes one pass over the
+    // particles per acoustic step; the reduced value is bit-identical to the stand-alone reduction).
+    void fuseTimeStepReduction(AcousticTimeStepBase &time_step) { fused_time_step_ = &time_step; }
+    void unfuseTimeStepReduction() { fused_time_step_ = nullptr; }
+    std::vector<BaseDynamics<void> *> deviceInteract(Real dt, const std::vector<BaseDynamics<void> *> &post)
+    {
+        ExecutionInstance &ex = execution_instance();
+        sphb200_fluid_args_t a = fluidArgs();
+        float *slot = nullptr;
+        Real h_min = sph_body_.getSPHAdaptation().MinimumSmoothingLength();
+        if (fused_time_step_)
+        {
+            slot = fused_time_step_->fusedSlot();
+            SPHCK_CALL(sphb200_fill_f32, slot, 0.0f, 1, ex.stream());
+            h_min = fused_time_step_->minimumSmoothingLength();
+        }
+        SPHCK_CALL(sphb200_acoustic_2nd_half, &a, dt, h_min, slot, ex.stream());
+        if (fused_time_step_) fused_time_step_->setPrimed(true);
+        return post;
+    }
+};
+
+// aliases, acoustic_step_1st_half.h:196-201 / acoustic_step_2nd_half.h:183-191
+using AcousticStep1stHalfWithWallRiemannCK = AcousticStep1stHalfWithWall<AcousticRiemannSolverCK, NoKernelCorrectionCK>;
+using AcousticStep2ndHalfWithWallRiemannCK = AcousticStep2ndHalfWithWall<AcousticRiemannSolverCK, NoKernelCorrectionCK>;
+using AcousticStep1stHalfWithWallRiemannCorrectionCK = AcousticStep1stHalfWithWall<AcousticRiemannSolverCK, LinearCorrectionCK>;
+using AcousticStep2ndHalfWithWallRiemannCorrectionCK = AcousticStep2ndHalfWithWall<AcousticRiemannSolverCK, LinearCorrectionCK>;
+using AcousticStep1stHalfWithWallNoRiemannCK = AcousticStep1stHalfWithWall<NoRiemannSolverCK, NoKernelCorrectionCK>;
+using AcousticStep2ndHalfWithWallNoRiemannCK = AcousticStep2ndHalfWithWall<NoRiemannSolverCK, NoKernelCorrectionCK>;
+using AcousticStep1stHalfWithWallDissipativeRiemannCK = AcousticStep1stHalfWithWall<DissipativeRiemannSolverCK, NoKernelCorrectionCK>;
+using AcousticStep2ndHalfWithWallDissipativeRiemannCK = AcousticStep2ndHalfWithWall<DissipativeRiemannSolverCK, NoKernelCorrectionCK>;
+} // namespace fluid_dynamics
+
+// ---- general dynamics ----
+template <class GravityType> class GravityForceCK : public fluid_dynamics::FluidDynamicsBase
+{
+    GravityType gravity_;
+
+  public:
+    GravityForceCK(SPHBody &body, const GravityType &gravity) : FluidDynamicsBase(body), gravity_(gravity)
+    {
+        // ForcePriorCK: force_prior_ck.cpp:13-14
+        particles_.registerStateVariable<Vecd>("ForcePrior");
+        particles_.registerStateVariable<Vecd>("PreviousGravityForceCK");
+        particles_.addEvolvingVariable<Vecd>("ForcePrior");
+        particles_.addEvolvingVariable<Vecd>("PreviousGravityForceCK");
+    }
+    void deviceUpdate(Real)
+    {
+        sphb200_fluid_view_t f = fluidView();
+        float g[3];
+        gravity_.toArray(g);
+        SPHCK_CALL(sphb200_gravity_force, &f, g, (sphb200_vec4_t *)particles_.deviceData<Vecd>("PreviousGravityForceCK"),
+                   execution_instance().stream());
+    }
+};
+
+class LinearCorrectionMatrixComplex : public fluid_dynamics::FluidDynamicsBase
+{
+    Real alpha_;
+
+  public:
+    LinearCorrectionMatrixComplex(DynamicsArgsT<Inner<>, double> args, Contact<> &contact)
+        : FluidDynamicsBase(args.identifier_, &contact), alpha_(Real(std::get<0>(args.others_)))
+    {
+        particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity());
+    }
+    LinearCorrectionMatrixComplex(Inner<> &inner, Contact<> &contact, Real alpha = Real(0))
+        : FluidDynamicsBase(inner, &contact), alpha_(alpha)
+    {
+        particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity());
+    }
+    std::vector<BaseDynamics<void> *> deviceInteract(Real, const std::vector<BaseDynamics<void> *> &post)
+    {
+        sphb200_fluid_args_t a = fluidArgs();
+        SPHCK_CALL(sphb200_linear_correction_matrix, &a, alpha_, execution_instance().stream());
+        return post;
+    }
+};
+
+class TotalMechanicalEnergyCK : public fluid_dynamics::FluidDynamicsBase
+{
+    Gravity gravity_;
+
+  public:
+    using OutputType = double;
+    TotalMechanicalEnergyCK(SPHBody &body, const Gravity &gravity) : FluidDynamicsBase(body), gravity_(gravity)
+    {
+        particles_.registerStateVariable<Vecd>("Velocity");
+    }
+    double deviceReduce(Real)
+    {
+        sphb200_fluid_view_t f = fluidView();
+        float g[3];
+        gravity_.toArray(g);
+        double e = 0;
+        SPHCK_CALL(sphb200_total_mechanical_energy, &f, g, &e, execution_instance().stream());
+        return e;
+    }
+};
+} // namespace SPH
+#endif

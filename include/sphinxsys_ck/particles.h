@@ -1,0 +1,536 @@
+// sphinxsys_ck/particles.h — DiscreteVariable / SingleVariable, BaseParticles, bodies and the SPHSystem.
+//
+// Storage model: every per-particle variable has ONE device array whose order follows the body's
+// cell-linked list ("slot order"); UpdateCellLinkedList re-establishes that order every time it runs by one fused
+// gather of all variables. The order the reference would have (ids fixed between ParticleSortCK calls) is kept as
+// the `ReferenceID` variable, and host synchronisation goes through it, so host arrays (`Data()`), I/O and parity
+// checks see exactly the reference's particle numbering.
+//
+// Reference (relative to /root/reference/src/shared):
+//   DiscreteVariable / SingleVariable ... common/sphinxsys_variable.h:50-378, src_sycl/.../sphinxsys_variable_sycl.hpp
+//   BaseParticles ....................... particles/base_particles.h:80-263, base_particles.cpp:33-36,84-96
+//   SPHBody / RealBody / FluidBody ...... bodies/base_body.h, bodies/solid_body.h, bodies/fluid_body.h
+//   materials ........................... materials/weakly_compressible_fluid.h:40-70, base_material.cpp:37-40,67-75
+//   SPHSystem ........................... sphinxsys_system/sph_system.h, sph_system.cpp:39
+#ifndef SPHINXSYS_CK_PARTICLES_H
+#define SPHINXSYS_CK_PARTICLES_H
+
+#include <cstring>
+#include <map>
+
+#include "geometry.h"
+
+namespace SPH
+{
+template <class T> struct DeviceType;
+template <> struct DeviceType<Real> { static constexpr uint32_t bytes = 4; };
+template <> struct DeviceType<UnsignedInt> { static constexpr uint32_t bytes = 4; };
+template <> struct DeviceType<int> { static constexpr uint32_t bytes = 4; };
+template <> struct DeviceType<Vecd> { static constexpr uint32_t bytes = 16; }; // float4 on the device
+template <> struct DeviceType<Matd> { static constexpr uint32_t bytes = 36; };
+
+inline void *deviceAllocate(size_t bytes)
+{
+    void *p = nullptr;
+    execution_instance().ctx(); // selects the device
+    int rc = sphb200_malloc_device(&p, bytes);
+    if (rc != 0) throw SphError("sphb200_malloc_device(" + std::to_string(bytes) + ") failed: " + std::to_string(rc));
+    return p;
+}
+
+// RAII device array
+class DeviceBuffer
+{
+    void *p_ = nullptr;
+    size_t bytes_ = 0;
+
+  public:
+    DeviceBuffer() = default;
+    explicit DeviceBuffer(size_t bytes) { reset(bytes); }
+    DeviceBuffer(const DeviceBuffer &) = delete;
+    DeviceBuffer &operator=(const DeviceBuffer &) = delete;
+    ~DeviceBuffer() { release(); }
+    void release()
+    {
+        if (p_) sphb200_free_device(p_);
+        p_ = nullptr;
+        bytes_ = 0;
+    }
+    void reset(size_t bytes)
+    {
+        release();
+        p_ = deviceAllocate(bytes ? bytes : 4);
+        bytes_ = bytes;
+    }
+    void ensure(size_t bytes) // grow without copy (DiscreteVariable::reallocateData semantics)
+    {
+        if (bytes > bytes_) reset(bytes);
+    }
+    void swap(DeviceBuffer &o)
+    {
+        std::swap(p_, o.p_);
+        std::swap(bytes_, o.bytes_);
+    }
+    template <class T = void> T *get() const { return (T *)p_; }
+    size_t bytes() const { return bytes_; }
+};
+
+class BaseParticles;
+
+class DiscreteVariableBase
+{
+  protected:
+    std::string name_;
+    size_t size_;        // allocated elements (particles bound + 1)
+    uint32_t elem_bytes_; // device element size
+    DeviceBuffer dev_, shadow_;
+    BaseParticles *particles_ = nullptr;
+
+  public:
+    DiscreteVariableBase(const std::string &name, size_t size, uint32_t elem_bytes, BaseParticles *particles)
+        : name_(name), size_(size), elem_bytes_(elem_bytes), dev_(size * elem_bytes), particles_(particles) {}
+    virtual ~DiscreteVariableBase() {}
+    const std::string &Name() const { return name_; }
+    size_t getDataSize() const { return size_; }
+    uint32_t deviceElementBytes() const { return elem_bytes_; }
+    void *deviceAddress() const { return dev_.get(); }
+    void *shadowAddress()
+    {
+        shadow_.ensure(size_ * elem_bytes_);
+        return shadow_.get();
+    }
+    void swapWithShadow() { dev_.swap(shadow_); }
+    void fillDeviceZero()
+    {
+        std::vector<char> z(size_ * elem_bytes_, 0);
+        execution_instance().check(sphb200_copy_h2d(dev_.get(), z.data(), z.size(), execution_instance().stream()), "copy_h2d");
+        execution_instance().synchronize();
+    }
+};
+
+template <class T> class DiscreteVariable : public DiscreteVariableBase
+{
+    std::vector<T> host_; // reference particle order; valid after synchronizeWithDevice()
+
+  public:
+    DiscreteVariable(const std::string &name, size_t size, BaseParticles *particles)
+        : DiscreteVariableBase(name, size, DeviceType<T>::bytes, particles) {}
+    // host view (created on demand), reference order
+    T *Data()
+    {
+        if (host_.size() != size_) host_.assign(size_, T());
+        return host_.data();
+    }
+    // device view: Real*/UnsignedInt* as is, Vecd as sphb200_vec4_t*, Matd as 9 packed floats
+    template <class Policy> void *DelegatedData(const Policy &)
+    {
+        execution::require_device_policy<Policy>();
+        return deviceAddress();
+    }
+    void synchronizeToDevice();   // host (reference order) -> device (slot order)
+    void synchronizeWithDevice(); // device -> host
+};
+
+// SingleVariable<T>: a named scalar living on the host, mirrored to the device on demand (sphinxsys_variable.h:50-120)
+template <class T> class SingleVariable
+{
+    std::string name_;
+    T value_;
+
+  public:
+    SingleVariable(const std::string &name, const T &v) : name_(name), value_(v) {}
+    const std::string &Name() const { return name_; }
+    T getValue() const { return value_; }
+    void setValue(const T &v) { value_ = v; }
+    void incrementValue(const T &v) { value_ += v; }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+class BaseParticles
+{
+    size_t total_real_particles_, particles_bound_;
+    std::map<std::string, std::unique_ptr<DiscreteVariableBase>> all_variables_;
+    std::vector<DiscreteVariableBase *> ordered_; // registration order (the order the fused gather uses)
+    std::vector<DiscreteVariableBase *> evolving_variables_;
+    std::vector<std::string> derived_;            // variables rebuilt after a reorder instead of being gathered
+    DiscreteVariable<UnsignedInt> *dv_reference_id_ = nullptr;
+    DeviceBuffer inverse_, staging_;
+    uint64_t storage_version_ = 1, inverse_version_ = 0;
+    bool identity_order_ = true; // ReferenceID == iota (no reorder happened yet)
+
+  public:
+    explicit BaseParticles(size_t n) : total_real_particles_(n), particles_bound_(n)
+    {
+        dv_reference_id_ = registerStateVariable<UnsignedInt>("ReferenceID");
+        SPHCK_CALL(sphb200_iota_u32, (uint32_t *)dv_reference_id_->deviceAddress(), n + 1, execution_instance().stream());
+    }
+    size_t TotalRealParticles() const { return total_real_particles_; }
+    size_t ParticlesBound() const { return particles_bound_; }
+    uint64_t storageVersion() const { return storage_version_; }
+
+    template <class T> DiscreteVariable<T> *registerStateVariable(const std::string &name, const T &init = T())
+    {
+        auto it = all_variables_.find(name);
+        if (it != all_variables_.end())
+        {
+            auto *v = dynamic_cast<DiscreteVariable<T> *>(it->second.get());
+            if (!v) throw SphError("registerStateVariable: '" + name + "' already registered with another type");
+            return v;
+        }
+        auto *v = new DiscreteVariable<T>(name, particles_bound_ + 1, this);
+        all_variables_[name].reset(v);
+        ordered_.push_back(v);
+        fillDevice(v, init);
+        return v;
+    }
+    template <class T> DiscreteVariable<T> *getVariableByName(const std::string &name)
+    {
+        auto it = all_variables_.find(name);
+        DiscreteVariable<T> *v = it == all_variables_.end() ? nullptr : dynamic_cast<DiscreteVariable<T> *>(it->second.get());
+        if (!v)
+        {
+            // sphinxsys_variable.h:252-257
+            std::cout << "\n Error: the variable '" << name << "' is not registered!" << std::endl;
+            throw SphError("the variable '" + name + "' is not registered");
+        }
+        return v;
+    }
+    bool hasVariable(const std::string &name) const { return all_variables_.count(name) != 0; }
+    template <class T> void *deviceData(const std::string &name) { return getVariableByName<T>(name)->deviceAddress(); }
+    template <class T> void *deviceDataOrNull(const std::string &name)
+    {
+        return hasVariable(name) ? getVariableByName<T>(name)->deviceAddress() : nullptr;
+    }
+    template <class T> void addEvolvingVariable(const std::string &name)
+    {
+        DiscreteVariableBase *v = getVariableByName<T>(name);
+        for (auto *e : evolving_variables_)
+            if (e == v) return;
+        evolving_variables_.push_back(v);
+    }
+    const std::vector<DiscreteVariableBase *> &EvolvingVariables() const { return evolving_variables_; }
+    bool isEvolving(const DiscreteVariableBase *v) const
+    {
+        for (auto *e : evolving_variables_)
+            if (e == v) return true;
+        return false;
+    }
+    // a derived variable is recomputed by its owner after a storage reorder (it is skipped by the gather)
+    void markDerived(const std::string &name) { derived_.push_back(name); }
+    std::vector<DiscreteVariableBase *> reorderedVariables() const
+    {
+        std::vector<DiscreteVariableBase *> out;
+        for (auto *v : ordered_)
+        {
+            bool skip = false;
+            for (auto &d : derived_)
+                if (d == v->Name()) skip = true;
+            if (!skip) out.push_back(v);
+        }
+        return out;
+    }
+    void storageReordered()
+    {
+        ++storage_version_;
+        identity_order_ = false;
+    }
+    uint32_t *referenceID() { return (uint32_t *)dv_reference_id_->deviceAddress(); }
+    DiscreteVariable<UnsignedInt> *referenceIDVariable() { return dv_reference_id_; }
+
+    // slot of reference id r (inverse of ReferenceID), cached per storage version
+    uint32_t *inverseReferenceID()
+    {
+        uint32_t n = (uint32_t)total_real_particles_;
+        inverse_.ensure((n + 1) * sizeof(uint32_t));
+        if (inverse_version_ != storage_version_)
+        {
+            SPHCK_CALL(sphb200_update_sorted_id, referenceID(), inverse_.get<uint32_t>(), n, execution_instance().stream());
+            inverse_version_ = storage_version_;
+        }
+        return inverse_.get<uint32_t>();
+    }
+
+    // ---- host <-> device, through the reference order ----
+    template <class T> void upload(DiscreteVariable<T> *v, const T *host)
+    {
+        uint32_t n = (uint32_t)total_real_particles_;
+        if (n == 0) return;
+        ExecutionInstance &ex = execution_instance();
+        const uint32_t eb = v->deviceElementBytes();
+        const size_t host_bytes = sizeof(T) * (size_t)n;
+        const size_t raw_bytes = ((host_bytes + 63) / 64) * 64;
+        staging_.ensure(raw_bytes + (size_t)eb * n + 64);
+        char *raw = staging_.get<char>();
+        char *conv = raw + raw_bytes;
+        ex.check(sphb200_copy_h2d(raw, host, host_bytes, ex.stream()), "sphb200_copy_h2d");
+        void *src = raw;
+        if (std::is_same<T, Vecd>::value)
+        {
+            SPHCK_CALL(sphb200_vec3_to_vec4, (sphb200_vec4_t *)conv, (const float *)raw, n, ex.stream());
+            src = conv;
+        }
+        if (identity_order_)
+            ex.check(sphb200_copy_d2d(v->deviceAddress(), src, (size_t)eb * n, ex.stream()), "sphb200_copy_d2d");
+        else
+        {
+            void *dst[1] = {v->deviceAddress()};
+            const void *srcs[1] = {src};
+            uint32_t bytes[1] = {eb};
+            SPHCK_CALL(sphb200_gather_multi, 1, dst, srcs, bytes, referenceID(), n, ex.stream());
+        }
+        ex.synchronize(); // the host buffer may be pageable
+    }
+    template <class T> void download(DiscreteVariable<T> *v, T *host)
+    {
+        uint32_t n = (uint32_t)total_real_particles_;
+        if (n == 0) return;
+        ExecutionInstance &ex = execution_instance();
+        const uint32_t eb = v->deviceElementBytes();
+        const size_t a = (((size_t)eb * n + 63) / 64) * 64;
+        staging_.ensure(a + sizeof(T) * (size_t)n + 64);
+        char *ordered = staging_.get<char>();
+        char *packed = ordered + a;
+        const void *src = v->deviceAddress();
+        if (!identity_order_)
+        {
+            void *dst[1] = {ordered};
+            const void *srcs[1] = {src};
+            uint32_t bytes[1] = {eb};
+            SPHCK_CALL(sphb200_gather_multi, 1, dst, srcs, bytes, inverseReferenceID(), n, ex.stream());
+            src = ordered;
+        }
+        if (std::is_same<T, Vecd>::value)
+        {
+            SPHCK_CALL(sphb200_vec4_to_vec3, (float *)packed, (const sphb200_vec4_t *)src, n, ex.stream());
+            src = packed;
+        }
+        ex.check(sphb200_copy_d2h(host, src, sizeof(T) * (size_t)n, ex.stream()), "sphb200_copy_d2h");
+        ex.synchronize();
+    }
+
+  private:
+    template <class T> void fillDevice(DiscreteVariable<T> *v, const T &init)
+    {
+        std::vector<T> h(v->getDataSize(), init);
+        size_t n_keep = total_real_particles_;
+        // fill all allocated elements (including the padding entry) directly, order-independent
+        ExecutionInstance &ex = execution_instance();
+        if (std::is_same<T, Vecd>::value)
+        {
+            std::vector<float> h4(4 * h.size());
+            for (size_t i = 0; i < h.size(); ++i)
+            {
+                const Vecd &p = *(const Vecd *)&h[i];
+                h4[4 * i] = p.x; h4[4 * i + 1] = p.y; h4[4 * i + 2] = p.z; h4[4 * i + 3] = 0;
+            }
+            ex.check(sphb200_copy_h2d(v->deviceAddress(), h4.data(), h4.size() * 4, ex.stream()), "sphb200_copy_h2d");
+            ex.synchronize();
+        }
+        else
+        {
+            ex.check(sphb200_copy_h2d(v->deviceAddress(), h.data(), h.size() * sizeof(T), ex.stream()), "sphb200_copy_h2d");
+            ex.synchronize();
+        }
+        (void)n_keep;
+    }
+};
+
+template <class T> void DiscreteVariable<T>::synchronizeToDevice() { particles_->upload(this, Data()); }
+template <class T> void DiscreteVariable<T>::synchronizeWithDevice() { particles_->download(this, Data()); }
+
+// ---------------------------------------------------------------------------------------------------------
+// materials
+// ---------------------------------------------------------------------------------------------------------
+class BaseMaterial
+{
+  public:
+    virtual ~BaseMaterial() {}
+    virtual Real ReferenceDensity() const = 0;
+};
+class WeaklyCompressibleFluid : public BaseMaterial
+{
+  public:
+    Real rho0_, c0_, p0_;
+    WeaklyCompressibleFluid(Real rho0, Real c0) : rho0_(rho0), c0_(c0), p0_(rho0 * c0 * c0) {}
+    Real ReferenceDensity() const override { return rho0_; }
+    Real ReferenceSoundSpeed() const { return c0_; }
+};
+class Solid : public BaseMaterial
+{
+  public:
+    Real rho0_;
+    explicit Solid(Real rho0 = 1.0) : rho0_(rho0) {}
+    Real ReferenceDensity() const override { return rho0_; }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// SPHSystem and bodies
+// ---------------------------------------------------------------------------------------------------------
+class SPHBody;
+struct Lattice {};
+
+class SPHSystem
+{
+  public:
+    BoundingBoxd system_domain_bounds_;
+    Real global_resolution_;
+    int dim_;
+    std::vector<SPHBody *> bodies_;
+    std::map<std::string, std::unique_ptr<SingleVariable<Real>>> system_variables_;
+    // sph_system.cpp:39: the case bounds are expanded by 4 dp on every side
+    SPHSystem(const BoundingBoxd &case_bounds, Real resolution, int dim = 3) : global_resolution_(resolution), dim_(dim)
+    {
+        system_domain_bounds_ = case_bounds;
+        for (int d = 0; d < dim; ++d)
+        {
+            // evaluated in double and rounded once, as the case files' double literals are
+            system_domain_bounds_.lower_[d] = Real(double(case_bounds.lower_[d]) - 4.0 * double(resolution));
+            system_domain_bounds_.upper_[d] = Real(double(case_bounds.upper_[d]) + 4.0 * double(resolution));
+        }
+        system_variables_["PhysicalTime"].reset(new SingleVariable<Real>("PhysicalTime", 0));
+    }
+    void setSystemDomainBoundsExact(const BoundingBoxd &b) { system_domain_bounds_ = b; }
+    template <class T> SingleVariable<T> *getSystemVariableByName(const std::string &name)
+    {
+        auto it = system_variables_.find(name);
+        if (it == system_variables_.end()) throw SphError("system variable '" + name + "' not found");
+        return it->second.get();
+    }
+    int Dimensions() const { return dim_; }
+};
+
+class CellLinkedList;
+
+class SPHBody
+{
+  protected:
+    SPHSystem &sph_system_;
+    std::string name_;
+    std::shared_ptr<ComplexShape> shape_;
+    std::unique_ptr<SPHAdaptation> adaptation_;
+    std::unique_ptr<BaseParticles> particles_;
+    std::unique_ptr<BaseMaterial> material_;
+    std::unique_ptr<CellLinkedList> cell_linked_list_;
+    bool posvol_dirty_ = true;
+    bool cell_ordered_ = false;
+
+  public:
+    SPHBody(SPHSystem &system, std::shared_ptr<ComplexShape> shape)
+        : sph_system_(system), name_(shape->Name()), shape_(shape),
+          adaptation_(new SPHAdaptation(system.global_resolution_, system.dim_))
+    {
+        system.bodies_.push_back(this);
+    }
+    SPHBody(SPHSystem &system, const std::string &name)
+        : sph_system_(system), name_(name), adaptation_(new SPHAdaptation(system.global_resolution_, system.dim_))
+    {
+        system.bodies_.push_back(this);
+    }
+    virtual ~SPHBody();
+    const std::string &Name() const { return name_; }
+    SPHSystem &getSPHSystem() { return sph_system_; }
+    SPHAdaptation &getSPHAdaptation() { return *adaptation_; }
+    BaseParticles &getBaseParticles()
+    {
+        if (!particles_) throw SphError("body '" + name_ + "': particles not generated");
+        return *particles_;
+    }
+    BaseMaterial &getBaseMaterial() { return *material_; }
+    ComplexShape &getInitialShape() { return *shape_; }
+    size_t TotalRealParticles() { return getBaseParticles().TotalRealParticles(); }
+    CellLinkedList &getCellLinkedList();
+    template <class MaterialType, typename... Args> MaterialType *defineMatterMaterial(Args &&...args)
+    {
+        MaterialType *m = new MaterialType(std::forward<Args>(args)...);
+        material_.reset(m);
+        return m;
+    }
+    // generateParticles<BaseParticles, Lattice>(): lattice points inside the body shape
+    template <class ParticlesType, class Generator> void generateParticles()
+    {
+        std::vector<Vecd> pos = generateLattice(*shape_, sph_system_.system_domain_bounds_, sph_system_.global_resolution_, sph_system_.dim_);
+        Real vol = Real(std::pow(sph_system_.global_resolution_, Real(sph_system_.dim_)));
+        generateParticlesFromPositions(pos, vol);
+    }
+    // positions handed over by the caller (e.g. a reload file): base_particles.cpp:33-36, base_material.cpp:37-40
+    void generateParticlesFromPositions(const std::vector<Vecd> &pos, Real vol)
+    {
+        size_t n = pos.size();
+        particles_.reset(new BaseParticles(n));
+        BaseParticles &p = *particles_;
+        auto *dv_pos = p.registerStateVariable<Vecd>("Position");
+        auto *dv_vol = p.registerStateVariable<Real>("VolumetricMeasure", vol);
+        p.registerStateVariable<Vecd>("PosVol"); // derived gather record (x, y, z, Vol)
+        p.markDerived("PosVol");
+        Real rho0 = material_ ? material_->ReferenceDensity() : Real(1);
+        p.registerStateVariable<Real>("Density", rho0);
+        p.registerStateVariable<Real>("Mass", rho0 * vol);
+        auto *dv_oid = p.registerStateVariable<UnsignedInt>("OriginalID");
+        SPHCK_CALL(sphb200_iota_u32, (uint32_t *)dv_oid->deviceAddress(), n + 1, execution_instance().stream());
+        p.addEvolvingVariable<Vecd>("Position");
+        p.addEvolvingVariable<Real>("VolumetricMeasure");
+        p.addEvolvingVariable<UnsignedInt>("OriginalID");
+        if (n) p.upload(dv_pos, pos.data());
+        (void)dv_vol;
+        posvol_dirty_ = true;
+    }
+    // (x, y, z, Vol) gather record; refreshed lazily whenever Position or VolumetricMeasure changed
+    void setPosVolDirty() { posvol_dirty_ = true; }
+    void refreshPosVol()
+    {
+        if (!posvol_dirty_) return;
+        BaseParticles &p = getBaseParticles();
+        SPHCK_CALL(sphb200_pack_posvol, (sphb200_vec4_t *)p.deviceData<Vecd>("PosVol"),
+                   (const sphb200_vec4_t *)p.deviceData<Vecd>("Position"), (const float *)p.deviceData<Real>("VolumetricMeasure"),
+                   (uint32_t)p.TotalRealParticles(), execution_instance().stream());
+        posvol_dirty_ = false;
+    }
+    bool isCellOrdered() const { return cell_ordered_; }
+    void setCellOrdered(bool v) { cell_ordered_ = v; }
+};
+using RealBody = SPHBody;
+
+class FluidBody : public SPHBody
+{
+  public:
+    using SPHBody::SPHBody;
+    // FluidBody water_block(sph_system, initial_water_block): the shape object is copied (dambreak.cpp:80-81)
+    template <class ShapeType, typename = typename std::enable_if<std::is_base_of<ComplexShape, ShapeType>::value>::type>
+    FluidBody(SPHSystem &system, const ShapeType &shape) : SPHBody(system, std::shared_ptr<ComplexShape>(new ShapeType(shape))) {}
+    WeaklyCompressibleFluid &getFluid() { return dynamic_cast<WeaklyCompressibleFluid &>(getBaseMaterial()); }
+};
+
+class SolidBody : public SPHBody
+{
+  public:
+    using SPHBody::SPHBody;
+    // Solid::AverageVelocity/AverageAcceleration are registered on demand by Interaction<Wall>
+    // (base_material.cpp:67-75, interaction_ck.hpp:79-91); a static wall leaves them unregistered (== 0).
+    void registerWallVariables(const std::vector<Vecd> *normals = nullptr)
+    {
+        BaseParticles &p = getBaseParticles();
+        auto *dv_n = p.registerStateVariable<Vecd>("NormalDirection");
+        auto *dv_vol = p.getVariableByName<Real>("VolumetricMeasure");
+        auto *dv_ref = p.registerStateVariable<Real>("VolumetricMeasureRef");
+        size_t n = p.TotalRealParticles();
+        ExecutionInstance &ex = execution_instance();
+        ex.check(sphb200_copy_d2d(dv_ref->deviceAddress(), dv_vol->deviceAddress(), n * sizeof(Real), ex.stream()), "sphb200_copy_d2d");
+        if (normals && n) p.upload(dv_n, normals->data());
+    }
+    // NormalFromBodyShapeCK (host-side in the reference case file: StateDynamics<ParallelPolicy, ...>)
+    void computeNormalFromBodyShape()
+    {
+        BaseParticles &p = getBaseParticles();
+        auto *dv_pos = p.getVariableByName<Vecd>("Position");
+        dv_pos->synchronizeWithDevice();
+        size_t n = p.TotalRealParticles();
+        std::vector<Vecd> normals(n);
+        for (size_t i = 0; i < n; ++i) normals[i] = shape_->directionToSurface(dv_pos->Data()[i], sph_system_.dim_);
+        registerWallVariables(&normals);
+    }
+};
+
+inline std::shared_ptr<ComplexShape> makeSharedShape(ComplexShape *s) { return std::shared_ptr<ComplexShape>(s); }
+template <class T, typename... Args> std::shared_ptr<T> makeShared(Args &&...args) { return std::make_shared<T>(std::forward<Args>(args)...); }
+} // namespace SPH
+#endif

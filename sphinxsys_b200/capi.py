@@ -59,7 +59,7 @@ class RelationT(C.Structure):
 class SearchT(C.Structure):
     _fields_ = [("tar_mesh", MeshT), ("kernel", KernelT), ("src_pos", _P), ("n_src", C.c_uint32), ("src_order", _P),
                 ("src_sorted_pos", _P), ("tar_pos", _P), ("tar_list", CellListT), ("is_inner", C.c_int32),
-                ("search_depth", C.c_int32)]
+                ("search_depth", C.c_int32), ("cell_ordered", C.c_int32)]
 
 
 class FluidArgs(C.Structure):
@@ -82,9 +82,11 @@ SYMBOLS = {
     "sphb200_free_host": (_I, [_P]),
     "sphb200_copy_h2d": (_I, [_P, _P, C.c_size_t, _P]),
     "sphb200_copy_d2h": (_I, [_P, _P, C.c_size_t, _P]),
+    "sphb200_copy_d2d": (_I, [_P, _P, C.c_size_t, _P]),
     "sphb200_stream_sync": (_I, [_P]),
     "sphb200_fill_u32": (_I, [_CTX, _P, _U32, _U64, _P]),
     "sphb200_fill_f32": (_I, [_CTX, _P, _F, _U64, _P]),
+    "sphb200_iota_u32": (_I, [_CTX, _P, _U64, _P]),
     "sphb200_vec3_to_vec4": (_I, [_CTX, _P, _P, _U32, _P]),
     "sphb200_vec4_to_vec3": (_I, [_CTX, _P, _P, _U32, _P]),
     "sphb200_pack_posvol": (_I, [_CTX, _P, _P, _P, _U32, _P]),
@@ -94,10 +96,12 @@ SYMBOLS = {
     "sphb200_morton_keys": (_I, [_CTX, C.POINTER(MeshT), _P, _U32, _P, _P, _P, _P]),
     "sphb200_update_sorted_id": (_I, [_CTX, _P, _P, _U32, _P]),
     "sphb200_cell_list_build": (_I, [_CTX, C.POINTER(MeshT), _P, _U32, CellListT, _P]),
+    "sphb200_cell_list_build_reorder": (_I, [_CTX, C.POINTER(MeshT), _P, _U32, _P, CellListT, _I, C.POINTER(_P), C.POINTER(_P),
+                                             C.POINTER(_U32), _P]),
     "sphb200_relation_count": (_I, [_CTX, C.POINTER(SearchT), RelationT, C.POINTER(_U64), _P]),
     "sphb200_relation_fill": (_I, [_CTX, C.POINTER(SearchT), RelationT, _P]),
     "sphb200_relation_build_fixed": (_I, [_CTX, C.POINTER(SearchT), RelationT, _U32, C.POINTER(_U32), _P]),
-    "sphb200_relation_export_csr": (_I, [_CTX, RelationT, _U32, _P, _P, _U64, _P]),
+    "sphb200_relation_export_csr": (_I, [_CTX, RelationT, _U32, _P, _P, _P, _P, _U64, _P]),
     "sphb200_gravity_force": (_I, [_CTX, C.POINTER(FluidView), C.POINTER(_F * 3), _P, _P]),
     "sphb200_compression_summation": (_I, [_CTX, C.POINTER(FluidArgs), _I, _P]),
     "sphb200_density_regularization": (_I, [_CTX, C.POINTER(FluidArgs), _P]),

@@ -1,0 +1,242 @@
+// host_api.cpp — C entry points that let the Python test/bench harness drive the C++ host layer
+// (include/sphinxsys_ck/*.h). Builds libsphb200_host.so; links libsphb200.so (the CUDA library) and nothing else.
+// All particle arrays cross this boundary in the REFERENCE particle order and in the reference's packed layout
+// (Vecd = 3 floats), i.e. what a SPHinXsys user sees in DiscreteVariable::Data().
+#include <cstring>
+#include <string>
+
+#include "../../include/sphinxsys_ck/dambreak_case.h"
+
+using namespace SPH;
+
+namespace
+{
+thread_local std::string g_error;
+
+struct Handle
+{
+    std::unique_ptr<DamBreakCK> sim;
+};
+
+template <class F> int guarded(F &&f)
+{
+    try
+    {
+        f();
+        return 0;
+    }
+    catch (const std::exception &e)
+    {
+        g_error = e.what();
+        return -1;
+    }
+}
+
+std::vector<Vecd> toVecd(const float *xyz, uint64_t n)
+{
+    std::vector<Vecd> v(n);
+    for (uint64_t i = 0; i < n; ++i) v[i] = Vecd(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    return v;
+}
+
+SPHBody &body(Handle *h, int which) { return which ? (SPHBody &)h->sim->wall_boundary : (SPHBody &)h->sim->water_block; }
+} // namespace
+
+extern "C"
+{
+    struct sphck_dambreak_options
+    {
+        int32_t dim;
+        double dp, DL, DH, DW, LL, LH, LW;
+        int32_t correction, fused_time_step, fused_regularization, sort_interval, device;
+        int32_t relation_stride;  // < 0: default; 0: exact two-phase build; > 0: one-pass stride
+        double system_lower[3], system_upper[3]; // exact system bounds in Real (what the harness used for its lattice)
+        int32_t use_system_bounds;
+    };
+
+    const char *sphck_last_error() { return g_error.c_str(); }
+
+    // fluid_xyz / wall_xyz / wall_normal_xyz may be NULL: the C++ lattice generator and shape normals are used then
+    void *sphck_dambreak_create(const sphck_dambreak_options *o, const float *fluid_xyz, uint64_t n_fluid, const float *wall_xyz,
+                                const float *wall_normal_xyz, uint64_t n_wall)
+    {
+        Handle *h = new Handle();
+        int rc = guarded([&] {
+            execution_instance().setDevice(o->device);
+            DamBreakParameters q;
+            q.dim = o->dim; q.dp = o->dp;
+            q.DL = o->DL; q.DH = o->DH; q.DW = o->DW; q.LL = o->LL; q.LH = o->LH; q.LW = o->LW;
+            q.correction = o->correction != 0;
+            q.fused_time_step = o->fused_time_step != 0;
+            q.fused_regularization = o->fused_regularization != 0;
+            q.sort_interval = o->sort_interval;
+            std::vector<Vecd> fp, wp, wn;
+            BoundingBoxd sb;
+            if (o->use_system_bounds)
+                sb = BoundingBoxd(Vecd(Real(o->system_lower[0]), Real(o->system_lower[1]), Real(o->system_lower[2])),
+                                  Vecd(Real(o->system_upper[0]), Real(o->system_upper[1]), Real(o->system_upper[2])));
+            if (fluid_xyz) fp = toVecd(fluid_xyz, n_fluid);
+            if (wall_xyz) wp = toVecd(wall_xyz, n_wall);
+            if (wall_normal_xyz) wn = toVecd(wall_normal_xyz, n_wall);
+            h->sim.reset(new DamBreakCK(q, fluid_xyz ? &fp : nullptr, wall_xyz ? &wp : nullptr, wall_normal_xyz ? &wn : nullptr,
+                                        o->use_system_bounds ? &sb : nullptr));
+            if (o->relation_stride >= 0)
+            {
+                h->sim->water_block_inner->fixed_stride_ = (uint32_t)o->relation_stride;
+                h->sim->water_wall_contact->fixed_stride_ = (uint32_t)o->relation_stride;
+            }
+        });
+        if (rc)
+        {
+            delete h;
+            return nullptr;
+        }
+        return h;
+    }
+    void sphck_destroy(void *hp) { delete (Handle *)hp; }
+
+    uint64_t sphck_count(void *hp, int which) { return body((Handle *)hp, which).TotalRealParticles(); }
+    uint64_t sphck_launches(void *) { return execution_instance().launches(); }
+    int sphck_synchronize(void *) { return guarded([] { execution_instance().synchronize(); }); }
+
+    // mesh / kernel PODs as computed by the host layer (parity of the host arithmetic with the oracle's inputs)
+    int sphck_mesh(void *hp, int which, sphb200_mesh_t *out)
+    {
+        return guarded([&] { *out = body((Handle *)hp, which).getCellLinkedList().mesh_; });
+    }
+    int sphck_kernel(void *hp, sphb200_kernel_t *out)
+    {
+        return guarded([&] { *out = ((Handle *)hp)->sim->water_block_inner->kernel_; });
+    }
+
+    // one name per dynamics object of the case (tests drive them one by one)
+    int sphck_exec(void *hp, const char *op_c, double a0, double *result)
+    {
+        Handle *h = (Handle *)hp;
+        DamBreakCK &s = *h->sim;
+        std::string op(op_c);
+        double r = 0;
+        int rc = guarded([&] {
+            if (op == "initialize") s.initialize();
+            else if (op == "step_outer") r = s.stepOuter();
+            else if (op == "run_outer")
+            {
+                long n = (long)a0, total = 0;
+                for (long k = 0; k < n; ++k) total += s.stepOuter();
+                r = (double)total;
+            }
+            else if (op == "gravity") s.constant_gravity->exec();
+            else if (op == "cell_list_fluid") s.water_cell_linked_list->exec();
+            else if (op == "cell_list_wall") s.wall_cell_linked_list->exec();
+            else if (op == "relations") s.water_block_update_complex_relation->exec();
+            else if (op == "sort") { s.particle_sort->exec(); s.fluid_acoustic_time_step->setPrimed(false); }
+            else if (op == "density_summation") s.fluid_density_summation->exec();
+            else if (op == "density_regularization") s.fluid_density_regularization->exec();
+            else if (op == "advection_setup") s.water_advection_step_setup->exec();
+            else if (op == "update_position") s.water_update_particle_position->exec();
+            else if (op == "advection_dt") r = s.fluid_advection_time_step->exec();
+            else if (op == "advection_dt_reduced") r = s.fluid_advection_time_step->ReducedValue();
+            else if (op == "acoustic_dt") r = s.fluid_acoustic_time_step->exec();
+            else if (op == "acoustic_dt_reduced") r = s.fluid_acoustic_time_step->ReducedValue();
+            else if (op == "acoustic_dt_unprime") s.fluid_acoustic_time_step->setPrimed(false);
+            else if (op == "acoustic1") s.fluid_acoustic_step_1st_half->exec(Real(a0));
+            else if (op == "acoustic2") s.fluid_acoustic_step_2nd_half->exec(Real(a0));
+            else if (op == "linear_correction") { if (s.fluid_linear_correction_matrix) s.fluid_linear_correction_matrix->exec(); }
+            else if (op == "energy") r = s.record_water_mechanical_energy->exec();
+            else if (op == "physical_time") r = s.physical_time;
+            else if (op == "acoustic_steps") r = (double)s.acoustic_steps;
+            else if (op == "outer_steps") r = (double)s.number_of_iterations;
+            else if (op == "last_acoustic_dt") r = s.last_acoustic_dt;
+            else if (op == "inner_total") r = (double)s.water_block_inner->total_;
+            else if (op == "inner_stride") r = (double)s.water_block_inner->fixed_stride_;
+            else if (op == "inner_max_count") r = (double)s.water_block_inner->max_count_;
+            else if (op == "set_relation_stride")
+            {
+                s.water_block_inner->fixed_stride_ = (uint32_t)a0;
+                s.water_wall_contact->fixed_stride_ = (uint32_t)a0;
+            }
+            else throw SphError("unknown op '" + op + "'");
+        });
+        if (result) *result = r;
+        return rc;
+    }
+
+    // phase-granular 1st half (parity tests against the reference's per-phase kernels)
+    int sphck_acoustic1_phase(void *hp, int phase /*0 initialize, 1 interact+update*/, double dt)
+    {
+        return guarded([&] {
+            auto *ph = dynamic_cast<fluid_dynamics::AcousticStep1stHalfPhases *>(((Handle *)hp)->sim->fluid_acoustic_step_1st_half.get());
+            if (!ph) throw SphError("1st half does not expose phases");
+            if (phase == 0) ph->deviceInitialize(Real(dt));
+            else ph->deviceInteractAndUpdate(Real(dt));
+        });
+    }
+
+    // kind: 0 Real, 1 Vecd (3 floats per particle), 2 UnsignedInt, 3 Matd (9 floats). Reference particle order.
+    int sphck_download(void *hp, int which, const char *name, int kind, void *out)
+    {
+        return guarded([&] {
+            BaseParticles &p = body((Handle *)hp, which).getBaseParticles();
+            if (kind == 0) p.download(p.getVariableByName<Real>(name), (Real *)out);
+            else if (kind == 1) p.download(p.getVariableByName<Vecd>(name), (Vecd *)out);
+            else if (kind == 2) p.download(p.getVariableByName<UnsignedInt>(name), (UnsignedInt *)out);
+            else p.download(p.getVariableByName<Matd>(name), (Matd *)out);
+        });
+    }
+    int sphck_upload(void *hp, int which, const char *name, int kind, const void *in)
+    {
+        return guarded([&] {
+            SPHBody &b = body((Handle *)hp, which);
+            BaseParticles &p = b.getBaseParticles();
+            if (kind == 0) p.upload(p.getVariableByName<Real>(name), (const Real *)in);
+            else if (kind == 1) p.upload(p.getVariableByName<Vecd>(name), (const Vecd *)in);
+            else if (kind == 2) p.upload(p.getVariableByName<UnsignedInt>(name), (const UnsignedInt *)in);
+            else p.upload(p.getVariableByName<Matd>(name), (const Matd *)in);
+            b.setPosVolDirty();
+            ((Handle *)hp)->sim->fluid_acoustic_time_step->setPrimed(false);
+        });
+    }
+    int sphck_has_variable(void *hp, int which, const char *name) { return body((Handle *)hp, which).getBaseParticles().hasVariable(name) ? 1 : 0; }
+
+    // raw (slot-order) device pointer of a variable, for harness-side pinned-memory transfers
+    void *sphck_device_pointer(void *hp, int which, const char *name, int kind)
+    {
+        void *out = nullptr;
+        guarded([&] {
+            BaseParticles &p = body((Handle *)hp, which).getBaseParticles();
+            if (kind == 0) out = p.deviceData<Real>(name);
+            else if (kind == 1) out = p.deviceData<Vecd>(name);
+            else if (kind == 2) out = p.deviceData<UnsignedInt>(name);
+            else out = p.deviceData<Matd>(name);
+        });
+        return out;
+    }
+
+    // cell-linked list (cell_offset[cells + 1]) and relation CSR in reference ids.
+    int sphck_cell_offsets(void *hp, int which, uint32_t *out, uint64_t count)
+    {
+        return guarded([&] {
+            CellLinkedList &cl = body((Handle *)hp, which).getCellLinkedList();
+            ExecutionInstance &ex = execution_instance();
+            ex.check(sphb200_copy_d2h(out, cl.cell_offset_.get(), count * sizeof(uint32_t), ex.stream()), "sphb200_copy_d2h");
+            ex.synchronize();
+        });
+    }
+    // relation 0 inner, 1 contact. Call with index == NULL to get the sizes first.
+    int sphck_export_csr(void *hp, int relation, uint32_t *offset, uint32_t *index, uint64_t index_capacity, uint64_t *total)
+    {
+        return guarded([&] {
+            DamBreakCK &s = *((Handle *)hp)->sim;
+            RelationBase &r = relation ? (RelationBase &)*s.water_wall_contact : (RelationBase &)*s.water_block_inner;
+            std::vector<uint32_t> off, idx;
+            r.exportCSR(off, idx);
+            if (total) *total = idx.size();
+            if (offset) std::memcpy(offset, off.data(), off.size() * sizeof(uint32_t));
+            if (index)
+            {
+                if (idx.size() > index_capacity) throw SphError("sphck_export_csr: index capacity too small");
+                std::memcpy(index, idx.data(), idx.size() * sizeof(uint32_t));
+            }
+        });
+    }
+}

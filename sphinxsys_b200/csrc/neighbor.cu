@@ -493,7 +493,8 @@ __global__ void __launch_bounds__(256) k_counts_by_id(const u32 *__restrict__ co
 }
 __global__ void __launch_bounds__(128)
     k_export_csr(const u32 *__restrict__ count, const u32 *__restrict__ slice_offset, const u32 *__restrict__ index,
-                 const u32 *__restrict__ order, u32 n, const u32 *__restrict__ particle_offset, u32 *__restrict__ neighbor_index)
+                 const u32 *__restrict__ order, const u32 *__restrict__ tar_ids, u32 n, const u32 *__restrict__ particle_offset,
+                 u32 *__restrict__ neighbor_index)
 {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= n) return;
@@ -501,20 +502,26 @@ __global__ void __launch_bounds__(128)
     u64 src = (u64)slice_offset[t >> 5] + (t & 31u);
     u32 dst = particle_offset[i];
     u32 c = count[t];
-    for (u32 k = 0; k < c; ++k) neighbor_index[dst + k] = index[src + 32ull * k];
+    for (u32 k = 0; k < c; ++k)
+    {
+        u32 j = index[src + 32ull * k];
+        neighbor_index[dst + k] = tar_ids ? tar_ids[j] : j;
+    }
 }
 
-extern "C" int sphb200_relation_export_csr(sphb200_context_t *ctx, sphb200_relation_t rel, uint32_t n, uint32_t *particle_offset,
-                                           uint32_t *neighbor_index, uint64_t index_capacity, void *stream)
+extern "C" int sphb200_relation_export_csr(sphb200_context_t *ctx, sphb200_relation_t rel, uint32_t n, const uint32_t *src_ids,
+                                           const uint32_t *tar_ids, uint32_t *particle_offset, uint32_t *neighbor_index,
+                                           uint64_t index_capacity, void *stream)
 {
     SPH_CHECK_ARG(ctx, ctx && rel.count && rel.slice_offset && particle_offset, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    const u32 *order = src_ids ? src_ids : rel.order;
     void *p;
     int rc = sph_scratch(ctx, 3, ((size_t)n + 1) * sizeof(u32) + 64, &p);
     if (rc) return rc;
     u32 *by_id = (u32 *)p;
     SPH_CUDA(ctx, cudaMemsetAsync(by_id + n, 0, sizeof(u32), st));
-    if (n) SPH_LAUNCH(ctx, k_counts_by_id, sph_blocks(n, 256), 256, 0, st, rel.count, rel.order, n, by_id);
+    if (n) SPH_LAUNCH(ctx, k_counts_by_id, sph_blocks(n, 256), 256, 0, st, rel.count, order, n, by_id);
     // particle_offset = exclusive scan of the per-particle counts over n+1 entries
     rc = sph_scan_u32(ctx, by_id, particle_offset, (u64)n + 1, 0, st);
     if (rc) return rc;
@@ -528,7 +535,7 @@ extern "C" int sphb200_relation_export_csr(sphb200_context_t *ctx, sphb200_relat
                  (unsigned long long)index_capacity);
         return SPHB200_E_CAPACITY;
     }
-    SPH_LAUNCH(ctx, k_export_csr, sph_blocks(n, 128), 128, 0, st, rel.count, rel.slice_offset, rel.index, rel.order, n,
+    SPH_LAUNCH(ctx, k_export_csr, sph_blocks(n, 128), 128, 0, st, rel.count, rel.slice_offset, rel.index, order, tar_ids, n,
                particle_offset, neighbor_index);
     return 0;
 }

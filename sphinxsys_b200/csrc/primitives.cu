@@ -58,6 +58,10 @@ extern "C" int sphb200_copy_d2h(void *dst, const void *src, size_t bytes, void *
 {
     return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, (cudaStream_t)stream);
 }
+extern "C" int sphb200_copy_d2d(void *dst, const void *src, size_t bytes, void *stream)
+{
+    return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
+}
 extern "C" int sphb200_stream_sync(void *stream) { return (int)cudaStreamSynchronize((cudaStream_t)stream); }
 
 // =====================================================================================================
@@ -83,6 +87,20 @@ extern "C" int sphb200_fill_f32(sphb200_context_t *ctx, float *dst, float value,
     SPH_CHECK_ARG(ctx, ctx && (dst || n == 0), "null pointer");
     if (n == 0) return 0;
     SPH_LAUNCH(ctx, k_fill<float>, fill_grid(n), 256, 0, stream, dst, value, n);
+    return 0;
+}
+
+__global__ void k_iota(u32 *dst, u64 n)
+{
+    u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (; i < n; i += stride) dst[i] = (u32)i;
+}
+extern "C" int sphb200_iota_u32(sphb200_context_t *ctx, uint32_t *dst, uint64_t n, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && (dst || n == 0), "null pointer");
+    if (n == 0) return 0;
+    SPH_LAUNCH(ctx, k_iota, fill_grid(n), 256, 0, stream, dst, n);
     return 0;
 }
 

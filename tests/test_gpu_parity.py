@@ -168,9 +168,8 @@ def pair3d():
     pos, vel = perturb_state(case)
     case.fluid_pos = pos
     gpu = make_gpu(case, fused_time_step=False)
-    gpu.upload_state()
-    gpu.water_block.particles.upload("Velocity", vel)
-    gpu.initialize(upload=False)
+    gpu.upload("Velocity", vel)
+    gpu.initialize()
     o32 = make_oracle(case, f64=False)
     o64 = make_oracle(case, f64=True)
     for o in (o32, o64):
@@ -179,25 +178,60 @@ def pair3d():
     return case, gpu, o32, o64
 
 
+def _raw_u32(gpu, name, wall=False):
+    """A u32 variable in STORAGE (slot) order, straight from the device."""
+    from sphinxsys_b200 import capi
+    n = gpu.n_wall if wall else gpu.n_fluid
+    ptr = gpu.lib.sphck_device_pointer(gpu._h, int(wall), name.encode(), 2)
+    out = np.empty(n, dtype=np.uint32)
+    lib = capi.load()
+    assert lib.sphb200_copy_d2h(out.ctypes.data, ptr, n * 4, None) == 0
+    assert lib.sphb200_stream_sync(None) == 0
+    return out
+
+
+@pytest.mark.parametrize("dim,dp", [(3, 0.05), (2, 0.025), (3, 0.00625)])
+def test_host_layer_pods_match_harness(dim, dp):
+    """Mesh and tabulated-kernel PODs computed by the C++ host layer (geometry.h) are bit-identical to the ones
+    the oracle is given (hostmath.py), and its lattice generator + shape normals reproduce the harness arrays."""
+    from sphinxsys_b200 import capi, cases
+    from sphinxsys_b200.host import DamBreakCK
+    if dp < 0.01:
+        gpu = DamBreakCK(None, dim=dim, dp=dp, generate=True)
+        assert gpu.n_fluid == 4_096_000 and gpu.n_wall == 3_034_688  # SURVEY.md §8: config 2
+        m = gpu.mesh()
+        assert tuple(m.cells) == (341, 134, 41)
+        return
+    case = cases.dam_break(dim=dim, dp=dp)
+    gpu = DamBreakCK(case, generate=True)  # C++ generator, no arrays handed over
+    for wall in (False, True):
+        m, ref = gpu.mesh(wall), capi.mesh_t(case.mesh)
+        assert bytes(m) == bytes(ref)
+    k, kref = gpu.kernel(), capi.kernel_t(case.kernel)
+    assert bytes(k) == bytes(kref)
+    assert (gpu.n_fluid, gpu.n_wall) == (case.n_fluid, case.n_wall)
+    assert np.array_equal(gpu.download("Position"), case.fluid_pos)
+    assert np.array_equal(gpu.download("Position", wall=True), case.wall_pos)
+    assert np.max(np.abs(gpu.download("NormalDirection", wall=True) - case.wall_normal)) <= 1e-6
+
+
 def test_cell_list_bit_exact(pair3d):
+    """cell_offset identical; storage follows the cell order, and the reference ids read in storage order are the
+    oracle's particle_index (ascending id inside a cell)."""
     case, gpu, o32, _ = pair3d
-    cells = case.mesh.total_cells
-    for body, prefix in ((gpu.water_block, "fluid"), (gpu.wall_boundary, "wall")):
-        cll = body.getCellLinkedList()
-        off = cll.cell_offset[: cells + 1].cpu().numpy().view(np.uint32)
-        idx = cll.particle_index[: body.n].cpu().numpy().view(np.uint32)
-        assert np.array_equal(off, o32.uint(f"{prefix}_cell_offset"))
-        assert np.array_equal(idx, o32.uint(f"{prefix}_particle_index")[: body.n])
+    for wall, prefix in ((False, "fluid"), (True, "wall")):
+        n = gpu.n_wall if wall else gpu.n_fluid
+        assert np.array_equal(gpu.cell_offsets(wall), o32.uint(f"{prefix}_cell_offset"))
+        assert np.array_equal(_raw_u32(gpu, "ReferenceID", wall), o32.uint(f"{prefix}_particle_index")[:n])
 
 
 def test_neighbour_lists_bit_exact(pair3d):
     case, gpu, o32, _ = pair3d
-    for rel, name in ((gpu.water_block_inner, "inner"), (gpu.water_wall_contact, "contact")):
-        off, idx = rel.export_csr()
+    for contact, name in ((False, "inner"), (True, "contact")):
+        off, idx = gpu.export_csr(contact)
         ref_off, ref_idx = o32.uint(f"{name}_offset"), o32.uint(f"{name}_index")
         assert np.array_equal(off, ref_off)
         total = int(ref_off[-1])
-        assert rel.total >= total
         assert np.array_equal(idx[:total], ref_idx[:total])  # same sets AND same (reference search) order
     _report("neighbours_3d", {"inner_total": int(o32.uint("inner_offset")[-1]), "contact_total": int(o32.uint("contact_offset")[-1])})
 
@@ -206,27 +240,22 @@ def test_exact_two_phase_build_equals_one_pass(pair3d):
     """count -> scan -> fill (the reference's phases) and the one-pass fixed-stride build give identical lists;
     a stride that is too small is reported, not silently truncated."""
     case, gpu, o32, _ = pair3d
-    rel = gpu.water_block_inner
     ref_off, ref_idx = o32.uint("inner_offset"), o32.uint("inner_index")
-    keep = rel.fixed_stride
+    keep = int(gpu.exec("inner_stride"))
     try:
-        rel.fixed_stride = 0
-        gpu.water_block_update_complex_relation.exec()
-        off, idx = rel.export_csr()
-        assert rel.total == int(np.sum(32 * np.max(np.diff(np.concatenate([ref_off.astype(np.int64)]))[
-            gpu.water_block.getCellLinkedList().particle_index[: case.n_fluid].cpu().numpy().astype(np.int64)][
-            : (case.n_fluid // 32) * 32].reshape(-1, 32), axis=1))) + (32 * int(np.max(np.diff(ref_off.astype(np.int64))[
-                gpu.water_block.getCellLinkedList().particle_index[: case.n_fluid].cpu().numpy().astype(np.int64)][
-                (case.n_fluid // 32) * 32:])) if case.n_fluid % 32 else 0)
+        gpu.exec("set_relation_stride", 0)
+        gpu.exec("relations")
+        off, idx = gpu.export_csr()
         assert np.array_equal(off, ref_off) and np.array_equal(idx[: ref_off[-1]], ref_idx[: ref_off[-1]])
-        rel.fixed_stride = 16  # far too small for ~65 neighbours: must fall back to the exact build
-        gpu.water_block_update_complex_relation.exec()
-        assert rel.fixed_stride == 0 and rel.max_count == int(np.max(np.diff(ref_off.astype(np.int64))))
-        off, idx = rel.export_csr()
+        gpu.exec("set_relation_stride", 16)  # far too small for ~65 neighbours: must fall back to the exact build
+        gpu.exec("relations")
+        assert int(gpu.exec("inner_stride")) == 0
+        assert int(gpu.exec("inner_max_count")) == int(np.max(np.diff(ref_off.astype(np.int64))))
+        off, idx = gpu.export_csr()
         assert np.array_equal(off, ref_off) and np.array_equal(idx[: ref_off[-1]], ref_idx[: ref_off[-1]])
     finally:
-        rel.fixed_stride = keep
-        gpu.water_block_update_complex_relation.exec()
+        gpu.exec("set_relation_stride", keep)
+        gpu.exec("relations")
 
 
 def _compare(gpu, o32, o64, names_real, names_vec, tag, tol):
@@ -254,37 +283,35 @@ def test_per_dynamics_parity_3d(pair3d):
     case, gpu, o32, o64 = pair3d
     tol = {"default": 1e-5, "Pressure": 3e-4, "CompressionRate": 5e-5, "Force": 5e-5}
     # density summation + regularisation
-    gpu.fluid_density_summation.exec()
+    gpu.exec("density_summation")
     for o in (o32, o64):
         o.exec("compression_summation")
         o.exec("density_regularization")
     _compare(gpu, o32, o64, ["CompressionSummation", "Compression", "Density"], [], "density_summation", tol)
-    gpu.water_advection_step_setup.exec()
+    gpu.exec("advection_setup")
     for o in (o32, o64):
         o.exec("advection_setup")
     _compare(gpu, o32, o64, ["VolumetricMeasure"], ["Displacement"], "advection_setup", tol)
     # time steps
-    adv = gpu.fluid_advection_time_step.exec()
-    ac = gpu.fluid_acoustic_time_step.exec()
+    adv = gpu.exec("advection_dt")
+    ac = gpu.exec("acoustic_dt")
     assert abs(adv - o32.exec("advection_dt")) <= 1e-6 * adv
     assert abs(ac - o32.exec("acoustic_dt")) <= 1e-6 * ac
-    assert np.float32(gpu.fluid_advection_time_step.last_reduced) == np.float32(o32.exec("advection_dt_reduced"))  # exact max
+    assert np.float32(gpu.exec("advection_dt_reduced")) == np.float32(o32.exec("advection_dt_reduced"))  # exact max
     dt = float(np.float32(ac))
     # 1st half, phase by phase
-    a = gpu.system.args()
-    gpu.system.prepare()
-    gpu.ctx.call("sphb200_acoustic_1st_half_initialize", C.byref(a), dt, _s())
+    gpu.acoustic1_phase(0, dt)
     for o in (o32, o64):
         o.exec("acoustic1_init", dt)
     _compare(gpu, o32, o64, ["Compression", "Density", "Pressure"], ["Displacement"], "a1_init", tol)
-    gpu.ctx.call("sphb200_acoustic_1st_half_interact", C.byref(a), dt, 1, _s())
+    gpu.acoustic1_phase(1, dt)
     for o in (o32, o64):
         o.exec("acoustic1_inner")
         o.exec("acoustic1_wall")
         o.exec("acoustic1_update", dt)
     _compare(gpu, o32, o64, ["CompressionRate"], ["Force", "Velocity"], "a1_interact_update", tol)
     # 2nd half (single fused launch)
-    gpu.fluid_acoustic_step_2nd_half.exec(dt)
+    gpu.exec("acoustic2", dt)
     for o in (o32, o64):
         o.exec("acoustic2", dt)
     _compare(gpu, o32, o64, ["CompressionRate", "Compression", "Density"], ["Force", "Displacement"], "a2", tol)
@@ -293,20 +320,24 @@ def test_per_dynamics_parity_3d(pair3d):
     assert abs(e - o64.exec("energy")) <= 1e-5 * abs(e)
 
 
-def test_fused_time_step_equals_standalone(pair3d):
+def test_fused_time_step_equals_standalone():
     """The max folded into the 2nd-half launch must equal the stand-alone AcousticTimeStepCK reduction bit for bit."""
-    case, gpu, o32, o64 = pair3d
-    nr = gpu.fluid_acoustic_step_2nd_half.enable_fused_time_step()
+    from sphinxsys_b200 import cases
+    case = cases.dam_break(dim=3, dp=0.05)
+    pos, vel = perturb_state(case)
+    case.fluid_pos = pos
+    gpu = make_gpu(case, fused_time_step=True)
+    gpu.upload("Velocity", vel)
+    gpu.initialize()
+    gpu.exec("density_summation")
+    gpu.exec("advection_setup")
     dt = 1e-4
-    gpu.fluid_acoustic_step_1st_half.exec(dt)
-    gpu.fluid_acoustic_step_2nd_half.exec(dt)
-    fused = float(nr.item())
-    gpu.fluid_acoustic_time_step.exec()
-    assert np.float32(fused) == np.float32(gpu.fluid_acoustic_time_step.last_reduced)
-    gpu.fluid_acoustic_step_2nd_half.next_reduced = None
-    for o in (o32, o64):
-        o.exec("acoustic1", dt)
-        o.exec("acoustic2", dt)
+    gpu.exec("acoustic1", dt)
+    gpu.exec("acoustic2", dt)
+    gpu.exec("acoustic_dt")           # primed: read back from the fused slot
+    fused = gpu.exec("acoustic_dt_reduced")
+    gpu.exec("acoustic_dt")           # not primed any more: stand-alone reduction over the same state
+    assert np.float32(fused) == np.float32(gpu.exec("acoustic_dt_reduced"))
 
 
 @pytest.mark.parametrize("dim,dp,correction,n_outer", [(3, 0.05, False, 12), (3, 0.05, True, 6), (2, 0.025, False, 30)])
@@ -327,7 +358,7 @@ def test_multi_step_drift(dim, dp, correction, n_outer):
     assert int(o32.exec("acoustic_steps")) == n_ac, "both sides must take the same number of acoustic sub-steps"
     assert abs(gpu.physical_time - o32.exec("physical_time")) <= 1e-5 * gpu.physical_time
     rep = {}
-    # both sides sorted with the same stable permutation: compare in storage order
+    # both sides renumber with the same stable permutation at every sort: compare in the reference particle order
     assert np.array_equal(gpu_field(gpu, "OriginalID"), o32.uint("OriginalID"))
     for nm, w, tol in (("Position", 3, 5e-6), ("Velocity", 3, 2e-4), ("Density", 1, 1e-6), ("Compression", 1, 1e-6)):
         e = rel_err(gpu_field(gpu, nm), oracle_field(o32, nm, w))
@@ -339,6 +370,10 @@ def test_multi_step_drift(dim, dp, correction, n_outer):
     front_gpu = float(gpu_field(gpu, "Position")[:, 0].max())
     front_ref = float(oracle_field(o32, "Position", 3)[:, 0].max())
     assert abs(front_gpu - front_ref) <= 1e-5 * abs(front_ref)
+    # neighbour sets after the run (sorted + reordered storage) still match the oracle's, in reference ids
+    off, idx = gpu.export_csr()
+    assert np.array_equal(off, o32.uint("inner_offset"))
+    assert np.array_equal(idx, o32.uint("inner_index")[: off[-1]])
     _report(f"drift_{dim}d_corr{int(correction)}", rep)
 
 

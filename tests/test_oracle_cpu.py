@@ -263,10 +263,25 @@ def test_capi_exports_every_declared_symbol():
     assert lib.sphb200_version() == 100
 
 
+def test_host_layer_library_loads_and_fails_loudly_without_gpu():
+    """libsphb200_host.so (the C++ host layer) loads on a CPU box; creating a case without a CUDA device raises
+    instead of falling back to anything."""
+    import torch
+    from sphinxsys_b200 import capi, host
+    lib = host.load()
+    for name in ("sphck_dambreak_create", "sphck_exec", "sphck_download", "sphck_upload", "sphck_export_csr",
+                 "sphck_cell_offsets", "sphck_acoustic1_phase", "sphck_mesh", "sphck_kernel", "sphck_launches"):
+        assert hasattr(lib, name)
+    if not torch.cuda.is_available():
+        with pytest.raises(capi.SphB200Error):
+            host.DamBreakCK(None, dim=2, dp=0.025, generate=True)
+
+
 def test_product_does_not_import_oracle():
     """The product package must never route through the oracle (or any CPU fallback)."""
     pkg = os.path.join(os.path.dirname(HERE), "sphinxsys_b200")
-    for root, _, files in os.walk(pkg):
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    for root, _, files in list(os.walk(pkg)) + list(os.walk(inc)):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 src = open(os.path.join(root, f)).read()
