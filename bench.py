@@ -160,11 +160,29 @@ def run_ours(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     # The C++ host layer builds the case itself (lattice generator + shape normals, include/sphinxsys_ck/dambreak_case.h)
-    # and runs the case-file loop; Python only times it. Weak scaling: every rank runs the config-2 cross-section
-    # (one z-slab of a tank stretched world x in z).
-    solver = DamBreakCK(None, dim=3, dp=args.dp, device_index=local_rank, fused_time_step=True, sort_interval=100, generate=True)
+    # and runs the case-file loop; Python only times it. Weak scaling: the SAME dam break refined
+    # so that the fluid holds world x 4,096,000 particles (dp = 0.00625 / world^(1/3)), split into x-slabs of equal
+    # particle count, one per GPU, with NCCL halo exchange of contiguous cell-plane ranges.
+    dp = args.dp / (world ** (1.0 / 3.0)) if world > 1 else args.dp
+    uid = None
+    if world > 1:
+        from sphinxsys_b200.host import comm_unique_id
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(buf, src=0)
+        uid = bytes(buf.cpu().numpy().tobytes())
+    solver = DamBreakCK(None, dim=3, dp=dp, device_index=local_rank, fused_time_step=True, sort_interval=100, generate=True,
+                        rank=rank, nranks=world, unique_id=uid)
     solver.initialize()
-    n_fluid, n_wall = solver.n_fluid, solver.n_wall
+    n_own = solver.own_range()[1]
+    n_wall = solver.n_wall
+    if world > 1:
+        tn = torch.tensor([float(n_own)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tn, op=dist.ReduceOp.SUM)
+        n_fluid = int(tn.item())          # global fluid particles
+    else:
+        n_fluid = solver.n_fluid
 
     def barrier():
         if world > 1:
@@ -190,14 +208,9 @@ def run_ours(args, rank, world, local_rank):
     launches = solver.launches - launches0
     t = torch.tensor([ms, float(n_ac)], dtype=torch.float64, device="cuda")
     if world > 1:
-        tmax = t.clone()
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        tsum = t.clone()
-        dist.all_reduce(tsum, op=dist.ReduceOp.SUM)
-        ms = float(tmax[0])
-        total_particle_steps = n_fluid * float(tsum[1])
-    else:
-        total_particle_steps = n_fluid * float(n_ac)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # every rank takes the same sub-steps (global dt); time = slowest rank
+        ms = float(t[0])
+    total_particle_steps = n_fluid * float(n_ac)  # n_fluid is the GLOBAL particle count
     value = total_particle_steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (2nd-half fused launch), timed live on the same state ----
@@ -206,7 +219,7 @@ def run_ours(args, rank, world, local_rank):
     ms_a2 = time_kernel(lambda: solver.exec("acoustic2", dt * 1e-3), 20, torch)
     ms_a1 = time_kernel(lambda: solver.exec("acoustic1", dt * 1e-3), 20, torch)
     ms_sum = time_kernel(lambda: solver.exec("density_summation"), 10, torch)
-    ms_cl = time_kernel(lambda: solver.exec("cell_list_fluid"), 10, torch)
+    ms_cl = time_kernel(lambda: solver.exec("rebuild"), 10, torch)  # cell list + storage reorder (+ migration/ghosts if decomposed)
     ms_rel = time_kernel(lambda: solver.exec("relations"), 5, torch)
     solver.exec("acoustic_dt_unprime")
     traffic = None
@@ -215,10 +228,10 @@ def run_ours(args, rank, world, local_rank):
         traffic = tj.get("k_a2", {}).get(str(n_fluid))
     except Exception:
         pass
-    ach_a2 = A_STEP_2ND * n_fluid / (ms_a2 * 1e-3) / 1e9
+    ach_a2 = A_STEP_2ND * n_own / (ms_a2 * 1e-3) / 1e9  # per GPU
     roofline = {"bound": "hbm", "kernel": "k_a2 (AcousticStep2ndHalf: initialize+inner+wall+update+dt-max, one launch)",
                 "achieved": ach_a2, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach_a2 / peak,
-                "traffic": traffic, "algorithmic_bytes_per_launch": A_STEP_2ND * n_fluid, "launch_ms": ms_a2,
+                "traffic": traffic, "algorithmic_bytes_per_launch": A_STEP_2ND * n_own, "launch_ms": ms_a2,
                 "note": "pair arithmetic (~80 neighbours x ~40 instr) is FP32-issue/L1 bound before it is HBM bound; see DESIGN.md §5",
                 "other_kernels_ms": {"acoustic_1st_half(init+interact)": ms_a1, "density_summation": ms_sum,
                                      "cell_list_build+reorder": ms_cl, "relation_build(inner+contact)": ms_rel}}
@@ -228,26 +241,52 @@ def run_ours(args, rank, world, local_rank):
                 "VolumetricMeasureRef", "PreviousGravityForceCK"]
     out_names = ["Position", "Velocity", "Density"]
 
+    decomposed = world > 1
+
     def pinned_like(name):
-        w = 3 if name in host.VEC_NAMES else 1
-        tns = torch.empty((n_fluid, w) if w == 3 else (n_fluid,), dtype=torch.float32).pin_memory()
+        # single GPU: the reference's packed layout in reference particle order; decomposed: this rank's own slots raw
+        w = (4 if decomposed else 3) if name in host.VEC_NAMES else 1
+        rows = n_own + n_own // 4 if decomposed else n_fluid
+        tns = torch.empty((rows, w) if w > 1 else (rows,), dtype=torch.float32).pin_memory()
         return tns, tns.numpy()
 
     host_in = {nm: pinned_like(nm) for nm in in_names}
     host_out = {nm: pinned_like(nm) for nm in out_names}
-    for nm in in_names:
-        solver.download(nm, out=host_in[nm][1])
-    h2d = sum(tn.numel() * 4 for tn, _ in host_in.values())
-    d2h = sum(tn.numel() * 4 for tn, _ in host_out.values())
+
+    def fetch_inputs():
+        for nm in in_names:
+            if decomposed:
+                solver.download_own_into(nm, host_in[nm][1])
+            else:
+                solver.download(nm, out=host_in[nm][1])
+
+    fetch_inputs()
+    per = lambda nm, vecw: (vecw if nm in host.VEC_NAMES else 1) * 4
+    h2d = sum(per(nm, 4 if decomposed else 3) * (n_own if decomposed else n_fluid) for nm in in_names)
+    d2h = sum(per(nm, 4 if decomposed else 3) * (n_own if decomposed else n_fluid) for nm in out_names)
+    if decomposed:
+        th = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(th, op=dist.ReduceOp.SUM)
+        h2d, d2h = int(th[0]), int(th[1])
 
     def e2e_step():
-        for nm in in_names:
-            solver.upload(nm, host_in[nm][1])           # DiscreteVariable::synchronizeToDevice (reference order)
-        solver.exec("cell_list_fluid")
+        if decomposed:
+            for nm in in_names:
+                solver.upload_own(nm, host_in[nm][1])   # own slots, storage order, from pinned memory
+            solver.exec("rebuild")
+        else:
+            for nm in in_names:
+                solver.upload(nm, host_in[nm][1])       # DiscreteVariable::synchronizeToDevice (reference order)
+            solver.exec("cell_list_fluid")
         solver.exec("relations")
         n = solver.step_outer()
-        for nm in out_names:
-            solver.download(nm, out=host_out[nm][1])    # DiscreteVariable::synchronizeWithDevice
+        if decomposed:
+            for nm in out_names:
+                solver.download_own_into(nm, host_out[nm][1])
+            fetch_inputs()                              # the own set changed (migration): next step's inputs
+        else:
+            for nm in out_names:
+                solver.download(nm, out=host_out[nm][1])  # DiscreteVariable::synchronizeWithDevice
         return n
 
     e2e_step()
@@ -261,13 +300,9 @@ def run_ours(args, rank, world, local_rank):
     sec = time.perf_counter() - t0
     tt = torch.tensor([sec, float(n_ac_e2e)], dtype=torch.float64, device="cuda")
     if world > 1:
-        tm = tt.clone()
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        ts = tt.clone()
-        dist.all_reduce(ts, op=dist.ReduceOp.SUM)
-        sec, tot = float(tm[0]), n_fluid * float(ts[1])
-    else:
-        tot = n_fluid * float(n_ac_e2e)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        sec = float(tt[0])
+    tot = n_fluid * float(n_ac_e2e)
     e2e = {"value": tot / sec, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "steps": k_e2e, "note": "per step: H2D of all evolving variables from pinned host memory (reference particle order), "
                                    "cell-list + relation rebuild, one outer step, D2H of Position/Velocity/Density"}
@@ -285,11 +320,14 @@ def run_ours(args, rank, world, local_rank):
             "metric": "particle-steps/sec (3D WCSPH dam break)", "value": value, "unit": "particle-steps/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"3-D dam break WCSPH (tests_sycl dambreak geometry), dp={args.dp}: {n_fluid} fluid + {n_wall} wall "
-                                   f"particles per GPU, AcousticRiemann + wall, Wendland C2 tabulated, sort every 100 outer steps",
-                       "n_fluid_per_gpu": n_fluid, "n_wall_per_gpu": n_wall, "acoustic_steps_per_outer": n_ac_per_outer,
-                       "l2_policy": "working set (~2 GB incl. neighbour lists) larger than L2, no flush",
-                       "parallelism": "1 GPU" if world == 1 else f"{world} z-slab replicas (halo exchange pending)"},
+            "config": {"workload": f"3-D dam break WCSPH (tests_sycl dambreak geometry), dp={dp:.6g}: {n_fluid} fluid + {n_wall} wall "
+                                   f"particles, AcousticRiemann + wall, Wendland C2 tabulated, sort every 100 outer steps",
+                       "n_fluid_global": n_fluid, "n_fluid_per_gpu": n_fluid // world, "n_wall": n_wall,
+                       "acoustic_steps_per_outer": n_ac_per_outer,
+                       "l2_policy": "working set (~2 GB per GPU incl. neighbour lists) larger than L2, no flush",
+                       "parallelism": "1 GPU" if world == 1 else
+                       f"{world} x-slabs of equal particle count on the global mesh, NCCL halo exchange of contiguous cell-plane ranges, "
+                       f"full wall copy per rank"},
             "roofline": roofline,
             "whole_step_hbm_frac": value * alg_bytes / 1e9 / peak,
             "algorithmic_bytes_per_particle_step": alg_bytes,

@@ -37,7 +37,8 @@ enum
     SPHB200_E_INVALID = -1,     /* bad argument (null pointer, unsupported enum, n too large) */
     SPHB200_E_CAPACITY = -2,    /* output buffer smaller than required; required size is returned */
     SPHB200_E_UNSUPPORTED = -3, /* type tuple outside the closed set listed in DESIGN.md */
-    SPHB200_E_NOMEM = -4
+    SPHB200_E_NOMEM = -4,
+    SPHB200_E_COMM = -5         /* NCCL missing or a collective failed (see sphb200_last_error_string) */
 };
 
 typedef struct sphb200_context sphb200_context_t; /* opaque; one per GPU, one driving host thread */
@@ -98,6 +99,8 @@ typedef struct
     float *B;                     /* LinearCorrectionMatrix, 9 floats row-major per particle, or NULL */
     sphb200_vec4_t *posvol;       /* derived gather record (x, y, z, Vol): refresh with sphb200_pack_posvol
                                      whenever Position or VolumetricMeasure changed */
+    uint32_t active_begin;        /* dynamics update the slots [active_begin, active_end) only; slots outside (ghost */
+    uint32_t active_end;          /* particles of a decomposed run) are read as neighbours. active_end == 0: [0, n) */
 } sphb200_fluid_view_t;
 
 /* Device views of one wall (contact) body; ref: interaction_ck.hpp:79-91 (Interaction<Wall>). */
@@ -151,6 +154,7 @@ typedef struct
     sphb200_cell_list_t tar_list;         /* target cell-linked list */
     int32_t is_inner;                     /* 1: Inner<> (exclude j == i), 0: Contact<> */
     int32_t search_depth;                 /* cells each side: 1 inner; contact: cell_linked_list.hpp:161-167 */
+    uint32_t src_begin, src_end;          /* source slots searched: [src_begin, src_end); src_end == 0: [0, n_src) */
     int32_t cell_ordered;                 /* 1: src_pos and tar_pos are STORED in the cell order of their own lists
                                              (slot == particle id, particle_index == identity, src_order == NULL; see
                                              sphb200_cell_list_build_reorder): selects the warp-uniform search */
@@ -291,6 +295,28 @@ int sphb200_linear_correction_matrix(sphb200_context_t *ctx, const sphb200_fluid
 /* ReduceDynamicsCK<TotalMechanicalEnergyCK>; ref: general_dynamics/general_reduce_ck.h:52-88 */
 int sphb200_total_mechanical_energy(sphb200_context_t *ctx, const sphb200_fluid_view_t *fluid, const float gravity[3],
                                     double *energy_host, void *stream);
+
+/* ---------------------------------------------------------------------------------------------------
+ * slab-decomposed multi-GPU runs (new: the reference has no distributed path). One process and one context per
+ * GPU; the communicator is NCCL over NVLink/NVSwitch. Bootstrap: rank 0 calls sphb200_comm_unique_id and hands
+ * the 128 bytes to the other ranks by whatever the launcher offers (torch.distributed, MPI, a file).
+ * Storage follows the cell order with x the slowest axis, so the cell planes a neighbouring slab needs are
+ * contiguous ranges of every variable array: exchanges send and receive those ranges in place.
+ * ------------------------------------------------------------------------------------------------- */
+#define SPHB200_UNIQUE_ID_BYTES 128
+int sphb200_comm_unique_id(void *id128);
+int sphb200_comm_create(sphb200_context_t *ctx, int nranks, int rank, const void *id128);
+int sphb200_comm_destroy(sphb200_context_t *ctx);
+int sphb200_comm_rank(const sphb200_context_t *ctx);
+int sphb200_comm_size(const sphb200_context_t *ctx);
+/* one grouped send/recv with rank-1 ("left") and rank+1 ("right"): `count` device segments per direction; what a
+ * rank sends left arrives in its left neighbour's recv_right segments of the same index. Missing neighbours are skipped. */
+int sphb200_comm_exchange(sphb200_context_t *ctx, int count, const void *const *send_left, const size_t *send_left_bytes,
+                          void *const *recv_left, const size_t *recv_left_bytes, const void *const *send_right,
+                          const size_t *send_right_bytes, void *const *recv_right, const size_t *recv_right_bytes, void *stream);
+int sphb200_comm_allreduce_max_f32(sphb200_context_t *ctx, float *dev_inout, int n, void *stream);
+int sphb200_comm_allreduce_sum_f64(sphb200_context_t *ctx, double *dev_inout, int n, void *stream);
+int sphb200_comm_allgather_u64(sphb200_context_t *ctx, const uint64_t *dev_send, uint64_t *dev_recv, int n_per_rank, void *stream);
 
 #ifdef __cplusplus
 }

@@ -26,7 +26,7 @@ class CellLinkedList
         // grid spacing = kernel cut-off radius, buffer width 2 (adaptation.cpp:80-85, cell_linked_list.cpp:14)
         mesh_ = makeMesh(sys.system_domain_bounds_, body.getSPHAdaptation().CutOffRadius(), 2, sys.dim_);
         total_cells_ = (size_t)mesh_.cells[0] * mesh_.cells[1] * mesh_.cells[2];
-        size_t n = body.TotalRealParticles();
+        size_t n = body.getBaseParticles().ParticlesBound();
         cell_offset_.reset((total_cells_ + 2) * sizeof(uint32_t));
         particle_index_.reset((std::max(n, total_cells_) + 2) * sizeof(uint32_t)); // cell_linked_list.cpp:172-174
     }
@@ -63,7 +63,7 @@ class RelationBase
 
     RelationBase(SPHBody &source, SPHBody &target, bool is_inner) : source_(source), target_(target), is_inner_(is_inner)
     {
-        size_t n = source.TotalRealParticles();
+        size_t n = source.getBaseParticles().ParticlesBound();
         count_.reset((n + 2) * sizeof(uint32_t));
         slice_offset_.reset(((n + 31) / 32 + 2) * sizeof(uint32_t));
         capacity_ = n + 1; // relation_ck.hpp:17,28-31: the first exec always grows it
@@ -107,6 +107,8 @@ class RelationBase
         s.tar_list = tcl.view();
         s.is_inner = is_inner_ ? 1 : 0;
         s.search_depth = search_depth_;
+        s.src_begin = (uint32_t)source_.getBaseParticles().activeBegin();
+        s.src_end = (uint32_t)source_.getBaseParticles().activeEnd();
         s.cell_ordered = (source_.isCellOrdered() && target_.isCellOrdered()) ? 1 : 0;
         return s;
     }

@@ -6,6 +6,7 @@
 #define SPHINXSYS_CK_DAMBREAK_CASE_H
 
 #include "sphinxsys_ck.h"
+#include "slab_decomposition.h"
 
 namespace SPH
 {
@@ -19,6 +20,8 @@ struct DamBreakParameters
     bool fused_time_step = true;
     bool fused_regularization = true;
     int sort_interval = 100;   // :217-220
+    // slab decomposition over the GPUs of one node (needs sphb200_comm_create on this process's context first)
+    int rank = 0, nranks = 1;
     static DamBreakParameters twoDimensional(double dp = 0.025)
     {
         DamBreakParameters p;
@@ -74,6 +77,8 @@ class DamBreakCK
     std::unique_ptr<ReduceDynamicsCK<P, fluid_dynamics::AdvectionTimeStepCK>> fluid_advection_time_step;
     std::unique_ptr<ReduceDynamicsCK<P, fluid_dynamics::AcousticTimeStepCK<WeaklyCompressibleFluid>>> fluid_acoustic_time_step;
     std::unique_ptr<ReduceDynamicsCK<P, TotalMechanicalEnergyCK>> record_water_mechanical_energy;
+    std::unique_ptr<SlabDecomposition> decomposition; // nranks > 1 only
+    fluid_dynamics::AcousticStep1stHalfPhases *first_half_phases_ = nullptr;
     SingleVariable<Real> *sv_physical_time = nullptr;
     size_t number_of_iterations = 0, acoustic_steps = 0;
     double physical_time = 0; // accumulated in double for reporting; the SingleVariable keeps the Real copy
@@ -111,7 +116,37 @@ class DamBreakCK
         }
         Real vol = Real(std::pow(Real(q.dp), Real(q.dim)));
         water_block.defineMatterMaterial<WeaklyCompressibleFluid>(Real(q.rho0_f), c_f_);
-        if (fluid_positions) water_block.generateParticlesFromPositions(*fluid_positions, vol);
+        std::vector<int> cuts;
+        if (q.nranks > 1)
+        {
+            // every rank generates the global lattice, keeps the particles of its own cell planes and their global numbers
+            if (q.correction) throw SphError("slab decomposition: LinearCorrectionCK variants are not decomposed yet");
+            std::vector<Vecd> all = fluid_positions ? *fluid_positions
+                                                    : generateLattice(water_block.getInitialShape(), sph_system.system_domain_bounds_, Real(q.dp), q.dim);
+            SPHAdaptation &ad = water_block.getSPHAdaptation();
+            sphb200_mesh_t mesh = makeMesh(sph_system.system_domain_bounds_, ad.CutOffRadius(), 2, q.dim);
+            std::vector<uint64_t> per_plane(mesh.cells[0], 0);
+            std::vector<int> plane(all.size());
+            for (size_t i = 0; i < all.size(); ++i)
+            {
+                plane[i] = hostCellCoordinate(all[i].x, mesh.lower[0], mesh.spacing, mesh.cells[0]);
+                per_plane[plane[i]]++;
+            }
+            cuts = planSlabCuts(per_plane, q.nranks);
+            std::vector<Vecd> own;
+            std::vector<UnsignedInt> ids;
+            uint64_t max_plane = 0;
+            for (uint64_t c : per_plane) max_plane = std::max(max_plane, c);
+            for (size_t i = 0; i < all.size(); ++i)
+                if (plane[i] >= cuts[q.rank] && plane[i] < cuts[q.rank + 1])
+                {
+                    own.push_back(all[i]);
+                    ids.push_back((UnsignedInt)i);
+                }
+            size_t bound = own.size() + own.size() / 4 + 8 * (size_t)max_plane + 4096;
+            water_block.generateParticlesFromPositions(own, vol, bound, &ids);
+        }
+        else if (fluid_positions) water_block.generateParticlesFromPositions(*fluid_positions, vol);
         else water_block.generateParticles<BaseParticles, Lattice>();
         wall_boundary.defineMatterMaterial<Solid>();
         if (wall_positions) wall_boundary.generateParticlesFromPositions(*wall_positions, vol);
@@ -153,13 +188,22 @@ class DamBreakCK
         fluid_advection_time_step.reset(new ReduceDynamicsCK<P, AdvectionTimeStepCK>(water_block, U_f_));
         record_water_mechanical_energy.reset(new ReduceDynamicsCK<P, TotalMechanicalEnergyCK>(water_block, gravity));
         sv_physical_time = sph_system.getSystemVariableByName<Real>("PhysicalTime");
+        first_half_phases_ = dynamic_cast<fluid_dynamics::AcousticStep1stHalfPhases *>(fluid_acoustic_step_1st_half.get());
+        if (q.nranks > 1)
+        {
+            decomposition.reset(new SlabDecomposition(water_block, q.rank, q.nranks, cuts));
+            fluid_advection_time_step->setDecomposition(decomposition.get());
+            fluid_acoustic_time_step->setDecomposition(decomposition.get());
+            record_water_mechanical_energy->setDecomposition(decomposition.get());
+        }
     }
 
     // dambreak.cpp:152-160
     void initialize()
     {
         constant_gravity->exec();
-        water_cell_linked_list->exec();
+        if (decomposition) decomposition->rebuild();
+        else water_cell_linked_list->exec();
         wall_cell_linked_list->exec();
         water_block_update_complex_relation->exec();
         fluid_acoustic_time_step->setPrimed(false);
@@ -171,14 +215,24 @@ class DamBreakCK
         fluid_density_summation->exec();
         if (!q_.fused_regularization) fluid_density_regularization->exec();
         water_advection_step_setup->exec();
+        if (decomposition) decomposition->refreshGhosts({"VolumetricMeasure"}); // neighbours read V_j of ghost particles
         Real advection_dt = fluid_advection_time_step->exec();
         if (q_.correction) fluid_linear_correction_matrix->exec();
         Real relaxation_time = 0, acoustic_dt = 0;
         int n_inner = 0;
         while (relaxation_time < advection_dt)
         {
-            acoustic_dt = fluid_acoustic_time_step->exec();
-            fluid_acoustic_step_1st_half->exec(acoustic_dt);
+            acoustic_dt = fluid_acoustic_time_step->exec(); // global max when decomposed
+            if (decomposition)
+            {
+                // the two neighbour-read variables of the half steps are refreshed on the ghost planes in between
+                first_half_phases_->deviceInitialize(acoustic_dt);
+                decomposition->refreshGhosts({"Pressure"});
+                first_half_phases_->deviceInteractAndUpdate(acoustic_dt);
+                decomposition->refreshGhosts({"Velocity"});
+            }
+            else
+                fluid_acoustic_step_1st_half->exec(acoustic_dt);
             fluid_acoustic_step_2nd_half->exec(acoustic_dt);
             relaxation_time += acoustic_dt;
             physical_time += acoustic_dt;
@@ -188,12 +242,14 @@ class DamBreakCK
         acoustic_steps += n_inner;
         water_update_particle_position->exec();
         number_of_iterations++;
-        if (q_.sort_interval > 0 && number_of_iterations % q_.sort_interval == 0 && number_of_iterations != 1)
+        // decomposed runs keep the initial global numbering (ParticleSortCK only renumbers: storage is cell ordered anyway)
+        if (!decomposition && q_.sort_interval > 0 && number_of_iterations % q_.sort_interval == 0 && number_of_iterations != 1)
         {
             particle_sort->exec();
             fluid_acoustic_time_step->setPrimed(false); // Force/ForcePrior pairing changed (see ParticleSortCK)
         }
-        water_cell_linked_list->exec();
+        if (decomposition) decomposition->rebuild(); // migration + ghost planes + cell-linked list
+        else water_cell_linked_list->exec();
         water_block_update_complex_relation->exec();
         last_acoustic_dt = acoustic_dt;
         last_advection_dt = advection_dt;

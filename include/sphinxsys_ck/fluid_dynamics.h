@@ -18,6 +18,7 @@
 #define SPHINXSYS_CK_FLUID_DYNAMICS_H
 
 #include "configuration.h"
+#include "slab_decomposition.h"
 
 namespace SPH
 {
@@ -127,8 +128,10 @@ class FluidDynamicsBase
     BaseParticles &particles_;
     RelationBase *inner_ = nullptr, *contact_ = nullptr;
     int riemann_ = 1, correction_ = 0, free_surface_ = 1;
+    SlabDecomposition *decomposition_ = nullptr; // reductions become global when set
 
   public:
+    void setDecomposition(SlabDecomposition *d) { decomposition_ = d; }
     explicit FluidDynamicsBase(SPHBody &body) : sph_body_(body), particles_(body.getBaseParticles()) {}
     FluidDynamicsBase(RelationBase &inner, RelationBase *contact)
         : sph_body_(inner.source_), particles_(inner.source_.getBaseParticles()), inner_(&inner), contact_(contact) {}
@@ -189,6 +192,8 @@ class FluidDynamicsBase
         f.compression_sum = (float *)p.deviceDataOrNull<Real>("CompressionSummation");
         f.B = (float *)p.deviceDataOrNull<Matd>("LinearCorrectionMatrix");
         f.posvol = (sphb200_vec4_t *)p.deviceDataOrNull<Vecd>("PosVol");
+        f.active_begin = (uint32_t)p.activeBegin();
+        f.active_end = (uint32_t)p.activeEnd();
         return f;
     }
     sphb200_fluid_t material()
@@ -297,6 +302,11 @@ class AdvectionTimeStepCK : public FluidDynamicsBase
         sphb200_fluid_view_t f = fluidView();
         float dt = 0;
         SPHCK_CALL(sphb200_advection_time_step, &f, h_min_, u_ref_, cfl_, &reduced_, &dt, execution_instance().stream());
+        if (decomposition_)
+        {
+            reduced_ = decomposition_->allReduceMax(reduced_);
+            dt = cfl_ * h_min_ / (std::max(std::sqrt(reduced_), u_ref_) + TinyReal); // fluid_time_step_ck.cpp:24-27
+        }
         return dt;
     }
 };
@@ -330,6 +340,7 @@ class AcousticTimeStepBase : public FluidDynamicsBase
         {
             // same 4-byte device->host read the stand-alone reduction ends with (particle_iterators_sycl.h:80-105)
             primed_ = false;
+            if (decomposition_) decomposition_->allReduceMaxDevice(fused_slot_.get<float>());
             ex.check(sphb200_copy_d2h(&reduced_, fused_slot_.get(), sizeof(float), ex.stream()), "sphb200_copy_d2h");
             ex.synchronize();
             return cfl_ * h_min_ / (reduced_ + TinyReal); // FinishDynamics::Result, fluid_time_step_ck.hpp:31-36
@@ -337,6 +348,11 @@ class AcousticTimeStepBase : public FluidDynamicsBase
         sphb200_fluid_args_t a = fluidArgs();
         float dt = 0;
         SPHCK_CALL(sphb200_acoustic_time_step, &a, h_min_, cfl_, &reduced_, &dt, ex.stream());
+        if (decomposition_)
+        {
+            reduced_ = decomposition_->allReduceMax(reduced_);
+            dt = cfl_ * h_min_ / (reduced_ + TinyReal);
+        }
         return dt;
     }
 };
@@ -532,6 +548,7 @@ class TotalMechanicalEnergyCK : public fluid_dynamics::FluidDynamicsBase
         gravity_.toArray(g);
         double e = 0;
         SPHCK_CALL(sphb200_total_mechanical_energy, &f, g, &e, execution_instance().stream());
+        if (decomposition_) e = decomposition_->allReduceSum(e);
         return e;
     }
 };

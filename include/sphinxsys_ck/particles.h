@@ -158,14 +158,33 @@ class BaseParticles
     uint64_t storage_version_ = 1, inverse_version_ = 0;
     bool identity_order_ = true; // ReferenceID == iota (no reorder happened yet)
 
+    size_t active_begin_ = 0, active_end_ = 0; // slots the dynamics update (own particles of a decomposed run)
+
   public:
-    explicit BaseParticles(size_t n) : total_real_particles_(n), particles_bound_(n)
+    // n particles now, room for `bound` (>= n): ghost and migrated particles of a decomposed run live behind / around
+    // the real ones, as the reference keeps buffer and ghost particles behind the real ones (base_particles.h:67-72)
+    explicit BaseParticles(size_t n, size_t bound = 0) : total_real_particles_(n), particles_bound_(std::max(n, bound))
     {
+        active_end_ = n;
         dv_reference_id_ = registerStateVariable<UnsignedInt>("ReferenceID");
-        SPHCK_CALL(sphb200_iota_u32, (uint32_t *)dv_reference_id_->deviceAddress(), n + 1, execution_instance().stream());
+        SPHCK_CALL(sphb200_iota_u32, (uint32_t *)dv_reference_id_->deviceAddress(), particles_bound_ + 1, execution_instance().stream());
     }
+    // number of stored particles (own + ghosts in a decomposed run)
     size_t TotalRealParticles() const { return total_real_particles_; }
     size_t ParticlesBound() const { return particles_bound_; }
+    void setTotalRealParticles(size_t n)
+    {
+        if (n > particles_bound_) throw SphError("particle storage exhausted: " + std::to_string(n) + " > bound " + std::to_string(particles_bound_));
+        total_real_particles_ = n;
+    }
+    size_t activeBegin() const { return active_begin_; }
+    size_t activeEnd() const { return active_end_; }
+    void setActiveRange(size_t b, size_t e)
+    {
+        active_begin_ = b;
+        active_end_ = e;
+    }
+    const std::vector<DiscreteVariableBase *> &allVariablesInOrder() const { return ordered_; }
     uint64_t storageVersion() const { return storage_version_; }
 
     template <class T> DiscreteVariable<T> *registerStateVariable(const std::string &name, const T &init = T())
@@ -233,6 +252,20 @@ class BaseParticles
     {
         ++storage_version_;
         identity_order_ = false;
+    }
+    // raw copy of the slots [begin, begin + count) of a variable (storage order; Vecd comes as float4)
+    void downloadRaw(DiscreteVariableBase *v, void *host, size_t begin, size_t count)
+    {
+        ExecutionInstance &ex = execution_instance();
+        const uint32_t eb = v->deviceElementBytes();
+        if (count) ex.check(sphb200_copy_d2h(host, (const char *)v->deviceAddress() + begin * eb, count * eb, ex.stream()), "sphb200_copy_d2h");
+        ex.synchronize();
+    }
+    DiscreteVariableBase *findVariable(const std::string &name)
+    {
+        auto it = all_variables_.find(name);
+        if (it == all_variables_.end()) throw SphError("the variable '" + name + "' is not registered");
+        return it->second.get();
     }
     uint32_t *referenceID() { return (uint32_t *)dv_reference_id_->deviceAddress(); }
     DiscreteVariable<UnsignedInt> *referenceIDVariable() { return dv_reference_id_; }
@@ -453,10 +486,13 @@ class SPHBody
         generateParticlesFromPositions(pos, vol);
     }
     // positions handed over by the caller (e.g. a reload file): base_particles.cpp:33-36, base_material.cpp:37-40
-    void generateParticlesFromPositions(const std::vector<Vecd> &pos, Real vol)
+    // `bound` reserves room for migrated and ghost particles; `reference_ids` (optional) are the global particle
+    // numbers of a decomposed run (default: 0..n-1)
+    void generateParticlesFromPositions(const std::vector<Vecd> &pos, Real vol, size_t bound = 0,
+                                        const std::vector<UnsignedInt> *reference_ids = nullptr)
     {
         size_t n = pos.size();
-        particles_.reset(new BaseParticles(n));
+        particles_.reset(new BaseParticles(n, bound));
         BaseParticles &p = *particles_;
         auto *dv_pos = p.registerStateVariable<Vecd>("Position");
         auto *dv_vol = p.registerStateVariable<Real>("VolumetricMeasure", vol);
@@ -467,6 +503,13 @@ class SPHBody
         p.registerStateVariable<Real>("Mass", rho0 * vol);
         auto *dv_oid = p.registerStateVariable<UnsignedInt>("OriginalID");
         SPHCK_CALL(sphb200_iota_u32, (uint32_t *)dv_oid->deviceAddress(), n + 1, execution_instance().stream());
+        if (reference_ids && n)
+        {
+            ExecutionInstance &ex = execution_instance();
+            ex.check(sphb200_copy_h2d(p.referenceID(), reference_ids->data(), n * sizeof(UnsignedInt), ex.stream()), "sphb200_copy_h2d");
+            ex.check(sphb200_copy_h2d(dv_oid->deviceAddress(), reference_ids->data(), n * sizeof(UnsignedInt), ex.stream()), "sphb200_copy_h2d");
+            ex.synchronize();
+        }
         p.addEvolvingVariable<Vecd>("Position");
         p.addEvolvingVariable<Real>("VolumetricMeasure");
         p.addEvolvingVariable<UnsignedInt>("OriginalID");

@@ -1,0 +1,254 @@
+// sphinxsys_ck/slab_decomposition.h — 1-D slab domain decomposition of a fluid body over the GPUs of one node.
+// NEW functionality (the reference has no distributed path). One process per GPU.
+//
+// * Every rank keeps the GLOBAL mesh, so cell ids are the single-GPU ones; rank r owns the cell planes
+//   [cut[r], cut[r+1]) along x (the slowest cell axis) and keeps a full copy of the static wall body.
+// * Storage stays cell ordered: `left ghost plane | own planes | right ghost plane`. A cell plane is therefore ONE
+//   contiguous slot range of every variable array, in the same particle order on the sender and on the receiver
+//   (in-cell order = ascending global ReferenceID), so halo refresh is a grouped ncclSend/ncclRecv out of and into the
+//   variable arrays themselves — no pack/unpack kernels, no index maps.
+// * rebuild() replaces UpdateCellLinkedList::exec() once per advection step: sort the own particles by their new cell,
+//   hand the planes next to each cut (particles that left the slab + the boundary plane) to the neighbour in one
+//   message per variable, append what arrives, sort again. Particles move less than one cell per advection step (CFL),
+//   so leavers are always in the plane next to the cut. Dynamics then run on the active slot range only.
+// * Cuts are particle-count quantiles of the initial distribution along x (planSlabCuts); they stay fixed in this
+//   round (dynamic re-cutting at sort time is listed as next in DESIGN.md §6).
+#ifndef SPHINXSYS_CK_SLAB_DECOMPOSITION_H
+#define SPHINXSYS_CK_SLAB_DECOMPOSITION_H
+
+#include <algorithm>
+
+#include "configuration.h"
+
+namespace SPH
+{
+// Mesh::CellIndexFromPosition along one axis on the host, same arithmetic as the device (base_mesh.hxx:9-15)
+inline int hostCellCoordinate(Real x, Real lower, Real spacing, int cells)
+{
+    Real t = x - lower;
+    Real u = t / spacing;
+    int k = (int)std::floor(u);
+    return std::min(std::max(k, 0), cells - 1);
+}
+
+// Cell-plane cuts cut[0..nranks] with cut[0] = 0, cut[nranks] = planes: every rank gets whole planes and, as far as
+// whole planes allow, the same number of particles. Ranks never get an empty plane range.
+inline std::vector<int> planSlabCuts(const std::vector<uint64_t> &particles_per_plane, int nranks)
+{
+    const int planes = (int)particles_per_plane.size();
+    if (nranks < 1 || planes < nranks) throw SphError("planSlabCuts: fewer cell planes than ranks");
+    uint64_t total = 0;
+    for (uint64_t c : particles_per_plane) total += c;
+    std::vector<int> cut(nranks + 1, 0);
+    cut[nranks] = planes;
+    uint64_t cum = 0;
+    int p = 0;
+    for (int r = 1; r < nranks; ++r)
+    {
+        // smallest plane index whose cumulative count reaches r/nranks of the total
+        const double target = double(total) * double(r) / double(nranks);
+        while (p < planes && double(cum + particles_per_plane[p]) <= target) cum += particles_per_plane[p++];
+        // choose the nearer side of the plane that straddles the target
+        int c = p;
+        if (p < planes && (target - double(cum)) > (double(cum + particles_per_plane[p]) - target)) c = p + 1;
+        c = std::max(c, cut[r - 1] + 1);               // at least one plane per rank
+        c = std::min(c, planes - (nranks - r));        // leave one plane for each remaining rank
+        cut[r] = c;
+        while (p < c) cum += particles_per_plane[p++];
+    }
+    return cut;
+}
+
+class SlabDecomposition
+{
+    SPHBody &body_;
+    int rank_, nranks_;
+    std::vector<int> cuts_;
+    uint32_t plane_cells_; // cells per x plane (ny * nz)
+    // slot offsets after the last rebuild: ghosts [0, a0) | first own plane [a0, f1) ... last own plane [l0, a1) | ghosts [a1, n)
+    uint32_t a0_ = 0, f1_ = 0, l0_ = 0, a1_ = 0, n_ = 0;
+    DeviceBuffer scalars_; // small device scratch for counts and reductions
+    uint64_t migrated_out_ = 0, ghost_particles_ = 0;
+
+    uint32_t readOffset(uint32_t cell)
+    {
+        uint32_t v = 0;
+        ExecutionInstance &ex = execution_instance();
+        ex.check(sphb200_copy_d2h(&v, body_.getCellLinkedList().cell_offset_.get<uint32_t>() + cell, sizeof(uint32_t), ex.stream()), "sphb200_copy_d2h");
+        ex.synchronize();
+        return v;
+    }
+    void readOffsets(const uint32_t *cells, uint32_t *out, int count)
+    {
+        ExecutionInstance &ex = execution_instance();
+        for (int k = 0; k < count; ++k)
+            ex.check(sphb200_copy_d2h(out + k, body_.getCellLinkedList().cell_offset_.get<uint32_t>() + cells[k], sizeof(uint32_t), ex.stream()), "sphb200_copy_d2h");
+        ex.synchronize();
+    }
+    // cell-list build + storage reorder of the slots [begin, begin + n) into [0, n)
+    void reorder(uint32_t begin, uint32_t n)
+    {
+        BaseParticles &p = body_.getBaseParticles();
+        CellLinkedList &cl = body_.getCellLinkedList();
+        std::vector<DiscreteVariableBase *> vars = p.reorderedVariables();
+        std::vector<void *> dst(vars.size());
+        std::vector<const void *> src(vars.size());
+        std::vector<uint32_t> bytes(vars.size());
+        for (size_t k = 0; k < vars.size(); ++k)
+        {
+            bytes[k] = vars[k]->deviceElementBytes();
+            dst[k] = vars[k]->shadowAddress();
+            src[k] = (const char *)vars[k]->deviceAddress() + (size_t)begin * bytes[k];
+        }
+        SPHCK_CALL(sphb200_cell_list_build_reorder, &cl.mesh_, (const sphb200_vec4_t *)p.deviceData<Vecd>("Position") + begin, n,
+                   p.referenceID() + begin, cl.view(), (int)vars.size(), dst.data(), src.data(), bytes.data(),
+                   execution_instance().stream());
+        for (auto *v : vars) v->swapWithShadow();
+        p.storageReordered();
+    }
+
+  public:
+    SlabDecomposition(SPHBody &body, int rank, int nranks, const std::vector<int> &cuts)
+        : body_(body), rank_(rank), nranks_(nranks), cuts_(cuts), scalars_(256)
+    {
+        const sphb200_mesh_t &m = body.getCellLinkedList().mesh_;
+        plane_cells_ = (uint32_t)m.cells[1] * (uint32_t)m.cells[2];
+        if ((int)cuts.size() != nranks + 1 || cuts.front() != 0 || cuts.back() != m.cells[0])
+            throw SphError("SlabDecomposition: cuts must run from 0 to the number of x planes");
+        BaseParticles &p = body.getBaseParticles();
+        n_ = (uint32_t)p.TotalRealParticles();
+        a0_ = 0;
+        a1_ = n_;
+        p.setActiveRange(a0_, a1_);
+    }
+    int rank() const { return rank_; }
+    int size() const { return nranks_; }
+    const std::vector<int> &cuts() const { return cuts_; }
+    uint32_t ownParticles() const { return a1_ - a0_; }
+    uint32_t ownBegin() const { return a0_; }
+    uint32_t storedParticles() const { return n_; }
+    uint64_t ghostParticles() const { return ghost_particles_; }
+    uint64_t migratedOut() const { return migrated_out_; }
+
+    // once per advection step, instead of UpdateCellLinkedList::exec()
+    void rebuild()
+    {
+        ExecutionInstance &ex = execution_instance();
+        BaseParticles &p = body_.getBaseParticles();
+        void *st = ex.stream();
+        const uint32_t n_old = a1_ - a0_;
+        // 1. own particles into their new cell order, at the front of the arrays (old ghosts are dropped)
+        reorder(a0_, n_old);
+        const uint32_t X0 = (uint32_t)cuts_[rank_], X1 = (uint32_t)cuts_[rank_ + 1];
+        uint32_t cells[2] = {(X0 + 1) * plane_cells_, (X1 - 1) * plane_cells_}, off[2];
+        readOffsets(cells, off, 2);
+        // left message: slots [0, off[0]) = particles that moved into plane X0-1 + the first own plane;
+        // right message: slots [off[1], n_old) = the last own plane + particles that moved into plane X1
+        const uint32_t send_l = rank_ > 0 ? off[0] : 0, send_r = rank_ + 1 < nranks_ ? n_old - off[1] : 0;
+        // 2. sizes
+        uint64_t host_counts[4] = {send_l, send_r, 0, 0};
+        uint64_t *d = scalars_.get<uint64_t>();
+        ex.check(sphb200_copy_h2d(d, host_counts, sizeof(host_counts), st), "sphb200_copy_h2d");
+        {
+            const void *sl[1] = {d}, *sr[1] = {d + 1};
+            void *rl[1] = {d + 2}, *rr[1] = {d + 3};
+            size_t b[1] = {sizeof(uint64_t)};
+            SPHCK_CALL(sphb200_comm_exchange, 1, sl, b, rl, b, sr, b, rr, b, st);
+        }
+        ex.check(sphb200_copy_d2h(host_counts, d, sizeof(host_counts), st), "sphb200_copy_d2h");
+        ex.synchronize();
+        const uint32_t recv_l = rank_ > 0 ? (uint32_t)host_counts[2] : 0, recv_r = rank_ + 1 < nranks_ ? (uint32_t)host_counts[3] : 0;
+        const size_t n_tot = (size_t)n_old + recv_l + recv_r;
+        p.setTotalRealParticles(n_tot); // throws if the reserved storage is exhausted
+        // 3. payload: every stored variable, one contiguous segment per variable and direction
+        {
+            std::vector<DiscreteVariableBase *> vars = p.reorderedVariables();
+            const size_t k = vars.size();
+            std::vector<const void *> sl(k), sr(k);
+            std::vector<void *> rl(k), rr(k);
+            std::vector<size_t> bsl(k), bsr(k), brl(k), brr(k);
+            for (size_t i = 0; i < k; ++i)
+            {
+                const size_t eb = vars[i]->deviceElementBytes();
+                char *base = (char *)vars[i]->deviceAddress();
+                sl[i] = base;
+                bsl[i] = send_l * eb;
+                sr[i] = base + (size_t)off[1] * eb;
+                bsr[i] = send_r * eb;
+                rl[i] = base + (size_t)n_old * eb;
+                brl[i] = recv_l * eb;
+                rr[i] = base + ((size_t)n_old + recv_l) * eb;
+                brr[i] = recv_r * eb;
+            }
+            SPHCK_CALL(sphb200_comm_exchange, (int)k, sl.data(), bsl.data(), rl.data(), brl.data(), sr.data(), bsr.data(), rr.data(),
+                       brr.data(), st);
+        }
+        // 4. everything into cell order; own particles are the planes [X0, X1)
+        reorder(0, (uint32_t)n_tot);
+        uint32_t cells2[4] = {X0 * plane_cells_, (X0 + 1) * plane_cells_, (X1 - 1) * plane_cells_, X1 * plane_cells_}, off2[4];
+        readOffsets(cells2, off2, 4);
+        a0_ = off2[0];
+        f1_ = off2[1];
+        l0_ = off2[2];
+        a1_ = off2[3];
+        n_ = (uint32_t)n_tot;
+        p.setActiveRange(a0_, a1_);
+        body_.setCellOrdered(true);
+        body_.setPosVolDirty();
+        ghost_particles_ = (uint64_t)a0_ + (n_ - a1_);
+        migrated_out_ += (uint64_t)(send_l - std::min(send_l, f1_ - a0_)); // rough: leavers are what was sent beyond the plane
+    }
+
+    // refresh named variables on the ghost planes from their owners (contiguous ranges, in place)
+    void refreshGhosts(std::initializer_list<const char *> names)
+    {
+        BaseParticles &p = body_.getBaseParticles();
+        const size_t k = names.size();
+        std::vector<const void *> sl(k), sr(k);
+        std::vector<void *> rl(k), rr(k);
+        std::vector<size_t> bsl(k), bsr(k), brl(k), brr(k);
+        size_t i = 0;
+        for (const char *nm : names)
+        {
+            DiscreteVariableBase *v = p.findVariable(nm);
+            const size_t eb = v->deviceElementBytes();
+            char *base = (char *)v->deviceAddress();
+            sl[i] = base + (size_t)a0_ * eb;             // my first plane -> left neighbour's right ghosts
+            bsl[i] = (size_t)(f1_ - a0_) * eb;
+            sr[i] = base + (size_t)l0_ * eb;             // my last plane -> right neighbour's left ghosts
+            bsr[i] = (size_t)(a1_ - l0_) * eb;
+            rl[i] = base;                                // left ghosts [0, a0)
+            brl[i] = (size_t)a0_ * eb;
+            rr[i] = base + (size_t)a1_ * eb;             // right ghosts [a1, n)
+            brr[i] = (size_t)(n_ - a1_) * eb;
+            ++i;
+        }
+        SPHCK_CALL(sphb200_comm_exchange, (int)k, sl.data(), bsl.data(), rl.data(), brl.data(), sr.data(), bsr.data(), rr.data(),
+                   brr.data(), execution_instance().stream());
+    }
+
+    Real allReduceMax(Real v)
+    {
+        ExecutionInstance &ex = execution_instance();
+        float *d = scalars_.get<float>() + 16;
+        ex.check(sphb200_copy_h2d(d, &v, sizeof(float), ex.stream()), "sphb200_copy_h2d");
+        SPHCK_CALL(sphb200_comm_allreduce_max_f32, d, 1, ex.stream());
+        ex.check(sphb200_copy_d2h(&v, d, sizeof(float), ex.stream()), "sphb200_copy_d2h");
+        ex.synchronize();
+        return v;
+    }
+    // in place on a device float (the fused acoustic-dt slot)
+    void allReduceMaxDevice(float *dev) { SPHCK_CALL(sphb200_comm_allreduce_max_f32, dev, 1, execution_instance().stream()); }
+    double allReduceSum(double v)
+    {
+        ExecutionInstance &ex = execution_instance();
+        double *d = scalars_.get<double>() + 16;
+        ex.check(sphb200_copy_h2d(d, &v, sizeof(double), ex.stream()), "sphb200_copy_h2d");
+        SPHCK_CALL(sphb200_comm_allreduce_sum_f64, d, 1, ex.stream());
+        ex.check(sphb200_copy_d2h(&v, d, sizeof(double), ex.stream()), "sphb200_copy_d2h");
+        ex.synchronize();
+        return v;
+    }
+};
+} // namespace SPH
+#endif

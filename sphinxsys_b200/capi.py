@@ -40,7 +40,8 @@ _P = C.c_void_p
 class FluidView(C.Structure):
     _fields_ = [("n", C.c_uint32), ("pos", _P), ("vel", _P), ("dpos", _P), ("force", _P), ("force_prior", _P),
                 ("vol", _P), ("mass", _P), ("rho", _P), ("p", _P), ("compression", _P), ("compression_rate", _P),
-                ("vol_ref", _P), ("compression_sum", _P), ("B", _P), ("posvol", _P)]
+                ("vol_ref", _P), ("compression_sum", _P), ("B", _P), ("posvol", _P),
+                ("active_begin", C.c_uint32), ("active_end", C.c_uint32)]
 
 
 class WallView(C.Structure):
@@ -59,7 +60,7 @@ class RelationT(C.Structure):
 class SearchT(C.Structure):
     _fields_ = [("tar_mesh", MeshT), ("kernel", KernelT), ("src_pos", _P), ("n_src", C.c_uint32), ("src_order", _P),
                 ("src_sorted_pos", _P), ("tar_pos", _P), ("tar_list", CellListT), ("is_inner", C.c_int32),
-                ("search_depth", C.c_int32), ("cell_ordered", C.c_int32)]
+                ("search_depth", C.c_int32), ("src_begin", C.c_uint32), ("src_end", C.c_uint32), ("cell_ordered", C.c_int32)]
 
 
 class FluidArgs(C.Structure):
@@ -114,6 +115,15 @@ SYMBOLS = {
     "sphb200_acoustic_1st_half_initialize": (_I, [_CTX, C.POINTER(FluidArgs), _F, _P]),
     "sphb200_acoustic_1st_half_interact": (_I, [_CTX, C.POINTER(FluidArgs), _F, _I, _P]),
     "sphb200_linear_correction_matrix": (_I, [_CTX, C.POINTER(FluidArgs), _F, _P]),
+    "sphb200_comm_unique_id": (_I, [_P]),
+    "sphb200_comm_create": (_I, [_CTX, _I, _I, _P]),
+    "sphb200_comm_destroy": (_I, [_CTX]),
+    "sphb200_comm_rank": (_I, [_CTX]),
+    "sphb200_comm_size": (_I, [_CTX]),
+    "sphb200_comm_exchange": (_I, [_CTX, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "sphb200_comm_allreduce_max_f32": (_I, [_CTX, _P, _I, _P]),
+    "sphb200_comm_allreduce_sum_f64": (_I, [_CTX, _P, _I, _P]),
+    "sphb200_comm_allgather_u64": (_I, [_CTX, _P, _P, _I, _P]),
     "sphb200_total_mechanical_energy": (_I, [_CTX, C.POINTER(FluidView), C.POINTER(_F * 3), C.POINTER(C.c_double), _P]),
 }
 

@@ -22,6 +22,9 @@ struct sphb200_context
     // small pinned host block + device scalar block for value-returning calls
     void *host_pinned; // 256 B
     void *dev_scalars; // 256 B
+    // slab-decomposed runs: NCCL communicator (comm.cu), null for single-GPU use
+    void *comm;
+    int rank, nranks;
 };
 
 #define SPH_CHECK_ARG(ctx, cond, msg)                                                              \

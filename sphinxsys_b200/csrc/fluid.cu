@@ -32,6 +32,7 @@ struct FArgs
 {
     // fluid
     u32 n;
+    u32 begin, end; // active slots [begin, end): ghost slots outside are read as neighbours but never written
     float4 *pos, *vel, *dpos, *force, *force_prior, *posvol;
     float *vol, *mass, *rho, *p, *C, *Cdot, *vol_ref, *Csum, *B;
     // wall
@@ -75,6 +76,13 @@ static int make_fargs(sphb200_context *ctx, const sphb200_fluid_args_t *s, FArgs
 {
     const sphb200_fluid_view_t &f = s->fluid;
     a->n = f.n;
+    a->begin = f.active_end ? f.active_begin : 0u;
+    a->end = f.active_end ? f.active_end : f.n;
+    if (a->begin > a->end || a->end > f.n)
+    {
+        snprintf(ctx->err, sizeof(ctx->err), "active range [%u, %u) outside [0, %u)", a->begin, a->end, f.n);
+        return SPHB200_E_INVALID;
+    }
     a->pos = (float4 *)f.pos; a->vel = (float4 *)f.vel; a->dpos = (float4 *)f.dpos;
     a->force = (float4 *)f.force; a->force_prior = (float4 *)f.force_prior; a->posvol = (float4 *)f.posvol;
     a->vol = f.vol; a->mass = f.mass; a->rho = f.rho; a->p = f.p; a->C = f.compression; a->Cdot = f.compression_rate;
@@ -128,6 +136,11 @@ static int make_fargs(sphb200_context *ctx, const sphb200_fluid_args_t *s, FArgs
     a->dim = k.dim;
     return 0;
 }
+
+// slot handled by this thread: launches start at the 32-aligned slot below `begin` so that lane == slot % 32
+// (the SELL-32 relation layout relies on it)
+__device__ __forceinline__ u32 active_slot(const FArgs &a) { return (a.begin & ~31u) + blockIdx.x * blockDim.x + threadIdx.x; }
+static inline unsigned active_blocks(const FArgs &a, unsigned threads) { return sph_blocks(a.end - (a.begin & ~31u), threads); }
 
 __device__ __forceinline__ void stage_tab(const KTab &src, float4 *dst)
 {
@@ -183,8 +196,20 @@ template <int RIEMANN> __device__ __forceinline__ float pjump(const FArgs &a, fl
 }
 
 // =====================================================================================================
-// simple per-particle dynamics
+// simple per-particle dynamics (run on the active slot range of the view: pointers are shifted by `b`)
 // =====================================================================================================
+struct Range
+{
+    u32 b, n;
+};
+static inline Range active_range(const sphb200_fluid_view_t *f)
+{
+    Range r;
+    r.b = f->active_end ? f->active_begin : 0u;
+    u32 e = f->active_end ? f->active_end : f->n;
+    r.n = e > r.b ? e - r.b : 0u;
+    return r;
+}
 __global__ void __launch_bounds__(256)
     k_gravity(u32 n, const float *__restrict__ mass, float4 *__restrict__ force_prior, float4 *__restrict__ prev, float gx,
               float gy, float gz)
@@ -202,9 +227,10 @@ extern "C" int sphb200_gravity_force(sphb200_context_t *ctx, const sphb200_fluid
                                      sphb200_vec4_t *previous_force, void *stream)
 {
     SPH_CHECK_ARG(ctx, ctx && f && g && previous_force && f->mass && f->force_prior, "null pointer");
-    if (f->n)
-        SPH_LAUNCH(ctx, k_gravity, sph_blocks(f->n, 256), 256, 0, stream, f->n, f->mass, (float4 *)f->force_prior,
-                   (float4 *)previous_force, g[0], g[1], g[2]);
+    Range r = active_range(f);
+    if (r.n)
+        SPH_LAUNCH(ctx, k_gravity, sph_blocks(r.n, 256), 256, 0, stream, r.n, f->mass + r.b, (float4 *)f->force_prior + r.b,
+                   (float4 *)previous_force + r.b, g[0], g[1], g[2]);
     return 0;
 }
 
@@ -220,9 +246,10 @@ __global__ void __launch_bounds__(256)
 extern "C" int sphb200_advection_setup(sphb200_context_t *ctx, const sphb200_fluid_view_t *f, void *stream)
 {
     SPH_CHECK_ARG(ctx, ctx && f && f->mass && f->rho && f->vol && f->dpos, "null pointer");
-    if (f->n)
-        SPH_LAUNCH(ctx, k_advection_setup, sph_blocks(f->n, 256), 256, 0, stream, f->n, f->mass, f->rho, f->vol,
-                   (float4 *)f->dpos);
+    Range r = active_range(f);
+    if (r.n)
+        SPH_LAUNCH(ctx, k_advection_setup, sph_blocks(r.n, 256), 256, 0, stream, r.n, f->mass + r.b, f->rho + r.b, f->vol + r.b,
+                   (float4 *)f->dpos + r.b);
     return 0;
 }
 
@@ -237,9 +264,10 @@ __global__ void __launch_bounds__(256) k_update_position(u32 n, float4 *__restri
 extern "C" int sphb200_update_position(sphb200_context_t *ctx, const sphb200_fluid_view_t *f, void *stream)
 {
     SPH_CHECK_ARG(ctx, ctx && f && f->pos && f->dpos, "null pointer");
-    if (f->n)
-        SPH_LAUNCH(ctx, k_update_position, sph_blocks(f->n, 256), 256, 0, stream, f->n, (float4 *)f->pos,
-                   (const float4 *)f->dpos);
+    Range r = active_range(f);
+    if (r.n)
+        SPH_LAUNCH(ctx, k_update_position, sph_blocks(r.n, 256), 256, 0, stream, r.n, (float4 *)f->pos + r.b,
+                   (const float4 *)f->dpos + r.b);
     return 0;
 }
 
@@ -308,8 +336,9 @@ extern "C" int sphb200_advection_time_step(sphb200_context_t *ctx, const sphb200
     SPH_CHECK_ARG(ctx, ctx && f && f->vel, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     SPH_CUDA(ctx, cudaMemsetAsync(ctx->dev_scalars, 0, sizeof(float), st));
-    if (f->n)
-        SPH_LAUNCH(ctx, k_reduce_advection, min(sph_blocks(f->n, 256), 148u * 8u), 256, 0, st, f->n, (const float4 *)f->vel,
+    Range r = active_range(f);
+    if (r.n)
+        SPH_LAUNCH(ctx, k_reduce_advection, min(sph_blocks(r.n, 256), 148u * 8u), 256, 0, st, r.n, (const float4 *)f->vel + r.b,
                    (float *)ctx->dev_scalars);
     float red;
     int rc = read_scalar(ctx, &red, st);
@@ -327,9 +356,10 @@ extern "C" int sphb200_acoustic_time_step(sphb200_context_t *ctx, const sphb200_
     cudaStream_t st = (cudaStream_t)stream;
     const sphb200_fluid_view_t &f = s->fluid;
     SPH_CUDA(ctx, cudaMemsetAsync(ctx->dev_scalars, 0, sizeof(float), st));
-    if (f.n)
-        SPH_LAUNCH(ctx, k_reduce_acoustic, min(sph_blocks(f.n, 256), 148u * 8u), 256, 0, st, f.n, (const float4 *)f.vel,
-                   (const float4 *)f.force, (const float4 *)f.force_prior, f.mass, s->material.c0, h_min,
+    Range r = active_range(&f);
+    if (r.n)
+        SPH_LAUNCH(ctx, k_reduce_acoustic, min(sph_blocks(r.n, 256), 148u * 8u), 256, 0, st, r.n, (const float4 *)f.vel + r.b,
+                   (const float4 *)f.force + r.b, (const float4 *)f.force_prior + r.b, f.mass + r.b, s->material.c0, h_min,
                    (float *)ctx->dev_scalars);
     float red;
     int rc = read_scalar(ctx, &red, st);
@@ -371,9 +401,10 @@ extern "C" int sphb200_total_mechanical_energy(sphb200_context_t *ctx, const sph
     SPH_CHECK_ARG(ctx, ctx && f && g && energy_host && f->pos && f->vel && f->mass, "null pointer");
     cudaStream_t st = (cudaStream_t)stream;
     SPH_CUDA(ctx, cudaMemsetAsync(ctx->dev_scalars, 0, sizeof(double), st));
-    if (f->n)
-        SPH_LAUNCH(ctx, k_energy, min(sph_blocks(f->n, 256), 148u * 4u), 256, 0, st, f->n, (const float4 *)f->pos,
-                   (const float4 *)f->vel, f->mass, g[0], g[1], g[2], (double *)ctx->dev_scalars);
+    Range r = active_range(f);
+    if (r.n)
+        SPH_LAUNCH(ctx, k_energy, min(sph_blocks(r.n, 256), 148u * 4u), 256, 0, st, r.n, (const float4 *)f->pos + r.b,
+                   (const float4 *)f->vel + r.b, f->mass + r.b, g[0], g[1], g[2], (double *)ctx->dev_scalars);
     SPH_CUDA(ctx, cudaMemcpyAsync(ctx->host_pinned, ctx->dev_scalars, sizeof(double), cudaMemcpyDeviceToHost, st));
     SPH_CUDA(ctx, cudaStreamSynchronize(st));
     *energy_host = *(double *)ctx->host_pinned;
@@ -387,8 +418,8 @@ __global__ void __launch_bounds__(FL_THREADS) k_compression_summation(FArgs a, K
 {
     __shared__ float4 tab[KT_SLOTS];
     stage_tab(wtab, tab);
-    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n) return;
+    u32 t = active_slot(a);
+    if (t < a.begin || t >= a.end) return;
     const u32 i = a.order ? a.order[t] : t;
     float4 xi = a.pos[i];
     float s = a.W0 * a.vol_ref[i];
@@ -438,7 +469,7 @@ extern "C" int sphb200_compression_summation(sphb200_context_t *ctx, const sphb2
     SPH_CHECK_ARG(ctx, a.n == 0 || (a.pos && a.vol_ref && a.Csum && a.in_count && a.in_slice && a.in_index), "null fluid array");
     SPH_CHECK_ARG(ctx, !regularize || (a.C && a.rho), "null fluid array");
     SPH_CHECK_ARG(ctx, a.n_wall == 0 || (a.w_pos && a.w_vol_ref && a.ct_count && a.ct_slice && a.ct_index), "null wall array");
-    if (a.n) SPH_LAUNCH(ctx, k_compression_summation, sph_blocks(a.n, FL_THREADS), FL_THREADS, 0, stream, a, wtab, regularize);
+    if (a.end > a.begin) SPH_LAUNCH(ctx, k_compression_summation, active_blocks(a, FL_THREADS), FL_THREADS, 0, stream, a, wtab, regularize);
     return 0;
 }
 
@@ -457,9 +488,10 @@ extern "C" int sphb200_density_regularization(sphb200_context_t *ctx, const sphb
 {
     SPH_CHECK_ARG(ctx, ctx && s && s->fluid.compression_sum && s->fluid.compression && s->fluid.rho, "null pointer");
     const sphb200_fluid_view_t &f = s->fluid;
-    if (f.n)
-        SPH_LAUNCH(ctx, k_density_regularization, sph_blocks(f.n, 256), 256, 0, stream, f.n, f.compression_sum, f.compression,
-                   f.rho, s->material.rho0, s->material.free_surface);
+    Range r = active_range(&f);
+    if (r.n)
+        SPH_LAUNCH(ctx, k_density_regularization, sph_blocks(r.n, 256), 256, 0, stream, r.n, f.compression_sum + r.b,
+                   f.compression + r.b, f.rho + r.b, s->material.rho0, s->material.free_surface);
     return 0;
 }
 
@@ -470,8 +502,8 @@ extern "C" int sphb200_density_regularization(sphb200_context_t *ctx, const sphb
 // neighbours, which must all be post-initialize.
 __global__ void __launch_bounds__(256) k_a1_init(FArgs a, float dt)
 {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
+    u32 i = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.end) return;
     float C = a.C[i] + 0.5f * dt * a.Cdot[i];
     float rho = C * a.rho0;
     a.C[i] = C;
@@ -489,8 +521,8 @@ __global__ void __launch_bounds__(FL_THREADS) k_a1_interact(FArgs a, KTab dwtab,
 {
     __shared__ float4 tab[KT_SLOTS];
     stage_tab(dwtab, tab);
-    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n) return;
+    u32 t = active_slot(a);
+    if (t < a.begin || t >= a.end) return;
     const u32 i = a.order ? a.order[t] : t;
     const float4 xi = a.posvol[i];
     const float p_i = a.p[i];
@@ -614,13 +646,13 @@ extern "C" int sphb200_acoustic_1st_half_initialize(sphb200_context_t *ctx, cons
     if (rc) return rc;
     rc = check_acoustic_args(ctx, a, false);
     if (rc) return rc;
-    if (a.n) SPH_LAUNCH(ctx, k_a1_init, sph_blocks(a.n, 256), 256, 0, stream, a, dt);
+    if (a.end > a.begin) SPH_LAUNCH(ctx, k_a1_init, sph_blocks(a.end - a.begin, 256), 256, 0, stream, a, dt);
     return 0;
 }
 
 template <bool CORR> static int launch_a1(sphb200_context *ctx, const FArgs &a, const KTab &t, int riemann, float dt, int upd, void *stream)
 {
-    unsigned g = sph_blocks(a.n, FL_THREADS);
+    unsigned g = active_blocks(a, FL_THREADS);
     switch (riemann)
     {
     case 0: SPH_LAUNCH(ctx, (k_a1_interact<0, CORR>), g, FL_THREADS, 0, stream, a, t, dt, upd); break;
@@ -641,7 +673,7 @@ extern "C" int sphb200_acoustic_1st_half_interact(sphb200_context_t *ctx, const 
     rc = check_acoustic_args(ctx, a, false);
     if (rc) return rc;
     SPH_CHECK_ARG(ctx, !s->material.correction || a.B, "LinearCorrectionCK needs fluid.B");
-    if (a.n == 0) return 0;
+    if (a.end <= a.begin) return 0;
     return s->material.correction ? launch_a1<true>(ctx, a, dwtab, s->material.riemann, dt, do_update, stream)
                                   : launch_a1<false>(ctx, a, dwtab, s->material.riemann, dt, do_update, stream);
 }
@@ -662,9 +694,9 @@ __global__ void __launch_bounds__(FL_THREADS) k_a2(FArgs a, KTab dwtab, float dt
 {
     __shared__ float4 tab[KT_SLOTS];
     stage_tab(dwtab, tab);
-    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 t = active_slot(a);
     float measure = 0.f;
-    if (t < a.n)
+    if (t >= a.begin && t < a.end)
     {
         const u32 i = a.order ? a.order[t] : t;
         const float4 xi = a.posvol[i];
@@ -762,7 +794,7 @@ __global__ void __launch_bounds__(FL_THREADS) k_a2(FArgs a, KTab dwtab, float dt
 template <bool CORR>
 static int launch_a2(sphb200_context *ctx, const FArgs &a, const KTab &t, int riemann, float dt, float h_min, float *nr, void *stream)
 {
-    unsigned g = sph_blocks(a.n, FL_THREADS);
+    unsigned g = active_blocks(a, FL_THREADS);
     switch (riemann)
     {
     case 0: SPH_LAUNCH(ctx, (k_a2<0, CORR>), g, FL_THREADS, 0, stream, a, t, dt, h_min, nr); break;
@@ -783,7 +815,7 @@ extern "C" int sphb200_acoustic_2nd_half(sphb200_context_t *ctx, const sphb200_f
     rc = check_acoustic_args(ctx, a, true);
     if (rc) return rc;
     SPH_CHECK_ARG(ctx, !s->material.correction || a.B, "LinearCorrectionCK needs fluid.B");
-    if (a.n == 0) return 0;
+    if (a.end <= a.begin) return 0;
     return s->material.correction ? launch_a2<true>(ctx, a, dwtab, s->material.riemann, dt, h_min, next_reduced_dev, stream)
                                   : launch_a2<false>(ctx, a, dwtab, s->material.riemann, dt, h_min, next_reduced_dev, stream);
 }
@@ -808,8 +840,8 @@ __global__ void __launch_bounds__(FL_THREADS) k_linear_correction(FArgs a, KTab 
 {
     __shared__ float4 tab[KT_SLOTS];
     stage_tab(dwtab, tab);
-    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= a.n) return;
+    u32 t = active_slot(a);
+    if (t < a.begin || t >= a.end) return;
     const u32 i = a.order ? a.order[t] : t;
     const float4 xi = a.posvol[i];
     float b[9];
@@ -877,6 +909,6 @@ extern "C" int sphb200_linear_correction_matrix(sphb200_context_t *ctx, const sp
     if (rc) return rc;
     SPH_CHECK_ARG(ctx, a.n == 0 || (a.posvol && a.B && a.in_count && a.in_slice && a.in_index), "null fluid array");
     SPH_CHECK_ARG(ctx, a.n_wall == 0 || (a.w_posvol && a.ct_count && a.ct_slice && a.ct_index), "null wall array");
-    if (a.n) SPH_LAUNCH(ctx, k_linear_correction, sph_blocks(a.n, FL_THREADS), FL_THREADS, 0, stream, a, dwtab, alpha);
+    if (a.end > a.begin) SPH_LAUNCH(ctx, k_linear_correction, active_blocks(a, FL_THREADS), FL_THREADS, 0, stream, a, dwtab, alpha);
     return 0;
 }

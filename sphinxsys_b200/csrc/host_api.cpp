@@ -52,9 +52,66 @@ extern "C"
         int32_t relation_stride;  // < 0: default; 0: exact two-phase build; > 0: one-pass stride
         double system_lower[3], system_upper[3]; // exact system bounds in Real (what the harness used for its lattice)
         int32_t use_system_bounds;
+        int32_t rank, nranks;            // slab decomposition: one process per GPU
+        uint8_t unique_id[128];          // communicator id from sphck_comm_unique_id on rank 0 (nranks > 1)
     };
 
     const char *sphck_last_error() { return g_error.c_str(); }
+    int sphck_comm_unique_id(void *id128) { return sphb200_comm_unique_id(id128); }
+    // decomposed runs: slots [begin, begin + count) hold this rank's own particles; stored = own + ghosts
+    int sphck_own_range(void *hp, uint64_t *begin, uint64_t *count, uint64_t *stored)
+    {
+        return guarded([&] {
+            BaseParticles &p = ((Handle *)hp)->sim->water_block.getBaseParticles();
+            *begin = p.activeBegin();
+            *count = p.activeEnd() - p.activeBegin();
+            *stored = p.TotalRealParticles();
+        });
+    }
+    // raw copy of `count` slots starting at `begin` (storage order, device element layout: Vecd = 4 floats)
+    int sphck_download_raw(void *hp, int which, const char *name, void *out, uint64_t begin, uint64_t count)
+    {
+        return guarded([&] {
+            Handle *h = (Handle *)hp;
+            BaseParticles &p = (which ? (SPHBody &)h->sim->wall_boundary : (SPHBody &)h->sim->water_block).getBaseParticles();
+            p.downloadRaw(p.findVariable(name), out, begin, count);
+        });
+    }
+    // raw upload into `count` slots starting at `begin` (storage order, device element layout)
+    int sphck_upload_raw(void *hp, int which, const char *name, const void *in, uint64_t begin, uint64_t count)
+    {
+        return guarded([&] {
+            Handle *h = (Handle *)hp;
+            SPHBody &b = which ? (SPHBody &)h->sim->wall_boundary : (SPHBody &)h->sim->water_block;
+            BaseParticles &p = b.getBaseParticles();
+            DiscreteVariableBase *v = p.findVariable(name);
+            ExecutionInstance &ex = execution_instance();
+            const size_t eb = v->deviceElementBytes();
+            if (begin + count > p.ParticlesBound()) throw SphError("sphck_upload_raw: range outside the storage");
+            if (count) ex.check(sphb200_copy_h2d((char *)v->deviceAddress() + begin * eb, in, count * eb, ex.stream()), "sphb200_copy_h2d");
+            b.setPosVolDirty();
+            h->sim->fluid_acoustic_time_step->setPrimed(false);
+        });
+    }
+    int sphck_cuts(void *hp, int32_t *out, int capacity)
+    {
+        return guarded([&] {
+            DamBreakCK &s = *((Handle *)hp)->sim;
+            if (!s.decomposition) throw SphError("not a decomposed run");
+            const std::vector<int> &c = s.decomposition->cuts();
+            if ((int)c.size() > capacity) throw SphError("capacity too small");
+            for (size_t i = 0; i < c.size(); ++i) out[i] = c[i];
+        });
+    }
+    // host-only planning helper (no GPU needed): cuts from a particles-per-plane histogram
+    int sphck_plan_slab_cuts(const uint64_t *per_plane, int planes, int nranks, int32_t *cuts_out)
+    {
+        return guarded([&] {
+            std::vector<uint64_t> h(per_plane, per_plane + planes);
+            std::vector<int> c = planSlabCuts(h, nranks);
+            for (size_t i = 0; i < c.size(); ++i) cuts_out[i] = c[i];
+        });
+    }
 
     // fluid_xyz / wall_xyz / wall_normal_xyz may be NULL: the C++ lattice generator and shape normals are used then
     void *sphck_dambreak_create(const sphck_dambreak_options *o, const float *fluid_xyz, uint64_t n_fluid, const float *wall_xyz,
@@ -70,6 +127,10 @@ extern "C"
             q.fused_time_step = o->fused_time_step != 0;
             q.fused_regularization = o->fused_regularization != 0;
             q.sort_interval = o->sort_interval;
+            q.rank = o->rank;
+            q.nranks = o->nranks > 0 ? o->nranks : 1;
+            if (q.nranks > 1)
+                execution_instance().check(sphb200_comm_create(execution_instance().ctx(), q.nranks, q.rank, o->unique_id), "sphb200_comm_create");
             std::vector<Vecd> fp, wp, wn;
             BoundingBoxd sb;
             if (o->use_system_bounds)
@@ -147,6 +208,8 @@ extern "C"
             else if (op == "acoustic_steps") r = (double)s.acoustic_steps;
             else if (op == "outer_steps") r = (double)s.number_of_iterations;
             else if (op == "last_acoustic_dt") r = s.last_acoustic_dt;
+            else if (op == "ghost_particles") r = s.decomposition ? (double)s.decomposition->ghostParticles() : 0.0;
+            else if (op == "rebuild") { if (s.decomposition) s.decomposition->rebuild(); else s.water_cell_linked_list->exec(); }
             else if (op == "inner_total") r = (double)s.water_block_inner->total_;
             else if (op == "inner_stride") r = (double)s.water_block_inner->fixed_stride_;
             else if (op == "inner_max_count") r = (double)s.water_block_inner->max_count_;

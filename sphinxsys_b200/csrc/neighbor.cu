@@ -158,10 +158,20 @@ struct SearchArgs
     const u32 *cell_offset;
     const u32 *particle_index;
     u32 n_src;
+    u32 src_begin, src_end; // source slots searched
     float inv_h, ks2;
     int depth;
     int cell_ordered;
 };
+// launches start at the 32-aligned slot below src_begin so that lane == slot % 32 (SELL-32 layout)
+__device__ __forceinline__ u32 search_slot(const SearchArgs &a) { return (a.src_begin & ~31u) + blockIdx.x * blockDim.x + threadIdx.x; }
+static inline unsigned search_blocks(const SearchArgs &a, unsigned threads) { return sph_blocks(a.src_end - (a.src_begin & ~31u), threads); }
+// the first active lane of a warp publishes per-slice values
+__device__ __forceinline__ bool slice_writer(bool active)
+{
+    u32 b = __ballot_sync(0xffffffffu, active);
+    return active && (threadIdx.x & 31) == (u32)(__ffs(b) - 1);
+}
 
 // Neighbor<SPHAdaptation,SPHAdaptation>::NeighborCriterion, neighbor_method.hpp:152-156; every op rounded
 // separately so that set membership is bit-identical to the CPU evaluation.
@@ -230,9 +240,10 @@ __global__ void __launch_bounds__(128)
     k_relation(SearchArgs a, u32 *__restrict__ count, u32 *__restrict__ slice, u32 *__restrict__ index, u64 capacity, u32 stride,
                u32 *__restrict__ max_count)
 {
-    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    u32 t = search_slot(a);
     u32 c = 0;
-    if (t < a.n_src)
+    const bool active = t >= a.src_begin && t < a.src_end;
+    if (active)
     {
         u32 i;
         float4 xi;
@@ -283,8 +294,8 @@ __global__ void __launch_bounds__(128)
     k_relation_ordered(SearchArgs a, u32 *__restrict__ count, u32 *__restrict__ slice, u32 *__restrict__ index, u64 capacity,
                        u32 stride, u32 *__restrict__ max_count)
 {
-    const u32 t = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = t < a.n_src;
+    const u32 t = search_slot(a);
+    const bool active = t >= a.src_begin && t < a.src_end;
     const DMesh &m = a.m;
     float4 xi = active ? a.src_pos[t] : make_float4(0.f, 0.f, 0.f, 0.f);
     const int ca = cell_coord(xi.x, m.lx, m.spacing, m.cx);
@@ -344,12 +355,12 @@ __global__ void __launch_bounds__(128)
     if (MODE == 0)
     {
         u32 mx = warp_max_u32(c);
-        if ((threadIdx.x & 31) == 0 && active) slice[t >> 5] = mx * 32u;
+        if (slice_writer(active)) slice[t >> 5] = mx * 32u;
     }
     if (MODE == 2)
     {
         u32 mx = warp_max_u32(c);
-        if ((threadIdx.x & 31) == 0 && active)
+        if (slice_writer(active))
         {
             slice[t >> 5] = (t >> 5) * 32u * stride;
             if (mx > 0) atomicMax(max_count, mx);
@@ -369,6 +380,9 @@ static int make_search(sphb200_context *ctx, const sphb200_search_t *s, SearchAr
     a->cell_offset = s->tar_list.cell_offset;
     a->particle_index = s->tar_list.particle_index;
     a->n_src = s->n_src;
+    a->src_begin = s->src_end ? s->src_begin : 0u;
+    a->src_end = s->src_end ? s->src_end : s->n_src;
+    SPH_CHECK_ARG(ctx, a->src_begin <= a->src_end && a->src_end <= s->n_src, "source slot range outside [0, n_src)");
     a->inv_h = 1.0f / s->kernel.h; // inv_h_ = 1 / max(src_h, tar_h), neighbor_method.hpp:73-76
     a->ks2 = s->kernel.kernel_size * s->kernel.kernel_size;
     a->depth = s->search_depth;
@@ -391,7 +405,8 @@ template <int MODE>
 static int launch_relation(sphb200_context *ctx, const SearchArgs &a, bool inner, u32 *count, u32 *slice, u32 *index, u64 cap,
                            u32 stride, u32 *max_count, cudaStream_t st)
 {
-    unsigned g = sph_blocks(a.n_src, 128);
+    if (a.src_end <= a.src_begin) return 0;
+    unsigned g = search_blocks(a, 128);
     bool sorted = a.tar_sorted_pos != nullptr;
     if (a.cell_ordered)
     {
@@ -426,7 +441,7 @@ extern "C" int sphb200_relation_count(sphb200_context_t *ctx, const sphb200_sear
     rc = sph_scratch(ctx, 3, ((size_t)nslices + 1) * sizeof(u32) + 64, &p);
     if (rc) return rc;
     u32 *slice_len = (u32 *)p;
-    SPH_CUDA(ctx, cudaMemsetAsync(slice_len + nslices, 0, sizeof(u32), st));
+    SPH_CUDA(ctx, cudaMemsetAsync(slice_len, 0, ((size_t)nslices + 1) * sizeof(u32), st));
     rc = launch_relation<0>(ctx, a, search->is_inner != 0, rel.count, slice_len, nullptr, 0, 0, nullptr, st);
     if (rc) return rc;
     rc = sph_scan_u32(ctx, slice_len, rel.slice_offset, (u64)nslices + 1, 0, st);

@@ -21,6 +21,7 @@ extern "C" int sphb200_context_create(int device, sphb200_context_t **out)
     sphb200_context *ctx = new sphb200_context();
     memset(ctx, 0, sizeof(*ctx));
     ctx->device = device;
+    ctx->nranks = 1;
     e = cudaMallocHost(&ctx->host_pinned, 256);
     if (e == cudaSuccess) e = cudaMalloc(&ctx->dev_scalars, 256);
     if (e != cudaSuccess)
@@ -35,6 +36,7 @@ extern "C" int sphb200_context_create(int device, sphb200_context_t **out)
 extern "C" int sphb200_context_destroy(sphb200_context_t *ctx)
 {
     if (!ctx) return SPHB200_E_INVALID;
+    if (ctx->comm) sphb200_comm_destroy(ctx);
     for (int s = 0; s < 4; ++s)
         if (ctx->scratch[s]) cudaFree(ctx->scratch[s]);
     if (ctx->host_pinned) cudaFreeHost(ctx->host_pinned);

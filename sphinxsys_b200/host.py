@@ -28,7 +28,8 @@ class Options(C.Structure):
                 ("LL", C.c_double), ("LH", C.c_double), ("LW", C.c_double), ("correction", C.c_int32),
                 ("fused_time_step", C.c_int32), ("fused_regularization", C.c_int32), ("sort_interval", C.c_int32),
                 ("device", C.c_int32), ("relation_stride", C.c_int32), ("system_lower", C.c_double * 3),
-                ("system_upper", C.c_double * 3), ("use_system_bounds", C.c_int32)]
+                ("system_upper", C.c_double * 3), ("use_system_bounds", C.c_int32), ("rank", C.c_int32),
+                ("nranks", C.c_int32), ("unique_id", C.c_uint8 * 128)]
 
 
 _lib = None
@@ -60,9 +61,32 @@ def load():
         L.sphck_device_pointer.restype = C.c_void_p
         L.sphck_device_pointer.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_int]
         L.sphck_cell_offsets.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
+        L.sphck_comm_unique_id.argtypes = [C.c_void_p]
+        L.sphck_own_range.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
+        L.sphck_download_raw.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64]
+        L.sphck_upload_raw.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64]
+        L.sphck_cuts.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.sphck_plan_slab_cuts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.sphck_export_csr.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
+
+
+def comm_unique_id() -> bytes:
+    """128-byte NCCL communicator id (call on rank 0, hand to every rank: DamBreakCK(..., unique_id=...))."""
+    buf = (C.c_uint8 * 128)()
+    if load().sphck_comm_unique_id(buf) != 0:
+        raise capi.SphB200Error("sphck_comm_unique_id failed (NCCL not loadable?)")
+    return bytes(buf)
+
+
+def plan_slab_cuts(per_plane, nranks):
+    """Cell-plane cuts (host-only helper of include/sphinxsys_ck/slab_decomposition.h)."""
+    h = np.ascontiguousarray(per_plane, dtype=np.uint64)
+    out = np.zeros(nranks + 1, dtype=np.int32)
+    if load().sphck_plan_slab_cuts(h.ctypes.data, h.size, int(nranks), out.ctypes.data) != 0:
+        raise capi.SphB200Error("plan_slab_cuts failed: " + load().sphck_last_error().decode())
+    return out
 
 
 def _kind(name):
@@ -73,7 +97,8 @@ class DamBreakCK:
     """Handle of a C++ `SPH::DamBreakCK` (include/sphinxsys_ck/dambreak_case.h)."""
 
     def __init__(self, case=None, device_index=0, correction=False, fused_time_step=True, sort_interval=100,
-                 relation_stride=None, fused_regularization=True, dim=3, dp=0.05, generate=False):
+                 relation_stride=None, fused_regularization=True, dim=3, dp=0.05, generate=False, rank=0, nranks=1,
+                 unique_id=None, width_scale=1.0):
         self.lib = load()
         o = Options()
         if case is not None:
@@ -86,6 +111,14 @@ class DamBreakCK:
         o.sort_interval, o.device = int(sort_interval), int(device_index)
         o.relation_stride = -1 if relation_stride is None else int(relation_stride)
         o.use_system_bounds = 0
+        o.DW, o.LW = o.DW * width_scale, o.LW * width_scale
+        o.rank, o.nranks = int(rank), int(nranks)
+        if nranks > 1:
+            if unique_id is None or len(unique_id) != 128:
+                raise ValueError("decomposed runs need the 128-byte unique_id from comm_unique_id() on rank 0")
+            for i, b in enumerate(unique_id):
+                o.unique_id[i] = b
+        self.rank, self.nranks = int(rank), int(nranks)
         self.case = case
         if case is not None and not generate:
             fp = np.ascontiguousarray(case.fluid_pos, dtype=np.float32)
@@ -96,7 +129,7 @@ class DamBreakCK:
             self._h = self.lib.sphck_dambreak_create(C.byref(o), None, 0, None, None, 0)
         if not self._h:
             raise capi.SphB200Error("sphck_dambreak_create failed: " + self.lib.sphck_last_error().decode())
-        self.n_fluid = int(self.lib.sphck_count(self._h, 0))
+        self.n_fluid = int(self.lib.sphck_count(self._h, 0))  # stored fluid particles (own + ghosts when decomposed)
         self.n_wall = int(self.lib.sphck_count(self._h, 1))
 
     def close(self):
@@ -171,6 +204,36 @@ class DamBreakCK:
         dt = np.uint32 if k == 2 else np.float32
         a = np.ascontiguousarray(arr, dtype=dt)
         self._check(self.lib.sphck_upload(self._h, int(wall), name.encode(), k, a.ctypes.data), f"upload {name}")
+
+    def own_range(self):
+        """(begin, count, stored): slots of this rank's own particles and the stored total (own + ghosts)."""
+        b, c, s_ = C.c_uint64(0), C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.sphck_own_range(self._h, C.byref(b), C.byref(c), C.byref(s_)), "own_range")
+        return int(b.value), int(c.value), int(s_.value)
+
+    def download_own(self, name) -> np.ndarray:
+        """This rank's own particles of a variable in STORAGE order (pair with download_own('ReferenceID'))."""
+        b, c, _ = self.own_range()
+        k = _kind(name)
+        shape, dt = {0: ((c,), np.float32), 1: ((c, 4), np.float32), 2: ((c,), np.uint32), 3: ((c, 9), np.float32)}[k]
+        out = np.empty(shape, dtype=dt)
+        self._check(self.lib.sphck_download_raw(self._h, 0, name.encode(), out.ctypes.data, b, c), f"download_raw {name}")
+        return out[:, :3] if k == 1 else out
+
+    def download_own_into(self, name, out):
+        """download_own into a caller buffer (e.g. pinned): device element layout, Vecd = 4 floats per particle."""
+        b, c, _ = self.own_range()
+        self._check(self.lib.sphck_download_raw(self._h, 0, name.encode(), out.ctypes.data, b, c), f"download_raw {name}")
+
+    def upload_own(self, name, arr):
+        """Raw upload of this rank's own particles (storage order, device element layout). Asynchronous for pinned memory."""
+        b, c, _ = self.own_range()
+        self._check(self.lib.sphck_upload_raw(self._h, 0, name.encode(), arr.ctypes.data, b, c), f"upload_raw {name}")
+
+    def cuts(self) -> np.ndarray:
+        out = np.zeros(self.nranks + 1, dtype=np.int32)
+        self._check(self.lib.sphck_cuts(self._h, out.ctypes.data, out.size), "cuts")
+        return out
 
     def mesh(self, wall=False) -> capi.MeshT:
         m = capi.MeshT()
