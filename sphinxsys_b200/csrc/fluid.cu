@@ -45,6 +45,9 @@ struct FArgs
     const u32 *order; // slot -> particle id (the relations' row order), or nullptr
     // constants
     float inv_h, inv_dq, q_scale, W0;
+    // closed form of the tabulated Wendland C2 interpolant (see wendland_*): scales and error-term coefficients
+    int analytic;
+    float wl_w_scale, wl_w_c4, wl_w_c5, wl_four_dq, wl_dw_a, wl_dw_c;
     float rho0, c0, p0, Z, inv_Z_sum, inv_Z_ave, Z_geo, inv_c_ave, limiter;
     int free_surface, dim;
 };
@@ -113,6 +116,28 @@ static int make_fargs(sphb200_context *ctx, const sphb200_fluid_args_t *s, FArgs
     double dw_scale = w_scale * ih;
     if (wtab) build_tab(k.w, w_scale, wtab);
     if (dwtab) build_tab(k.dw, dw_scale, dwtab);
+    // Wendland C2 is a polynomial (W_1D degree 5, dW_1D degree 4), so the reference's 4-point Lagrange interpolant on
+    // its table equals f(q) - f[q0,q1,q2,q3,q] * prod(q - q_k) EXACTLY, with the divided difference in closed form
+    // (a4 + a5 * (q0+q1+q2+q3+q)). The kernels use that form when the table handed in really is the Wendland table
+    // (checked here node by node); any other table (Laguerre-Gauss, user kernels) takes the shared-memory table path.
+    {
+        const double dq = (double)k.kernel_size / 20.0;
+        bool is_wendland = k.kernel_size == 2.0f;
+        for (int i = 0; i < 24 && is_wendland; ++i)
+        {
+            double q = (double)((float)(i - 1) * (float)dq);
+            double w = pow(1.0 - 0.5 * q, 4) * (1.0 + 2.0 * q), dw = 0.625 * pow(q - 2.0, 3) * q;
+            if (fabs((double)k.w[i] - w) > 2e-6 || fabs((double)k.dw[i] - dw) > 2e-6) is_wendland = false;
+        }
+        a->analytic = is_wendland ? 1 : 0;
+        const double dq4 = dq * dq * dq * dq;
+        a->wl_w_scale = (float)w_scale;
+        a->wl_w_c4 = (float)((-0.9375 + 2.0 * 0.125 * dq) * dq4 * w_scale);
+        a->wl_w_c5 = (float)(0.125 * dq4 * w_scale);
+        a->wl_four_dq = (float)(4.0 * dq);
+        a->wl_dw_a = (float)(0.625 * dw_scale);
+        a->wl_dw_c = (float)(0.625 * dq4 * dw_scale);
+    }
     a->inv_h = inv_h;
     a->inv_dq = 20.0f / k.kernel_size;
     a->q_scale = inv_h * a->inv_dq; // r -> q / dq in one multiply
@@ -160,6 +185,47 @@ __device__ __forceinline__ float eval_tab(const float4 *tab, float r, float q_sc
     float s = u - (m - MAGIC);
     float4 c = tab[__float_as_int(m) & (KT_SLOTS - 1)];
     return fmaf(fmaf(fmaf(c.w, s, c.z), s, c.y), s, c.x);
+}
+
+// Closed form of the same interpolant for the Wendland C2 table (no memory access): with t = q/dq - floor(q/dq) and
+// s = t - 1/2, prod(q - q_k) = dq^4 (s^2 - 9/4)(s^2 - 1/4); dW_1D = 0.625 (q-2)^3 q has the constant divided
+// difference 0.625, W_1D = (1-q/2)^4 (1+2q) has a4 + a5 (q0+q1+q2+q3+q) with a4 = -15/16, a5 = 1/8.
+__device__ __forceinline__ float wendland_dw(const FArgs &a, float r)
+{
+    const float MAGIC = 12582912.0f;
+    float q = r * a.inv_h;
+    float u = fmaf(r, a.q_scale, -0.5f);
+    float m = u + MAGIC;
+    float s = u - (m - MAGIC);
+    float s2 = s * s;
+    float pi = (s2 - 2.25f) * (s2 - 0.25f);
+    float g = q - 2.0f;
+    float poly = (g * g) * (g * (q * a.wl_dw_a));
+    return fmaf(-a.wl_dw_c, pi, poly);
+}
+__device__ __forceinline__ float wendland_w(const FArgs &a, float r)
+{
+    const float MAGIC = 12582912.0f;
+    float q = r * a.inv_h;
+    float u = fmaf(r, a.q_scale, -0.5f);
+    float m = u + MAGIC;
+    float loc = m - MAGIC;
+    float s = u - loc;
+    float s2 = s * s;
+    float pi = (s2 - 2.25f) * (s2 - 0.25f);
+    float h = fmaf(-0.5f, q, 1.0f);
+    float h2 = h * h;
+    float poly = (h2 * h2) * (fmaf(2.0f, q, 1.0f) * a.wl_w_scale);
+    float dd = fmaf(a.wl_w_c5, fmaf(loc, a.wl_four_dq, q), a.wl_w_c4);
+    return fmaf(-dd, pi, poly);
+}
+template <bool ANALYTIC> __device__ __forceinline__ float kernel_dw(const FArgs &a, const float4 *tab, float r)
+{
+    return ANALYTIC ? wendland_dw(a, r) : eval_tab(tab, r, a.q_scale);
+}
+template <bool ANALYTIC> __device__ __forceinline__ float kernel_w(const FArgs &a, const float4 *tab, float r)
+{
+    return ANALYTIC ? wendland_w(a, r) : eval_tab(tab, r, a.q_scale);
 }
 
 // 1/sqrt(x) for x > 0 (MUFU.RSQ, flush-to-zero form: no denormal fix-up code); callers clamp x away from 0
@@ -414,10 +480,11 @@ extern "C" int sphb200_total_mechanical_energy(sphb200_context_t *ctx, const sph
 // =====================================================================================================
 // compression (density) summation + regularisation
 // =====================================================================================================
+template <bool ANALYTIC>
 __global__ void __launch_bounds__(FL_THREADS) k_compression_summation(FArgs a, KTab wtab, int regularize)
 {
     __shared__ float4 tab[KT_SLOTS];
-    stage_tab(wtab, tab);
+    if (!ANALYTIC) stage_tab(wtab, tab);
     u32 t = active_slot(a);
     if (t < a.begin || t >= a.end) return;
     const u32 i = a.order ? a.order[t] : t;
@@ -433,7 +500,7 @@ __global__ void __launch_bounds__(FL_THREADS) k_compression_summation(FArgs a, K
             float4 xj = a.pos[j];
             float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
             float r = sqrtf(dx * dx + dy * dy + dz * dz);
-            s += eval_tab(tab, r, a.q_scale) * a.vol_ref[j];
+            s += kernel_w<ANALYTIC>(a, tab, r) * a.vol_ref[j];
         }
     }
     if (a.n_wall)
@@ -447,7 +514,7 @@ __global__ void __launch_bounds__(FL_THREADS) k_compression_summation(FArgs a, K
             float4 xj = a.w_pos[j];
             float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
             float r = sqrtf(dx * dx + dy * dy + dz * dz);
-            s += eval_tab(tab, r, a.q_scale) * a.w_vol_ref[j];
+            s += kernel_w<ANALYTIC>(a, tab, r) * a.w_vol_ref[j];
         }
     }
     a.Csum[i] = s;
@@ -469,7 +536,11 @@ extern "C" int sphb200_compression_summation(sphb200_context_t *ctx, const sphb2
     SPH_CHECK_ARG(ctx, a.n == 0 || (a.pos && a.vol_ref && a.Csum && a.in_count && a.in_slice && a.in_index), "null fluid array");
     SPH_CHECK_ARG(ctx, !regularize || (a.C && a.rho), "null fluid array");
     SPH_CHECK_ARG(ctx, a.n_wall == 0 || (a.w_pos && a.w_vol_ref && a.ct_count && a.ct_slice && a.ct_index), "null wall array");
-    if (a.end > a.begin) SPH_LAUNCH(ctx, k_compression_summation, active_blocks(a, FL_THREADS), FL_THREADS, 0, stream, a, wtab, regularize);
+    if (a.end > a.begin)
+    {
+        if (a.analytic) SPH_LAUNCH(ctx, k_compression_summation<true>, active_blocks(a, FL_THREADS), FL_THREADS, 0, stream, a, wtab, regularize);
+        else SPH_LAUNCH(ctx, k_compression_summation<false>, active_blocks(a, FL_THREADS), FL_THREADS, 0, stream, a, wtab, regularize);
+    }
     return 0;
 }
 
@@ -516,11 +587,11 @@ __global__ void __launch_bounds__(256) k_a1_init(FArgs a, float dt)
 
 // InteractKernel::interact (inner, :89-111; wall, :157-180) + UpdateKernel::update (:122-127), one launch:
 // update touches only particle i's own velocity, which no neighbour reads in this half step.
-template <int RIEMANN, bool CORR>
+template <int RIEMANN, bool CORR, bool ANALYTIC>
 __global__ void __launch_bounds__(FL_THREADS) k_a1_interact(FArgs a, KTab dwtab, float dt, int do_update)
 {
     __shared__ float4 tab[KT_SLOTS];
-    stage_tab(dwtab, tab);
+    if (!ANALYTIC) stage_tab(dwtab, tab);
     u32 t = active_slot(a);
     if (t < a.begin || t >= a.end) return;
     const u32 i = a.order ? a.order[t] : t;
@@ -543,7 +614,7 @@ __global__ void __launch_bounds__(FL_THREADS) k_a1_interact(FArgs a, KTab dwtab,
             float r2 = dx * dx + dy * dy + dz * dz;
             float r, inv_r;
             dist(r2, r, inv_r);
-            float dWV = eval_tab(tab, r, a.q_scale) * xj.w;
+            float dWV = kernel_dw<ANALYTIC>(a, tab, r) * xj.w;
             if (CORR)
             {
                 float Bj[9];
@@ -586,7 +657,7 @@ __global__ void __launch_bounds__(FL_THREADS) k_a1_interact(FArgs a, KTab dwtab,
                 float r2 = dx * dx + dy * dy + dz * dz;
                 float r, inv_r;
                 dist(r2, r, inv_r);
-                float dWV = eval_tab(tab, r, a.q_scale) * xj.w;
+                float dWV = kernel_dw<ANALYTIC>(a, tab, r) * xj.w;
                 float ex = dx * inv_r, ey = dy * inv_r, ez = dz * inv_r;
                 float rx = ax, ry = ay, rz = az;
                 if (a.w_acc)
@@ -650,16 +721,21 @@ extern "C" int sphb200_acoustic_1st_half_initialize(sphb200_context_t *ctx, cons
     return 0;
 }
 
-template <bool CORR> static int launch_a1(sphb200_context *ctx, const FArgs &a, const KTab &t, int riemann, float dt, int upd, void *stream)
+template <bool CORR, bool ANALYTIC>
+static int launch_a1_k(sphb200_context *ctx, const FArgs &a, const KTab &t, int riemann, float dt, int upd, void *stream)
 {
     unsigned g = active_blocks(a, FL_THREADS);
     switch (riemann)
     {
-    case 0: SPH_LAUNCH(ctx, (k_a1_interact<0, CORR>), g, FL_THREADS, 0, stream, a, t, dt, upd); break;
-    case 1: SPH_LAUNCH(ctx, (k_a1_interact<1, CORR>), g, FL_THREADS, 0, stream, a, t, dt, upd); break;
-    default: SPH_LAUNCH(ctx, (k_a1_interact<2, CORR>), g, FL_THREADS, 0, stream, a, t, dt, upd); break;
+    case 0: SPH_LAUNCH(ctx, (k_a1_interact<0, CORR, ANALYTIC>), g, FL_THREADS, 0, stream, a, t, dt, upd); break;
+    case 1: SPH_LAUNCH(ctx, (k_a1_interact<1, CORR, ANALYTIC>), g, FL_THREADS, 0, stream, a, t, dt, upd); break;
+    default: SPH_LAUNCH(ctx, (k_a1_interact<2, CORR, ANALYTIC>), g, FL_THREADS, 0, stream, a, t, dt, upd); break;
     }
     return 0;
+}
+template <bool CORR> static int launch_a1(sphb200_context *ctx, const FArgs &a, const KTab &t, int riemann, float dt, int upd, void *stream)
+{
+    return a.analytic ? launch_a1_k<CORR, true>(ctx, a, t, riemann, dt, upd, stream) : launch_a1_k<CORR, false>(ctx, a, t, riemann, dt, upd, stream);
 }
 
 extern "C" int sphb200_acoustic_1st_half_interact(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, float dt, int do_update,
@@ -689,11 +765,11 @@ extern "C" int sphb200_acoustic_1st_half(sphb200_context_t *ctx, const sphb200_f
 // acoustic step, 2nd half — initialize + interact(inner) + interact(wall) + update in ONE launch: neighbours
 // only read Position/Vol/Velocity here, none of which this half step writes.
 // =====================================================================================================
-template <int RIEMANN, bool CORR>
+template <int RIEMANN, bool CORR, bool ANALYTIC>
 __global__ void __launch_bounds__(FL_THREADS) k_a2(FArgs a, KTab dwtab, float dt, float h_min, float *next_reduced)
 {
     __shared__ float4 tab[KT_SLOTS];
-    stage_tab(dwtab, tab);
+    if (!ANALYTIC) stage_tab(dwtab, tab);
     u32 t = active_slot(a);
     float measure = 0.f;
     if (t >= a.begin && t < a.end)
@@ -723,7 +799,7 @@ __global__ void __launch_bounds__(FL_THREADS) k_a2(FArgs a, KTab dwtab, float dt
                 float r2 = dx * dx + dy * dy + dz * dz;
                 float r, inv_r;
                 dist(r2, r, inv_r);
-                float dWV = eval_tab(tab, r, a.q_scale) * xj.w;
+                float dWV = kernel_dw<ANALYTIC>(a, tab, r) * xj.w;
                 float ex = dx * inv_r, ey = dy * inv_r, ez = dz * inv_r;
                 // AverageV (riemann_solver_ck.hpp:26-31) with Z_i == Z_j: 2 (v_i - v_ave) = v_i - v_j
                 float ux = vi.x - vj.x, uy = vi.y - vj.y, uz = vi.z - vj.z;
@@ -754,7 +830,7 @@ __global__ void __launch_bounds__(FL_THREADS) k_a2(FArgs a, KTab dwtab, float dt
                 float r2 = dx * dx + dy * dy + dz * dz;
                 float r, inv_r;
                 dist(r2, r, inv_r);
-                float dWV = eval_tab(tab, r, a.q_scale) * xj.w;
+                float dWV = kernel_dw<ANALYTIC>(a, tab, r) * xj.w;
                 float ex = dx * inv_r, ey = dy * inv_r, ez = dz * inv_r;
                 float vx = vi.x, vy = vi.y, vz = vi.z;
                 if (a.w_vel)
@@ -791,17 +867,23 @@ __global__ void __launch_bounds__(FL_THREADS) k_a2(FArgs a, KTab dwtab, float dt
     if (next_reduced) block_max_to_global(measure, next_reduced);
 }
 
-template <bool CORR>
-static int launch_a2(sphb200_context *ctx, const FArgs &a, const KTab &t, int riemann, float dt, float h_min, float *nr, void *stream)
+template <bool CORR, bool ANALYTIC>
+static int launch_a2_k(sphb200_context *ctx, const FArgs &a, const KTab &t, int riemann, float dt, float h_min, float *nr, void *stream)
 {
     unsigned g = active_blocks(a, FL_THREADS);
     switch (riemann)
     {
-    case 0: SPH_LAUNCH(ctx, (k_a2<0, CORR>), g, FL_THREADS, 0, stream, a, t, dt, h_min, nr); break;
-    case 1: SPH_LAUNCH(ctx, (k_a2<1, CORR>), g, FL_THREADS, 0, stream, a, t, dt, h_min, nr); break;
-    default: SPH_LAUNCH(ctx, (k_a2<2, CORR>), g, FL_THREADS, 0, stream, a, t, dt, h_min, nr); break;
+    case 0: SPH_LAUNCH(ctx, (k_a2<0, CORR, ANALYTIC>), g, FL_THREADS, 0, stream, a, t, dt, h_min, nr); break;
+    case 1: SPH_LAUNCH(ctx, (k_a2<1, CORR, ANALYTIC>), g, FL_THREADS, 0, stream, a, t, dt, h_min, nr); break;
+    default: SPH_LAUNCH(ctx, (k_a2<2, CORR, ANALYTIC>), g, FL_THREADS, 0, stream, a, t, dt, h_min, nr); break;
     }
     return 0;
+}
+template <bool CORR>
+static int launch_a2(sphb200_context *ctx, const FArgs &a, const KTab &t, int riemann, float dt, float h_min, float *nr, void *stream)
+{
+    return a.analytic ? launch_a2_k<CORR, true>(ctx, a, t, riemann, dt, h_min, nr, stream)
+                      : launch_a2_k<CORR, false>(ctx, a, t, riemann, dt, h_min, nr, stream);
 }
 
 extern "C" int sphb200_acoustic_2nd_half(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, float dt, float h_min,

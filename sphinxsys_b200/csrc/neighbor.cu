@@ -294,6 +294,7 @@ __global__ void __launch_bounds__(128)
     k_relation_ordered(SearchArgs a, u32 *__restrict__ count, u32 *__restrict__ slice, u32 *__restrict__ index, u64 capacity,
                        u32 stride, u32 *__restrict__ max_count)
 {
+    constexpr int CH = 16; // candidates tested per chunk; hits of a chunk are collected in per-lane bit masks
     const u32 t = search_slot(a);
     const bool active = t >= a.src_begin && t < a.src_end;
     const DMesh &m = a.m;
@@ -302,10 +303,16 @@ __global__ void __launch_bounds__(128)
     const int cb = cell_coord(xi.y, m.ly, m.spacing, m.cy);
     const int cc = cell_coord(xi.z, m.lz, m.spacing, m.cz);
     const int d = a.depth;
-    const float inv_h2 = a.inv_h * a.inv_h;
-    const float sure_in = a.ks2 * (1.0f - 1.0e-4f), sure_out = a.ks2 * (1.0f + 1.0e-4f);
-    const u64 base = (MODE == 1 ? (u64)(active ? slice[t >> 5] : 0u) : (u64)(t >> 5) * 32ull * stride) + (t & 31u);
-    const u32 limit = MODE == 2 ? stride : 0xffffffffu;
+    // thresholds on the UNSCALED squared distance: surely inside / surely outside the support; in between the
+    // separately rounded reference expression decides (within())
+    const float h2 = 1.0f / (a.inv_h * a.inv_h);
+    const float sure_in = a.ks2 * (1.0f - 1.0e-4f) * h2, sure_out = a.ks2 * (1.0f + 1.0e-4f) * h2;
+    // entries of this slot live at index[off], index[off + 32], ...; off_end bounds what may be written
+    u64 base64 = (MODE == 1 ? (u64)(active ? slice[t >> 5] : 0u) : (u64)(t >> 5) * 32ull * stride) + (t & 31u);
+    u64 room = capacity > base64 ? (capacity - base64 + 31ull) / 32ull : 0ull; // rows that fit below `capacity`
+    if (MODE == 2 && room > stride) room = stride;
+    u32 *const out = index + base64;
+    const u32 row_limit = (u32)(room > 0xffffffffull ? 0xffffffffull : room);
     u32 c = 0;
     u32 todo = __ballot_sync(0xffffffffu, active);
     while (todo)
@@ -327,26 +334,47 @@ __global__ void __launch_bounds__(128)
                 {
                     const u32 col = cell_linear(m, x, y, 0);
                     const u32 rb = a.cell_offset[col + z0], re = a.cell_offset[col + z1];
-                    const u32 lo = a.cell_offset[col + wz0];
-                    const u32 win = a.cell_offset[col + wz1] - lo;
-#pragma unroll 4
-                    for (u32 k = rb; k < re; ++k)
+                    const u32 lo = a.cell_offset[col + wz0], hi = a.cell_offset[col + wz1];
+                    for (u32 kb = rb; kb < re; kb += CH)
                     {
-                        const float4 xj = a.tar_pos[k];
-                        const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-                        const float r2 = inv_h2 * fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                        bool hit = r2 < sure_in;
-                        if (!hit && r2 < sure_out) hit = within(xi, xj, a.inv_h, a.ks2);
-                        hit = hit && (k - lo) < win && !(INNER && k == t);
-                        if (hit)
+                        u32 sure = 0, maybe = 0;
+                        const float4 *__restrict__ pk = a.tar_pos + kb;
+                        auto test = [&](int b, u32 bit) {
+                            const float4 xj = pk[b];
+                            const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
+                            if (r2 < sure_in) sure |= bit;
+                            if (r2 < sure_out) maybe |= bit;
+                        };
+                        if (kb + CH <= re)
                         {
-                            if (MODE != 0)
-                            {
-                                const u64 pos = base + 32ull * c;
-                                if (c < limit && pos < capacity) index[pos] = k;
-                            }
-                            ++c;
+#pragma unroll
+                            for (int b = 0; b < CH; ++b) test(b, 1u << b);
                         }
+                        else
+                            for (int b = 0; kb + (u32)b < re; ++b) test(b, 1u << b);
+                        // the lane's own cell window [lo, hi) as a bit range of this chunk; INNER: not itself
+                        const u32 blo = lo > kb ? min(lo - kb, 32u) : 0u, bhi = hi > kb ? min(hi - kb, 32u) : 0u;
+                        u32 wmask = (bhi >= 32u ? 0xffffffffu : (1u << bhi) - 1u) & ~(blo >= 32u ? 0xffffffffu : (1u << blo) - 1u);
+                        if (INNER && t - kb < (u32)CH) wmask &= ~(1u << (t - kb));
+                        maybe &= wmask & ~sure;
+                        sure &= wmask;
+                        while (maybe) // rare: within 1e-4 of the threshold
+                        {
+                            const u32 b = __ffs(maybe) - 1;
+                            maybe &= maybe - 1;
+                            if (within(xi, a.tar_pos[kb + b], a.inv_h, a.ks2)) sure |= 1u << b;
+                        }
+                        if (MODE == 0)
+                            c += __popc(sure);
+                        else
+                            while (sure) // ascending bit order == reference search order
+                            {
+                                const u32 b = __ffs(sure) - 1;
+                                sure &= sure - 1;
+                                if (c < row_limit) out[32ull * c] = kb + b;
+                                ++c;
+                            }
                     }
                 }
         }

@@ -320,6 +320,39 @@ def test_per_dynamics_parity_3d(pair3d):
     assert abs(e - o64.exec("energy")) <= 1e-5 * abs(e)
 
 
+def test_per_dynamics_parity_2d():
+    """One acoustic step of the 2-D dam break (dim-2 kernel normalisation, one cell layer in z), field by field
+    within 1e-5 of the field norm against the double oracle (pressure: its fp32 granularity)."""
+    from sphinxsys_b200 import cases
+    case = cases.dam_break(dim=2, dp=0.025)
+    pos, vel = perturb_state(case)
+    case.fluid_pos = pos
+    gpu = make_gpu(case, fused_time_step=False)
+    gpu.upload("Velocity", vel)
+    gpu.initialize()
+    o32, o64 = make_oracle(case, f64=False), make_oracle(case, f64=True)
+    for o in (o32, o64):
+        o.real("Velocity", 3)[:] = vel.reshape(-1)
+        o.exec("prepare_ck")
+    off, idx = gpu.export_csr()
+    assert np.array_equal(off, o32.uint("inner_offset")) and np.array_equal(idx, o32.uint("inner_index")[: off[-1]])
+    tol = {"default": 1e-5, "Pressure": 3e-4, "CompressionRate": 5e-5, "Force": 5e-5}
+    gpu.exec("density_summation")
+    gpu.exec("advection_setup")
+    for o in (o32, o64):
+        for op in ("compression_summation", "density_regularization", "advection_setup"):
+            o.exec(op)
+    _compare(gpu, o32, o64, ["CompressionSummation", "Compression", "Density", "VolumetricMeasure"], [], "2d_density", tol)
+    dt = float(np.float32(gpu.exec("acoustic_dt")))
+    assert abs(dt - o32.exec("acoustic_dt")) <= 1e-6 * dt
+    gpu.exec("acoustic1", dt)
+    gpu.exec("acoustic2", dt)
+    for o in (o32, o64):
+        o.exec("acoustic1", dt)
+        o.exec("acoustic2", dt)
+    _compare(gpu, o32, o64, ["CompressionRate", "Compression", "Density", "Pressure"], ["Force", "Velocity", "Displacement"], "2d_step", tol)
+
+
 def test_fused_time_step_equals_standalone():
     """The max folded into the 2nd-half launch must equal the stand-alone AcousticTimeStepCK reduction bit for bit."""
     from sphinxsys_b200 import cases
@@ -343,7 +376,9 @@ def test_fused_time_step_equals_standalone():
 @pytest.mark.parametrize("dim,dp,correction,n_outer", [(3, 0.05, False, 12), (3, 0.05, True, 6), (2, 0.025, False, 30)])
 def test_multi_step_drift(dim, dp, correction, n_outer):
     """Run the case-file loop on both sides from the true initial condition; compare after n_outer advection steps.
-    Bounds: fields within 2e-4 (positions 5e-6, i.e. a few ulp of the tank length) of the oracle in max-norm after n_outer*~5 acoustic steps;
+    Bounds: fields within 2e-4 (positions 5e-6, i.e. a few ulp of the tank length) of the fp32 oracle in max-norm
+    after n_outer*~5 acoustic steps — or twice the fp32 oracle's own distance to the fp64 oracle on the same run if
+    that is larger (the flow amplifies rounding differences: 1.8e-4 in velocity on the 2-D case after 150 sub-steps);
     total mechanical energy within 1e-5 relative; free-surface front position (max x) within 1e-5."""
     from sphinxsys_b200 import cases
     case = cases.dam_break(dim=dim, dp=dp)
@@ -351,10 +386,14 @@ def test_multi_step_drift(dim, dp, correction, n_outer):
     gpu.initialize()
     o32 = make_oracle(case, f64=False, correction=int(correction))
     o32.exec("prepare_ck")
+    o64 = make_oracle(case, f64=True, correction=int(correction))
+    o64.exec("prepare_ck")
     n_ac = 0
     for _ in range(n_outer):
         n_ac += gpu.step_outer()
     o32.exec("run_ck", 1e9, n_outer, 1e9, 5)
+    o64.exec("run_ck", 1e9, n_outer, 1e9, 5)
+    same_path = int(o64.exec("acoustic_steps")) == n_ac
     assert int(o32.exec("acoustic_steps")) == n_ac, "both sides must take the same number of acoustic sub-steps"
     assert abs(gpu.physical_time - o32.exec("physical_time")) <= 1e-5 * gpu.physical_time
     rep = {}
@@ -362,8 +401,9 @@ def test_multi_step_drift(dim, dp, correction, n_outer):
     assert np.array_equal(gpu_field(gpu, "OriginalID"), o32.uint("OriginalID"))
     for nm, w, tol in (("Position", 3, 5e-6), ("Velocity", 3, 2e-4), ("Density", 1, 1e-6), ("Compression", 1, 1e-6)):
         e = rel_err(gpu_field(gpu, nm), oracle_field(o32, nm, w))
-        rep[nm] = e
-        assert e <= tol, f"{nm}: {e:.3e} after {n_outer} outer / {n_ac} acoustic steps"
+        noise = rel_err(oracle_field(o32, nm, w), oracle_field(o64, nm, w)) if same_path else 0.0
+        rep[nm] = {"gpu_vs_oracle32": e, "oracle32_vs_oracle64": noise}
+        assert e <= max(tol, 2.0 * noise), f"{nm}: {e:.3e} (fp32 noise {noise:.3e}) after {n_outer} outer / {n_ac} acoustic steps"
     e_gpu, e_ref = gpu.energy(), o32.exec("energy")
     rep["energy"] = [e_gpu, e_ref]
     assert abs(e_gpu - e_ref) <= 1e-5 * abs(e_ref)
