@@ -97,8 +97,12 @@ typedef struct
     float *vol_ref;               /* VolumetricMeasureRef */
     float *compression_sum;       /* CompressionSummation */
     float *B;                     /* LinearCorrectionMatrix, 9 floats row-major per particle, or NULL */
-    sphb200_vec4_t *posvol;       /* derived gather record (x, y, z, Vol): refresh with sphb200_pack_posvol
-                                     whenever Position or VolumetricMeasure changed */
+    sphb200_vec4_t *posvol;       /* derived gather records, one load per neighbour instead of two; refresh with
+                                     sphb200_pack_records whenever their sources changed outside the library:
+                                     posvol = (x, y, z, Vol)                         [1st half, correction matrix] */
+    sphb200_vec4_t *posvolref;    /* (x, y, z, VolRef)                             [compression summation] */
+    void *posvolvel;              /* 32-byte records (x, y, z, Vol, vx, vy, vz, -) [2nd half: one 256-bit load];
+                                     the 1st-half update keeps the velocity part current */
     uint32_t active_begin;        /* dynamics update the slots [active_begin, active_end) only; slots outside (ghost */
     uint32_t active_end;          /* particles of a decomposed run) are read as neighbours. active_end == 0: [0, n) */
 } sphb200_fluid_view_t;
@@ -109,6 +113,7 @@ typedef struct
     uint32_t n;
     const sphb200_vec4_t *pos;      /* Position */
     const sphb200_vec4_t *posvol;   /* (x, y, z, Vol) */
+    const sphb200_vec4_t *posvolref;/* (x, y, z, VolRef) */
     const sphb200_vec4_t *vel_ave;  /* AverageVelocity, or NULL == 0 */
     const sphb200_vec4_t *acc_ave;  /* AverageAcceleration, or NULL == 0 */
     const sphb200_vec4_t *normal;   /* NormalDirection */
@@ -186,6 +191,10 @@ int sphb200_vec3_to_vec4(sphb200_context_t *ctx, sphb200_vec4_t *dst, const floa
 int sphb200_vec4_to_vec3(sphb200_context_t *ctx, float *dst3, const sphb200_vec4_t *src, uint32_t n, void *stream);
 int sphb200_pack_posvol(sphb200_context_t *ctx, sphb200_vec4_t *posvol, const sphb200_vec4_t *pos, const float *vol,
                         uint32_t n, void *stream);
+/* all gather records of a body in one pass; any output (and the inputs only it needs) may be NULL */
+int sphb200_pack_records(sphb200_context_t *ctx, uint32_t n, const sphb200_vec4_t *pos, const float *vol, const float *vol_ref,
+                         const sphb200_vec4_t *vel, sphb200_vec4_t *posvol, sphb200_vec4_t *posvolref, void *posvolvel,
+                         void *stream);
 
 /* ---------------------------------------------------------------------------------------------------
  * primitives  (replaces algorithm_primitive_sycl.h:44-137)

@@ -229,7 +229,7 @@ class DamBreakCK
                 first_half_phases_->deviceInitialize(acoustic_dt);
                 decomposition->refreshGhosts({"Pressure"});
                 first_half_phases_->deviceInteractAndUpdate(acoustic_dt);
-                decomposition->refreshGhosts({"Velocity"});
+                decomposition->refreshGhosts({"PosVolVel"}); // the 2nd half reads neighbour velocities from the gather record
             }
             else
                 fluid_acoustic_step_1st_half->exec(acoustic_dt);

@@ -192,6 +192,8 @@ class FluidDynamicsBase
         f.compression_sum = (float *)p.deviceDataOrNull<Real>("CompressionSummation");
         f.B = (float *)p.deviceDataOrNull<Matd>("LinearCorrectionMatrix");
         f.posvol = (sphb200_vec4_t *)p.deviceDataOrNull<Vecd>("PosVol");
+        f.posvolref = (sphb200_vec4_t *)p.deviceDataOrNull<Vecd>("PosVolRef");
+        f.posvolvel = p.deviceDataOrNull<GatherRecord8>("PosVolVel");
         f.active_begin = (uint32_t)p.activeBegin();
         f.active_end = (uint32_t)p.activeEnd();
         return f;
@@ -230,6 +232,7 @@ class FluidDynamicsBase
             a.wall.n = (uint32_t)wp.TotalRealParticles();
             a.wall.pos = (const sphb200_vec4_t *)wp.deviceData<Vecd>("Position");
             a.wall.posvol = (const sphb200_vec4_t *)wp.deviceData<Vecd>("PosVol");
+            a.wall.posvolref = (const sphb200_vec4_t *)wp.deviceDataOrNull<Vecd>("PosVolRef");
             a.wall.vel_ave = (const sphb200_vec4_t *)wp.deviceDataOrNull<Vecd>("AverageVelocity");
             a.wall.acc_ave = (const sphb200_vec4_t *)wp.deviceDataOrNull<Vecd>("AverageAcceleration");
             a.wall.normal = (const sphb200_vec4_t *)wp.deviceDataOrNull<Vecd>("NormalDirection");

@@ -28,6 +28,8 @@ template <> struct DeviceType<UnsignedInt> { static constexpr uint32_t bytes = 4
 template <> struct DeviceType<int> { static constexpr uint32_t bytes = 4; };
 template <> struct DeviceType<Vecd> { static constexpr uint32_t bytes = 16; }; // float4 on the device
 template <> struct DeviceType<Matd> { static constexpr uint32_t bytes = 36; };
+struct GatherRecord8 { Real v[8] = {0, 0, 0, 0, 0, 0, 0, 0}; }; // 32-byte derived record (library extension)
+template <> struct DeviceType<GatherRecord8> { static constexpr uint32_t bytes = 32; };
 
 inline void *deviceAllocate(size_t bytes)
 {
@@ -498,6 +500,8 @@ class SPHBody
         auto *dv_vol = p.registerStateVariable<Real>("VolumetricMeasure", vol);
         p.registerStateVariable<Vecd>("PosVol"); // derived gather record (x, y, z, Vol)
         p.markDerived("PosVol");
+        p.registerStateVariable<Vecd>("PosVolRef"); // (x, y, z, VolRef)
+        p.markDerived("PosVolRef");
         Real rho0 = material_ ? material_->ReferenceDensity() : Real(1);
         p.registerStateVariable<Real>("Density", rho0);
         p.registerStateVariable<Real>("Mass", rho0 * vol);
@@ -523,9 +527,19 @@ class SPHBody
     {
         if (!posvol_dirty_) return;
         BaseParticles &p = getBaseParticles();
-        SPHCK_CALL(sphb200_pack_posvol, (sphb200_vec4_t *)p.deviceData<Vecd>("PosVol"),
-                   (const sphb200_vec4_t *)p.deviceData<Vecd>("Position"), (const float *)p.deviceData<Real>("VolumetricMeasure"),
-                   (uint32_t)p.TotalRealParticles(), execution_instance().stream());
+        const bool has_ref = p.hasVariable("VolumetricMeasureRef"), has_vel = p.hasVariable("Velocity");
+        if (has_vel && !p.hasVariable("PosVolVel"))
+        {
+            p.registerStateVariable<GatherRecord8>("PosVolVel"); // (x, y, z, Vol, vx, vy, vz, -)
+            p.markDerived("PosVolVel");
+        }
+        SPHCK_CALL(sphb200_pack_records, (uint32_t)p.TotalRealParticles(), (const sphb200_vec4_t *)p.deviceData<Vecd>("Position"),
+                   (const float *)p.deviceData<Real>("VolumetricMeasure"),
+                   has_ref ? (const float *)p.deviceData<Real>("VolumetricMeasureRef") : nullptr,
+                   has_vel ? (const sphb200_vec4_t *)p.deviceData<Vecd>("Velocity") : nullptr,
+                   (sphb200_vec4_t *)p.deviceData<Vecd>("PosVol"),
+                   has_ref ? (sphb200_vec4_t *)p.deviceData<Vecd>("PosVolRef") : nullptr,
+                   has_vel ? p.deviceData<GatherRecord8>("PosVolVel") : nullptr, execution_instance().stream());
         posvol_dirty_ = false;
     }
     bool isCellOrdered() const { return cell_ordered_; }

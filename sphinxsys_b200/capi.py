@@ -41,11 +41,11 @@ class FluidView(C.Structure):
     _fields_ = [("n", C.c_uint32), ("pos", _P), ("vel", _P), ("dpos", _P), ("force", _P), ("force_prior", _P),
                 ("vol", _P), ("mass", _P), ("rho", _P), ("p", _P), ("compression", _P), ("compression_rate", _P),
                 ("vol_ref", _P), ("compression_sum", _P), ("B", _P), ("posvol", _P),
-                ("active_begin", C.c_uint32), ("active_end", C.c_uint32)]
+                ("posvolref", _P), ("posvolvel", _P), ("active_begin", C.c_uint32), ("active_end", C.c_uint32)]
 
 
 class WallView(C.Structure):
-    _fields_ = [("n", C.c_uint32), ("pos", _P), ("posvol", _P), ("vel_ave", _P), ("acc_ave", _P), ("normal", _P),
+    _fields_ = [("n", C.c_uint32), ("pos", _P), ("posvol", _P), ("posvolref", _P), ("vel_ave", _P), ("acc_ave", _P), ("normal", _P),
                 ("vol_ref", _P)]
 
 
@@ -91,6 +91,7 @@ SYMBOLS = {
     "sphb200_vec3_to_vec4": (_I, [_CTX, _P, _P, _U32, _P]),
     "sphb200_vec4_to_vec3": (_I, [_CTX, _P, _P, _U32, _P]),
     "sphb200_pack_posvol": (_I, [_CTX, _P, _P, _P, _U32, _P]),
+    "sphb200_pack_records": (_I, [_CTX, _U32, _P, _P, _P, _P, _P, _P, _P, _P]),
     "sphb200_exclusive_scan_u32": (_I, [_CTX, _P, _P, _U64, C.POINTER(_U32), _P]),
     "sphb200_sort_pairs_u32": (_I, [_CTX, _P, _P, _U64, _I, _P]),
     "sphb200_gather_multi": (_I, [_CTX, _I, C.POINTER(_P), C.POINTER(_P), C.POINTER(_U32), _P, _U32, _P]),

@@ -34,10 +34,12 @@ struct FArgs
     u32 n;
     u32 begin, end; // active slots [begin, end): ghost slots outside are read as neighbours but never written
     float4 *pos, *vel, *dpos, *force, *force_prior, *posvol;
+    const float4 *posvolref; // (x, y, z, VolRef)
+    float4 *rec2;            // 32-byte records (x, y, z, Vol | vx, vy, vz, -)
     float *vol, *mass, *rho, *p, *C, *Cdot, *vol_ref, *Csum, *B;
     // wall
     u32 n_wall;
-    const float4 *w_pos, *w_posvol, *w_vel, *w_acc, *w_n;
+    const float4 *w_pos, *w_posvol, *w_posvolref, *w_vel, *w_acc, *w_n;
     const float *w_vol_ref;
     // relations
     const u32 *in_count, *in_slice, *in_index;
@@ -88,11 +90,12 @@ static int make_fargs(sphb200_context *ctx, const sphb200_fluid_args_t *s, FArgs
     }
     a->pos = (float4 *)f.pos; a->vel = (float4 *)f.vel; a->dpos = (float4 *)f.dpos;
     a->force = (float4 *)f.force; a->force_prior = (float4 *)f.force_prior; a->posvol = (float4 *)f.posvol;
+    a->posvolref = (const float4 *)f.posvolref; a->rec2 = (float4 *)f.posvolvel;
     a->vol = f.vol; a->mass = f.mass; a->rho = f.rho; a->p = f.p; a->C = f.compression; a->Cdot = f.compression_rate;
     a->vol_ref = f.vol_ref; a->Csum = f.compression_sum; a->B = f.B;
     const sphb200_wall_view_t &w = s->wall;
     a->n_wall = w.n;
-    a->w_pos = (const float4 *)w.pos; a->w_posvol = (const float4 *)w.posvol; a->w_vel = (const float4 *)w.vel_ave;
+    a->w_pos = (const float4 *)w.pos; a->w_posvol = (const float4 *)w.posvol; a->w_posvolref = (const float4 *)w.posvolref; a->w_vel = (const float4 *)w.vel_ave;
     a->w_acc = (const float4 *)w.acc_ave; a->w_n = (const float4 *)w.normal; a->w_vol_ref = w.vol_ref;
     a->in_count = s->inner.count; a->in_slice = s->inner.slice_offset; a->in_index = s->inner.index;
     a->ct_count = w.n ? s->contact.count : nullptr;
@@ -226,6 +229,14 @@ template <bool ANALYTIC> __device__ __forceinline__ float kernel_dw(const FArgs 
 template <bool ANALYTIC> __device__ __forceinline__ float kernel_w(const FArgs &a, const float4 *tab, float r)
 {
     return ANALYTIC ? wendland_w(a, r) : eval_tab(tab, r, a.q_scale);
+}
+
+// one 256-bit load (LDG.E.256 on sm_100a) of a 32-byte record that is not written during the launch
+__device__ __forceinline__ void load_rec2(const float4 *rec, u32 j, float4 &a, float4 &b)
+{
+    asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w)
+        : "l"(rec + 2ull * j));
 }
 
 // 1/sqrt(x) for x > 0 (MUFU.RSQ, flush-to-zero form: no denormal fix-up code); callers clamp x away from 0
@@ -497,10 +508,10 @@ __global__ void __launch_bounds__(FL_THREADS) k_compression_summation(FArgs a, K
         for (u32 k = 0; k < cnt; ++k)
         {
             u32 j = idx[32ull * k];
-            float4 xj = a.pos[j];
+            float4 xj = a.posvolref[j];
             float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
             float r = sqrtf(dx * dx + dy * dy + dz * dz);
-            s += kernel_w<ANALYTIC>(a, tab, r) * a.vol_ref[j];
+            s += kernel_w<ANALYTIC>(a, tab, r) * xj.w;
         }
     }
     if (a.n_wall)
@@ -511,10 +522,10 @@ __global__ void __launch_bounds__(FL_THREADS) k_compression_summation(FArgs a, K
         for (u32 k = 0; k < cnt; ++k)
         {
             u32 j = idx[32ull * k];
-            float4 xj = a.w_pos[j];
+            float4 xj = a.w_posvolref[j];
             float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
             float r = sqrtf(dx * dx + dy * dy + dz * dz);
-            s += kernel_w<ANALYTIC>(a, tab, r) * a.w_vol_ref[j];
+            s += kernel_w<ANALYTIC>(a, tab, r) * xj.w;
         }
     }
     a.Csum[i] = s;
@@ -533,9 +544,9 @@ extern "C" int sphb200_compression_summation(sphb200_context_t *ctx, const sphb2
     KTab wtab;
     int rc = make_fargs(ctx, s, &a, &wtab, nullptr);
     if (rc) return rc;
-    SPH_CHECK_ARG(ctx, a.n == 0 || (a.pos && a.vol_ref && a.Csum && a.in_count && a.in_slice && a.in_index), "null fluid array");
+    SPH_CHECK_ARG(ctx, a.n == 0 || (a.pos && a.posvolref && a.vol_ref && a.Csum && a.in_count && a.in_slice && a.in_index), "null fluid array");
     SPH_CHECK_ARG(ctx, !regularize || (a.C && a.rho), "null fluid array");
-    SPH_CHECK_ARG(ctx, a.n_wall == 0 || (a.w_pos && a.w_vol_ref && a.ct_count && a.ct_slice && a.ct_index), "null wall array");
+    SPH_CHECK_ARG(ctx, a.n_wall == 0 || (a.w_posvolref && a.ct_count && a.ct_slice && a.ct_index), "null wall array");
     if (a.end > a.begin)
     {
         if (a.analytic) SPH_LAUNCH(ctx, k_compression_summation<true>, active_blocks(a, FL_THREADS), FL_THREADS, 0, stream, a, wtab, regularize);
@@ -696,6 +707,7 @@ __global__ void __launch_bounds__(FL_THREADS) k_a1_interact(FArgs a, KTab dwtab,
         v.y += (Fp.y + F.y) / m_i * dt;
         v.z += (Fp.z + F.z) / m_i * dt;
         a.vel[i] = v;
+        if (a.rec2) a.rec2[2ull * i + 1] = v; // keep the 2nd-half gather record current
     }
 }
 
@@ -706,6 +718,7 @@ static int check_acoustic_args(sphb200_context *ctx, const FArgs &a, bool second
                   "null fluid array");
     SPH_CHECK_ARG(ctx, a.n_wall == 0 || (a.w_posvol && a.ct_count && a.ct_slice && a.ct_index), "null wall array");
     SPH_CHECK_ARG(ctx, !second || a.n_wall == 0 || a.w_n, "null wall normal");
+    SPH_CHECK_ARG(ctx, !second || a.n == 0 || a.rec2, "null posvolvel record array");
     return 0;
 }
 
@@ -793,8 +806,8 @@ __global__ void __launch_bounds__(FL_THREADS) k_a2(FArgs a, KTab dwtab, float dt
             for (u32 k = 0; k < cnt; ++k)
             {
                 u32 j = idx[32ull * k];
-                float4 xj = a.posvol[j];
-                float4 vj = a.vel[j];
+                float4 xj, vj;
+                load_rec2(a.rec2, j, xj, vj);
                 float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
                 float r2 = dx * dx + dy * dy + dz * dz;
                 float r, inv_r;

@@ -130,6 +130,44 @@ __global__ void k_pack_posvol(float4 *posvol, const float4 *pos, const float *vo
         posvol[i] = p;
     }
 }
+__global__ void __launch_bounds__(256)
+    k_pack_records(u32 n, const float4 *__restrict__ pos, const float *__restrict__ vol, const float *__restrict__ vol_ref,
+                   const float4 *__restrict__ vel, float4 *__restrict__ posvol, float4 *__restrict__ posvolref, float4 *__restrict__ posvolvel)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pos[i];
+    if (posvol || posvolvel)
+    {
+        p.w = vol[i];
+        if (posvol) posvol[i] = p;
+        if (posvolvel)
+        {
+            posvolvel[2ull * i] = p;
+            float4 v = vel[i];
+            v.w = 0.f;
+            posvolvel[2ull * i + 1] = v;
+        }
+    }
+    if (posvolref)
+    {
+        p.w = vol_ref[i];
+        posvolref[i] = p;
+    }
+}
+extern "C" int sphb200_pack_records(sphb200_context_t *ctx, uint32_t n, const sphb200_vec4_t *pos, const float *vol, const float *vol_ref,
+                                    const sphb200_vec4_t *vel, sphb200_vec4_t *posvol, sphb200_vec4_t *posvolref, void *posvolvel,
+                                    void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && (pos || n == 0), "null pointer");
+    SPH_CHECK_ARG(ctx, n == 0 || !(posvol || posvolvel) || vol, "posvol / posvolvel need vol");
+    SPH_CHECK_ARG(ctx, n == 0 || !posvolref || vol_ref, "posvolref needs vol_ref");
+    SPH_CHECK_ARG(ctx, n == 0 || !posvolvel || vel, "posvolvel needs vel");
+    if (n) SPH_LAUNCH(ctx, k_pack_records, sph_blocks(n, 256), 256, 0, stream, n, (const float4 *)pos, vol, vol_ref,
+                      (const float4 *)vel, (float4 *)posvol, (float4 *)posvolref, (float4 *)posvolvel);
+    return 0;
+}
+
 extern "C" int sphb200_vec3_to_vec4(sphb200_context_t *ctx, sphb200_vec4_t *dst, const float *src3, uint32_t n, void *stream)
 {
     SPH_CHECK_ARG(ctx, ctx && ((dst && src3) || n == 0), "null pointer");
