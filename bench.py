@@ -329,7 +329,7 @@ def run_ours(args, rank, world, local_rank):
                        f"{world} x-slabs of equal particle count on the global mesh, NCCL halo exchange of contiguous cell-plane ranges, "
                        f"full wall copy per rank"},
             "roofline": roofline,
-            "whole_step_hbm_frac": value * alg_bytes / 1e9 / peak,
+            "whole_step_hbm_frac": value / world * alg_bytes / 1e9 / peak,  # per GPU
             "algorithmic_bytes_per_particle_step": alg_bytes,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
