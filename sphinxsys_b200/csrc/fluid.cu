@@ -20,6 +20,7 @@
 #include "common.cuh"
 
 constexpr int FL_THREADS = 128;
+constexpr int FL_MIN_BLOCKS = 10; // <= 48 registers: 62% occupancy instead of 50% (the gather loops are latency/L1 bound)
 constexpr int KT_INTERVALS = 21; // intervals of the 24-entry table that q in [0, 2] can select
 constexpr int KT_SLOTS = 32;     // padded so that (index & 31) can never leave the table
 
@@ -599,7 +600,7 @@ __global__ void __launch_bounds__(256) k_a1_init(FArgs a, float dt)
 // InteractKernel::interact (inner, :89-111; wall, :157-180) + UpdateKernel::update (:122-127), one launch:
 // update touches only particle i's own velocity, which no neighbour reads in this half step.
 template <int RIEMANN, bool CORR, bool ANALYTIC>
-__global__ void __launch_bounds__(FL_THREADS) k_a1_interact(FArgs a, KTab dwtab, float dt, int do_update)
+__global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs a, KTab dwtab, float dt, int do_update)
 {
     __shared__ float4 tab[KT_SLOTS];
     if (!ANALYTIC) stage_tab(dwtab, tab);
@@ -779,7 +780,7 @@ extern "C" int sphb200_acoustic_1st_half(sphb200_context_t *ctx, const sphb200_f
 // only read Position/Vol/Velocity here, none of which this half step writes.
 // =====================================================================================================
 template <int RIEMANN, bool CORR, bool ANALYTIC>
-__global__ void __launch_bounds__(FL_THREADS) k_a2(FArgs a, KTab dwtab, float dt, float h_min, float *next_reduced)
+__global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a2(FArgs a, KTab dwtab, float dt, float h_min, float *next_reduced)
 {
     __shared__ float4 tab[KT_SLOTS];
     if (!ANALYTIC) stage_tab(dwtab, tab);
