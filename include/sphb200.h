@@ -76,6 +76,13 @@ typedef struct
     int32_t correction;    /* 0 NoKernelCorrectionCK, 1 LinearCorrectionCK (needs fluid.B) */
     float limiter_coeff;   /* 3.0 (riemann_solver_ck.h:97) */
     int32_t free_surface;  /* DensityRegularization flow type: 1 FreeSurface, 0 Internal */
+    int32_t formulation;   /* 0: CK (state Compression/CompressionRate, tabulated kernel, current positions);
+                              1: legacy Integration1stHalf/2ndHalf + DensitySummation (state Density/DensityChangeRate
+                                 passed in rho / compression_rate, analytic kernel, pair geometry FROZEN at the last
+                                 configuration update: keep the gather records packed at that time, pass dpos == pos).
+                              ref: particle_dynamics/fluid_dynamics/fluid_integration.hpp:49-231, density_summation.cpp:8-78 */
+    float sigma0;          /* legacy DensitySummation: lattice number density (adaptation.cpp:26-60) */
+    float wall_rho0;       /* legacy DensitySummation: reference density of the contact (wall) material */
 } sphb200_fluid_t;
 
 /* Device views of one fluid body (the DiscreteVariables the acoustic steps register,
@@ -158,6 +165,8 @@ typedef struct
     const sphb200_vec4_t *tar_pos;        /* target Position */
     sphb200_cell_list_t tar_list;         /* target cell-linked list */
     int32_t is_inner;                     /* 1: Inner<> (exclude j == i), 0: Contact<> */
+    int32_t legacy_criterion;             /* 0: |inv_h d|^2 < kernel_size^2 (neighbor_method.hpp:152-156);
+                                             1: |d|^2 < (kernel_size h)^2, NeighborBuilder (kernels/base_kernel.h:105-114) */
     int32_t search_depth;                 /* cells each side: 1 inner; contact: cell_linked_list.hpp:161-167 */
     uint32_t src_begin, src_end;          /* source slots searched: [src_begin, src_end); src_end == 0: [0, n_src) */
     int32_t cell_ordered;                 /* 1: src_pos and tar_pos are STORED in the cell order of their own lists
@@ -286,6 +295,11 @@ int sphb200_advection_time_step(sphb200_context_t *ctx, const sphb200_fluid_view
                                 float cfl, float *reduced_host, float *dt_host, void *stream);
 int sphb200_acoustic_time_step(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, float h_min, float cfl,
                                float *reduced_host, float *dt_host, void *stream);
+/* legacy ReduceDynamics<AdvectionViscousTimeStep>: max(|v|^2, 4 h |F + F_prior| / m); the legacy AcousticTimeStep
+ * (max(c0 + |v|)) is sphb200_acoustic_time_step with material.formulation == 1.
+ * ref: particle_dynamics/fluid_dynamics/fluid_time_step.cpp:21-59 */
+int sphb200_advection_time_step_legacy(sphb200_context_t *ctx, const sphb200_fluid_view_t *fluid, float h_min, float u_ref,
+                                       float cfl, float *reduced_host, float *dt_host, void *stream);
 /* InteractionDynamicsCK<AcousticStep1stHalf<Inner<OneLevel,..>,Contact<Wall,..>>>::exec(dt):
  * initialize -> interact(inner) -> interact(wall) -> update, ref: acoustic_step_1st_half.hpp:66-180,
  * interaction_algorithms_ck.cpp:29-34.  Two launches (initialize; fused interact+update). */

@@ -60,6 +60,7 @@ class RelationBase
     uint32_t fixed_stride_ = 0, max_count_ = 0; // one-pass build with a fixed row stride; 0 = exact two-phase build
     sphb200_kernel_t kernel_;
     int search_depth_ = 1;
+    bool legacy_criterion_ = false; // NeighborBuilder criterion |d|^2 < rc^2 (legacy InnerRelation / ContactRelation)
 
     RelationBase(SPHBody &source, SPHBody &target, bool is_inner) : source_(source), target_(target), is_inner_(is_inner)
     {
@@ -106,6 +107,7 @@ class RelationBase
         s.tar_pos = (const sphb200_vec4_t *)target_.getBaseParticles().deviceData<Vecd>("Position");
         s.tar_list = tcl.view();
         s.is_inner = is_inner_ ? 1 : 0;
+        s.legacy_criterion = legacy_criterion_ ? 1 : 0;
         s.search_depth = search_depth_;
         s.src_begin = (uint32_t)source_.getBaseParticles().activeBegin();
         s.src_end = (uint32_t)source_.getBaseParticles().activeEnd();

@@ -5,8 +5,11 @@
 #ifndef SPHINXSYS_CK_DAMBREAK_CASE_H
 #define SPHINXSYS_CK_DAMBREAK_CASE_H
 
+#include <functional>
+
 #include "sphinxsys_ck.h"
 #include "slab_decomposition.h"
+#include "legacy_dynamics.h"
 
 namespace SPH
 {
@@ -20,6 +23,9 @@ struct DamBreakParameters
     bool fused_time_step = true;
     bool fused_regularization = true;
     int sort_interval = 100;   // :217-220
+    // legacy API + formulation (tests/2d_examples/test_2d_dambreak/Dambreak.cpp, tests/3d_examples/test_3d_dambreak):
+    // Integration1stHalf/2ndHalfWithWallRiemann, DensitySummationComplexFreeSurface, state Density/DensityChangeRate
+    bool legacy = false;
     // slab decomposition over the GPUs of one node (needs sphb200_comm_create on this process's context first)
     int rank = 0, nranks = 1;
     static DamBreakParameters twoDimensional(double dp = 0.025)
@@ -72,10 +78,15 @@ class DamBreakCK
     std::unique_ptr<StateDynamics<P, fluid_dynamics::UpdateParticlePosition>> water_update_particle_position;
     std::unique_ptr<InteractionDynamicsCK<P, LinearCorrectionMatrixComplex>> fluid_linear_correction_matrix;
     std::unique_ptr<InteractionDynamicsBase> fluid_acoustic_step_1st_half, fluid_acoustic_step_2nd_half;
-    std::unique_ptr<InteractionDynamicsCK<P, fluid_dynamics::CompressionSummation<Inner<>, Contact<>>>> fluid_density_summation;
+    std::unique_ptr<InteractionDynamicsBase> fluid_density_summation;
     std::unique_ptr<StateDynamics<P, fluid_dynamics::DensityRegularization<SPHBody, WeaklyCompressibleFluid, FreeSurface>>> fluid_density_regularization;
-    std::unique_ptr<ReduceDynamicsCK<P, fluid_dynamics::AdvectionTimeStepCK>> fluid_advection_time_step;
-    std::unique_ptr<ReduceDynamicsCK<P, fluid_dynamics::AcousticTimeStepCK<WeaklyCompressibleFluid>>> fluid_acoustic_time_step;
+    std::unique_ptr<BaseDynamics<Real>> fluid_advection_time_step_owner, fluid_acoustic_time_step_owner;
+    fluid_dynamics::AcousticTimeStepBase *fluid_acoustic_time_step = nullptr; // exec(), setPrimed(), ReducedValue()
+    BaseDynamics<Real> *fluid_advection_time_step = nullptr;
+    std::function<Real()> advection_reduced_value;
+    // legacy-API objects (q.legacy)
+    std::unique_ptr<ComplexRelation> water_wall_complex;
+    fluid_dynamics::FluidDynamicsBase *cuts_adv_ = nullptr;
     std::unique_ptr<ReduceDynamicsCK<P, TotalMechanicalEnergyCK>> record_water_mechanical_energy;
     std::unique_ptr<SlabDecomposition> decomposition; // nranks > 1 only
     fluid_dynamics::AcousticStep1stHalfPhases *first_half_phases_ = nullptr;
@@ -154,45 +165,76 @@ class DamBreakCK
         if (wall_normals) wall_boundary.registerWallVariables(wall_normals);
         else wall_boundary.computeNormalFromBodyShape(); // NormalFromBodyShapeCK, run on the host (dambreak.cpp:119,153)
 
-        water_block_inner.reset(new Inner<>(water_block));
-        water_wall_contact.reset(new Contact<>(water_block, {&wall_boundary}));
+        using namespace fluid_dynamics;
         water_cell_linked_list.reset(new UpdateCellLinkedList<P, RealBody>(water_block));
         wall_cell_linked_list.reset(new UpdateCellLinkedList<P, RealBody>(wall_boundary));
-        water_block_update_complex_relation.reset(new UpdateRelation<P, Inner<>, Contact<>>(*water_block_inner, *water_wall_contact));
         particle_sort.reset(new ParticleSortCK<P>(water_block));
         constant_gravity.reset(new StateDynamics<P, GravityForceCK<Gravity>>(water_block, gravity));
-        water_advection_step_setup.reset(new StateDynamics<P, fluid_dynamics::AdvectionStepSetup>(water_block));
-        water_update_particle_position.reset(new StateDynamics<P, fluid_dynamics::UpdateParticlePosition>(water_block));
-        using namespace fluid_dynamics;
-        if (q.correction)
+        if (q.legacy)
         {
-            fluid_linear_correction_matrix.reset(new InteractionDynamicsCK<P, LinearCorrectionMatrixComplex>(
-                DynamicsArgs(*water_block_inner, 0.5), *water_wall_contact));
-            fluid_acoustic_step_1st_half.reset(new InteractionDynamicsCK<P, AcousticStep1stHalfWithWallRiemannCorrectionCK>(*water_block_inner, *water_wall_contact));
-            auto *a2 = new InteractionDynamicsCK<P, AcousticStep2ndHalfWithWallRiemannCorrectionCK>(*water_block_inner, *water_wall_contact);
-            fluid_acoustic_step_2nd_half.reset(a2);
-            fluid_acoustic_time_step.reset(new ReduceDynamicsCK<P, AcousticTimeStepCK<WeaklyCompressibleFluid>>(water_block));
-            if (q.fused_time_step) a2->fuseTimeStepReduction(*fluid_acoustic_time_step);
+            // Dambreak.cpp:97-116 — the legacy class names over the same kernels (legacy_dynamics.h)
+            if (q.correction || q.nranks > 1) throw SphError("legacy formulation: no kernel correction, no decomposition");
+            auto *inner = new InnerRelation(water_block);
+            auto *contact = new ContactRelation(water_block, {&wall_boundary});
+            water_block_inner.reset(inner);
+            water_wall_contact.reset(contact);
+            water_wall_complex.reset(new ComplexRelation(*inner, *contact));
+            fluid_acoustic_step_1st_half.reset(new Dynamics1Level<Integration1stHalfWithWallRiemann>(*inner, *contact));
+            auto *second = new Dynamics1Level<Integration2ndHalfWithWallRiemann>(*inner, *contact);
+            fluid_acoustic_step_2nd_half.reset(second);
+            fluid_density_summation.reset(new InteractionWithUpdate<DensitySummationComplexFreeSurface>(*inner, *contact));
+            auto *adv = new ReduceDynamics<AdvectionViscousTimeStep>(water_block, U_f_);
+            fluid_advection_time_step_owner.reset(adv);
+            fluid_advection_time_step = adv;
+            advection_reduced_value = [adv]() { return adv->ReducedValue(); };
+            auto *ac = new ReduceDynamics<AcousticTimeStep>(water_block);
+            fluid_acoustic_time_step_owner.reset(ac);
+            fluid_acoustic_time_step = ac;
+            if (q.fused_time_step) second->fuseTimeStepReduction(*ac);
         }
         else
         {
-            fluid_acoustic_step_1st_half.reset(new InteractionDynamicsCK<P, AcousticStep1stHalfWithWallRiemannCK>(*water_block_inner, *water_wall_contact));
-            auto *a2 = new InteractionDynamicsCK<P, AcousticStep2ndHalfWithWallRiemannCK>(*water_block_inner, *water_wall_contact);
-            fluid_acoustic_step_2nd_half.reset(a2);
-            fluid_acoustic_time_step.reset(new ReduceDynamicsCK<P, AcousticTimeStepCK<WeaklyCompressibleFluid>>(water_block));
-            if (q.fused_time_step) a2->fuseTimeStepReduction(*fluid_acoustic_time_step);
+            water_block_inner.reset(new Inner<>(water_block));
+            water_wall_contact.reset(new Contact<>(water_block, {&wall_boundary}));
+            water_advection_step_setup.reset(new StateDynamics<P, AdvectionStepSetup>(water_block));
+            water_update_particle_position.reset(new StateDynamics<P, UpdateParticlePosition>(water_block));
+            auto *ac = new ReduceDynamicsCK<P, AcousticTimeStepCK<WeaklyCompressibleFluid>>(water_block);
+            fluid_acoustic_time_step_owner.reset(ac);
+            fluid_acoustic_time_step = ac;
+            if (q.correction)
+            {
+                fluid_linear_correction_matrix.reset(new InteractionDynamicsCK<P, LinearCorrectionMatrixComplex>(
+                    DynamicsArgs(*water_block_inner, 0.5), *water_wall_contact));
+                fluid_acoustic_step_1st_half.reset(new InteractionDynamicsCK<P, AcousticStep1stHalfWithWallRiemannCorrectionCK>(*water_block_inner, *water_wall_contact));
+                auto *a2 = new InteractionDynamicsCK<P, AcousticStep2ndHalfWithWallRiemannCorrectionCK>(*water_block_inner, *water_wall_contact);
+                fluid_acoustic_step_2nd_half.reset(a2);
+                if (q.fused_time_step) a2->fuseTimeStepReduction(*ac);
+            }
+            else
+            {
+                fluid_acoustic_step_1st_half.reset(new InteractionDynamicsCK<P, AcousticStep1stHalfWithWallRiemannCK>(*water_block_inner, *water_wall_contact));
+                auto *a2 = new InteractionDynamicsCK<P, AcousticStep2ndHalfWithWallRiemannCK>(*water_block_inner, *water_wall_contact);
+                fluid_acoustic_step_2nd_half.reset(a2);
+                if (q.fused_time_step) a2->fuseTimeStepReduction(*ac);
+            }
+            auto *sum = new InteractionDynamicsCK<P, CompressionSummation<Inner<>, Contact<>>>(*water_block_inner, *water_wall_contact);
+            fluid_density_summation.reset(sum);
+            fluid_density_regularization.reset(new StateDynamics<P, DensityRegularization<SPHBody, WeaklyCompressibleFluid, FreeSurface>>(water_block));
+            if (q.fused_regularization) sum->addPostStateDynamics(*fluid_density_regularization);
+            auto *adv = new ReduceDynamicsCK<P, AdvectionTimeStepCK>(water_block, U_f_);
+            fluid_advection_time_step_owner.reset(adv);
+            fluid_advection_time_step = adv;
+            advection_reduced_value = [adv]() { return adv->ReducedValue(); };
+            cuts_adv_ = adv; // gets the decomposition below, once it exists
         }
-        fluid_density_summation.reset(new InteractionDynamicsCK<P, CompressionSummation<Inner<>, Contact<>>>(*water_block_inner, *water_wall_contact));
-        fluid_density_regularization.reset(new StateDynamics<P, DensityRegularization<SPHBody, WeaklyCompressibleFluid, FreeSurface>>(water_block));
-        if (q.fused_regularization) fluid_density_summation->addPostStateDynamics(*fluid_density_regularization);
-        fluid_advection_time_step.reset(new ReduceDynamicsCK<P, AdvectionTimeStepCK>(water_block, U_f_));
+        water_block_update_complex_relation.reset(new UpdateRelation<P, Inner<>, Contact<>>(*water_block_inner, *water_wall_contact));
         record_water_mechanical_energy.reset(new ReduceDynamicsCK<P, TotalMechanicalEnergyCK>(water_block, gravity));
         sv_physical_time = sph_system.getSystemVariableByName<Real>("PhysicalTime");
         first_half_phases_ = dynamic_cast<fluid_dynamics::AcousticStep1stHalfPhases *>(fluid_acoustic_step_1st_half.get());
         if (q.nranks > 1)
         {
             decomposition.reset(new SlabDecomposition(water_block, q.rank, q.nranks, cuts));
-            fluid_advection_time_step->setDecomposition(decomposition.get());
+            cuts_adv_->setDecomposition(decomposition.get());
             fluid_acoustic_time_step->setDecomposition(decomposition.get());
             record_water_mechanical_energy->setDecomposition(decomposition.get());
         }
@@ -205,13 +247,46 @@ class DamBreakCK
         if (decomposition) decomposition->rebuild();
         else water_cell_linked_list->exec();
         wall_cell_linked_list->exec();
-        water_block_update_complex_relation->exec();
+        if (q_.legacy) water_wall_complex->updateConfiguration();
+        else water_block_update_complex_relation->exec();
         fluid_acoustic_time_step->setPrimed(false);
+    }
+
+    // one advection step of the legacy case file, Dambreak.cpp:166-215
+    int stepOuterLegacy()
+    {
+        Real advection_dt = fluid_advection_time_step->exec();
+        fluid_density_summation->exec(); // fluid_density_by_summation
+        Real relaxation_time = 0, acoustic_dt = 0;
+        int n_inner = 0;
+        while (relaxation_time < advection_dt)
+        {
+            acoustic_dt = fluid_acoustic_time_step->exec();
+            fluid_acoustic_step_1st_half->exec(acoustic_dt); // fluid_pressure_relaxation
+            fluid_acoustic_step_2nd_half->exec(acoustic_dt); // fluid_density_relaxation
+            relaxation_time += acoustic_dt;
+            physical_time += acoustic_dt;
+            sv_physical_time->incrementValue(acoustic_dt);
+            ++n_inner;
+        }
+        acoustic_steps += n_inner;
+        number_of_iterations++;
+        if (q_.sort_interval > 0 && number_of_iterations % q_.sort_interval == 0 && number_of_iterations != 1)
+        {
+            particle_sort->exec(); // particle_sorting
+            fluid_acoustic_time_step->setPrimed(false);
+        }
+        water_cell_linked_list->exec();           // water_block.updateCellLinkedList()
+        water_wall_complex->updateConfiguration(); // neighbour lists + frozen pair geometry
+        last_acoustic_dt = acoustic_dt;
+        last_advection_dt = advection_dt;
+        return n_inner;
     }
 
     // one advection step, dambreak.cpp:188-222; returns the number of acoustic sub-steps taken
     int stepOuter()
     {
+        if (q_.legacy) return stepOuterLegacy();
         fluid_density_summation->exec();
         if (!q_.fused_regularization) fluid_density_regularization->exec();
         water_advection_step_setup->exec();

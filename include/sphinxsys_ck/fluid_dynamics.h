@@ -129,6 +129,8 @@ class FluidDynamicsBase
     RelationBase *inner_ = nullptr, *contact_ = nullptr;
     int riemann_ = 1, correction_ = 0, free_surface_ = 1;
     SlabDecomposition *decomposition_ = nullptr; // reductions become global when set
+    int formulation_ = 0;                        // 0 CK, 1 legacy (legacy_dynamics.h)
+    Real sigma0_ = 0, wall_rho0_ = 1;            // legacy DensitySummation constants
 
   public:
     void setDecomposition(SlabDecomposition *d) { decomposition_ = d; }
@@ -196,6 +198,16 @@ class FluidDynamicsBase
         f.posvolvel = p.deviceDataOrNull<GatherRecord8>("PosVolVel");
         f.active_begin = (uint32_t)p.activeBegin();
         f.active_end = (uint32_t)p.activeEnd();
+        if (formulation_ == 1)
+        {
+            // legacy state: Density/DensityChangeRate, positions advance inside the half steps (dpos aliases pos), pair
+            // geometry comes from the gather records frozen at the last updateConfiguration()
+            f.dpos = f.pos;
+            f.compression = nullptr;
+            f.compression_rate = (float *)p.deviceDataOrNull<Real>("DensityChangeRate");
+            f.compression_sum = (float *)p.deviceDataOrNull<Real>("DensitySummation");
+            f.posvolref = f.posvol; // no VolumetricMeasureRef in the legacy state: the summation ignores the weight
+        }
         return f;
     }
     sphb200_fluid_t material()
@@ -208,6 +220,9 @@ class FluidDynamicsBase
         m.correction = correction_;
         m.limiter_coeff = Real(3.0); // riemann_solver_ck.h:97
         m.free_surface = free_surface_;
+        m.formulation = formulation_;
+        m.sigma0 = sigma0_;
+        m.wall_rho0 = wall_rho0_;
         return m;
     }
     sphb200_fluid_args_t fluidArgs()
@@ -328,6 +343,7 @@ class AcousticTimeStepBase : public FluidDynamicsBase
         registerAcousticVariables();
     }
     Real ReducedValue() const { return reduced_; }
+    Real exec(Real dt = 0.0) { return deviceReduce(dt); } // same as ReduceDynamicsCK<...>::exec through a base pointer
     Real minimumSmoothingLength() const { return h_min_; }
     // hooks used by AcousticStep2ndHalf when the reduction is folded into its launch
     float *fusedSlot()

@@ -31,7 +31,8 @@ class KernelT(C.Structure):
 
 class FluidT(C.Structure):
     _fields_ = [("rho0", C.c_float), ("c0", C.c_float), ("riemann", C.c_int32), ("correction", C.c_int32),
-                ("limiter_coeff", C.c_float), ("free_surface", C.c_int32)]
+                ("limiter_coeff", C.c_float), ("free_surface", C.c_int32), ("formulation", C.c_int32),
+                ("sigma0", C.c_float), ("wall_rho0", C.c_float)]
 
 
 _P = C.c_void_p
@@ -59,7 +60,7 @@ class RelationT(C.Structure):
 
 class SearchT(C.Structure):
     _fields_ = [("tar_mesh", MeshT), ("kernel", KernelT), ("src_pos", _P), ("n_src", C.c_uint32), ("src_order", _P),
-                ("src_sorted_pos", _P), ("tar_pos", _P), ("tar_list", CellListT), ("is_inner", C.c_int32),
+                ("src_sorted_pos", _P), ("tar_pos", _P), ("tar_list", CellListT), ("is_inner", C.c_int32), ("legacy_criterion", C.c_int32),
                 ("search_depth", C.c_int32), ("src_begin", C.c_uint32), ("src_end", C.c_uint32), ("cell_ordered", C.c_int32)]
 
 
@@ -111,6 +112,7 @@ SYMBOLS = {
     "sphb200_update_position": (_I, [_CTX, C.POINTER(FluidView), _P]),
     "sphb200_advection_time_step": (_I, [_CTX, C.POINTER(FluidView), _F, _F, _F, C.POINTER(_F), C.POINTER(_F), _P]),
     "sphb200_acoustic_time_step": (_I, [_CTX, C.POINTER(FluidArgs), _F, _F, C.POINTER(_F), C.POINTER(_F), _P]),
+    "sphb200_advection_time_step_legacy": (_I, [_CTX, C.POINTER(FluidView), _F, _F, _F, C.POINTER(_F), C.POINTER(_F), _P]),
     "sphb200_acoustic_1st_half": (_I, [_CTX, C.POINTER(FluidArgs), _F, _P]),
     "sphb200_acoustic_2nd_half": (_I, [_CTX, C.POINTER(FluidArgs), _F, _F, _P, _P]),
     "sphb200_acoustic_1st_half_initialize": (_I, [_CTX, C.POINTER(FluidArgs), _F, _P]),

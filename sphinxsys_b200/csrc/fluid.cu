@@ -53,6 +53,9 @@ struct FArgs
     float wl_w_scale, wl_w_c4, wl_w_c5, wl_four_dq, wl_dw_a, wl_dw_c;
     float rho0, c0, p0, Z, inv_Z_sum, inv_Z_ave, Z_geo, inv_c_ave, limiter;
     int free_surface, dim;
+    int legacy;               // 1: state is Density/DensityChangeRate (in rho / Cdot), analytic kernel
+    float lg_sum_scale;       // legacy DensitySummation: rho0 / sigma0
+    float lg_wall_scale;      // rho0^2 / sigma0
 };
 
 // Per-interval cubic coefficients of the 4-point Lagrange interpolant (kernel_tabulated_ck.h:45-58).
@@ -134,7 +137,14 @@ static int make_fargs(sphb200_context *ctx, const sphb200_fluid_args_t *s, FArgs
             if (fabs((double)k.w[i] - w) > 2e-6 || fabs((double)k.dw[i] - dw) > 2e-6) is_wendland = false;
         }
         a->analytic = is_wendland ? 1 : 0;
-        const double dq4 = dq * dq * dq * dq;
+        a->legacy = s->material.formulation == 1;
+        if (a->legacy && !is_wendland)
+        {
+            snprintf(ctx->err, sizeof(ctx->err), "legacy formulation: only the Wendland C2 kernel has a device path");
+            return SPHB200_E_UNSUPPORTED;
+        }
+        // legacy evaluates the analytic kernel: same closed form with the interpolation-error term switched off
+        const double dq4 = a->legacy ? 0.0 : dq * dq * dq * dq;
         a->wl_w_scale = (float)w_scale;
         a->wl_w_c4 = (float)((-0.9375 + 2.0 * 0.125 * dq) * dq4 * w_scale);
         a->wl_w_c5 = (float)(0.125 * dq4 * w_scale);
@@ -146,6 +156,8 @@ static int make_fargs(sphb200_context *ctx, const sphb200_fluid_args_t *s, FArgs
     a->inv_dq = 20.0f / k.kernel_size;
     a->q_scale = inv_h * a->inv_dq; // r -> q / dq in one multiply
     a->W0 = (float)((k.dim == 2 ? sih * sih : sih * sih * sih) * k.dimension_factor * k.w[1]);
+    a->lg_sum_scale = s->material.sigma0 > 0.f ? s->material.rho0 / s->material.sigma0 : 0.f;
+    a->lg_wall_scale = s->material.sigma0 > 0.f ? s->material.rho0 * s->material.rho0 / s->material.sigma0 : 0.f;
     const sphb200_fluid_t &m = s->material;
     if (m.riemann < 0 || m.riemann > 2 || m.correction < 0 || m.correction > 1)
     {
@@ -399,6 +411,32 @@ __global__ void __launch_bounds__(256)
         v = fmaxf(v, acoustic_measure(vel[i], force[i], force_prior[i], mass[i], c0, h_min));
     block_max_to_global(v, out);
 }
+// legacy AcousticTimeStep::reduce = c0 + |v| (fluid_time_step.cpp:21-36)
+__global__ void __launch_bounds__(256) k_reduce_acoustic_legacy(u32 n, const float4 *__restrict__ vel, float c0, float *out)
+{
+    float v = 0.f;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        float4 u = vel[i];
+        v = fmaxf(v, __fadd_rn(c0, sqrtf(norm2_rn(u.x, u.y, u.z))));
+    }
+    block_max_to_global(v, out);
+}
+// legacy AdvectionViscousTimeStep / AdvectionTimeStep::reduce = max(|v|^2, 4 h |F + F_prior| / m) (fluid_time_step.cpp:38-59)
+__global__ void __launch_bounds__(256)
+    k_reduce_advection_legacy(u32 n, const float4 *__restrict__ vel, const float4 *__restrict__ force,
+                              const float4 *__restrict__ force_prior, const float *__restrict__ mass, float h_min, float *out)
+{
+    float v = 0.f;
+    for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+    {
+        float4 u = vel[i], F = force[i], Fp = force_prior[i];
+        float fn = sqrtf(norm2_rn(__fadd_rn(F.x, Fp.x), __fadd_rn(F.y, Fp.y), __fadd_rn(F.z, Fp.z)));
+        float acc = __fdiv_rn(__fmul_rn(__fmul_rn(4.0f, h_min), fn), mass[i]);
+        v = fmaxf(v, fmaxf(norm2_rn(u.x, u.y, u.z), acc));
+    }
+    block_max_to_global(v, out);
+}
 
 static int read_scalar(sphb200_context *ctx, float *host, cudaStream_t st)
 {
@@ -427,6 +465,25 @@ extern "C" int sphb200_advection_time_step(sphb200_context_t *ctx, const sphb200
     return 0;
 }
 
+extern "C" int sphb200_advection_time_step_legacy(sphb200_context_t *ctx, const sphb200_fluid_view_t *f, float h_min, float u_ref,
+                                                  float cfl, float *reduced_host, float *dt_host, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && f && f->vel && f->force && f->force_prior && f->mass, "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    SPH_CUDA(ctx, cudaMemsetAsync(ctx->dev_scalars, 0, sizeof(float), st));
+    Range r = active_range(f);
+    if (r.n)
+        SPH_LAUNCH(ctx, k_reduce_advection_legacy, min(sph_blocks(r.n, 256), 148u * 8u), 256, 0, st, r.n, (const float4 *)f->vel + r.b,
+                   (const float4 *)f->force + r.b, (const float4 *)f->force_prior + r.b, f->mass + r.b, h_min,
+                   (float *)ctx->dev_scalars);
+    float red;
+    int rc = read_scalar(ctx, &red, st);
+    if (rc) return rc;
+    if (reduced_host) *reduced_host = red;
+    if (dt_host) *dt_host = cfl * h_min / (fmaxf(sqrtf(red), u_ref) + 2.71051e-20f);
+    return 0;
+}
+
 extern "C" int sphb200_acoustic_time_step(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, float h_min, float cfl,
                                           float *reduced_host, float *dt_host, void *stream)
 {
@@ -435,7 +492,10 @@ extern "C" int sphb200_acoustic_time_step(sphb200_context_t *ctx, const sphb200_
     const sphb200_fluid_view_t &f = s->fluid;
     SPH_CUDA(ctx, cudaMemsetAsync(ctx->dev_scalars, 0, sizeof(float), st));
     Range r = active_range(&f);
-    if (r.n)
+    if (r.n && s->material.formulation == 1)
+        SPH_LAUNCH(ctx, k_reduce_acoustic_legacy, min(sph_blocks(r.n, 256), 148u * 8u), 256, 0, st, r.n, (const float4 *)f.vel + r.b,
+                   s->material.c0, (float *)ctx->dev_scalars);
+    else if (r.n)
         SPH_LAUNCH(ctx, k_reduce_acoustic, min(sph_blocks(r.n, 256), 148u * 8u), 256, 0, st, r.n, (const float4 *)f.vel + r.b,
                    (const float4 *)f.force + r.b, (const float4 *)f.force_prior + r.b, f.mass + r.b, s->material.c0, h_min,
                    (float *)ctx->dev_scalars);
@@ -501,7 +561,7 @@ __global__ void __launch_bounds__(FL_THREADS) k_compression_summation(FArgs a, K
     if (t < a.begin || t >= a.end) return;
     const u32 i = a.order ? a.order[t] : t;
     float4 xi = a.pos[i];
-    float s = a.W0 * a.vol_ref[i];
+    float s = a.legacy ? a.W0 : a.W0 * a.vol_ref[i];
     {
         u32 cnt = a.in_count[t];
         const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
@@ -512,9 +572,10 @@ __global__ void __launch_bounds__(FL_THREADS) k_compression_summation(FArgs a, K
             float4 xj = a.posvolref[j];
             float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
             float r = sqrtf(dx * dx + dy * dy + dz * dz);
-            s += kernel_w<ANALYTIC>(a, tab, r) * xj.w;
+            s += kernel_w<ANALYTIC>(a, tab, r) * (a.legacy ? 1.0f : xj.w);
         }
     }
+    float sw = 0.f; // legacy: wall part is weighted separately (density_summation.cpp:58-78)
     if (a.n_wall)
     {
         u32 cnt = a.ct_count[t];
@@ -526,8 +587,17 @@ __global__ void __launch_bounds__(FL_THREADS) k_compression_summation(FArgs a, K
             float4 xj = a.w_posvolref[j];
             float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
             float r = sqrtf(dx * dx + dy * dy + dz * dz);
-            s += kernel_w<ANALYTIC>(a, tab, r) * xj.w;
+            float w = kernel_w<ANALYTIC>(a, tab, r) * xj.w;
+            if (a.legacy) sw += w; else s += w;
         }
+    }
+    if (a.legacy)
+    {
+        // DensitySummation<Inner<FreeSurface>> + <Contact<>>: rho_sum = sigma rho0/sigma0 + (sum_wall W m_j/rho0_wall) rho0^2/(sigma0 m_i)
+        float rs = s * a.lg_sum_scale + sw * a.lg_wall_scale / a.mass[i];
+        a.Csum[i] = rs;
+        a.rho[i] = a.free_surface ? fmaxf(rs, a.rho0) : rs;
+        return;
     }
     a.Csum[i] = s;
     if (regularize)
@@ -545,8 +615,8 @@ extern "C" int sphb200_compression_summation(sphb200_context_t *ctx, const sphb2
     KTab wtab;
     int rc = make_fargs(ctx, s, &a, &wtab, nullptr);
     if (rc) return rc;
-    SPH_CHECK_ARG(ctx, a.n == 0 || (a.pos && a.posvolref && a.vol_ref && a.Csum && a.in_count && a.in_slice && a.in_index), "null fluid array");
-    SPH_CHECK_ARG(ctx, !regularize || (a.C && a.rho), "null fluid array");
+    SPH_CHECK_ARG(ctx, a.n == 0 || (a.pos && a.posvolref && (a.vol_ref || a.legacy) && a.Csum && a.in_count && a.in_slice && a.in_index), "null fluid array");
+    SPH_CHECK_ARG(ctx, a.legacy ? (a.rho && a.mass) : (!regularize || (a.C && a.rho)), "null fluid array");
     SPH_CHECK_ARG(ctx, a.n_wall == 0 || (a.w_posvolref && a.ct_count && a.ct_slice && a.ct_index), "null wall array");
     if (a.end > a.begin)
     {
@@ -587,9 +657,15 @@ __global__ void __launch_bounds__(256) k_a1_init(FArgs a, float dt)
 {
     u32 i = a.begin + blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= a.end) return;
-    float C = a.C[i] + 0.5f * dt * a.Cdot[i];
-    float rho = C * a.rho0;
-    a.C[i] = C;
+    float rho;
+    if (a.legacy) // Integration1stHalf::initialization, fluid_integration.hpp:49-56
+        rho = a.rho[i] + a.Cdot[i] * dt * 0.5f;
+    else
+    {
+        float C = a.C[i] + 0.5f * dt * a.Cdot[i];
+        rho = C * a.rho0;
+        a.C[i] = C;
+    }
     a.rho[i] = rho;
     a.p[i] = a.p0 * (rho / a.rho0 - 1.0f);
     float4 d = a.dpos[i], v = a.vel[i];
@@ -697,7 +773,7 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
     F.x += fx * vol_i; F.y += fy * vol_i; F.z += fz * vol_i;
     F.x += wx * vol_i; F.y += wy * vol_i; F.z += wz * vol_i;
     a.force[i] = F;
-    const float C_i = a.C[i];
+    const float C_i = a.legacy ? a.rho[i] : a.C[i];
     float cd = diss * C_i;
     cd += wdiss * C_i;
     a.Cdot[i] = cd;
@@ -714,7 +790,7 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
 
 static int check_acoustic_args(sphb200_context *ctx, const FArgs &a, bool second)
 {
-    SPH_CHECK_ARG(ctx, a.n == 0 || (a.posvol && a.vel && a.dpos && a.force && a.force_prior && a.mass && a.rho && a.p && a.C &&
+    SPH_CHECK_ARG(ctx, a.n == 0 || (a.posvol && a.vel && a.dpos && a.force && a.force_prior && a.mass && a.rho && a.p && (a.C || a.legacy) &&
                                     a.Cdot && a.in_count && a.in_slice && a.in_index),
                   "null fluid array");
     SPH_CHECK_ARG(ctx, a.n_wall == 0 || (a.w_posvol && a.ct_count && a.ct_slice && a.ct_index), "null wall array");
@@ -864,7 +940,7 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a2(FArgs a, KTab 
             }
         }
         const float vol_i = xi.w;
-        float C = a.C[i];
+        float C = a.legacy ? a.rho[i] : a.C[i];
         float cd = a.Cdot[i];
         cd += div * C;
         cd += wdiv * C;
@@ -873,10 +949,17 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a2(FArgs a, KTab 
         F.x += wx * vol_i; F.y += wy * vol_i; F.z += wz * vol_i;
         a.force[i] = F;
         // UpdateKernel::update, acoustic_step_2nd_half.hpp:83-89
-        C += 0.5f * dt * cd;
-        a.C[i] = C;
-        a.rho[i] = C * a.rho0;
-        if (next_reduced) measure = acoustic_measure(vi, F, a.force_prior[i], a.mass[i], a.c0, h_min);
+        if (a.legacy)
+            a.rho[i] = C + cd * dt * 0.5f; // Integration2ndHalf::update, fluid_integration.hpp:172-176
+        else
+        {
+            C += 0.5f * dt * cd;
+            a.C[i] = C;
+            a.rho[i] = C * a.rho0;
+        }
+        if (next_reduced)
+            measure = a.legacy ? __fadd_rn(a.c0, sqrtf(norm2_rn(vi.x, vi.y, vi.z)))
+                               : acoustic_measure(vi, F, a.force_prior[i], a.mass[i], a.c0, h_min);
     }
     if (next_reduced) block_max_to_global(measure, next_reduced);
 }

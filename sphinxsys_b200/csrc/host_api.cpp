@@ -52,6 +52,7 @@ extern "C"
         int32_t relation_stride;  // < 0: default; 0: exact two-phase build; > 0: one-pass stride
         double system_lower[3], system_upper[3]; // exact system bounds in Real (what the harness used for its lattice)
         int32_t use_system_bounds;
+        int32_t legacy;                  // legacy API/formulation (Integration1stHalf/2ndHalf, DensitySummation)
         int32_t rank, nranks;            // slab decomposition: one process per GPU
         uint8_t unique_id[128];          // communicator id from sphck_comm_unique_id on rank 0 (nranks > 1)
     };
@@ -127,6 +128,7 @@ extern "C"
             q.fused_time_step = o->fused_time_step != 0;
             q.fused_regularization = o->fused_regularization != 0;
             q.sort_interval = o->sort_interval;
+            q.legacy = o->legacy != 0;
             q.rank = o->rank;
             q.nranks = o->nranks > 0 ? o->nranks : 1;
             if (q.nranks > 1)
@@ -189,14 +191,18 @@ extern "C"
             else if (op == "gravity") s.constant_gravity->exec();
             else if (op == "cell_list_fluid") s.water_cell_linked_list->exec();
             else if (op == "cell_list_wall") s.wall_cell_linked_list->exec();
-            else if (op == "relations") s.water_block_update_complex_relation->exec();
+            else if (op == "relations")
+            {
+                if (s.water_wall_complex) s.water_wall_complex->updateConfiguration();
+                else s.water_block_update_complex_relation->exec();
+            }
             else if (op == "sort") { s.particle_sort->exec(); s.fluid_acoustic_time_step->setPrimed(false); }
             else if (op == "density_summation") s.fluid_density_summation->exec();
-            else if (op == "density_regularization") s.fluid_density_regularization->exec();
-            else if (op == "advection_setup") s.water_advection_step_setup->exec();
-            else if (op == "update_position") s.water_update_particle_position->exec();
+            else if (op == "density_regularization") { if (s.fluid_density_regularization) s.fluid_density_regularization->exec(); }
+            else if (op == "advection_setup") { if (s.water_advection_step_setup) s.water_advection_step_setup->exec(); }
+            else if (op == "update_position") { if (s.water_update_particle_position) s.water_update_particle_position->exec(); }
             else if (op == "advection_dt") r = s.fluid_advection_time_step->exec();
-            else if (op == "advection_dt_reduced") r = s.fluid_advection_time_step->ReducedValue();
+            else if (op == "advection_dt_reduced") r = s.advection_reduced_value();
             else if (op == "acoustic_dt") r = s.fluid_acoustic_time_step->exec();
             else if (op == "acoustic_dt_reduced") r = s.fluid_acoustic_time_step->ReducedValue();
             else if (op == "acoustic_dt_unprime") s.fluid_acoustic_time_step->setPrimed(false);

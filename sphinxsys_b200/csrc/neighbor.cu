@@ -160,6 +160,8 @@ struct SearchArgs
     u32 n_src;
     u32 src_begin, src_end; // source slots searched
     float inv_h, ks2;
+    float rc2; // legacy criterion threshold (kernel_size * h)^2
+    int legacy_criterion;
     int depth;
     int cell_ordered;
 };
@@ -182,6 +184,17 @@ __device__ __forceinline__ bool within(float4 xi, float4 xj, float inv_h, float 
     float sz = __fmul_rn(inv_h, __fsub_rn(xi.z, xj.z));
     float r2 = __fadd_rn(__fadd_rn(__fmul_rn(sx, sx), __fmul_rn(sy, sy)), __fmul_rn(sz, sz));
     return r2 < ks2;
+}
+// legacy NeighborBuilder criterion, kernels/base_kernel.h:105-114: displacement.squaredNorm() < rc_ref_sqr
+__device__ __forceinline__ bool within_legacy(float4 xi, float4 xj, float rc2)
+{
+    float dx = __fsub_rn(xi.x, xj.x), dy = __fsub_rn(xi.y, xj.y), dz = __fsub_rn(xi.z, xj.z);
+    float r2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    return r2 < rc2;
+}
+__device__ __forceinline__ bool criterion(const float4 &xi, const float4 &xj, float inv_h, float ks2, float rc2, int legacy)
+{
+    return legacy ? within_legacy(xi, xj, rc2) : within(xi, xj, inv_h, ks2);
 }
 
 // Enumerate candidates in the reference order: cells x -> y -> z (mesh_iterators.hpp:18-27); for fixed (x, y)
@@ -209,7 +222,7 @@ __device__ __forceinline__ void for_each_neighbor(const SearchArgs &a, u32 i, fl
                 if (SORTED)
                 {
                     float4 xj = a.tar_sorted_pos[k];
-                    if (within(xi, xj, a.inv_h, a.ks2))
+                    if (criterion(xi, xj, a.inv_h, a.ks2, a.rc2, a.legacy_criterion))
                     {
                         u32 j = a.particle_index[k];
                         if (!(INNER && j == i)) f(j);
@@ -220,7 +233,7 @@ __device__ __forceinline__ void for_each_neighbor(const SearchArgs &a, u32 i, fl
                     u32 j = a.particle_index[k];
                     if (INNER && j == i) continue;
                     float4 xj = a.tar_pos[j];
-                    if (within(xi, xj, a.inv_h, a.ks2)) f(j);
+                    if (criterion(xi, xj, a.inv_h, a.ks2, a.rc2, a.legacy_criterion)) f(j);
                 }
             }
         }
@@ -363,7 +376,7 @@ __global__ void __launch_bounds__(128)
                         {
                             const u32 b = __ffs(maybe) - 1;
                             maybe &= maybe - 1;
-                            if (within(xi, a.tar_pos[kb + b], a.inv_h, a.ks2)) sure |= 1u << b;
+                            if (criterion(xi, a.tar_pos[kb + b], a.inv_h, a.ks2, a.rc2, a.legacy_criterion)) sure |= 1u << b;
                         }
                         if (MODE == 0)
                             c += __popc(sure);
@@ -413,6 +426,11 @@ static int make_search(sphb200_context *ctx, const sphb200_search_t *s, SearchAr
     SPH_CHECK_ARG(ctx, a->src_begin <= a->src_end && a->src_end <= s->n_src, "source slot range outside [0, n_src)");
     a->inv_h = 1.0f / s->kernel.h; // inv_h_ = 1 / max(src_h, tar_h), neighbor_method.hpp:73-76
     a->ks2 = s->kernel.kernel_size * s->kernel.kernel_size;
+    {
+        float rc = s->kernel.kernel_size * s->kernel.h;
+        a->rc2 = rc * rc;
+    }
+    a->legacy_criterion = s->legacy_criterion;
     a->depth = s->search_depth;
     a->cell_ordered = s->cell_ordered;
     if (s->cell_ordered && s->n_src)

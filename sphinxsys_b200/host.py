@@ -28,7 +28,7 @@ class Options(C.Structure):
                 ("LL", C.c_double), ("LH", C.c_double), ("LW", C.c_double), ("correction", C.c_int32),
                 ("fused_time_step", C.c_int32), ("fused_regularization", C.c_int32), ("sort_interval", C.c_int32),
                 ("device", C.c_int32), ("relation_stride", C.c_int32), ("system_lower", C.c_double * 3),
-                ("system_upper", C.c_double * 3), ("use_system_bounds", C.c_int32), ("rank", C.c_int32),
+                ("system_upper", C.c_double * 3), ("use_system_bounds", C.c_int32), ("legacy", C.c_int32), ("rank", C.c_int32),
                 ("nranks", C.c_int32), ("unique_id", C.c_uint8 * 128)]
 
 
@@ -98,7 +98,7 @@ class DamBreakCK:
 
     def __init__(self, case=None, device_index=0, correction=False, fused_time_step=True, sort_interval=100,
                  relation_stride=None, fused_regularization=True, dim=3, dp=0.05, generate=False, rank=0, nranks=1,
-                 unique_id=None, width_scale=1.0):
+                 unique_id=None, width_scale=1.0, legacy=False):
         self.lib = load()
         o = Options()
         if case is not None:
@@ -112,6 +112,7 @@ class DamBreakCK:
         o.relation_stride = -1 if relation_stride is None else int(relation_stride)
         o.use_system_bounds = 0
         o.DW, o.LW = o.DW * width_scale, o.LW * width_scale
+        o.legacy = int(bool(legacy))
         o.rank, o.nranks = int(rank), int(nranks)
         if nranks > 1:
             if unique_id is None or len(unique_id) != 128:

@@ -353,6 +353,75 @@ def test_per_dynamics_parity_2d():
     _compare(gpu, o32, o64, ["CompressionRate", "Compression", "Density", "Pressure"], ["Force", "Velocity", "Displacement"], "2d_step", tol)
 
 
+@pytest.mark.parametrize("dim,dp", [(2, 0.025), (3, 0.05)])
+def test_legacy_formulation_parity(dim, dp):
+    """The legacy API (Integration1stHalf/2ndHalfWithWallRiemann, DensitySummationComplexFreeSurface, AcousticTimeStep,
+    AdvectionViscousTimeStep, InnerRelation/ContactRelation) against the oracle's legacy path
+    (fluid_integration.hpp:49-231, density_summation.cpp, fluid_time_step.cpp): neighbour lists bit-exact with the
+    |d|^2 < rc^2 criterion, fields within 1e-5 of the field norm over TWO acoustic steps (the second one exercises the
+    pair geometry frozen at the configuration update while positions have moved)."""
+    from sphinxsys_b200 import cases
+    case = cases.dam_break(dim=dim, dp=dp)
+    pos, vel = perturb_state(case)
+    case.fluid_pos = pos
+    gpu = make_gpu(case, fused_time_step=False, legacy=True)
+    gpu.upload("Velocity", vel)
+    gpu.initialize()
+    o32, o64 = make_oracle(case, f64=False), make_oracle(case, f64=True)
+    for o in (o32, o64):
+        o.real("Velocity", 3)[:] = vel.reshape(-1)
+        o.exec("prepare_legacy")
+    for contact, name in ((False, "inner"), (True, "contact")):
+        off, idx = gpu.export_csr(contact)
+        assert np.array_equal(off, o32.uint(f"{name}_offset")) and np.array_equal(idx, o32.uint(f"{name}_index")[: off[-1]])
+    tol = {"default": 1e-5, "Pressure": 3e-4, "DensityChangeRate": 5e-5, "Force": 5e-5}
+    adv = gpu.exec("advection_dt")
+    assert abs(adv - o32.exec("legacy_advection_dt")) <= 1e-6 * adv
+    gpu.exec("density_summation")
+    for o in (o32, o64):
+        o.exec("legacy_density_summation")
+    _compare(gpu, o32, o64, ["DensitySummation", "Density"], [], f"legacy{dim}d_density", tol)
+    for step in range(2):
+        ac = gpu.exec("acoustic_dt")
+        assert abs(ac - o32.exec("legacy_acoustic_dt")) <= 1e-6 * ac
+        dt = float(np.float32(ac))
+        gpu.exec("acoustic1", dt)
+        for o in (o32, o64):
+            o.exec("legacy1", dt)
+        _compare(gpu, o32, o64, ["Density", "Pressure", "DensityChangeRate"], ["Force", "Velocity", "Position"], f"legacy{dim}d_1st_{step}", tol)
+        gpu.exec("acoustic2", dt)
+        for o in (o32, o64):
+            o.exec("legacy2", dt)
+        _compare(gpu, o32, o64, ["Density", "DensityChangeRate"], ["Force", "Position"], f"legacy{dim}d_2nd_{step}", tol)
+
+
+def test_legacy_case_loop_drift_2d():
+    """Config 1 of BASELINE.json (test_2d_dambreak, legacy formulation) through the legacy case loop
+    (Dambreak.cpp:166-215) for 110 advection steps including the particle sort at step 100, against the oracle."""
+    from sphinxsys_b200 import cases
+    case = cases.dam_break(dim=2, dp=0.025)
+    gpu = make_gpu(case, fused_time_step=True, legacy=True)
+    gpu.initialize()
+    o32, o64 = make_oracle(case, f64=False), make_oracle(case, f64=True)
+    n_outer = 110
+    n_ac = gpu.run_outer(n_outer)
+    for o in (o32, o64):
+        o.exec("prepare_legacy")
+        o.exec("run_legacy", 1e9, n_outer, 1e9, 0)
+    assert int(o32.exec("acoustic_steps")) == n_ac
+    same_path = int(o64.exec("acoustic_steps")) == n_ac
+    assert np.array_equal(gpu_field(gpu, "OriginalID"), o32.uint("OriginalID"))
+    rep = {}
+    for nm, w, tol in (("Position", 3, 5e-6), ("Velocity", 3, 2e-4), ("Density", 1, 2e-6)):
+        e = rel_err(gpu_field(gpu, nm), oracle_field(o32, nm, w))
+        noise = rel_err(oracle_field(o32, nm, w), oracle_field(o64, nm, w)) if same_path else 0.0
+        rep[nm] = {"gpu_vs_oracle32": e, "oracle32_vs_oracle64": noise}
+        assert e <= max(tol, 2.0 * noise), f"{nm}: {e:.3e} (fp32 noise {noise:.3e})"
+    e_gpu, e_ref = gpu.energy(), o32.exec("energy")
+    assert abs(e_gpu - e_ref) <= 1e-5 * abs(e_ref)
+    _report("legacy_drift_2d", rep)
+
+
 def test_fused_time_step_equals_standalone():
     """The max folded into the 2nd-half launch must equal the stand-alone AcousticTimeStepCK reduction bit for bit."""
     from sphinxsys_b200 import cases
