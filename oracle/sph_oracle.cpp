@@ -360,6 +360,12 @@ void buildContact(CSR &csr, const CellList<R> &tar_cl, const R *src_pos, u32 n_s
                   const Crit &crit)
 {
     std::vector<u32> count(n_src + 1, 0);
+    if (tar_cl.cell_offset.empty()) // no contact body (or its cell list was never built): empty relation
+    {
+        csr.offset.assign(n_src + 1, 0);
+        csr.index.assign(1, 0);
+        return;
+    }
 #pragma omp parallel for schedule(dynamic, 256)
     for (long i = 0; i < (long)n_src; ++i)
     {

@@ -185,3 +185,25 @@ def fluid_block(n_side, dp=0.01, jitter=0.0, seed=1, dtype=np.float32, dim=3):
     if dim == 2:
         pos = np.concatenate([pos, np.zeros((pos.shape[0], 1))], axis=1)
     return np.ascontiguousarray(pos.astype(dtype))
+
+
+def random_block(n, seed=1, dp=0.01, dtype=np.float32, particles_per_cell=17.6):
+    """Config 5 of BASELINE.json (neighbour-search micro-benchmark): n positions uniform-random in a cube sized so that
+    a cell of the cell-linked list (edge = cut-off radius 2.6 dp) holds `particles_per_cell` particles on average.
+    Returned as a DamBreakCase-shaped object without walls so the oracle and the host layer can both consume it."""
+    R = dtype
+    h = 1.3 * dp
+    kernel = hm.make_kernel(h, 3, hm.KERNEL_WENDLAND_C2, dtype=R)
+    cell = kernel.cutoff
+    edge = cell * (n / particles_per_cell) ** (1.0 / 3.0)
+    rng = np.random.default_rng(seed)
+    pos = rng.uniform(0.0, edge, size=(n, 3)).astype(R)
+    case = DamBreakCase(3, dp, R, edge, edge, edge, edge, edge, edge, 0.0, 1.0, 1.0, 2.0, 20.0, h)
+    case.fluid_pos = np.ascontiguousarray(pos)
+    case.wall_pos = np.zeros((0, 3), dtype=R)
+    case.wall_normal = np.zeros((0, 3), dtype=R)
+    case.vol = float(R(dp) ** 3)
+    case.kernel = kernel
+    case.mesh = hm.make_mesh(np.zeros(3), np.full(3, edge), kernel.cutoff, 2, dtype=R)
+    case.sigma0 = hm.lattice_number_density(kernel, dp)
+    return case
