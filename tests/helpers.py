@@ -48,3 +48,21 @@ def perturb_state(case, seed=7, vel_scale=0.3, jitter=0.15):
     if d == 3:
         vel[:, 2] = 0.1 * vel_scale * np.sin(3.0 * pos[:, 0]) + 0.05 * rng.standard_normal(pos.shape[0])
     return pos.astype(case.dtype), vel.astype(case.dtype)
+
+
+def dtw_distance(a, b, window=5):
+    """Restatement of RegressionTestDynamicTimeWarping::calculateDTWDistance (dynamic_time_warping_method.hpp:17-55),
+    including its window handling (cells outside the band stay 0)."""
+    la, lb = len(a), len(b)
+    assert 0.8 * la <= lb <= 1.2 * la
+    D = np.zeros((la, lb))
+    D[0, 0] = abs(a[0] - b[0])
+    for i in range(1, la):
+        D[i, 0] = D[i - 1, 0] + abs(a[i] - b[0])
+    for j in range(1, lb):
+        D[0, j] = D[0, j - 1] + abs(a[0] - b[j])
+    w = max(window, abs(la - lb))
+    for i in range(1, la):
+        for j in range(max(1, i - w), min(lb, i + w)):
+            D[i, j] = abs(a[i] - b[j]) + min(D[i - 1, j], D[i, j - 1], D[i - 1, j - 1])
+    return float(D[la - 1, lb - 1])
