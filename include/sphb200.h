@@ -172,7 +172,22 @@ typedef struct
     int32_t cell_ordered;                 /* 1: src_pos and tar_pos are STORED in the cell order of their own lists
                                              (slot == particle id, particle_index == identity, src_order == NULL; see
                                              sphb200_cell_list_build_reorder): selects the warp-uniform search */
+    /* optional SECOND candidate set on the same mesh, searched after the first and appended to the same rows
+     * (cell_ordered searches only). Used for the periodic images of the target body, which are stored cell ordered
+     * behind its real particles: hits are recorded as tar2_index_base + (slot in tar2_pos). tar2_pos == NULL: none. */
+    const sphb200_vec4_t *tar2_pos;
+    sphb200_cell_list_t tar2_list;
+    uint32_t tar2_index_base;
 } sphb200_search_t;
+
+/* Periodic box of a body; ref: particle_dynamics/general_dynamics/domian_bouding/domain_bounding.h:48-66
+ * (PeriodicAlongAxis: bounding_bounds_, axis_, periodic_translation_ = upper - lower), one bit per periodic axis. */
+typedef struct
+{
+    float lower[3], upper[3]; /* bounding_bounds_ */
+    int32_t axes;             /* bit d: periodic along axis d */
+    float cutoff;             /* cut_off_radius_max_: images are made for particles closer than this to a periodic face */
+} sphb200_periodic_t;
 
 /* ---------------------------------------------------------------------------------------------------
  * context, diagnostics, memory  (replaces implementation_sycl.h:43-160 ExecutionInstance + USM helpers)
@@ -259,6 +274,24 @@ int sphb200_relation_fill(sphb200_context_t *ctx, const sphb200_search_t *search
  * sphb200_relation_count/_fill (nothing is silently dropped). */
 int sphb200_relation_build_fixed(sphb200_context_t *ctx, const sphb200_search_t *search, sphb200_relation_t rel,
                                  uint32_t stride, uint32_t *max_count_host, void *stream);
+/* PeriodicBounding::checkLowerBound/checkUpperBound for every periodic axis: x < lower -> x += L; x > upper -> x -= L.
+ * ref: domain_bounding.h:98-108 */
+int sphb200_periodic_bounding(sphb200_context_t *ctx, const sphb200_periodic_t *box, sphb200_vec4_t *pos, uint32_t n,
+                              void *stream);
+/* PeriodicCellLinkedList::exec for all periodic axes at once: every particle with lower < x < lower + cutoff gets an
+ * image at x + L, every particle with upper - cutoff < x < upper one at x - L, and the combinations over the axes
+ * (what the reference's axis-by-axis insertion of ghost list entries produces, domain_bounding.cpp:18-65).
+ * Images are written in ascending source order: image_pos[k] (translated position), image_src[k] (source particle).
+ * The number of images is returned in *count_host (synchronises); if it exceeds `capacity` nothing is written and
+ * SPHB200_E_CAPACITY is returned so the caller can grow the buffers. */
+int sphb200_periodic_images(sphb200_context_t *ctx, const sphb200_periodic_t *box, const sphb200_vec4_t *pos, uint32_t n,
+                            sphb200_vec4_t *image_pos, uint32_t *image_src, uint32_t capacity, uint32_t *count_host,
+                            void *stream);
+/* Refresh of image (ghost) particles stored behind the real ones: for g < n_ghost copies `copy_bytes` bytes at
+ * `offset_bytes` inside element ghost_src[g] of `array` to the same place inside element n_real + g.
+ * elem_bytes, offset_bytes and copy_bytes are multiples of 4. */
+int sphb200_ghost_copy(sphb200_context_t *ctx, void *array, uint32_t elem_bytes, uint32_t offset_bytes, uint32_t copy_bytes,
+                       const uint32_t *ghost_src, uint32_t n_real, uint32_t n_ghost, void *stream);
 /* SELL-32 (slot order) -> reference CSR indexed by particle id (particle_offset_[n+1], neighbor_index_[total]).
  * src_ids: slot -> id of the source particle (NULL: rel.order, else identity); tar_ids: stored target index -> id
  * (NULL: identity). Row order is preserved. */

@@ -39,12 +39,16 @@ class CellLinkedList
         return v;
     }
 };
-inline SPHBody::~SPHBody() {}
 inline CellLinkedList &SPHBody::getCellLinkedList()
 {
     if (!cell_linked_list_) cell_linked_list_.reset(new CellLinkedList(*this));
     return *cell_linked_list_;
 }
+} // namespace SPH
+#include "periodic_images.h"
+namespace SPH
+{
+inline SPHBody::~SPHBody() {}
 
 // ---------------------------------------------------------------------------------------------------------
 // relations
@@ -99,6 +103,8 @@ class RelationBase
     {
         sphb200_search_t s;
         std::memset(&s, 0, sizeof(s));
+        if (source_.periodicImages()) source_.periodicImages()->ensure();
+        if (target_.periodicImages()) target_.periodicImages()->ensure();
         CellLinkedList &tcl = target_.getCellLinkedList();
         s.tar_mesh = tcl.mesh_;
         s.kernel = kernel_;
@@ -112,6 +118,15 @@ class RelationBase
         s.src_begin = (uint32_t)source_.getBaseParticles().activeBegin();
         s.src_end = (uint32_t)source_.getBaseParticles().activeEnd();
         s.cell_ordered = (source_.isCellOrdered() && target_.isCellOrdered()) ? 1 : 0;
+        if (PeriodicImages *im = target_.periodicImages())
+            if (im->ghostParticles())
+            {
+                // the images of the target body: second candidate set, stored behind its real particles
+                if (!s.cell_ordered) throw SphError("periodic images need cell-ordered bodies");
+                s.tar2_pos = s.tar_pos + im->realParticles();
+                s.tar2_list = im->listView();
+                s.tar2_index_base = im->realParticles();
+            }
         return s;
     }
     void grow(uint64_t entries)
@@ -124,7 +139,7 @@ class RelationBase
     // the reference's particle_offset_/neighbor_index_ CSR, in REFERENCE particle ids (host arrays)
     void exportCSR(std::vector<uint32_t> &offset, std::vector<uint32_t> &index)
     {
-        uint32_t n = (uint32_t)source_.TotalRealParticles();
+        uint32_t n = (uint32_t)source_.getBaseParticles().hostSyncCount(); // rows of image particles are empty and not exported
         ExecutionInstance &ex = execution_instance();
         DeviceBuffer d_off((n + 2) * sizeof(uint32_t)), d_idx((std::max<uint64_t>(total_, 1)) * sizeof(uint32_t));
         SPHCK_CALL(sphb200_relation_export_csr, view(), n, source_.getBaseParticles().referenceID(),
@@ -174,6 +189,13 @@ template <class ExecutionPolicy, class BodyType = RealBody> class UpdateCellLink
     {
         BaseParticles &p = body_.getBaseParticles();
         CellLinkedList &cl = body_.getCellLinkedList();
+        if (PeriodicImages *im = body_.periodicImages())
+        {
+            // the images of the previous configuration are dropped; ghost_creation_ makes the new ones
+            p.setTotalRealParticles(im->realParticles());
+            p.setActiveRange(0, im->realParticles());
+            im->invalidate();
+        }
         uint32_t n = (uint32_t)p.TotalRealParticles();
         std::vector<DiscreteVariableBase *> vars = p.reorderedVariables();
         std::vector<void *> dst(vars.size());
@@ -209,8 +231,8 @@ template <class ExecutionPolicy, class... RelationTypes> class UpdateRelation : 
         ExecutionInstance &ex = execution_instance();
         for (RelationBase *r : relations_)
         {
-            uint32_t n = (uint32_t)r->source_.TotalRealParticles();
-            sphb200_search_t s = r->search();
+            sphb200_search_t s = r->search(); // creates pending periodic images first: they are stored particles too
+            uint32_t n = s.n_src;
             if (r->fixed_stride_)
             {
                 uint64_t need = (uint64_t)((n + 31) / 32) * 32ull * r->fixed_stride_;
@@ -254,7 +276,7 @@ template <class ExecutionPolicy> class ParticleSortCK : public BaseDynamics<void
     {
         ExecutionInstance &ex = execution_instance();
         BaseParticles &p = body_.getBaseParticles();
-        uint32_t n = (uint32_t)p.TotalRealParticles();
+        uint32_t n = (uint32_t)p.hostSyncCount(); // real particles (images of a periodic body are not renumbered)
         if (n == 0) return;
         size_t nb = ((size_t)n + 1) * sizeof(uint32_t);
         for (DeviceBuffer *b : {&keys_slot_, &keys_ref_, &perm_, &new_of_old_, &new_rid_, &carry_perm_}) b->ensure(nb);

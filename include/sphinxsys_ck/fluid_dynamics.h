@@ -97,6 +97,12 @@ class InteractionDynamicsBase : public BaseDynamics<void>
     InteractionDynamicsBase &addPostStateDynamics(BaseDynamics<void> &d) { post_processes_.push_back(&d); return *this; }
 };
 
+// dynamics whose initialize step writes something neighbours read in the interact step expose the two phases
+template <class T, class = void> struct HasInitializePhase : std::false_type {};
+template <class T>
+struct HasInitializePhase<T, std::void_t<decltype(std::declval<T &>().deviceInitialize(Real(0))), decltype(std::declval<T &>().deviceInteractAndUpdate(Real(0)))>>
+    : std::true_type {};
+
 template <class ExecutionPolicy, class InteractionType>
 class InteractionDynamicsCK : public InteractionType, public InteractionDynamicsBase
 {
@@ -108,8 +114,21 @@ class InteractionDynamicsCK : public InteractionType, public InteractionDynamics
     // runAllSteps (interaction_algorithms_ck.cpp:6-34): [initialize] -> pre -> interact(inner, contacts) -> post -> [update].
     // initialize/interact/update of one dynamics are fused inside the library wherever no neighbour reads the value
     // being written; a post process the library can fold into the same launch is handed to deviceInteract().
+    // With pre processes queued (e.g. the ghost update of a periodic condition, throat.cpp:183-184) a dynamics whose
+    // initialize step feeds its interact step runs initialize first, exactly as the reference orders them.
     void exec(Real dt = 0.0) override
     {
+        if constexpr (HasInitializePhase<InteractionType>::value)
+        {
+            if (!pre_processes_.empty())
+            {
+                this->deviceInitialize(dt);
+                for (auto *d : pre_processes_) d->exec(dt);
+                this->deviceInteractAndUpdate(dt);
+                for (auto *d : post_processes_) d->exec(dt);
+                return;
+            }
+        }
         for (auto *d : pre_processes_) d->exec(dt);
         std::vector<BaseDynamics<void> *> remaining = this->deviceInteract(dt, post_processes_);
         for (auto *d : remaining) d->exec(dt);
@@ -229,6 +248,7 @@ class FluidDynamicsBase
     {
         sphb200_fluid_args_t a;
         std::memset(&a, 0, sizeof(a));
+        if (sph_body_.periodicImages()) sph_body_.periodicImages()->ensure();
         sph_body_.refreshPosVol();
         a.fluid = fluidView();
         a.material = material();
@@ -414,9 +434,22 @@ template <> class CompressionSummation<Inner<>> : public FluidDynamicsBase
     explicit CompressionSummation(Inner<> &inner) : FluidDynamicsBase(inner, nullptr) { registerSummationVariables(); }
     std::vector<BaseDynamics<void> *> deviceInteract(Real, const std::vector<BaseDynamics<void> *> &post)
     {
+        int regularize = 0;
+        std::vector<BaseDynamics<void> *> remaining;
+        for (auto *d : post)
+        {
+            auto *reg = dynamic_cast<DensityRegularizationBase *>(d);
+            if (reg && &reg->getSPHBody() == &sph_body_ && !regularize)
+            {
+                regularize = 1;
+                free_surface_ = reg->flowType();
+            }
+            else
+                remaining.push_back(d);
+        }
         sphb200_fluid_args_t a = fluidArgs();
-        SPHCK_CALL(sphb200_compression_summation, &a, 0, execution_instance().stream());
-        return post;
+        SPHCK_CALL(sphb200_compression_summation, &a, regularize, execution_instance().stream());
+        return remaining;
     }
 };
 
@@ -433,6 +466,14 @@ template <class RiemannType, class CorrectionType>
 class AcousticStep1stHalfWithWall : public FluidDynamicsBase, public AcousticStep1stHalfPhases
 {
   public:
+    // AcousticStep1stHalf<Inner<OneLevel, Riemann, Correction>> without a contact part
+    explicit AcousticStep1stHalfWithWall(Inner<> &inner) : FluidDynamicsBase(inner, nullptr)
+    {
+        riemann_ = RiemannType::kind;
+        correction_ = CorrectionType::kind;
+        registerAcousticVariables();
+        if (correction_) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity());
+    }
     AcousticStep1stHalfWithWall(Inner<> &inner, Contact<> &contact) : FluidDynamicsBase(inner, &contact)
     {
         riemann_ = RiemannType::kind;
@@ -463,6 +504,13 @@ template <class RiemannType, class CorrectionType> class AcousticStep2ndHalfWith
     AcousticTimeStepBase *fused_time_step_ = nullptr;
 
   public:
+    explicit AcousticStep2ndHalfWithWall(Inner<> &inner) : FluidDynamicsBase(inner, nullptr)
+    {
+        riemann_ = RiemannType::kind;
+        correction_ = CorrectionType::kind;
+        registerAcousticVariables();
+        if (correction_) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity());
+    }
     AcousticStep2ndHalfWithWall(Inner<> &inner, Contact<> &contact) : FluidDynamicsBase(inner, &contact)
     {
         riemann_ = RiemannType::kind;
@@ -501,6 +549,12 @@ using AcousticStep1stHalfWithWallNoRiemannCK = AcousticStep1stHalfWithWall<NoRie
 using AcousticStep2ndHalfWithWallNoRiemannCK = AcousticStep2ndHalfWithWall<NoRiemannSolverCK, NoKernelCorrectionCK>;
 using AcousticStep1stHalfWithWallDissipativeRiemannCK = AcousticStep1stHalfWithWall<DissipativeRiemannSolverCK, NoKernelCorrectionCK>;
 using AcousticStep2ndHalfWithWallDissipativeRiemannCK = AcousticStep2ndHalfWithWall<DissipativeRiemannSolverCK, NoKernelCorrectionCK>;
+// AcousticStep1stHalf/2ndHalf<Inner<OneLevel, Riemann, NoKernelCorrectionCK>>: the same classes built from the inner
+// relation alone (bodies without walls, e.g. the periodic Taylor-Green vortex)
+using AcousticStep1stHalfInnerRiemannCK = AcousticStep1stHalfWithWallRiemannCK;
+using AcousticStep2ndHalfInnerRiemannCK = AcousticStep2ndHalfWithWallRiemannCK;
+using AcousticStep1stHalfInnerNoRiemannCK = AcousticStep1stHalfWithWallNoRiemannCK;
+using AcousticStep2ndHalfInnerNoRiemannCK = AcousticStep2ndHalfWithWallNoRiemannCK;
 } // namespace fluid_dynamics
 
 // ---- general dynamics ----

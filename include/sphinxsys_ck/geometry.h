@@ -189,6 +189,24 @@ class ComplexShape
     template <class ShapeType> void subtract(const Transform &t, const Vecd &halfsize) { items_.push_back({ShapeType(t, halfsize), false}); }
     template <class ShapeType> void add(const double center[3], const double halfsize[3]) { items_.push_back({ShapeType(center, halfsize), true}); }
     template <class ShapeType> void subtract(const double center[3], const double halfsize[3]) { items_.push_back({ShapeType(center, halfsize), false}); }
+    // bounding box of the added sub-shapes (Shape::getBounds), rounded once to Real
+    BoundingBoxd getBounds() const
+    {
+        double lo[3] = {1e300, 1e300, 1e300}, up[3] = {-1e300, -1e300, -1e300};
+        bool any = false;
+        for (const Item &it : items_)
+            if (it.add)
+            {
+                any = true;
+                for (int d = 0; d < 3; ++d)
+                {
+                    lo[d] = std::fmin(lo[d], it.box.center_[d] - it.box.halfsize_[d]);
+                    up[d] = std::fmax(up[d], it.box.center_[d] + it.box.halfsize_[d]);
+                }
+            }
+        if (!any) return BoundingBoxd();
+        return BoundingBoxd(Vecd(Real(lo[0]), Real(lo[1]), Real(lo[2])), Vecd(Real(up[0]), Real(up[1]), Real(up[2])));
+    }
     bool checkContain(const Vecd &p, int dim) const
     {
         bool in = false;

@@ -186,6 +186,9 @@ class BaseParticles
         active_begin_ = b;
         active_end_ = e;
     }
+    // particles the host sees through DiscreteVariable::Data(): the real ones. Image (ghost) particles of a periodic
+    // body are stored behind them ([activeEnd, TotalRealParticles)) and never cross to the host.
+    size_t hostSyncCount() const { return active_begin_ == 0 && active_end_ <= total_real_particles_ ? active_end_ : total_real_particles_; }
     const std::vector<DiscreteVariableBase *> &allVariablesInOrder() const { return ordered_; }
     uint64_t storageVersion() const { return storage_version_; }
 
@@ -275,7 +278,7 @@ class BaseParticles
     // slot of reference id r (inverse of ReferenceID), cached per storage version
     uint32_t *inverseReferenceID()
     {
-        uint32_t n = (uint32_t)total_real_particles_;
+        uint32_t n = (uint32_t)hostSyncCount();
         inverse_.ensure((n + 1) * sizeof(uint32_t));
         if (inverse_version_ != storage_version_)
         {
@@ -288,7 +291,7 @@ class BaseParticles
     // ---- host <-> device, through the reference order ----
     template <class T> void upload(DiscreteVariable<T> *v, const T *host)
     {
-        uint32_t n = (uint32_t)total_real_particles_;
+        uint32_t n = (uint32_t)hostSyncCount();
         if (n == 0) return;
         ExecutionInstance &ex = execution_instance();
         const uint32_t eb = v->deviceElementBytes();
@@ -317,7 +320,7 @@ class BaseParticles
     }
     template <class T> void download(DiscreteVariable<T> *v, T *host)
     {
-        uint32_t n = (uint32_t)total_real_particles_;
+        uint32_t n = (uint32_t)hostSyncCount();
         if (n == 0) return;
         ExecutionInstance &ex = execution_instance();
         const uint32_t eb = v->deviceElementBytes();
@@ -435,6 +438,8 @@ class SPHSystem
 };
 
 class CellLinkedList;
+class PeriodicImages;
+template <typename... T> class Ghost;
 
 class SPHBody
 {
@@ -446,6 +451,8 @@ class SPHBody
     std::unique_ptr<BaseParticles> particles_;
     std::unique_ptr<BaseMaterial> material_;
     std::unique_ptr<CellLinkedList> cell_linked_list_;
+    std::unique_ptr<PeriodicImages> periodic_images_; // periodic_images.h; null for bodies without periodic conditions
+    size_t particle_reserve_ = 0;                     // room for ghost particles behind the real ones
     bool posvol_dirty_ = true;
     bool cell_ordered_ = false;
 
@@ -474,6 +481,11 @@ class SPHBody
     ComplexShape &getInitialShape() { return *shape_; }
     size_t TotalRealParticles() { return getBaseParticles().TotalRealParticles(); }
     CellLinkedList &getCellLinkedList();
+    PeriodicImages *periodicImages() { return periodic_images_.get(); }
+    PeriodicImages &definePeriodicImages();
+    // the bounds of the body shape (base_body.cpp: getSPHBodyBounds)
+    BoundingBoxd getSPHBodyBounds() { return shape_->getBounds(); }
+    void reserveParticles(size_t extra) { particle_reserve_ += extra; }
     template <class MaterialType, typename... Args> MaterialType *defineMatterMaterial(Args &&...args)
     {
         MaterialType *m = new MaterialType(std::forward<Args>(args)...);
@@ -487,6 +499,24 @@ class SPHBody
         Real vol = Real(std::pow(sph_system_.global_resolution_, Real(sph_system_.dim_)));
         generateParticlesFromPositions(pos, vol);
     }
+    // generateParticlesWithReserve<BaseParticles, Lattice>(ghost_x, ghost_y, ...): room for the ghost particles of the
+    // periodic conditions is reserved behind the real particles (base_body.h generateParticlesWithReserve,
+    // particle_reserve.h, ghost_bounding.cpp:9-26)
+    template <class ParticlesType, class Generator, class... Reserves> void generateParticlesWithReserve(Reserves &...reserves)
+    {
+        std::vector<Vecd> pos = generateLattice(*shape_, sph_system_.system_domain_bounds_, sph_system_.global_resolution_, sph_system_.dim_);
+        Real vol = Real(std::pow(sph_system_.global_resolution_, Real(sph_system_.dim_)));
+        reserveFor(reserves...);
+        generateParticlesFromPositions(pos, vol);
+    }
+    // the same reservation for particles handed over by the caller (reload files, harness-generated lattices)
+    template <class... Reserves> void reserveFor(Reserves &...reserves)
+    {
+        size_t dummy[] = {0, (particle_reserve_ += reserves.reserveSize(sph_system_.global_resolution_, sph_system_.dim_), size_t(0))...};
+        (void)dummy;
+        int dummy2[] = {0, (reserves.setReserved(), 0)...};
+        (void)dummy2;
+    }
     // positions handed over by the caller (e.g. a reload file): base_particles.cpp:33-36, base_material.cpp:37-40
     // `bound` reserves room for migrated and ghost particles; `reference_ids` (optional) are the global particle
     // numbers of a decomposed run (default: 0..n-1)
@@ -494,6 +524,7 @@ class SPHBody
                                         const std::vector<UnsignedInt> *reference_ids = nullptr)
     {
         size_t n = pos.size();
+        if (bound == 0 && particle_reserve_) bound = n + particle_reserve_;
         particles_.reset(new BaseParticles(n, bound));
         BaseParticles &p = *particles_;
         auto *dv_pos = p.registerStateVariable<Vecd>("Position");
@@ -523,6 +554,7 @@ class SPHBody
     }
     // (x, y, z, Vol) gather record; refreshed lazily whenever Position or VolumetricMeasure changed
     void setPosVolDirty() { posvol_dirty_ = true; }
+    bool recordsDirty() const { return posvol_dirty_; }
     void refreshPosVol()
     {
         if (!posvol_dirty_) return;

@@ -1,0 +1,198 @@
+// sphinxsys_ck/taylor_green_case.h — periodic Taylor-Green vortex (2-D and 3-D) on the CK dynamics: the periodic
+// boundary path of the hot path (BASELINE config 4).
+//
+// The reference offers periodic conditions on its TBB path only; this case is the CK spelling of
+//   tests/2d_examples/test_2d_taylor_green/taylor_green.cpp:62-200 (bodies, initial condition, loop order:
+//       bounding -> cell-linked list -> periodic images -> configuration)
+// with the ghost-particle form of the periodic condition used as in
+//   tests/2d_examples/test_2d_throat/throat.cpp:137-138,182-184,204-205,271-278
+//       (Ghost<PeriodicAlongAxis>, generateParticlesWithReserve, ghost_update_ as pre-process of the half steps)
+// and the acoustic/advection sequencing of tests/tests_sycl/3d_examples/test_3d_dambreak_sycl/dambreak.cpp:188-222.
+// Inviscid, no transport-velocity correction (those dynamics are outside SURVEY.md §8a).
+#ifndef SPHINXSYS_CK_TAYLOR_GREEN_CASE_H
+#define SPHINXSYS_CK_TAYLOR_GREEN_CASE_H
+
+#include <functional>
+
+#include "sphinxsys_ck.h"
+
+namespace SPH
+{
+struct TaylorGreenParameters
+{
+    int dim = 3;
+    double dp = 1.0 / 32.0;   // global_resolution
+    double L = 1.0;           // DL = DH (= DW): the periodic box is [0, L]^dim (taylor_green.cpp:14-15)
+    double rho0_f = 1.0, U_f = 1.0; // :19-20; c_f = 10 U_f
+    int sort_interval = 100;
+    bool fused_time_step = true;
+    bool fused_regularization = true;
+};
+
+class TaylorGreenWaterBlock : public ComplexShape
+{
+  public:
+    TaylorGreenWaterBlock(const std::string &name, const TaylorGreenParameters &q) : ComplexShape(name)
+    {
+        double half[3] = {0.5 * q.L, 0.5 * q.L, q.dim == 3 ? 0.5 * q.L : 0.0};
+        add<GeometricShapeBox>(half, half);
+    }
+};
+
+class TaylorGreenCK
+{
+  public:
+    using P = MainExecutionPolicy;
+    using GhostUpdate = PeriodicConditionUsingGhostParticles::Update;
+    TaylorGreenParameters q_;
+    Real U_f_, c_f_;
+    SPHSystem sph_system;
+    FluidBody water_block;
+    std::vector<std::unique_ptr<Ghost<PeriodicAlongAxis>>> ghost_along_axis;
+    std::unique_ptr<Inner<>> water_block_inner;
+    std::unique_ptr<UpdateCellLinkedList<P, RealBody>> water_cell_linked_list;
+    std::unique_ptr<UpdateRelation<P, Inner<>>> water_block_update_inner_relation;
+    std::unique_ptr<ParticleSortCK<P>> particle_sort;
+    std::unique_ptr<StateDynamics<P, fluid_dynamics::AdvectionStepSetup>> water_advection_step_setup;
+    std::unique_ptr<StateDynamics<P, fluid_dynamics::UpdateParticlePosition>> water_update_particle_position;
+    std::unique_ptr<InteractionDynamicsCK<P, fluid_dynamics::AcousticStep1stHalfInnerRiemannCK>> fluid_acoustic_step_1st_half;
+    std::unique_ptr<InteractionDynamicsCK<P, fluid_dynamics::AcousticStep2ndHalfInnerRiemannCK>> fluid_acoustic_step_2nd_half;
+    std::unique_ptr<InteractionDynamicsCK<P, fluid_dynamics::CompressionSummation<Inner<>>>> fluid_density_summation;
+    std::unique_ptr<StateDynamics<P, fluid_dynamics::DensityRegularization<SPHBody, WeaklyCompressibleFluid, Internal>>> fluid_density_regularization;
+    std::unique_ptr<ReduceDynamicsCK<P, fluid_dynamics::AdvectionTimeStepCK>> fluid_advection_time_step;
+    std::unique_ptr<ReduceDynamicsCK<P, fluid_dynamics::AcousticTimeStepCK<WeaklyCompressibleFluid>>> fluid_acoustic_time_step;
+    std::vector<std::unique_ptr<PeriodicConditionUsingGhostParticles>> periodic_condition; // x, y(, z)
+    std::unique_ptr<GhostUpdate> volume_ghost_update, pressure_ghost_update, velocity_ghost_update;
+    Gravity no_gravity;
+    std::unique_ptr<ReduceDynamicsCK<P, TotalMechanicalEnergyCK>> record_total_kinetic_energy; // zero gravity: kinetic part only
+    SingleVariable<Real> *sv_physical_time = nullptr;
+    size_t number_of_iterations = 0, acoustic_steps = 0;
+    double physical_time = 0;
+    Real last_acoustic_dt = 0, last_advection_dt = 0;
+
+    static BoundingBoxd caseBounds(const TaylorGreenParameters &q)
+    {
+        return BoundingBoxd(Vecd(0, 0, 0), Vecd(Real(q.L), Real(q.L), q.dim == 3 ? Real(q.L) : Real(0)));
+    }
+    // TaylorGreenInitialCondition (taylor_green.cpp:44-57) and its usual 3-D extension
+    static Vecd initialVelocity(const Vecd &x, int dim, Real U)
+    {
+        const double two_pi = 2.0 * 3.14159265358979323846;
+        if (dim == 2)
+            return Vecd(Real(-U * std::cos(two_pi * x.x) * std::sin(two_pi * x.y)), Real(U * std::sin(two_pi * x.x) * std::cos(two_pi * x.y)), 0);
+        return Vecd(Real(U * std::sin(two_pi * x.x) * std::cos(two_pi * x.y) * std::cos(two_pi * x.z)),
+                    Real(-U * std::cos(two_pi * x.x) * std::sin(two_pi * x.y) * std::cos(two_pi * x.z)), 0);
+    }
+
+    // positions / velocities == nullptr: lattice and analytic initial condition generated here; otherwise the
+    // arrays handed over (packed xyz, reference order), e.g. a jittered lattice made by the harness
+    explicit TaylorGreenCK(const TaylorGreenParameters &q, const std::vector<Vecd> *positions = nullptr,
+                           const std::vector<Vecd> *velocities = nullptr, const BoundingBoxd *exact_system_bounds = nullptr)
+        : q_(q), U_f_(Real(q.U_f)), c_f_(Real(10.0) * U_f_), sph_system(caseBounds(q), Real(q.dp), q.dim),
+          water_block(sph_system, makeShared<TaylorGreenWaterBlock>("WaterBody", q)), no_gravity(Vecd(0, 0, 0))
+    {
+        using namespace fluid_dynamics;
+        if (exact_system_bounds) sph_system.setSystemDomainBoundsExact(*exact_system_bounds);
+        water_block.defineMatterMaterial<WeaklyCompressibleFluid>(Real(q.rho0_f), c_f_);
+        BoundingBoxd box = water_block.getSPHBodyBounds();
+        for (int a = 0; a < q.dim; ++a) ghost_along_axis.emplace_back(new Ghost<PeriodicAlongAxis>(box, a));
+        if (q.dim == 3) water_block.reserveFor(*ghost_along_axis[0], *ghost_along_axis[1], *ghost_along_axis[2]);
+        else water_block.reserveFor(*ghost_along_axis[0], *ghost_along_axis[1]);
+        if (positions) water_block.generateParticlesFromPositions(*positions, Real(std::pow(Real(q.dp), Real(q.dim))));
+        else water_block.generateParticles<BaseParticles, Lattice>();
+
+        water_block_inner.reset(new Inner<>(water_block));
+        water_cell_linked_list.reset(new UpdateCellLinkedList<P, RealBody>(water_block));
+        water_block_update_inner_relation.reset(new UpdateRelation<P, Inner<>>(*water_block_inner));
+        particle_sort.reset(new ParticleSortCK<P>(water_block));
+        water_advection_step_setup.reset(new StateDynamics<P, AdvectionStepSetup>(water_block));
+        water_update_particle_position.reset(new StateDynamics<P, UpdateParticlePosition>(water_block));
+        fluid_acoustic_step_1st_half.reset(new InteractionDynamicsCK<P, AcousticStep1stHalfInnerRiemannCK>(*water_block_inner));
+        fluid_acoustic_step_2nd_half.reset(new InteractionDynamicsCK<P, AcousticStep2ndHalfInnerRiemannCK>(*water_block_inner));
+        fluid_density_summation.reset(new InteractionDynamicsCK<P, CompressionSummation<Inner<>>>(*water_block_inner));
+        fluid_density_regularization.reset(new StateDynamics<P, DensityRegularization<SPHBody, WeaklyCompressibleFluid, Internal>>(water_block));
+        if (q.fused_regularization) fluid_density_summation->addPostStateDynamics(*fluid_density_regularization);
+        fluid_advection_time_step.reset(new ReduceDynamicsCK<P, AdvectionTimeStepCK>(water_block, U_f_));
+        fluid_acoustic_time_step.reset(new ReduceDynamicsCK<P, AcousticTimeStepCK<WeaklyCompressibleFluid>>(water_block));
+        if (q.fused_time_step) fluid_acoustic_step_2nd_half->fuseTimeStepReduction(*fluid_acoustic_time_step);
+        for (int a = 0; a < q.dim; ++a)
+            periodic_condition.emplace_back(new PeriodicConditionUsingGhostParticles(water_block, *ghost_along_axis[a]));
+        // what the neighbours of a ghost read, refreshed where it changes (throat.cpp:183-184 queues ghost_update_ the same way)
+        PeriodicImages &images = periodic_condition[0]->images();
+        volume_ghost_update.reset(new GhostUpdate(images, {"VolumetricMeasure"}));
+        pressure_ghost_update.reset(new GhostUpdate(images, {"Pressure"}));
+        velocity_ghost_update.reset(new GhostUpdate(images, {"PosVolVel"}));
+        fluid_acoustic_step_1st_half->addPreContactInteraction(*pressure_ghost_update);
+        fluid_acoustic_step_2nd_half->addPreContactInteraction(*velocity_ghost_update);
+        record_total_kinetic_energy.reset(new ReduceDynamicsCK<P, TotalMechanicalEnergyCK>(water_block, no_gravity));
+        sv_physical_time = sph_system.getSystemVariableByName<Real>("PhysicalTime");
+
+        // initial_condition.exec()
+        BaseParticles &particles = water_block.getBaseParticles();
+        auto *dv_vel = particles.getVariableByName<Vecd>("Velocity");
+        size_t n = particles.TotalRealParticles();
+        if (velocities)
+        {
+            if (velocities->size() != n) throw SphError("TaylorGreenCK: velocity array size mismatch");
+            for (size_t i = 0; i < n; ++i) dv_vel->Data()[i] = (*velocities)[i];
+        }
+        else
+        {
+            auto *dv_pos = particles.getVariableByName<Vecd>("Position");
+            dv_pos->synchronizeWithDevice();
+            for (size_t i = 0; i < n; ++i) dv_vel->Data()[i] = initialVelocity(dv_pos->Data()[i], q.dim, U_f_);
+        }
+        dv_vel->synchronizeToDevice();
+    }
+
+    // bounding -> cell-linked list -> periodic images -> configuration (taylor_green.cpp:186-191)
+    void updateConfiguration(bool bounding)
+    {
+        if (bounding)
+            for (auto &pc : periodic_condition) pc->bounding_.exec();
+        water_cell_linked_list->exec();
+        for (auto &pc : periodic_condition) pc->ghost_creation_.exec();
+        water_block_update_inner_relation->exec();
+    }
+    void initialize()
+    {
+        updateConfiguration(false); // taylor_green.cpp:131-134
+        fluid_acoustic_time_step->setPrimed(false);
+    }
+
+    // one advection step; returns the number of acoustic sub-steps taken
+    int stepOuter()
+    {
+        fluid_density_summation->exec();
+        if (!q_.fused_regularization) fluid_density_regularization->exec();
+        water_advection_step_setup->exec();
+        volume_ghost_update->exec(); // neighbours read V_j of the images
+        Real advection_dt = fluid_advection_time_step->exec();
+        Real relaxation_time = 0, acoustic_dt = 0;
+        int n_inner = 0;
+        while (relaxation_time < advection_dt)
+        {
+            acoustic_dt = fluid_acoustic_time_step->exec();
+            fluid_acoustic_step_1st_half->exec(acoustic_dt); // initialize -> ghost pressure -> interact + update
+            fluid_acoustic_step_2nd_half->exec(acoustic_dt); // ghost velocity -> one fused launch
+            relaxation_time += acoustic_dt;
+            physical_time += acoustic_dt;
+            sv_physical_time->incrementValue(acoustic_dt);
+            ++n_inner;
+        }
+        acoustic_steps += n_inner;
+        water_update_particle_position->exec();
+        number_of_iterations++;
+        if (q_.sort_interval > 0 && number_of_iterations % q_.sort_interval == 0 && number_of_iterations != 1)
+        {
+            particle_sort->exec();
+            fluid_acoustic_time_step->setPrimed(false);
+        }
+        updateConfiguration(true);
+        last_acoustic_dt = acoustic_dt;
+        last_advection_dt = advection_dt;
+        return n_inner;
+    }
+};
+} // namespace SPH
+#endif

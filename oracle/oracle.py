@@ -36,7 +36,8 @@ class ParamsPOD(C.Structure):
                 ("rho0", C.c_double), ("c0", C.c_double), ("gravity", C.c_double * 3), ("U_ref", C.c_double),
                 ("h_min", C.c_double), ("acoustic_cfl", C.c_double), ("advection_cfl", C.c_double),
                 ("correction_alpha", C.c_double), ("sigma0", C.c_double), ("wall_rho0", C.c_double),
-                ("contact_depth", C.c_int), ("threads", C.c_int)]
+                ("contact_depth", C.c_int), ("threads", C.c_int), ("periodic_axes", C.c_int),
+                ("periodic_lower", C.c_double * 3), ("periodic_upper", C.c_double * 3), ("periodic_cutoff", C.c_double)]
 
 
 _lib = None
@@ -133,6 +134,12 @@ class OracleSim:
         p.U_ref, p.h_min = case.U_ref, case.kernel.h
         p.acoustic_cfl, p.advection_cfl, p.correction_alpha = 0.6, 0.25, 0.5
         p.sigma0, p.wall_rho0, p.contact_depth, p.threads = case.sigma0, 1.0, contact_depth, threads
+        p.periodic_axes = int(getattr(case, "periodic_axes", 0))
+        if p.periodic_axes:
+            for d in range(3):
+                p.periodic_lower[d] = case.periodic_lower[d]
+                p.periodic_upper[d] = case.periodic_upper[d]
+            p.periodic_cutoff = float(self.dtype(case.kernel.cutoff))
         self._params = p
         kp, mp = kernel_pod(case.kernel), mesh_pod(case.mesh)
         self._h = lib().orc_create(int(f64), C.byref(p), C.byref(kp), C.byref(mp), C.byref(mp), case.n_fluid, case.n_wall)
@@ -144,6 +151,8 @@ class OracleSim:
         self.real("Mass")[:] = case.rho0 * case.vol
         self.real("Density")[:] = case.rho0
         self.real("Compression")[:] = 1.0
+        if getattr(case, "fluid_vel", None) is not None:
+            self.real("Velocity", 3)[:] = case.fluid_vel.reshape(-1)
         if case.n_wall:
             self.real("Position", 3, wall=True)[:] = case.wall_pos.reshape(-1)
             self.real("VolumetricMeasure", wall=True)[:] = case.vol

@@ -280,12 +280,19 @@ u32 exclusiveScan(const u32 *in, u32 *out, u32 n)
 struct CSR
 {
     std::vector<u32> offset, index;
+    std::vector<unsigned char> shift; // periodic runs: image code of every entry (13 = the particle itself), else empty
 };
 
+// Periodic runs follow PeriodicConditionUsingCellLinkedList (particle_dynamics/general_dynamics/domian_bouding/
+// domain_bounding.cpp:18-65): besides the particles, the cell-linked list holds ghost ENTRIES (source index,
+// translated position); `ext_*` is that entry table (real particles first), `particle_index` then holds entry ids.
 template <class R> struct CellList
 {
     Mesh<R> mesh;
     std::vector<u32> cell_offset, particle_index;
+    std::vector<u32> ext_index;           // entry -> source particle
+    std::vector<R> ext_pos;               // entry -> (translated) position
+    std::vector<unsigned char> ext_shift; // entry -> image code (sx+1) + 3 (sy+1) + 9 (sz+1), s in {-1, 0, +1}
 };
 
 // ref: shared_ck/.../update_cell_linked_list.hpp:40-106 (count -> scan -> fill)
@@ -336,21 +343,33 @@ template <class R, class Crit>
 void buildInner(CSR &csr, const CellList<R> &cl, const R *pos, u32 n, const Crit &crit)
 {
     std::vector<u32> count(n + 1, 0);
+    const bool ext = !cl.ext_index.empty(); // periodic: the list holds entries (source, translated position)
+    const R *epos = ext ? cl.ext_pos.data() : pos;
+    // an entry is a neighbour unless it is the particle itself (a particle's own images count only in boxes narrower
+    // than two cut-off radii, which the periodic conditions do not support)
+    auto hit = [&](long i, u32 e) { return e != (u32)i && crit(pos + 3 * i, epos + 3 * e); };
 #pragma omp parallel for schedule(dynamic, 256)
     for (long i = 0; i < (long)n; ++i)
     {
         u32 c = 0;
-        searchBox(cl, pos + 3 * i, 1, [&](u32 j) { if (j != (u32)i && crit(pos + 3 * i, pos + 3 * j)) ++c; });
+        searchBox(cl, pos + 3 * i, 1, [&](u32 e) { if (hit(i, e)) ++c; });
         count[i] = c;
     }
     csr.offset.assign(n + 1, 0);
     exclusiveScan(count.data(), csr.offset.data(), n + 1);
     csr.index.assign(std::max<u32>(csr.offset[n], 1), 0);
+    csr.shift.clear();
+    if (ext) csr.shift.assign(csr.index.size(), 13);
 #pragma omp parallel for schedule(dynamic, 256)
     for (long i = 0; i < (long)n; ++i)
     {
         u32 k = csr.offset[i];
-        searchBox(cl, pos + 3 * i, 1, [&](u32 j) { if (j != (u32)i && crit(pos + 3 * i, pos + 3 * j)) csr.index[k++] = j; });
+        searchBox(cl, pos + 3 * i, 1, [&](u32 e) {
+            if (!hit(i, e)) return;
+            if (ext) { csr.index[k] = cl.ext_index[e]; csr.shift[k] = cl.ext_shift[e]; }
+            else csr.index[k] = e;
+            ++k;
+        });
     }
 }
 
@@ -405,6 +424,9 @@ struct ParamsPOD
     double wall_rho0;       // legacy: Solid reference density (1.0)
     int contact_depth;      // search depth in the wall mesh (cell_linked_list.hpp:161-167)
     int threads;            // 0 = leave OpenMP default
+    int periodic_axes;      // bit d: periodic along axis d (PeriodicAlongAxis, domain_bounding.h:48-66)
+    double periodic_lower[3], periodic_upper[3]; // bounding_bounds_ (already rounded to Real by the caller)
+    double periodic_cutoff; // cut_off_radius_max_
 };
 
 template <class R> struct Body
@@ -494,7 +516,81 @@ template <class R> struct Sim
     // =================================================================================
     // configuration dynamics
     // =================================================================================
-    void cellListFluid() { buildCellList(fluid_cl, fluid.r("Position", 3).data(), fluid.n); }
+    // PeriodicBounding::checkLowerBound/checkUpperBound, axis by axis; ref: domain_bounding.h:98-108
+    void periodicBounding()
+    {
+        std::vector<R> &pos = fluid.r("Position", 3);
+        for (int a = 0; a < 3; ++a)
+        {
+            if (!(P.periodic_axes >> a & 1)) continue;
+            const R lo = R(P.periodic_lower[a]), up = R(P.periodic_upper[a]), L = up - lo;
+            for (u32 i = 0; i < fluid.n; ++i)
+            {
+                R &x = pos[3 * i + a];
+                if (x < lo) x += L;
+                else if (x > up) x -= L;
+            }
+        }
+    }
+    // UpdateCellLinkedList, then for periodic runs PeriodicCellLinkedList::exec of every periodic axis in turn:
+    // every list entry (ghost entries of the earlier axes included) with lower < x < lower + cutoff gets a ghost
+    // entry at x + L, every one with upper - cutoff < x < upper one at x - L; ref: domain_bounding.cpp:18-65
+    void cellListFluid()
+    {
+        const std::vector<R> &pos = fluid.r("Position", 3);
+        if (!P.periodic_axes)
+        {
+            fluid_cl.ext_index.clear(); fluid_cl.ext_pos.clear(); fluid_cl.ext_shift.clear();
+            buildCellList(fluid_cl, pos.data(), fluid.n);
+            return;
+        }
+        std::vector<u32> &ei = fluid_cl.ext_index;
+        std::vector<R> &ep = fluid_cl.ext_pos;
+        std::vector<unsigned char> &es = fluid_cl.ext_shift;
+        ei.resize(fluid.n); std::iota(ei.begin(), ei.end(), 0u);
+        ep.assign(pos.begin(), pos.begin() + size_t(3) * fluid.n);
+        es.assign(fluid.n, 13);
+        const int weight[3] = {1, 3, 9};
+        for (int a = 0; a < 3; ++a)
+        {
+            if (!(P.periodic_axes >> a & 1)) continue;
+            const R lo = R(P.periodic_lower[a]), up = R(P.periodic_upper[a]), L = up - lo, rc = R(P.periodic_cutoff);
+            const size_t m = ei.size();
+            for (size_t e = 0; e < m; ++e)
+            {
+                const R x = ep[3 * e + a];
+                for (int side = 0; side < 2; ++side)
+                {
+                    const bool near = side == 0 ? (x > lo && x < lo + rc) : (x < up && x > up - rc);
+                    if (!near) continue;
+                    ei.push_back(ei[e]);
+                    for (int d = 0; d < 3; ++d) ep.push_back(ep[3 * e + d]);
+                    ep[ep.size() - 3 + a] = side == 0 ? x + L : x - L;
+                    es.push_back((unsigned char)(es[e] + (side == 0 ? weight[a] : -weight[a])));
+                }
+            }
+        }
+        buildCellList(fluid_cl, ep.data(), (u32)ei.size());
+    }
+    // x_i - x_j of entry n of the inner relation; for a periodic image x_j is the TRANSLATED position, rounded as the
+    // reference's ghost list entry is (particle_position +/- periodic_translation_, domain_bounding.cpp:26,45)
+    inline V3<R> innerDisp(const std::vector<R> &pos, u32 i, u32 n) const
+    {
+        V3<R> xj = vec(pos, inner.index[n]);
+        if (!inner.shift.empty() && inner.shift[n] != 13)
+        {
+            int code = inner.shift[n];
+            const int s[3] = {code % 3 - 1, (code / 3) % 3 - 1, code / 9 - 1};
+            R *c[3] = {&xj.x, &xj.y, &xj.z};
+            for (int a = 0; a < 3; ++a)
+            {
+                const R L = R(P.periodic_upper[a]) - R(P.periodic_lower[a]);
+                if (s[a] > 0) *c[a] = *c[a] + L;
+                else if (s[a] < 0) *c[a] = *c[a] - L;
+            }
+        }
+        return vec(pos, i) - xj;
+    }
     void cellListWall() { buildCellList(wall_cl, wall.r("Position", 3).data(), wall.n); }
 
     void relationsCK()
@@ -611,7 +707,7 @@ template <class R> struct Sim
             for (u32 n = inner.offset[i]; n < inner.offset[i + 1]; ++n)
             {
                 u32 j = inner.index[n];
-                s += K.W(vec(pos, i) - vec(pos, j)) * Vref[j];
+                s += K.W(innerDisp(pos, i, n)) * Vref[j];
             }
             for (u32 n = contact.offset[i]; n < contact.offset[i + 1]; ++n)
             {
@@ -711,7 +807,7 @@ template <class R> struct Sim
             for (u32 n = inner.offset[i]; n < inner.offset[i + 1]; ++n)
             {
                 u32 j = inner.index[n];
-                V3<R> d = vec(pos, i) - vec(pos, j);
+                V3<R> d = innerDisp(pos, i, n);
                 R dWV = K.dW(d) * Vol[j];
                 V3<R> e = d.normalized();
                 if (corr)
@@ -789,7 +885,7 @@ template <class R> struct Sim
             for (u32 n = inner.offset[i]; n < inner.offset[i + 1]; ++n)
             {
                 u32 j = inner.index[n];
-                V3<R> d = vec(pos, i) - vec(pos, j);
+                V3<R> d = innerDisp(pos, i, n);
                 R dWV = K.dW(d) * Vol[j];
                 V3<R> e = d.normalized();
                 V3<R> vj = vec(vel, j);
@@ -871,7 +967,7 @@ template <class R> struct Sim
             for (u32 n = inner.offset[i]; n < inner.offset[i + 1]; ++n)
             {
                 u32 j = inner.index[n];
-                acc(vec(pos, i) - vec(pos, j), Vol[j]);
+                acc(innerDisp(pos, i, n), Vol[j]);
             }
             for (u32 n = contact.offset[i]; n < contact.offset[i + 1]; ++n)
             {
@@ -1086,6 +1182,7 @@ template <class R> struct Sim
                 updatePosition();
                 ++outer_steps; ++done;
                 if (sort_interval > 0 && outer_steps % sort_interval == 0 && outer_steps != 1) sortParticles(false);
+                if (P.periodic_axes) periodicBounding(); // taylor_green.cpp:186-191: bounding, cell list, images, configuration
                 cellListFluid();
                 relationsCK();
             }
@@ -1161,6 +1258,7 @@ double execOp(Sim<R> &s, const std::string &op, double a0, double a1, double a2,
     s.ensureFluidState();
     if (op == "gravity") s.gravityForce();
     else if (op == "cell_list_fluid") s.cellListFluid();
+    else if (op == "periodic_bounding") s.periodicBounding();
     else if (op == "cell_list_wall") s.cellListWall();
     else if (op == "relations") s.relationsCK();
     else if (op == "relations_legacy") s.relationsLegacy();
@@ -1262,6 +1360,7 @@ extern "C"
     else if (k == "wall_particle_index") v = &S->wall_cl.particle_index;                                             \
     else if (k == "inner_offset") v = &S->inner.offset;                                                              \
     else if (k == "inner_index") v = &S->inner.index;                                                                \
+    else if (k == "fluid_ext_index") v = &S->fluid_cl.ext_index;                                                     \
     else if (k == "contact_offset") v = &S->contact.offset;                                                          \
     else if (k == "contact_index") v = &S->contact.index;                                                            \
     else { S->ensureFluidState(); v = &S->fluid.uint[k]; }

@@ -61,7 +61,12 @@ class RelationT(C.Structure):
 class SearchT(C.Structure):
     _fields_ = [("tar_mesh", MeshT), ("kernel", KernelT), ("src_pos", _P), ("n_src", C.c_uint32), ("src_order", _P),
                 ("src_sorted_pos", _P), ("tar_pos", _P), ("tar_list", CellListT), ("is_inner", C.c_int32), ("legacy_criterion", C.c_int32),
-                ("search_depth", C.c_int32), ("src_begin", C.c_uint32), ("src_end", C.c_uint32), ("cell_ordered", C.c_int32)]
+                ("search_depth", C.c_int32), ("src_begin", C.c_uint32), ("src_end", C.c_uint32), ("cell_ordered", C.c_int32),
+                ("tar2_pos", _P), ("tar2_list", CellListT), ("tar2_index_base", C.c_uint32)]
+
+
+class PeriodicT(C.Structure):
+    _fields_ = [("lower", C.c_float * 3), ("upper", C.c_float * 3), ("axes", C.c_int32), ("cutoff", C.c_float)]
 
 
 class FluidArgs(C.Structure):
@@ -104,6 +109,9 @@ SYMBOLS = {
     "sphb200_relation_count": (_I, [_CTX, C.POINTER(SearchT), RelationT, C.POINTER(_U64), _P]),
     "sphb200_relation_fill": (_I, [_CTX, C.POINTER(SearchT), RelationT, _P]),
     "sphb200_relation_build_fixed": (_I, [_CTX, C.POINTER(SearchT), RelationT, _U32, C.POINTER(_U32), _P]),
+    "sphb200_periodic_bounding": (_I, [_CTX, C.POINTER(PeriodicT), _P, _U32, _P]),
+    "sphb200_periodic_images": (_I, [_CTX, C.POINTER(PeriodicT), _P, _U32, _P, _P, _U32, C.POINTER(_U32), _P]),
+    "sphb200_ghost_copy": (_I, [_CTX, _P, _U32, _U32, _U32, _P, _U32, _U32, _P]),
     "sphb200_relation_export_csr": (_I, [_CTX, RelationT, _U32, _P, _P, _P, _P, _U64, _P]),
     "sphb200_gravity_force": (_I, [_CTX, C.POINTER(FluidView), C.POINTER(_F * 3), _P, _P]),
     "sphb200_compression_summation": (_I, [_CTX, C.POINTER(FluidArgs), _I, _P]),

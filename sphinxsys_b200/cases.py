@@ -49,6 +49,13 @@ class DamBreakCase:
     mesh: hm.MeshSpec = None
     kernel: hm.KernelSpec = None
     sigma0: float = 0.0
+    # periodic box (Taylor-Green): bit d of periodic_axes = periodic along axis d; bounds already rounded to `dtype`
+    periodic_axes: int = 0
+    periodic_lower: tuple = (0.0, 0.0, 0.0)
+    periodic_upper: tuple = (0.0, 0.0, 0.0)
+    fluid_vel: np.ndarray = field(repr=False, default=None)
+    system_lower: tuple = None
+    system_upper: tuple = None
 
     @property
     def n_fluid(self):
@@ -206,4 +213,52 @@ def random_block(n, seed=1, dp=0.01, dtype=np.float32, particles_per_cell=17.6):
     case.kernel = kernel
     case.mesh = hm.make_mesh(np.zeros(3), np.full(3, edge), kernel.cutoff, 2, dtype=R)
     case.sigma0 = hm.lattice_number_density(kernel, dp)
+    return case
+
+
+def taylor_green(dim=3, n_side=32, jitter=0.05, seed=2024, dtype=np.float32, L=1.0, U=1.0) -> DamBreakCase:
+    """Periodic Taylor-Green vortex (BASELINE config 4): n_side^dim particles on the lattice of the periodic box
+    [0, L]^dim with a deterministic jitter of `jitter` dp, no walls, no gravity, c0 = 10 U.
+
+    Reference: tests/2d_examples/test_2d_taylor_green/taylor_green.cpp:14-57 (box, material, initial condition; the 3-D
+    velocity field is the usual extension v = U (sin 2pi x cos 2pi y cos 2pi z, -cos 2pi x sin 2pi y cos 2pi z, 0)).
+    Returned in the DamBreakCase shape (without wall particles) so the oracle and the host layer both consume it."""
+    R = dtype
+    dp = L / n_side
+    h = 1.3 * dp
+    case = DamBreakCase(dim, dp, R, L, L, L if dim == 3 else 0.0, L, L, L if dim == 3 else 0.0, 0.0, 1.0, 0.0, float(U), 10.0 * U, h)
+    sys_lo = np.array([0.0 - 4 * dp] * dim)
+    sys_up = np.array([L + 4 * dp] * dim)
+    axes = [_lattice_axis(sys_lo[d], sys_up[d], dp, R) for d in range(dim)]
+    sel = [a[(a >= 0.0) & (a <= L)] for a in axes]
+    grids = np.meshgrid(*sel, indexing="ij")
+    pos = np.stack([g_.reshape(-1) for g_ in grids], axis=1).astype(np.float64)
+    if jitter:
+        rng = np.random.default_rng(seed)
+        pos = pos + jitter * dp * rng.uniform(-1.0, 1.0, size=pos.shape)
+    if dim == 2:
+        pos = np.concatenate([pos, np.zeros((pos.shape[0], 1))], axis=1)
+    pos = np.ascontiguousarray(pos.astype(R))
+    x, y, z = (pos[:, k].astype(np.float64) for k in range(3))
+    tp = 2.0 * np.pi
+    vel = np.zeros_like(pos, dtype=np.float64)
+    if dim == 2:
+        vel[:, 0] = -U * np.cos(tp * x) * np.sin(tp * y)
+        vel[:, 1] = U * np.sin(tp * x) * np.cos(tp * y)
+    else:
+        vel[:, 0] = U * np.sin(tp * x) * np.cos(tp * y) * np.cos(tp * z)
+        vel[:, 1] = -U * np.cos(tp * x) * np.sin(tp * y) * np.cos(tp * z)
+    case.fluid_pos = pos
+    case.fluid_vel = np.ascontiguousarray(vel.astype(R))
+    case.wall_pos = np.zeros((0, 3), dtype=R)
+    case.wall_normal = np.zeros((0, 3), dtype=R)
+    case.vol = float(R(dp) ** dim)
+    case.kernel = hm.make_kernel(h, dim, hm.KERNEL_WENDLAND_C2, dtype=R)
+    case.mesh = hm.make_mesh(sys_lo, sys_up, case.kernel.cutoff, 2, dtype=R)
+    case.sigma0 = hm.lattice_number_density(case.kernel, dp)
+    case.periodic_axes = (1 << dim) - 1
+    case.periodic_lower = (0.0, 0.0, 0.0)
+    case.periodic_upper = tuple(float(R(L)) if d < dim else 0.0 for d in range(3))
+    case.system_lower = tuple(float(R(v)) for v in sys_lo) + ((0.0,) if dim == 2 else ())
+    case.system_upper = tuple(float(R(v)) for v in sys_up) + ((0.0,) if dim == 2 else ())
     return case

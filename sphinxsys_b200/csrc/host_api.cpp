@@ -6,6 +6,7 @@
 #include <string>
 
 #include "../../include/sphinxsys_ck/dambreak_case.h"
+#include "../../include/sphinxsys_ck/taylor_green_case.h"
 
 using namespace SPH;
 
@@ -15,7 +16,27 @@ thread_local std::string g_error;
 
 struct Handle
 {
-    std::unique_ptr<DamBreakCK> sim;
+    std::unique_ptr<DamBreakCK> sim;   // dam break (CK or legacy spelling) ...
+    std::unique_ptr<TaylorGreenCK> tg; // ... or the periodic Taylor-Green vortex
+    SPHBody &body(int which)
+    {
+        if (tg)
+        {
+            if (which) throw SphError("the Taylor-Green case has no wall body");
+            return tg->water_block;
+        }
+        return which ? (SPHBody &)sim->wall_boundary : (SPHBody &)sim->water_block;
+    }
+    RelationBase &relation(int which)
+    {
+        if (tg)
+        {
+            if (which) throw SphError("the Taylor-Green case has no contact relation");
+            return *tg->water_block_inner;
+        }
+        return which ? (RelationBase &)*sim->water_wall_contact : (RelationBase &)*sim->water_block_inner;
+    }
+    fluid_dynamics::AcousticTimeStepBase *acousticTimeStep() { return tg ? tg->fluid_acoustic_time_step.get() : sim->fluid_acoustic_time_step; }
 };
 
 template <class F> int guarded(F &&f)
@@ -39,7 +60,7 @@ std::vector<Vecd> toVecd(const float *xyz, uint64_t n)
     return v;
 }
 
-SPHBody &body(Handle *h, int which) { return which ? (SPHBody &)h->sim->wall_boundary : (SPHBody &)h->sim->water_block; }
+SPHBody &body(Handle *h, int which) { return h->body(which); }
 } // namespace
 
 extern "C"
@@ -63,7 +84,7 @@ extern "C"
     int sphck_own_range(void *hp, uint64_t *begin, uint64_t *count, uint64_t *stored)
     {
         return guarded([&] {
-            BaseParticles &p = ((Handle *)hp)->sim->water_block.getBaseParticles();
+            BaseParticles &p = ((Handle *)hp)->body(0).getBaseParticles();
             *begin = p.activeBegin();
             *count = p.activeEnd() - p.activeBegin();
             *stored = p.TotalRealParticles();
@@ -74,7 +95,7 @@ extern "C"
     {
         return guarded([&] {
             Handle *h = (Handle *)hp;
-            BaseParticles &p = (which ? (SPHBody &)h->sim->wall_boundary : (SPHBody &)h->sim->water_block).getBaseParticles();
+            BaseParticles &p = h->body(which).getBaseParticles();
             p.downloadRaw(p.findVariable(name), out, begin, count);
         });
     }
@@ -83,7 +104,7 @@ extern "C"
     {
         return guarded([&] {
             Handle *h = (Handle *)hp;
-            SPHBody &b = which ? (SPHBody &)h->sim->wall_boundary : (SPHBody &)h->sim->water_block;
+            SPHBody &b = h->body(which);
             BaseParticles &p = b.getBaseParticles();
             DiscreteVariableBase *v = p.findVariable(name);
             ExecutionInstance &ex = execution_instance();
@@ -91,12 +112,13 @@ extern "C"
             if (begin + count > p.ParticlesBound()) throw SphError("sphck_upload_raw: range outside the storage");
             if (count) ex.check(sphb200_copy_h2d((char *)v->deviceAddress() + begin * eb, in, count * eb, ex.stream()), "sphb200_copy_h2d");
             b.setPosVolDirty();
-            h->sim->fluid_acoustic_time_step->setPrimed(false);
+            h->acousticTimeStep()->setPrimed(false);
         });
     }
     int sphck_cuts(void *hp, int32_t *out, int capacity)
     {
         return guarded([&] {
+            if (!((Handle *)hp)->sim) throw SphError("not a decomposed run");
             DamBreakCK &s = *((Handle *)hp)->sim;
             if (!s.decomposition) throw SphError("not a decomposed run");
             const std::vector<int> &c = s.decomposition->cuts();
@@ -156,9 +178,50 @@ extern "C"
         }
         return h;
     }
+    struct sphck_taylor_green_options
+    {
+        int32_t dim;
+        double dp, L, U_f;
+        int32_t fused_time_step, fused_regularization, sort_interval, device, relation_stride;
+        double system_lower[3], system_upper[3];
+        int32_t use_system_bounds;
+    };
+    // xyz / vel_xyz may be NULL: lattice and analytic initial condition are generated by the C++ case then
+    void *sphck_taylor_green_create(const sphck_taylor_green_options *o, const float *xyz, const float *vel_xyz, uint64_t n)
+    {
+        Handle *h = new Handle();
+        int rc = guarded([&] {
+            execution_instance().setDevice(o->device);
+            TaylorGreenParameters q;
+            q.dim = o->dim; q.dp = o->dp; q.L = o->L; q.U_f = o->U_f;
+            q.fused_time_step = o->fused_time_step != 0;
+            q.fused_regularization = o->fused_regularization != 0;
+            q.sort_interval = o->sort_interval;
+            std::vector<Vecd> pos, vel;
+            if (xyz) pos = toVecd(xyz, n);
+            if (vel_xyz) vel = toVecd(vel_xyz, n);
+            BoundingBoxd sb;
+            if (o->use_system_bounds)
+                sb = BoundingBoxd(Vecd(Real(o->system_lower[0]), Real(o->system_lower[1]), Real(o->system_lower[2])),
+                                  Vecd(Real(o->system_upper[0]), Real(o->system_upper[1]), Real(o->system_upper[2])));
+            h->tg.reset(new TaylorGreenCK(q, xyz ? &pos : nullptr, vel_xyz ? &vel : nullptr, o->use_system_bounds ? &sb : nullptr));
+            if (o->relation_stride >= 0) h->tg->water_block_inner->fixed_stride_ = (uint32_t)o->relation_stride;
+        });
+        if (rc)
+        {
+            delete h;
+            return nullptr;
+        }
+        return h;
+    }
     void sphck_destroy(void *hp) { delete (Handle *)hp; }
 
-    uint64_t sphck_count(void *hp, int which) { return body((Handle *)hp, which).TotalRealParticles(); }
+    uint64_t sphck_count(void *hp, int which)
+    {
+        Handle *h = (Handle *)hp;
+        if (h->tg) return which ? 0 : h->tg->water_block.getBaseParticles().hostSyncCount();
+        return body(h, which).TotalRealParticles();
+    }
     uint64_t sphck_launches(void *) { return execution_instance().launches(); }
     int sphck_synchronize(void *) { return guarded([] { execution_instance().synchronize(); }); }
 
@@ -169,16 +232,61 @@ extern "C"
     }
     int sphck_kernel(void *hp, sphb200_kernel_t *out)
     {
-        return guarded([&] { *out = ((Handle *)hp)->sim->water_block_inner->kernel_; });
+        return guarded([&] { *out = ((Handle *)hp)->relation(0).kernel_; });
     }
 
     // one name per dynamics object of the case (tests drive them one by one)
     int sphck_exec(void *hp, const char *op_c, double a0, double *result)
     {
         Handle *h = (Handle *)hp;
-        DamBreakCK &s = *h->sim;
         std::string op(op_c);
         double r = 0;
+        if (h->tg)
+        {
+            TaylorGreenCK &s = *h->tg;
+            int rc = guarded([&] {
+                if (op == "initialize") s.initialize();
+                else if (op == "step_outer") r = s.stepOuter();
+                else if (op == "run_outer")
+                {
+                    long n = (long)a0, total = 0;
+                    for (long k = 0; k < n; ++k) total += s.stepOuter();
+                    r = (double)total;
+                }
+                else if (op == "cell_list_fluid") s.water_cell_linked_list->exec();
+                else if (op == "periodic_bounding") { for (auto &pc : s.periodic_condition) pc->bounding_.exec(); }
+                else if (op == "ghost_creation") { for (auto &pc : s.periodic_condition) pc->ghost_creation_.exec(); }
+                else if (op == "ghost_update") s.periodic_condition[0]->ghost_update_.exec();
+                else if (op == "ghost_particles") { s.periodic_condition[0]->images().ensure(); r = (double)s.periodic_condition[0]->images().ghostParticles(); }
+                else if (op == "relations") s.water_block_update_inner_relation->exec();
+                else if (op == "update_configuration") s.updateConfiguration(a0 != 0.0);
+                else if (op == "sort") { s.particle_sort->exec(); s.fluid_acoustic_time_step->setPrimed(false); }
+                else if (op == "density_summation") s.fluid_density_summation->exec();
+                else if (op == "density_regularization") s.fluid_density_regularization->exec();
+                else if (op == "advection_setup") { s.water_advection_step_setup->exec(); s.volume_ghost_update->exec(); }
+                else if (op == "update_position") s.water_update_particle_position->exec();
+                else if (op == "advection_dt") r = s.fluid_advection_time_step->exec();
+                else if (op == "advection_dt_reduced") r = s.fluid_advection_time_step->ReducedValue();
+                else if (op == "acoustic_dt") r = s.fluid_acoustic_time_step->exec();
+                else if (op == "acoustic_dt_reduced") r = s.fluid_acoustic_time_step->ReducedValue();
+                else if (op == "acoustic_dt_unprime") s.fluid_acoustic_time_step->setPrimed(false);
+                else if (op == "acoustic1") s.fluid_acoustic_step_1st_half->exec(Real(a0));
+                else if (op == "acoustic2") s.fluid_acoustic_step_2nd_half->exec(Real(a0));
+                else if (op == "energy") r = s.record_total_kinetic_energy->exec();
+                else if (op == "physical_time") r = s.physical_time;
+                else if (op == "acoustic_steps") r = (double)s.acoustic_steps;
+                else if (op == "outer_steps") r = (double)s.number_of_iterations;
+                else if (op == "last_acoustic_dt") r = s.last_acoustic_dt;
+                else if (op == "inner_total") r = (double)s.water_block_inner->total_;
+                else if (op == "inner_stride") r = (double)s.water_block_inner->fixed_stride_;
+                else if (op == "inner_max_count") r = (double)s.water_block_inner->max_count_;
+                else if (op == "set_relation_stride") s.water_block_inner->fixed_stride_ = (uint32_t)a0;
+                else throw SphError("unknown op '" + op + "'");
+            });
+            if (result) *result = r;
+            return rc;
+        }
+        DamBreakCK &s = *h->sim;
         int rc = guarded([&] {
             if (op == "initialize") s.initialize();
             else if (op == "step_outer") r = s.stepOuter();
@@ -234,7 +342,9 @@ extern "C"
     int sphck_acoustic1_phase(void *hp, int phase /*0 initialize, 1 interact+update*/, double dt)
     {
         return guarded([&] {
-            auto *ph = dynamic_cast<fluid_dynamics::AcousticStep1stHalfPhases *>(((Handle *)hp)->sim->fluid_acoustic_step_1st_half.get());
+            Handle *h = (Handle *)hp;
+            auto *ph = h->tg ? static_cast<fluid_dynamics::AcousticStep1stHalfPhases *>(h->tg->fluid_acoustic_step_1st_half.get())
+                             : dynamic_cast<fluid_dynamics::AcousticStep1stHalfPhases *>(h->sim->fluid_acoustic_step_1st_half.get());
             if (!ph) throw SphError("1st half does not expose phases");
             if (phase == 0) ph->deviceInitialize(Real(dt));
             else ph->deviceInteractAndUpdate(Real(dt));
@@ -262,7 +372,7 @@ extern "C"
             else if (kind == 2) p.upload(p.getVariableByName<UnsignedInt>(name), (const UnsignedInt *)in);
             else p.upload(p.getVariableByName<Matd>(name), (const Matd *)in);
             b.setPosVolDirty();
-            ((Handle *)hp)->sim->fluid_acoustic_time_step->setPrimed(false);
+            ((Handle *)hp)->acousticTimeStep()->setPrimed(false);
         });
     }
     int sphck_has_variable(void *hp, int which, const char *name) { return body((Handle *)hp, which).getBaseParticles().hasVariable(name) ? 1 : 0; }
@@ -295,8 +405,7 @@ extern "C"
     int sphck_export_csr(void *hp, int relation, uint32_t *offset, uint32_t *index, uint64_t index_capacity, uint64_t *total)
     {
         return guarded([&] {
-            DamBreakCK &s = *((Handle *)hp)->sim;
-            RelationBase &r = relation ? (RelationBase &)*s.water_wall_contact : (RelationBase &)*s.water_block_inner;
+            RelationBase &r = ((Handle *)hp)->relation(relation);
             std::vector<uint32_t> off, idx;
             r.exportCSR(off, idx);
             if (total) *total = idx.size();

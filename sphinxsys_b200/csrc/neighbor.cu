@@ -164,6 +164,10 @@ struct SearchArgs
     int legacy_criterion;
     int depth;
     int cell_ordered;
+    // optional second candidate set on the same mesh (periodic images stored behind the real particles)
+    const float4 *tar2_pos;
+    const u32 *cell_offset2;
+    u32 index_base2;
 };
 // launches start at the 32-aligned slot below src_begin so that lane == slot % 32 (SELL-32 layout)
 __device__ __forceinline__ u32 search_slot(const SearchArgs &a) { return (a.src_begin & ~31u) + blockIdx.x * blockDim.x + threadIdx.x; }
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(128)
 // The criterion is decided by a fused-arithmetic estimate when it is more than 1e-4 away from the threshold and
 // by the separately rounded reference expression (within()) otherwise, so set membership stays bit-identical.
 // -----------------------------------------------------------------------------------------------------
-template <bool INNER, int MODE>
+template <bool INNER, int MODE, bool TWO>
 __global__ void __launch_bounds__(128)
     k_relation_ordered(SearchArgs a, u32 *__restrict__ count, u32 *__restrict__ slice, u32 *__restrict__ index, u64 capacity,
                        u32 stride, u32 *__restrict__ max_count)
@@ -327,6 +331,13 @@ __global__ void __launch_bounds__(128)
     u32 *const out = index + base64;
     const u32 row_limit = (u32)(room > 0xffffffffull ? 0xffffffffull : room);
     u32 c = 0;
+    for (int pass = 0; pass < (TWO ? 2 : 1); ++pass)
+    {
+    // pass 1 walks the second candidate set (periodic images): same mesh, its own cell list, no self exclusion
+    const float4 *__restrict__ tpos = TWO && pass ? a.tar2_pos : a.tar_pos;
+    const u32 *__restrict__ coff = TWO && pass ? a.cell_offset2 : a.cell_offset;
+    const u32 ibase = TWO && pass ? a.index_base2 : 0u;
+    const bool self_excl = INNER && !(TWO && pass);
     u32 todo = __ballot_sync(0xffffffffu, active);
     while (todo)
     {
@@ -346,12 +357,12 @@ __global__ void __launch_bounds__(128)
                 for (int y = y0; y < y1; ++y)
                 {
                     const u32 col = cell_linear(m, x, y, 0);
-                    const u32 rb = a.cell_offset[col + z0], re = a.cell_offset[col + z1];
-                    const u32 lo = a.cell_offset[col + wz0], hi = a.cell_offset[col + wz1];
+                    const u32 rb = coff[col + z0], re = coff[col + z1];
+                    const u32 lo = coff[col + wz0], hi = coff[col + wz1];
                     for (u32 kb = rb; kb < re; kb += CH)
                     {
                         u32 sure = 0, maybe = 0;
-                        const float4 *__restrict__ pk = a.tar_pos + kb;
+                        const float4 *__restrict__ pk = tpos + kb;
                         auto test = [&](int b, u32 bit) {
                             const float4 xj = pk[b];
                             const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
@@ -369,14 +380,14 @@ __global__ void __launch_bounds__(128)
                         // the lane's own cell window [lo, hi) as a bit range of this chunk; INNER: not itself
                         const u32 blo = lo > kb ? min(lo - kb, 32u) : 0u, bhi = hi > kb ? min(hi - kb, 32u) : 0u;
                         u32 wmask = (bhi >= 32u ? 0xffffffffu : (1u << bhi) - 1u) & ~(blo >= 32u ? 0xffffffffu : (1u << blo) - 1u);
-                        if (INNER && t - kb < (u32)CH) wmask &= ~(1u << (t - kb));
+                        if (self_excl && t - kb < (u32)CH) wmask &= ~(1u << (t - kb));
                         maybe &= wmask & ~sure;
                         sure &= wmask;
                         while (maybe) // rare: within 1e-4 of the threshold
                         {
                             const u32 b = __ffs(maybe) - 1;
                             maybe &= maybe - 1;
-                            if (criterion(xi, a.tar_pos[kb + b], a.inv_h, a.ks2, a.rc2, a.legacy_criterion)) sure |= 1u << b;
+                            if (criterion(xi, tpos[kb + b], a.inv_h, a.ks2, a.rc2, a.legacy_criterion)) sure |= 1u << b;
                         }
                         if (MODE == 0)
                             c += __popc(sure);
@@ -385,12 +396,13 @@ __global__ void __launch_bounds__(128)
                             {
                                 const u32 b = __ffs(sure) - 1;
                                 sure &= sure - 1;
-                                if (c < row_limit) out[32ull * c] = kb + b;
+                                if (c < row_limit) out[32ull * c] = ibase + kb + b;
                                 ++c;
                             }
                     }
                 }
         }
+    }
     }
     if (MODE != 1 && active) count[t] = c;
     if (MODE == 0)
@@ -433,6 +445,10 @@ static int make_search(sphb200_context *ctx, const sphb200_search_t *s, SearchAr
     a->legacy_criterion = s->legacy_criterion;
     a->depth = s->search_depth;
     a->cell_ordered = s->cell_ordered;
+    a->tar2_pos = (const float4 *)s->tar2_pos;
+    a->cell_offset2 = s->tar2_list.cell_offset;
+    a->index_base2 = s->tar2_index_base;
+    SPH_CHECK_ARG(ctx, !s->tar2_pos || (s->cell_ordered && s->tar2_list.cell_offset), "a second candidate set needs a cell_ordered search and its cell list");
     if (s->cell_ordered && s->n_src)
     {
         SPH_CHECK_ARG(ctx, a->src_pos && a->tar_pos && a->cell_offset && !a->src_order, "cell_ordered search needs src_pos, tar_pos, cell_offset and no src_order");
@@ -456,8 +472,13 @@ static int launch_relation(sphb200_context *ctx, const SearchArgs &a, bool inner
     bool sorted = a.tar_sorted_pos != nullptr;
     if (a.cell_ordered)
     {
-        if (inner) SPH_LAUNCH(ctx, (k_relation_ordered<true, MODE>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
-        else SPH_LAUNCH(ctx, (k_relation_ordered<false, MODE>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
+        if (a.tar2_pos)
+        {
+            if (inner) SPH_LAUNCH(ctx, (k_relation_ordered<true, MODE, true>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
+            else SPH_LAUNCH(ctx, (k_relation_ordered<false, MODE, true>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
+        }
+        else if (inner) SPH_LAUNCH(ctx, (k_relation_ordered<true, MODE, false>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
+        else SPH_LAUNCH(ctx, (k_relation_ordered<false, MODE, false>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
         return 0;
     }
     if (inner && sorted) SPH_LAUNCH(ctx, (k_relation<true, true, MODE>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
@@ -598,5 +619,175 @@ extern "C" int sphb200_relation_export_csr(sphb200_context_t *ctx, sphb200_relat
     }
     SPH_LAUNCH(ctx, k_export_csr, sph_blocks(n, 128), 128, 0, st, rel.count, rel.slice_offset, rel.index, order, tar_ids, n,
                particle_offset, neighbor_index);
+    return 0;
+}
+
+// =====================================================================================================
+// periodic boundary: bounding (wrap) and image particles
+// ref: particle_dynamics/general_dynamics/domian_bouding/domain_bounding.h:48-175, domain_bounding.cpp:18-65.
+// The reference inserts, axis by axis, ghost ENTRIES (source index, translated position) into the cell-linked list;
+// here the images become ghost PARTICLES stored cell ordered behind the real ones (the storage convention of the
+// slab-decomposed runs), so every kernel reads them like any other neighbour.
+// =====================================================================================================
+struct DPeriodic
+{
+    float lower[3], upper[3], shift[3], cutoff;
+    int axes;
+};
+static inline DPeriodic make_dperiodic(const sphb200_periodic_t *b)
+{
+    DPeriodic d;
+    for (int k = 0; k < 3; ++k)
+    {
+        d.lower[k] = b->lower[k];
+        d.upper[k] = b->upper[k];
+        d.shift[k] = b->upper[k] - b->lower[k]; // periodic_translation_, in Real (domain_bounding.h:56-57)
+    }
+    d.cutoff = b->cutoff;
+    d.axes = b->axes;
+    return d;
+}
+__device__ __forceinline__ float &comp(float4 &v, int k) { return k == 0 ? v.x : (k == 1 ? v.y : v.z); }
+
+__global__ void __launch_bounds__(256) k_periodic_bounding(DPeriodic b, float4 *__restrict__ pos, u32 n)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 x = pos[i];
+    bool changed = false;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+        if (b.axes >> k & 1)
+        {
+            float &c = comp(x, k);
+            if (c < b.lower[k]) { c = __fadd_rn(c, b.shift[k]); changed = true; }      // checkLowerBound
+            else if (c > b.upper[k]) { c = __fsub_rn(c, b.shift[k]); changed = true; } // checkUpperBound
+        }
+    if (changed) pos[i] = x;
+}
+extern "C" int sphb200_periodic_bounding(sphb200_context_t *ctx, const sphb200_periodic_t *box, sphb200_vec4_t *pos, uint32_t n,
+                                         void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && box && (pos || n == 0), "null pointer");
+    if (n) SPH_LAUNCH(ctx, k_periodic_bounding, sph_blocks(n, 256), 256, 0, stream, make_dperiodic(box), (float4 *)pos, n);
+    return 0;
+}
+
+// per axis: bit 0 = image at +L (particle near the lower face), bit 1 = image at -L (near the upper face)
+__device__ __forceinline__ int image_options(const DPeriodic &b, float c, int k)
+{
+    if (!(b.axes >> k & 1)) return 0;
+    int o = 0;
+    if (c > b.lower[k] && c < __fadd_rn(b.lower[k], b.cutoff)) o |= 1; // InsertListDataNearLowerBound
+    if (c < b.upper[k] && c > __fsub_rn(b.upper[k], b.cutoff)) o |= 2; // InsertListDataNearUpperBound
+    return o;
+}
+__device__ __forceinline__ int option_count(int o) { return 1 + (o & 1) + (o >> 1 & 1); }
+// MODE 0: number of images per particle; MODE 1: write them at offset[i]
+template <int MODE>
+__global__ void __launch_bounds__(256)
+    k_periodic_images(DPeriodic b, const float4 *__restrict__ pos, u32 n, u32 *__restrict__ count, const u32 *__restrict__ offset,
+                      float4 *__restrict__ image_pos, u32 *__restrict__ image_src)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 x = pos[i];
+    const int ox = image_options(b, x.x, 0), oy = image_options(b, x.y, 1), oz = image_options(b, x.z, 2);
+    if (MODE == 0)
+    {
+        count[i] = (u32)(option_count(ox) * option_count(oy) * option_count(oz) - 1);
+        return;
+    }
+    if ((ox | oy | oz) == 0) return;
+    u32 k = offset[i];
+    // choice 0: stay, 1: +L, 2: -L ; the all-stay combination is the particle itself
+    for (int cx = 0; cx < 3; ++cx)
+    {
+        if (cx && !(ox >> (cx - 1) & 1)) continue;
+        for (int cy = 0; cy < 3; ++cy)
+        {
+            if (cy && !(oy >> (cy - 1) & 1)) continue;
+            for (int cz = 0; cz < 3; ++cz)
+            {
+                if (cz && !(oz >> (cz - 1) & 1)) continue;
+                if ((cx | cy | cz) == 0) continue;
+                float4 y = x;
+                if (cx) y.x = cx == 1 ? __fadd_rn(x.x, b.shift[0]) : __fsub_rn(x.x, b.shift[0]);
+                if (cy) y.y = cy == 1 ? __fadd_rn(x.y, b.shift[1]) : __fsub_rn(x.y, b.shift[1]);
+                if (cz) y.z = cz == 1 ? __fadd_rn(x.z, b.shift[2]) : __fsub_rn(x.z, b.shift[2]);
+                image_pos[k] = y;
+                image_src[k] = i;
+                ++k;
+            }
+        }
+    }
+}
+extern "C" int sphb200_periodic_images(sphb200_context_t *ctx, const sphb200_periodic_t *box, const sphb200_vec4_t *pos, uint32_t n,
+                                       sphb200_vec4_t *image_pos, uint32_t *image_src, uint32_t capacity, uint32_t *count_host,
+                                       void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && box && count_host && (pos || n == 0), "null pointer");
+    *count_host = 0;
+    if (n == 0 || box->axes == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    void *p;
+    int rc = sph_scratch(ctx, 2, 2 * ((size_t)n + 1) * sizeof(u32) + 64, &p);
+    if (rc) return rc;
+    u32 *cnt = (u32 *)p, *off = cnt + n + 1;
+    DPeriodic b = make_dperiodic(box);
+    SPH_CUDA(ctx, cudaMemsetAsync(cnt + n, 0, sizeof(u32), st));
+    SPH_LAUNCH(ctx, k_periodic_images<0>, sph_blocks(n, 256), 256, 0, st, b, (const float4 *)pos, n, cnt, nullptr, nullptr, nullptr);
+    rc = sph_scan_u32(ctx, cnt, off, (u64)n + 1, 0, st);
+    if (rc) return rc;
+    SPH_CUDA(ctx, cudaMemcpyAsync(ctx->host_pinned, off + n, sizeof(u32), cudaMemcpyDeviceToHost, st));
+    SPH_CUDA(ctx, cudaStreamSynchronize(st));
+    const u32 total = *(u32 *)ctx->host_pinned;
+    *count_host = total;
+    if (total > capacity)
+    {
+        snprintf(ctx->err, sizeof(ctx->err), "periodic_images: %u images, capacity %u", total, capacity);
+        return SPHB200_E_CAPACITY;
+    }
+    if (total == 0) return 0;
+    SPH_CHECK_ARG(ctx, image_pos && image_src, "null output");
+    SPH_LAUNCH(ctx, k_periodic_images<1>, sph_blocks(n, 256), 256, 0, st, b, (const float4 *)pos, n, nullptr, off, (float4 *)image_pos,
+               image_src);
+    return 0;
+}
+
+// word-granular copy of a slice of every ghost element from its source element
+__global__ void __launch_bounds__(256)
+    k_ghost_copy(u32 *__restrict__ array, u32 elem_words, u32 offset_words, u32 copy_words, const u32 *__restrict__ ghost_src,
+                 u32 n_real, u64 total_words)
+{
+    u64 w = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= total_words) return;
+    u32 g = (u32)(w / copy_words), k = (u32)(w % copy_words);
+    array[((u64)n_real + g) * elem_words + offset_words + k] = array[(u64)ghost_src[g] * elem_words + offset_words + k];
+}
+__global__ void __launch_bounds__(256)
+    k_ghost_copy16(uint4 *__restrict__ array, u32 elem_q, u32 offset_q, const u32 *__restrict__ ghost_src, u32 n_real, u32 n_ghost)
+{
+    u32 g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_ghost) return;
+    array[((u64)n_real + g) * elem_q + offset_q] = array[(u64)ghost_src[g] * elem_q + offset_q];
+}
+extern "C" int sphb200_ghost_copy(sphb200_context_t *ctx, void *array, uint32_t elem_bytes, uint32_t offset_bytes, uint32_t copy_bytes,
+                                  const uint32_t *ghost_src, uint32_t n_real, uint32_t n_ghost, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && ((array && ghost_src) || n_ghost == 0), "null pointer");
+    SPH_CHECK_ARG(ctx, elem_bytes % 4 == 0 && offset_bytes % 4 == 0 && copy_bytes % 4 == 0 && copy_bytes > 0 &&
+                           offset_bytes + copy_bytes <= elem_bytes,
+                  "sizes must be multiples of 4 with offset + copy <= element");
+    if (n_ghost == 0) return 0;
+    if (copy_bytes == 16 && elem_bytes % 16 == 0 && offset_bytes % 16 == 0)
+        SPH_LAUNCH(ctx, k_ghost_copy16, sph_blocks(n_ghost, 256), 256, 0, stream, (uint4 *)array, elem_bytes / 16, offset_bytes / 16,
+                   ghost_src, n_real, n_ghost);
+    else
+    {
+        u64 total = (u64)n_ghost * (copy_bytes / 4);
+        SPH_LAUNCH(ctx, k_ghost_copy, sph_blocks(total, 256), 256, 0, stream, (u32 *)array, elem_bytes / 4, offset_bytes / 4,
+                   copy_bytes / 4, ghost_src, n_real, total);
+    }
     return 0;
 }

@@ -32,6 +32,13 @@ class Options(C.Structure):
                 ("nranks", C.c_int32), ("unique_id", C.c_uint8 * 128)]
 
 
+class TaylorGreenOptions(C.Structure):
+    _fields_ = [("dim", C.c_int32), ("dp", C.c_double), ("L", C.c_double), ("U_f", C.c_double), ("fused_time_step", C.c_int32),
+                ("fused_regularization", C.c_int32), ("sort_interval", C.c_int32), ("device", C.c_int32),
+                ("relation_stride", C.c_int32), ("system_lower", C.c_double * 3), ("system_upper", C.c_double * 3),
+                ("use_system_bounds", C.c_int32)]
+
+
 _lib = None
 
 
@@ -45,6 +52,8 @@ def load():
         L.sphck_last_error.restype = C.c_char_p
         L.sphck_dambreak_create.restype = C.c_void_p
         L.sphck_dambreak_create.argtypes = [C.POINTER(Options), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.sphck_taylor_green_create.restype = C.c_void_p
+        L.sphck_taylor_green_create.argtypes = [C.POINTER(TaylorGreenOptions), C.c_void_p, C.c_void_p, C.c_uint64]
         L.sphck_destroy.argtypes = [C.c_void_p]
         L.sphck_count.restype = C.c_uint64
         L.sphck_count.argtypes = [C.c_void_p, C.c_int]
@@ -261,3 +270,41 @@ class DamBreakCK:
         idx = np.empty(max(int(total.value), 1), dtype=np.uint32)
         self._check(self.lib.sphck_export_csr(self._h, int(contact), off.ctypes.data, idx.ctypes.data, idx.size, C.byref(total)), "export_csr")
         return off, idx[: int(total.value)]
+
+
+class TaylorGreenCK(DamBreakCK):
+    """Handle of a C++ `SPH::TaylorGreenCK` (include/sphinxsys_ck/taylor_green_case.h): periodic box, no wall body.
+    Shares the driving interface of DamBreakCK (exec by name, upload/download in the reference particle order)."""
+
+    def __init__(self, case=None, device_index=0, fused_time_step=True, sort_interval=100, relation_stride=None,
+                 fused_regularization=True, dim=3, n_side=32, generate=False):
+        self.lib = load()
+        o = TaylorGreenOptions()
+        if case is not None:
+            o.dim, o.dp, o.L, o.U_f = case.dim, case.dp, case.DL, case.U_ref
+        else:
+            o.dim, o.dp, o.L, o.U_f = dim, 1.0 / n_side, 1.0, 1.0
+        o.fused_time_step, o.fused_regularization = int(fused_time_step), int(fused_regularization)
+        o.sort_interval, o.device = int(sort_interval), int(device_index)
+        o.relation_stride = -1 if relation_stride is None else int(relation_stride)
+        o.use_system_bounds = 0
+        self.rank, self.nranks, self.case = 0, 1, case
+        if case is not None and not generate:
+            if case.system_lower is not None:
+                o.use_system_bounds = 1
+                for d in range(3):
+                    o.system_lower[d] = case.system_lower[d]
+                    o.system_upper[d] = case.system_upper[d]
+            fp = np.ascontiguousarray(case.fluid_pos, dtype=np.float32)
+            fv = np.ascontiguousarray(case.fluid_vel, dtype=np.float32)
+            self._h = self.lib.sphck_taylor_green_create(C.byref(o), fp.ctypes.data, fv.ctypes.data, fp.shape[0])
+        else:
+            self._h = self.lib.sphck_taylor_green_create(C.byref(o), None, None, 0)
+        if not self._h:
+            raise capi.SphB200Error("sphck_taylor_green_create failed: " + self.lib.sphck_last_error().decode())
+        self.n_fluid = int(self.lib.sphck_count(self._h, 0))
+        self.n_wall = 0
+
+    @property
+    def ghost_particles(self) -> int:
+        return int(self.exec("ghost_particles"))
