@@ -36,6 +36,19 @@ class WallBoundary : public ComplexShape
     }
 };
 
+// observation points (dambreak.cpp:54-65)
+static StdVec<Vecd> createObservationPoints()
+{
+    StdVec<Vecd> observation_points;
+    observation_points.push_back(Vecd(DL, 0.01, 0.5 * DW));
+    observation_points.push_back(Vecd(DL, 0.1, 0.5 * DW));
+    observation_points.push_back(Vecd(DL, 0.2, 0.5 * DW));
+    observation_points.push_back(Vecd(DL, 0.24, 0.5 * DW));
+    observation_points.push_back(Vecd(DL, 0.252, 0.5 * DW));
+    observation_points.push_back(Vecd(DL, 0.266, 0.5 * DW));
+    return observation_points;
+}
+
 int main(int ac, char *av[])
 {
     if (ac > 1) global_resolution = Real(std::atof(av[1]));
@@ -54,13 +67,18 @@ int main(int ac, char *av[])
     SolidBody wall_boundary(sph_system, makeShared<WallBoundary>("WallBoundary"));
     wall_boundary.defineMatterMaterial<Solid>();
     wall_boundary.generateParticles<BaseParticles, Lattice>();
+
+    ObserverBody fluid_observer(sph_system, "FluidObserver");
+    fluid_observer.generateParticles<ObserverParticles>(createObservationPoints());
     //	Define body relation map.
     Inner<> water_block_inner(water_block);
     Contact<> water_wall_contact(water_block, {&wall_boundary});
+    Contact<> fluid_observer_contact(fluid_observer, {&water_block});
     //	Define the numerical methods used in the simulation.
     UpdateCellLinkedList<MainExecutionPolicy, RealBody> water_cell_linked_list(water_block);
     UpdateCellLinkedList<MainExecutionPolicy, RealBody> wall_cell_linked_list(wall_boundary);
     UpdateRelation<MainExecutionPolicy, Inner<>, Contact<>> water_block_update_complex_relation(water_block_inner, water_wall_contact);
+    UpdateRelation<MainExecutionPolicy, Contact<>> fluid_observer_contact_relation(fluid_observer_contact);
     ParticleSortCK<MainExecutionPolicy> particle_sort(water_block);
 
     Gravity gravity(Vec3d(0.0, -gravity_g, 0.0));
@@ -68,17 +86,22 @@ int main(int ac, char *av[])
     StateDynamics<MainExecutionPolicy, fluid_dynamics::AdvectionStepSetup> water_advection_step_setup(water_block);
     StateDynamics<MainExecutionPolicy, fluid_dynamics::UpdateParticlePosition> water_update_particle_position(water_block);
 
-    InteractionDynamicsCK<MainExecutionPolicy, fluid_dynamics::AcousticStep1stHalfWithWallRiemannCK>
+    InteractionDynamicsCK<MainExecutionPolicy, LinearCorrectionMatrixComplex>
+        fluid_linear_correction_matrix(DynamicsArgs(water_block_inner, 0.5), water_wall_contact);
+    InteractionDynamicsCK<MainExecutionPolicy, fluid_dynamics::AcousticStep1stHalfWithWallRiemannCorrectionCK>
         fluid_acoustic_step_1st_half(water_block_inner, water_wall_contact);
-    InteractionDynamicsCK<MainExecutionPolicy, fluid_dynamics::AcousticStep2ndHalfWithWallRiemannCK>
+    InteractionDynamicsCK<MainExecutionPolicy, fluid_dynamics::AcousticStep2ndHalfWithWallRiemannCorrectionCK>
         fluid_acoustic_step_2nd_half(water_block_inner, water_wall_contact);
     InteractionDynamicsCK<MainExecutionPolicy, fluid_dynamics::CompressionSummation<Inner<>, Contact<>>>
         fluid_density_summation(water_block_inner, water_wall_contact);
     StateDynamics<MainExecutionPolicy, fluid_dynamics::DensityRegularization<SPHBody, WeaklyCompressibleFluid, FreeSurface>>
         fluid_density_regularization(water_block);
+    InteractionDynamicsCK<MainExecutionPolicy, fluid_dynamics::FreeSurfaceIndicationComplexSpatialTemporalCK>
+        fluid_boundary_indicator(water_block_inner, water_wall_contact);
     ReduceDynamicsCK<MainExecutionPolicy, fluid_dynamics::AdvectionTimeStepCK> fluid_advection_time_step(water_block, U_f);
     ReduceDynamicsCK<MainExecutionPolicy, fluid_dynamics::AcousticTimeStepCK<WeaklyCompressibleFluid>> fluid_acoustic_time_step(water_block);
     ReduceDynamicsCK<MainExecutionPolicy, TotalMechanicalEnergyCK> record_water_mechanical_energy(water_block, gravity);
+    ObservedQuantityRecording<MainExecutionPolicy, Real> fluid_observer_pressure(fluid_observer_contact, "Pressure");
     //	Prepare the simulation with cell linked list, configuration and case specified initial condition.
     SingleVariable<Real> *sv_physical_time = sph_system.getSystemVariableByName<Real>("PhysicalTime");
     wall_boundary.computeNormalFromBodyShape(); // NormalFromBodyShapeCK, a host dynamics in the reference too
@@ -87,6 +110,7 @@ int main(int ac, char *av[])
     water_cell_linked_list.exec();
     wall_cell_linked_list.exec();
     water_block_update_complex_relation.exec();
+    fluid_observer_contact_relation.exec();
     //	Setup for time-stepping control
     size_t number_of_iterations = 0, acoustic_steps = 0;
     int screen_output_interval = 100;
@@ -94,6 +118,7 @@ int main(int ac, char *av[])
     auto t1 = std::chrono::steady_clock::now();
     std::cout << "N_fluid = " << water_block.TotalRealParticles() << "  N_wall = " << wall_boundary.TotalRealParticles()
               << "  E0 = " << std::setprecision(9) << record_water_mechanical_energy.exec() << "\n";
+    fluid_observer_pressure.writeToFile(number_of_iterations);
     //	Main loop starts here.
     while (sv_physical_time->getValue() < end_time)
     {
@@ -104,6 +129,8 @@ int main(int ac, char *av[])
             fluid_density_regularization.exec();
             water_advection_step_setup.exec();
             Real advection_dt = fluid_advection_time_step.exec();
+            fluid_boundary_indicator.exec();
+            fluid_linear_correction_matrix.exec();
 
             Real relaxation_time = 0.0;
             Real acoustic_dt = 0.0;
@@ -133,11 +160,19 @@ int main(int ac, char *av[])
             }
             water_cell_linked_list.exec();
             water_block_update_complex_relation.exec();
+            fluid_observer_contact_relation.exec();
+            fluid_observer_pressure.writeToFile(number_of_iterations);
         }
         std::cout << "t = " << sv_physical_time->getValue() << "  TotalMechanicalEnergy = " << record_water_mechanical_energy.exec() << "\n";
     }
     execution_instance().synchronize();
     double seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t1).count();
+    {
+        const auto &last = fluid_observer_pressure.records().back();
+        std::cout << "probe pressures at t = " << sv_physical_time->getValue() << ":";
+        for (Real p : last) std::cout << " " << p;
+        std::cout << "  (" << fluid_observer_pressure.records().size() << " records)\n";
+    }
     std::cout << "Total wall time for computation: " << seconds << " seconds; "
               << double(water_block.TotalRealParticles()) * double(acoustic_steps) / seconds << " particle-steps/s\n";
     return 0;

@@ -348,6 +348,21 @@ int sphb200_acoustic_1st_half_interact(sphb200_context_t *ctx, const sphb200_flu
                                        void *stream);
 /* LinearCorrectionMatrix<Inner<WithUpdate>,Contact<>>; ref: general_dynamics/kernel_correction_ck.hpp:40-95 */
 int sphb200_linear_correction_matrix(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, float alpha, void *stream);
+/* InteractionDynamicsCK<FreeSurfaceIndicationCK<Inner<WithUpdate>, Contact<>>>::exec: inner interact (position
+ * divergence, spatial-temporal override next to the previous surface) -> contact interact -> update (Indicator,
+ * PreviousSurfaceIndicator). threshold = 0.75 * Dimensions, smoothing_length = ReferenceSmoothingLength().
+ * Two launches (update reads the neighbours' PositionDivergence).
+ * ref: general_dynamics/surface_indication/surface_indication_ck.hpp:12-160 */
+int sphb200_free_surface_indication(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, int32_t *indicator,
+                                    float *position_divergence, int32_t *previous_indicator, float threshold,
+                                    float smoothing_length, void *stream);
+/* Interpolation<Contact<DataType>>::InteractKernel::interact for an observer body:
+ * out[i] = sum_j W_ij V_j data[j] / (sum_j W_ij V_j + TinyReal) over the rows of `rel` (observer -> observed body).
+ * width 1: Real data; width 4: Vecd data as stored on the device (float4, all four lanes are interpolated).
+ * ref: general_dynamics/interpolation_dynamics.hpp:44-60 */
+int sphb200_interpolate(sphb200_context_t *ctx, const sphb200_kernel_t *kernel, const sphb200_vec4_t *src_pos, uint32_t n_src,
+                        sphb200_relation_t rel, const sphb200_vec4_t *tar_posvol, const float *tar_data, int width, float *out,
+                        void *stream);
 /* ReduceDynamicsCK<TotalMechanicalEnergyCK>; ref: general_dynamics/general_reduce_ck.h:52-88 */
 int sphb200_total_mechanical_energy(sphb200_context_t *ctx, const sphb200_fluid_view_t *fluid, const float gravity[3],
                                     double *energy_host, void *stream);

@@ -47,6 +47,7 @@ struct Vecd
     static Vecd Zero() { return Vecd(); }
 };
 using Vec3d = Vecd;
+template <class T> using StdVec = std::vector<T>; // base_data_type.h
 using Vec2d = Vecd;
 inline Vecd operator*(Real s, const Vecd &v) { return v * s; }
 

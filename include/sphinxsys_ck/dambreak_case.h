@@ -20,6 +20,8 @@ struct DamBreakParameters
     double DL = 5.366, DH = 2.0, DW = 0.5, LL = 2.0, LH = 1.0, LW = 0.5; // dambreak.cpp:13-18
     double rho0_f = 1.0, gravity_g = 1.0;                                // :22-23
     bool correction = false;   // LinearCorrectionCK variants (the reference case file uses them; the hot path is without)
+    bool surface_indicator = false; // FreeSurfaceIndicationComplexSpatialTemporalCK in the loop (dambreak.cpp:133-134,192)
+    bool observers = false;         // FluidObserver pressure probes of the case file (dambreak.cpp:54-65,87-88,140-141,223-224)
     bool fused_time_step = true;
     bool fused_regularization = true;
     int sort_interval = 100;   // :217-220
@@ -77,6 +79,11 @@ class DamBreakCK
     std::unique_ptr<StateDynamics<P, fluid_dynamics::AdvectionStepSetup>> water_advection_step_setup;
     std::unique_ptr<StateDynamics<P, fluid_dynamics::UpdateParticlePosition>> water_update_particle_position;
     std::unique_ptr<InteractionDynamicsCK<P, LinearCorrectionMatrixComplex>> fluid_linear_correction_matrix;
+    std::unique_ptr<InteractionDynamicsCK<P, fluid_dynamics::FreeSurfaceIndicationComplexSpatialTemporalCK>> fluid_boundary_indicator;
+    std::unique_ptr<ObserverBody> fluid_observer;
+    std::unique_ptr<Contact<>> fluid_observer_contact;
+    std::unique_ptr<UpdateRelation<P, Contact<>>> fluid_observer_contact_relation;
+    std::unique_ptr<ObservedQuantityRecording<P, Real>> fluid_observer_pressure;
     std::unique_ptr<InteractionDynamicsBase> fluid_acoustic_step_1st_half, fluid_acoustic_step_2nd_half;
     std::unique_ptr<InteractionDynamicsBase> fluid_density_summation;
     std::unique_ptr<StateDynamics<P, fluid_dynamics::DensityRegularization<SPHBody, WeaklyCompressibleFluid, FreeSurface>>> fluid_density_regularization;
@@ -95,6 +102,18 @@ class DamBreakCK
     double physical_time = 0; // accumulated in double for reporting; the SingleVariable keeps the Real copy
     Real last_acoustic_dt = 0, last_advection_dt = 0;
 
+    // createObservationPoints(), dambreak.cpp:54-65 (3-D) and Dambreak.cpp:27-28 (2-D)
+    static std::vector<Vecd> createObservationPoints(const DamBreakParameters &q)
+    {
+        std::vector<Vecd> pts;
+        if (q.dim == 2)
+        {
+            pts.push_back(Vecd(Real(q.DL), Real(0.2), 0));
+            return pts;
+        }
+        for (double y : {0.01, 0.1, 0.2, 0.24, 0.252, 0.266}) pts.push_back(Vecd(Real(q.DL), Real(y), Real(0.5 * q.DW)));
+        return pts;
+    }
     static BoundingBoxd caseBounds(const DamBreakParameters &q)
     {
         double BW = 4.0 * q.dp;
@@ -226,6 +245,21 @@ class DamBreakCK
             fluid_advection_time_step = adv;
             advection_reduced_value = [adv]() { return adv->ReducedValue(); };
             cuts_adv_ = adv; // gets the decomposition below, once it exists
+            if (q.surface_indicator)
+            {
+                if (q.nranks > 1) throw SphError("slab decomposition: FreeSurfaceIndicationCK is not decomposed yet");
+                fluid_boundary_indicator.reset(new InteractionDynamicsCK<P, FreeSurfaceIndicationComplexSpatialTemporalCK>(*water_block_inner, *water_wall_contact));
+            }
+            if (q.observers)
+            {
+                if (q.nranks > 1) throw SphError("slab decomposition: observers are not decomposed yet");
+                registerPressure();
+                fluid_observer.reset(new ObserverBody(sph_system, "FluidObserver"));
+                fluid_observer->generateParticles<ObserverParticles>(createObservationPoints(q));
+                fluid_observer_contact.reset(new Contact<>(*fluid_observer, {&water_block}));
+                fluid_observer_contact_relation.reset(new UpdateRelation<P, Contact<>>(*fluid_observer_contact));
+                fluid_observer_pressure.reset(new ObservedQuantityRecording<P, Real>(*fluid_observer_contact, "Pressure"));
+            }
         }
         water_block_update_complex_relation.reset(new UpdateRelation<P, Inner<>, Contact<>>(*water_block_inner, *water_wall_contact));
         record_water_mechanical_energy.reset(new ReduceDynamicsCK<P, TotalMechanicalEnergyCK>(water_block, gravity));
@@ -240,6 +274,8 @@ class DamBreakCK
         }
     }
 
+    void registerPressure() { water_block.getBaseParticles().registerStateVariable<Real>("Pressure"); }
+
     // dambreak.cpp:152-160
     void initialize()
     {
@@ -249,6 +285,11 @@ class DamBreakCK
         wall_cell_linked_list->exec();
         if (q_.legacy) water_wall_complex->updateConfiguration();
         else water_block_update_complex_relation->exec();
+        if (fluid_observer_contact_relation)
+        {
+            fluid_observer_contact_relation->exec();
+            fluid_observer_pressure->writeToFile(number_of_iterations); // first output before the main loop, dambreak.cpp:177
+        }
         fluid_acoustic_time_step->setPrimed(false);
     }
 
@@ -292,6 +333,7 @@ class DamBreakCK
         water_advection_step_setup->exec();
         if (decomposition) decomposition->refreshGhosts({"VolumetricMeasure"}); // neighbours read V_j of ghost particles
         Real advection_dt = fluid_advection_time_step->exec();
+        if (fluid_boundary_indicator) fluid_boundary_indicator->exec();
         if (q_.correction) fluid_linear_correction_matrix->exec();
         Real relaxation_time = 0, acoustic_dt = 0;
         int n_inner = 0;
@@ -326,6 +368,11 @@ class DamBreakCK
         if (decomposition) decomposition->rebuild(); // migration + ghost planes + cell-linked list
         else water_cell_linked_list->exec();
         water_block_update_complex_relation->exec();
+        if (fluid_observer_contact_relation)
+        {
+            fluid_observer_contact_relation->exec();
+            fluid_observer_pressure->writeToFile(number_of_iterations);
+        }
         last_acoustic_dt = acoustic_dt;
         last_advection_dt = advection_dt;
         return n_inner;

@@ -17,6 +17,9 @@
 #ifndef SPHINXSYS_CK_FLUID_DYNAMICS_H
 #define SPHINXSYS_CK_FLUID_DYNAMICS_H
 
+#include <fstream>
+#include <iomanip>
+
 #include "configuration.h"
 #include "slab_decomposition.h"
 
@@ -555,6 +558,38 @@ using AcousticStep1stHalfInnerRiemannCK = AcousticStep1stHalfWithWallRiemannCK;
 using AcousticStep2ndHalfInnerRiemannCK = AcousticStep2ndHalfWithWallRiemannCK;
 using AcousticStep1stHalfInnerNoRiemannCK = AcousticStep1stHalfWithWallNoRiemannCK;
 using AcousticStep2ndHalfInnerNoRiemannCK = AcousticStep2ndHalfWithWallNoRiemannCK;
+// ---- free-surface indication (general_dynamics/surface_indication/surface_indication_ck.h:19-170) ----
+// InteractionDynamicsCK<P, FreeSurfaceIndicationCK<Inner<WithUpdate>, Contact<>>>(inner, contact).exec():
+// inner interact (PositionDivergence, spatial-temporal override next to the previous surface) -> contact interact ->
+// update (Indicator, PreviousSurfaceIndicator).
+template <typename... RelationTypes> class FreeSurfaceIndicationCK;
+template <> class FreeSurfaceIndicationCK<Inner<WithUpdate>, Contact<>> : public FluidDynamicsBase
+{
+    Real threshold_by_dimensions_, smoothing_length_;
+
+  public:
+    FreeSurfaceIndicationCK(Inner<> &inner, Contact<> &contact)
+        : FluidDynamicsBase(inner, &contact), threshold_by_dimensions_(Real(0.75) * Real(inner.source_.getSPHSystem().dim_)),
+          smoothing_length_(inner.source_.getSPHAdaptation().ReferenceSmoothingLength())
+    {
+        // surface_indication_ck.hpp:17-20,42-46
+        particles_.registerStateVariable<int>("Indicator");
+        particles_.registerStateVariable<Real>("PositionDivergence");
+        particles_.registerStateVariable<int>("PreviousSurfaceIndicator", 1);
+        particles_.addEvolvingVariable<int>("PreviousSurfaceIndicator");
+    }
+    std::vector<BaseDynamics<void> *> deviceInteract(Real, const std::vector<BaseDynamics<void> *> &post)
+    {
+        if (decomposition_) throw SphError("FreeSurfaceIndicationCK: not available in slab-decomposed runs yet");
+        sphb200_fluid_args_t a = fluidArgs();
+        SPHCK_CALL(sphb200_free_surface_indication, &a, (int32_t *)particles_.deviceData<int>("Indicator"),
+                   (float *)particles_.deviceData<Real>("PositionDivergence"),
+                   (int32_t *)particles_.deviceData<int>("PreviousSurfaceIndicator"), threshold_by_dimensions_, smoothing_length_,
+                   execution_instance().stream());
+        return post;
+    }
+};
+using FreeSurfaceIndicationComplexSpatialTemporalCK = FreeSurfaceIndicationCK<Inner<WithUpdate>, Contact<>>;
 } // namespace fluid_dynamics
 
 // ---- general dynamics ----
@@ -624,6 +659,91 @@ class TotalMechanicalEnergyCK : public fluid_dynamics::FluidDynamicsBase
         if (decomposition_) e = decomposition_->allReduceSum(e);
         return e;
     }
+};
+
+// ---- observation (general_dynamics/interpolation_dynamics.h:43-150, io_system/io_observation_ck.h:38-107) ----
+// ObservingQuantityCK<P, DataType>(contact, "Name"): Interpolation<Contact<DataType>> of a variable of the observed
+// body at the particles of an observer body; the result lives in the observer's variable of the same name.
+template <class ExecutionPolicy, class DataType> class ObservingQuantityCK : public BaseDynamics<void>
+{
+    Contact<> &contact_;
+    std::string variable_name_;
+    DiscreteVariable<DataType> *dv_interpolated_quantities_;
+
+  public:
+    ObservingQuantityCK(Contact<> &contact, const std::string &variable_name)
+        : contact_(contact), variable_name_(variable_name),
+          dv_interpolated_quantities_(contact.source_.getBaseParticles().template registerStateVariable<DataType>(variable_name))
+    {
+        execution::require_device_policy<ExecutionPolicy>();
+        static_assert(std::is_same<DataType, Real>::value || std::is_same<DataType, Vecd>::value, "observed quantities are Real or Vecd");
+        contact.target_.getBaseParticles().template getVariableByName<DataType>(variable_name); // must exist on the observed body
+    }
+    DiscreteVariable<DataType> *dvInterpolatedQuantities() { return dv_interpolated_quantities_; }
+    void exec(Real dt = 0.0) override
+    {
+        SPHBody &observer = contact_.source_, &observed = contact_.target_;
+        observed.refreshPosVol();
+        BaseParticles &op = observer.getBaseParticles(), &tp = observed.getBaseParticles();
+        SPHCK_CALL(sphb200_interpolate, &contact_.kernel_, (const sphb200_vec4_t *)op.deviceData<Vecd>("Position"),
+                   (uint32_t)op.TotalRealParticles(), contact_.view(), (const sphb200_vec4_t *)tp.deviceData<Vecd>("PosVol"),
+                   (const float *)tp.template deviceData<DataType>(variable_name_), std::is_same<DataType, Vecd>::value ? 4 : 1,
+                   (float *)dv_interpolated_quantities_->deviceAddress(), execution_instance().stream());
+    }
+};
+
+// ObservedQuantityRecording<P, DataType>(contact, "Name"): writeToFile(iteration) runs the observation, brings the values
+// to the host and appends one record (physical time + one value per observer); records are kept in memory and, when an
+// output path is set, appended to a .dat file in the reference's column layout (io_observation_ck.h:69-94).
+template <class ExecutionPolicy, class DataType> class ObservedQuantityRecording
+{
+    SPHBody &observer_;
+    ObservingQuantityCK<ExecutionPolicy, DataType> observation_method_;
+    DiscreteVariable<DataType> *dv_interpolated_quantities_;
+    size_t number_of_observe_;
+    SingleVariable<Real> *sv_physical_time_;
+    std::string quantity_name_, file_path_;
+    bool header_written_ = false;
+    std::vector<Real> times_;
+    std::vector<std::vector<DataType>> records_;
+
+  public:
+    ObservedQuantityRecording(Contact<> &contact_relation, const std::string &variable_name)
+        : observer_(contact_relation.getSPHBody()), observation_method_(contact_relation, variable_name),
+          dv_interpolated_quantities_(observation_method_.dvInterpolatedQuantities()),
+          number_of_observe_(observer_.getBaseParticles().TotalRealParticles()),
+          sv_physical_time_(observer_.getSPHSystem().template getSystemVariableByName<Real>("PhysicalTime")), quantity_name_(variable_name) {}
+    void setOutputPath(const std::string &folder) { file_path_ = folder + "/" + observer_.Name() + "_" + quantity_name_ + ".dat"; }
+    void writeToFile(size_t iteration_step = 0)
+    {
+        observation_method_.exec();
+        dv_interpolated_quantities_->synchronizeWithDevice();
+        const DataType *v = dv_interpolated_quantities_->Data();
+        times_.push_back(sv_physical_time_->getValue());
+        records_.emplace_back(v, v + number_of_observe_);
+        if (file_path_.empty()) return;
+        if (!header_written_)
+        {
+            std::ofstream out(file_path_.c_str(), std::ios::out);
+            out << "run_time" << "   ";
+            for (size_t i = 0; i != number_of_observe_; ++i) out << quantity_name_ << "[" << i << "]" << "   ";
+            out << "\n";
+            header_written_ = true;
+        }
+        std::ofstream out(file_path_.c_str(), std::ios::app);
+        out << sv_physical_time_->getValue() << "   ";
+        for (size_t i = 0; i != number_of_observe_; ++i) writeValue(out, v[i]);
+        out << "\n";
+    }
+    DataType *getObservedQuantity() { return dv_interpolated_quantities_->Data(); }
+    size_t NumberOfObservedQuantity() { return number_of_observe_; }
+    DiscreteVariable<DataType> &getObservedVariable() { return *dv_interpolated_quantities_; }
+    const std::vector<Real> &recordedTimes() const { return times_; }
+    const std::vector<std::vector<DataType>> &records() const { return records_; }
+
+  private:
+    static void writeValue(std::ostream &out, Real v) { out << std::fixed << std::setprecision(9) << v << "   "; }
+    static void writeValue(std::ostream &out, const Vecd &v) { out << std::fixed << std::setprecision(9) << v.x << "   " << v.y << "   " << v.z << "   "; }
 };
 } // namespace SPH
 #endif

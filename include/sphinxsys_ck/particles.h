@@ -619,6 +619,20 @@ class SolidBody : public SPHBody
     }
 };
 
+// ObserverBody fluid_observer(sph_system, "FluidObserver"); fluid_observer.generateParticles<ObserverParticles>(points);
+// ref: bodies/base_body.h (ObserverBody), particle_generator (ObserverParticles): probe particles at given positions
+struct ObserverParticles {};
+class ObserverBody : public SPHBody
+{
+  public:
+    ObserverBody(SPHSystem &system, const std::string &name) : SPHBody(system, name) {}
+    template <class ParticlesType> void generateParticles(const std::vector<Vecd> &positions)
+    {
+        static_assert(std::is_same<ParticlesType, ObserverParticles>::value, "ObserverBody holds ObserverParticles");
+        generateParticlesFromPositions(positions, Real(0)); // observers carry no volume (they are never neighbours)
+    }
+};
+
 inline std::shared_ptr<ComplexShape> makeSharedShape(ComplexShape *s) { return std::shared_ptr<ComplexShape>(s); }
 template <class T, typename... Args> std::shared_ptr<T> makeShared(Args &&...args) { return std::make_shared<T>(std::forward<Args>(args)...); }
 } // namespace SPH

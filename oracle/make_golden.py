@@ -51,6 +51,49 @@ def reference_goldens():
     return out
 
 
+PROBES_3D = [[5.366, y, 0.25] for y in (0.01, 0.1, 0.2, 0.24, 0.252, 0.266)]  # createObservationPoints, dambreak.cpp:54-65
+
+
+def read_probe_series(path):
+    """{probe: [values]} from an ObservedQuantityRecording regression file (Particle_k snapshot_i="...")."""
+    s = open(path).read()
+    out = []
+    for k in range(64):
+        m = re.search(r"<Particle_%d ([^>]*)/>" % k, s)
+        if not m:
+            break
+        vals = re.findall(r'snapshot_(\d+)="([^"]+)"', m.group(1))
+        out.append([float("%.6g" % float(v)) for _, v in sorted(vals, key=lambda x: int(x[0]))])
+    return out
+
+
+def reference_pressure_goldens():
+    d = "tests_sycl/3d_examples/test_3d_dambreak_sycl/regression_test_tool"
+    base = os.path.join(REF, d)
+    thr = re.findall(r'Pressure_(\d+)="([^"]+)"', open(os.path.join(base, "FluidObserver_Pressure_dtwdistance.xml")).read())
+    return {"3d_dambreak_ck_sycl": {
+        "source": d, "probes": PROBES_3D,
+        "dtw_threshold": [float(v) for _, v in sorted(thr, key=lambda x: int(x[0]))],
+        "runs": {str(r): read_probe_series(os.path.join(base, f"FluidObserver_Pressure_Run_{r}_result.xml")) for r in (0, 10, 20)}}}
+
+
+def oracle_probe_series():
+    """The complete reference case file on the oracle (LinearCorrection variants + FreeSurfaceIndication + observers)."""
+    t0 = time.time()
+    c3 = cases.dam_break(dim=3, dp=0.05, dtype=np.float32)
+    s = orc.OracleSim(c3, f64=False, correction=1, surface_indicator=1, observers=PROBES_3D)
+    s.exec("prepare_ck")
+    s.exec("run_ck", 20.0, 1e9, 1.0, 100)
+    t, e = s.series()
+    p = s.probe_series()
+    print("3d ck full case done", time.time() - t0, p.shape, flush=True)
+    return {"3d_dambreak_ck_f32_full_case": {
+        "time": t.tolist(), "energy": e.tolist(), "pressure": [[float("%.6g" % v) for v in p[:, k]] for k in range(p.shape[1])],
+        "surface_particles_end": int(s.uint("Indicator").sum()),
+        "args": {"dim": 3, "dp": 0.05, "f64": False, "correction": 1, "surface_indicator": 1, "observers": PROBES_3D,
+                 "end_time": 20.0, "record_interval": 1.0, "sort_interval": 100}}}
+
+
 def oracle_series():
     out = {}
     t0 = time.time()
@@ -77,6 +120,11 @@ def oracle_series():
 
 if __name__ == "__main__":
     os.makedirs(OUT, exist_ok=True)
+    if "--pressure" in sys.argv:  # only the probe fixtures (the energy fixtures are left as they are)
+        if os.path.isdir(REF):
+            json.dump(reference_pressure_goldens(), open(os.path.join(OUT, "reference_pressure_probes.json"), "w"))
+        json.dump(oracle_probe_series(), open(os.path.join(OUT, "oracle_probe_series.json"), "w"))
+        sys.exit(0)
     if os.path.isdir(REF):
         json.dump(reference_goldens(), open(os.path.join(OUT, "reference_regression.json"), "w"), indent=1)
     json.dump(oracle_series(), open(os.path.join(OUT, "oracle_energy_series.json"), "w"), indent=1)

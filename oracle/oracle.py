@@ -37,7 +37,8 @@ class ParamsPOD(C.Structure):
                 ("h_min", C.c_double), ("acoustic_cfl", C.c_double), ("advection_cfl", C.c_double),
                 ("correction_alpha", C.c_double), ("sigma0", C.c_double), ("wall_rho0", C.c_double),
                 ("contact_depth", C.c_int), ("threads", C.c_int), ("periodic_axes", C.c_int),
-                ("periodic_lower", C.c_double * 3), ("periodic_upper", C.c_double * 3), ("periodic_cutoff", C.c_double)]
+                ("periodic_lower", C.c_double * 3), ("periodic_upper", C.c_double * 3), ("periodic_cutoff", C.c_double),
+                ("surface_indicator", C.c_int)]
 
 
 _lib = None
@@ -60,6 +61,8 @@ def lib():
         L.orc_exec.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_double, C.c_double, C.c_double]
         L.orc_series.restype = C.c_uint64
         L.orc_series.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.orc_probe_series.restype = C.c_uint64
+        L.orc_probe_series.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.orc_exclusive_scan_u32.restype = C.c_uint32
         L.orc_exclusive_scan_u32.argtypes = [C.c_void_p, C.c_void_p, C.c_uint32]
         L.orc_cell_keys.argtypes = [C.c_int, C.c_void_p, C.c_uint32, C.POINTER(MeshPOD), C.c_void_p, C.c_void_p]
@@ -122,7 +125,8 @@ def kernel_eval(kspec, which, q, f64=False):
 class OracleSim:
     """One fluid body + one wall body + inner/contact relations, advanced by the oracle."""
 
-    def __init__(self, case, f64=False, riemann=1, correction=0, free_surface=1, threads=0, contact_depth=1):
+    def __init__(self, case, f64=False, riemann=1, correction=0, free_surface=1, threads=0, contact_depth=1,
+                 surface_indicator=0, observers=None):
         self.case = case
         self.f64 = bool(f64)
         self.dtype = np.float64 if f64 else np.float32
@@ -140,6 +144,7 @@ class OracleSim:
                 p.periodic_lower[d] = case.periodic_lower[d]
                 p.periodic_upper[d] = case.periodic_upper[d]
             p.periodic_cutoff = float(self.dtype(case.kernel.cutoff))
+        p.surface_indicator = int(surface_indicator)
         self._params = p
         kp, mp = kernel_pod(case.kernel), mesh_pod(case.mesh)
         self._h = lib().orc_create(int(f64), C.byref(p), C.byref(kp), C.byref(mp), C.byref(mp), case.n_fluid, case.n_wall)
@@ -160,6 +165,14 @@ class OracleSim:
             self.real("Mass", wall=True)[:] = 1.0 * case.vol
             self.real("NormalDirection", 3, wall=True)[:] = case.wall_normal.reshape(-1)
 
+        if observers is not None and len(observers):
+            obs = np.asarray(observers, dtype=self.dtype).reshape(-1, 3)
+            self.n_observer = obs.shape[0]
+            self.exec("set_observers", self.n_observer)
+            self.real("Position", 3, body=2)[:] = obs.reshape(-1)
+        else:
+            self.n_observer = 0
+
     def __del__(self):
         try:
             if self._h:
@@ -168,10 +181,10 @@ class OracleSim:
         except Exception:
             pass
 
-    def real(self, name, width=1, wall=False) -> np.ndarray:
-        """numpy VIEW of a named Real array (re-fetch after ops that may reallocate, e.g. sort)."""
+    def real(self, name, width=1, wall=False, body=None) -> np.ndarray:
+        """numpy VIEW of a named Real array (re-fetch after ops that may reallocate, e.g. sort). body: 0 fluid, 1 wall, 2 observer."""
         ln = C.c_uint64()
-        ptr = lib().orc_real(self._h, int(wall), name.encode(), width, C.byref(ln))
+        ptr = lib().orc_real(self._h, int(wall) if body is None else int(body), name.encode(), width, C.byref(ln))
         ct = C.c_double if self.f64 else C.c_float
         if ln.value == 0:
             return np.empty(0, dtype=self.dtype)
@@ -189,6 +202,14 @@ class OracleSim:
         if r == -12345.0:
             raise ValueError(f"unknown oracle op {op}")
         return r
+
+    def probe_series(self):
+        """rows recorded by prepare_ck / run_ck: interpolated Pressure at every observer, one row per recorded step"""
+        rows = int(lib().orc_probe_series(self._h, None, 0))
+        out = np.empty((rows, max(self.n_observer, 1)), dtype=np.float64)
+        if rows:
+            lib().orc_probe_series(self._h, out.ctypes.data, rows)
+        return out[:, : self.n_observer]
 
     def series(self):
         n = lib().orc_series(self._h, None, None, 0)

@@ -427,6 +427,7 @@ struct ParamsPOD
     int periodic_axes;      // bit d: periodic along axis d (PeriodicAlongAxis, domain_bounding.h:48-66)
     double periodic_lower[3], periodic_upper[3]; // bounding_bounds_ (already rounded to Real by the caller)
     double periodic_cutoff; // cut_off_radius_max_
+    int surface_indicator;  // 1: FreeSurfaceIndicationCK runs in the case loop (dambreak.cpp:133-134,192)
 };
 
 template <class R> struct Body
@@ -446,9 +447,10 @@ template <class R> struct Sim
 {
     ParamsPOD P;
     Kernel<R> K;
-    Body<R> fluid, wall;
+    Body<R> fluid, wall, observer;
     CellList<R> fluid_cl, wall_cl;
-    CSR inner, contact;
+    CSR inner, contact, observer_contact;
+    std::vector<std::vector<double>> probe_series; // one row per recorded step: interpolated pressure at every probe
     // legacy per-pair storage (AoS Neighborhood restated in CSR order; neighborhood.h:49-66)
     std::vector<R> in_W, in_dW, in_r, in_e, ct_W, ct_dW, ct_r, ct_e;
     // riemann constants; ref: riemann_solver_ck.hpp:58-69
@@ -670,6 +672,12 @@ template <class R> struct Sim
             for (u32 i = 0; i < n; ++i)
                 for (size_t e = 0; e < w; ++e) a[w * i + e] = tmp[w * perm[i] + e];
         }
+        if (!legacy && fluid.uint.count("PreviousSurfaceIndicator")) // evolving: surface_indication_ck.hpp:43
+        {
+            std::vector<u32> &a = fluid.uint["PreviousSurfaceIndicator"];
+            std::vector<u32> t2(a);
+            for (u32 i = 0; i < n; ++i) a[i] = t2[perm[i]];
+        }
         std::vector<u32> &oid = fluid.uint["OriginalID"], &sid = fluid.uint["SortedID"];
         std::vector<u32> tmp(oid);
         for (u32 i = 0; i < n; ++i) oid[i] = tmp[perm[i]];
@@ -727,6 +735,97 @@ template <class R> struct Sim
             C[i] = P.free_surface ? SMAX(sum[i], R(1)) : sum[i];
             rho[i] = C[i] * rho0;
         }
+    }
+    // FreeSurfaceIndicationCK<Inner<WithUpdate>, Contact<>>; ref: general_dynamics/surface_indication/
+    // surface_indication_ck.hpp:12-160 (constructor constants :19-20, inner interact :52-70, near-previous :72-87,
+    // update :98-107, very-near :109-128, contact interact :149-160); sequencing interaction_algorithms_ck.cpp:6-34
+    void surfaceIndication()
+    {
+        const u32 n = fluid.n;
+        const std::vector<R> &pos = fluid.r("Position", 3), &Vol = fluid.r("VolumetricMeasure");
+        const std::vector<R> &wpos = wall.r("Position", 3), &wVol = wall.r("VolumetricMeasure");
+        std::vector<R> &pos_div = fluid.r("PositionDivergence");
+        std::vector<u32> &ind = fluid.uint["Indicator"], &prev = fluid.uint["PreviousSurfaceIndicator"];
+        if (ind.size() != n) ind.assign(n, 0u);
+        if (prev.size() != n) prev.assign(n, 1u); // registerStateVariable<int>("PreviousSurfaceIndicator", 1)
+        const R threshold = R(0.75) * R(P.dim), h = R(P.h_min);
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long i = 0; i < (long)n; ++i)
+        {
+            R pd(0);
+            for (u32 m = inner.offset[i]; m < inner.offset[i + 1]; ++m)
+            {
+                V3<R> d = innerDisp(pos, i, m);
+                pd -= K.dW(d) * Vol[inner.index[m]] * d.norm();
+            }
+            if (pd < threshold && prev[i] != 1u)
+            {
+                bool near_previous = false;
+                for (u32 m = inner.offset[i]; m < inner.offset[i + 1] && !near_previous; ++m)
+                    near_previous = prev[inner.index[m]] == 1u;
+                if (!near_previous) pd = R(2.0) * threshold;
+            }
+            R pw(0);
+            for (u32 m = contact.offset[i]; m < contact.offset[i + 1]; ++m)
+            {
+                u32 j = contact.index[m];
+                V3<R> d = vec(pos, i) - vec(wpos, j);
+                pw -= K.dW(d) * wVol[j] * d.norm();
+            }
+            pos_div[i] = pd + pw;
+        }
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long i = 0; i < (long)n; ++i)
+        {
+            u32 v = 1u;
+            if (pos_div[i] > threshold)
+            {
+                bool very_near = false;
+                for (u32 m = inner.offset[i]; m < inner.offset[i + 1] && !very_near; ++m)
+                {
+                    u32 j = inner.index[m];
+                    if (pos_div[j] < threshold && innerDisp(pos, i, m).norm() < h) very_near = true;
+                }
+                if (!very_near) v = 0u;
+            }
+            ind[i] = v;
+        }
+        prev = ind;
+    }
+    // observer probes: UpdateRelation<Contact<>> (observer -> fluid) + Interpolation<Contact<Real>> of "Pressure";
+    // ref: update_body_relation.hpp:199-288, general_dynamics/interpolation_dynamics.hpp:44-60, io_observation_ck.h:69-94
+    void observerRelation()
+    {
+        if (!observer.n) return;
+        const Kernel<R> &k = K;
+        auto crit = [&k](const R *a, const R *b) { return k.criterion(a, b); };
+        buildContact(observer_contact, fluid_cl, observer.r("Position", 3).data(), observer.n, fluid.r("Position", 3).data(), 1, crit);
+    }
+    void observe(const std::string &name)
+    {
+        if (!observer.n) return;
+        const std::vector<R> &opos = observer.r("Position", 3), &pos = fluid.r("Position", 3), &Vol = fluid.r("VolumetricMeasure");
+        const std::vector<R> &data = fluid.r(name);
+        std::vector<R> &out = observer.r(name);
+        for (u32 i = 0; i < observer.n; ++i)
+        {
+            R q(0), total(0);
+            for (u32 m = observer_contact.offset[i]; m < observer_contact.offset[i + 1]; ++m)
+            {
+                u32 j = observer_contact.index[m];
+                R w = K.W(vec(opos, i) - vec(pos, j)) * Vol[j];
+                q += w * data[j];
+                total += w;
+            }
+            out[i] = q / (total + R(2.71051e-20));
+        }
+    }
+    void recordProbes()
+    {
+        if (!observer.n) return;
+        observe("Pressure");
+        const std::vector<R> &out = observer.r("Pressure");
+        probe_series.emplace_back(out.begin(), out.end());
     }
     // ref: fluid_time_step_ck.h:139-180
     void advectionSetup()
@@ -1154,8 +1253,10 @@ template <class R> struct Sim
         cellListFluid();
         cellListWall();
         relationsCK();
-        energy_series.clear(); time_series.clear();
+        observerRelation();
+        energy_series.clear(); time_series.clear(); probe_series.clear();
         energy_series.push_back(mechanicalEnergy()); time_series.push_back(physical_time);
+        recordProbes(); // fluid_observer_pressure.writeToFile(number_of_iterations) before the loop, dambreak.cpp:177
     }
     long runCK(double end_time, long max_outer, double record_interval, int sort_interval)
     {
@@ -1169,6 +1270,7 @@ template <class R> struct Sim
                 densityRegularization();
                 advectionSetup();
                 double adv_dt = advectionDt();
+                if (P.surface_indicator) surfaceIndication(); // fluid_boundary_indicator.exec(), dambreak.cpp:192
                 if (P.correction) linearCorrection();
                 double relax = 0;
                 while (relax < adv_dt)
@@ -1185,6 +1287,8 @@ template <class R> struct Sim
                 if (P.periodic_axes) periodicBounding(); // taylor_green.cpp:186-191: bounding, cell list, images, configuration
                 cellListFluid();
                 relationsCK();
+                observerRelation(); // fluid_observer_contact_relation.exec(); fluid_observer_pressure.writeToFile(), :223-224
+                recordProbes();
             }
             if (integration_time >= record_interval)
             {
@@ -1283,6 +1387,11 @@ double execOp(Sim<R> &s, const std::string &op, double a0, double a1, double a2,
     else if (op == "acoustic2_wall") s.a2Wall();
     else if (op == "acoustic2_update") s.a2Update(R(a0));
     else if (op == "linear_correction") s.linearCorrection();
+    else if (op == "surface_indication") s.surfaceIndication();
+    else if (op == "set_observers") { s.observer.n = (u32)a0; s.observer.real.clear(); }
+    else if (op == "observer_relation") s.observerRelation();
+    else if (op == "observe_pressure") s.observe("Pressure");
+    else if (op == "probe_records") return (double)s.probe_series.size();
     else if (op == "energy") return s.mechanicalEnergy();
     else if (op == "legacy_density_summation") s.legacyDensitySummation();
     else if (op == "legacy1") s.legacy1(R(a0));
@@ -1335,12 +1444,12 @@ extern "C"
         Handle *h = (Handle *)hp;
         if (h->f64)
         {
-            auto &b = body ? h->d->wall : h->d->fluid;
+            auto &b = body == 2 ? h->d->observer : (body ? h->d->wall : h->d->fluid);
             auto &v = b.r(name, width);
             *len = v.size();
             return v.data();
         }
-        auto &b = body ? h->f->wall : h->f->fluid;
+        auto &b = body == 2 ? h->f->observer : (body ? h->f->wall : h->f->fluid);
         auto &v = b.r(name, width);
         *len = v.size();
         return v.data();
@@ -1363,6 +1472,8 @@ extern "C"
     else if (k == "fluid_ext_index") v = &S->fluid_cl.ext_index;                                                     \
     else if (k == "contact_offset") v = &S->contact.offset;                                                          \
     else if (k == "contact_index") v = &S->contact.index;                                                            \
+    else if (k == "observer_offset") v = &S->observer_contact.offset;                                                \
+    else if (k == "observer_index") v = &S->observer_contact.index;                                                  \
     else { S->ensureFluidState(); v = &S->fluid.uint[k]; }
         if (h->f64) { PICK(h->d) } else { PICK(h->f) }
 #undef PICK
@@ -1383,6 +1494,16 @@ extern "C"
         uint64_t m = std::min<uint64_t>(cap, e.size());
         for (uint64_t i = 0; i < m; ++i) { times[i] = t[i]; energy[i] = e[i]; }
         return e.size();
+    }
+
+    // recorded probe rows of the last prepare_ck/run_ck: out[row * n_probe + k]
+    uint64_t orc_probe_series(void *hp, double *out, uint64_t cap_rows)
+    {
+        Handle *h = (Handle *)hp;
+        const std::vector<std::vector<double>> &p = h->f64 ? h->d->probe_series : h->f->probe_series;
+        for (uint64_t r = 0; r < p.size() && r < cap_rows; ++r)
+            for (size_t k = 0; k < p[r].size(); ++k) out[r * p[r].size() + k] = p[r][k];
+        return p.size();
     }
 
     // ---- stand-alone primitives (no Sim) ----

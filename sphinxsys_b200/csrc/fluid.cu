@@ -1091,3 +1091,177 @@ extern "C" int sphb200_linear_correction_matrix(sphb200_context_t *ctx, const sp
     if (a.end > a.begin) SPH_LAUNCH(ctx, k_linear_correction, active_blocks(a, FL_THREADS), FL_THREADS, 0, stream, a, dwtab, alpha);
     return 0;
 }
+
+// =====================================================================================================
+// free-surface indication: FreeSurfaceIndicationCK<Inner<WithUpdate>, Contact<>>
+// general_dynamics/surface_indication/surface_indication_ck.hpp:52-160
+// =====================================================================================================
+// inner InteractKernel::interact (:52-70) + isNearPreviousFreeSurface (:72-87) + contact InteractKernel::interact (:149-160),
+// one launch: the contact part only adds to the particle's own PositionDivergence.
+template <bool ANALYTIC>
+__global__ void __launch_bounds__(FL_THREADS) k_surface_interact(FArgs a, KTab dwtab, const int *__restrict__ previous,
+                                                                  float *__restrict__ pos_div, float threshold)
+{
+    __shared__ float4 tab[KT_SLOTS];
+    if (!ANALYTIC) stage_tab(dwtab, tab);
+    u32 t = active_slot(a);
+    if (t < a.begin || t >= a.end) return;
+    const u32 i = a.order ? a.order[t] : t;
+    const float4 xi = a.posvol[i];
+    const u32 cnt = a.in_count[t];
+    const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
+    float pd = 0.f;
+#pragma unroll 4
+    for (u32 k = 0; k < cnt; ++k)
+    {
+        float4 xj = a.posvol[idx[32ull * k]];
+        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+        float r, inv_r;
+        dist(dx * dx + dy * dy + dz * dz, r, inv_r);
+        pd -= kernel_dw<ANALYTIC>(a, tab, r) * xj.w * r;
+    }
+    if (pd < threshold && previous[i] != 1)
+    {
+        // only particles that newly look like surface particles pay for the second sweep
+        bool near_previous = false;
+        for (u32 k = 0; k < cnt && !near_previous; ++k) near_previous = previous[idx[32ull * k]] == 1;
+        if (!near_previous) pd = 2.0f * threshold;
+    }
+    float pw = 0.f;
+    if (a.n_wall)
+    {
+        u32 wc = a.ct_count[t];
+        const u32 *widx = a.ct_index + (u64)a.ct_slice[t >> 5] + (t & 31u);
+#pragma unroll 4
+        for (u32 k = 0; k < wc; ++k)
+        {
+            float4 xj = a.w_posvol[widx[32ull * k]];
+            float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+            float r, inv_r;
+            dist(dx * dx + dy * dy + dz * dz, r, inv_r);
+            pw -= kernel_dw<ANALYTIC>(a, tab, r) * xj.w * r;
+        }
+    }
+    pos_div[i] = pd + pw;
+}
+
+// UpdateKernel::update (:98-107) + isVeryNearFreeSurface (:109-128). Separate launch: reads PositionDivergence of neighbours.
+__global__ void __launch_bounds__(FL_THREADS) k_surface_update(FArgs a, const float *__restrict__ pos_div, int *__restrict__ indicator,
+                                                                int *__restrict__ previous, float threshold, float smoothing_length)
+{
+    u32 t = active_slot(a);
+    if (t < a.begin || t >= a.end) return;
+    const u32 i = a.order ? a.order[t] : t;
+    int ind = 1;
+    if (pos_div[i] > threshold)
+    {
+        const float4 xi = a.posvol[i];
+        const u32 cnt = a.in_count[t];
+        const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
+        bool very_near = false;
+        for (u32 k = 0; k < cnt && !very_near; ++k)
+        {
+            u32 j = idx[32ull * k];
+            if (pos_div[j] < threshold)
+            {
+                float4 xj = a.posvol[j];
+                float dx = __fsub_rn(xi.x, xj.x), dy = __fsub_rn(xi.y, xj.y), dz = __fsub_rn(xi.z, xj.z);
+                very_near = sqrtf(norm2_rn(dx, dy, dz)) < smoothing_length; // same rounding as the CPU evaluation
+            }
+        }
+        if (!very_near) ind = 0;
+    }
+    indicator[i] = ind;
+    previous[i] = ind;
+}
+
+extern "C" int sphb200_free_surface_indication(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, int32_t *indicator,
+                                               float *position_divergence, int32_t *previous_indicator, float threshold,
+                                               float smoothing_length, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && s && indicator && position_divergence && previous_indicator, "null pointer");
+    FArgs a;
+    KTab dwtab;
+    int rc = make_fargs(ctx, s, &a, nullptr, &dwtab);
+    if (rc) return rc;
+    SPH_CHECK_ARG(ctx, a.n == 0 || (a.posvol && a.in_count && a.in_slice && a.in_index), "null fluid array");
+    SPH_CHECK_ARG(ctx, a.n_wall == 0 || (a.w_posvol && a.ct_count && a.ct_slice && a.ct_index), "null wall array");
+    if (a.end <= a.begin) return 0;
+    unsigned g = active_blocks(a, FL_THREADS);
+    if (a.analytic) SPH_LAUNCH(ctx, k_surface_interact<true>, g, FL_THREADS, 0, stream, a, dwtab, previous_indicator, position_divergence, threshold);
+    else SPH_LAUNCH(ctx, k_surface_interact<false>, g, FL_THREADS, 0, stream, a, dwtab, previous_indicator, position_divergence, threshold);
+    SPH_LAUNCH(ctx, k_surface_update, g, FL_THREADS, 0, stream, a, position_divergence, indicator, previous_indicator, threshold,
+               smoothing_length);
+    return 0;
+}
+
+// =====================================================================================================
+// observation: Interpolation<Contact<DataType>>::InteractKernel::interact, general_dynamics/interpolation_dynamics.hpp:44-60
+//   out_i = sum_j W_ij V_j data_j / (sum_j W_ij V_j + TinyReal)
+// One thread per observer particle (observer bodies hold a handful of probes; their rows are in plain slot order).
+// =====================================================================================================
+template <int WIDTH, bool ANALYTIC>
+__global__ void __launch_bounds__(128) k_interpolate(FArgs a, KTab wtab, const float4 *__restrict__ src_pos, u32 n_src,
+                                                     const u32 *__restrict__ count, const u32 *__restrict__ slice,
+                                                     const u32 *__restrict__ index, const float4 *__restrict__ tar_posvol,
+                                                     const float *__restrict__ tar_data, float *__restrict__ out)
+{
+    __shared__ float4 tab[KT_SLOTS];
+    if (!ANALYTIC) stage_tab(wtab, tab);
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_src) return;
+    const float4 xi = src_pos[t];
+    const u32 cnt = count[t];
+    const u32 *idx = index + (u64)slice[t >> 5] + (t & 31u);
+    float acc[WIDTH];
+#pragma unroll
+    for (int c = 0; c < WIDTH; ++c) acc[c] = 0.f;
+    float total = 0.f;
+    for (u32 k = 0; k < cnt; ++k)
+    {
+        u32 j = idx[32ull * k];
+        float4 xj = tar_posvol[j];
+        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+        float r = sqrtf(dx * dx + dy * dy + dz * dz);
+        float w = kernel_w<ANALYTIC>(a, tab, r) * xj.w;
+#pragma unroll
+        for (int c = 0; c < WIDTH; ++c) acc[c] += w * tar_data[(u64)WIDTH * j + c];
+        total += w;
+    }
+    const float denom = total + 2.71051e-20f; // TinyReal, base_data_type.h:207
+#pragma unroll
+    for (int c = 0; c < WIDTH; ++c) out[(u64)WIDTH * t + c] = acc[c] / denom;
+}
+
+extern "C" int sphb200_interpolate(sphb200_context_t *ctx, const sphb200_kernel_t *kernel, const sphb200_vec4_t *src_pos,
+                                   uint32_t n_src, sphb200_relation_t rel, const sphb200_vec4_t *tar_posvol, const float *tar_data,
+                                   int width, float *out, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && kernel, "null pointer");
+    SPH_CHECK_ARG(ctx, width == 1 || width == 4, "width must be 1 (Real) or 4 (Vecd stored as float4)");
+    if (n_src == 0) return 0;
+    SPH_CHECK_ARG(ctx, src_pos && rel.count && rel.slice_offset && rel.index && tar_posvol && tar_data && out, "null pointer");
+    SPH_CHECK_ARG(ctx, rel.order == nullptr, "observer rows must be in plain slot order");
+    sphb200_fluid_args_t s;
+    memset(&s, 0, sizeof(s));
+    s.kernel = *kernel;
+    s.material.rho0 = 1.f;
+    s.material.c0 = 1.f;
+    FArgs a;
+    KTab wtab;
+    int rc = make_fargs(ctx, &s, &a, &wtab, nullptr);
+    if (rc) return rc;
+    unsigned g = sph_blocks(n_src, 128);
+    const float4 *sp = (const float4 *)src_pos, *tp = (const float4 *)tar_posvol;
+    if (width == 1)
+    {
+        if (a.analytic) SPH_LAUNCH(ctx, (k_interpolate<1, true>), g, 128, 0, stream, a, wtab, sp, n_src, rel.count, rel.slice_offset, rel.index, tp, tar_data, out);
+        else SPH_LAUNCH(ctx, (k_interpolate<1, false>), g, 128, 0, stream, a, wtab, sp, n_src, rel.count, rel.slice_offset, rel.index, tp, tar_data, out);
+    }
+    else
+    {
+        if (a.analytic) SPH_LAUNCH(ctx, (k_interpolate<4, true>), g, 128, 0, stream, a, wtab, sp, n_src, rel.count, rel.slice_offset, rel.index, tp, tar_data, out);
+        else SPH_LAUNCH(ctx, (k_interpolate<4, false>), g, 128, 0, stream, a, wtab, sp, n_src, rel.count, rel.slice_offset, rel.index, tp, tar_data, out);
+    }
+    return 0;
+}

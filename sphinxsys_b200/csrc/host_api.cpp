@@ -76,6 +76,8 @@ extern "C"
         int32_t legacy;                  // legacy API/formulation (Integration1stHalf/2ndHalf, DensitySummation)
         int32_t rank, nranks;            // slab decomposition: one process per GPU
         uint8_t unique_id[128];          // communicator id from sphck_comm_unique_id on rank 0 (nranks > 1)
+        int32_t surface_indicator;       // FreeSurfaceIndicationComplexSpatialTemporalCK in the loop
+        int32_t observers;               // the case file's pressure probes (ObserverBody + ObservedQuantityRecording)
     };
 
     const char *sphck_last_error() { return g_error.c_str(); }
@@ -151,6 +153,8 @@ extern "C"
             q.fused_regularization = o->fused_regularization != 0;
             q.sort_interval = o->sort_interval;
             q.legacy = o->legacy != 0;
+            q.surface_indicator = o->surface_indicator != 0;
+            q.observers = o->observers != 0;
             q.rank = o->rank;
             q.nranks = o->nranks > 0 ? o->nranks : 1;
             if (q.nranks > 1)
@@ -317,6 +321,19 @@ extern "C"
             else if (op == "acoustic1") s.fluid_acoustic_step_1st_half->exec(Real(a0));
             else if (op == "acoustic2") s.fluid_acoustic_step_2nd_half->exec(Real(a0));
             else if (op == "linear_correction") { if (s.fluid_linear_correction_matrix) s.fluid_linear_correction_matrix->exec(); }
+            else if (op == "surface_indication")
+            {
+                if (!s.fluid_boundary_indicator) throw SphError("case built without surface_indicator");
+                s.fluid_boundary_indicator->exec();
+            }
+            else if (op == "observer_relation") { if (s.fluid_observer_contact_relation) s.fluid_observer_contact_relation->exec(); }
+            else if (op == "observe_pressure")
+            {
+                if (!s.fluid_observer_pressure) throw SphError("case built without observers");
+                s.fluid_observer_pressure->writeToFile(s.number_of_iterations);
+            }
+            else if (op == "probe_records") r = s.fluid_observer_pressure ? (double)s.fluid_observer_pressure->records().size() : 0.0;
+            else if (op == "probe_count") r = s.fluid_observer_pressure ? (double)s.fluid_observer_pressure->NumberOfObservedQuantity() : 0.0;
             else if (op == "energy") r = s.record_water_mechanical_energy->exec();
             else if (op == "physical_time") r = s.physical_time;
             else if (op == "acoustic_steps") r = (double)s.acoustic_steps;
@@ -359,6 +376,7 @@ extern "C"
             if (kind == 0) p.download(p.getVariableByName<Real>(name), (Real *)out);
             else if (kind == 1) p.download(p.getVariableByName<Vecd>(name), (Vecd *)out);
             else if (kind == 2) p.download(p.getVariableByName<UnsignedInt>(name), (UnsignedInt *)out);
+            else if (kind == 4) p.download(p.getVariableByName<int>(name), (int *)out);
             else p.download(p.getVariableByName<Matd>(name), (Matd *)out);
         });
     }
@@ -370,6 +388,7 @@ extern "C"
             if (kind == 0) p.upload(p.getVariableByName<Real>(name), (const Real *)in);
             else if (kind == 1) p.upload(p.getVariableByName<Vecd>(name), (const Vecd *)in);
             else if (kind == 2) p.upload(p.getVariableByName<UnsignedInt>(name), (const UnsignedInt *)in);
+            else if (kind == 4) p.upload(p.getVariableByName<int>(name), (const int *)in);
             else p.upload(p.getVariableByName<Matd>(name), (const Matd *)in);
             b.setPosVolDirty();
             ((Handle *)hp)->acousticTimeStep()->setPrimed(false);
@@ -389,6 +408,22 @@ extern "C"
             else out = p.deviceData<Matd>(name);
         });
         return out;
+    }
+
+    // recorded probe rows (ObservedQuantityRecording::records()): times[rows], values[rows * probes]
+    int sphck_probe_records(void *hp, double *times, double *values, uint64_t capacity_rows)
+    {
+        return guarded([&] {
+            Handle *h = (Handle *)hp;
+            if (!h->sim || !h->sim->fluid_observer_pressure) throw SphError("case built without observers");
+            auto &rec = *h->sim->fluid_observer_pressure;
+            const auto &rows = rec.records();
+            for (size_t r = 0; r < rows.size() && r < capacity_rows; ++r)
+            {
+                times[r] = rec.recordedTimes()[r];
+                for (size_t k = 0; k < rows[r].size(); ++k) values[r * rows[r].size() + k] = rows[r][k];
+            }
+        });
     }
 
     // cell-linked list (cell_offset[cells + 1]) and relation CSR in reference ids.

@@ -21,6 +21,7 @@ VEC_NAMES = {"Position", "Velocity", "Displacement", "Force", "ForcePrior", "Nor
              "AverageVelocity", "AverageAcceleration"}
 UINT_NAMES = {"OriginalID", "SortedID", "ReferenceID"}
 MAT_NAMES = {"LinearCorrectionMatrix"}
+INT_NAMES = {"Indicator", "PreviousSurfaceIndicator"}
 
 
 class Options(C.Structure):
@@ -29,7 +30,7 @@ class Options(C.Structure):
                 ("fused_time_step", C.c_int32), ("fused_regularization", C.c_int32), ("sort_interval", C.c_int32),
                 ("device", C.c_int32), ("relation_stride", C.c_int32), ("system_lower", C.c_double * 3),
                 ("system_upper", C.c_double * 3), ("use_system_bounds", C.c_int32), ("legacy", C.c_int32), ("rank", C.c_int32),
-                ("nranks", C.c_int32), ("unique_id", C.c_uint8 * 128)]
+                ("nranks", C.c_int32), ("unique_id", C.c_uint8 * 128), ("surface_indicator", C.c_int32), ("observers", C.c_int32)]
 
 
 class TaylorGreenOptions(C.Structure):
@@ -77,6 +78,7 @@ def load():
         L.sphck_cuts.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.sphck_plan_slab_cuts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.sphck_export_csr.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.sphck_probe_records.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         _lib = L
     return _lib
 
@@ -99,7 +101,7 @@ def plan_slab_cuts(per_plane, nranks):
 
 
 def _kind(name):
-    return 1 if name in VEC_NAMES else (2 if name in UINT_NAMES else (3 if name in MAT_NAMES else 0))
+    return 1 if name in VEC_NAMES else (2 if name in UINT_NAMES else (3 if name in MAT_NAMES else (4 if name in INT_NAMES else 0)))
 
 
 class DamBreakCK:
@@ -107,7 +109,7 @@ class DamBreakCK:
 
     def __init__(self, case=None, device_index=0, correction=False, fused_time_step=True, sort_interval=100,
                  relation_stride=None, fused_regularization=True, dim=3, dp=0.05, generate=False, rank=0, nranks=1,
-                 unique_id=None, width_scale=1.0, legacy=False):
+                 unique_id=None, width_scale=1.0, legacy=False, surface_indicator=False, observers=False):
         self.lib = load()
         o = Options()
         if case is not None:
@@ -122,6 +124,7 @@ class DamBreakCK:
         o.use_system_bounds = 0
         o.DW, o.LW = o.DW * width_scale, o.LW * width_scale
         o.legacy = int(bool(legacy))
+        o.surface_indicator, o.observers = int(bool(surface_indicator)), int(bool(observers))
         o.rank, o.nranks = int(rank), int(nranks)
         if nranks > 1:
             if unique_id is None or len(unique_id) != 128:
@@ -203,7 +206,8 @@ class DamBreakCK:
         """Host copy of a variable in the reference particle order (Vecd packed as 3 floats)."""
         n = self.n_wall if wall else self.n_fluid
         k = _kind(name)
-        shape, dt = {0: ((n,), np.float32), 1: ((n, 3), np.float32), 2: ((n,), np.uint32), 3: ((n, 9), np.float32)}[k]
+        shape, dt = {0: ((n,), np.float32), 1: ((n, 3), np.float32), 2: ((n,), np.uint32), 3: ((n, 9), np.float32),
+                     4: ((n,), np.int32)}[k]
         if out is None:
             out = np.empty(shape, dtype=dt)
         self._check(self.lib.sphck_download(self._h, int(wall), name.encode(), k, out.ctypes.data), f"download {name}")
@@ -211,7 +215,7 @@ class DamBreakCK:
 
     def upload(self, name, arr, wall=False):
         k = _kind(name)
-        dt = np.uint32 if k == 2 else np.float32
+        dt = np.uint32 if k == 2 else (np.int32 if k == 4 else np.float32)
         a = np.ascontiguousarray(arr, dtype=dt)
         self._check(self.lib.sphck_upload(self._h, int(wall), name.encode(), k, a.ctypes.data), f"upload {name}")
 
@@ -239,6 +243,15 @@ class DamBreakCK:
         """Raw upload of this rank's own particles (storage order, device element layout). Asynchronous for pinned memory."""
         b, c, _ = self.own_range()
         self._check(self.lib.sphck_upload_raw(self._h, 0, name.encode(), arr.ctypes.data, b, c), f"upload_raw {name}")
+
+    def probe_records(self):
+        """(times[rows], pressure[rows, probes]) recorded by the case's ObservedQuantityRecording so far."""
+        rows, probes = int(self.exec("probe_records")), int(self.exec("probe_count"))
+        t = np.zeros(rows, dtype=np.float64)
+        v = np.zeros((rows, max(probes, 1)), dtype=np.float64)
+        if rows:
+            self._check(self.lib.sphck_probe_records(self._h, t.ctypes.data, v.ctypes.data, rows), "probe_records")
+        return t, v[:, :probes]
 
     def cuts(self) -> np.ndarray:
         out = np.zeros(self.nranks + 1, dtype=np.int32)
