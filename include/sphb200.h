@@ -151,6 +151,11 @@ typedef struct
     uint32_t *index;        /* [capacity] */
     uint64_t capacity;      /* entries allocated for `index` */
     const uint32_t *order;  /* [n] slot -> source particle id, or NULL (identity) */
+    int32_t bank_aligned;   /* 1 (cell-ordered one-pass builds only): after the search the entries of every row are permuted
+                               inside groups of 32 so that entry s in row k of slot t has (s - t - k) mod 8 == 0 wherever
+                               possible — in every row the 8 lanes of a quarter warp then gather records from 8 different
+                               L1 bank groups. Entry SET and count are unchanged; sphb200_relation_export_csr sorts such rows
+                               back into ascending target order. 0: rows in search order (cells x -> y -> z, in-cell order). */
 } sphb200_relation_t;
 
 /* One neighbour search: which particles look (src, in slot order), where they look (tar body + its cell list) */
@@ -294,7 +299,8 @@ int sphb200_ghost_copy(sphb200_context_t *ctx, void *array, uint32_t elem_bytes,
                        const uint32_t *ghost_src, uint32_t n_real, uint32_t n_ghost, void *stream);
 /* SELL-32 (slot order) -> reference CSR indexed by particle id (particle_offset_[n+1], neighbor_index_[total]).
  * src_ids: slot -> id of the source particle (NULL: rel.order, else identity); tar_ids: stored target index -> id
- * (NULL: identity). Row order is preserved. */
+ * (NULL: identity). Row order is preserved (rel.bank_aligned: rows are emitted in ascending stored target index, which
+ * is the reference search order for cell-ordered bodies). */
 int sphb200_relation_export_csr(sphb200_context_t *ctx, sphb200_relation_t rel, uint32_t n, const uint32_t *src_ids,
                                 const uint32_t *tar_ids, uint32_t *particle_offset, uint32_t *neighbor_index,
                                 uint64_t index_capacity, void *stream);

@@ -65,6 +65,7 @@ class RelationBase
     sphb200_kernel_t kernel_;
     int search_depth_ = 1;
     bool legacy_criterion_ = false; // NeighborBuilder criterion |d|^2 < rc^2 (legacy InnerRelation / ContactRelation)
+    bool bank_aligned_ = false;     // rows laid out for the L1 banks by the last build (sphb200_relation_t::bank_aligned)
 
     RelationBase(SPHBody &source, SPHBody &target, bool is_inner) : source_(source), target_(target), is_inner_(is_inner)
     {
@@ -97,6 +98,7 @@ class RelationBase
         r.index = index_.get<uint32_t>();
         r.capacity = capacity_;
         r.order = nullptr; // storage is cell ordered: slot == particle id
+        r.bank_aligned = bank_aligned_ ? 1 : 0;
         return r;
     }
     sphb200_search_t search()
@@ -220,6 +222,16 @@ template <class ExecutionPolicy, class BodyType = RealBody> class UpdateCellLink
 // ---------------------------------------------------------------------------------------------------------
 // UpdateRelation<Policy, Inner<>, Contact<>> (any number of relations, executed in order)
 // ---------------------------------------------------------------------------------------------------------
+// SPHB200_BANK_ALIGN=0 in the environment switches the L1-bank-aligned row layout off (A/B measurements only)
+inline bool bankAlignEnabled()
+{
+    static const bool on = [] {
+        const char *e = std::getenv("SPHB200_BANK_ALIGN");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 template <class ExecutionPolicy, class... RelationTypes> class UpdateRelation : public BaseDynamics<void>
 {
     std::vector<RelationBase *> relations_;
@@ -233,6 +245,7 @@ template <class ExecutionPolicy, class... RelationTypes> class UpdateRelation : 
         {
             sphb200_search_t s = r->search(); // creates pending periodic images first: they are stored particles too
             uint32_t n = s.n_src;
+            r->bank_aligned_ = r->fixed_stride_ && s.cell_ordered && bankAlignEnabled();
             if (r->fixed_stride_)
             {
                 uint64_t need = (uint64_t)((n + 31) / 32) * 32ull * r->fixed_stride_;
@@ -243,6 +256,7 @@ template <class ExecutionPolicy, class... RelationTypes> class UpdateRelation : 
                 r->total_ = need;
                 if (mx <= r->fixed_stride_) continue;
                 r->fixed_stride_ = 0; // a row overflowed the stride: rebuild exactly, and stay exact from now on
+                r->bank_aligned_ = false;
             }
             uint64_t required = 0;
             SPHCK_CALL(sphb200_relation_count, &s, r->view(), &required, ex.stream());

@@ -55,7 +55,8 @@ class CellListT(C.Structure):
 
 
 class RelationT(C.Structure):
-    _fields_ = [("count", _P), ("slice_offset", _P), ("index", _P), ("capacity", C.c_uint64), ("order", _P)]
+    _fields_ = [("count", _P), ("slice_offset", _P), ("index", _P), ("capacity", C.c_uint64), ("order", _P),
+                ("bank_aligned", C.c_int32)]
 
 
 class SearchT(C.Structure):

@@ -20,7 +20,10 @@
 #include "common.cuh"
 
 constexpr int FL_THREADS = 128;
-constexpr int FL_MIN_BLOCKS = 10; // <= 48 registers: 62% occupancy instead of 50% (the gather loops are latency/L1 bound)
+#ifndef SPH_FL_MIN_BLOCKS
+#define SPH_FL_MIN_BLOCKS 8
+#endif
+constexpr int FL_MIN_BLOCKS = SPH_FL_MIN_BLOCKS; // 8: <= 64 registers, 50% occupancy with 4 gathers in flight per warp (scripts/gpu_variants.sh sweep)
 constexpr int KT_INTERVALS = 21; // intervals of the 24-entry table that q in [0, 2] can select
 constexpr int KT_SLOTS = 32;     // padded so that (index & 31) can never leave the table
 
@@ -276,6 +279,45 @@ __device__ __forceinline__ void load_mat(const float *B, u32 i, float *out)
 #pragma unroll
     for (int k = 0; k < 9; ++k) out[k] = B[9ull * i + k];
 }
+
+
+// -----------------------------------------------------------------------------------------------------
+// Neighbour loop with explicit memory-level parallelism. A plain `for (k < cnt)` loop has a lane-dependent exit, so
+// the compiler may not hoist the index load or the gather of iteration k+1 above the exit test of iteration k: every
+// iteration then pays index latency (the index stream comes from DRAM) + gather latency back to back, and the kernels
+// were latency bound at one outstanding gather per warp (profiles/r01_v4_*). Here the rows of a slot are walked in
+// batches of U: the U indices of the NEXT batch are loaded while the current batch is gathered and evaluated, and the
+// U gathers of a batch are issued together. Rows past the end are clamped to the last valid row (always a legal
+// index) and masked out by `valid`, which the bodies fold into the pair weight.
+//   gather(u, j)        : load what the pair needs into slot u of the body's staging registers
+//   compute(u, valid)   : evaluate pair u; valid == false must contribute nothing
+// -----------------------------------------------------------------------------------------------------
+#ifndef SPH_NB_U
+#define SPH_NB_U 4
+#endif
+constexpr int NB_U = SPH_NB_U;
+template <int U = NB_U, class Gather, class Compute>
+__device__ __forceinline__ void for_neighbors(const u32 *__restrict__ idx, u32 cnt, Gather gather, Compute compute)
+{
+    if (cnt == 0) return;
+    const u32 last = cnt - 1u;
+    u32 j[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) j[u] = idx[32ull * min((u32)u, last)];
+    for (u32 k = 0; k < cnt; k += U)
+    {
+        u32 jn[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) jn[u] = idx[32ull * min(k + U + (u32)u, last)];
+#pragma unroll
+        for (int u = 0; u < U; ++u) gather(u, j[u]);
+#pragma unroll
+        for (int u = 0; u < U; ++u) compute(u, k + (u32)u < cnt);
+#pragma unroll
+        for (int u = 0; u < U; ++u) j[u] = jn[u];
+    }
+}
+constexpr int NB_WALL_U = 2; // wall pairs need up to three records each: smaller batches keep the kernels spill-free
 
 // RiemannSolver<...>::ComputingKernel::DissipativePJump, riemann_solver_ck.hpp:44-49
 template <int RIEMANN> __device__ __forceinline__ float pjump(const FArgs &a, float u)
@@ -565,31 +607,35 @@ __global__ void __launch_bounds__(FL_THREADS) k_compression_summation(FArgs a, K
     {
         u32 cnt = a.in_count[t];
         const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
-#pragma unroll 4
-        for (u32 k = 0; k < cnt; ++k)
-        {
-            u32 j = idx[32ull * k];
-            float4 xj = a.posvolref[j];
-            float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-            float r = sqrtf(dx * dx + dy * dy + dz * dz);
-            s += kernel_w<ANALYTIC>(a, tab, r) * (a.legacy ? 1.0f : xj.w);
-        }
+        float4 xj[NB_U];
+        const bool legacy = a.legacy != 0;
+        for_neighbors(
+            idx, cnt, [&](int u, u32 j) { xj[u] = a.posvolref[j]; },
+            [&](int u, bool valid) {
+                float dx = xi.x - xj[u].x, dy = xi.y - xj[u].y, dz = xi.z - xj[u].z;
+                float r, inv_r;
+                dist(dx * dx + dy * dy + dz * dz, r, inv_r);
+                float w = kernel_w<ANALYTIC>(a, tab, r) * (legacy ? 1.0f : xj[u].w);
+                s += valid ? w : 0.f;
+            });
     }
     float sw = 0.f; // legacy: wall part is weighted separately (density_summation.cpp:58-78)
     if (a.n_wall)
     {
         u32 cnt = a.ct_count[t];
         const u32 *idx = a.ct_index + (u64)a.ct_slice[t >> 5] + (t & 31u);
-#pragma unroll 4
-        for (u32 k = 0; k < cnt; ++k)
-        {
-            u32 j = idx[32ull * k];
-            float4 xj = a.w_posvolref[j];
-            float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-            float r = sqrtf(dx * dx + dy * dy + dz * dz);
-            float w = kernel_w<ANALYTIC>(a, tab, r) * xj.w;
-            if (a.legacy) sw += w; else s += w;
-        }
+        float4 xj[NB_U];
+        const bool legacy = a.legacy != 0;
+        for_neighbors(
+            idx, cnt, [&](int u, u32 j) { xj[u] = a.w_posvolref[j]; },
+            [&](int u, bool valid) {
+                float dx = xi.x - xj[u].x, dy = xi.y - xj[u].y, dz = xi.z - xj[u].z;
+                float r, inv_r;
+                dist(dx * dx + dy * dy + dz * dz, r, inv_r);
+                float w = kernel_w<ANALYTIC>(a, tab, r) * xj[u].w;
+                w = valid ? w : 0.f;
+                if (legacy) sw += w; else s += w;
+            });
     }
     if (a.legacy)
     {
@@ -692,37 +738,45 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
     {
         u32 cnt = a.in_count[t];
         const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
-#pragma unroll 4
-        for (u32 k = 0; k < cnt; ++k)
-        {
-            u32 j = idx[32ull * k];
-            float4 xj = a.posvol[j];
-            float p_j = a.p[j];
-            float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-            float r2 = dx * dx + dy * dy + dz * dz;
-            float r, inv_r;
-            dist(r2, r, inv_r);
-            float dWV = kernel_dw<ANALYTIC>(a, tab, r) * xj.w;
-            if (CORR)
-            {
-                float Bj[9];
-                load_mat(a.B, j, Bj);
-                float3 e = make_float3(dx * inv_r, dy * inv_r, dz * inv_r);
-                float3 bje = mat_vec(Bj, e), bie = mat_vec(Bi, e);
-                // AverageP(B_j p_i, B_i p_j) * 2 dWV * e
-                float c = dWV; // 2 dWV * Z / (Z + Z)
-                fx -= c * (p_i * bje.x + p_j * bie.x);
-                fy -= c * (p_i * bje.y + p_j * bie.y);
-                fz -= c * (p_i * bje.z + p_j * bie.z);
-            }
-            else
-            {
-                // AverageP (riemann_solver_ck.hpp:19-24) with Z_i == Z_j (one fluid): 2 * pave = p_i + p_j
-                float c = (p_i + p_j) * dWV * inv_r;
-                fx -= c * dx; fy -= c * dy; fz -= c * dz;
-            }
-            if (RIEMANN) diss += (p_i - p_j) * a.inv_Z_ave * dWV; // DissipativeUJump, :51-56
-        }
+        float4 xjs[NB_U];
+        float pjs[NB_U];
+        u32 js[NB_U];
+        for_neighbors(
+            idx, cnt,
+            [&](int u, u32 j) {
+                xjs[u] = a.posvol[j];
+                pjs[u] = a.p[j];
+                if (CORR) js[u] = j;
+            },
+            [&](int u, bool valid) {
+                const float4 xj = xjs[u];
+                const float p_j = pjs[u];
+                float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                float r2 = dx * dx + dy * dy + dz * dz;
+                float r, inv_r;
+                dist(r2, r, inv_r);
+                float dWV = kernel_dw<ANALYTIC>(a, tab, r) * xj.w;
+                dWV = valid ? dWV : 0.f;
+                if (CORR)
+                {
+                    float Bj[9];
+                    load_mat(a.B, js[u], Bj);
+                    float3 e = make_float3(dx * inv_r, dy * inv_r, dz * inv_r);
+                    float3 bje = mat_vec(Bj, e), bie = mat_vec(Bi, e);
+                    // AverageP(B_j p_i, B_i p_j) * 2 dWV * e
+                    float c = dWV; // 2 dWV * Z / (Z + Z)
+                    fx -= c * (p_i * bje.x + p_j * bie.x);
+                    fy -= c * (p_i * bje.y + p_j * bie.y);
+                    fz -= c * (p_i * bje.z + p_j * bie.z);
+                }
+                else
+                {
+                    // AverageP (riemann_solver_ck.hpp:19-24) with Z_i == Z_j (one fluid): 2 * pave = p_i + p_j
+                    float c = (p_i + p_j) * dWV * inv_r;
+                    fx -= c * dx; fy -= c * dy; fz -= c * dz;
+                }
+                if (RIEMANN) diss += (p_i - p_j) * a.inv_Z_ave * dWV; // DissipativeUJump, :51-56
+            });
     }
     float wx = 0.f, wy = 0.f, wz = 0.f, wdiss = 0.f;
     const float vol_i = xi.w;
@@ -736,21 +790,27 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
             const float rho_i = a.rho[i];
             const float ax = Fp.x / m_i, ay = Fp.y / m_i, az = Fp.z / m_i;
             const u32 *idx = a.ct_index + (u64)a.ct_slice[t >> 5] + (t & 31u);
-#pragma unroll 4
-            for (u32 k = 0; k < cnt; ++k)
-            {
-                u32 j = idx[32ull * k];
-                float4 xj = a.w_posvol[j];
+            float4 xjs[NB_WALL_U], was[NB_WALL_U];
+            const bool has_acc = a.w_acc != nullptr;
+            for_neighbors<NB_WALL_U>(
+                idx, cnt,
+                [&](int q, u32 j) {
+                    xjs[q] = a.w_posvol[j];
+                    if (has_acc) was[q] = a.w_acc[j];
+                },
+                [&](int q, bool valid) {
+                const float4 xj = xjs[q];
                 float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
                 float r2 = dx * dx + dy * dy + dz * dz;
                 float r, inv_r;
                 dist(r2, r, inv_r);
                 float dWV = kernel_dw<ANALYTIC>(a, tab, r) * xj.w;
+                dWV = valid ? dWV : 0.f;
                 float ex = dx * inv_r, ey = dy * inv_r, ez = dz * inv_r;
                 float rx = ax, ry = ay, rz = az;
-                if (a.w_acc)
+                if (has_acc)
                 {
-                    float4 wa = a.w_acc[j];
+                    float4 wa = was[q];
                     rx -= wa.x; ry -= wa.y; rz -= wa.z;
                 }
                 float face_acc = -(rx * ex + ry * ey + rz * ez);
@@ -766,7 +826,7 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
                     wx -= c * ex; wy -= c * ey; wz -= c * ez;
                 }
                 if (RIEMANN) wdiss += (p_i - p_w) * a.inv_Z_ave * dWV;
-            }
+                });
         }
     }
     float4 F = a.force[i];
@@ -879,17 +939,17 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a2(FArgs a, KTab 
         {
             u32 cnt = a.in_count[t];
             const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
-#pragma unroll 4
-            for (u32 k = 0; k < cnt; ++k)
-            {
-                u32 j = idx[32ull * k];
-                float4 xj, vj;
-                load_rec2(a.rec2, j, xj, vj);
+            float4 xjs[NB_U], vjs[NB_U];
+            for_neighbors(
+                idx, cnt, [&](int q, u32 j) { load_rec2(a.rec2, j, xjs[q], vjs[q]); },
+                [&](int q, bool valid) {
+                const float4 xj = xjs[q], vj = vjs[q];
                 float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
                 float r2 = dx * dx + dy * dy + dz * dz;
                 float r, inv_r;
                 dist(r2, r, inv_r);
                 float dWV = kernel_dw<ANALYTIC>(a, tab, r) * xj.w;
+                dWV = valid ? dWV : 0.f;
                 float ex = dx * inv_r, ey = dy * inv_r, ez = dz * inv_r;
                 // AverageV (riemann_solver_ck.hpp:26-31) with Z_i == Z_j: 2 (v_i - v_ave) = v_i - v_j
                 float ux = vi.x - vj.x, uy = vi.y - vj.y, uz = vi.z - vj.z;
@@ -903,29 +963,35 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a2(FArgs a, KTab 
                     div += u * dWV;
                 float c = pjump<RIEMANN>(a, u) * dWV;
                 px += c * ex; py += c * ey; pz += c * ez;
-            }
+                });
         }
         float wdiv = 0.f, wx = 0.f, wy = 0.f, wz = 0.f;
         if (a.n_wall)
         {
             u32 cnt = a.ct_count[t];
             const u32 *idx = a.ct_index + (u64)a.ct_slice[t >> 5] + (t & 31u);
-#pragma unroll 4
-            for (u32 k = 0; k < cnt; ++k)
-            {
-                u32 j = idx[32ull * k];
-                float4 xj = a.w_posvol[j];
-                float4 nj = a.w_n[j];
+            float4 xjs[NB_WALL_U], njs[NB_WALL_U], wvs[NB_WALL_U];
+            const bool has_vel = a.w_vel != nullptr;
+            for_neighbors<NB_WALL_U>(
+                idx, cnt,
+                [&](int q, u32 j) {
+                    xjs[q] = a.w_posvol[j];
+                    njs[q] = a.w_n[j];
+                    if (has_vel) wvs[q] = a.w_vel[j];
+                },
+                [&](int q, bool valid) {
+                const float4 xj = xjs[q], nj = njs[q];
                 float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
                 float r2 = dx * dx + dy * dy + dz * dz;
                 float r, inv_r;
                 dist(r2, r, inv_r);
                 float dWV = kernel_dw<ANALYTIC>(a, tab, r) * xj.w;
+                dWV = valid ? dWV : 0.f;
                 float ex = dx * inv_r, ey = dy * inv_r, ez = dz * inv_r;
                 float vx = vi.x, vy = vi.y, vz = vi.z;
-                if (a.w_vel)
+                if (has_vel)
                 {
-                    float4 wv = a.w_vel[j];
+                    float4 wv = wvs[q];
                     vx -= wv.x; vy -= wv.y; vz -= wv.z;
                 }
                 vx *= 2.0f; vy *= 2.0f; vz *= 2.0f; // vel_diff = 2 (v_i - v_wall)
@@ -937,7 +1003,7 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a2(FArgs a, KTab 
                 float u = vx * nx + vy * ny + vz * nz;
                 float c = pjump<RIEMANN>(a, u) * dWV;
                 wx += c * nx; wy += c * ny; wz += c * nz;
-            }
+                });
         }
         const float vol_i = xi.w;
         float C = a.legacy ? a.rho[i] : a.C[i];

@@ -421,6 +421,83 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+
+// -----------------------------------------------------------------------------------------------------
+// L1-bank-aligned rows (sphb200_relation_t::bank_aligned). A per-lane gather of 16-byte records is served per quarter
+// warp, and its cost is the bank-conflict degree of the 8 addresses, not the number of cache lines touched (measured:
+// scripts/microbench/l1_gather.cu, profiles/r01_l1_gather_microbench.txt — 11.5 data-pipe wavefronts per warp gather for
+// random slots, 5.75 when (slot mod 8) is distinct inside every quarter warp, 5.2 fully coalesced). The rows of a slot
+// are therefore permuted so that, as far as possible, the entry s in row k of slot t satisfies (s - t - k) mod 8 == 0:
+// in row k lane l then reads a record of bank class (l + k) mod 8, distinct across the 8 lanes of a quarter warp.
+// The permutation is local: each group of 32 consecutive rows (entries in ascending order) is re-laid out on its own —
+// an entry takes the first free position of its class inside the group, the leftovers fill the remaining positions —
+// which aligns ~87 % of the entries (a global layout reaches 92 %) but needs only a 4 KB shared-memory tile per warp
+// and two coalesced passes over the slice. Entry SET and count of every row are untouched; the class depends only on
+// s - t, i.e. not on where the slab of a decomposed run starts, so summation order and every result bit are the same
+// on 1 and on N GPUs.
+// -----------------------------------------------------------------------------------------------------
+constexpr int BA_GROUP = 32, BA_WARPS = 4;
+__global__ void __launch_bounds__(32 * BA_WARPS)
+    k_bank_align(u32 *__restrict__ index, const u32 *__restrict__ count, const u32 *__restrict__ slice, u32 first_slice, u32 n_slices,
+                 u32 src_begin, u32 src_end, u32 stride)
+{
+    __shared__ u32 ba_tile[BA_WARPS][BA_GROUP][32];
+    const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+    const u32 sl = first_slice + blockIdx.x * BA_WARPS + w;
+    if (sl >= first_slice + n_slices) return;
+    u32 *tile = &ba_tile[w][0][lane]; // this lane's column: entry of position p at tile[32 p] (bank == lane: conflict free)
+    const u32 t = sl * 32u + lane;
+    const bool active = t >= src_begin && t < src_end;
+    const u32 c = active ? min(count[t], stride) : 0u;
+    const u32 cmax = warp_max_u32(c);
+    u32 *col = index + (u64)slice[sl] + lane;
+    for (u32 g = 0; g < cmax; g += BA_GROUP)
+    {
+        // rows [g, g + 32) of the warp: coalesced 128-byte loads, all independent (rows < cmax exist for every lane)
+        u32 sv[BA_GROUP];
+#pragma unroll
+        for (int u = 0; u < BA_GROUP; ++u) sv[u] = g + u < cmax ? col[32ull * (g + u)] : 0u;
+        const u32 n = c > g ? min(c - g, (u32)BA_GROUP) : 0u; // entries of this lane in the group
+        u32 used = 0, waiting = 0;                               // positions taken / entries not yet placed
+#pragma unroll
+        for (int u = 0; u < BA_GROUP; ++u)
+        {
+            if ((u32)u >= n) continue;
+            // wanted positions: p with (g + p) = (s - t) mod 8, i.e. p = ((s - t - g) mod 8) + 8 q
+            const u32 p0 = (sv[u] - t - g) & 7u;
+            const u32 free_of_class = ~used & (0x01010101u << p0) & (n >= 32u ? 0xffffffffu : (1u << n) - 1u);
+            if (free_of_class)
+            {
+                const u32 p = __ffs(free_of_class) - 1u;
+                tile[32u * p] = sv[u];
+                used |= 1u << p;
+            }
+            else
+                waiting |= 1u << u;
+        }
+#pragma unroll
+        for (int u = 0; u < BA_GROUP; ++u)
+        {
+            if (!((waiting >> u) & 1u)) continue;
+            const u32 p = __ffs(~used) - 1u; // lowest free position (< n: as many free positions as waiting entries)
+            tile[32u * p] = sv[u];
+            used |= 1u << p;
+        }
+        // every lane only touches its own column of the tile and of the slice: no warp synchronisation is needed
+#pragma unroll 8
+        for (u32 p = 0; p < n; ++p) col[32ull * (g + p)] = tile[32u * p];
+    }
+}
+
+static int bank_align(sphb200_context *ctx, const SearchArgs &a, u32 *count, u32 *slice, u32 *index, u32 stride, cudaStream_t st)
+{
+    if (a.src_end <= a.src_begin) return 0;
+    const u32 first = a.src_begin >> 5, n_slices = ((a.src_end + 31u) >> 5) - first;
+    SPH_LAUNCH(ctx, k_bank_align, sph_blocks(n_slices, BA_WARPS), 32 * BA_WARPS, 0, st, index, count, slice, first, n_slices, a.src_begin,
+               a.src_end, stride);
+    return 0;
+}
+
 static int make_search(sphb200_context *ctx, const sphb200_search_t *s, SearchArgs *a)
 {
     SPH_CHECK_ARG(ctx, s->search_depth >= 1 && s->search_depth <= 4, "search depth out of range");
@@ -557,6 +634,11 @@ extern "C" int sphb200_relation_build_fixed(sphb200_context_t *ctx, const sphb20
         if (rc) return rc;
         rc = launch_relation<2>(ctx, a, search->is_inner != 0, rel.count, rel.slice_offset, rel.index, rel.capacity, stride, dmax, st);
         if (rc) return rc;
+        if (rel.bank_aligned)
+        {
+            rc = bank_align(ctx, a, rel.count, rel.slice_offset, rel.index, stride, st);
+            if (rc) return rc;
+        }
     }
     if (max_count_host)
     {
@@ -572,6 +654,32 @@ __global__ void __launch_bounds__(256) k_counts_by_id(const u32 *__restrict__ co
 {
     u32 t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t < n) by_id[order ? order[t] : t] = count[t];
+}
+// rows of a bank-aligned relation leave in ascending target slot order (= the reference search order for cell-ordered
+// bodies): repeated minimum selection, quadratic in the row length, which is fine for an export-only path
+__global__ void __launch_bounds__(128)
+    k_export_csr_sorted(const u32 *__restrict__ count, const u32 *__restrict__ slice_offset, const u32 *__restrict__ index,
+                        const u32 *__restrict__ order, const u32 *__restrict__ tar_ids, u32 n, const u32 *__restrict__ particle_offset,
+                        u32 *__restrict__ neighbor_index)
+{
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    u32 i = order ? order[t] : t;
+    u64 src = (u64)slice_offset[t >> 5] + (t & 31u);
+    u32 dst = particle_offset[i];
+    u32 c = count[t];
+    long long last = -1;
+    for (u32 k = 0; k < c; ++k)
+    {
+        u32 best = 0xffffffffu;
+        for (u32 q = 0; q < c; ++q)
+        {
+            u32 j = index[src + 32ull * q];
+            if ((long long)j > last && j < best) best = j;
+        }
+        neighbor_index[dst + k] = tar_ids ? tar_ids[best] : best;
+        last = best;
+    }
 }
 __global__ void __launch_bounds__(128)
     k_export_csr(const u32 *__restrict__ count, const u32 *__restrict__ slice_offset, const u32 *__restrict__ index,
@@ -617,8 +725,12 @@ extern "C" int sphb200_relation_export_csr(sphb200_context_t *ctx, sphb200_relat
                  (unsigned long long)index_capacity);
         return SPHB200_E_CAPACITY;
     }
-    SPH_LAUNCH(ctx, k_export_csr, sph_blocks(n, 128), 128, 0, st, rel.count, rel.slice_offset, rel.index, order, tar_ids, n,
-               particle_offset, neighbor_index);
+    if (rel.bank_aligned)
+        SPH_LAUNCH(ctx, k_export_csr_sorted, sph_blocks(n, 128), 128, 0, st, rel.count, rel.slice_offset, rel.index, order, tar_ids, n,
+                   particle_offset, neighbor_index);
+    else
+        SPH_LAUNCH(ctx, k_export_csr, sph_blocks(n, 128), 128, 0, st, rel.count, rel.slice_offset, rel.index, order, tar_ids, n,
+                   particle_offset, neighbor_index);
     return 0;
 }
 
