@@ -232,7 +232,8 @@ def run_ours(args, rank, world, local_rank):
     roofline = {"bound": "hbm", "kernel": "k_a2 (AcousticStep2ndHalf: initialize+inner+wall+update+dt-max, one launch)",
                 "achieved": ach_a2, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach_a2 / peak,
                 "traffic": traffic, "algorithmic_bytes_per_launch": A_STEP_2ND * n_own, "launch_ms": ms_a2,
-                "note": "pair arithmetic (~80 neighbours x ~40 instr) is FP32-issue/L1 bound before it is HBM bound; see DESIGN.md §5",
+                "note": "pair arithmetic (~85 neighbours x ~50 instr, one 32-byte gather each) runs at 84 % of the L1 data-pipe and 72 % of the "
+                        "issue peak (profiles/r01_v4_ncu_full.txt): bound by L1 bank wavefronts and FP32 issue, not by HBM; see DESIGN.md §4",
                 "other_kernels_ms": {"acoustic_1st_half(init+interact)": ms_a1, "density_summation": ms_sum,
                                      "cell_list_build+reorder": ms_cl, "relation_build(inner+contact)": ms_rel}}
 
@@ -289,23 +290,65 @@ def run_ours(args, rank, world, local_rank):
                 solver.download(nm, out=host_out[nm][1])  # DiscreteVariable::synchronizeWithDevice
         return n
 
-    e2e_step()
-    barrier()
     k_e2e = max(3, min(args.steps, 10))
-    t0 = time.perf_counter()
-    n_ac_e2e = 0
-    for _ in range(k_e2e):
-        n_ac_e2e += e2e_step()
-    barrier()
-    sec = time.perf_counter() - t0
+    if decomposed:
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_ac_e2e = 0
+        for _ in range(k_e2e):
+            n_ac_e2e += e2e_step()
+        barrier()
+        sec = time.perf_counter() - t0
+        e2e_note = ("per step: H2D of all evolving variables of the rank's own particles from pinned host memory, migration + "
+                    "cell-list + relation rebuild, one outer step, D2H of Position/Velocity/Density")
+    else:
+        # single GPU: the same host buffers go through the HostTransferPipeline of the host layer — H2D of step s+1 and
+        # D2H of step s-1 run on a side stream while step s computes; every step's copies are inside the timed region
+        solver.pipeline_create(in_names, out_names)
+        ins = [host_in[nm][1] for nm in in_names]
+        outs = [host_out[nm][1] for nm in out_names]
+
+        def run_pipelined(k):
+            n_ac = 0
+            solver.pipeline_stage_uploads(ins)
+            for s_ in range(k):
+                solver.pipeline_commit_uploads()
+                if s_ + 1 < k:
+                    solver.pipeline_stage_uploads(ins)   # next step's inputs: overlaps this step's dynamics
+                solver.exec("cell_list_fluid")
+                solver.exec("relations")
+                n_ac += solver.step_outer()
+                solver.pipeline_stage_downloads(outs)    # overlaps the next step's dynamics
+            solver.pipeline_synchronize()
+            return n_ac
+
+        run_pipelined(2)
+        barrier()
+        t0 = time.perf_counter()
+        n_ac_e2e = run_pipelined(k_e2e)
+        barrier()
+        sec = time.perf_counter() - t0
+        pb_in, pb_out = solver.pipeline_bytes()
+        assert (pb_in, pb_out) == (h2d, d2h), (pb_in, h2d, pb_out, d2h)
+        # the synchronous spelling (DiscreteVariable::synchronizeToDevice / synchronizeWithDevice per variable) for comparison
+        e2e_step()
+        torch.cuda.synchronize()
+        t1 = time.perf_counter()
+        n_sync = sum(e2e_step() for _ in range(3))
+        torch.cuda.synchronize()
+        sec_sync = time.perf_counter() - t1
+        e2e_note = ("per step: H2D of all evolving variables from pinned host memory (reference particle order), cell-list + "
+                    "relation rebuild, one outer step, D2H of Position/Velocity/Density; copies run on a side stream and overlap "
+                    "the neighbouring steps' dynamics (HostTransferPipeline); synchronous per-variable spelling: "
+                    f"{n_fluid * float(n_sync) / sec_sync:.4g} particle-steps/s")
     tt = torch.tensor([sec, float(n_ac_e2e)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         sec = float(tt[0])
     tot = n_fluid * float(n_ac_e2e)
     e2e = {"value": tot / sec, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-           "steps": k_e2e, "note": "per step: H2D of all evolving variables from pinned host memory (reference particle order), "
-                                   "cell-list + relation rebuild, one outer step, D2H of Position/Velocity/Density"}
+           "steps": k_e2e, "note": e2e_note}
 
     # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample ----
     cpu = None

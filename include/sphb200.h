@@ -212,6 +212,14 @@ int sphb200_copy_h2d(void *dst, const void *src, size_t bytes, void *stream); /*
 int sphb200_copy_d2h(void *dst, const void *src, size_t bytes, void *stream); /* copyFromDevice :129-139 */
 int sphb200_copy_d2d(void *dst, const void *src, size_t bytes, void *stream);
 int sphb200_stream_sync(void *stream);
+/* transfer overlap (extension; the SYCL build has a single in-order queue): a non-blocking side stream and events, so
+ * that sphb200_copy_h2d / _d2h on pinned host memory run while dynamics execute on the main stream */
+int sphb200_stream_create(void **stream);
+int sphb200_stream_destroy(void *stream);
+int sphb200_event_create(void **event);
+int sphb200_event_destroy(void *event);
+int sphb200_event_record(void *event, void *stream);
+int sphb200_stream_wait_event(void *stream, void *event);
 int sphb200_fill_u32(sphb200_context_t *ctx, uint32_t *dst, uint32_t value, uint64_t n, void *stream);
 int sphb200_fill_f32(sphb200_context_t *ctx, float *dst, float value, uint64_t n, void *stream);
 int sphb200_iota_u32(sphb200_context_t *ctx, uint32_t *dst, uint64_t n, void *stream); /* dst[i] = i */

@@ -191,6 +191,7 @@ class BaseParticles
     size_t hostSyncCount() const { return active_begin_ == 0 && active_end_ <= total_real_particles_ ? active_end_ : total_real_particles_; }
     const std::vector<DiscreteVariableBase *> &allVariablesInOrder() const { return ordered_; }
     uint64_t storageVersion() const { return storage_version_; }
+    bool identityOrder() const { return identity_order_; }
 
     template <class T> DiscreteVariable<T> *registerStateVariable(const std::string &name, const T &init = T())
     {
@@ -371,6 +372,150 @@ class BaseParticles
         }
         (void)n_keep;
     }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// HostTransferPipeline (extension): synchronizeToDevice / synchronizeWithDevice of a fixed set of variables, split into
+// an asynchronous copy on a side stream and a device-side re-ordering step on the main stream, so that the host <->
+// device traffic of step s+1 / s-1 overlaps the dynamics of step s. Host buffers must be pinned and hold the variables
+// in the reference particle order and layout (Vecd = 3 Reals), exactly what DiscreteVariable::Data() holds.
+//   stageUploads(host...)   side stream : waits until the previous commit has consumed the staging, H2D of every input
+//   commitUploads()         main stream : waits for the H2D, Vecd 3->4 conversion + gather into the slot order
+//   stageDownloads(host...) main stream : gather into the reference order (+ 4->3), then side stream: D2H
+//   synchronize()           host waits for the side stream
+// ---------------------------------------------------------------------------------------------------------
+class HostTransferPipeline
+{
+    struct Item
+    {
+        DiscreteVariableBase *v;
+        bool is_vec;
+        size_t host_elem_bytes;
+        DeviceBuffer raw, conv;
+    };
+    BaseParticles &p_;
+    std::vector<std::unique_ptr<Item>> ins_, outs_;
+    void *copy_stream_ = nullptr, *ev_h2d_ = nullptr, *ev_commit_ = nullptr, *ev_out_ready_ = nullptr, *ev_d2h_ = nullptr;
+
+    template <class T> static Item *makeItem(DiscreteVariable<T> *v)
+    {
+        Item *it = new Item();
+        it->v = v;
+        it->is_vec = std::is_same<T, Vecd>::value;
+        it->host_elem_bytes = sizeof(T);
+        return it;
+    }
+
+  public:
+    explicit HostTransferPipeline(BaseParticles &particles) : p_(particles)
+    {
+        ExecutionInstance &ex = execution_instance();
+        ex.ctx();
+        ex.check(sphb200_stream_create(&copy_stream_), "sphb200_stream_create");
+        for (void **e : {&ev_h2d_, &ev_commit_, &ev_out_ready_, &ev_d2h_}) ex.check(sphb200_event_create(e), "sphb200_event_create");
+    }
+    HostTransferPipeline(const HostTransferPipeline &) = delete;
+    ~HostTransferPipeline()
+    {
+        for (void *e : {ev_h2d_, ev_commit_, ev_out_ready_, ev_d2h_})
+            if (e) sphb200_event_destroy(e);
+        if (copy_stream_) sphb200_stream_destroy(copy_stream_);
+    }
+    template <class T> void addInput(DiscreteVariable<T> *v) { ins_.emplace_back(makeItem(v)); }
+    template <class T> void addOutput(DiscreteVariable<T> *v) { outs_.emplace_back(makeItem(v)); }
+    size_t inputs() const { return ins_.size(); }
+    size_t outputs() const { return outs_.size(); }
+    size_t inputBytes() const
+    {
+        size_t b = 0;
+        for (auto &it : ins_) b += it->host_elem_bytes * p_.hostSyncCount();
+        return b;
+    }
+    size_t outputBytes() const
+    {
+        size_t b = 0;
+        for (auto &it : outs_) b += it->host_elem_bytes * p_.hostSyncCount();
+        return b;
+    }
+    void stageUploads(const void *const *pinned_host)
+    {
+        ExecutionInstance &ex = execution_instance();
+        const size_t n = p_.hostSyncCount();
+        ex.check(sphb200_stream_wait_event(copy_stream_, ev_commit_), "sphb200_stream_wait_event");
+        for (size_t k = 0; k < ins_.size(); ++k)
+        {
+            Item &it = *ins_[k];
+            it.raw.ensure(it.host_elem_bytes * n + 64);
+            ex.check(sphb200_copy_h2d(it.raw.get(), pinned_host[k], it.host_elem_bytes * n, copy_stream_), "sphb200_copy_h2d");
+        }
+        ex.check(sphb200_event_record(ev_h2d_, copy_stream_), "sphb200_event_record");
+    }
+    void commitUploads()
+    {
+        ExecutionInstance &ex = execution_instance();
+        void *st = ex.stream();
+        const uint32_t n = (uint32_t)p_.hostSyncCount();
+        ex.check(sphb200_stream_wait_event(st, ev_h2d_), "sphb200_stream_wait_event");
+        std::vector<void *> dst;
+        std::vector<const void *> src;
+        std::vector<uint32_t> bytes;
+        for (auto &ip : ins_)
+        {
+            Item &it = *ip;
+            const void *from = it.raw.get();
+            if (it.is_vec)
+            {
+                it.conv.ensure((size_t)16 * n + 64);
+                SPHCK_CALL(sphb200_vec3_to_vec4, (sphb200_vec4_t *)it.conv.get(), (const float *)it.raw.get(), n, st);
+                from = it.conv.get();
+            }
+            dst.push_back(it.v->deviceAddress());
+            src.push_back(from);
+            bytes.push_back(it.v->deviceElementBytes());
+        }
+        if (p_.identityOrder())
+            for (size_t k = 0; k < dst.size(); ++k) ex.check(sphb200_copy_d2d(dst[k], src[k], (size_t)bytes[k] * n, st), "sphb200_copy_d2d");
+        else if (!dst.empty())
+            SPHCK_CALL(sphb200_gather_multi, (int)dst.size(), dst.data(), src.data(), bytes.data(), p_.referenceID(), n, st);
+        ex.check(sphb200_event_record(ev_commit_, st), "sphb200_event_record");
+    }
+    void stageDownloads(void *const *pinned_host)
+    {
+        ExecutionInstance &ex = execution_instance();
+        void *st = ex.stream();
+        const uint32_t n = (uint32_t)p_.hostSyncCount();
+        ex.check(sphb200_stream_wait_event(st, ev_d2h_), "sphb200_stream_wait_event"); // the previous D2H has left the staging
+        std::vector<void *> dst;
+        std::vector<const void *> src;
+        std::vector<uint32_t> bytes;
+        for (auto &op : outs_)
+        {
+            Item &it = *op;
+            it.raw.ensure((size_t)it.v->deviceElementBytes() * n + 64);
+            dst.push_back(it.raw.get());
+            src.push_back(it.v->deviceAddress());
+            bytes.push_back(it.v->deviceElementBytes());
+        }
+        if (p_.identityOrder())
+            for (size_t k = 0; k < dst.size(); ++k) ex.check(sphb200_copy_d2d(dst[k], src[k], (size_t)bytes[k] * n, st), "sphb200_copy_d2d");
+        else if (!dst.empty())
+            SPHCK_CALL(sphb200_gather_multi, (int)dst.size(), dst.data(), src.data(), bytes.data(), p_.inverseReferenceID(), n, st);
+        for (auto &op : outs_)
+            if (op->is_vec)
+            {
+                op->conv.ensure((size_t)12 * n + 64);
+                SPHCK_CALL(sphb200_vec4_to_vec3, (float *)op->conv.get(), (const sphb200_vec4_t *)op->raw.get(), n, st);
+            }
+        ex.check(sphb200_event_record(ev_out_ready_, st), "sphb200_event_record");
+        ex.check(sphb200_stream_wait_event(copy_stream_, ev_out_ready_), "sphb200_stream_wait_event");
+        for (size_t k = 0; k < outs_.size(); ++k)
+        {
+            Item &it = *outs_[k];
+            ex.check(sphb200_copy_d2h(pinned_host[k], it.is_vec ? it.conv.get() : it.raw.get(), it.host_elem_bytes * n, copy_stream_), "sphb200_copy_d2h");
+        }
+        ex.check(sphb200_event_record(ev_d2h_, copy_stream_), "sphb200_event_record");
+    }
+    void synchronize() { execution_instance().check(sphb200_stream_sync(copy_stream_), "sphb200_stream_sync"); }
 };
 
 template <class T> void DiscreteVariable<T>::synchronizeToDevice() { particles_->upload(this, Data()); }

@@ -13,7 +13,7 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread', 'smsp__inst_executed.sum',
         'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum',
         'l1tex__t_sector_hit_rate.pct', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
-        'l1tex__data_pipe_lsu_wavefronts.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts.avg', 'sm__cycles_elapsed.avg', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
         'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_lg_throttle_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio',
@@ -35,6 +35,9 @@ for r in rows[2:]:
 open(dst + '_ncu_full.txt', 'w').write('\n'.join(out) + '\n')
 print('\n'.join(out))
 
+import os
+if not os.path.exists(f'{src}/launches.csv'):
+    sys.exit(0)
 rows = list(csv.reader(open(f'{src}/launches.csv')))
 h = next(i for i, r in enumerate(rows) if 'Kernel Name' in r)
 hdr = rows[h]

@@ -127,6 +127,12 @@ SYMBOLS = {
     "sphb200_acoustic_1st_half_initialize": (_I, [_CTX, C.POINTER(FluidArgs), _F, _P]),
     "sphb200_acoustic_1st_half_interact": (_I, [_CTX, C.POINTER(FluidArgs), _F, _I, _P]),
     "sphb200_linear_correction_matrix": (_I, [_CTX, C.POINTER(FluidArgs), _F, _P]),
+    "sphb200_stream_create": (_I, [C.POINTER(_P)]),
+    "sphb200_stream_destroy": (_I, [_P]),
+    "sphb200_event_create": (_I, [C.POINTER(_P)]),
+    "sphb200_event_destroy": (_I, [_P]),
+    "sphb200_event_record": (_I, [_P, _P]),
+    "sphb200_stream_wait_event": (_I, [_P, _P]),
     "sphb200_free_surface_indication": (_I, [_CTX, C.POINTER(FluidArgs), _P, _P, _P, _F, _F, _P]),
     "sphb200_interpolate": (_I, [_CTX, C.POINTER(KernelT), _P, C.c_uint32, RelationT, _P, _P, _I, _P, _P]),
     "sphb200_comm_unique_id": (_I, [_P]),

@@ -18,6 +18,7 @@ struct Handle
 {
     std::unique_ptr<DamBreakCK> sim;   // dam break (CK or legacy spelling) ...
     std::unique_ptr<TaylorGreenCK> tg; // ... or the periodic Taylor-Green vortex
+    std::unique_ptr<HostTransferPipeline> pipeline; // overlapped host <-> device transfers of the fluid body (bench e2e)
     SPHBody &body(int which)
     {
         if (tg)
@@ -408,6 +409,62 @@ extern "C"
             else out = p.deviceData<Matd>(name);
         });
         return out;
+    }
+
+    // ---- overlapped transfers (HostTransferPipeline of the fluid body); names are separated by ',' ----
+    int sphck_pipeline_create(void *hp, const char *inputs, const char *outputs)
+    {
+        return guarded([&] {
+            Handle *h = (Handle *)hp;
+            BaseParticles &p = h->body(0).getBaseParticles();
+            h->pipeline.reset(new HostTransferPipeline(p));
+            auto add = [&](const char *list, bool input) {
+                std::string s(list ? list : ""), name;
+                size_t pos = 0;
+                while (pos <= s.size())
+                {
+                    size_t e = s.find(',', pos);
+                    if (e == std::string::npos) e = s.size();
+                    name = s.substr(pos, e - pos);
+                    pos = e + 1;
+                    if (name.empty()) continue;
+                    DiscreteVariableBase *v = p.findVariable(name);
+                    if (auto *r = dynamic_cast<DiscreteVariable<Real> *>(v)) input ? h->pipeline->addInput(r) : h->pipeline->addOutput(r);
+                    else if (auto *q = dynamic_cast<DiscreteVariable<Vecd> *>(v)) input ? h->pipeline->addInput(q) : h->pipeline->addOutput(q);
+                    else throw SphError("pipeline: only Real and Vecd variables are supported: " + name);
+                }
+            };
+            add(inputs, true);
+            add(outputs, false);
+        });
+    }
+    int sphck_pipeline_stage_uploads(void *hp, const void *const *pinned_host)
+    {
+        return guarded([&] { ((Handle *)hp)->pipeline->stageUploads(pinned_host); });
+    }
+    int sphck_pipeline_commit_uploads(void *hp)
+    {
+        return guarded([&] {
+            Handle *h = (Handle *)hp;
+            h->pipeline->commitUploads();
+            h->body(0).setPosVolDirty();
+            h->acousticTimeStep()->setPrimed(false);
+        });
+    }
+    int sphck_pipeline_stage_downloads(void *hp, void *const *pinned_host)
+    {
+        return guarded([&] { ((Handle *)hp)->pipeline->stageDownloads(pinned_host); });
+    }
+    int sphck_pipeline_synchronize(void *hp)
+    {
+        return guarded([&] { ((Handle *)hp)->pipeline->synchronize(); });
+    }
+    int sphck_pipeline_bytes(void *hp, uint64_t *in_bytes, uint64_t *out_bytes)
+    {
+        return guarded([&] {
+            *in_bytes = ((Handle *)hp)->pipeline->inputBytes();
+            *out_bytes = ((Handle *)hp)->pipeline->outputBytes();
+        });
     }
 
     // recorded probe rows (ObservedQuantityRecording::records()): times[rows], values[rows * probes]

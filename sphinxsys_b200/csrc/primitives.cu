@@ -65,6 +65,26 @@ extern "C" int sphb200_copy_d2d(void *dst, const void *src, size_t bytes, void *
     return (int)cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, (cudaStream_t)stream);
 }
 extern "C" int sphb200_stream_sync(void *stream) { return (int)cudaStreamSynchronize((cudaStream_t)stream); }
+// a second, non-blocking stream and events: host <-> device transfers that overlap the dynamics running on the
+// caller's main stream (the SYCL build has one in-order queue; overlap is an extension of this library)
+extern "C" int sphb200_stream_create(void **stream)
+{
+    cudaStream_t s = nullptr;
+    cudaError_t e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    *stream = (void *)s;
+    return (int)e;
+}
+extern "C" int sphb200_stream_destroy(void *stream) { return (int)cudaStreamDestroy((cudaStream_t)stream); }
+extern "C" int sphb200_event_create(void **event)
+{
+    cudaEvent_t ev = nullptr;
+    cudaError_t e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    *event = (void *)ev;
+    return (int)e;
+}
+extern "C" int sphb200_event_destroy(void *event) { return (int)cudaEventDestroy((cudaEvent_t)event); }
+extern "C" int sphb200_event_record(void *event, void *stream) { return (int)cudaEventRecord((cudaEvent_t)event, (cudaStream_t)stream); }
+extern "C" int sphb200_stream_wait_event(void *stream, void *event) { return (int)cudaStreamWaitEvent((cudaStream_t)stream, (cudaEvent_t)event, 0); }
 
 // =====================================================================================================
 // fills, layout conversion

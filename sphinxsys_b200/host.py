@@ -79,6 +79,12 @@ def load():
         L.sphck_plan_slab_cuts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
         L.sphck_export_csr.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.sphck_probe_records.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.sphck_pipeline_create.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
+        L.sphck_pipeline_stage_uploads.argtypes = [C.c_void_p, C.c_void_p]
+        L.sphck_pipeline_commit_uploads.argtypes = [C.c_void_p]
+        L.sphck_pipeline_stage_downloads.argtypes = [C.c_void_p, C.c_void_p]
+        L.sphck_pipeline_synchronize.argtypes = [C.c_void_p]
+        L.sphck_pipeline_bytes.argtypes = [C.c_void_p, C.POINTER(C.c_uint64), C.POINTER(C.c_uint64)]
         _lib = L
     return _lib
 
@@ -252,6 +258,30 @@ class DamBreakCK:
         if rows:
             self._check(self.lib.sphck_probe_records(self._h, t.ctypes.data, v.ctypes.data, rows), "probe_records")
         return t, v[:, :probes]
+
+    # ---- overlapped host <-> device transfers (HostTransferPipeline; host arrays must be pinned, reference order) ----
+    def pipeline_create(self, inputs, outputs):
+        self._check(self.lib.sphck_pipeline_create(self._h, ",".join(inputs).encode(), ",".join(outputs).encode()), "pipeline_create")
+        self._pipe_in, self._pipe_out = list(inputs), list(outputs)
+
+    def pipeline_stage_uploads(self, arrays):
+        ptrs = (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+        self._check(self.lib.sphck_pipeline_stage_uploads(self._h, ptrs), "pipeline_stage_uploads")
+
+    def pipeline_commit_uploads(self):
+        self._check(self.lib.sphck_pipeline_commit_uploads(self._h), "pipeline_commit_uploads")
+
+    def pipeline_stage_downloads(self, arrays):
+        ptrs = (C.c_void_p * len(arrays))(*[a.ctypes.data for a in arrays])
+        self._check(self.lib.sphck_pipeline_stage_downloads(self._h, ptrs), "pipeline_stage_downloads")
+
+    def pipeline_synchronize(self):
+        self._check(self.lib.sphck_pipeline_synchronize(self._h), "pipeline_synchronize")
+
+    def pipeline_bytes(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.sphck_pipeline_bytes(self._h, C.byref(a), C.byref(b)), "pipeline_bytes")
+        return int(a.value), int(b.value)
 
     def cuts(self) -> np.ndarray:
         out = np.zeros(self.nranks + 1, dtype=np.int32)

@@ -710,3 +710,54 @@ def test_full_3d_dambreak_ck_energy_series_meets_reference_dtw():
                                   "threshold": ref["dtw_threshold"], "series": series})
     assert abs(series[0] - 0.5) < 1e-5
     assert max(d) <= ref["dtw_threshold"], f"DTW {d} > {ref['dtw_threshold']}"
+
+
+def test_host_transfer_pipeline_equals_synchronous_transfers():
+    """HostTransferPipeline (H2D / D2H on a side stream, overlapping the neighbouring steps) against the synchronous
+    DiscreteVariable::synchronizeToDevice / synchronizeWithDevice spelling: two identical cases driven through the same
+    4 end-to-end steps from the same pinned host inputs must produce bit-identical outputs, step by step."""
+    from sphinxsys_b200 import cases
+    from sphinxsys_b200.host import VEC_NAMES
+    case = cases.dam_break(dim=3, dp=0.05)
+    in_names = ["Position", "VolumetricMeasure", "Velocity", "Mass", "ForcePrior", "Compression", "CompressionRate",
+                "VolumetricMeasureRef", "PreviousGravityForceCK"]
+    out_names = ["Position", "Velocity", "Density"]
+    a, b = make_gpu(case, sort_interval=2), make_gpu(case, sort_interval=2)
+    for g in (a, b):
+        g.initialize()
+        g.run_outer(3)
+    n = a.n_fluid
+
+    def pinned(name):
+        t = torch.empty((n, 3) if name in VEC_NAMES else (n,), dtype=torch.float32).pin_memory()
+        return t, t.numpy()
+    host_in = {nm: pinned(nm) for nm in in_names}
+    for nm in in_names:
+        a.download(nm, out=host_in[nm][1])
+        assert np.array_equal(host_in[nm][1], b.download(nm))
+    steps = 4
+    sync_out = []
+    for _ in range(steps):
+        for nm in in_names:
+            a.upload(nm, host_in[nm][1])
+        a.exec("cell_list_fluid")
+        a.exec("relations")
+        a.step_outer()
+        sync_out.append({nm: a.download(nm).copy() for nm in out_names})
+    b.pipeline_create(in_names, out_names)
+    outs = [[pinned(nm) for nm in out_names] for _ in range(steps)]  # one output set per step: nothing is overwritten
+    ins = [host_in[nm][1] for nm in in_names]
+    b.pipeline_stage_uploads(ins)
+    for s in range(steps):
+        b.pipeline_commit_uploads()
+        if s + 1 < steps:
+            b.pipeline_stage_uploads(ins)
+        b.exec("cell_list_fluid")
+        b.exec("relations")
+        b.step_outer()
+        b.pipeline_stage_downloads([o[1] for o in outs[s]])
+    b.pipeline_synchronize()
+    assert b.pipeline_bytes() == (sum(host_in[nm][1].nbytes for nm in in_names), sum(o[1].nbytes for o in outs[0]))
+    for s in range(steps):
+        for k, nm in enumerate(out_names):
+            assert np.array_equal(outs[s][k][1], sync_out[s][nm]), (s, nm)
