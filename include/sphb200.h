@@ -377,6 +377,22 @@ int sphb200_free_surface_indication(sphb200_context_t *ctx, const sphb200_fluid_
 int sphb200_interpolate(sphb200_context_t *ctx, const sphb200_kernel_t *kernel, const sphb200_vec4_t *src_pos, uint32_t n_src,
                         sphb200_relation_t rel, const sphb200_vec4_t *tar_posvol, const float *tar_data, int width, float *out,
                         void *stream);
+/* InteractionDynamicsCK<ViscousForceCK<Inner<WithUpdate, Viscosity, Correction>, Contact<Wall, Viscosity, Correction>>>::exec:
+ * inner interact -> wall interact -> ForcePriorCK update (ForcePrior += F - Previous; Previous = F), one launch.
+ * Needs fluid.posvolvel (the 32-byte gather record) and fluid.force_prior; material.correction selects the B-matrix form.
+ * ref: fluid_dynamics/viscous_force.hpp:44-103, general_dynamics/force_prior_ck.h:53-57, materials/viscosity.h:40-67 */
+int sphb200_viscous_force(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, float mu, float smoothing_length,
+                          sphb200_vec4_t *viscous_force, sphb200_vec4_t *previous_viscous_force, void *stream);
+/* KernelGradientIntegral<Inner<Correction>, Contact<Boundary, Correction>>: kgi_i = -sum (B_i + B_j) dW V_j e_ij
+ * - sum_wall 2 B_i dW V_j e_ij; ref: general_dynamics/kernel_gradient_integral.hpp:33-78 */
+int sphb200_kernel_gradient_integral(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, sphb200_vec4_t *kernel_gradient_integral,
+                                     void *stream);
+/* StateDynamics<TransportVelocityCorrectionCK<SPHBody, Limiter, Scopes...>>: dpos_i += coefficient h^2 limiter(h^2 |kgi|^2) kgi_i.
+ * limiter 0 NoLimiter, 1 TruncatedLinear(slope); indicator != NULL restricts the update to BulkParticles (Indicator == 0).
+ * ref: fluid_dynamics/transport_velocity_correction_ck.hpp:39-50, common/common_functors.h:69-94 */
+int sphb200_transport_velocity_correction(sphb200_context_t *ctx, const sphb200_fluid_view_t *fluid,
+                                          const sphb200_vec4_t *kernel_gradient_integral, float coefficient, float h_ref, int limiter,
+                                          float limiter_slope, const int32_t *indicator, void *stream);
 /* ReduceDynamicsCK<TotalMechanicalEnergyCK>; ref: general_dynamics/general_reduce_ck.h:52-88 */
 int sphb200_total_mechanical_energy(sphb200_context_t *ctx, const sphb200_fluid_view_t *fluid, const float gravity[3],
                                     double *energy_host, void *stream);

@@ -22,6 +22,9 @@ struct DamBreakParameters
     bool correction = false;   // LinearCorrectionCK variants (the reference case file uses them; the hot path is without)
     bool surface_indicator = false; // FreeSurfaceIndicationComplexSpatialTemporalCK in the loop (dambreak.cpp:133-134,192)
     bool observers = false;         // FluidObserver pressure probes of the case file (dambreak.cpp:54-65,87-88,140-141,223-224)
+    double mu_f = 0.0;              // > 0: Viscosity closure + ViscousForceWithWallCK after the advection set-up
+    bool transport_velocity = false; // KernelGradientIntegral(Corrected)Complex + TransportVelocityCorrectionCK<SPHBody, TruncatedLinear>
+                                     // (lid_driven_cavity_sycl.cpp:208-214,268-276)
     bool fused_time_step = true;
     bool fused_regularization = true;
     int sort_interval = 100;   // :217-220
@@ -80,6 +83,8 @@ class DamBreakCK
     std::unique_ptr<StateDynamics<P, fluid_dynamics::UpdateParticlePosition>> water_update_particle_position;
     std::unique_ptr<InteractionDynamicsCK<P, LinearCorrectionMatrixComplex>> fluid_linear_correction_matrix;
     std::unique_ptr<InteractionDynamicsCK<P, fluid_dynamics::FreeSurfaceIndicationComplexSpatialTemporalCK>> fluid_boundary_indicator;
+    std::unique_ptr<InteractionDynamicsBase> fluid_viscous_force, kernel_gradient_integral;
+    std::unique_ptr<StateDynamics<P, fluid_dynamics::TransportVelocityCorrectionCK<SPHBody, TruncatedLinear>>> transport_correction;
     std::unique_ptr<ObserverBody> fluid_observer;
     std::unique_ptr<Contact<>> fluid_observer_contact;
     std::unique_ptr<UpdateRelation<P, Contact<>>> fluid_observer_contact_relation;
@@ -145,7 +150,8 @@ class DamBreakCK
             sph_system.setSystemDomainBoundsExact(exact_system_bounds ? *exact_system_bounds : sb);
         }
         Real vol = Real(std::pow(Real(q.dp), Real(q.dim)));
-        water_block.defineMatterMaterial<WeaklyCompressibleFluid>(Real(q.rho0_f), c_f_);
+        if (q.mu_f > 0) water_block.defineClosure<WeaklyCompressibleFluid, Viscosity>(Real(q.rho0_f), c_f_, Real(q.mu_f));
+        else water_block.defineMatterMaterial<WeaklyCompressibleFluid>(Real(q.rho0_f), c_f_);
         std::vector<int> cuts;
         if (q.nranks > 1)
         {
@@ -245,6 +251,25 @@ class DamBreakCK
             fluid_advection_time_step = adv;
             advection_reduced_value = [adv]() { return adv->ReducedValue(); };
             cuts_adv_ = adv; // gets the decomposition below, once it exists
+            if (q.mu_f > 0 || q.transport_velocity)
+            {
+                if (q.nranks > 1) throw SphError("slab decomposition: viscous force / transport velocity are not decomposed yet");
+                if (q.mu_f > 0)
+                {
+                    if (q.correction)
+                        fluid_viscous_force.reset(new InteractionDynamicsCK<P, ViscousForceCK<Inner<WithUpdate, Viscosity, LinearCorrectionCK>, Contact<Wall, Viscosity, LinearCorrectionCK>>>(*water_block_inner, *water_wall_contact));
+                    else
+                        fluid_viscous_force.reset(new InteractionDynamicsCK<P, ViscousForceWithWallCK>(*water_block_inner, *water_wall_contact));
+                }
+                if (q.transport_velocity)
+                {
+                    if (q.correction)
+                        kernel_gradient_integral.reset(new InteractionDynamicsCK<P, KernelGradientIntegralCorrectedComplex>(*water_block_inner, *water_wall_contact));
+                    else
+                        kernel_gradient_integral.reset(new InteractionDynamicsCK<P, KernelGradientIntegralComplex>(*water_block_inner, *water_wall_contact));
+                    transport_correction.reset(new StateDynamics<P, TransportVelocityCorrectionCK<SPHBody, TruncatedLinear>>(water_block));
+                }
+            }
             if (q.surface_indicator)
             {
                 if (q.nranks > 1) throw SphError("slab decomposition: FreeSurfaceIndicationCK is not decomposed yet");
@@ -332,6 +357,12 @@ class DamBreakCK
         if (!q_.fused_regularization) fluid_density_regularization->exec();
         water_advection_step_setup->exec();
         if (decomposition) decomposition->refreshGhosts({"VolumetricMeasure"}); // neighbours read V_j of ghost particles
+        if (fluid_viscous_force) fluid_viscous_force->exec(); // lid_driven_cavity_sycl.cpp:268-276
+        if (kernel_gradient_integral)
+        {
+            kernel_gradient_integral->exec();
+            transport_correction->exec();
+        }
         Real advection_dt = fluid_advection_time_step->exec();
         if (fluid_boundary_indicator) fluid_boundary_indicator->exec();
         if (q_.correction) fluid_linear_correction_matrix->exec();

@@ -33,6 +33,11 @@ struct OneLevel {};
 struct Wall {};
 struct FreeSurface {};
 struct Internal {};
+struct Boundary {};
+struct BulkParticles {};
+// limiters, common/common_functors.h:69-94
+struct NoLimiter { static constexpr int kind = 0; static constexpr float slope = 0.f; };
+struct TruncatedLinear { static constexpr int kind = 1; static constexpr float slope = 100.f; };
 struct NoKernelCorrectionCK { static constexpr int kind = 0; };
 struct LinearCorrectionCK { static constexpr int kind = 1; };
 namespace fluid_dynamics
@@ -590,6 +595,76 @@ template <> class FreeSurfaceIndicationCK<Inner<WithUpdate>, Contact<>> : public
     }
 };
 using FreeSurfaceIndicationComplexSpatialTemporalCK = FreeSurfaceIndicationCK<Inner<WithUpdate>, Contact<>>;
+// ---- viscous force (fluid_dynamics/viscous_force.h:40-131) ----
+// InteractionDynamicsCK<P, ViscousForceCK<Inner<WithUpdate, Viscosity, Correction>[, Contact<Wall, Viscosity, Correction>]>>:
+// inner interact -> wall interact -> ForcePriorCK update ("ViscousForce" enters ForcePrior as a difference to its previous value)
+template <typename... RelationTypes> class ViscousForceCK;
+class ViscousForceBase : public FluidDynamicsBase
+{
+  protected:
+    Real mu_, smoothing_length_;
+    ViscousForceBase(Inner<> &inner, Contact<> *contact, int correction) : FluidDynamicsBase(inner, contact)
+    {
+        correction_ = correction;
+        auto *visc = dynamic_cast<Viscosity *>(&inner.source_.getBaseMaterial());
+        if (!visc) throw SphError("ViscousForceCK: the fluid material carries no Viscosity (use defineClosure<WeaklyCompressibleFluid, Viscosity>)");
+        mu_ = visc->ReferenceViscosity();
+        smoothing_length_ = inner.source_.getSPHAdaptation().ReferenceSmoothingLength();
+        particles_.registerStateVariable<Vecd>("Velocity");
+        particles_.registerStateVariable<Vecd>("ViscousForce");
+        particles_.registerStateVariable<Vecd>("PreviousViscousForce"); // ForcePriorCK, force_prior_ck.cpp:13-14
+        particles_.registerStateVariable<Vecd>("ForcePrior");
+        particles_.addEvolvingVariable<Vecd>("ForcePrior");
+        particles_.addEvolvingVariable<Vecd>("PreviousViscousForce");
+        if (correction) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity());
+    }
+
+  public:
+    std::vector<BaseDynamics<void> *> deviceInteract(Real, const std::vector<BaseDynamics<void> *> &post)
+    {
+        sphb200_fluid_args_t a = fluidArgs();
+        SPHCK_CALL(sphb200_viscous_force, &a, mu_, smoothing_length_, (sphb200_vec4_t *)particles_.deviceData<Vecd>("ViscousForce"),
+                   (sphb200_vec4_t *)particles_.deviceData<Vecd>("PreviousViscousForce"), execution_instance().stream());
+        return post;
+    }
+};
+template <class CorrectionType> class ViscousForceCK<Inner<WithUpdate, Viscosity, CorrectionType>> : public ViscousForceBase
+{
+  public:
+    explicit ViscousForceCK(Inner<> &inner) : ViscousForceBase(inner, nullptr, CorrectionType::kind) {}
+};
+template <class CorrectionType>
+class ViscousForceCK<Inner<WithUpdate, Viscosity, CorrectionType>, Contact<Wall, Viscosity, CorrectionType>> : public ViscousForceBase
+{
+  public:
+    ViscousForceCK(Inner<> &inner, Contact<> &contact) : ViscousForceBase(inner, &contact, CorrectionType::kind) {}
+};
+using ViscousForceInnerCK = ViscousForceCK<Inner<WithUpdate, Viscosity, NoKernelCorrectionCK>>;
+using ViscousForceWithWallCK = ViscousForceCK<Inner<WithUpdate, Viscosity, NoKernelCorrectionCK>, Contact<Wall, Viscosity, NoKernelCorrectionCK>>;
+
+// ---- transport velocity correction (fluid_dynamics/transport_velocity_correction_ck.h:12-44) ----
+// StateDynamics<P, TransportVelocityCorrectionCK<SPHBody, LimiterType[, BulkParticles]>>(body[, coefficient = 0.2])
+template <class DynamicsIdentifier, class LimiterType, typename... ParticleScopes> class TransportVelocityCorrectionCK : public FluidDynamicsBase
+{
+    Real h_ref_, coefficient_;
+    static constexpr bool bulk_only_ = (std::is_same<ParticleScopes, BulkParticles>::value || ... || false);
+
+  public:
+    explicit TransportVelocityCorrectionCK(SPHBody &body, Real coefficient = Real(0.2))
+        : FluidDynamicsBase(body), h_ref_(body.getSPHAdaptation().ReferenceSmoothingLength()), coefficient_(coefficient)
+    {
+        particles_.getVariableByName<Vecd>("Displacement");
+        particles_.getVariableByName<Vecd>("KernelGradientIntegral");
+        if (bulk_only_) particles_.getVariableByName<int>("Indicator");
+    }
+    void deviceUpdate(Real)
+    {
+        sphb200_fluid_view_t f = fluidView();
+        SPHCK_CALL(sphb200_transport_velocity_correction, &f, (const sphb200_vec4_t *)particles_.deviceData<Vecd>("KernelGradientIntegral"),
+                   coefficient_, h_ref_, LimiterType::kind, LimiterType::slope,
+                   bulk_only_ ? (const int32_t *)particles_.deviceData<int>("Indicator") : nullptr, execution_instance().stream());
+    }
+};
 } // namespace fluid_dynamics
 
 // ---- general dynamics ----
@@ -638,6 +713,42 @@ class LinearCorrectionMatrixComplex : public fluid_dynamics::FluidDynamicsBase
         return post;
     }
 };
+
+// ---- kernel gradient integral (general_dynamics/kernel_gradient_integral.h:36-114) ----
+template <typename... RelationTypes> class KernelGradientIntegral;
+class KernelGradientIntegralBase : public fluid_dynamics::FluidDynamicsBase
+{
+  protected:
+    KernelGradientIntegralBase(Inner<> &inner, Contact<> *contact, int correction) : FluidDynamicsBase(inner, contact)
+    {
+        correction_ = correction;
+        particles_.registerStateVariable<Vecd>("KernelGradientIntegral");
+        if (correction) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity());
+    }
+
+  public:
+    std::vector<BaseDynamics<void> *> deviceInteract(Real, const std::vector<BaseDynamics<void> *> &post)
+    {
+        sphb200_fluid_args_t a = fluidArgs();
+        SPHCK_CALL(sphb200_kernel_gradient_integral, &a, (sphb200_vec4_t *)particles_.deviceData<Vecd>("KernelGradientIntegral"),
+                   execution_instance().stream());
+        return post;
+    }
+};
+template <class CorrectionType> class KernelGradientIntegral<Inner<CorrectionType>> : public KernelGradientIntegralBase
+{
+  public:
+    explicit KernelGradientIntegral(Inner<> &inner) : KernelGradientIntegralBase(inner, nullptr, CorrectionType::kind) {}
+};
+template <class CorrectionType>
+class KernelGradientIntegral<Inner<CorrectionType>, Contact<Boundary, CorrectionType>> : public KernelGradientIntegralBase
+{
+  public:
+    KernelGradientIntegral(Inner<> &inner, Contact<> &contact) : KernelGradientIntegralBase(inner, &contact, CorrectionType::kind) {}
+};
+using KernelGradientIntegralInner = KernelGradientIntegral<Inner<NoKernelCorrectionCK>>;
+using KernelGradientIntegralComplex = KernelGradientIntegral<Inner<NoKernelCorrectionCK>, Contact<Boundary, NoKernelCorrectionCK>>;
+using KernelGradientIntegralCorrectedComplex = KernelGradientIntegral<Inner<LinearCorrectionCK>, Contact<Boundary, LinearCorrectionCK>>;
 
 class TotalMechanicalEnergyCK : public fluid_dynamics::FluidDynamicsBase
 {

@@ -538,6 +538,21 @@ class WeaklyCompressibleFluid : public BaseMaterial
     Real ReferenceDensity() const override { return rho0_; }
     Real ReferenceSoundSpeed() const { return c0_; }
 };
+// Viscosity (materials/viscosity.h:40-67): reference viscosity mu; a fluid body carries it through
+// defineClosure<WeaklyCompressibleFluid, Viscosity>(rho0, c0, mu) (base_body.h defineClosure, closure.h)
+class Viscosity
+{
+    Real mu_;
+
+  public:
+    explicit Viscosity(Real mu) : mu_(mu) {}
+    Real ReferenceViscosity() const { return mu_; }
+};
+template <class MaterialType, class ViscosityType> class Closure : public MaterialType, public ViscosityType
+{
+  public:
+    template <class A, class B, class C> Closure(A rho0, B c0, C mu) : MaterialType(Real(rho0), Real(c0)), ViscosityType(Real(mu)) {}
+};
 class Solid : public BaseMaterial
 {
   public:
@@ -634,6 +649,13 @@ class SPHBody
     template <class MaterialType, typename... Args> MaterialType *defineMatterMaterial(Args &&...args)
     {
         MaterialType *m = new MaterialType(std::forward<Args>(args)...);
+        material_.reset(m);
+        return m;
+    }
+    // defineClosure<WeaklyCompressibleFluid, Viscosity>(rho0, c0, mu): the fluid material with its viscosity model
+    template <class MaterialType, class ViscosityType, typename... Args> Closure<MaterialType, ViscosityType> *defineClosure(Args &&...args)
+    {
+        auto *m = new Closure<MaterialType, ViscosityType>(std::forward<Args>(args)...);
         material_.reset(m);
         return m;
     }

@@ -27,6 +27,8 @@ struct TaylorGreenParameters
     int sort_interval = 100;
     bool fused_time_step = true;
     bool fused_regularization = true;
+    double mu_f = 0.0;               // > 0: Viscosity closure + ViscousForceInnerCK in the loop (taylor_green.cpp:21-22,108: rho0 U L / Re)
+    bool transport_velocity = false; // KernelGradientIntegralInner + TransportVelocityCorrectionCK<SPHBody, TruncatedLinear> (:109)
 };
 
 class TaylorGreenWaterBlock : public ComplexShape
@@ -63,6 +65,9 @@ class TaylorGreenCK
     std::unique_ptr<ReduceDynamicsCK<P, fluid_dynamics::AcousticTimeStepCK<WeaklyCompressibleFluid>>> fluid_acoustic_time_step;
     std::vector<std::unique_ptr<PeriodicConditionUsingGhostParticles>> periodic_condition; // x, y(, z)
     std::unique_ptr<GhostUpdate> volume_ghost_update, pressure_ghost_update, velocity_ghost_update;
+    std::unique_ptr<InteractionDynamicsCK<P, fluid_dynamics::ViscousForceInnerCK>> viscous_force;
+    std::unique_ptr<InteractionDynamicsCK<P, KernelGradientIntegralInner>> kernel_gradient_integral;
+    std::unique_ptr<StateDynamics<P, fluid_dynamics::TransportVelocityCorrectionCK<SPHBody, TruncatedLinear>>> transport_velocity_correction;
     Gravity no_gravity;
     std::unique_ptr<ReduceDynamicsCK<P, TotalMechanicalEnergyCK>> record_total_kinetic_energy; // zero gravity: kinetic part only
     SingleVariable<Real> *sv_physical_time = nullptr;
@@ -93,7 +98,8 @@ class TaylorGreenCK
     {
         using namespace fluid_dynamics;
         if (exact_system_bounds) sph_system.setSystemDomainBoundsExact(*exact_system_bounds);
-        water_block.defineMatterMaterial<WeaklyCompressibleFluid>(Real(q.rho0_f), c_f_);
+        if (q.mu_f > 0) water_block.defineClosure<WeaklyCompressibleFluid, Viscosity>(Real(q.rho0_f), c_f_, Real(q.mu_f));
+        else water_block.defineMatterMaterial<WeaklyCompressibleFluid>(Real(q.rho0_f), c_f_);
         BoundingBoxd box = water_block.getSPHBodyBounds();
         for (int a = 0; a < q.dim; ++a) ghost_along_axis.emplace_back(new Ghost<PeriodicAlongAxis>(box, a));
         if (q.dim == 3) water_block.reserveFor(*ghost_along_axis[0], *ghost_along_axis[1], *ghost_along_axis[2]);
@@ -124,6 +130,12 @@ class TaylorGreenCK
         velocity_ghost_update.reset(new GhostUpdate(images, {"PosVolVel"}));
         fluid_acoustic_step_1st_half->addPreContactInteraction(*pressure_ghost_update);
         fluid_acoustic_step_2nd_half->addPreContactInteraction(*velocity_ghost_update);
+        if (q.mu_f > 0) viscous_force.reset(new InteractionDynamicsCK<P, ViscousForceInnerCK>(*water_block_inner));
+        if (q.transport_velocity)
+        {
+            kernel_gradient_integral.reset(new InteractionDynamicsCK<P, KernelGradientIntegralInner>(*water_block_inner));
+            transport_velocity_correction.reset(new StateDynamics<P, TransportVelocityCorrectionCK<SPHBody, TruncatedLinear>>(water_block));
+        }
         record_total_kinetic_energy.reset(new ReduceDynamicsCK<P, TotalMechanicalEnergyCK>(water_block, no_gravity));
         sv_physical_time = sph_system.getSystemVariableByName<Real>("PhysicalTime");
 
@@ -167,6 +179,13 @@ class TaylorGreenCK
         if (!q_.fused_regularization) fluid_density_regularization->exec();
         water_advection_step_setup->exec();
         volume_ghost_update->exec(); // neighbours read V_j of the images
+        // viscous force, kernel gradient integral, transport correction: order of lid_driven_cavity_sycl.cpp:268-276
+        if (viscous_force) viscous_force->exec();
+        if (kernel_gradient_integral)
+        {
+            kernel_gradient_integral->exec();
+            transport_velocity_correction->exec();
+        }
         Real advection_dt = fluid_advection_time_step->exec();
         Real relaxation_time = 0, acoustic_dt = 0;
         int n_inner = 0;

@@ -38,7 +38,8 @@ class ParamsPOD(C.Structure):
                 ("correction_alpha", C.c_double), ("sigma0", C.c_double), ("wall_rho0", C.c_double),
                 ("contact_depth", C.c_int), ("threads", C.c_int), ("periodic_axes", C.c_int),
                 ("periodic_lower", C.c_double * 3), ("periodic_upper", C.c_double * 3), ("periodic_cutoff", C.c_double),
-                ("surface_indicator", C.c_int)]
+                ("surface_indicator", C.c_int), ("viscosity", C.c_double), ("transport_velocity", C.c_int),
+                ("transport_coefficient", C.c_double)]
 
 
 _lib = None
@@ -126,7 +127,7 @@ class OracleSim:
     """One fluid body + one wall body + inner/contact relations, advanced by the oracle."""
 
     def __init__(self, case, f64=False, riemann=1, correction=0, free_surface=1, threads=0, contact_depth=1,
-                 surface_indicator=0, observers=None):
+                 surface_indicator=0, observers=None, viscosity=0.0, transport_velocity=0):
         self.case = case
         self.f64 = bool(f64)
         self.dtype = np.float64 if f64 else np.float32
@@ -145,6 +146,7 @@ class OracleSim:
                 p.periodic_upper[d] = case.periodic_upper[d]
             p.periodic_cutoff = float(self.dtype(case.kernel.cutoff))
         p.surface_indicator = int(surface_indicator)
+        p.viscosity, p.transport_velocity, p.transport_coefficient = float(viscosity), int(transport_velocity), 0.2
         self._params = p
         kp, mp = kernel_pod(case.kernel), mesh_pod(case.mesh)
         self._h = lib().orc_create(int(f64), C.byref(p), C.byref(kp), C.byref(mp), C.byref(mp), case.n_fluid, case.n_wall)

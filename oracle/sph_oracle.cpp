@@ -428,6 +428,9 @@ struct ParamsPOD
     double periodic_lower[3], periodic_upper[3]; // bounding_bounds_ (already rounded to Real by the caller)
     double periodic_cutoff; // cut_off_radius_max_
     int surface_indicator;  // 1: FreeSurfaceIndicationCK runs in the case loop (dambreak.cpp:133-134,192)
+    double viscosity;       // mu of the Viscosity closure; > 0: ViscousForceCK runs in the case loop
+    int transport_velocity; // 1: KernelGradientIntegral + TransportVelocityCorrectionCK<TruncatedLinear> run in the case loop
+    double transport_coefficient; // 0.2 (transport_velocity_correction_ck.h:19)
 };
 
 template <class R> struct Body
@@ -664,6 +667,8 @@ template <class R> struct Sim
         else
             names = {"Position", "VolumetricMeasure", "Velocity", "Mass", "ForcePrior", "Compression", "CompressionRate",
                      "VolumetricMeasureRef", "PreviousGravityForceCK"};
+        // ForcePriorCK registers the previous value of its force as evolving (force_prior_ck.cpp:13-14)
+        if (!legacy && fluid.real.count("PreviousViscousForce")) names.push_back("PreviousViscousForce");
         for (const std::string &nm : names)
         {
             std::vector<R> &a = fluid.real[nm];
@@ -826,6 +831,101 @@ template <class R> struct Sim
         observe("Pressure");
         const std::vector<R> &out = observer.r("Pressure");
         probe_series.emplace_back(out.begin(), out.end());
+    }
+    // correction_(i): identity for NoKernelCorrectionCK, B_i for LinearCorrectionCK (kernel_correction_ck.h:42-187)
+    inline M3<R> corrMat(const std::vector<R> &B, u32 i) const
+    {
+        if (P.correction) return mat(B, i);
+        M3<R> m;
+        std::memset(m.m, 0, sizeof(m.m));
+        m.m[0] = m.m[4] = m.m[8] = R(1);
+        return m;
+    }
+    // ViscousForceCK<Inner<WithUpdate, Viscosity, Correction>, Contact<Wall, ...>> + ForcePriorCK::UpdateKernel;
+    // ref: fluid_dynamics/viscous_force.hpp:44-103, general_dynamics/force_prior_ck.h:53-57, materials/viscosity.h:60-66
+    void viscousForce()
+    {
+        const u32 n = fluid.n;
+        const std::vector<R> &pos = fluid.r("Position", 3), &Vol = fluid.r("VolumetricMeasure"), &vel = fluid.r("Velocity", 3);
+        const std::vector<R> &wpos = wall.r("Position", 3), &wVol = wall.r("VolumetricMeasure"), &wvel = wall.r("Velocity", 3);
+        const std::vector<R> &B = fluid.r("LinearCorrectionMatrix", 9);
+        std::vector<R> &F = fluid.r("ViscousForce", 3), &prev = fluid.r("PreviousViscousForce", 3), &Fp = fluid.r("ForcePrior", 3);
+        const R mu = R(P.viscosity), h = R(P.h_min), eps = R(0.01) * h * h;
+        const R mu_ij = R(2.0) * mu * mu / (mu + mu); // PairGeomAverageFixed
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long i = 0; i < (long)n; ++i)
+        {
+            V3<R> f, fw;
+            const V3<R> vi = vec(vel, i);
+            const M3<R> Bi = corrMat(B, i);
+            for (u32 m = inner.offset[i]; m < inner.offset[i + 1]; ++m)
+            {
+                u32 j = inner.index[m];
+                V3<R> d = innerDisp(pos, i, m);
+                V3<R> e = d.normalized();
+                R dWV = K.dW(d) * Vol[j];
+                V3<R> vel_derivative = (vi - vec(vel, j)) / (d.squaredNorm() + eps);
+                M3<R> Bs = Bi + corrMat(B, j);
+                f += d.dot(Bs * e) * mu_ij * vel_derivative * dWV;
+            }
+            for (u32 m = contact.offset[i]; m < contact.offset[i + 1]; ++m)
+            {
+                u32 j = contact.index[m];
+                V3<R> d = vec(pos, i) - vec(wpos, j);
+                V3<R> e = d.normalized();
+                R dWV = K.dW(d) * wVol[j];
+                V3<R> vel_derivative = R(2.0) * (vi - vec(wvel, j)) / (d.squaredNorm() + eps);
+                fw += R(2.0) * d.dot(Bi * e) * mu * vel_derivative * dWV;
+            }
+            V3<R> total = f * Vol[i] + fw * Vol[i];
+            setv(F, i, total);
+            setv(Fp, i, vec(Fp, i) + (total - vec(prev, i)));
+            setv(prev, i, total);
+        }
+    }
+    // KernelGradientIntegral<Inner<Correction>, Contact<Boundary, Correction>>; ref: general_dynamics/kernel_gradient_integral.hpp:33-78
+    void kernelGradientIntegral()
+    {
+        const u32 n = fluid.n;
+        const std::vector<R> &pos = fluid.r("Position", 3), &Vol = fluid.r("VolumetricMeasure");
+        const std::vector<R> &wpos = wall.r("Position", 3), &wVol = wall.r("VolumetricMeasure");
+        const std::vector<R> &B = fluid.r("LinearCorrectionMatrix", 9);
+        std::vector<R> &kgi = fluid.r("KernelGradientIntegral", 3);
+#pragma omp parallel for schedule(dynamic, 256)
+        for (long i = 0; i < (long)n; ++i)
+        {
+            V3<R> g, gw;
+            const M3<R> Bi = corrMat(B, i);
+            for (u32 m = inner.offset[i]; m < inner.offset[i + 1]; ++m)
+            {
+                u32 j = inner.index[m];
+                V3<R> d = innerDisp(pos, i, m);
+                g -= ((Bi + corrMat(B, j)) * d.normalized()) * (K.dW(d) * Vol[j]);
+            }
+            for (u32 m = contact.offset[i]; m < contact.offset[i + 1]; ++m)
+            {
+                u32 j = contact.index[m];
+                V3<R> d = vec(pos, i) - vec(wpos, j);
+                gw -= (Bi * d.normalized()) * (R(2.0) * K.dW(d) * wVol[j]);
+            }
+            setv(kgi, i, g + gw);
+        }
+    }
+    // TransportVelocityCorrectionCK<SPHBody, TruncatedLinear | NoLimiter, [BulkParticles]>;
+    // ref: fluid_dynamics/transport_velocity_correction_ck.hpp:39-50, common/common_functors.h:69-94
+    void transportVelocityCorrection(int limiter, bool bulk_only)
+    {
+        const std::vector<R> &kgi = fluid.r("KernelGradientIntegral", 3);
+        std::vector<R> &dpos = fluid.r("Displacement", 3);
+        const R h = R(P.h_min), h2 = h * h, scaling = R(P.transport_coefficient) * h2;
+        const std::vector<u32> *ind = bulk_only ? &fluid.uint["Indicator"] : nullptr;
+        for (u32 i = 0; i < fluid.n; ++i)
+        {
+            if (ind && (*ind)[i] != 0u) continue;
+            V3<R> g = vec(kgi, i);
+            R lim = limiter ? SMIN(R(100.0) * (h2 * g.squaredNorm()), R(1)) : R(1);
+            setv(dpos, i, vec(dpos, i) + (scaling * lim) * g);
+        }
     }
     // ref: fluid_time_step_ck.h:139-180
     void advectionSetup()
@@ -1269,6 +1369,12 @@ template <class R> struct Sim
                 compressionSummation();
                 densityRegularization();
                 advectionSetup();
+                if (P.viscosity > 0) viscousForce(); // lid_driven_cavity_sycl.cpp:268-276: viscous force, [correction, indicator,] integral, transport
+                if (P.transport_velocity)
+                {
+                    kernelGradientIntegral();
+                    transportVelocityCorrection(1, false);
+                }
                 double adv_dt = advectionDt();
                 if (P.surface_indicator) surfaceIndication(); // fluid_boundary_indicator.exec(), dambreak.cpp:192
                 if (P.correction) linearCorrection();
@@ -1388,6 +1494,9 @@ double execOp(Sim<R> &s, const std::string &op, double a0, double a1, double a2,
     else if (op == "acoustic2_update") s.a2Update(R(a0));
     else if (op == "linear_correction") s.linearCorrection();
     else if (op == "surface_indication") s.surfaceIndication();
+    else if (op == "viscous_force") s.viscousForce();
+    else if (op == "kernel_gradient_integral") s.kernelGradientIntegral();
+    else if (op == "transport_velocity_correction") s.transportVelocityCorrection((int)a0, a1 != 0.0);
     else if (op == "set_observers") { s.observer.n = (u32)a0; s.observer.real.clear(); }
     else if (op == "observer_relation") s.observerRelation();
     else if (op == "observe_pressure") s.observe("Pressure");

@@ -1331,3 +1331,260 @@ extern "C" int sphb200_interpolate(sphb200_context_t *ctx, const sphb200_kernel_
     }
     return 0;
 }
+
+// =====================================================================================================
+// viscous force: ViscousForceCK<Inner<WithUpdate, Viscosity, Correction>, Contact<Wall, Viscosity, Correction>> + the
+// ForcePriorCK update it carries; fluid_dynamics/viscous_force.hpp:44-103, general_dynamics/force_prior_ck.h:53-57
+//   inner: F_i = V_i sum_j r_ij.((B_i + B_j) e_ij) mu_ij (v_i - v_j) / (r^2 + 0.01 h^2) dW_ij V_j
+//   wall : F_i += V_i sum_j 2 r_ij.(B_i e_ij) mu 2 (v_i - v_wall,j) / (r^2 + 0.01 h^2) dW_ij V_j
+//   then : ForcePrior += F - Previous; Previous = F          (one launch: only the particle's own data is written)
+// =====================================================================================================
+template <bool CORR, bool ANALYTIC>
+__global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS)
+    k_viscous_force(FArgs a, KTab dwtab, float mu, float h2_eps, float4 *__restrict__ viscous_force, float4 *__restrict__ previous_force)
+{
+    __shared__ float4 tab[KT_SLOTS];
+    if (!ANALYTIC) stage_tab(dwtab, tab);
+    u32 t = active_slot(a);
+    if (t < a.begin || t >= a.end) return;
+    const u32 i = a.order ? a.order[t] : t;
+    const float4 xi = a.posvol[i];
+    const float4 vi = a.vel[i];
+    float Bi[9];
+    if (CORR) load_mat(a.B, i, Bi);
+    float fx = 0.f, fy = 0.f, fz = 0.f;
+    {
+        u32 cnt = a.in_count[t];
+        const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
+        float4 xjs[NB_U], vjs[NB_U];
+        u32 js[NB_U];
+        for_neighbors(
+            idx, cnt,
+            [&](int q, u32 j) {
+                load_rec2(a.rec2, j, xjs[q], vjs[q]);
+                if (CORR) js[q] = j;
+            },
+            [&](int q, bool valid) {
+                const float4 xj = xjs[q], vj = vjs[q];
+                float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                float r2 = dx * dx + dy * dy + dz * dz;
+                float r, inv_r;
+                dist(r2, r, inv_r);
+                float dWV = kernel_dw<ANALYTIC>(a, tab, r) * xj.w;
+                dWV = valid ? dWV : 0.f;
+                float proj; // r_ij . ((B_i + B_j) e_ij)
+                if (CORR)
+                {
+                    float Bj[9];
+                    load_mat(a.B, js[q], Bj);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) Bj[k] += Bi[k];
+                    float3 be = mat_vec(Bj, make_float3(dx * inv_r, dy * inv_r, dz * inv_r));
+                    proj = dx * be.x + dy * be.y + dz * be.z;
+                }
+                else
+                    proj = 2.0f * r; // (1 + 1) r_ij . e_ij
+                float c = proj * mu * dWV / (r2 + h2_eps);
+                fx += c * (vi.x - vj.x); fy += c * (vi.y - vj.y); fz += c * (vi.z - vj.z);
+            });
+    }
+    float wx = 0.f, wy = 0.f, wz = 0.f;
+    if (a.n_wall)
+    {
+        u32 cnt = a.ct_count[t];
+        const u32 *idx = a.ct_index + (u64)a.ct_slice[t >> 5] + (t & 31u);
+        float4 xjs[NB_WALL_U], wvs[NB_WALL_U];
+        const bool has_vel = a.w_vel != nullptr;
+        for_neighbors<NB_WALL_U>(
+            idx, cnt,
+            [&](int q, u32 j) {
+                xjs[q] = a.w_posvol[j];
+                if (has_vel) wvs[q] = a.w_vel[j];
+            },
+            [&](int q, bool valid) {
+                const float4 xj = xjs[q];
+                float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                float r2 = dx * dx + dy * dy + dz * dz;
+                float r, inv_r;
+                dist(r2, r, inv_r);
+                float dWV = kernel_dw<ANALYTIC>(a, tab, r) * xj.w;
+                dWV = valid ? dWV : 0.f;
+                float proj;
+                if (CORR)
+                {
+                    float3 be = mat_vec(Bi, make_float3(dx * inv_r, dy * inv_r, dz * inv_r));
+                    proj = dx * be.x + dy * be.y + dz * be.z;
+                }
+                else
+                    proj = r;
+                float ux = vi.x, uy = vi.y, uz = vi.z;
+                if (has_vel) { ux -= wvs[q].x; uy -= wvs[q].y; uz -= wvs[q].z; }
+                float c = 2.0f * proj * mu * dWV / (r2 + h2_eps) * 2.0f;
+                wx += c * ux; wy += c * uy; wz += c * uz;
+            });
+    }
+    const float vol_i = xi.w;
+    float4 F = make_float4(fx * vol_i, fy * vol_i, fz * vol_i, 0.f);
+    F.x += wx * vol_i; F.y += wy * vol_i; F.z += wz * vol_i;
+    viscous_force[i] = F;
+    float4 P = previous_force[i], Fp = a.force_prior[i];
+    Fp.x += F.x - P.x; Fp.y += F.y - P.y; Fp.z += F.z - P.z;
+    a.force_prior[i] = Fp;
+    previous_force[i] = F;
+}
+
+extern "C" int sphb200_viscous_force(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, float mu, float smoothing_length,
+                                     sphb200_vec4_t *viscous_force, sphb200_vec4_t *previous_viscous_force, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && s && viscous_force && previous_viscous_force, "null pointer");
+    FArgs a;
+    KTab dwtab;
+    int rc = make_fargs(ctx, s, &a, nullptr, &dwtab);
+    if (rc) return rc;
+    SPH_CHECK_ARG(ctx, a.n == 0 || (a.posvol && a.vel && a.rec2 && a.force_prior && a.in_count && a.in_slice && a.in_index), "null fluid array");
+    SPH_CHECK_ARG(ctx, a.n_wall == 0 || (a.w_posvol && a.ct_count && a.ct_slice && a.ct_index), "null wall array");
+    SPH_CHECK_ARG(ctx, !s->material.correction || a.B, "LinearCorrectionCK needs fluid.B");
+    if (a.end <= a.begin) return 0;
+    const float h2_eps = 0.01f * smoothing_length * smoothing_length;
+    unsigned g = active_blocks(a, FL_THREADS);
+    float4 *vf = (float4 *)viscous_force, *pf = (float4 *)previous_viscous_force;
+    if (s->material.correction)
+    {
+        if (a.analytic) SPH_LAUNCH(ctx, (k_viscous_force<true, true>), g, FL_THREADS, 0, stream, a, dwtab, mu, h2_eps, vf, pf);
+        else SPH_LAUNCH(ctx, (k_viscous_force<true, false>), g, FL_THREADS, 0, stream, a, dwtab, mu, h2_eps, vf, pf);
+    }
+    else
+    {
+        if (a.analytic) SPH_LAUNCH(ctx, (k_viscous_force<false, true>), g, FL_THREADS, 0, stream, a, dwtab, mu, h2_eps, vf, pf);
+        else SPH_LAUNCH(ctx, (k_viscous_force<false, false>), g, FL_THREADS, 0, stream, a, dwtab, mu, h2_eps, vf, pf);
+    }
+    return 0;
+}
+
+// =====================================================================================================
+// KernelGradientIntegral<Inner<Correction>, Contact<Boundary, Correction>>; general_dynamics/kernel_gradient_integral.hpp:33-78
+//   kgi_i = - sum_j (B_i + B_j) dW_ij V_j e_ij - sum_wall 2 B_i dW_ij V_j e_ij
+// =====================================================================================================
+template <bool CORR, bool ANALYTIC>
+__global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_kernel_gradient_integral(FArgs a, KTab dwtab, float4 *__restrict__ kgi)
+{
+    __shared__ float4 tab[KT_SLOTS];
+    if (!ANALYTIC) stage_tab(dwtab, tab);
+    u32 t = active_slot(a);
+    if (t < a.begin || t >= a.end) return;
+    const u32 i = a.order ? a.order[t] : t;
+    const float4 xi = a.posvol[i];
+    float Bi[9];
+    if (CORR) load_mat(a.B, i, Bi);
+    float gx = 0.f, gy = 0.f, gz = 0.f;
+    {
+        u32 cnt = a.in_count[t];
+        const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
+        float4 xjs[NB_U];
+        u32 js[NB_U];
+        for_neighbors(
+            idx, cnt,
+            [&](int q, u32 j) {
+                xjs[q] = a.posvol[j];
+                if (CORR) js[q] = j;
+            },
+            [&](int q, bool valid) {
+                const float4 xj = xjs[q];
+                float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                float r, inv_r;
+                dist(dx * dx + dy * dy + dz * dz, r, inv_r);
+                float dWV = kernel_dw<ANALYTIC>(a, tab, r) * xj.w;
+                dWV = valid ? dWV : 0.f;
+                float3 e = make_float3(dx * inv_r, dy * inv_r, dz * inv_r);
+                if (CORR)
+                {
+                    float Bj[9];
+                    load_mat(a.B, js[q], Bj);
+#pragma unroll
+                    for (int k = 0; k < 9; ++k) Bj[k] += Bi[k];
+                    e = mat_vec(Bj, e);
+                }
+                else
+                    dWV *= 2.0f;
+                gx -= dWV * e.x; gy -= dWV * e.y; gz -= dWV * e.z;
+            });
+    }
+    if (a.n_wall)
+    {
+        u32 cnt = a.ct_count[t];
+        const u32 *idx = a.ct_index + (u64)a.ct_slice[t >> 5] + (t & 31u);
+        float4 xjs[NB_U];
+        for_neighbors(
+            idx, cnt, [&](int q, u32 j) { xjs[q] = a.w_posvol[j]; },
+            [&](int q, bool valid) {
+                const float4 xj = xjs[q];
+                float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                float r, inv_r;
+                dist(dx * dx + dy * dy + dz * dz, r, inv_r);
+                float dWV = 2.0f * kernel_dw<ANALYTIC>(a, tab, r) * xj.w;
+                dWV = valid ? dWV : 0.f;
+                float3 e = make_float3(dx * inv_r, dy * inv_r, dz * inv_r);
+                if (CORR) e = mat_vec(Bi, e);
+                gx -= dWV * e.x; gy -= dWV * e.y; gz -= dWV * e.z;
+            });
+    }
+    kgi[i] = make_float4(gx, gy, gz, 0.f);
+}
+
+extern "C" int sphb200_kernel_gradient_integral(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, sphb200_vec4_t *kernel_gradient_integral,
+                                                void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && s && kernel_gradient_integral, "null pointer");
+    FArgs a;
+    KTab dwtab;
+    int rc = make_fargs(ctx, s, &a, nullptr, &dwtab);
+    if (rc) return rc;
+    SPH_CHECK_ARG(ctx, a.n == 0 || (a.posvol && a.in_count && a.in_slice && a.in_index), "null fluid array");
+    SPH_CHECK_ARG(ctx, a.n_wall == 0 || (a.w_posvol && a.ct_count && a.ct_slice && a.ct_index), "null wall array");
+    SPH_CHECK_ARG(ctx, !s->material.correction || a.B, "LinearCorrectionCK needs fluid.B");
+    if (a.end <= a.begin) return 0;
+    unsigned g = active_blocks(a, FL_THREADS);
+    float4 *out = (float4 *)kernel_gradient_integral;
+    if (s->material.correction)
+    {
+        if (a.analytic) SPH_LAUNCH(ctx, (k_kernel_gradient_integral<true, true>), g, FL_THREADS, 0, stream, a, dwtab, out);
+        else SPH_LAUNCH(ctx, (k_kernel_gradient_integral<true, false>), g, FL_THREADS, 0, stream, a, dwtab, out);
+    }
+    else
+    {
+        if (a.analytic) SPH_LAUNCH(ctx, (k_kernel_gradient_integral<false, true>), g, FL_THREADS, 0, stream, a, dwtab, out);
+        else SPH_LAUNCH(ctx, (k_kernel_gradient_integral<false, false>), g, FL_THREADS, 0, stream, a, dwtab, out);
+    }
+    return 0;
+}
+
+// TransportVelocityCorrectionCK<..., Limiter, Scopes...>::UpdateKernel::update; fluid_dynamics/transport_velocity_correction_ck.hpp:39-50
+//   dpos_i += coefficient h^2 limiter(h^2 |kgi_i|^2) kgi_i   (h_ratio == 1: single resolution), inside the particle scope
+__global__ void __launch_bounds__(256)
+    k_transport_velocity_correction(u32 n, float4 *__restrict__ dpos, const float4 *__restrict__ kgi, float scaling, float h2, int limiter,
+                                    float slope, const int *__restrict__ indicator)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (indicator && indicator[i] != 0) return; // BulkParticles: Indicator == 0 (particle_functors_ck.h:69-98)
+    float4 g = kgi[i];
+    float sq = g.x * g.x + g.y * g.y + g.z * g.z;
+    float lim = limiter ? fminf(slope * (h2 * sq), 1.0f) : 1.0f; // TruncatedLinear / NoLimiter, common_functors.h:69-94
+    float c = scaling * lim;
+    float4 d = dpos[i];
+    d.x += c * g.x; d.y += c * g.y; d.z += c * g.z;
+    dpos[i] = d;
+}
+extern "C" int sphb200_transport_velocity_correction(sphb200_context_t *ctx, const sphb200_fluid_view_t *f,
+                                                     const sphb200_vec4_t *kernel_gradient_integral, float coefficient, float h_ref,
+                                                     int limiter, float limiter_slope, const int32_t *indicator, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && f && f->dpos && kernel_gradient_integral, "null pointer");
+    SPH_CHECK_ARG(ctx, limiter == 0 || limiter == 1, "limiter: 0 NoLimiter, 1 TruncatedLinear");
+    Range r = active_range(f);
+    if (r.n)
+        SPH_LAUNCH(ctx, k_transport_velocity_correction, sph_blocks(r.n, 256), 256, 0, stream, r.n, (float4 *)f->dpos + r.b,
+                   (const float4 *)kernel_gradient_integral + r.b, coefficient * h_ref * h_ref, h_ref * h_ref, limiter, limiter_slope,
+                   indicator ? indicator + r.b : nullptr);
+    return 0;
+}

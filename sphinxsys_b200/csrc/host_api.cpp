@@ -79,6 +79,8 @@ extern "C"
         uint8_t unique_id[128];          // communicator id from sphck_comm_unique_id on rank 0 (nranks > 1)
         int32_t surface_indicator;       // FreeSurfaceIndicationComplexSpatialTemporalCK in the loop
         int32_t observers;               // the case file's pressure probes (ObserverBody + ObservedQuantityRecording)
+        double mu_f;                     // > 0: Viscosity closure + ViscousForceWithWallCK
+        int32_t transport_velocity;      // KernelGradientIntegral(Corrected)Complex + TransportVelocityCorrectionCK
     };
 
     const char *sphck_last_error() { return g_error.c_str(); }
@@ -156,6 +158,8 @@ extern "C"
             q.legacy = o->legacy != 0;
             q.surface_indicator = o->surface_indicator != 0;
             q.observers = o->observers != 0;
+            q.mu_f = o->mu_f;
+            q.transport_velocity = o->transport_velocity != 0;
             q.rank = o->rank;
             q.nranks = o->nranks > 0 ? o->nranks : 1;
             if (q.nranks > 1)
@@ -190,6 +194,8 @@ extern "C"
         int32_t fused_time_step, fused_regularization, sort_interval, device, relation_stride;
         double system_lower[3], system_upper[3];
         int32_t use_system_bounds;
+        double mu_f;                 // > 0: viscous (ViscousForceInnerCK)
+        int32_t transport_velocity;  // KernelGradientIntegralInner + TransportVelocityCorrectionCK
     };
     // xyz / vel_xyz may be NULL: lattice and analytic initial condition are generated by the C++ case then
     void *sphck_taylor_green_create(const sphck_taylor_green_options *o, const float *xyz, const float *vel_xyz, uint64_t n)
@@ -202,6 +208,8 @@ extern "C"
             q.fused_time_step = o->fused_time_step != 0;
             q.fused_regularization = o->fused_regularization != 0;
             q.sort_interval = o->sort_interval;
+            q.mu_f = o->mu_f;
+            q.transport_velocity = o->transport_velocity != 0;
             std::vector<Vecd> pos, vel;
             if (xyz) pos = toVecd(xyz, n);
             if (vel_xyz) vel = toVecd(vel_xyz, n);
@@ -270,6 +278,9 @@ extern "C"
                 else if (op == "density_regularization") s.fluid_density_regularization->exec();
                 else if (op == "advection_setup") { s.water_advection_step_setup->exec(); s.volume_ghost_update->exec(); }
                 else if (op == "update_position") s.water_update_particle_position->exec();
+                else if (op == "viscous_force") { if (!s.viscous_force) throw SphError("case built without viscosity"); s.viscous_force->exec(); }
+                else if (op == "kernel_gradient_integral") { if (!s.kernel_gradient_integral) throw SphError("case built without transport velocity"); s.kernel_gradient_integral->exec(); }
+                else if (op == "transport_velocity_correction") { if (!s.transport_velocity_correction) throw SphError("case built without transport velocity"); s.transport_velocity_correction->exec(); }
                 else if (op == "advection_dt") r = s.fluid_advection_time_step->exec();
                 else if (op == "advection_dt_reduced") r = s.fluid_advection_time_step->ReducedValue();
                 else if (op == "acoustic_dt") r = s.fluid_acoustic_time_step->exec();
@@ -327,6 +338,9 @@ extern "C"
                 if (!s.fluid_boundary_indicator) throw SphError("case built without surface_indicator");
                 s.fluid_boundary_indicator->exec();
             }
+            else if (op == "viscous_force") { if (!s.fluid_viscous_force) throw SphError("case built without viscosity"); s.fluid_viscous_force->exec(); }
+            else if (op == "kernel_gradient_integral") { if (!s.kernel_gradient_integral) throw SphError("case built without transport velocity"); s.kernel_gradient_integral->exec(); }
+            else if (op == "transport_velocity_correction") { if (!s.transport_correction) throw SphError("case built without transport velocity"); s.transport_correction->exec(); }
             else if (op == "observer_relation") { if (s.fluid_observer_contact_relation) s.fluid_observer_contact_relation->exec(); }
             else if (op == "observe_pressure")
             {

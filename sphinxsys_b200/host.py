@@ -18,7 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 HOST_LIB_PATH = os.path.join(_HERE, "libsphb200_host.so")
 
 VEC_NAMES = {"Position", "Velocity", "Displacement", "Force", "ForcePrior", "NormalDirection", "PreviousGravityForceCK",
-             "AverageVelocity", "AverageAcceleration"}
+             "AverageVelocity", "AverageAcceleration", "ViscousForce", "PreviousViscousForce", "KernelGradientIntegral"}
 UINT_NAMES = {"OriginalID", "SortedID", "ReferenceID"}
 MAT_NAMES = {"LinearCorrectionMatrix"}
 INT_NAMES = {"Indicator", "PreviousSurfaceIndicator"}
@@ -30,14 +30,15 @@ class Options(C.Structure):
                 ("fused_time_step", C.c_int32), ("fused_regularization", C.c_int32), ("sort_interval", C.c_int32),
                 ("device", C.c_int32), ("relation_stride", C.c_int32), ("system_lower", C.c_double * 3),
                 ("system_upper", C.c_double * 3), ("use_system_bounds", C.c_int32), ("legacy", C.c_int32), ("rank", C.c_int32),
-                ("nranks", C.c_int32), ("unique_id", C.c_uint8 * 128), ("surface_indicator", C.c_int32), ("observers", C.c_int32)]
+                ("nranks", C.c_int32), ("unique_id", C.c_uint8 * 128), ("surface_indicator", C.c_int32), ("observers", C.c_int32),
+                ("mu_f", C.c_double), ("transport_velocity", C.c_int32)]
 
 
 class TaylorGreenOptions(C.Structure):
     _fields_ = [("dim", C.c_int32), ("dp", C.c_double), ("L", C.c_double), ("U_f", C.c_double), ("fused_time_step", C.c_int32),
                 ("fused_regularization", C.c_int32), ("sort_interval", C.c_int32), ("device", C.c_int32),
                 ("relation_stride", C.c_int32), ("system_lower", C.c_double * 3), ("system_upper", C.c_double * 3),
-                ("use_system_bounds", C.c_int32)]
+                ("use_system_bounds", C.c_int32), ("mu_f", C.c_double), ("transport_velocity", C.c_int32)]
 
 
 _lib = None
@@ -115,7 +116,8 @@ class DamBreakCK:
 
     def __init__(self, case=None, device_index=0, correction=False, fused_time_step=True, sort_interval=100,
                  relation_stride=None, fused_regularization=True, dim=3, dp=0.05, generate=False, rank=0, nranks=1,
-                 unique_id=None, width_scale=1.0, legacy=False, surface_indicator=False, observers=False):
+                 unique_id=None, width_scale=1.0, legacy=False, surface_indicator=False, observers=False, mu_f=0.0,
+                 transport_velocity=False):
         self.lib = load()
         o = Options()
         if case is not None:
@@ -131,6 +133,7 @@ class DamBreakCK:
         o.DW, o.LW = o.DW * width_scale, o.LW * width_scale
         o.legacy = int(bool(legacy))
         o.surface_indicator, o.observers = int(bool(surface_indicator)), int(bool(observers))
+        o.mu_f, o.transport_velocity = float(mu_f), int(bool(transport_velocity))
         o.rank, o.nranks = int(rank), int(nranks)
         if nranks > 1:
             if unique_id is None or len(unique_id) != 128:
@@ -320,9 +323,10 @@ class TaylorGreenCK(DamBreakCK):
     Shares the driving interface of DamBreakCK (exec by name, upload/download in the reference particle order)."""
 
     def __init__(self, case=None, device_index=0, fused_time_step=True, sort_interval=100, relation_stride=None,
-                 fused_regularization=True, dim=3, n_side=32, generate=False):
+                 fused_regularization=True, dim=3, n_side=32, generate=False, mu_f=0.0, transport_velocity=False):
         self.lib = load()
         o = TaylorGreenOptions()
+        o.mu_f, o.transport_velocity = float(mu_f), int(bool(transport_velocity))
         if case is not None:
             o.dim, o.dp, o.L, o.U_f = case.dim, case.dp, case.DL, case.U_ref
         else:
