@@ -303,15 +303,29 @@ __global__ void __launch_bounds__(128)
 // candidate load is a broadcast. A lane accepts candidate k only inside its own clamped cell window
 // [lo, hi) — exactly the cells the reference visits (cell_linked_list.hpp:113-167) — and rows come out in the
 // reference order (cells x -> y -> z, then in-cell order).
-// The criterion is decided by a fused-arithmetic estimate when it is more than 1e-4 away from the threshold and
-// by the separately rounded reference expression (within()) otherwise, so set membership stays bit-identical.
+// The criterion is decided by the sign of a fused-arithmetic estimate; a lane whose chunk holds a candidate within
+// 2e-5 (relative) of the threshold re-decides that chunk with the separately rounded reference expression (within()),
+// so set membership stays bit-identical. Per candidate: one broadcast LDS.128, 3 FADD, 3 FFMA, one funnel shift (sign
+// bit into the hit mask) and one FMNMX (ambiguity tracker) — the integer/predicate pipe runs at half the FP32 rate on
+// sm_100 (scripts/microbench/ffma2.cu), which is what bounded the two-threshold FSETP/SEL form used before.
 // -----------------------------------------------------------------------------------------------------
 template <bool INNER, int MODE, bool TWO>
 __global__ void __launch_bounds__(128)
     k_relation_ordered(SearchArgs a, u32 *__restrict__ count, u32 *__restrict__ slice, u32 *__restrict__ index, u64 capacity,
                        u32 stride, u32 *__restrict__ max_count)
 {
-    constexpr int CH = 16; // candidates tested per chunk; hits of a chunk are collected in per-lane bit masks
+    constexpr int CH = 32; // candidates tested per chunk; hits of a chunk are collected in a per-lane bit mask
+    constexpr int NW = 32; // chunk masks a lane may hold back before its hits are written out
+    __shared__ float4 rel_tile[4][2 * CH];
+    __shared__ u32 rel_mask[4][NW][32];
+    __shared__ u32 rel_base[4][NW];
+    const u32 lane = threadIdx.x & 31u;
+    float4 *const warp_tile = rel_tile[threadIdx.x >> 5];
+    u32 *const my_mask = &rel_mask[threadIdx.x >> 5][0][lane]; // word w of this lane at my_mask[32 w] (bank == lane)
+    u32 *const warp_base = rel_base[threadIdx.x >> 5];
+    u32 buf = 0;
+    u32 nw = 0, nzw = 0, pend = 0; // held-back words, bitmap of the non-empty ones, hits in them
+    const float4 far = make_float4(1.0e18f, 1.0e18f, 1.0e18f, 0.f); // stands in for candidates past the stored range
     const u32 t = search_slot(a);
     const bool active = t >= a.src_begin && t < a.src_end;
     const DMesh &m = a.m;
@@ -320,10 +334,12 @@ __global__ void __launch_bounds__(128)
     const int cb = cell_coord(xi.y, m.ly, m.spacing, m.cy);
     const int cc = cell_coord(xi.z, m.lz, m.spacing, m.cz);
     const int d = a.depth;
-    // thresholds on the UNSCALED squared distance: surely inside / surely outside the support; in between the
-    // separately rounded reference expression decides (within())
+    // The fused estimate s = |xi - xj|^2 - thr (thr = the support radius squared, unscaled) decides a candidate by its
+    // sign; `amb` tracks min |s| over the chunk. Only when some candidate of the chunk lies within `band` of the threshold
+    // (relative 2e-5: two orders above the rounding difference between the estimate and the reference expression) is the
+    // chunk of that lane re-decided with the separately rounded reference expression (criterion()).
     const float h2 = 1.0f / (a.inv_h * a.inv_h);
-    const float sure_in = a.ks2 * (1.0f - 1.0e-4f) * h2, sure_out = a.ks2 * (1.0f + 1.0e-4f) * h2;
+    const float thr = a.legacy_criterion ? a.rc2 : a.ks2 * h2, nthr = -thr, band = 2.0e-5f * thr;
     // entries of this slot live at index[off], index[off + 32], ...; off_end bounds what may be written
     u64 base64 = (MODE == 1 ? (u64)(active ? slice[t >> 5] : 0u) : (u64)(t >> 5) * 32ull * stride) + (t & 31u);
     u64 room = capacity > base64 ? (capacity - base64 + 31ull) / 32ull : 0ull; // rows that fit below `capacity`
@@ -331,6 +347,35 @@ __global__ void __launch_bounds__(128)
     u32 *const out = index + base64;
     const u32 row_limit = (u32)(room > 0xffffffffull ? 0xffffffffull : room);
     u32 c = 0;
+    // Deferred emission. Writing the hits of each chunk at once costs max-over-lanes(hits in the chunk) iterations per
+    // chunk — 3.4x the mean, because the lanes' hits peak in different chunks (measured: 293 iterations per warp for 85
+    // rows, half of the kernel's stall samples). The chunk masks are held back in shared memory instead and written in
+    // ONE flat loop whose trip count is the largest pending hit count of the warp (~100): every iteration each lane
+    // takes its next hit — lowest word first, lowest bit first, i.e. still the reference search order.
+    auto flush = [&]() {
+        __syncwarp();
+        const u32 trip = warp_max_u32(pend);
+        const u32 todo_w = c < row_limit ? min(pend, row_limit - c) : 0u; // rows beyond the limit are only counted
+        u32 bits = 0, cur = 0, cw = c;
+        for (u32 k = 0; k < trip; ++k)
+            if (k < todo_w)
+            {
+                if (bits == 0)
+                {
+                    const u32 w = __ffs(nzw) - 1;
+                    nzw &= nzw - 1;
+                    bits = my_mask[32u * w];
+                    cur = warp_base[w];
+                }
+                const u32 b = __ffs(bits) - 1;
+                bits &= bits - 1;
+                out[32ull * cw] = cur + b;
+                ++cw;
+            }
+        c += pend;
+        nw = 0, nzw = 0, pend = 0;
+        __syncwarp();
+    };
     for (int pass = 0; pass < (TWO ? 2 : 1); ++pass)
     {
     // pass 1 walks the second candidate set (periodic images): same mesh, its own cell list, no self exclusion
@@ -338,72 +383,83 @@ __global__ void __launch_bounds__(128)
     const u32 *__restrict__ coff = TWO && pass ? a.cell_offset2 : a.cell_offset;
     const u32 ibase = TWO && pass ? a.index_base2 : 0u;
     const bool self_excl = INNER && !(TWO && pass);
+    const u32 n_tar = coff[(u32)m.cx * (u32)m.cy * (u32)m.cz]; // stored candidates: full chunks may read (not accept) past a run
     u32 todo = __ballot_sync(0xffffffffu, active);
-    while (todo)
+    while (todo) // the WHOLE warp walks the runs of every column group (uniform control flow); non-members accept nothing
     {
         const int leader = __ffs(todo) - 1;
         const int la = __shfl_sync(0xffffffffu, ca, leader), lb = __shfl_sync(0xffffffffu, cb, leader);
         const bool in = active && ca == la && cb == lb;
-        const u32 g = __ballot_sync(0xffffffffu, in);
-        todo &= ~g;
-        if (in)
-        {
-            const int zmin = __reduce_min_sync(g, cc), zmax = __reduce_max_sync(g, cc);
-            const int x0 = max(0, la - d), x1 = min(m.cx, la + d + 1);
-            const int y0 = max(0, lb - d), y1 = min(m.cy, lb + d + 1);
-            const int z0 = max(0, zmin - d), z1 = min(m.cz, zmax + d + 1);
-            const int wz0 = max(0, cc - d), wz1 = min(m.cz, cc + d + 1);
-            for (int x = x0; x < x1; ++x)
-                for (int y = y0; y < y1; ++y)
+        todo &= ~__ballot_sync(0xffffffffu, in);
+        const int zmin = __reduce_min_sync(0xffffffffu, in ? cc : 0x7fffffff), zmax = __reduce_max_sync(0xffffffffu, in ? cc : -1);
+        const int x0 = max(0, la - d), x1 = min(m.cx, la + d + 1);
+        const int y0 = max(0, lb - d), y1 = min(m.cy, lb + d + 1);
+        const int z0 = max(0, zmin - d), z1 = min(m.cz, zmax + d + 1);
+        const int wz0 = max(0, cc - d), wz1 = min(m.cz, cc + d + 1);
+        for (int x = x0; x < x1; ++x)
+            for (int y = y0; y < y1; ++y)
+            {
+                const u32 col = cell_linear(m, x, y, 0);
+                const u32 rb = coff[col + z0], re = coff[col + z1];
+                const u32 lo = in ? coff[col + wz0] : 0u, hi = in ? coff[col + wz1] : 0u;
+                // chunk staging: lane l fetches candidate kb + l (one coalesced 512-byte load per chunk), the warp
+                // exchanges the chunk through its shared-memory tile and every lane reads candidate b with a broadcast
+                // LDS.128. (A broadcast LDG.128 costs 4 L1 data-pipe wavefronts — it is served per quarter warp even when
+                // all lanes read the same 16 bytes — which bounded this kernel at 83 % L1 before; profiles/r01_v5_*.)
+                // Two tiles per warp: one __syncwarp per chunk orders the stores of chunk i+2 behind the reads of chunk i.
+                float4 nxt = rb + lane < n_tar ? tpos[rb + lane] : far;
+                for (u32 kb = rb; kb < re; kb += CH)
                 {
-                    const u32 col = cell_linear(m, x, y, 0);
-                    const u32 rb = coff[col + z0], re = coff[col + z1];
-                    const u32 lo = coff[col + wz0], hi = coff[col + wz1];
-                    for (u32 kb = rb; kb < re; kb += CH)
-                    {
-                        u32 sure = 0, maybe = 0;
-                        const float4 *__restrict__ pk = tpos + kb;
-                        auto test = [&](int b, u32 bit) {
-                            const float4 xj = pk[b];
-                            const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-                            const float r2 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
-                            if (r2 < sure_in) sure |= bit;
-                            if (r2 < sure_out) maybe |= bit;
-                        };
-                        if (kb + CH <= re)
-                        {
+                    float4 *tile = warp_tile + buf * CH;
+                    buf ^= 1u;
+                    tile[lane] = nxt;
+                    __syncwarp();
+                    if (kb + CH < re) nxt = kb + CH + lane < n_tar ? tpos[kb + CH + lane] : far;
+                    // hits: the sign bit of s is shifted into the mask with one funnel shift per candidate (candidate b
+                    // ends at bit 31-b, reversed afterwards); candidates past the run are dropped by the window mask
+                    u32 hits = 0;
+                    float amb = 3.0e38f;
 #pragma unroll
-                            for (int b = 0; b < CH; ++b) test(b, 1u << b);
-                        }
-                        else
-                            for (int b = 0; kb + (u32)b < re; ++b) test(b, 1u << b);
-                        // the lane's own cell window [lo, hi) as a bit range of this chunk; INNER: not itself
-                        const u32 blo = lo > kb ? min(lo - kb, 32u) : 0u, bhi = hi > kb ? min(hi - kb, 32u) : 0u;
-                        u32 wmask = (bhi >= 32u ? 0xffffffffu : (1u << bhi) - 1u) & ~(blo >= 32u ? 0xffffffffu : (1u << blo) - 1u);
-                        if (self_excl && t - kb < (u32)CH) wmask &= ~(1u << (t - kb));
-                        maybe &= wmask & ~sure;
-                        sure &= wmask;
-                        while (maybe) // rare: within 1e-4 of the threshold
+                    for (int b = 0; b < CH; ++b)
+                    {
+                        const float4 xj = tile[b];
+                        const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                        const float s = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, nthr)));
+                        hits = __funnelshift_l(__float_as_uint(s), hits, 1);
+                        amb = fminf(amb, fabsf(s));
+                    }
+                    hits = __brev(hits);
+                    // the lane's own cell window [lo, hi) as a bit range of this chunk; INNER: not itself
+                    const u32 blo = lo > kb ? min(lo - kb, 32u) : 0u, bhi = hi > kb ? min(hi - kb, 32u) : 0u;
+                    u32 wmask = (bhi >= 32u ? 0xffffffffu : (1u << bhi) - 1u) & ~(blo >= 32u ? 0xffffffffu : (1u << blo) - 1u);
+                    if (self_excl && t - kb < (u32)CH) wmask &= ~(1u << (t - kb));
+                    if (amb <= band && wmask) // rare: some candidate within 2e-5 of the threshold -> reference expression
+                    {
+                        hits = 0;
+                        for (u32 w = wmask; w;)
                         {
-                            const u32 b = __ffs(maybe) - 1;
-                            maybe &= maybe - 1;
-                            if (criterion(xi, tpos[kb + b], a.inv_h, a.ks2, a.rc2, a.legacy_criterion)) sure |= 1u << b;
+                            const u32 b = __ffs(w) - 1;
+                            w &= w - 1;
+                            if (criterion(xi, tile[b], a.inv_h, a.ks2, a.rc2, a.legacy_criterion)) hits |= 1u << b;
                         }
-                        if (MODE == 0)
-                            c += __popc(sure);
-                        else
-                            while (sure) // ascending bit order == reference search order
-                            {
-                                const u32 b = __ffs(sure) - 1;
-                                sure &= sure - 1;
-                                if (c < row_limit) out[32ull * c] = ibase + kb + b;
-                                ++c;
-                            }
+                    }
+                    hits &= wmask;
+                    if (MODE == 0)
+                        c += __popc(hits);
+                    else
+                    {
+                        if (nw == NW) flush();
+                        my_mask[32u * nw] = hits;
+                        warp_base[nw] = ibase + kb; // same value from every lane
+                        nzw |= (hits != 0u ? 1u : 0u) << nw;
+                        pend += __popc(hits);
+                        ++nw;
                     }
                 }
-        }
+            }
     }
     }
+    if (MODE != 0) flush();
     if (MODE != 1 && active) count[t] = c;
     if (MODE == 0)
     {
