@@ -295,6 +295,27 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// packed fp32x2 arithmetic (sm_100: FADD2 / FFMA2 — two IEEE fp32 operations per issue slot)
+__device__ __forceinline__ unsigned long long pk2(float lo, float hi)
+{
+    unsigned long long r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(unsigned long long v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long add2(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigned long long b, unsigned long long c)
+{
+    unsigned long long r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+
 // -----------------------------------------------------------------------------------------------------
 // Warp-uniform search for CELL-ORDERED storage (slot == particle id on both sides).
 // The 32 lanes of a warp are storage neighbours, i.e. they sit in the same (x, y) cell column and in a few
@@ -316,11 +337,11 @@ __global__ void __launch_bounds__(128)
 {
     constexpr int CH = 32; // candidates tested per chunk; hits of a chunk are collected in a per-lane bit mask
     constexpr int NW = 32; // chunk masks a lane may hold back before its hits are written out
-    __shared__ float4 rel_tile[4][2 * CH];
+    __shared__ __align__(16) float rel_tile[4][2][3][CH]; // per warp: two tiles of x[CH], y[CH], z[CH]
     __shared__ u32 rel_mask[4][NW][32];
     __shared__ u32 rel_base[4][NW];
     const u32 lane = threadIdx.x & 31u;
-    float4 *const warp_tile = rel_tile[threadIdx.x >> 5];
+    float(*const warp_tile)[3][CH] = rel_tile[threadIdx.x >> 5];
     u32 *const my_mask = &rel_mask[threadIdx.x >> 5][0][lane]; // word w of this lane at my_mask[32 w] (bank == lane)
     u32 *const warp_base = rel_base[threadIdx.x >> 5];
     u32 buf = 0;
@@ -339,7 +360,8 @@ __global__ void __launch_bounds__(128)
     // (relative 2e-5: two orders above the rounding difference between the estimate and the reference expression) is the
     // chunk of that lane re-decided with the separately rounded reference expression (criterion()).
     const float h2 = 1.0f / (a.inv_h * a.inv_h);
-    const float thr = a.legacy_criterion ? a.rc2 : a.ks2 * h2, nthr = -thr, band = 2.0e-5f * thr;
+    const float thr = a.legacy_criterion ? a.rc2 : a.ks2 * h2, band = 2.0e-5f * thr;
+    const unsigned long long nthr2 = pk2(-thr, -thr), nxi_x = pk2(-xi.x, -xi.x), nxi_y = pk2(-xi.y, -xi.y), nxi_z = pk2(-xi.z, -xi.z);
     // entries of this slot live at index[off], index[off + 32], ...; off_end bounds what may be written
     u64 base64 = (MODE == 1 ? (u64)(active ? slice[t >> 5] : 0u) : (u64)(t >> 5) * 32ull * stride) + (t & 31u);
     u64 room = capacity > base64 ? (capacity - base64 + 31ull) / 32ull : 0ull; // rows that fit below `capacity`
@@ -410,23 +432,36 @@ __global__ void __launch_bounds__(128)
                 float4 nxt = rb + lane < n_tar ? tpos[rb + lane] : far;
                 for (u32 kb = rb; kb < re; kb += CH)
                 {
-                    float4 *tile = warp_tile + buf * CH;
+                    float(*tile)[CH] = warp_tile[buf];
                     buf ^= 1u;
-                    tile[lane] = nxt;
+                    tile[0][lane] = nxt.x, tile[1][lane] = nxt.y, tile[2][lane] = nxt.z;
                     __syncwarp();
                     if (kb + CH < re) nxt = kb + CH + lane < n_tar ? tpos[kb + CH + lane] : far;
                     // hits: the sign bit of s is shifted into the mask with one funnel shift per candidate (candidate b
-                    // ends at bit 31-b, reversed afterwards); candidates past the run are dropped by the window mask
+                    // ends at bit 31-b, reversed afterwards); candidates past the run are dropped by the window mask.
+                    // Four candidates per step: three broadcast LDS.128 (x, y, z of candidates 4q..4q+3), then two packed
+                    // evaluations of s = |xj - xi|^2 - thr (3 FADD2 + 3 FFMA2 each).
                     u32 hits = 0;
                     float amb = 3.0e38f;
 #pragma unroll
-                    for (int b = 0; b < CH; ++b)
+                    for (int q = 0; q < CH / 4; ++q)
                     {
-                        const float4 xj = tile[b];
-                        const float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-                        const float s = fmaf(dz, dz, fmaf(dy, dy, fmaf(dx, dx, nthr)));
-                        hits = __funnelshift_l(__float_as_uint(s), hits, 1);
-                        amb = fminf(amb, fabsf(s));
+                        const float4 X = *reinterpret_cast<const float4 *>(&tile[0][4 * q]);
+                        const float4 Y = *reinterpret_cast<const float4 *>(&tile[1][4 * q]);
+                        const float4 Z = *reinterpret_cast<const float4 *>(&tile[2][4 * q]);
+                        const unsigned long long dx0 = add2(pk2(X.x, X.y), nxi_x), dx1 = add2(pk2(X.z, X.w), nxi_x);
+                        const unsigned long long dy0 = add2(pk2(Y.x, Y.y), nxi_y), dy1 = add2(pk2(Y.z, Y.w), nxi_y);
+                        const unsigned long long dz0 = add2(pk2(Z.x, Z.y), nxi_z), dz1 = add2(pk2(Z.z, Z.w), nxi_z);
+                        const unsigned long long s01 = fma2(dz0, dz0, fma2(dy0, dy0, fma2(dx0, dx0, nthr2)));
+                        const unsigned long long s23 = fma2(dz1, dz1, fma2(dy1, dy1, fma2(dx1, dx1, nthr2)));
+                        float s0, s1, s2, s3;
+                        upk2(s01, s0, s1);
+                        upk2(s23, s2, s3);
+                        hits = __funnelshift_l(__float_as_uint(s0), hits, 1);
+                        hits = __funnelshift_l(__float_as_uint(s1), hits, 1);
+                        hits = __funnelshift_l(__float_as_uint(s2), hits, 1);
+                        hits = __funnelshift_l(__float_as_uint(s3), hits, 1);
+                        amb = fminf(fminf(amb, fminf(fabsf(s0), fabsf(s1))), fminf(fabsf(s2), fabsf(s3)));
                     }
                     hits = __brev(hits);
                     // the lane's own cell window [lo, hi) as a bit range of this chunk; INNER: not itself
@@ -440,7 +475,7 @@ __global__ void __launch_bounds__(128)
                         {
                             const u32 b = __ffs(w) - 1;
                             w &= w - 1;
-                            if (criterion(xi, tile[b], a.inv_h, a.ks2, a.rc2, a.legacy_criterion)) hits |= 1u << b;
+                            if (criterion(xi, make_float4(tile[0][b], tile[1][b], tile[2][b], 0.f), a.inv_h, a.ks2, a.rc2, a.legacy_criterion)) hits |= 1u << b;
                         }
                     }
                     hits &= wmask;
