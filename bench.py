@@ -173,7 +173,7 @@ def run_ours(args, rank, world, local_rank):
         dist.broadcast(buf, src=0)
         uid = bytes(buf.cpu().numpy().tobytes())
     solver = DamBreakCK(None, dim=3, dp=dp, device_index=local_rank, fused_time_step=True, sort_interval=100, generate=True,
-                        rank=rank, nranks=world, unique_id=uid)
+                        rank=rank, nranks=world, unique_id=uid, serial_exchange=args.serial_exchange)
     solver.initialize()
     n_own = solver.own_range()[1]
     n_wall = solver.n_wall
@@ -390,6 +390,7 @@ def main():
     ap.add_argument("--ref-dp", type=float, default=0.0125, help="resolution of the bounded CPU sample (512,000 fluid)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--serial-exchange", action="store_true", help="N > 1: plane exchange in line with the dynamics (no overlap)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

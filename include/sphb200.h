@@ -215,6 +215,9 @@ int sphb200_stream_sync(void *stream);
 /* transfer overlap (extension; the SYCL build has a single in-order queue): a non-blocking side stream and events, so
  * that sphb200_copy_h2d / _d2h on pinned host memory run while dynamics execute on the main stream */
 int sphb200_stream_create(void **stream);
+/* side stream whose kernels are scheduled ahead of (high_priority != 0) or behind the other streams' pending blocks:
+ * the halo exchange and the boundary-plane launches of a decomposed run (slab_decomposition.h) */
+int sphb200_stream_create_with_priority(void **stream, int high_priority);
 int sphb200_stream_destroy(void *stream);
 int sphb200_event_create(void **event);
 int sphb200_event_destroy(void *event);
@@ -405,6 +408,12 @@ int sphb200_total_mechanical_energy(sphb200_context_t *ctx, const sphb200_fluid_
  * contiguous ranges of every variable array: exchanges send and receive those ranges in place.
  * ------------------------------------------------------------------------------------------------- */
 #define SPHB200_UNIQUE_ID_BYTES 128
+/* Slab decomposition (new): indices of the slots in [begin, begin + n) whose x cell plane
+ * (Mesh::CellIndexFromPosition, base_mesh.hxx:9-15) is <= plane_left (left list) or >= plane_right (right list); a
+ * negative plane switches the side off. counts[0..1] (device) receive the list lengths. List order is unspecified. */
+int sphb200_slab_select(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, const sphb200_vec4_t *pos, uint32_t begin,
+                        uint32_t n, int plane_left, int plane_right, uint32_t *left_idx, uint32_t *right_idx,
+                        uint32_t *counts, void *stream);
 int sphb200_comm_unique_id(void *id128);
 int sphb200_comm_create(sphb200_context_t *ctx, int nranks, int rank, const void *id128);
 int sphb200_comm_destroy(sphb200_context_t *ctx);

@@ -124,6 +124,7 @@ class ExecutionInstance
         return ctx_;
     }
     void *stream() const { return stream_; }
+    void setStream(void *s) { stream_ = s; } // see StreamScope
     int device() const { return device_; }
     void check(int rc, const char *what)
     {
@@ -137,6 +138,19 @@ class ExecutionInstance
     uint64_t launches() { return ctx_ ? sphb200_launch_count(ctx_) : 0; }
 };
 inline ExecutionInstance &execution_instance() { return ExecutionInstance::get(); }
+
+// Every library call made while the scope lives is issued on `stream` instead of the default stream (ordering against
+// the default stream is then the caller's business: events).
+class StreamScope
+{
+    void *saved_;
+
+  public:
+    explicit StreamScope(void *stream) : saved_(execution_instance().stream()) { execution_instance().setStream(stream); }
+    ~StreamScope() { execution_instance().setStream(saved_); }
+    StreamScope(const StreamScope &) = delete;
+    StreamScope &operator=(const StreamScope &) = delete;
+};
 
 #define SPHCK_CALL(fn, ...) ::SPH::execution_instance().check(fn(::SPH::execution_instance().ctx(), __VA_ARGS__), #fn)
 

@@ -33,6 +33,7 @@ struct DamBreakParameters
     bool legacy = false;
     // slab decomposition over the GPUs of one node (needs sphb200_comm_create on this process's context first)
     int rank = 0, nranks = 1;
+    bool overlap_exchange = true; // decomposed runs: hide the plane exchange behind interior compute (acousticStepOverlapped)
     static DamBreakParameters twoDimensional(double dp = 0.025)
     {
         DamBreakParameters p;
@@ -102,6 +103,7 @@ class DamBreakCK
     std::unique_ptr<ReduceDynamicsCK<P, TotalMechanicalEnergyCK>> record_water_mechanical_energy;
     std::unique_ptr<SlabDecomposition> decomposition; // nranks > 1 only
     fluid_dynamics::AcousticStep1stHalfPhases *first_half_phases_ = nullptr;
+    fluid_dynamics::AcousticStep2ndHalfPhases *second_half_phases_ = nullptr;
     SingleVariable<Real> *sv_physical_time = nullptr;
     size_t number_of_iterations = 0, acoustic_steps = 0;
     double physical_time = 0; // accumulated in double for reporting; the SingleVariable keeps the Real copy
@@ -290,6 +292,7 @@ class DamBreakCK
         record_water_mechanical_energy.reset(new ReduceDynamicsCK<P, TotalMechanicalEnergyCK>(water_block, gravity));
         sv_physical_time = sph_system.getSystemVariableByName<Real>("PhysicalTime");
         first_half_phases_ = dynamic_cast<fluid_dynamics::AcousticStep1stHalfPhases *>(fluid_acoustic_step_1st_half.get());
+        second_half_phases_ = dynamic_cast<fluid_dynamics::AcousticStep2ndHalfPhases *>(fluid_acoustic_step_2nd_half.get());
         if (q.nranks > 1)
         {
             decomposition.reset(new SlabDecomposition(water_block, q.rank, q.nranks, cuts));
@@ -349,6 +352,53 @@ class DamBreakCK
         return n_inner;
     }
 
+    // One acoustic step of a decomposed run with the plane exchange hidden behind interior compute.
+    // Default stream M: initialize (all own slots), then the INTERIOR launches of both halves. High-priority side
+    // stream S: exchange of Pressure, 1st half on the boundary planes, exchange of the velocity records, 2nd half on
+    // the boundary planes. Boundary launches run first on S because the neighbour rank waits for their results; they
+    // and the NCCL kernels slot into the SMs the interior launch frees, so neither stream idles the GPU.
+    //   event 0  M -> S  initialize done (the boundary 1st half reads every neighbour's Pressure)
+    //   event 1  S -> M  1st half done on the boundary planes (the interior 2nd half reads their velocities)
+    //   event 2  M -> S  1st half done on the interior (the boundary 2nd half reads its velocities)
+    //   event 3  S -> M  2nd half done on the boundary planes: the step is complete on M
+    void acousticStepOverlapped(Real dt)
+    {
+        using SlotRange = SlabDecomposition::SlotRange;
+        SlabDecomposition &d = *decomposition;
+        BaseParticles &p = water_block.getBaseParticles();
+        void *M = execution_instance().stream(), *S = d.sideStream();
+        const SlotRange own{d.ownBegin(), d.ownBegin() + d.ownParticles()}, in = d.interior();
+        const SlotRange edge[2] = {d.leftBoundary(), d.rightBoundary()};
+        auto on = [&](const SlotRange &r, auto &&launch) {
+            if (r.empty()) return;
+            p.setActiveRange(r.begin, r.end);
+            launch();
+        };
+        second_half_phases_->primeFusedReduction();
+        first_half_phases_->deviceInitialize(dt);
+        d.signal(0, M);
+        {
+            StreamScope side(S);
+            d.await(0, S);
+            d.refreshGhosts({"Pressure"});
+            for (const SlotRange &r : edge) on(r, [&] { first_half_phases_->deviceInteractAndUpdate(dt); });
+            d.signal(1, S);
+            d.refreshGhosts({"PosVolVel"}); // the velocity records of the boundary planes are final: send them now
+        }
+        on(in, [&] { first_half_phases_->deviceInteractAndUpdate(dt); });
+        d.signal(2, M);
+        d.await(1, M);
+        {
+            StreamScope side(S);
+            d.await(2, S);
+            for (const SlotRange &r : edge) on(r, [&] { second_half_phases_->deviceLaunch(dt); });
+            d.signal(3, S);
+        }
+        on(in, [&] { second_half_phases_->deviceLaunch(dt); });
+        d.await(3, M);
+        p.setActiveRange(own.begin, own.end);
+    }
+
     // one advection step, dambreak.cpp:188-222; returns the number of acoustic sub-steps taken
     int stepOuter()
     {
@@ -371,17 +421,22 @@ class DamBreakCK
         while (relaxation_time < advection_dt)
         {
             acoustic_dt = fluid_acoustic_time_step->exec(); // global max when decomposed
-            if (decomposition)
+            if (decomposition && q_.overlap_exchange)
+                acousticStepOverlapped(acoustic_dt);
+            else if (decomposition)
             {
                 // the two neighbour-read variables of the half steps are refreshed on the ghost planes in between
                 first_half_phases_->deviceInitialize(acoustic_dt);
                 decomposition->refreshGhosts({"Pressure"});
                 first_half_phases_->deviceInteractAndUpdate(acoustic_dt);
                 decomposition->refreshGhosts({"PosVolVel"}); // the 2nd half reads neighbour velocities from the gather record
+                fluid_acoustic_step_2nd_half->exec(acoustic_dt);
             }
             else
+            {
                 fluid_acoustic_step_1st_half->exec(acoustic_dt);
-            fluid_acoustic_step_2nd_half->exec(acoustic_dt);
+                fluid_acoustic_step_2nd_half->exec(acoustic_dt);
+            }
             relaxation_time += acoustic_dt;
             physical_time += acoustic_dt;
             sv_physical_time->incrementValue(acoustic_dt);

@@ -507,7 +507,16 @@ class AcousticStep1stHalfWithWall : public FluidDynamicsBase, public AcousticSte
     }
 };
 
-template <class RiemannType, class CorrectionType> class AcousticStep2ndHalfWithWall : public FluidDynamicsBase
+// launch-granular access to the 2nd half (prime the fused reduction once, then one launch per active slot range)
+class AcousticStep2ndHalfPhases
+{
+  public:
+    virtual ~AcousticStep2ndHalfPhases() {}
+    virtual void primeFusedReduction() = 0;
+    virtual void deviceLaunch(Real dt) = 0;
+};
+
+template <class RiemannType, class CorrectionType> class AcousticStep2ndHalfWithWall : public FluidDynamicsBase, public AcousticStep2ndHalfPhases
 {
     AcousticTimeStepBase *fused_time_step_ = nullptr;
 
@@ -532,19 +541,25 @@ template <class RiemannType, class CorrectionType> class AcousticStep2ndHalfWith
     void unfuseTimeStepReduction() { fused_time_step_ = nullptr; }
     std::vector<BaseDynamics<void> *> deviceInteract(Real dt, const std::vector<BaseDynamics<void> *> &post)
     {
-        ExecutionInstance &ex = execution_instance();
-        sphb200_fluid_args_t a = fluidArgs();
-        float *slot = nullptr;
-        Real h_min = sph_body_.getSPHAdaptation().MinimumSmoothingLength();
-        if (fused_time_step_)
-        {
-            slot = fused_time_step_->fusedSlot();
-            SPHCK_CALL(sphb200_fill_f32, slot, 0.0f, 1, ex.stream());
-            h_min = fused_time_step_->minimumSmoothingLength();
-        }
-        SPHCK_CALL(sphb200_acoustic_2nd_half, &a, dt, h_min, slot, ex.stream());
-        if (fused_time_step_) fused_time_step_->setPrimed(true);
+        primeFusedReduction();
+        deviceLaunch(dt);
         return post;
+    }
+    // the two halves of deviceInteract(), for runs that advance the active slots in several launches (interior and
+    // boundary planes of a decomposed run): prime once, then one deviceLaunch() per slot range — every launch folds its
+    // particles into the same reduction slot
+    void primeFusedReduction() override
+    {
+        if (!fused_time_step_) return;
+        SPHCK_CALL(sphb200_fill_f32, fused_time_step_->fusedSlot(), 0.0f, 1, execution_instance().stream());
+        fused_time_step_->setPrimed(true);
+    }
+    void deviceLaunch(Real dt) override
+    {
+        sphb200_fluid_args_t a = fluidArgs();
+        float *slot = fused_time_step_ ? fused_time_step_->fusedSlot() : nullptr;
+        Real h_min = fused_time_step_ ? fused_time_step_->minimumSmoothingLength() : sph_body_.getSPHAdaptation().MinimumSmoothingLength();
+        SPHCK_CALL(sphb200_acoustic_2nd_half, &a, dt, h_min, slot, execution_instance().stream());
     }
 };
 

@@ -8,8 +8,8 @@
 //   (in-cell order = ascending global ReferenceID), so halo refresh is a grouped ncclSend/ncclRecv out of and into the
 //   variable arrays themselves — no pack/unpack kernels, no index maps.
 // * rebuild() replaces UpdateCellLinkedList::exec() once per advection step: sort the own particles by their new cell,
-//   hand the planes next to each cut (particles that left the slab + the boundary plane) to the neighbour in one
-//   message per variable, append what arrives, sort again. Particles move less than one cell per advection step (CFL),
+//   pick the particles next to each cut (those that left the slab + the boundary plane) with one pass over the own
+//   positions, hand them to the neighbour in one message per variable, append what arrives, sort everything into cell order. Particles move less than one cell per advection step (CFL),
 //   so leavers are always in the plane next to the cut. Dynamics then run on the active slot range only.
 // * Cuts are particle-count quantiles of the initial distribution along x (planSlabCuts); they stay fixed in this
 //   round (dynamic re-cutting at sort time is listed as next in DESIGN.md §6).
@@ -68,7 +68,12 @@ class SlabDecomposition
     // slot offsets after the last rebuild: ghosts [0, a0) | first own plane [a0, f1) ... last own plane [l0, a1) | ghosts [a1, n)
     uint32_t a0_ = 0, f1_ = 0, l0_ = 0, a1_ = 0, n_ = 0;
     DeviceBuffer scalars_; // small device scratch for counts and reductions
+    DeviceBuffer select_;  // index lists of the outgoing particles (rebuild)
     uint64_t migrated_out_ = 0, ghost_particles_ = 0;
+    // overlap of the plane exchange with interior compute: a high-priority side stream carries the exchanges and the
+    // boundary-plane launches, the default stream the interior launches; events order the two (dambreak_case.h)
+    void *side_stream_ = nullptr;
+    void *events_[4] = {nullptr, nullptr, nullptr, nullptr};
 
     uint32_t readOffset(uint32_t cell)
     {
@@ -121,8 +126,51 @@ class SlabDecomposition
         a1_ = n_;
         p.setActiveRange(a0_, a1_);
     }
+    ~SlabDecomposition()
+    {
+        for (void *e : events_)
+            if (e) sphb200_event_destroy(e);
+        if (side_stream_) sphb200_stream_destroy(side_stream_);
+    }
+    SlabDecomposition(const SlabDecomposition &) = delete;
+    SlabDecomposition &operator=(const SlabDecomposition &) = delete;
     int rank() const { return rank_; }
     int size() const { return nranks_; }
+    // --- boundary / interior split of the own slots (valid after rebuild()) ---
+    // Boundary planes are the own planes a neighbour rank reads (and whose particles read ghost planes): the first own
+    // plane if there is a left neighbour, the last own plane if there is a right neighbour. Interior slots read own
+    // particles only, so they can be advanced while the ghost planes are in flight.
+    struct SlotRange
+    {
+        uint32_t begin, end;
+        bool empty() const { return end <= begin; }
+    };
+    SlotRange leftBoundary() const
+    {
+        if (rank_ == 0) return {a0_, a0_};
+        return {a0_, std::min(f1_, a1_)};
+    }
+    SlotRange rightBoundary() const
+    {
+        if (rank_ + 1 >= nranks_) return {a1_, a1_};
+        return {std::max(l0_, leftBoundary().end), a1_}; // one-plane slabs: the plane is the left boundary already
+    }
+    SlotRange interior() const { return {leftBoundary().end, rightBoundary().begin}; }
+    void *sideStream()
+    {
+        if (!side_stream_) execution_instance().check(sphb200_stream_create_with_priority(&side_stream_, 1), "sphb200_stream_create_with_priority");
+        return side_stream_;
+    }
+    void *event(int k)
+    {
+        if (!events_[k]) execution_instance().check(sphb200_event_create(&events_[k]), "sphb200_event_create");
+        return events_[k];
+    }
+    // signal(k, s): event k marks everything issued so far on stream s; await(k, s): stream s does not run past this
+    // point before that mark is reached (signal must be issued first in host order)
+    void signal(int k, void *stream) { execution_instance().check(sphb200_event_record(event(k), stream), "sphb200_event_record"); }
+    void await(int k, void *stream) { execution_instance().check(sphb200_stream_wait_event(stream, event(k)), "sphb200_stream_wait_event"); }
+
     const std::vector<int> &cuts() const { return cuts_; }
     uint32_t ownParticles() const { return a1_ - a0_; }
     uint32_t ownBegin() const { return a0_; }
@@ -135,19 +183,27 @@ class SlabDecomposition
     {
         ExecutionInstance &ex = execution_instance();
         BaseParticles &p = body_.getBaseParticles();
+        CellLinkedList &cl = body_.getCellLinkedList();
         void *st = ex.stream();
         const uint32_t n_old = a1_ - a0_;
-        // 1. own particles into their new cell order, at the front of the arrays (old ghosts are dropped)
-        reorder(a0_, n_old);
-        const uint32_t X0 = (uint32_t)cuts_[rank_], X1 = (uint32_t)cuts_[rank_ + 1];
-        uint32_t cells[2] = {(X0 + 1) * plane_cells_, (X1 - 1) * plane_cells_}, off[2];
-        readOffsets(cells, off, 2);
-        // left message: slots [0, off[0]) = particles that moved into plane X0-1 + the first own plane;
-        // right message: slots [off[1], n_old) = the last own plane + particles that moved into plane X1
-        const uint32_t send_l = rank_ > 0 ? off[0] : 0, send_r = rank_ + 1 < nranks_ ? n_old - off[1] : 0;
-        // 2. sizes
-        uint64_t host_counts[4] = {send_l, send_r, 0, 0};
+        const int X0 = cuts_[rank_], X1 = cuts_[rank_ + 1];
+        std::vector<DiscreteVariableBase *> vars = p.reorderedVariables();
+        const size_t k = vars.size();
+        // 1. what the neighbours need of the own slots [a0, a1): the first / last own plane and whatever moved beyond
+        //    it (particles move less than one cell per advection step, so leavers sit next to the cut). One pass over the
+        //    own positions (sphb200_slab_select) instead of a cell-order sort: the receiver sorts the lot anyway.
+        select_.ensure((size_t)2 * n_old * sizeof(uint32_t) + 64);
+        uint32_t *left_idx = select_.get<uint32_t>(), *right_idx = left_idx + n_old;
+        uint32_t *d_counts = scalars_.get<uint32_t>() + 48; // bytes 192..199 of the 256-byte scratch
+        SPHCK_CALL(sphb200_slab_select, &cl.mesh_, (const sphb200_vec4_t *)p.deviceData<Vecd>("Position"), a0_, n_old,
+                   rank_ > 0 ? X0 : -1, rank_ + 1 < nranks_ ? X1 - 1 : -1, left_idx, right_idx, d_counts, st);
+        // 2. sizes: own counts to the host (the gathers and sends are sized by them), then swapped with the neighbours
         uint64_t *d = scalars_.get<uint64_t>();
+        uint32_t sel[2] = {0, 0};
+        ex.check(sphb200_copy_d2h(sel, d_counts, sizeof(sel), st), "sphb200_copy_d2h");
+        ex.synchronize();
+        const uint32_t send_l = sel[0], send_r = sel[1];
+        uint64_t host_counts[4] = {send_l, send_r, 0, 0};
         ex.check(sphb200_copy_h2d(d, host_counts, sizeof(host_counts), st), "sphb200_copy_h2d");
         {
             const void *sl[1] = {d}, *sr[1] = {d + 1};
@@ -156,36 +212,51 @@ class SlabDecomposition
             SPHCK_CALL(sphb200_comm_exchange, 1, sl, b, rl, b, sr, b, rr, b, st);
         }
         ex.check(sphb200_copy_d2h(host_counts, d, sizeof(host_counts), st), "sphb200_copy_d2h");
+        // meanwhile: stage the outgoing particles of every variable in its shadow array: [0, send_l) left, then right
+        std::vector<void *> stage_l(k), stage_r(k);
+        std::vector<const void *> src(k);
+        std::vector<uint32_t> bytes(k);
+        for (size_t i = 0; i < k; ++i)
+        {
+            bytes[i] = vars[i]->deviceElementBytes();
+            src[i] = vars[i]->deviceAddress();
+            stage_l[i] = vars[i]->shadowAddress();
+            stage_r[i] = (char *)stage_l[i] + (size_t)send_l * bytes[i];
+        }
+        if (send_l) SPHCK_CALL(sphb200_gather_multi, (int)k, stage_l.data(), src.data(), bytes.data(), left_idx, send_l, st);
+        if (send_r) SPHCK_CALL(sphb200_gather_multi, (int)k, stage_r.data(), src.data(), bytes.data(), right_idx, send_r, st);
         ex.synchronize();
         const uint32_t recv_l = rank_ > 0 ? (uint32_t)host_counts[2] : 0, recv_r = rank_ + 1 < nranks_ ? (uint32_t)host_counts[3] : 0;
         const size_t n_tot = (size_t)n_old + recv_l + recv_r;
-        p.setTotalRealParticles(n_tot); // throws if the reserved storage is exhausted
-        // 3. payload: every stored variable, one contiguous segment per variable and direction
+        p.setTotalRealParticles((size_t)a0_ + n_tot); // throws if the reserved storage is exhausted
+        // 3. payload: one contiguous segment per variable and direction, received right behind the own slots (the old
+        //    ghosts are dropped; particles that left stay here as ghosts of their new owner)
         {
-            std::vector<DiscreteVariableBase *> vars = p.reorderedVariables();
-            const size_t k = vars.size();
             std::vector<const void *> sl(k), sr(k);
             std::vector<void *> rl(k), rr(k);
             std::vector<size_t> bsl(k), bsr(k), brl(k), brr(k);
             for (size_t i = 0; i < k; ++i)
             {
-                const size_t eb = vars[i]->deviceElementBytes();
+                const size_t eb = bytes[i];
                 char *base = (char *)vars[i]->deviceAddress();
-                sl[i] = base;
+                sl[i] = stage_l[i];
                 bsl[i] = send_l * eb;
-                sr[i] = base + (size_t)off[1] * eb;
+                sr[i] = stage_r[i];
                 bsr[i] = send_r * eb;
-                rl[i] = base + (size_t)n_old * eb;
+                rl[i] = base + (size_t)a1_ * eb;
                 brl[i] = recv_l * eb;
-                rr[i] = base + ((size_t)n_old + recv_l) * eb;
+                rr[i] = base + ((size_t)a1_ + recv_l) * eb;
                 brr[i] = recv_r * eb;
             }
             SPHCK_CALL(sphb200_comm_exchange, (int)k, sl.data(), bsl.data(), rl.data(), brl.data(), sr.data(), bsr.data(), rr.data(),
                        brr.data(), st);
         }
-        // 4. everything into cell order; own particles are the planes [X0, X1)
-        reorder(0, (uint32_t)n_tot);
-        uint32_t cells2[4] = {X0 * plane_cells_, (X0 + 1) * plane_cells_, (X1 - 1) * plane_cells_, X1 * plane_cells_}, off2[4];
+        // 4. everything into cell order at the front of the arrays; own particles are the planes [X0, X1)
+        reorder(a0_, (uint32_t)n_tot);
+        p.setTotalRealParticles(n_tot);
+        uint32_t cells2[4] = {(uint32_t)X0 * plane_cells_, (uint32_t)(X0 + 1) * plane_cells_, (uint32_t)(X1 - 1) * plane_cells_,
+                              (uint32_t)X1 * plane_cells_},
+                 off2[4];
         readOffsets(cells2, off2, 4);
         a0_ = off2[0];
         f1_ = off2[1];
@@ -196,7 +267,7 @@ class SlabDecomposition
         body_.setCellOrdered(true);
         body_.setPosVolDirty();
         ghost_particles_ = (uint64_t)a0_ + (n_ - a1_);
-        migrated_out_ += (uint64_t)(send_l - std::min(send_l, f1_ - a0_)); // rough: leavers are what was sent beyond the plane
+        migrated_out_ += (uint64_t)send_l + send_r; // boundary-plane particles and leavers handed to the neighbours
     }
 
     // refresh named variables on the ghost planes from their owners (contiguous ranges, in place)

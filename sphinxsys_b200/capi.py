@@ -128,6 +128,8 @@ SYMBOLS = {
     "sphb200_acoustic_1st_half_interact": (_I, [_CTX, C.POINTER(FluidArgs), _F, _I, _P]),
     "sphb200_linear_correction_matrix": (_I, [_CTX, C.POINTER(FluidArgs), _F, _P]),
     "sphb200_stream_create": (_I, [C.POINTER(_P)]),
+    "sphb200_slab_select": (_I, [_CTX, C.POINTER(MeshT), _P, _U32, _U32, _I, _I, _P, _P, _P, _P]),
+    "sphb200_stream_create_with_priority": (_I, [C.POINTER(_P), _I]),
     "sphb200_stream_destroy": (_I, [_P]),
     "sphb200_event_create": (_I, [C.POINTER(_P)]),
     "sphb200_event_destroy": (_I, [_P]),

@@ -81,6 +81,7 @@ extern "C"
         int32_t observers;               // the case file's pressure probes (ObserverBody + ObservedQuantityRecording)
         double mu_f;                     // > 0: Viscosity closure + ViscousForceWithWallCK
         int32_t transport_velocity;      // KernelGradientIntegral(Corrected)Complex + TransportVelocityCorrectionCK
+        int32_t serial_exchange;         // decomposed runs: 1 = plane exchange in line with the dynamics (no overlap)
     };
 
     const char *sphck_last_error() { return g_error.c_str(); }
@@ -161,6 +162,7 @@ extern "C"
             q.mu_f = o->mu_f;
             q.transport_velocity = o->transport_velocity != 0;
             q.rank = o->rank;
+            q.overlap_exchange = o->serial_exchange == 0;
             q.nranks = o->nranks > 0 ? o->nranks : 1;
             if (q.nranks > 1)
                 execution_instance().check(sphb200_comm_create(execution_instance().ctx(), q.nranks, q.rank, o->unique_id), "sphb200_comm_create");

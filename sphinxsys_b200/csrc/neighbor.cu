@@ -994,3 +994,49 @@ extern "C" int sphb200_ghost_copy(sphb200_context_t *ctx, void *array, uint32_t 
     }
     return 0;
 }
+
+// =====================================================================================================
+// slab decomposition: which own particles does a neighbour rank need? (slab_decomposition.h)
+// =====================================================================================================
+// Slot i of [begin, begin + n) goes on the LEFT list if its x cell plane is <= plane_left (the first own plane and
+// whatever moved below it), on the RIGHT list if it is >= plane_right (the last own plane and above); plane < 0 switches
+// a side off. Lists are appended with warp-aggregated atomics (order irrelevant: the receiver brings everything into
+// cell order, in-cell by ReferenceID). counts[0], counts[1] must be zero on entry.
+__global__ void __launch_bounds__(256)
+    k_slab_select(DMesh m, const float4 *__restrict__ pos, u32 begin, u32 n, int plane_left, int plane_right,
+                  u32 *__restrict__ left_idx, u32 *__restrict__ right_idx, u32 *__restrict__ counts)
+{
+    const u32 k = blockIdx.x * blockDim.x + threadIdx.x;
+    bool l = false, r = false;
+    if (k < n)
+    {
+        const int cx = cell_coord(pos[begin + k].x, m.lx, m.spacing, m.cx);
+        l = plane_left >= 0 && cx <= plane_left;
+        r = plane_right >= 0 && cx >= plane_right;
+    }
+    const u32 lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+    const u32 bl = __ballot_sync(0xffffffffu, l), br = __ballot_sync(0xffffffffu, r);
+    u32 base_l = 0, base_r = 0;
+    if (lane == 0)
+    {
+        if (bl) base_l = atomicAdd(counts, __popc(bl));
+        if (br) base_r = atomicAdd(counts + 1, __popc(br));
+    }
+    base_l = __shfl_sync(0xffffffffu, base_l, 0);
+    base_r = __shfl_sync(0xffffffffu, base_r, 0);
+    if (l) left_idx[base_l + __popc(bl & below)] = begin + k;
+    if (r) right_idx[base_r + __popc(br & below)] = begin + k;
+}
+
+extern "C" int sphb200_slab_select(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, const sphb200_vec4_t *pos, uint32_t begin,
+                                   uint32_t n, int plane_left, int plane_right, uint32_t *left_idx, uint32_t *right_idx,
+                                   uint32_t *counts, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && mesh && counts && (n == 0 || (pos && left_idx && right_idx)), "null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    SPH_CUDA(ctx, cudaMemsetAsync(counts, 0, 2 * sizeof(u32), st));
+    if (n == 0) return 0;
+    SPH_LAUNCH(ctx, k_slab_select, sph_blocks(n, 256), 256, 0, st, make_dmesh(mesh), (const float4 *)pos, begin, n, plane_left,
+               plane_right, left_idx, right_idx, counts);
+    return 0;
+}

@@ -74,6 +74,16 @@ extern "C" int sphb200_stream_create(void **stream)
     *stream = (void *)s;
     return (int)e;
 }
+extern "C" int sphb200_stream_create_with_priority(void **stream, int high_priority)
+{
+    int lo = 0, hi = 0; // numerically lower == higher priority
+    cudaError_t e = cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (e != cudaSuccess) return (int)e;
+    cudaStream_t s = nullptr;
+    e = cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, high_priority ? hi : lo);
+    *stream = (void *)s;
+    return (int)e;
+}
 extern "C" int sphb200_stream_destroy(void *stream) { return (int)cudaStreamDestroy((cudaStream_t)stream); }
 extern "C" int sphb200_event_create(void **event)
 {

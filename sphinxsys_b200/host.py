@@ -31,7 +31,7 @@ class Options(C.Structure):
                 ("device", C.c_int32), ("relation_stride", C.c_int32), ("system_lower", C.c_double * 3),
                 ("system_upper", C.c_double * 3), ("use_system_bounds", C.c_int32), ("legacy", C.c_int32), ("rank", C.c_int32),
                 ("nranks", C.c_int32), ("unique_id", C.c_uint8 * 128), ("surface_indicator", C.c_int32), ("observers", C.c_int32),
-                ("mu_f", C.c_double), ("transport_velocity", C.c_int32)]
+                ("mu_f", C.c_double), ("transport_velocity", C.c_int32), ("serial_exchange", C.c_int32)]
 
 
 class TaylorGreenOptions(C.Structure):
@@ -117,9 +117,10 @@ class DamBreakCK:
     def __init__(self, case=None, device_index=0, correction=False, fused_time_step=True, sort_interval=100,
                  relation_stride=None, fused_regularization=True, dim=3, dp=0.05, generate=False, rank=0, nranks=1,
                  unique_id=None, width_scale=1.0, legacy=False, surface_indicator=False, observers=False, mu_f=0.0,
-                 transport_velocity=False):
+                 transport_velocity=False, serial_exchange=False):
         self.lib = load()
         o = Options()
+        o.serial_exchange = int(bool(serial_exchange))
         if case is not None:
             dim, dp = case.dim, case.dp
             o.DL, o.DH, o.DW, o.LL, o.LH, o.LW = case.DL, case.DH, case.DW, case.LL, case.LH, case.LW

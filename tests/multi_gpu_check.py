@@ -28,6 +28,7 @@ def main():
     ap.add_argument("--dp", type=float, default=0.05)
     ap.add_argument("--outer", type=int, default=8)
     ap.add_argument("--out", default="")
+    ap.add_argument("--serial-exchange", action="store_true", help="plane exchange in line with the dynamics (no overlap)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -36,7 +37,7 @@ def main():
     uid = [host.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     sim = host.DamBreakCK(None, dim=3, dp=args.dp, generate=True, device_index=local, sort_interval=0, rank=rank, nranks=world,
-                          unique_id=uid[0])
+                          unique_id=uid[0], serial_exchange=args.serial_exchange)
     sim.initialize()
     n_ac = sim.run_outer(args.outer)
     mine = {"rid": sim.download_own("ReferenceID"), "pos": sim.download_own("Position"), "vel": sim.download_own("Velocity"),
