@@ -274,13 +274,10 @@ def run_ours(args, rank, world, local_rank):
         if decomposed:
             for nm in in_names:
                 solver.upload_own(nm, host_in[nm][1])   # own slots, storage order, from pinned memory
-            solver.exec("rebuild")
         else:
             for nm in in_names:
                 solver.upload(nm, host_in[nm][1])       # DiscreteVariable::synchronizeToDevice (reference order)
-            solver.exec("cell_list_fluid")
-        solver.exec("relations")
-        n = solver.step_outer()
+        n = solver.step_outer()                         # configuration update (cell list, relations) FIRST, then the dynamics
         if decomposed:
             for nm in out_names:
                 solver.download_own_into(nm, host_out[nm][1])
@@ -291,6 +288,9 @@ def run_ours(args, rank, world, local_rank):
         return n
 
     k_e2e = max(3, min(args.steps, 10))
+    # the state arrives from the host every step: build the cell list and the relations for it at the START of the step
+    # (DamBreakCK::ConfigurationUpdate::BeforeDynamics) instead of at its end — the same launches per step as `value`
+    solver.exec("configuration_before_dynamics", 1.0)
     if decomposed:
         e2e_step()
         barrier()
@@ -301,7 +301,7 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         sec = time.perf_counter() - t0
         e2e_note = ("per step: H2D of all evolving variables of the rank's own particles from pinned host memory, migration + "
-                    "cell-list + relation rebuild, one outer step, D2H of Position/Velocity/Density")
+                    "cell-list + relation rebuild for the uploaded state, the dynamics of one outer step, D2H of Position/Velocity/Density")
     else:
         # single GPU: the same host buffers go through the HostTransferPipeline of the host layer — H2D of step s+1 and
         # D2H of step s-1 run on a side stream while step s computes; every step's copies are inside the timed region
@@ -316,9 +316,7 @@ def run_ours(args, rank, world, local_rank):
                 solver.pipeline_commit_uploads()
                 if s_ + 1 < k:
                     solver.pipeline_stage_uploads(ins)   # next step's inputs: overlaps this step's dynamics
-                solver.exec("cell_list_fluid")
-                solver.exec("relations")
-                n_ac += solver.step_outer()
+                n_ac += solver.step_outer()              # configuration update first (state came from the host), then dynamics
                 solver.pipeline_stage_downloads(outs)    # overlaps the next step's dynamics
             solver.pipeline_synchronize()
             return n_ac

@@ -399,10 +399,41 @@ class DamBreakCK
         p.setActiveRange(own.begin, own.end);
     }
 
+    // dambreak.cpp:216-224: particle sort (every sort_interval steps), cell-linked list, relations, observers
+    void updateConfiguration(bool allow_sort)
+    {
+        // decomposed runs keep the initial global numbering (ParticleSortCK only renumbers: storage is cell ordered anyway)
+        if (allow_sort && !decomposition && q_.sort_interval > 0 && number_of_iterations % q_.sort_interval == 0 && number_of_iterations != 1)
+        {
+            particle_sort->exec();
+            fluid_acoustic_time_step->setPrimed(false); // Force/ForcePrior pairing changed (see ParticleSortCK)
+        }
+        if (decomposition) decomposition->rebuild(); // migration + ghost planes + cell-linked list
+        else water_cell_linked_list->exec();
+        water_block_update_complex_relation->exec();
+        if (fluid_observer_contact_relation)
+        {
+            fluid_observer_contact_relation->exec();
+            fluid_observer_pressure->writeToFile(number_of_iterations);
+        }
+    }
+
+    // Where the configuration update of an advection step runs. AfterDynamics is the reference loop (dambreak.cpp:188-224).
+    // BeforeDynamics serves callers that hand the particle state in from HOST buffers every step (bench.py e2e,
+    // HostTransferPipeline): the lists must be built for the state that was just uploaded, and building them again at
+    // the end of the step for a state that is about to be overwritten would be wasted work. Same launches per step.
+    enum class ConfigurationUpdate { AfterDynamics, BeforeDynamics };
+    ConfigurationUpdate configuration_update = ConfigurationUpdate::AfterDynamics;
+
     // one advection step, dambreak.cpp:188-222; returns the number of acoustic sub-steps taken
     int stepOuter()
     {
         if (q_.legacy) return stepOuterLegacy();
+        if (configuration_update == ConfigurationUpdate::BeforeDynamics)
+        {
+            updateConfiguration(false);
+            fluid_acoustic_time_step->setPrimed(false); // the state came from outside: no fused reduction to reuse
+        }
         fluid_density_summation->exec();
         if (!q_.fused_regularization) fluid_density_regularization->exec();
         water_advection_step_setup->exec();
@@ -445,20 +476,7 @@ class DamBreakCK
         acoustic_steps += n_inner;
         water_update_particle_position->exec();
         number_of_iterations++;
-        // decomposed runs keep the initial global numbering (ParticleSortCK only renumbers: storage is cell ordered anyway)
-        if (!decomposition && q_.sort_interval > 0 && number_of_iterations % q_.sort_interval == 0 && number_of_iterations != 1)
-        {
-            particle_sort->exec();
-            fluid_acoustic_time_step->setPrimed(false); // Force/ForcePrior pairing changed (see ParticleSortCK)
-        }
-        if (decomposition) decomposition->rebuild(); // migration + ghost planes + cell-linked list
-        else water_cell_linked_list->exec();
-        water_block_update_complex_relation->exec();
-        if (fluid_observer_contact_relation)
-        {
-            fluid_observer_contact_relation->exec();
-            fluid_observer_pressure->writeToFile(number_of_iterations);
-        }
+        if (configuration_update == ConfigurationUpdate::AfterDynamics) updateConfiguration(true);
         last_acoustic_dt = acoustic_dt;
         last_advection_dt = advection_dt;
         return n_inner;

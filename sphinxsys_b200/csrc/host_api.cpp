@@ -314,6 +314,8 @@ extern "C"
                 for (long k = 0; k < n; ++k) total += s.stepOuter();
                 r = (double)total;
             }
+            else if (op == "configuration_before_dynamics")
+                s.configuration_update = a0 != 0.0 ? DamBreakCK::ConfigurationUpdate::BeforeDynamics : DamBreakCK::ConfigurationUpdate::AfterDynamics;
             else if (op == "gravity") s.constant_gravity->exec();
             else if (op == "cell_list_fluid") s.water_cell_linked_list->exec();
             else if (op == "cell_list_wall") s.wall_cell_linked_list->exec();
