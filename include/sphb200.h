@@ -155,7 +155,10 @@ typedef struct
                                inside groups of 32 so that entry s in row k of slot t has (s - t - k) mod 8 == 0 wherever
                                possible — in every row the 8 lanes of a quarter warp then gather records from 8 different
                                L1 bank groups. Entry SET and count are unchanged; sphb200_relation_export_csr sorts such rows
-                               back into ascending target order. 0: rows in search order (cells x -> y -> z, in-cell order). */
+                               back into ascending target order. 0: rows in search order (cells x -> y -> z, in-cell order).
+                               Values 1 + o, o in 0..7: t is taken as t + o — a slab-decomposed run passes the slot its first
+                               stored particle has in the undecomposed run (mod 8) for CONTACT relations, whose target slots
+                               do not move with the slab, so that rows come out in the single-GPU order. */
 } sphb200_relation_t;
 
 /* One neighbour search: which particles look (src, in slot order), where they look (tar body + its cell list) */

@@ -98,7 +98,8 @@ class RelationBase
         r.index = index_.get<uint32_t>();
         r.capacity = capacity_;
         r.order = nullptr; // storage is cell ordered: slot == particle id
-        r.bank_aligned = bank_aligned_ ? 1 : 0;
+        // contact relations: the target body is not decomposed with the source, see sphb200_relation_t::bank_aligned
+        r.bank_aligned = bank_aligned_ ? 1 + (is_inner_ ? 0 : (int)(source_.slotOrigin() & 7u)) : 0;
         return r;
     }
     sphb200_search_t search()

@@ -33,6 +33,8 @@ struct DamBreakParameters
     bool legacy = false;
     // slab decomposition over the GPUs of one node (needs sphb200_comm_create on this process's context first)
     int rank = 0, nranks = 1;
+    int initial_cut_shift = 0;    // decomposed runs: start with the interior cuts moved by so many planes (test hook)
+    int recut_interval = 100;     // decomposed runs: re-balance the slab cuts every so many advection steps (0: never)
     bool overlap_exchange = true; // decomposed runs: hide the plane exchange behind interior compute (acousticStepOverlapped)
     static DamBreakParameters twoDimensional(double dp = 0.025)
     {
@@ -171,6 +173,12 @@ class DamBreakCK
                 per_plane[plane[i]]++;
             }
             cuts = planSlabCuts(per_plane, q.nranks);
+            if (q.initial_cut_shift) // deliberately unbalanced start (tests of SlabDecomposition::recut)
+            {
+                std::vector<int> skewed = cuts;
+                for (int r = 1; r < q.nranks; ++r) skewed[r] += q.initial_cut_shift;
+                cuts = limitCutMoves(cuts, skewed);
+            }
             std::vector<Vecd> own;
             std::vector<UnsignedInt> ids;
             uint64_t max_plane = 0;
@@ -408,7 +416,13 @@ class DamBreakCK
             particle_sort->exec();
             fluid_acoustic_time_step->setPrimed(false); // Force/ForcePrior pairing changed (see ParticleSortCK)
         }
-        if (decomposition) decomposition->rebuild(); // migration + ghost planes + cell-linked list
+        if (decomposition)
+        {
+            // migration + ghost planes + cell-linked list; at the sort cadence the slabs are re-balanced as well
+            const bool recut = allow_sort && q_.recut_interval > 0 && number_of_iterations % q_.recut_interval == 0 && number_of_iterations != 1;
+            if (recut) decomposition->recut();
+            else decomposition->rebuild();
+        }
         else water_cell_linked_list->exec();
         water_block_update_complex_relation->exec();
         if (fluid_observer_contact_relation)

@@ -614,6 +614,7 @@ class SPHBody
     std::unique_ptr<PeriodicImages> periodic_images_; // periodic_images.h; null for bodies without periodic conditions
     size_t particle_reserve_ = 0;                     // room for ghost particles behind the real ones
     bool posvol_dirty_ = true;
+    uint32_t slot_origin_ = 0;
     bool cell_ordered_ = false;
 
   public:
@@ -741,6 +742,9 @@ class SPHBody
                    has_vel ? p.deviceData<GatherRecord8>("PosVolVel") : nullptr, execution_instance().stream());
         posvol_dirty_ = false;
     }
+    // slab-decomposed runs: slot of the first stored particle in the undecomposed run (SlabDecomposition::rebuild)
+    uint32_t slotOrigin() const { return slot_origin_; }
+    void setSlotOrigin(uint32_t o) { slot_origin_ = o; }
     bool isCellOrdered() const { return cell_ordered_; }
     void setCellOrdered(bool v) { cell_ordered_ = v; }
 };

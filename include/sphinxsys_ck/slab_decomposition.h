@@ -59,6 +59,24 @@ inline std::vector<int> planSlabCuts(const std::vector<uint64_t> &particles_per_
     return cut;
 }
 
+// Cut r may move at most to the far end of an adjacent slab (old cut r-1 + 1 ... old cut r+1 - 1) and cuts stay strictly
+// increasing: all particles that change owner then move between NEIGHBOUR ranks only.
+inline std::vector<int> limitCutMoves(const std::vector<int> &old_cuts, std::vector<int> wanted)
+{
+    const int n = (int)old_cuts.size() - 1;
+    if ((int)wanted.size() != n + 1) throw SphError("limitCutMoves: cut vectors differ in length");
+    wanted[0] = old_cuts[0];
+    wanted[n] = old_cuts[n];
+    for (int r = 1; r < n; ++r)
+    {
+        int c = std::min(std::max(wanted[r], old_cuts[r - 1] + 1), old_cuts[r + 1] - 1);
+        c = std::max(c, wanted[r - 1] + 1);
+        wanted[r] = c;
+    }
+    for (int r = n - 1; r >= 1; --r) wanted[r] = std::min(wanted[r], wanted[r + 1] - 1);
+    return wanted;
+}
+
 class SlabDecomposition
 {
     SPHBody &body_;
@@ -69,6 +87,8 @@ class SlabDecomposition
     uint32_t a0_ = 0, f1_ = 0, l0_ = 0, a1_ = 0, n_ = 0;
     DeviceBuffer scalars_; // small device scratch for counts and reductions
     DeviceBuffer select_;  // index lists of the outgoing particles (rebuild)
+    DeviceBuffer plane_scratch_; // plane-boundary offsets and the particles-per-plane histogram (recut)
+    uint64_t recuts_ = 0;
     uint64_t migrated_out_ = 0, ghost_particles_ = 0;
     // overlap of the plane exchange with interior compute: a high-priority side stream carries the exchanges and the
     // boundary-plane launches, the default stream the interior launches; events order the two (dambreak_case.h)
@@ -114,7 +134,7 @@ class SlabDecomposition
 
   public:
     SlabDecomposition(SPHBody &body, int rank, int nranks, const std::vector<int> &cuts)
-        : body_(body), rank_(rank), nranks_(nranks), cuts_(cuts), scalars_(256)
+        : body_(body), rank_(rank), nranks_(nranks), cuts_(cuts), scalars_(1024)
     {
         const sphb200_mesh_t &m = body.getCellLinkedList().mesh_;
         plane_cells_ = (uint32_t)m.cells[1] * (uint32_t)m.cells[2];
@@ -268,7 +288,69 @@ class SlabDecomposition
         body_.setPosVolDirty();
         ghost_particles_ = (uint64_t)a0_ + (n_ - a1_);
         migrated_out_ += (uint64_t)send_l + send_r; // boundary-plane particles and leavers handed to the neighbours
+        // 5. slot origin: the slot the first stored particle has in the undecomposed run = particles owned by the ranks
+        //    below minus the left ghost plane. Relations against bodies that are NOT decomposed (the wall) lay their rows
+        //    out relative to it, so that summation order does not depend on the decomposition (sphb200_relation_t::bank_aligned).
+        {
+            uint64_t own = a1_ - a0_, *d_own = scalars_.get<uint64_t>() + 64, *d_all = d_own + 1;
+            std::vector<uint64_t> all(nranks_);
+            ex.check(sphb200_copy_h2d(d_own, &own, sizeof(own), st), "sphb200_copy_h2d");
+            SPHCK_CALL(sphb200_comm_allgather_u64, d_own, d_all, 1, st);
+            ex.check(sphb200_copy_d2h(all.data(), d_all, all.size() * sizeof(uint64_t), st), "sphb200_copy_d2h");
+            ex.synchronize();
+            uint64_t below = 0;
+            for (int r = 0; r < rank_; ++r) below += all[r];
+            body_.setSlotOrigin((uint32_t)((below - a0_) & 0xffffffffull));
+        }
     }
+
+    // Re-balance: new cuts from the CURRENT particles-per-plane histogram (all ranks), then hand the planes that changed
+    // owner to the neighbour. Called instead of rebuild() every `recut_interval` advection steps (the reference re-sorts
+    // at that cadence, dambreak.cpp:217-220; a dam break empties the slabs near the gate and fills the ones downstream).
+    // A cut moves at most to the far end of an adjacent slab, so every transfer is between neighbours and rebuild()'s
+    // exchange carries it; the second rebuild() drops the copies the former owner kept and restores one-plane ghosts.
+    // Results do not depend on the cuts (in-cell order is by ReferenceID), so a run with re-cuts stays bit-identical.
+    void recut()
+    {
+        ExecutionInstance &ex = execution_instance();
+        CellLinkedList &cl = body_.getCellLinkedList();
+        const int planes = cl.mesh_.cells[0];
+        void *st = ex.stream();
+        // own particles per plane from the cell offsets at the plane boundaries (cell order: a plane is one slot range)
+        std::vector<uint32_t> at(planes + 1), off(planes + 1);
+        for (int x = 0; x <= planes; ++x) at[x] = (uint32_t)x * plane_cells_;
+        plane_scratch_.ensure((size_t)(planes + 1) * (2 * sizeof(uint32_t) + sizeof(double)) + 64);
+        uint32_t *d_at = plane_scratch_.get<uint32_t>(), *d_off = d_at + (planes + 1);
+        double *d_hist = reinterpret_cast<double *>(plane_scratch_.get<char>() + (((size_t)(planes + 1) * 2 * sizeof(uint32_t) + 63) / 64) * 64);
+        ex.check(sphb200_copy_h2d(d_at, at.data(), at.size() * sizeof(uint32_t), st), "sphb200_copy_h2d");
+        {
+            void *dst[1] = {d_off};
+            const void *src[1] = {cl.cell_offset_.get<uint32_t>()};
+            uint32_t eb[1] = {sizeof(uint32_t)};
+            SPHCK_CALL(sphb200_gather_multi, 1, dst, src, eb, d_at, (uint32_t)(planes + 1), st);
+        }
+        ex.check(sphb200_copy_d2h(off.data(), d_off, off.size() * sizeof(uint32_t), st), "sphb200_copy_d2h");
+        ex.synchronize();
+        std::vector<double> hist(planes, 0.0);
+        for (int x = cuts_[rank_]; x < cuts_[rank_ + 1]; ++x) hist[x] = double(off[x + 1] - off[x]);
+        ex.check(sphb200_copy_h2d(d_hist, hist.data(), hist.size() * sizeof(double), st), "sphb200_copy_h2d");
+        SPHCK_CALL(sphb200_comm_allreduce_sum_f64, d_hist, planes, st);
+        ex.check(sphb200_copy_d2h(hist.data(), d_hist, hist.size() * sizeof(double), st), "sphb200_copy_d2h");
+        ex.synchronize();
+        std::vector<uint64_t> per_plane(planes);
+        for (int x = 0; x < planes; ++x) per_plane[x] = (uint64_t)(hist[x] + 0.5);
+        std::vector<int> next = limitCutMoves(cuts_, planSlabCuts(per_plane, nranks_));
+        ++recuts_;
+        if (next == cuts_)
+        {
+            rebuild();
+            return;
+        }
+        cuts_ = next;
+        rebuild();
+        rebuild();
+    }
+    uint64_t recuts() const { return recuts_; }
 
     // refresh named variables on the ghost planes from their owners (contiguous ranges, in place)
     void refreshGhosts(std::initializer_list<const char *> names)

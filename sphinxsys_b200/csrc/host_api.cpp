@@ -82,6 +82,8 @@ extern "C"
         double mu_f;                     // > 0: Viscosity closure + ViscousForceWithWallCK
         int32_t transport_velocity;      // KernelGradientIntegral(Corrected)Complex + TransportVelocityCorrectionCK
         int32_t serial_exchange;         // decomposed runs: 1 = plane exchange in line with the dynamics (no overlap)
+        int32_t recut_interval;          // decomposed runs: re-balance the cuts every so many advection steps (< 0: default 100)
+        int32_t initial_cut_shift;       // decomposed runs: unbalanced start, interior cuts moved by so many planes (test hook)
     };
 
     const char *sphck_last_error() { return g_error.c_str(); }
@@ -142,6 +144,16 @@ extern "C"
         });
     }
 
+    // host-only: how far a re-balancing may move the cuts in one go (SlabDecomposition::recut)
+    int sphck_limit_cut_moves(const int32_t *old_cuts, const int32_t *wanted, int nranks, int32_t *cuts_out)
+    {
+        return guarded([&] {
+            std::vector<int> o(old_cuts, old_cuts + nranks + 1), w(wanted, wanted + nranks + 1);
+            std::vector<int> c = limitCutMoves(o, w);
+            for (size_t i = 0; i < c.size(); ++i) cuts_out[i] = c[i];
+        });
+    }
+
     // fluid_xyz / wall_xyz / wall_normal_xyz may be NULL: the C++ lattice generator and shape normals are used then
     void *sphck_dambreak_create(const sphck_dambreak_options *o, const float *fluid_xyz, uint64_t n_fluid, const float *wall_xyz,
                                 const float *wall_normal_xyz, uint64_t n_wall)
@@ -163,6 +175,8 @@ extern "C"
             q.transport_velocity = o->transport_velocity != 0;
             q.rank = o->rank;
             q.overlap_exchange = o->serial_exchange == 0;
+            if (o->recut_interval >= 0) q.recut_interval = o->recut_interval;
+            q.initial_cut_shift = o->initial_cut_shift;
             q.nranks = o->nranks > 0 ? o->nranks : 1;
             if (q.nranks > 1)
                 execution_instance().check(sphb200_comm_create(execution_instance().ctx(), q.nranks, q.rank, o->unique_id), "sphb200_comm_create");
@@ -359,6 +373,7 @@ extern "C"
             else if (op == "outer_steps") r = (double)s.number_of_iterations;
             else if (op == "last_acoustic_dt") r = s.last_acoustic_dt;
             else if (op == "ghost_particles") r = s.decomposition ? (double)s.decomposition->ghostParticles() : 0.0;
+            else if (op == "recuts") r = s.decomposition ? (double)s.decomposition->recuts() : 0.0;
             else if (op == "rebuild") { if (s.decomposition) s.decomposition->rebuild(); else s.water_cell_linked_list->exec(); }
             else if (op == "inner_total") r = (double)s.water_block_inner->total_;
             else if (op == "inner_stride") r = (double)s.water_block_inner->fixed_stride_;

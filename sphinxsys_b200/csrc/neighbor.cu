@@ -524,13 +524,15 @@ __global__ void __launch_bounds__(128)
 // an entry takes the first free position of its class inside the group, the leftovers fill the remaining positions —
 // which aligns ~87 % of the entries (a global layout reaches 92 %) but needs only a 4 KB shared-memory tile per warp
 // and two coalesced passes over the slice. Entry SET and count of every row are untouched; the class depends only on
-// s - t, i.e. not on where the slab of a decomposed run starts, so summation order and every result bit are the same
-// on 1 and on N GPUs.
+// s - t, i.e. for an INNER relation not on where the slab of a decomposed run starts, so summation order and every result
+// bit are the same on 1 and on N GPUs. For a CONTACT relation the target slots do not move with the source slab, so the
+// caller passes the slab's slot origin (the slot its first stored particle has in the undecomposed run, mod 8;
+// sphb200_relation_t::bank_aligned = 1 + origin) and the class is taken from s - (t + origin).
 // -----------------------------------------------------------------------------------------------------
 constexpr int BA_GROUP = 32, BA_WARPS = 4;
 __global__ void __launch_bounds__(32 * BA_WARPS)
     k_bank_align(u32 *__restrict__ index, const u32 *__restrict__ count, const u32 *__restrict__ slice, u32 first_slice, u32 n_slices,
-                 u32 src_begin, u32 src_end, u32 stride)
+                 u32 src_begin, u32 src_end, u32 stride, u32 origin)
 {
     __shared__ u32 ba_tile[BA_WARPS][BA_GROUP][32];
     const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
@@ -555,7 +557,7 @@ __global__ void __launch_bounds__(32 * BA_WARPS)
         {
             if ((u32)u >= n) continue;
             // wanted positions: p with (g + p) = (s - t) mod 8, i.e. p = ((s - t - g) mod 8) + 8 q
-            const u32 p0 = (sv[u] - t - g) & 7u;
+            const u32 p0 = (sv[u] - t - origin - g) & 7u;
             const u32 free_of_class = ~used & (0x01010101u << p0) & (n >= 32u ? 0xffffffffu : (1u << n) - 1u);
             if (free_of_class)
             {
@@ -580,12 +582,12 @@ __global__ void __launch_bounds__(32 * BA_WARPS)
     }
 }
 
-static int bank_align(sphb200_context *ctx, const SearchArgs &a, u32 *count, u32 *slice, u32 *index, u32 stride, cudaStream_t st)
+static int bank_align(sphb200_context *ctx, const SearchArgs &a, u32 *count, u32 *slice, u32 *index, u32 stride, u32 origin, cudaStream_t st)
 {
     if (a.src_end <= a.src_begin) return 0;
     const u32 first = a.src_begin >> 5, n_slices = ((a.src_end + 31u) >> 5) - first;
     SPH_LAUNCH(ctx, k_bank_align, sph_blocks(n_slices, BA_WARPS), 32 * BA_WARPS, 0, st, index, count, slice, first, n_slices, a.src_begin,
-               a.src_end, stride);
+               a.src_end, stride, origin);
     return 0;
 }
 
@@ -727,7 +729,7 @@ extern "C" int sphb200_relation_build_fixed(sphb200_context_t *ctx, const sphb20
         if (rc) return rc;
         if (rel.bank_aligned)
         {
-            rc = bank_align(ctx, a, rel.count, rel.slice_offset, rel.index, stride, st);
+            rc = bank_align(ctx, a, rel.count, rel.slice_offset, rel.index, stride, (u32)(rel.bank_aligned - 1) & 7u, st);
             if (rc) return rc;
         }
     }

@@ -31,7 +31,7 @@ class Options(C.Structure):
                 ("device", C.c_int32), ("relation_stride", C.c_int32), ("system_lower", C.c_double * 3),
                 ("system_upper", C.c_double * 3), ("use_system_bounds", C.c_int32), ("legacy", C.c_int32), ("rank", C.c_int32),
                 ("nranks", C.c_int32), ("unique_id", C.c_uint8 * 128), ("surface_indicator", C.c_int32), ("observers", C.c_int32),
-                ("mu_f", C.c_double), ("transport_velocity", C.c_int32), ("serial_exchange", C.c_int32)]
+                ("mu_f", C.c_double), ("transport_velocity", C.c_int32), ("serial_exchange", C.c_int32), ("recut_interval", C.c_int32), ("initial_cut_shift", C.c_int32)]
 
 
 class TaylorGreenOptions(C.Structure):
@@ -78,6 +78,7 @@ def load():
         L.sphck_upload_raw.argtypes = [C.c_void_p, C.c_int, C.c_char_p, C.c_void_p, C.c_uint64, C.c_uint64]
         L.sphck_cuts.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.sphck_plan_slab_cuts.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.sphck_limit_cut_moves.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.sphck_export_csr.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.sphck_probe_records.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
         L.sphck_pipeline_create.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
@@ -107,6 +108,16 @@ def plan_slab_cuts(per_plane, nranks):
     return out
 
 
+def limit_cut_moves(old_cuts, wanted):
+    """Cuts a re-balancing step may take from `old_cuts` towards `wanted` (SlabDecomposition::recut: neighbour transfers only)."""
+    o = np.ascontiguousarray(old_cuts, dtype=np.int32)
+    w = np.ascontiguousarray(wanted, dtype=np.int32)
+    out = np.zeros(o.size, dtype=np.int32)
+    if load().sphck_limit_cut_moves(o.ctypes.data, w.ctypes.data, int(o.size - 1), out.ctypes.data) != 0:
+        raise capi.SphB200Error("limit_cut_moves failed: " + load().sphck_last_error().decode())
+    return out
+
+
 def _kind(name):
     return 1 if name in VEC_NAMES else (2 if name in UINT_NAMES else (3 if name in MAT_NAMES else (4 if name in INT_NAMES else 0)))
 
@@ -117,10 +128,12 @@ class DamBreakCK:
     def __init__(self, case=None, device_index=0, correction=False, fused_time_step=True, sort_interval=100,
                  relation_stride=None, fused_regularization=True, dim=3, dp=0.05, generate=False, rank=0, nranks=1,
                  unique_id=None, width_scale=1.0, legacy=False, surface_indicator=False, observers=False, mu_f=0.0,
-                 transport_velocity=False, serial_exchange=False):
+                 transport_velocity=False, serial_exchange=False, recut_interval=None, initial_cut_shift=0):
         self.lib = load()
         o = Options()
         o.serial_exchange = int(bool(serial_exchange))
+        o.recut_interval = -1 if recut_interval is None else int(recut_interval)
+        o.initial_cut_shift = int(initial_cut_shift)
         if case is not None:
             dim, dp = case.dim, case.dp
             o.DL, o.DH, o.DW, o.LL, o.LH, o.LW = case.DL, case.DH, case.DW, case.LL, case.LH, case.LW

@@ -4,9 +4,12 @@
         tests/multi_gpu_check.py [--dp 0.05] [--outer 8] [--out gpurun_out/multi_gpu_check.json]
 
 Checks (rank 0): every global particle id is owned by exactly one rank after K advection steps (nothing lost or
-duplicated by migration), both runs took the same number of acoustic sub-steps, and positions, velocities and
-densities are IDENTICAL bit for bit: ghosts are exact copies, neighbour rows have the same order (cell, then global
-id) and the time-step reductions are exact maxima.
+duplicated by migration), both runs took the same number of acoustic sub-steps and reached the same physical time, and
+positions, velocities and densities are IDENTICAL bit for bit: ghosts are exact copies, neighbour rows have the same
+order (cell, then global id; bank-aligned rows are laid out relative to the slab's slot origin) and the time-step
+reductions are exact maxima. `--tolerance` relaxes the pass criterion to the fp32 summation-order tolerance SURVEY.md
+§8e asks for (1e-5 of the field maximum); `--trace` compares every registered variable after every advection step and
+reports where the first bit differs (that is how the slot-origin dependence of the contact rows was found).
 """
 import argparse
 import json
@@ -28,6 +31,11 @@ def main():
     ap.add_argument("--dp", type=float, default=0.05)
     ap.add_argument("--outer", type=int, default=8)
     ap.add_argument("--out", default="")
+    ap.add_argument("--recut-interval", type=int, default=5, help="re-balance the slab cuts every so many advection steps")
+    ap.add_argument("--cut-shift", type=int, default=0, help="start with the interior cuts moved by so many planes (the re-cuts undo it)")
+    ap.add_argument("--strict", action="store_true", help="(default) pass only if the fields are bit-identical to the single-GPU run")
+    ap.add_argument("--tolerance", action="store_true", help="pass if the fields agree within 1e-5 of the field maximum (SURVEY §8e) instead")
+    ap.add_argument("--trace", action="store_true", help="compare after EVERY advection step and report where the first difference appears")
     ap.add_argument("--serial-exchange", action="store_true", help="plane exchange in line with the dynamics (no overlap)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -37,12 +45,75 @@ def main():
     uid = [host.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
     sim = host.DamBreakCK(None, dim=3, dp=args.dp, generate=True, device_index=local, sort_interval=0, rank=rank, nranks=world,
-                          unique_id=uid[0], serial_exchange=args.serial_exchange)
+                          unique_id=uid[0], serial_exchange=args.serial_exchange, recut_interval=args.recut_interval, initial_cut_shift=args.cut_shift)
     sim.initialize()
+    cuts0 = sim.cuts().tolist()
+    if args.trace:
+        ref, prev_owner = None, None
+        if rank == 0:
+            ref = host.DamBreakCK(None, dim=3, dp=args.dp, generate=True, device_index=local, sort_interval=0)
+            ref.initialize()
+        for step in range(1, args.outer + 1):
+            sim.run_outer(1)
+            TRACED = (("rid", "ReferenceID"), ("pos", "Position"), ("vel", "Velocity"), ("rho", "Density"), ("force", "Force"),
+                      ("fprior", "ForcePrior"), ("mass", "Mass"), ("C", "Compression"), ("Cdot", "CompressionRate"),
+                      ("vol", "VolumetricMeasure"), ("volref", "VolumetricMeasureRef"), ("p", "Pressure"), ("dpos", "Displacement"))
+            mine = {k: sim.download_own(v) for k, v in TRACED}
+            mine["cuts"], mine["range"] = sim.cuts().tolist(), sim.own_range()
+            mine["rel"] = [sim.exec("inner_max_count"), sim.exec("inner_stride")]
+            parts = [None] * world if rank == 0 else None
+            dist.gather_object(mine, parts, dst=0)
+            stop = [False]
+            if rank == 0:
+                ref.run_outer(1)
+                rid = np.concatenate([p["rid"] for p in parts])
+                owner = np.concatenate([np.full(p["rid"].size, r) for r, p in enumerate(parts)])
+                print("MULTI_GPU_REL", step, [p["rel"] for p in parts], [ref.exec("inner_max_count"), ref.exec("inner_stride")], flush=True)
+                bad = {}
+                for key, name in TRACED[1:]:
+                    single = ref.download(name)
+                    glob = np.zeros_like(single)
+                    glob[rid] = np.concatenate([p[key] for p in parts])
+                    ne = glob.view(np.uint32) != single.view(np.uint32)
+                    bad[name] = np.flatnonzero(ne.reshape(single.shape[0], -1).any(axis=1))
+                po = np.zeros(rid.size, dtype=np.int64)
+                po[rid] = owner
+                if prev_owner is None:
+                    prev_owner = []
+                prev_owner.append(po)
+                if any(b.size for b in bad.values()):
+                    x = ref.download("Position")[:, 0]
+                    own_of = np.zeros(rid.size, dtype=np.int64)
+                    own_of[rid] = owner
+                    rep_moved = []
+                    for back in (3, 2, 1):  # owner changes in the rebuilds that ended steps s-2, s-1, s
+                        if len(prev_owner) > back:
+                            a_, b_ = prev_owner[-back - 1], prev_owner[-back]
+                            moved = np.flatnonzero(a_ != b_)
+                            rep_moved.append({"rebuild_of_step": step - back + 1, "count": int(moved.size), "ids": moved[:16].tolist(),
+                                              "x": [round(float(v), 4) for v in x[moved[:16]]], "from": a_[moved[:16]].tolist(), "to": b_[moved[:16]].tolist()})
+                    rep = {"first_bad_step": step, "cuts": parts[0]["cuts"], "ranges": [list(map(int, p["range"])) for p in parts],
+                           "changed_owner_in_previous_rebuild": rep_moved}
+                    for name, b in bad.items():
+                        if b.size:
+                            rep[name] = {"count": int(b.size), "x_min": float(x[b].min()), "x_max": float(x[b].max()),
+                                         "owners": np.bincount(own_of[b], minlength=world).tolist(), "ids": b[:12].tolist()}
+                    print("MULTI_GPU_TRACE " + json.dumps(rep), flush=True)
+                    if args.out:
+                        json.dump(rep, open(args.out, "w"), indent=1)
+                    stop[0] = True
+            dist.broadcast_object_list(stop, src=0)
+            if stop[0]:
+                break
+        else:
+            if rank == 0:
+                print("MULTI_GPU_TRACE " + json.dumps({"first_bad_step": None, "steps": args.outer}), flush=True)
+        dist.destroy_process_group()
+        sys.exit(0)
     n_ac = sim.run_outer(args.outer)
     mine = {"rid": sim.download_own("ReferenceID"), "pos": sim.download_own("Position"), "vel": sim.download_own("Velocity"),
-            "rho": sim.download_own("Density"), "n_ac": n_ac, "range": sim.own_range(), "cuts": sim.cuts().tolist(),
-            "energy": sim.energy(), "time": sim.physical_time}
+            "rho": sim.download_own("Density"), "cuts0": cuts0, "n_ac": n_ac, "range": sim.own_range(), "cuts": sim.cuts().tolist(),
+            "energy": sim.energy(), "time": sim.physical_time, "recuts": sim.exec("recuts")}
     parts = [None] * world if rank == 0 else None
     dist.gather_object(mine, parts, dst=0)
     ok, report = True, {}
@@ -56,6 +127,8 @@ def main():
         report["owned_per_rank"] = [int(p["rid"].size) for p in parts]
         report["stored_per_rank"] = [int(p["range"][2]) for p in parts]
         report["cuts"] = parts[0]["cuts"]
+        report["initial_cuts"] = parts[0]["cuts0"]
+        report["recuts"] = int(parts[0]["recuts"])
         report["acoustic_steps"] = [int(p["n_ac"]) for p in parts] + [int(n_ref)]
         ok &= rid.size == n and np.array_equal(np.sort(rid), np.arange(n, dtype=np.uint32))
         ok &= all(p["n_ac"] == n_ref for p in parts)
@@ -66,7 +139,9 @@ def main():
             diff = float(np.max(np.abs(glob.astype(np.float64) - single.astype(np.float64)))) if n else 0.0
             report[f"max_abs_diff_{name}"] = diff
             report[f"bitwise_equal_{name}"] = bool(np.array_equal(glob.view(np.uint32), single.view(np.uint32)))
-            ok &= report[f"bitwise_equal_{name}"]
+            scale = float(np.max(np.abs(single))) if n else 1.0
+            report[f"rel_diff_{name}"] = diff / scale if scale else 0.0
+            ok &= report[f"rel_diff_{name}"] <= 1e-5 if args.tolerance else report[f"bitwise_equal_{name}"]
         e_ref = ref.energy()
         report["energy"] = [parts[0]["energy"], e_ref]
         ok &= abs(parts[0]["energy"] - e_ref) <= 1e-9 * abs(e_ref)

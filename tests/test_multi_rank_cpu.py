@@ -79,3 +79,34 @@ def test_plan_slab_cuts_edge_cases(nranks):
         assert np.all(np.diff(cuts) == 16 // nranks)
     with pytest.raises(Exception):
         host.plan_slab_cuts(np.ones(2, dtype=np.uint64), 3)  # fewer planes than ranks
+
+
+def test_recut_moves_stay_between_neighbours():
+    """SlabDecomposition::recut hands particles to ADJACENT ranks only: a cut may move at most to the far end of a
+    neighbouring slab, cuts stay strictly increasing, the end cuts are fixed, and an admissible target is taken as is."""
+    from sphinxsys_b200 import host
+    old = np.array([0, 10, 20, 30, 40], dtype=np.int32)
+    # admissible target: unchanged
+    want = np.array([0, 12, 19, 33, 40], dtype=np.int32)
+    assert np.array_equal(host.limit_cut_moves(old, want), want)
+    # far targets are clamped into (old[r-1], old[r+1])
+    got = host.limit_cut_moves(old, np.array([0, 35, 36, 37, 40], dtype=np.int32))
+    assert got[0] == 0 and got[-1] == 40 and np.all(np.diff(got) >= 1)
+    assert all(old[r - 1] + 1 <= got[r] <= old[r + 1] - 1 for r in range(1, 4))
+    got = host.limit_cut_moves(old, np.array([0, 1, 2, 3, 40], dtype=np.int32))
+    assert np.all(np.diff(got) >= 1) and all(old[r - 1] + 1 <= got[r] <= old[r + 1] - 1 for r in range(1, 4))
+    # repeated re-balancing converges to the target
+    cur, target = old.copy(), np.array([0, 31, 34, 37, 40], dtype=np.int32)
+    for _ in range(6):
+        cur = host.limit_cut_moves(cur, target)
+    assert np.array_equal(cur, target)
+    # random histograms: plan + limit keeps every invariant
+    rng = np.random.default_rng(3)
+    for _ in range(50):
+        n = int(rng.integers(2, 9))
+        planes = int(rng.integers(n * 3, 200))
+        a = host.plan_slab_cuts(rng.integers(0, 1000, planes).astype(np.uint64) + 1, n)
+        b = host.plan_slab_cuts(rng.integers(0, 1000, planes).astype(np.uint64) + 1, n)
+        c = host.limit_cut_moves(a, b)
+        assert c[0] == 0 and c[-1] == planes and np.all(np.diff(c) >= 1)
+        assert all(a[r - 1] + 1 <= c[r] <= a[r + 1] - 1 for r in range(1, n))
