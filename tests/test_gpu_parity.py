@@ -510,6 +510,56 @@ def test_sort_permutation_properties_full_size(ctx):
     assert np.all(np.diff(p)[ties] > 0)
 
 
+def test_slab_select_primitive(ctx, oracle_lib):
+    """sphb200_slab_select (what a neighbour rank needs of the own slots): exactly the slots whose x cell plane — the
+    oracle's CellIndexFromPosition — is <= plane_left (left list) / >= plane_right (right list); list order is free."""
+    from sphinxsys_b200 import capi, cases
+    case = cases.dam_break(dim=3, dp=0.05)
+    pos = np.concatenate([case.fluid_pos, _random_positions(case, 30_000, 5)])
+    n = pos.shape[0]
+    ref_cell, _ = oracle_lib.cell_keys(pos, case.mesh)
+    cy, cz = int(case.mesh.cells[1]), int(case.mesh.cells[2])
+    plane = (ref_cell.astype(np.int64) // (cy * cz)).astype(np.int64)
+    p4 = torch.zeros((n, 4), dtype=torch.float32, device="cuda")
+    p4[:, :3] = torch.from_numpy(pos).cuda()
+    m = capi.mesh_t(case.mesh)
+    begin, cnt = 1000, n - 3000
+    for pl, pr in ((10, 20), (-1, 15), (12, -1), (25, 25), (-1, -1)):
+        left = torch.full((cnt + 1,), -1, dtype=torch.int32, device="cuda")
+        right = torch.full((cnt + 1,), -1, dtype=torch.int32, device="cuda")
+        counts = torch.full((2,), 77, dtype=torch.int32, device="cuda")
+        ctx.call("sphb200_slab_select", C.byref(m), _p(p4), begin, cnt, pl, pr, _p(left), _p(right), _p(counts), _s())
+        nl, nr = (int(v) for v in counts.cpu().numpy())
+        own = np.arange(begin, begin + cnt)
+        want_l = own[plane[own] <= pl] if pl >= 0 else own[:0]
+        want_r = own[plane[own] >= pr] if pr >= 0 else own[:0]
+        assert nl == want_l.size and nr == want_r.size
+        assert np.array_equal(np.sort(left[:nl].cpu().numpy()), want_l)
+        assert np.array_equal(np.sort(right[:nr].cpu().numpy()), want_r)
+
+
+def test_configuration_update_before_dynamics_is_the_same_step():
+    """DamBreakCK::ConfigurationUpdate::BeforeDynamics (bench.py e2e: the state comes from the host, so the cell list and
+    the relations are built at the START of the step) runs the same launches as the reference loop order and leaves the
+    same particle state, bit for bit — including the acoustic-dt reductions, which are then stand-alone instead of fused."""
+    from sphinxsys_b200 import cases
+    case = cases.dam_break(dim=3, dp=0.05)
+    pos, vel = perturb_state(case)
+    case.fluid_pos = pos
+    runs = []
+    for before in (False, True):
+        gpu = make_gpu(case, fused_time_step=True, sort_interval=0)
+        gpu.upload("Velocity", vel)
+        gpu.initialize()
+        if before:
+            gpu.exec("configuration_before_dynamics", 1.0)
+        n_ac = sum(gpu.step_outer() for _ in range(4))
+        runs.append((n_ac, gpu.physical_time, {nm: gpu.download(nm) for nm in ("Position", "Velocity", "Density")}))
+    assert runs[0][0] == runs[1][0] and runs[0][1] == runs[1][1]
+    for nm in ("Position", "Velocity", "Density"):
+        assert np.array_equal(runs[0][2][nm].view(np.uint32), runs[1][2][nm].view(np.uint32)), nm
+
+
 def test_slab_decomposed_run_matches_single_gpu():
     """2 ranks (x-slab decomposition, NCCL halo exchange of contiguous plane ranges) vs 1 GPU: bit-identical fields,
     no particle lost or duplicated. Needs 2 GPUs (skipped on a 1-GPU box; run by scripts/gpu_multi.sh)."""
