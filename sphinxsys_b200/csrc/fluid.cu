@@ -317,6 +317,10 @@ __device__ __forceinline__ void for_neighbors(const u32 *__restrict__ idx, u32 c
         for (int u = 0; u < U; ++u) j[u] = jn[u];
     }
 }
+#ifndef SPH_SUM_U
+#define SPH_SUM_U 4
+#endif
+constexpr int SUM_U = SPH_SUM_U; // the summation kernel is light on registers (32): deeper batches are affordable there
 constexpr int NB_WALL_U = 2; // wall pairs need up to three records each: smaller batches keep the kernels spill-free
 
 // RiemannSolver<...>::ComputingKernel::DissipativePJump, riemann_solver_ck.hpp:44-49
@@ -607,9 +611,9 @@ __global__ void __launch_bounds__(FL_THREADS) k_compression_summation(FArgs a, K
     {
         u32 cnt = a.in_count[t];
         const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
-        float4 xj[NB_U];
+        float4 xj[SUM_U];
         const bool legacy = a.legacy != 0;
-        for_neighbors(
+        for_neighbors<SUM_U>(
             idx, cnt, [&](int u, u32 j) { xj[u] = a.posvolref[j]; },
             [&](int u, bool valid) {
                 float dx = xi.x - xj[u].x, dy = xi.y - xj[u].y, dz = xi.z - xj[u].z;

@@ -394,37 +394,66 @@ __global__ void __launch_bounds__(RS_THREADS)
     hist[(u64)threadIdx.x * ntiles + blockIdx.x] = cnt[threadIdx.x];
 }
 
+// Stable scatter of one tile (RS_TILE pairs). The tile is first brought into digit order in shared memory — local
+// position = exclusive tile histogram of the digit + pairs of that digit in earlier rounds/warps + rank inside the warp
+// (warp match) — and then written out by sorted position: pairs of one digit leave as one contiguous run (16 pairs =
+// 64 bytes on average) instead of one 4-byte store per 32-byte sector, which is what bounded the direct scatter
+// (1.0 ms for 16.7 M pairs, 17 % of the HBM peak; profiles/r01_config5_microbench.json).
 __global__ void __launch_bounds__(RS_THREADS)
     k_rs_scatter(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u32 *__restrict__ keys_out,
                  u32 *__restrict__ vals_out, u64 n, int shift, const u32 *__restrict__ hist, u32 ntiles)
 {
-    __shared__ u32 base[256];
+    __shared__ u32 gbase[256];           // where the tile's pairs of digit d start in the output
+    __shared__ u32 lbase[256];           // running local position of digit d (starts at the exclusive tile histogram)
+    __shared__ u32 lstart[256];          // exclusive tile histogram
     __shared__ u32 wcnt[RS_WARPS][256];
+    __shared__ u32 skey[RS_TILE], sval[RS_TILE];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    base[threadIdx.x] = hist[(u64)threadIdx.x * ntiles + blockIdx.x];
+    const u64 tile_base = (u64)blockIdx.x * RS_TILE;
+    const u32 in_tile = (u32)min((u64)RS_TILE, n - tile_base);
+    {
+        // tile histogram from the scanned global one: hist is [digit][tile], exclusive over the whole array
+        const u64 at = (u64)threadIdx.x * ntiles + blockIdx.x;
+        const u32 here = hist[at];
+        const u32 next = at + 1 < (u64)256 * ntiles ? hist[at + 1] : (u32)n;
+        gbase[threadIdx.x] = here;
+        const u32 c = next - here;
+        // exclusive scan of the 256 counts: warp scan + scan of the 8 warp totals
+        u32 incl = c;
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) wcnt[w][threadIdx.x] = 0;
+        for (int o = 1; o < 32; o <<= 1)
+        {
+            u32 v = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += v;
+        }
+        __shared__ u32 wtot[RS_WARPS];
+        if (lane == 31) wtot[wid] = incl;
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w) wcnt[w][threadIdx.x] = 0;
+        __syncthreads();
+        u32 off = 0;
+        for (int w = 0; w < wid; ++w) off += wtot[w];
+        lstart[threadIdx.x] = lbase[threadIdx.x] = off + incl - c;
+    }
     __syncthreads();
-    u64 tile_base = (u64)blockIdx.x * RS_TILE;
 #pragma unroll 1
     for (int r = 0; r < RS_ITEMS; ++r)
     {
-        u64 idx = tile_base + (u64)r * RS_THREADS + threadIdx.x;
-        bool valid = idx < n;
-        u32 key = valid ? keys_in[idx] : 0u;
-        u32 val = valid ? vals_in[idx] : 0u;
-        u32 d = (key >> shift) & 255u;
-        u32 peers = __match_any_sync(0xffffffffu, valid ? d : (0x100u | (u32)lane));
-        u32 rank = __popc(peers & ((1u << lane) - 1u));
+        const u32 k = (u32)r * RS_THREADS + threadIdx.x;
+        const bool valid = k < in_tile;
+        const u32 key = valid ? keys_in[tile_base + k] : 0u;
+        const u32 val = valid ? vals_in[tile_base + k] : 0u;
+        const u32 d = (key >> shift) & 255u;
+        const u32 peers = __match_any_sync(0xffffffffu, valid ? d : (0x100u | (u32)lane));
+        const u32 rank = __popc(peers & ((1u << lane) - 1u));
         if (valid && rank == 0) wcnt[wid][d] = __popc(peers);
         __syncthreads();
         if (valid)
         {
-            u32 off = base[d];
+            u32 off = lbase[d];
             for (int w = 0; w < wid; ++w) off += wcnt[w][d];
-            u32 pos = off + rank;
-            keys_out[pos] = key;
-            vals_out[pos] = val;
+            skey[off + rank] = key;
+            sval[off + rank] = val;
         }
         __syncthreads();
         {
@@ -435,9 +464,19 @@ __global__ void __launch_bounds__(RS_THREADS)
                 s += wcnt[w][threadIdx.x];
                 wcnt[w][threadIdx.x] = 0;
             }
-            base[threadIdx.x] += s;
+            lbase[threadIdx.x] += s;
         }
         __syncthreads();
+    }
+    // write out by sorted position: consecutive threads -> consecutive output addresses inside a digit run
+#pragma unroll 4
+    for (u32 k = threadIdx.x; k < in_tile; k += RS_THREADS)
+    {
+        const u32 key = skey[k];
+        const u32 d = (key >> shift) & 255u;
+        const u32 pos = gbase[d] + (k - lstart[d]);
+        keys_out[pos] = key;
+        vals_out[pos] = sval[k];
     }
 }
 
