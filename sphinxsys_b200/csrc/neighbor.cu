@@ -295,6 +295,50 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// One lane's column of a SELL slice brought into the bank-aligned layout (see "L1-bank-aligned rows" below): `col` is the
+// lane's first entry (entries 32 apart), `tile` its column of a [32][32] shared-memory tile (entries 32 apart: bank ==
+// lane), c its row count, cmax the warp's. Every lane only touches its own column of the tile and of the slice, so no
+// warp synchronisation is needed — also not against the stores the same lane made to `col` earlier in the kernel.
+constexpr int BA_GROUP = 32;
+__device__ __forceinline__ void bank_align_column(u32 *__restrict__ col, u32 *__restrict__ tile, u32 c, u32 cmax, u32 t, u32 origin)
+{
+    for (u32 g = 0; g < cmax; g += BA_GROUP)
+    {
+        // rows [g, g + 32) of the warp: coalesced 128-byte loads, all independent (rows < cmax exist for every lane)
+        u32 sv[BA_GROUP];
+#pragma unroll
+        for (int u = 0; u < BA_GROUP; ++u) sv[u] = g + u < cmax ? col[32ull * (g + u)] : 0u;
+        const u32 n = c > g ? min(c - g, (u32)BA_GROUP) : 0u; // entries of this lane in the group
+        u32 used = 0, waiting = 0;                               // positions taken / entries not yet placed
+#pragma unroll
+        for (int u = 0; u < BA_GROUP; ++u)
+        {
+            if ((u32)u >= n) continue;
+            // wanted positions: p with (g + p) = (s - t) mod 8, i.e. p = ((s - t - g) mod 8) + 8 q
+            const u32 p0 = (sv[u] - t - origin - g) & 7u;
+            const u32 free_of_class = ~used & (0x01010101u << p0) & (n >= 32u ? 0xffffffffu : (1u << n) - 1u);
+            if (free_of_class)
+            {
+                const u32 p = __ffs(free_of_class) - 1u;
+                tile[32u * p] = sv[u];
+                used |= 1u << p;
+            }
+            else
+                waiting |= 1u << u;
+        }
+#pragma unroll
+        for (int u = 0; u < BA_GROUP; ++u)
+        {
+            if (!((waiting >> u) & 1u)) continue;
+            const u32 p = __ffs(~used) - 1u; // lowest free position (< n: as many free positions as waiting entries)
+            tile[32u * p] = sv[u];
+            used |= 1u << p;
+        }
+#pragma unroll 8
+        for (u32 p = 0; p < n; ++p) col[32ull * (g + p)] = tile[32u * p];
+    }
+}
+
 // packed fp32x2 arithmetic (sm_100: FADD2 / FFMA2 — two IEEE fp32 operations per issue slot)
 __device__ __forceinline__ unsigned long long pk2(float lo, float hi)
 {
@@ -333,7 +377,7 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 template <bool INNER, int MODE, bool TWO>
 __global__ void __launch_bounds__(128)
     k_relation_ordered(SearchArgs a, u32 *__restrict__ count, u32 *__restrict__ slice, u32 *__restrict__ index, u64 capacity,
-                       u32 stride, u32 *__restrict__ max_count)
+                       u32 stride, u32 *__restrict__ max_count, int align_origin)
 {
     constexpr int CH = 32; // candidates tested per chunk; hits of a chunk are collected in a per-lane bit mask
     constexpr int NW = 32; // chunk masks a lane may hold back before its hits are written out
@@ -495,6 +539,13 @@ __global__ void __launch_bounds__(128)
     }
     }
     if (MODE != 0) flush();
+    // bank-aligned rows (align_origin >= 0): the warp re-lays out the rows it has just written while they are still in
+    // L2 — the stand-alone pass (k_bank_align) streamed the whole index array from and to DRAM once more
+    if (MODE == 2 && align_origin >= 0)
+    {
+        const u32 cw = active ? min(c, row_limit) : 0u;
+        bank_align_column(out, my_mask, cw, warp_max_u32(cw), t, (u32)align_origin);
+    }
     if (MODE != 1 && active) count[t] = c;
     if (MODE == 0)
     {
@@ -529,7 +580,7 @@ __global__ void __launch_bounds__(128)
 // caller passes the slab's slot origin (the slot its first stored particle has in the undecomposed run, mod 8;
 // sphb200_relation_t::bank_aligned = 1 + origin) and the class is taken from s - (t + origin).
 // -----------------------------------------------------------------------------------------------------
-constexpr int BA_GROUP = 32, BA_WARPS = 4;
+constexpr int BA_WARPS = 4;
 __global__ void __launch_bounds__(32 * BA_WARPS)
     k_bank_align(u32 *__restrict__ index, const u32 *__restrict__ count, const u32 *__restrict__ slice, u32 first_slice, u32 n_slices,
                  u32 src_begin, u32 src_end, u32 stride, u32 origin)
@@ -538,48 +589,10 @@ __global__ void __launch_bounds__(32 * BA_WARPS)
     const u32 lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
     const u32 sl = first_slice + blockIdx.x * BA_WARPS + w;
     if (sl >= first_slice + n_slices) return;
-    u32 *tile = &ba_tile[w][0][lane]; // this lane's column: entry of position p at tile[32 p] (bank == lane: conflict free)
     const u32 t = sl * 32u + lane;
     const bool active = t >= src_begin && t < src_end;
     const u32 c = active ? min(count[t], stride) : 0u;
-    const u32 cmax = warp_max_u32(c);
-    u32 *col = index + (u64)slice[sl] + lane;
-    for (u32 g = 0; g < cmax; g += BA_GROUP)
-    {
-        // rows [g, g + 32) of the warp: coalesced 128-byte loads, all independent (rows < cmax exist for every lane)
-        u32 sv[BA_GROUP];
-#pragma unroll
-        for (int u = 0; u < BA_GROUP; ++u) sv[u] = g + u < cmax ? col[32ull * (g + u)] : 0u;
-        const u32 n = c > g ? min(c - g, (u32)BA_GROUP) : 0u; // entries of this lane in the group
-        u32 used = 0, waiting = 0;                               // positions taken / entries not yet placed
-#pragma unroll
-        for (int u = 0; u < BA_GROUP; ++u)
-        {
-            if ((u32)u >= n) continue;
-            // wanted positions: p with (g + p) = (s - t) mod 8, i.e. p = ((s - t - g) mod 8) + 8 q
-            const u32 p0 = (sv[u] - t - origin - g) & 7u;
-            const u32 free_of_class = ~used & (0x01010101u << p0) & (n >= 32u ? 0xffffffffu : (1u << n) - 1u);
-            if (free_of_class)
-            {
-                const u32 p = __ffs(free_of_class) - 1u;
-                tile[32u * p] = sv[u];
-                used |= 1u << p;
-            }
-            else
-                waiting |= 1u << u;
-        }
-#pragma unroll
-        for (int u = 0; u < BA_GROUP; ++u)
-        {
-            if (!((waiting >> u) & 1u)) continue;
-            const u32 p = __ffs(~used) - 1u; // lowest free position (< n: as many free positions as waiting entries)
-            tile[32u * p] = sv[u];
-            used |= 1u << p;
-        }
-        // every lane only touches its own column of the tile and of the slice: no warp synchronisation is needed
-#pragma unroll 8
-        for (u32 p = 0; p < n; ++p) col[32ull * (g + p)] = tile[32u * p];
-    }
+    bank_align_column(index + (u64)slice[sl] + lane, &ba_tile[w][0][lane], c, warp_max_u32(c), t, origin);
 }
 
 static int bank_align(sphb200_context *ctx, const SearchArgs &a, u32 *count, u32 *slice, u32 *index, u32 stride, u32 origin, cudaStream_t st)
@@ -635,8 +648,9 @@ static int make_search(sphb200_context *ctx, const sphb200_search_t *s, SearchAr
 
 template <int MODE>
 static int launch_relation(sphb200_context *ctx, const SearchArgs &a, bool inner, u32 *count, u32 *slice, u32 *index, u64 cap,
-                           u32 stride, u32 *max_count, cudaStream_t st)
+                           u32 stride, u32 *max_count, cudaStream_t st, int align_origin = -1, bool *aligned = nullptr)
 {
+    if (aligned) *aligned = a.cell_ordered && MODE == 2 && align_origin >= 0;
     if (a.src_end <= a.src_begin) return 0;
     unsigned g = search_blocks(a, 128);
     bool sorted = a.tar_sorted_pos != nullptr;
@@ -644,11 +658,11 @@ static int launch_relation(sphb200_context *ctx, const SearchArgs &a, bool inner
     {
         if (a.tar2_pos)
         {
-            if (inner) SPH_LAUNCH(ctx, (k_relation_ordered<true, MODE, true>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
-            else SPH_LAUNCH(ctx, (k_relation_ordered<false, MODE, true>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
+            if (inner) SPH_LAUNCH(ctx, (k_relation_ordered<true, MODE, true>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count, align_origin);
+            else SPH_LAUNCH(ctx, (k_relation_ordered<false, MODE, true>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count, align_origin);
         }
-        else if (inner) SPH_LAUNCH(ctx, (k_relation_ordered<true, MODE, false>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
-        else SPH_LAUNCH(ctx, (k_relation_ordered<false, MODE, false>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
+        else if (inner) SPH_LAUNCH(ctx, (k_relation_ordered<true, MODE, false>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count, align_origin);
+        else SPH_LAUNCH(ctx, (k_relation_ordered<false, MODE, false>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count, align_origin);
         return 0;
     }
     if (inner && sorted) SPH_LAUNCH(ctx, (k_relation<true, true, MODE>), g, 128, 0, st, a, count, slice, index, cap, stride, max_count);
@@ -725,9 +739,11 @@ extern "C" int sphb200_relation_build_fixed(sphb200_context_t *ctx, const sphb20
         SearchArgs a;
         int rc = make_search(ctx, search, &a);
         if (rc) return rc;
-        rc = launch_relation<2>(ctx, a, search->is_inner != 0, rel.count, rel.slice_offset, rel.index, rel.capacity, stride, dmax, st);
+        bool aligned = false;
+        rc = launch_relation<2>(ctx, a, search->is_inner != 0, rel.count, rel.slice_offset, rel.index, rel.capacity, stride, dmax, st,
+                                rel.bank_aligned ? (int)((u32)(rel.bank_aligned - 1) & 7u) : -1, &aligned);
         if (rc) return rc;
-        if (rel.bank_aligned)
+        if (rel.bank_aligned && !aligned) // generic (index-indirected) search: stand-alone layout pass
         {
             rc = bank_align(ctx, a, rel.count, rel.slice_offset, rel.index, stride, (u32)(rel.bank_aligned - 1) & 7u, st);
             if (rc) return rc;
