@@ -394,19 +394,23 @@ __global__ void __launch_bounds__(RS_THREADS)
     hist[(u64)threadIdx.x * ntiles + blockIdx.x] = cnt[threadIdx.x];
 }
 
-// Stable scatter of one tile (RS_TILE pairs). The tile is first brought into digit order in shared memory — local
-// position = exclusive tile histogram of the digit + pairs of that digit in earlier rounds/warps + rank inside the warp
-// (warp match) — and then written out by sorted position: pairs of one digit leave as one contiguous run (16 pairs =
-// 64 bytes on average) instead of one 4-byte store per 32-byte sector, which is what bounded the direct scatter
-// (1.0 ms for 16.7 M pairs, 17 % of the HBM peak; profiles/r01_config5_microbench.json).
-__global__ void __launch_bounds__(RS_THREADS)
+// Stable scatter of one tile (RS_TILE pairs). The tile is first brought into digit order in shared memory and then
+// written out by sorted position: pairs of one digit leave as one contiguous run (16 pairs = 64 bytes on average) instead
+// of one 4-byte store per 32-byte sector, which is what bounded the direct scatter at large sizes (33 -> 14 ms at 268 M
+// pairs; profiles/r01_config5_microbench.json). Ranking needs no block barrier per round: warp w owns the 512
+// consecutive pairs [512 w, 512 w + 512) of the tile, ranks them against its own digit counters (warp match + a running
+// per-warp count), and one pass over the 8 x 256 counters turns them into the warps' start positions inside the tile.
+#ifndef SPH_RS_MIN_BLOCKS
+#define SPH_RS_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(RS_THREADS, SPH_RS_MIN_BLOCKS)
     k_rs_scatter(const u32 *__restrict__ keys_in, const u32 *__restrict__ vals_in, u32 *__restrict__ keys_out,
                  u32 *__restrict__ vals_out, u64 n, int shift, const u32 *__restrict__ hist, u32 ntiles)
 {
     __shared__ u32 gbase[256];           // where the tile's pairs of digit d start in the output
-    __shared__ u32 lbase[256];           // running local position of digit d (starts at the exclusive tile histogram)
     __shared__ u32 lstart[256];          // exclusive tile histogram
-    __shared__ u32 wcnt[RS_WARPS][256];
+    __shared__ u32 wcnt[RS_WARPS][256];  // per-warp digit counts, then the warp's start position for the digit
+    __shared__ u32 wtot[RS_WARPS];
     __shared__ u32 skey[RS_TILE], sval[RS_TILE];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const u64 tile_base = (u64)blockIdx.x * RS_TILE;
@@ -426,56 +430,70 @@ __global__ void __launch_bounds__(RS_THREADS)
             u32 v = __shfl_up_sync(0xffffffffu, incl, o);
             if (lane >= o) incl += v;
         }
-        __shared__ u32 wtot[RS_WARPS];
         if (lane == 31) wtot[wid] = incl;
 #pragma unroll
         for (int w = 0; w < RS_WARPS; ++w) wcnt[w][threadIdx.x] = 0;
         __syncthreads();
         u32 off = 0;
         for (int w = 0; w < wid; ++w) off += wtot[w];
-        lstart[threadIdx.x] = lbase[threadIdx.x] = off + incl - c;
+        lstart[threadIdx.x] = off + incl - c;
     }
-    __syncthreads();
-#pragma unroll 1
+    // phase 1: rank every pair among the pairs of its digit inside the warp's 512 (warp barriers only)
+    u32 key[RS_ITEMS], val[RS_ITEMS], lrank[RS_ITEMS];
+    const u32 warp_first = (u32)wid * (RS_ITEMS * 32u);
+    u32 *mine = wcnt[wid];
+#pragma unroll
     for (int r = 0; r < RS_ITEMS; ++r)
     {
-        const u32 k = (u32)r * RS_THREADS + threadIdx.x;
+        const u32 k = warp_first + (u32)r * 32u + (u32)lane;
         const bool valid = k < in_tile;
-        const u32 key = valid ? keys_in[tile_base + k] : 0u;
-        const u32 val = valid ? vals_in[tile_base + k] : 0u;
-        const u32 d = (key >> shift) & 255u;
+        key[r] = valid ? keys_in[tile_base + k] : 0xffffffffu;
+        val[r] = valid ? vals_in[tile_base + k] : 0u;
+    }
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r)
+    {
+        const bool valid = warp_first + (u32)r * 32u + (u32)lane < in_tile;
+        const u32 d = (key[r] >> shift) & 255u;
         const u32 peers = __match_any_sync(0xffffffffu, valid ? d : (0x100u | (u32)lane));
         const u32 rank = __popc(peers & ((1u << lane) - 1u));
-        if (valid && rank == 0) wcnt[wid][d] = __popc(peers);
-        __syncthreads();
-        if (valid)
-        {
-            u32 off = lbase[d];
-            for (int w = 0; w < wid; ++w) off += wcnt[w][d];
-            skey[off + rank] = key;
-            sval[off + rank] = val;
-        }
-        __syncthreads();
-        {
-            u32 s = 0;
-#pragma unroll
-            for (int w = 0; w < RS_WARPS; ++w)
-            {
-                s += wcnt[w][threadIdx.x];
-                wcnt[w][threadIdx.x] = 0;
-            }
-            lbase[threadIdx.x] += s;
-        }
-        __syncthreads();
+        const u32 prev = valid ? mine[d] : 0u;
+        __syncwarp();
+        if (valid && rank == 0) mine[d] = prev + __popc(peers);
+        __syncwarp();
+        lrank[r] = prev + rank;
     }
-    // write out by sorted position: consecutive threads -> consecutive output addresses inside a digit run
+    __syncthreads();
+    // phase 2: counts -> start position of (warp, digit) inside the tile
+    {
+        u32 run = lstart[threadIdx.x];
+#pragma unroll
+        for (int w = 0; w < RS_WARPS; ++w)
+        {
+            const u32 c = wcnt[w][threadIdx.x];
+            wcnt[w][threadIdx.x] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+    // phase 3: into digit order
+#pragma unroll
+    for (int r = 0; r < RS_ITEMS; ++r)
+        if (warp_first + (u32)r * 32u + (u32)lane < in_tile)
+        {
+            const u32 at = mine[(key[r] >> shift) & 255u] + lrank[r];
+            skey[at] = key[r];
+            sval[at] = val[r];
+        }
+    __syncthreads();
+    // phase 4: write out by sorted position: consecutive threads -> consecutive output addresses inside a digit run
 #pragma unroll 4
     for (u32 k = threadIdx.x; k < in_tile; k += RS_THREADS)
     {
-        const u32 key = skey[k];
-        const u32 d = (key >> shift) & 255u;
+        const u32 kk = skey[k];
+        const u32 d = (kk >> shift) & 255u;
         const u32 pos = gbase[d] + (k - lstart[d]);
-        keys_out[pos] = key;
+        keys_out[pos] = kk;
         vals_out[pos] = sval[k];
     }
 }
