@@ -309,30 +309,45 @@ __device__ __forceinline__ void bank_align_column(u32 *__restrict__ col, u32 *__
 #pragma unroll
         for (int u = 0; u < BA_GROUP; ++u) sv[u] = g + u < cmax ? col[32ull * (g + u)] : 0u;
         const u32 n = c > g ? min(c - g, (u32)BA_GROUP) : 0u; // entries of this lane in the group
-        u32 used = 0, waiting = 0;                               // positions taken / entries not yet placed
+        // Entry u wants a position p with (g + p) = (s - t) mod 8, i.e. p = p0 + 8 q, p0 = (s - t - g) mod 8, and takes
+        // the first free one of its class. Positions of a class fill in the order q = 0, 1, 2, 3, so "first free" is a
+        // per-class counter: eight 4-bit counters in one word — one short add chain instead of a used-mask/ffs chain
+        // per entry. Entries whose class is full (p >= n) wait and fill the holes afterwards, lowest hole first.
+        const u32 shift0 = t + origin + g;
+        u32 taken = 0, waiting = 0; // 4-bit count per class / entries not yet placed
 #pragma unroll
         for (int u = 0; u < BA_GROUP; ++u)
         {
             if ((u32)u >= n) continue;
-            // wanted positions: p with (g + p) = (s - t) mod 8, i.e. p = ((s - t - g) mod 8) + 8 q
-            const u32 p0 = (sv[u] - t - origin - g) & 7u;
-            const u32 free_of_class = ~used & (0x01010101u << p0) & (n >= 32u ? 0xffffffffu : (1u << n) - 1u);
-            if (free_of_class)
+            const u32 p0 = (sv[u] - shift0) & 7u;
+            const u32 q = (taken >> (4u * p0)) & 15u;
+            const u32 p = p0 + 8u * q;
+            if (p < n)
             {
-                const u32 p = __ffs(free_of_class) - 1u;
                 tile[32u * p] = sv[u];
-                used |= 1u << p;
+                taken += 1u << (4u * p0);
             }
             else
                 waiting |= 1u << u;
         }
-#pragma unroll
-        for (int u = 0; u < BA_GROUP; ++u)
+        if (waiting)
         {
-            if (!((waiting >> u) & 1u)) continue;
-            const u32 p = __ffs(~used) - 1u; // lowest free position (< n: as many free positions as waiting entries)
-            tile[32u * p] = sv[u];
-            used |= 1u << p;
+            // positions taken so far: class p0 holds p0, p0 + 8, ... for its count
+            u32 used = 0;
+#pragma unroll
+            for (u32 p0 = 0; p0 < 8u; ++p0)
+            {
+                const u32 k = (taken >> (4u * p0)) & 15u;
+                used |= (0x01010101u & ((k >= 4u ? 0xffffffffu : (1u << (8u * k)) - 1u))) << p0;
+            }
+#pragma unroll
+            for (int u = 0; u < BA_GROUP; ++u)
+            {
+                if (!((waiting >> u) & 1u)) continue;
+                const u32 p = __ffs(~used) - 1u; // lowest free position (< n: as many free positions as waiting entries)
+                tile[32u * p] = sv[u];
+                used |= 1u << p;
+            }
         }
 #pragma unroll 8
         for (u32 p = 0; p < n; ++p) col[32ull * (g + p)] = tile[32u * p];
