@@ -281,7 +281,9 @@ def run_ours(args, rank, world, local_rank):
         if decomposed:
             for nm in out_names:
                 solver.download_own_into(nm, host_out[nm][1])
-            fetch_inputs()                              # the own set changed (migration): next step's inputs
+            # the configuration update ran at the START of the step on the uploaded state, so the rank still owns exactly
+            # the particles of its host buffers (nothing migrated since): the same buffers are the next step's inputs
+            assert solver.own_range()[1] == n_own, "own set changed during an e2e step"
         else:
             for nm in out_names:
                 solver.download(nm, out=host_out[nm][1])  # DiscreteVariable::synchronizeWithDevice
