@@ -206,6 +206,7 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     n_ac = solver.acoustic_steps - ac0
     launches = solver.launches - launches0
+    n_own = solver.own_range()[1]  # own particles of this rank after the timed steps (migration, re-cuts)
     t = torch.tensor([ms, float(n_ac)], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)  # every rank takes the same sub-steps (global dt); time = slowest rank
@@ -243,6 +244,7 @@ def run_ours(args, rank, world, local_rank):
     out_names = ["Position", "Velocity", "Density"]
 
     decomposed = world > 1
+    n_own = solver.own_range()[1]  # the own set as it is NOW (migration and re-cuts during the timed steps changed it)
 
     def pinned_like(name):
         # single GPU: the reference's packed layout in reference particle order; decomposed: this rank's own slots raw
