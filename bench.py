@@ -89,42 +89,60 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline_run(dp, max_outer, budget_s, threads=0):
-    """The oracle (CPU restatement of the reference's CK par_host data flow) on the host cores: bounded sample."""
+def cpu_baseline_run(dp, max_outer, budget_s, threads=0, warmup=0):
+    """The oracle (CPU restatement of the reference's CK par_host data flow) on the host cores: bounded sample.
+    `warmup` outer steps run untimed first; then up to `max_outer` timed outer steps (fewer only if budget_s runs out)."""
     from oracle import oracle as orc
     from sphinxsys_b200 import cases
     case = cases.dam_break(dim=3, dp=dp)
     sim = orc.OracleSim(case, f64=False, threads=threads)
     sim.exec("prepare_ck")
+    for _ in range(warmup):
+        sim.exec("run_ck", 1e9, 1, 1e9, 100)
+    n_ac0 = int(sim.exec("acoustic_steps"))
     t0 = time.perf_counter()
     done = 0
-    per_step = []
     while done < max_outer and (time.perf_counter() - t0) < budget_s:
-        t1 = time.perf_counter()
         sim.exec("run_ck", 1e9, 1, 1e9, 100)
-        per_step.append(time.perf_counter() - t1)
         done += 1
     elapsed = time.perf_counter() - t0
-    n_ac = int(sim.exec("acoustic_steps"))
+    n_ac = int(sim.exec("acoustic_steps")) - n_ac0
     return {"value": case.n_fluid * n_ac / elapsed, "unit": "particle-steps/s", "cores": orc.lib().orc_max_threads(),
             "kind": "port",
             "sample": f"3-D dam break dp={dp} ({case.n_fluid} fluid + {case.n_wall} wall), {done} outer / {n_ac} acoustic steps "
-                      f"in {elapsed:.1f} s, oracle fp32 + OpenMP (restatement of the reference CK par_host path, not the TBB build)",
-            "_elapsed": elapsed, "_steps": done, "_ms_per_step": 1e3 * elapsed / max(done, 1), "_n_fluid": case.n_fluid}
+                      f"in {elapsed:.1f} s after {warmup} untimed, oracle fp32 + OpenMP (restatement of the reference CK par_host "
+                      f"path, not the TBB build)",
+            "_elapsed": elapsed, "_steps": done, "_ms_per_step": 1e3 * elapsed / max(done, 1), "_n_fluid": case.n_fluid,
+            "_n_wall": case.n_wall, "_acoustic_per_outer": n_ac / max(done, 1)}
+
+
+REFERENCE_BUDGET_S = 150.0  # the whole --impl reference run (warm-up included) stays within a few minutes
 
 
 def run_reference(args, rank, world):
+    """Reference arm: the reference's CPU implementation of the path on the box's host cores. The reference itself
+    cannot be built in this image, so this is the oracle port with all host threads. W untimed warm-up
+    steps, then exactly K timed outer steps; each step is a bounded sample of config 2 (same case, coarser spacing),
+    the spacing chosen so that K + W steps fit REFERENCE_BUDGET_S."""
     if rank != 0:
         return
-    # bounded: each step is one outer step at a reduced resolution; the whole run is capped at ~2 minutes
+    steps, warmup = max(args.steps, 1), max(args.warmup, 0)
+    # one probe step at the finest sample resolution sizes the run: cost per outer step scales with the particle count
     dp = args.ref_dp
-    r = cpu_baseline_run(dp, max(args.steps + args.warmup, 1), 120.0)
+    probe = cpu_baseline_run(dp, 1, 1e9)
+    while probe["_elapsed"] * (steps + warmup) > REFERENCE_BUDGET_S and dp < 0.05:
+        probe["_elapsed"] /= 8.0
+        dp *= 2.0
+    r = cpu_baseline_run(dp, steps, 2.0 * REFERENCE_BUDGET_S, warmup=warmup)
     line = {
         "metric": "particle-steps/sec (3D WCSPH dam break)", "value": r["value"], "unit": "particle-steps/s",
-        "n_gpus": args.gpus, "steps": r["_steps"], "warmup": 0, "ms_per_step": r["_ms_per_step"],
+        "n_gpus": args.gpus, "steps": r["_steps"], "warmup": warmup, "ms_per_step": r["_ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "impl": "reference",
-        "config": {"workload": f"3-D dam break WCSPH, dp={dp} bounded sample of config 2 (dp=0.00625)", "n_fluid": r["_n_fluid"]},
+        "config": {"workload": "3-D dam break WCSPH (tests_sycl dambreak geometry), AcousticRiemann + wall, Wendland C2 tabulated; "
+                               f"bounded sample of config 2 (dp=0.00625) at dp={dp}: {r['_n_fluid']} fluid + {r['_n_wall']} wall particles",
+                   "n_fluid_global": r["_n_fluid"], "n_wall": r["_n_wall"], "acoustic_steps_per_outer": r["_acoustic_per_outer"],
+                   "parallelism": f"{r['cores']} host threads (OpenMP), rank 0 only"},
         "cpu_baseline": {k: v for k, v in r.items() if not k.startswith("_")},
         "e2e": {"value": r["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
