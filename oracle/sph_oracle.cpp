@@ -945,16 +945,21 @@ template <class R> struct Sim
         for (size_t k = 0; k < size_t(3) * fluid.n; ++k) pos[k] += dpos[k];
     }
     // ref: fluid_time_step_ck.h:106-109, fluid_time_step_ck.cpp:24-27; TinyReal base_data_type.h:207
+    // Slab-decomposed runs (oracle/decomposed.py): a rank stores its own particles first and the ghost planes behind
+    // them; the time-step reductions then run over the own particles only and the ranks combine the raw values (max).
+    long reduce_count = -1; // -1: all particles
+    u32 reduceCount() const { return reduce_count < 0 ? fluid.n : std::min<u32>((u32)reduce_count, fluid.n); }
     double advectionDtReduced()
     {
         const std::vector<R> &vel = fluid.r("Velocity", 3);
         R red = std::numeric_limits<R>::lowest();
-        for (u32 i = 0; i < fluid.n; ++i) red = SMAX(red, vec(vel, i).squaredNorm());
+        for (u32 i = 0; i < reduceCount(); ++i) red = SMAX(red, vec(vel, i).squaredNorm());
         return double(red);
     }
-    double advectionDt()
+    double advectionDt() { return advectionDtOf(advectionDtReduced()); }
+    double advectionDtOf(double reduced)
     {
-        R red = R(advectionDtReduced());
+        R red = R(reduced);
         return double(R(P.advection_cfl) * R(P.h_min) / (SMAX(R(std::sqrt(red)), R(P.U_ref)) + R(2.71051e-20)));
     }
     // ref: fluid_time_step_ck.hpp:51-57, :31-36
@@ -964,7 +969,7 @@ template <class R> struct Sim
                              &m = fluid.r("Mass");
         R hmin = R(P.h_min);
         R red = std::numeric_limits<R>::lowest();
-        for (u32 i = 0; i < fluid.n; ++i)
+        for (u32 i = 0; i < reduceCount(); ++i)
         {
             R fn = (vec(F, i) + vec(Fp, i)).norm();
             R acc = std::sqrt(R(4.0) * hmin * fn / m[i]);
@@ -972,9 +977,10 @@ template <class R> struct Sim
         }
         return double(red);
     }
-    double acousticDt()
+    double acousticDt() { return acousticDtOf(acousticDtReduced()); }
+    double acousticDtOf(double reduced)
     {
-        R red = R(acousticDtReduced());
+        R red = R(reduced);
         return double(R(P.acoustic_cfl) * R(P.h_min) / (red + R(2.71051e-20)));
     }
 
@@ -1482,6 +1488,9 @@ double execOp(Sim<R> &s, const std::string &op, double a0, double a1, double a2,
     else if (op == "advection_dt_reduced") return s.advectionDtReduced();
     else if (op == "acoustic_dt") return s.acousticDt();
     else if (op == "acoustic_dt_reduced") return s.acousticDtReduced();
+    else if (op == "advection_dt_of") return s.advectionDtOf(a0);
+    else if (op == "acoustic_dt_of") return s.acousticDtOf(a0);
+    else if (op == "set_reduce_count") s.reduce_count = (long)a0;
     else if (op == "acoustic1") s.acoustic1(R(a0));
     else if (op == "acoustic2") s.acoustic2(R(a0));
     else if (op == "acoustic1_init") s.a1Init(R(a0));

@@ -1,0 +1,168 @@
+"""N > 1 on the CPU: the exchange protocol of the slab-decomposed run against the single-domain oracle.
+
+oracle/decomposed.py restates what SlabDecomposition / DamBreakCK::stepOuter do on N GPUs — plane ownership, migration
+and ghost planes at the configuration update, the three ghost refreshes inside a step, own-particle reductions combined
+by max — with the oracle doing the arithmetic. The bar is the one the GPU runs are held to (tests/multi_gpu_check.py):
+every variable of every particle bit-identical to the undecomposed run. The ranks run as threads of this process for
+the wider sweeps and as two gloo processes (one process per rank, as on the GPUs) for the world_size-2 test.
+The periodic ring along x (BASELINE config 4 on N GPUs) is pinned here BEFORE its CUDA side exists: DESIGN.md §6c.
+"""
+import dataclasses
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+from oracle import decomposed as dec  # noqa: E402
+from oracle import oracle as orc  # noqa: E402
+from sphinxsys_b200 import cases  # noqa: E402
+
+
+def _single(case, steps, **kw):
+    g = orc.OracleSim(case, **kw)
+    g.exec("prepare_ck")
+    g.exec("run_ck", 1e9, steps, 1e9, 0)  # no ParticleSortCK: decomposed runs keep the initial numbering
+    return g
+
+
+def _mismatches(g, glob):
+    bad = []
+    for nm, w in dec.VARIABLES:
+        ref = g.real(nm, w).reshape(-1, w)
+        if not np.array_equal(ref.view(np.uint32), glob[nm].view(np.uint32)):
+            bad.append(nm)
+    return bad
+
+
+def _dam_break():
+    case = cases.dam_break(dim=3, dp=0.05)
+    planes = dec.x_plane(case.fluid_pos, case.mesh)
+    return case, planes
+
+
+def _ring_case(drift):
+    case = cases.taylor_green(dim=3, n_side=16)
+    mesh, first, planes = dec.aligned_periodic_mesh(case)
+    vel = case.fluid_vel.copy()
+    vel[:, 0] += np.float32(drift)  # uniform drift: particles cross the seam between the last and the first rank
+    return dataclasses.replace(case, mesh=mesh, fluid_vel=vel), first, planes
+
+
+@pytest.mark.parametrize("nranks,steps", [(2, 12), (4, 60)])
+def test_dam_break_slabs_bit_identical(nranks, steps):
+    case, planes = _dam_break()
+    cuts = dec.plan_cuts(planes, 0, case.mesh.cells[0], nranks)
+    g = _single(case, steps)
+    states, ranks = dec.run_threads(case, nranks, cuts, steps)
+    assert all(r.acoustic_steps == int(g.exec("acoustic_steps")) for r in ranks), "ranks disagree on the time steps"
+    assert _mismatches(g, dec.gather_by_gid(states, case.n_fluid)) == []
+    if steps >= 60:
+        assert sum(r.migrated for r in ranks) > 0, "the run should exercise migration"
+
+
+def test_dam_break_cuts_do_not_matter():
+    """Results do not depend on where the slabs are cut (in-cell order is by global id)."""
+    case, _ = _dam_break()
+    g = _single(case, 8)
+    for cuts in ([0, 7, 52], [0, 16, 52], [0, 5, 9, 52]):
+        states, _ = dec.run_threads(case, len(cuts) - 1, cuts, 8)
+        assert _mismatches(g, dec.gather_by_gid(states, case.n_fluid)) == []
+
+
+@pytest.mark.parametrize("stale", ["VolumetricMeasure", "Pressure", "Velocity"])
+def test_every_refresh_is_needed(stale):
+    """Each of the three ghost refreshes carries a value the neighbours' own particles read: dropping one breaks parity."""
+    case, planes = _dam_break()
+    cuts = dec.plan_cuts(planes, 0, case.mesh.cells[0], 2)
+    g = _single(case, 6)
+    states, _ = dec.run_threads(case, 2, cuts, 6, skip_refresh=[stale])
+    assert _mismatches(g, dec.gather_by_gid(states, case.n_fluid)) != []
+
+
+@pytest.mark.parametrize("nranks,steps,drift", [(2, 10, 1.0), (3, 30, 1.0), (2, 15, -1.5)])
+def test_periodic_ring_bit_identical(nranks, steps, drift):
+    case, first, planes = _ring_case(drift)
+    cuts = dec.plan_cuts(dec.x_plane(case.fluid_pos, case.mesh), first, first + planes, nranks)
+    g = _single(case, steps, free_surface=0)
+    states, ranks = dec.run_threads(case, nranks, cuts, steps, ring=True, free_surface=0)
+    assert _mismatches(g, dec.gather_by_gid(states, case.n_fluid)) == []
+    seam = ranks[-1] if drift > 0 else ranks[0]
+    assert seam.wrapped > 0, "particles should have crossed the periodic seam"
+
+
+def test_aligned_periodic_mesh_keeps_neighbour_sets():
+    """The aligned mesh (spacing L / floor(L / r_c) >= r_c) changes cells, not neighbours: same sorted rows as the case mesh."""
+    case = cases.taylor_green(dim=3, n_side=16)
+    mesh, first, planes = dec.aligned_periodic_mesh(case)
+    assert mesh.spacing >= case.kernel.cutoff and planes == int(1.0 / case.kernel.cutoff)
+    a = orc.OracleSim(case, free_surface=0)
+    b = orc.OracleSim(dataclasses.replace(case, mesh=mesh), free_surface=0)
+    rows = []
+    for s in (a, b):
+        s.exec("prepare_ck")
+        off, idx = s.uint("inner_offset"), s.uint("inner_index")
+        rows.append([tuple(sorted(idx[off[i]:off[i + 1]].tolist())) for i in range(0, case.n_fluid, 7)])
+    assert rows[0] == rows[1]
+
+
+# ---- one process per rank over gloo, as the GPU run has one process per GPU ----
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        out = {}
+        for name in ("dam_break", "ring"):
+            if name == "dam_break":
+                case, planes = _dam_break()
+                cuts, steps, kw, ring = dec.plan_cuts(planes, 0, case.mesh.cells[0], world), 10, {}, False
+            else:
+                case, first, nplanes = _ring_case(1.0)
+                cuts = dec.plan_cuts(dec.x_plane(case.fluid_pos, case.mesh), first, first + nplanes, world)
+                steps, kw, ring = 8, {"free_surface": 0}, True
+            sr = dec.SlabRank(case, dec.GlooComm(), cuts, ring=ring, **kw)
+            for _ in range(steps):
+                sr.step_outer()
+            states = [None] * world
+            dist.all_gather_object(states, sr.own_state())
+            if rank == 0:
+                g = _single(case, steps, **kw)
+                out[name] = (_mismatches(g, dec.gather_by_gid(states, case.n_fluid)), sr.acoustic_steps,
+                             int(g.exec("acoustic_steps")), sr.migrated + sr.wrapped)
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world_size_2_gloo_matches_single_domain():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for name in ("dam_break", "ring"):
+        bad, ac, ac_single, moved = results[0][name]
+        assert bad == [], f"{name}: variables differ from the single-domain oracle: {bad}"
+        assert ac == ac_single
+    assert results[0]["ring"][3] > 0
