@@ -423,10 +423,35 @@ int sphb200_comm_destroy(sphb200_context_t *ctx);
 int sphb200_comm_rank(const sphb200_context_t *ctx);
 int sphb200_comm_size(const sphb200_context_t *ctx);
 /* one grouped send/recv with rank-1 ("left") and rank+1 ("right"): `count` device segments per direction; what a
- * rank sends left arrives in its left neighbour's recv_right segments of the same index. Missing neighbours are skipped. */
+ * rank sends left arrives in its left neighbour's recv_right segments of the same index. Missing neighbours are skipped;
+ * in a ring (sphb200_comm_set_ring) there are none missing: rank 0's left neighbour is rank nranks-1. */
 int sphb200_comm_exchange(sphb200_context_t *ctx, int count, const void *const *send_left, const size_t *send_left_bytes,
                           void *const *recv_left, const size_t *recv_left_bytes, const void *const *send_right,
                           const size_t *send_right_bytes, void *const *recv_right, const size_t *recv_right_bytes, void *stream);
+/* Communicator of ONE rank without NCCL; with the ring switched on the rank is its own neighbour on both sides (a
+ * periodic box in one slab) and sphb200_comm_exchange copies device to device; reductions and all-gather are identities. */
+int sphb200_comm_create_self(sphb200_context_t *ctx);
+/* ring != 0 closes the slab chain (periodic along x, BASELINE config 4 on N GPUs): the neighbours of
+ * sphb200_comm_exchange become (rank - 1) mod nranks and (rank + 1) mod nranks. */
+int sphb200_comm_set_ring(sphb200_context_t *ctx, int ring);
+int sphb200_comm_is_ring(const sphb200_context_t *ctx);
+/* The periodic seam of a ring of slabs along x: the x axis of the body's mesh, the cell planes of the periodic box
+ * [first_plane, first_plane + box_planes), and the x ranges (inclusive, in the mesh's own cell arithmetic,
+ * base_mesh.hxx:9-15) of the box planes and of the one ghost plane on either side of the box. */
+typedef struct
+{
+    float mesh_lower, mesh_spacing;
+    int32_t mesh_cells, first_plane, box_planes;
+    float own_min, own_max;
+    float ghost_low_min, ghost_low_max;
+    float ghost_high_min, ghost_high_max;
+} sphb200_seam_t;
+/* Positions that crossed the seam: x of n records `stride_bytes` apart (x = the first float of a record: Position,
+ * PosVol, PosVolVel) += delta, delta = +/-(box_upper - box_lower): the translated position of the reference's periodic
+ * ghost entry, particle_dynamics/general_dynamics/domian_bouding/domain_bounding.cpp:26,45. Records whose plane was
+ * outside the box planes on the sender (leavers) end inside them, the others (its boundary plane) in the ghost plane. */
+int sphb200_seam_shift(sphb200_context_t *ctx, void *base, uint32_t stride_bytes, uint32_t n, float delta,
+                       const sphb200_seam_t *seam, void *stream);
 int sphb200_comm_allreduce_max_f32(sphb200_context_t *ctx, float *dev_inout, int n, void *stream);
 int sphb200_comm_allreduce_sum_f64(sphb200_context_t *ctx, double *dev_inout, int n, void *stream);
 int sphb200_comm_allgather_u64(sphb200_context_t *ctx, const uint64_t *dev_send, uint64_t *dev_recv, int n_per_rank, void *stream);

@@ -38,6 +38,16 @@ class CellLinkedList
         v.sorted_pos = nullptr;
         return v;
     }
+    // Another mesh for the same body (spacing >= cut-off radius keeps every neighbour set): ring-decomposed periodic
+    // runs need cell planes that tile the periodic box (alignedPeriodicMesh in slab_decomposition.h). Call it before
+    // anything sized by the cell count exists (periodic images, relations to this body).
+    void resetMesh(const sphb200_mesh_t &mesh, size_t particles_bound)
+    {
+        mesh_ = mesh;
+        total_cells_ = (size_t)mesh_.cells[0] * mesh_.cells[1] * mesh_.cells[2];
+        cell_offset_.reset((total_cells_ + 2) * sizeof(uint32_t));
+        particle_index_.reset((std::max(particles_bound, total_cells_) + 2) * sizeof(uint32_t));
+    }
 };
 inline CellLinkedList &SPHBody::getCellLinkedList()
 {

@@ -70,6 +70,10 @@ class PeriodicImages
     int armed_axes_ = 0;   // axes whose ghost_creation_ ran since the last cell-linked-list update
     bool valid_ = false;   // ghosts exist for the armed axes
     uint32_t n_real_ = 0, n_ghost_ = 0;
+    // slab-decomposed periodic runs (SlabDecomposition with a ring): the images of the remaining axes are made for every
+    // STORED particle (own + the ghost planes of the neighbour slabs), dynamics keep running on the own range
+    bool decomposed_ = false;
+    uint32_t own_begin_ = 0, own_end_ = 0;
     DeviceBuffer tmp_pos_, tmp_src_, ghost_src_, cell_offset_, particle_index_;
 
   public:
@@ -89,6 +93,15 @@ class PeriodicImages
         box_.upper[k] = b.upper_[k];
         box_.axes |= 1 << k;
     }
+    // SlabDecomposition::rebuild(): `stored` particles (own + x ghost planes) in cell order, own slots [begin, end)
+    void setStoredRange(uint32_t stored, uint32_t own_begin, uint32_t own_end)
+    {
+        decomposed_ = true;
+        n_real_ = stored;
+        own_begin_ = own_begin;
+        own_end_ = own_end;
+        invalidate();
+    }
     uint32_t realParticles() const { return n_real_; }
     uint32_t ghostParticles() const { return valid_ ? n_ghost_ : 0; }
     const uint32_t *ghostSource() const { return ghost_src_.get<uint32_t>(); }
@@ -100,7 +113,9 @@ class PeriodicImages
         BaseParticles &p = body_.getBaseParticles();
         sphb200_periodic_t b = box_;
         b.axes = 1 << axis;
-        SPHCK_CALL(sphb200_periodic_bounding, &b, (sphb200_vec4_t *)p.deviceData<Vecd>("Position"), n_real_, execution_instance().stream());
+        // decomposed runs: the own particles only (ghost planes beyond the seam are outside the box by construction)
+        const uint32_t first = decomposed_ ? own_begin_ : 0, count = decomposed_ ? own_end_ - own_begin_ : n_real_;
+        SPHCK_CALL(sphb200_periodic_bounding, &b, (sphb200_vec4_t *)p.deviceData<Vecd>("Position") + first, count, execution_instance().stream());
         body_.setPosVolDirty();
     }
     // ghost_creation_.exec() of one axis: the images themselves are made once, for all armed axes together, when
@@ -147,7 +162,8 @@ class PeriodicImages
         ex.check(rc, "sphb200_periodic_images");
         n_ghost_ = count;
         p.setTotalRealParticles((size_t)n_real_ + n_ghost_);
-        p.setActiveRange(0, n_real_);
+        if (decomposed_) p.setActiveRange(own_begin_, own_end_);
+        else p.setActiveRange(0, n_real_);
         // images into the cell order of their own list: translated positions straight into the tail of Position
         {
             char *pos_tail = (char *)p.deviceData<Vecd>("Position") + (size_t)n_real_ * 16;

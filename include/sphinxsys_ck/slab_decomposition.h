@@ -17,6 +17,9 @@
 #define SPHINXSYS_CK_SLAB_DECOMPOSITION_H
 
 #include <algorithm>
+#include <cmath>
+#include <limits>
+#include <utility>
 
 #include "configuration.h"
 
@@ -77,10 +80,89 @@ inline std::vector<int> limitCutMoves(const std::vector<int> &old_cuts, std::vec
     return wanted;
 }
 
+// Periodic runs along x on a RING of slabs (BASELINE config 4 on N GPUs): the first and the last rank are neighbours and
+// what crosses the seam travels with x shifted by -/+ L (sphb200_seam_shift). Ownership is by cell plane, so the planes
+// tile the box: [lower, upper) = the planes [first_plane, first_plane + box_planes) up to rounding, and the shift keeps
+// every particle in the plane it belongs to (sphb200_seam_t). The protocol is pinned on the CPU by oracle/decomposed.py
+// (tests/test_decomposed_oracle_cpu.py).
+struct SeamRing
+{
+    bool on = false;
+    Real lower = 0, upper = 0; // the periodic box along x
+    sphb200_seam_t seam;
+    int first_plane() const { return seam.first_plane; }
+    int box_planes() const { return seam.box_planes; }
+};
+
+// {largest x whose cell plane is < plane, smallest x whose cell plane is >= plane} by bisection over the mesh's own
+// cell arithmetic (monotone in x)
+inline std::pair<Real, Real> planeFace(const sphb200_mesh_t &m, int plane)
+{
+    const Real face = m.lower[0] + Real(plane) * m.spacing;
+    Real lo = face - Real(0.5) * m.spacing, hi = face + Real(0.5) * m.spacing;
+    if (!(hostCellCoordinate(lo, m.lower[0], m.spacing, m.cells[0]) < plane && hostCellCoordinate(hi, m.lower[0], m.spacing, m.cells[0]) >= plane))
+        throw SphError("planeFace: the cell arithmetic does not bracket the plane face");
+    for (int it = 0; it < 200; ++it)
+    {
+        const Real mid = lo + (hi - lo) * Real(0.5);
+        if (mid <= lo || mid >= hi) break;
+        if (hostCellCoordinate(mid, m.lower[0], m.spacing, m.cells[0]) < plane) lo = mid;
+        else hi = mid;
+    }
+    return {lo, hi};
+}
+
+// Mesh for a ring-decomposed periodic body: spacing = L_x / floor(L_x / cutoff) >= cutoff (neighbour sets do not depend
+// on the mesh once the spacing is at least the cut-off radius), `ghost_planes` cell layers around the box on every axis
+// (room for the images of the other axes and for the seam ghost planes).
+inline sphb200_mesh_t alignedPeriodicMesh(const BoundingBoxd &box, Real cutoff, int dim, SeamRing &ring, int ghost_planes = 2)
+{
+    const Real lo = box.lower_[0], up = box.upper_[0], L = up - lo;
+    const int planes = (int)std::floor(double(L) / double(cutoff));
+    if (planes < 3) throw SphError("alignedPeriodicMesh: the periodic box is narrower than three cut-off radii");
+    Real spacing = L / Real(planes);
+    while (spacing < cutoff) spacing = std::nextafter(spacing, std::numeric_limits<Real>::max());
+    sphb200_mesh_t m;
+    m.spacing = spacing;
+    for (int d = 0; d < 3; ++d)
+    {
+        if (d >= dim)
+        {
+            m.lower[d] = 0;
+            m.cells[d] = 1;
+            continue;
+        }
+        m.lower[d] = box.lower_[d] - Real(ghost_planes) * spacing;
+        m.cells[d] = d == 0 ? planes + 2 * ghost_planes
+                            : (int)std::ceil(double(box.upper_[d] - m.lower[d]) / double(spacing)) + ghost_planes;
+    }
+    const int k0 = ghost_planes;
+    ring.on = true;
+    ring.lower = lo;
+    ring.upper = up;
+    sphb200_seam_t &sm = ring.seam;
+    sm.mesh_lower = m.lower[0];
+    sm.mesh_spacing = spacing;
+    sm.mesh_cells = m.cells[0];
+    sm.first_plane = k0;
+    sm.box_planes = planes;
+    std::pair<Real, Real> f;
+    f = planeFace(m, k0 - 1);          sm.ghost_low_min = f.second;
+    f = planeFace(m, k0);              sm.ghost_low_max = f.first;  sm.own_min = f.second;
+    f = planeFace(m, k0 + planes);     sm.own_max = f.first;        sm.ghost_high_min = f.second;
+    f = planeFace(m, k0 + planes + 1); sm.ghost_high_max = f.first;
+    // the faces of the box sit on the plane faces up to rounding
+    const Real tol = Real(1e-5) * spacing;
+    if (std::abs(sm.own_min - lo) > tol || std::abs(sm.ghost_high_min - up) > tol)
+        throw SphError("alignedPeriodicMesh: the box faces are not on cell-plane faces");
+    return m;
+}
+
 class SlabDecomposition
 {
     SPHBody &body_;
     int rank_, nranks_;
+    SeamRing ring_;
     std::vector<int> cuts_;
     uint32_t plane_cells_; // cells per x plane (ny * nz)
     // slot offsets after the last rebuild: ghosts [0, a0) | first own plane [a0, f1) ... last own plane [l0, a1) | ghosts [a1, n)
@@ -133,12 +215,22 @@ class SlabDecomposition
     }
 
   public:
-    SlabDecomposition(SPHBody &body, int rank, int nranks, const std::vector<int> &cuts)
-        : body_(body), rank_(rank), nranks_(nranks), cuts_(cuts), scalars_(1024)
+    SlabDecomposition(SPHBody &body, int rank, int nranks, const std::vector<int> &cuts, const SeamRing &ring = SeamRing())
+        : body_(body), rank_(rank), nranks_(nranks), ring_(ring), cuts_(cuts), scalars_(1024)
     {
         const sphb200_mesh_t &m = body.getCellLinkedList().mesh_;
         plane_cells_ = (uint32_t)m.cells[1] * (uint32_t)m.cells[2];
-        if ((int)cuts.size() != nranks + 1 || cuts.front() != 0 || cuts.back() != m.cells[0])
+        if (ring_.on)
+        {
+            if ((int)cuts.size() != nranks + 1 || cuts.front() != ring_.first_plane() || cuts.back() != ring_.first_plane() + ring_.box_planes())
+                throw SphError("SlabDecomposition: the cuts of a ring must run over the cell planes of the periodic box");
+            for (int r = 0; r < nranks; ++r)
+                if (cuts[r + 1] <= cuts[r]) throw SphError("SlabDecomposition: every rank of a ring needs at least one plane");
+            if (nranks == 1 && ring_.box_planes() < 3) throw SphError("SlabDecomposition: a ring of one slab needs three planes");
+            if (!sphb200_comm_is_ring(execution_instance().ctx()))
+                throw SphError("SlabDecomposition: the communicator is not a ring (sphb200_comm_set_ring)");
+        }
+        else if ((int)cuts.size() != nranks + 1 || cuts.front() != 0 || cuts.back() != m.cells[0])
             throw SphError("SlabDecomposition: cuts must run from 0 to the number of x planes");
         BaseParticles &p = body.getBaseParticles();
         n_ = (uint32_t)p.TotalRealParticles();
@@ -156,6 +248,9 @@ class SlabDecomposition
     SlabDecomposition &operator=(const SlabDecomposition &) = delete;
     int rank() const { return rank_; }
     int size() const { return nranks_; }
+    bool isRing() const { return ring_.on; }
+    bool hasLeft() const { return ring_.on || rank_ > 0; }
+    bool hasRight() const { return ring_.on || rank_ + 1 < nranks_; }
     // --- boundary / interior split of the own slots (valid after rebuild()) ---
     // Boundary planes are the own planes a neighbour rank reads (and whose particles read ghost planes): the first own
     // plane if there is a left neighbour, the last own plane if there is a right neighbour. Interior slots read own
@@ -167,12 +262,12 @@ class SlabDecomposition
     };
     SlotRange leftBoundary() const
     {
-        if (rank_ == 0) return {a0_, a0_};
+        if (!hasLeft()) return {a0_, a0_};
         return {a0_, std::min(f1_, a1_)};
     }
     SlotRange rightBoundary() const
     {
-        if (rank_ + 1 >= nranks_) return {a1_, a1_};
+        if (!hasRight()) return {a1_, a1_};
         return {std::max(l0_, leftBoundary().end), a1_}; // one-plane slabs: the plane is the left boundary already
     }
     SlotRange interior() const { return {leftBoundary().end, rightBoundary().begin}; }
@@ -216,7 +311,7 @@ class SlabDecomposition
         uint32_t *left_idx = select_.get<uint32_t>(), *right_idx = left_idx + n_old;
         uint32_t *d_counts = scalars_.get<uint32_t>() + 48; // bytes 192..199 of the 256-byte scratch
         SPHCK_CALL(sphb200_slab_select, &cl.mesh_, (const sphb200_vec4_t *)p.deviceData<Vecd>("Position"), a0_, n_old,
-                   rank_ > 0 ? X0 : -1, rank_ + 1 < nranks_ ? X1 - 1 : -1, left_idx, right_idx, d_counts, st);
+                   hasLeft() ? X0 : -1, hasRight() ? X1 - 1 : -1, left_idx, right_idx, d_counts, st);
         // 2. sizes: own counts to the host (the gathers and sends are sized by them), then swapped with the neighbours
         uint64_t *d = scalars_.get<uint64_t>();
         uint32_t sel[2] = {0, 0};
@@ -246,7 +341,7 @@ class SlabDecomposition
         if (send_l) SPHCK_CALL(sphb200_gather_multi, (int)k, stage_l.data(), src.data(), bytes.data(), left_idx, send_l, st);
         if (send_r) SPHCK_CALL(sphb200_gather_multi, (int)k, stage_r.data(), src.data(), bytes.data(), right_idx, send_r, st);
         ex.synchronize();
-        const uint32_t recv_l = rank_ > 0 ? (uint32_t)host_counts[2] : 0, recv_r = rank_ + 1 < nranks_ ? (uint32_t)host_counts[3] : 0;
+        const uint32_t recv_l = hasLeft() ? (uint32_t)host_counts[2] : 0, recv_r = hasRight() ? (uint32_t)host_counts[3] : 0;
         const size_t n_tot = (size_t)n_old + recv_l + recv_r;
         p.setTotalRealParticles((size_t)a0_ + n_tot); // throws if the reserved storage is exhausted
         // 3. payload: one contiguous segment per variable and direction, received right behind the own slots (the old
@@ -271,6 +366,19 @@ class SlabDecomposition
             SPHCK_CALL(sphb200_comm_exchange, (int)k, sl.data(), bsl.data(), rl.data(), brl.data(), sr.data(), bsr.data(), rr.data(),
                        brr.data(), st);
         }
+        // ring: what came in over the seam (rank 0 from its left, the last rank from its right) is the neighbour's plane
+        // and leavers seen from the other side of the box: x -/+ L
+        if (ring_.on)
+        {
+            DiscreteVariableBase *pos = p.findVariable("Position");
+            char *base = (char *)pos->deviceAddress();
+            const uint32_t eb = pos->deviceElementBytes();
+            const Real L = ring_.upper - ring_.lower;
+            if (rank_ == 0 && recv_l)
+                SPHCK_CALL(sphb200_seam_shift, base + (size_t)a1_ * eb, eb, recv_l, -L, &ring_.seam, st);
+            if (rank_ == nranks_ - 1 && recv_r)
+                SPHCK_CALL(sphb200_seam_shift, base + ((size_t)a1_ + recv_l) * eb, eb, recv_r, L, &ring_.seam, st);
+        }
         // 4. everything into cell order at the front of the arrays; own particles are the planes [X0, X1)
         reorder(a0_, (uint32_t)n_tot);
         p.setTotalRealParticles(n_tot);
@@ -288,6 +396,8 @@ class SlabDecomposition
         body_.setPosVolDirty();
         ghost_particles_ = (uint64_t)a0_ + (n_ - a1_);
         migrated_out_ += (uint64_t)send_l + send_r; // boundary-plane particles and leavers handed to the neighbours
+        // periodic images of the other axes: made for all stored particles behind them, after this configuration update
+        if (PeriodicImages *im = body_.periodicImages()) im->setStoredRange(n_, a0_, a1_);
         // 5. slot origin: the slot the first stored particle has in the undecomposed run = particles owned by the ranks
         //    below minus the left ghost plane. Relations against bodies that are NOT decomposed (the wall) lay their rows
         //    out relative to it, so that summation order does not depend on the decomposition (sphb200_relation_t::bank_aligned).
@@ -312,6 +422,7 @@ class SlabDecomposition
     // Results do not depend on the cuts (in-cell order is by ReferenceID), so a run with re-cuts stays bit-identical.
     void recut()
     {
+        if (ring_.on) throw SphError("SlabDecomposition::recut: not available on a ring of slabs yet");
         ExecutionInstance &ex = execution_instance();
         CellLinkedList &cl = body_.getCellLinkedList();
         const int planes = cl.mesh_.cells[0];
@@ -353,7 +464,8 @@ class SlabDecomposition
     uint64_t recuts() const { return recuts_; }
 
     // refresh named variables on the ghost planes from their owners (contiguous ranges, in place)
-    void refreshGhosts(std::initializer_list<const char *> names)
+    void refreshGhosts(std::initializer_list<const char *> names) { refreshGhosts(std::vector<std::string>(names.begin(), names.end())); }
+    void refreshGhosts(const std::vector<std::string> &names)
     {
         BaseParticles &p = body_.getBaseParticles();
         const size_t k = names.size();
@@ -361,7 +473,7 @@ class SlabDecomposition
         std::vector<void *> rl(k), rr(k);
         std::vector<size_t> bsl(k), bsr(k), brl(k), brr(k);
         size_t i = 0;
-        for (const char *nm : names)
+        for (const std::string &nm : names)
         {
             DiscreteVariableBase *v = p.findVariable(nm);
             const size_t eb = v->deviceElementBytes();
@@ -378,6 +490,20 @@ class SlabDecomposition
         }
         SPHCK_CALL(sphb200_comm_exchange, (int)k, sl.data(), bsl.data(), rl.data(), brl.data(), sr.data(), bsr.data(), rr.data(),
                    brr.data(), execution_instance().stream());
+        // ring: records that carry a position arrive over the seam with the owner's x; shift them as rebuild() did
+        if (ring_.on && (rank_ == 0 || rank_ == nranks_ - 1))
+            for (const std::string &nm : names)
+            {
+                if (nm != "Position" && nm != "PosVol" && nm != "PosVolRef" && nm != "PosVolVel") continue;
+                DiscreteVariableBase *v = p.findVariable(nm);
+                char *base = (char *)v->deviceAddress();
+                const uint32_t eb = v->deviceElementBytes();
+                const Real L = ring_.upper - ring_.lower;
+                void *st = execution_instance().stream();
+                if (rank_ == 0 && a0_) SPHCK_CALL(sphb200_seam_shift, base, eb, a0_, -L, &ring_.seam, st);
+                if (rank_ == nranks_ - 1 && n_ > a1_)
+                    SPHCK_CALL(sphb200_seam_shift, base + (size_t)a1_ * eb, eb, n_ - a1_, L, &ring_.seam, st);
+            }
     }
 
     Real allReduceMax(Real v)

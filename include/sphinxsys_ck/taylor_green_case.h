@@ -27,6 +27,10 @@ struct TaylorGreenParameters
     int sort_interval = 100;
     bool fused_time_step = true;
     bool fused_regularization = true;
+    // ring decomposition along x (SURVEY.md §8e, config 4 on N GPUs): one process per GPU, the communicator of the
+    // context must be a ring already (sphb200_comm_create or _create_self, then sphb200_comm_set_ring)
+    bool ring = false;
+    int rank = 0, nranks = 1;
     double mu_f = 0.0;               // > 0: Viscosity closure + ViscousForceInnerCK in the loop (taylor_green.cpp:21-22,108: rho0 U L / Re)
     bool transport_velocity = false; // KernelGradientIntegralInner + TransportVelocityCorrectionCK<SPHBody, TruncatedLinear> (:109)
 };
@@ -46,6 +50,24 @@ class TaylorGreenCK
   public:
     using P = MainExecutionPolicy;
     using GhostUpdate = PeriodicConditionUsingGhostParticles::Update;
+    // ghost_update_ of a ring-decomposed run: first the ghost planes of the neighbour slabs (over the seam where needed),
+    // then the images of the other axes, which copy from own particles and ghost planes alike
+    class SeamGhostUpdate : public BaseDynamics<void>
+    {
+        SlabDecomposition &decomposition_;
+        PeriodicImages &images_;
+        std::vector<std::string> names_;
+
+      public:
+        SeamGhostUpdate(SlabDecomposition &d, PeriodicImages &images, std::initializer_list<const char *> names)
+            : decomposition_(d), images_(images), names_(names.begin(), names.end()) {}
+        void exec(Real = 0.0) override
+        {
+            images_.ensure(); // pending image creation changes the stored total, not the ghost planes: do it first
+            decomposition_.refreshGhosts(names_);
+            images_.update(names_);
+        }
+    };
     TaylorGreenParameters q_;
     Real U_f_, c_f_;
     SPHSystem sph_system;
@@ -64,7 +86,9 @@ class TaylorGreenCK
     std::unique_ptr<ReduceDynamicsCK<P, fluid_dynamics::AdvectionTimeStepCK>> fluid_advection_time_step;
     std::unique_ptr<ReduceDynamicsCK<P, fluid_dynamics::AcousticTimeStepCK<WeaklyCompressibleFluid>>> fluid_acoustic_time_step;
     std::vector<std::unique_ptr<PeriodicConditionUsingGhostParticles>> periodic_condition; // x, y(, z)
-    std::unique_ptr<GhostUpdate> volume_ghost_update, pressure_ghost_update, velocity_ghost_update;
+    std::unique_ptr<BaseDynamics<void>> volume_ghost_update, pressure_ghost_update, velocity_ghost_update;
+    std::unique_ptr<SlabDecomposition> decomposition; // ring runs only
+    SeamRing seam_ring;
     std::unique_ptr<InteractionDynamicsCK<P, fluid_dynamics::ViscousForceInnerCK>> viscous_force;
     std::unique_ptr<InteractionDynamicsCK<P, KernelGradientIntegralInner>> kernel_gradient_integral;
     std::unique_ptr<StateDynamics<P, fluid_dynamics::TransportVelocityCorrectionCK<SPHBody, TruncatedLinear>>> transport_velocity_correction;
@@ -91,8 +115,10 @@ class TaylorGreenCK
 
     // positions / velocities == nullptr: lattice and analytic initial condition generated here; otherwise the
     // arrays handed over (packed xyz, reference order), e.g. a jittered lattice made by the harness
+    // ring runs: positions / velocities / reference_ids are THIS rank's particles (global numbering in reference_ids)
     explicit TaylorGreenCK(const TaylorGreenParameters &q, const std::vector<Vecd> *positions = nullptr,
-                           const std::vector<Vecd> *velocities = nullptr, const BoundingBoxd *exact_system_bounds = nullptr)
+                           const std::vector<Vecd> *velocities = nullptr, const BoundingBoxd *exact_system_bounds = nullptr,
+                           const std::vector<UnsignedInt> *reference_ids = nullptr)
         : q_(q), U_f_(Real(q.U_f)), c_f_(Real(10.0) * U_f_), sph_system(caseBounds(q), Real(q.dp), q.dim),
           water_block(sph_system, makeShared<TaylorGreenWaterBlock>("WaterBody", q)), no_gravity(Vecd(0, 0, 0))
     {
@@ -104,7 +130,24 @@ class TaylorGreenCK
         for (int a = 0; a < q.dim; ++a) ghost_along_axis.emplace_back(new Ghost<PeriodicAlongAxis>(box, a));
         if (q.dim == 3) water_block.reserveFor(*ghost_along_axis[0], *ghost_along_axis[1], *ghost_along_axis[2]);
         else water_block.reserveFor(*ghost_along_axis[0], *ghost_along_axis[1]);
-        if (positions) water_block.generateParticlesFromPositions(*positions, Real(std::pow(Real(q.dp), Real(q.dim))));
+        std::vector<int> cuts;
+        if (q.ring)
+        {
+            // cell planes that tile the box; equal plane shares (the lattice is uniform); storage for the ghost planes of
+            // both neighbours, for migrants and for the images of the other axes of all of them
+            if (!positions) throw SphError("TaylorGreenCK: a ring run takes this rank's particles from the caller");
+            sphb200_mesh_t mesh = alignedPeriodicMesh(box, water_block.getSPHAdaptation().CutOffRadius(), q.dim, seam_ring);
+            if (seam_ring.box_planes() < q.nranks) throw SphError("TaylorGreenCK: fewer cell planes than ranks");
+            for (int r = 0; r <= q.nranks; ++r) cuts.push_back(seam_ring.first_plane() + (int)((long)seam_ring.box_planes() * r / q.nranks));
+            const int own_planes = cuts[q.rank + 1] - cuts[q.rank];
+            const size_t n = positions->size(), per_plane = n / (size_t)own_planes + 1;
+            size_t reserve = 0;
+            for (int a = 1; a < q.dim; ++a) reserve += ghost_along_axis[a]->reserveSize(Real(q.dp), q.dim);
+            const size_t bound = n + 4 * per_plane + 2 * reserve + 4096;
+            water_block.generateParticlesFromPositions(*positions, Real(std::pow(Real(q.dp), Real(q.dim))), bound, reference_ids);
+            water_block.getCellLinkedList().resetMesh(mesh, water_block.getBaseParticles().ParticlesBound());
+        }
+        else if (positions) water_block.generateParticlesFromPositions(*positions, Real(std::pow(Real(q.dp), Real(q.dim))));
         else water_block.generateParticles<BaseParticles, Lattice>();
 
         water_block_inner.reset(new Inner<>(water_block));
@@ -121,13 +164,27 @@ class TaylorGreenCK
         fluid_advection_time_step.reset(new ReduceDynamicsCK<P, AdvectionTimeStepCK>(water_block, U_f_));
         fluid_acoustic_time_step.reset(new ReduceDynamicsCK<P, AcousticTimeStepCK<WeaklyCompressibleFluid>>(water_block));
         if (q.fused_time_step) fluid_acoustic_step_2nd_half->fuseTimeStepReduction(*fluid_acoustic_time_step);
-        for (int a = 0; a < q.dim; ++a)
+        // ring runs: x is periodic through the slab exchange, images serve the other axes only
+        for (int a = q.ring ? 1 : 0; a < q.dim; ++a)
             periodic_condition.emplace_back(new PeriodicConditionUsingGhostParticles(water_block, *ghost_along_axis[a]));
         // what the neighbours of a ghost read, refreshed where it changes (throat.cpp:183-184 queues ghost_update_ the same way)
         PeriodicImages &images = periodic_condition[0]->images();
-        volume_ghost_update.reset(new GhostUpdate(images, {"VolumetricMeasure"}));
-        pressure_ghost_update.reset(new GhostUpdate(images, {"Pressure"}));
-        velocity_ghost_update.reset(new GhostUpdate(images, {"PosVolVel"}));
+        if (q.ring)
+        {
+            if (q.mu_f > 0 || q.transport_velocity) throw SphError("ring decomposition: viscous force / transport velocity are not decomposed yet");
+            decomposition.reset(new SlabDecomposition(water_block, q.rank, q.nranks, cuts, seam_ring));
+            fluid_advection_time_step->setDecomposition(decomposition.get());
+            fluid_acoustic_time_step->setDecomposition(decomposition.get());
+            volume_ghost_update.reset(new SeamGhostUpdate(*decomposition, images, {"VolumetricMeasure"}));
+            pressure_ghost_update.reset(new SeamGhostUpdate(*decomposition, images, {"Pressure"}));
+            velocity_ghost_update.reset(new SeamGhostUpdate(*decomposition, images, {"PosVolVel"}));
+        }
+        else
+        {
+            volume_ghost_update.reset(new GhostUpdate(images, {"VolumetricMeasure"}));
+            pressure_ghost_update.reset(new GhostUpdate(images, {"Pressure"}));
+            velocity_ghost_update.reset(new GhostUpdate(images, {"PosVolVel"}));
+        }
         fluid_acoustic_step_1st_half->addPreContactInteraction(*pressure_ghost_update);
         fluid_acoustic_step_2nd_half->addPreContactInteraction(*velocity_ghost_update);
         if (q.mu_f > 0) viscous_force.reset(new InteractionDynamicsCK<P, ViscousForceInnerCK>(*water_block_inner));
@@ -137,6 +194,7 @@ class TaylorGreenCK
             transport_velocity_correction.reset(new StateDynamics<P, TransportVelocityCorrectionCK<SPHBody, TruncatedLinear>>(water_block));
         }
         record_total_kinetic_energy.reset(new ReduceDynamicsCK<P, TotalMechanicalEnergyCK>(water_block, no_gravity));
+        if (decomposition) record_total_kinetic_energy->setDecomposition(decomposition.get());
         sv_physical_time = sph_system.getSystemVariableByName<Real>("PhysicalTime");
 
         // initial_condition.exec()
@@ -162,7 +220,9 @@ class TaylorGreenCK
     {
         if (bounding)
             for (auto &pc : periodic_condition) pc->bounding_.exec();
-        water_cell_linked_list->exec();
+        // ring: x is bounded by migration (what leaves the box over the seam arrives shifted on the other side)
+        if (decomposition) decomposition->rebuild();
+        else water_cell_linked_list->exec();
         for (auto &pc : periodic_condition) pc->ghost_creation_.exec();
         water_block_update_inner_relation->exec();
     }
@@ -202,7 +262,7 @@ class TaylorGreenCK
         acoustic_steps += n_inner;
         water_update_particle_position->exec();
         number_of_iterations++;
-        if (q_.sort_interval > 0 && number_of_iterations % q_.sort_interval == 0 && number_of_iterations != 1)
+        if (!decomposition && q_.sort_interval > 0 && number_of_iterations % q_.sort_interval == 0 && number_of_iterations != 1)
         {
             particle_sort->exec();
             fluid_acoustic_time_step->setPrimed(false);

@@ -24,6 +24,13 @@ class MeshT(C.Structure):
     _fields_ = [("lower", C.c_float * 3), ("spacing", C.c_float), ("cells", C.c_int32 * 3)]
 
 
+class SeamT(C.Structure):
+    """sphb200_seam_t: the periodic seam of a ring of slabs (x axis of the mesh, box planes, plane x ranges)."""
+    _fields_ = [("mesh_lower", C.c_float), ("mesh_spacing", C.c_float), ("mesh_cells", C.c_int32), ("first_plane", C.c_int32),
+                ("box_planes", C.c_int32), ("own_min", C.c_float), ("own_max", C.c_float), ("ghost_low_min", C.c_float),
+                ("ghost_low_max", C.c_float), ("ghost_high_min", C.c_float), ("ghost_high_max", C.c_float)]
+
+
 class KernelT(C.Structure):
     _fields_ = [("dim", C.c_int32), ("kind", C.c_int32), ("h", C.c_float), ("src_h", C.c_float),
                 ("kernel_size", C.c_float), ("dimension_factor", C.c_float), ("w", C.c_float * 24), ("dw", C.c_float * 24)]
@@ -146,6 +153,10 @@ SYMBOLS = {
     "sphb200_comm_rank": (_I, [_CTX]),
     "sphb200_comm_size": (_I, [_CTX]),
     "sphb200_comm_exchange": (_I, [_CTX, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "sphb200_comm_create_self": (_I, [_CTX]),
+    "sphb200_comm_set_ring": (_I, [_CTX, _I]),
+    "sphb200_comm_is_ring": (_I, [_CTX]),
+    "sphb200_seam_shift": (_I, [_CTX, _P, _U32, _U32, C.c_float, _P, _P]),
     "sphb200_comm_allreduce_max_f32": (_I, [_CTX, _P, _I, _P]),
     "sphb200_comm_allreduce_sum_f64": (_I, [_CTX, _P, _I, _P]),
     "sphb200_comm_allgather_u64": (_I, [_CTX, _P, _P, _I, _P]),

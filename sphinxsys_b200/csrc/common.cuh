@@ -25,6 +25,8 @@ struct sphb200_context
     // slab-decomposed runs: NCCL communicator (comm.cu), null for single-GPU use
     void *comm;
     int rank, nranks;
+    int ring;      // 1: the slab chain is closed (periodic along x): rank 0 and rank nranks-1 are neighbours
+    int self_comm; // 1: communicator of ONE rank without NCCL (a ring of one slab: exchanges are device copies)
 };
 
 #define SPH_CHECK_ARG(ctx, cond, msg)                                                              \

@@ -19,6 +19,14 @@ struct Handle
     std::unique_ptr<DamBreakCK> sim;   // dam break (CK or legacy spelling) ...
     std::unique_ptr<TaylorGreenCK> tg; // ... or the periodic Taylor-Green vortex
     std::unique_ptr<HostTransferPipeline> pipeline; // overlapped host <-> device transfers of the fluid body (bench e2e)
+    bool owns_comm = false; // ring runs made the context's communicator: give the context back without it
+    ~Handle()
+    {
+        pipeline.reset();
+        tg.reset();
+        sim.reset();
+        if (owns_comm) sphb200_comm_destroy(execution_instance().ctx());
+    }
     SPHBody &body(int which)
     {
         if (tg)
@@ -145,6 +153,18 @@ extern "C"
     }
 
     // host-only: how far a re-balancing may move the cuts in one go (SlabDecomposition::recut)
+    // mesh and seam thresholds of a ring-decomposed periodic body (host arithmetic only: no GPU needed)
+    int sphck_aligned_periodic_mesh(const double *lower, const double *upper, double cutoff, int dim, sphb200_mesh_t *mesh,
+                                    sphb200_seam_t *seam)
+    {
+        return guarded([&] {
+            const Vecd lo((Real)lower[0], (Real)lower[1], (Real)lower[2]), up((Real)upper[0], (Real)upper[1], (Real)upper[2]);
+            BoundingBoxd box(lo, up);
+            SeamRing ring;
+            *mesh = alignedPeriodicMesh(box, Real(cutoff), dim, ring);
+            *seam = ring.seam;
+        });
+    }
     int sphck_limit_cut_moves(const int32_t *old_cuts, const int32_t *wanted, int nranks, int32_t *cuts_out)
     {
         return guarded([&] {
@@ -243,6 +263,42 @@ extern "C"
         }
         return h;
     }
+    // Ring-decomposed Taylor-Green run (periodic along x through the slab exchange, config 4 on N GPUs): this rank's
+    // particles with their global numbers. nranks == 1 makes a ring of one slab on a communicator without NCCL.
+    void *sphck_taylor_green_create_ring(const sphck_taylor_green_options *o, const float *xyz, const float *vel_xyz,
+                                         const uint32_t *global_ids, uint64_t n, int32_t rank, int32_t nranks, const void *unique_id)
+    {
+        Handle *h = new Handle();
+        int rc = guarded([&] {
+            if (!xyz || !vel_xyz || !global_ids) throw SphError("ring run: positions, velocities and global ids are required");
+            execution_instance().setDevice(o->device);
+            sphb200_context_t *ctx = execution_instance().ctx();
+            if (nranks > 1) execution_instance().check(sphb200_comm_create(ctx, nranks, rank, unique_id), "sphb200_comm_create");
+            else execution_instance().check(sphb200_comm_create_self(ctx), "sphb200_comm_create_self");
+            execution_instance().check(sphb200_comm_set_ring(ctx, 1), "sphb200_comm_set_ring");
+            h->owns_comm = true;
+            TaylorGreenParameters q;
+            q.dim = o->dim; q.dp = o->dp; q.L = o->L; q.U_f = o->U_f;
+            q.fused_time_step = o->fused_time_step != 0;
+            q.fused_regularization = o->fused_regularization != 0;
+            q.sort_interval = 0;
+            q.ring = true; q.rank = rank; q.nranks = nranks;
+            std::vector<Vecd> pos = toVecd(xyz, n), vel = toVecd(vel_xyz, n);
+            std::vector<UnsignedInt> ids(global_ids, global_ids + n);
+            BoundingBoxd sb;
+            if (o->use_system_bounds)
+                sb = BoundingBoxd(Vecd(Real(o->system_lower[0]), Real(o->system_lower[1]), Real(o->system_lower[2])),
+                                  Vecd(Real(o->system_upper[0]), Real(o->system_upper[1]), Real(o->system_upper[2])));
+            h->tg.reset(new TaylorGreenCK(q, &pos, &vel, o->use_system_bounds ? &sb : nullptr, &ids));
+            if (o->relation_stride >= 0) h->tg->water_block_inner->fixed_stride_ = (uint32_t)o->relation_stride;
+        });
+        if (rc)
+        {
+            delete h;
+            return nullptr;
+        }
+        return h;
+    }
     void sphck_destroy(void *hp) { delete (Handle *)hp; }
 
     uint64_t sphck_count(void *hp, int which)
@@ -287,6 +343,9 @@ extern "C"
                 else if (op == "ghost_creation") { for (auto &pc : s.periodic_condition) pc->ghost_creation_.exec(); }
                 else if (op == "ghost_update") s.periodic_condition[0]->ghost_update_.exec();
                 else if (op == "ghost_particles") { s.periodic_condition[0]->images().ensure(); r = (double)s.periodic_condition[0]->images().ghostParticles(); }
+                else if (op == "plane_ghost_particles") r = s.decomposition ? (double)s.decomposition->ghostParticles() : 0.0;
+                else if (op == "handed_over") r = s.decomposition ? (double)s.decomposition->migratedOut() : 0.0;
+                else if (op == "box_planes") r = (double)s.seam_ring.box_planes();
                 else if (op == "relations") s.water_block_update_inner_relation->exec();
                 else if (op == "update_configuration") s.updateConfiguration(a0 != 0.0);
                 else if (op == "sort") { s.particle_sort->exec(); s.fluid_acoustic_time_step->setPrimed(false); }

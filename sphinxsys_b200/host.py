@@ -56,6 +56,10 @@ def load():
         L.sphck_dambreak_create.argtypes = [C.POINTER(Options), C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]
         L.sphck_taylor_green_create.restype = C.c_void_p
         L.sphck_taylor_green_create.argtypes = [C.POINTER(TaylorGreenOptions), C.c_void_p, C.c_void_p, C.c_uint64]
+        L.sphck_aligned_periodic_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
+        L.sphck_taylor_green_create_ring.restype = C.c_void_p
+        L.sphck_taylor_green_create_ring.argtypes = [C.POINTER(TaylorGreenOptions), C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64,
+                                                     C.c_int32, C.c_int32, C.c_char_p]
         L.sphck_destroy.argtypes = [C.c_void_p]
         L.sphck_count.restype = C.c_uint64
         L.sphck_count.argtypes = [C.c_void_p, C.c_int]
@@ -106,6 +110,16 @@ def plan_slab_cuts(per_plane, nranks):
     if load().sphck_plan_slab_cuts(h.ctypes.data, h.size, int(nranks), out.ctypes.data) != 0:
         raise capi.SphB200Error("plan_slab_cuts failed: " + load().sphck_last_error().decode())
     return out
+
+
+def aligned_periodic_mesh(lower, upper, cutoff, dim=3):
+    """(MeshT, SeamT) of a ring-decomposed periodic body (alignedPeriodicMesh in include/sphinxsys_ck/slab_decomposition.h)."""
+    lo = (C.c_double * 3)(*[float(v) for v in lower])
+    up = (C.c_double * 3)(*[float(v) for v in upper])
+    mesh, seam = capi.MeshT(), capi.SeamT()
+    if load().sphck_aligned_periodic_mesh(lo, up, float(cutoff), int(dim), C.byref(mesh), C.byref(seam)) != 0:
+        raise capi.SphB200Error("aligned_periodic_mesh failed: " + load().sphck_last_error().decode())
+    return mesh, seam
 
 
 def limit_cut_moves(old_cuts, wanted):
@@ -337,7 +351,10 @@ class TaylorGreenCK(DamBreakCK):
     Shares the driving interface of DamBreakCK (exec by name, upload/download in the reference particle order)."""
 
     def __init__(self, case=None, device_index=0, fused_time_step=True, sort_interval=100, relation_stride=None,
-                 fused_regularization=True, dim=3, n_side=32, generate=False, mu_f=0.0, transport_velocity=False):
+                 fused_regularization=True, dim=3, n_side=32, generate=False, mu_f=0.0, transport_velocity=False,
+                 ring=False, rank=0, nranks=1, unique_id=None, own=None):
+        """ring=True: periodic along x through a ring of slabs, one process per GPU (nranks == 1: a ring of one slab).
+        `own` (indices into the case's particle arrays, ascending) are this rank's particles; default all of them."""
         self.lib = load()
         o = TaylorGreenOptions()
         o.mu_f, o.transport_velocity = float(mu_f), int(bool(transport_velocity))
@@ -349,8 +366,18 @@ class TaylorGreenCK(DamBreakCK):
         o.sort_interval, o.device = int(sort_interval), int(device_index)
         o.relation_stride = -1 if relation_stride is None else int(relation_stride)
         o.use_system_bounds = 0
-        self.rank, self.nranks, self.case = 0, 1, case
-        if case is not None and not generate:
+        self.rank, self.nranks, self.case = int(rank), int(nranks), case
+        if ring:
+            if case is None:
+                raise ValueError("a ring run needs the case (this rank's particles are cut out of it)")
+            own = np.arange(case.n_fluid) if own is None else np.asarray(own)
+            fp = np.ascontiguousarray(case.fluid_pos[own], dtype=np.float32)
+            fv = np.ascontiguousarray(case.fluid_vel[own], dtype=np.float32)
+            ids = np.ascontiguousarray(own, dtype=np.uint32)
+            uid = bytes(unique_id) if unique_id is not None else bytes(128)
+            self._h = self.lib.sphck_taylor_green_create_ring(C.byref(o), fp.ctypes.data, fv.ctypes.data, ids.ctypes.data,
+                                                              fp.shape[0], int(rank), int(nranks), uid)
+        elif case is not None and not generate:
             if case.system_lower is not None:
                 o.use_system_bounds = 1
                 for d in range(3):

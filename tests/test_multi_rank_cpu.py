@@ -110,3 +110,54 @@ def test_recut_moves_stay_between_neighbours():
         c = host.limit_cut_moves(a, b)
         assert c[0] == 0 and c[-1] == planes and np.all(np.diff(c) >= 1)
         assert all(a[r - 1] + 1 <= c[r] <= a[r + 1] - 1 for r in range(1, n))
+
+
+@pytest.mark.parametrize("n_side", [16, 20, 32, 100, 256])
+def test_ring_seam_thresholds_follow_the_cell_arithmetic(n_side):
+    """Periodic ring of slabs (config 4 on N GPUs): the cell planes tile the box and the seam thresholds handed to
+    sphb200_seam_shift are exactly the x ranges of the planes in the mesh's own cell arithmetic (oracle cell keys), so a
+    shifted particle can be held in the plane it belongs to: leavers inside the box planes, boundary planes in the one
+    ghost plane beyond the face."""
+    from oracle import oracle as orc
+    from sphinxsys_b200 import host, hostmath as hm
+    f = np.float32
+    cutoff = f(2.0) * f(1.3) * f(1.0 / n_side)
+    m, sm = host.aligned_periodic_mesh((0, 0, 0), (1, 1, 1), cutoff)
+    mesh = hm.MeshSpec(tuple(m.lower), m.spacing, tuple(m.cells))
+    k0, P = sm.first_plane, sm.box_planes
+    assert m.spacing >= cutoff and P == int(1.0 / cutoff) and m.cells[0] == P + 2 * k0
+
+    def plane(x):
+        pos = np.full((len(x), 3), 0.5, dtype=f)
+        pos[:, 0] = x
+        cell, _ = orc.cell_keys(pos, mesh)
+        return cell.astype(np.int64) // (m.cells[1] * m.cells[2])
+
+    t = np.array([sm.ghost_low_min, sm.ghost_low_max, sm.own_min, sm.own_max, sm.ghost_high_min, sm.ghost_high_max], dtype=f)
+    assert plane(t).tolist() == [k0 - 1, k0 - 1, k0, k0 + P - 1, k0 + P, k0 + P]
+    beyond = np.array([np.nextafter(t[0], f(-9)), np.nextafter(t[2], f(-9)), np.nextafter(t[3], f(9)), np.nextafter(t[5], f(9))], dtype=f)
+    assert plane(beyond).tolist() == [k0 - 2, k0 - 1, k0 + P, k0 + P + 1]
+    assert abs(float(sm.own_min)) < 1e-7 and abs(float(sm.ghost_high_min) - 1.0) < 1e-6
+
+    # k_seam_shift restated: what crosses the seam lands in the plane its sender saw it in, moved by +/- P planes
+    rng = np.random.default_rng(n_side)
+    s, L = f(m.spacing), f(1.0)
+    for delta in (L, -L):
+        if delta > 0:   # rank 0 -> last rank: its first plane and its leavers (just below the box)
+            x = np.concatenate([rng.uniform(-0.3 * s, 0.0, 4000), rng.uniform(0.0, s, 4000), [sm.own_min, np.nextafter(f(sm.own_min), f(-9)),
+                                np.nextafter(f(sm.own_min) + s, f(-9)), -1e-30, 0.0]]).astype(f)
+            x = x[plane(x) <= k0]
+            y = x + delta
+            leaver = plane(x) < k0
+            y = np.where(leaver, np.minimum(y, f(sm.own_max)), np.minimum(np.maximum(y, f(sm.ghost_high_min)), f(sm.ghost_high_max)))
+        else:           # last rank -> rank 0: its last plane and its leavers (just above the box)
+            x = np.concatenate([rng.uniform(1.0, 1.0 + 0.3 * s, 4000), rng.uniform(1.0 - s, 1.0, 4000),
+                                [sm.own_max, sm.ghost_high_min, 1.0, np.nextafter(f(1.0), f(9))]]).astype(f)
+            x = x[plane(x) >= k0 + P - 1]
+            y = x + delta
+            leaver = plane(x) >= k0 + P
+            y = np.where(leaver, np.maximum(y, f(sm.own_min)), np.maximum(np.minimum(y, f(sm.ghost_low_max)), f(sm.ghost_low_min)))
+        moved = plane(y.astype(f)) - plane(x)
+        assert np.all(moved == (P if delta > 0 else -P)), "a shifted particle changed its plane relative to the box"
+        free = (y == x + delta)
+        assert free.mean() > 0.99, "the clamps act in rounding cases only"
