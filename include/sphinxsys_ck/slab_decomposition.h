@@ -11,8 +11,8 @@
 //   pick the particles next to each cut (those that left the slab + the boundary plane) with one pass over the own
 //   positions, hand them to the neighbour in one message per variable, append what arrives, sort everything into cell order. Particles move less than one cell per advection step (CFL),
 //   so leavers are always in the plane next to the cut. Dynamics then run on the active slot range only.
-// * Cuts are particle-count quantiles of the initial distribution along x (planSlabCuts); they stay fixed in this
-//   round (dynamic re-cutting at sort time is listed as next in DESIGN.md §6).
+// * Cuts are particle-count quantiles of the distribution along x (planSlabCuts), re-balanced at the sort cadence
+//   (recut()). Periodic boxes close the chain of slabs into a ring (SeamRing below).
 #ifndef SPHINXSYS_CK_SLAB_DECOMPOSITION_H
 #define SPHINXSYS_CK_SLAB_DECOMPOSITION_H
 
