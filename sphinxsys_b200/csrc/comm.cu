@@ -150,7 +150,8 @@ extern "C" int sphb200_comm_is_ring(const sphb200_context_t *ctx) { return ctx &
 
 // One grouped exchange with the left (rank-1) and right (rank+1) neighbour: `count` segments per direction.
 // send_left[k]/send_left_bytes[k] go to rank-1 and arrive in ITS recv_right[k]; symmetric for the other direction.
-// Ranks at the ends of the slab chain skip the missing side. All pointers are device pointers.
+// Ranks at the ends of the slab chain skip the missing side; on a ring (sphb200_comm_set_ring) the chain has no ends.
+// All pointers are device pointers.
 extern "C" int sphb200_comm_exchange(sphb200_context_t *ctx, int count, const void *const *send_left, const size_t *send_left_bytes,
                                      void *const *recv_left, const size_t *recv_left_bytes, const void *const *send_right,
                                      const size_t *send_right_bytes, void *const *recv_right, const size_t *recv_right_bytes,

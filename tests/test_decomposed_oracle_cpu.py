@@ -96,6 +96,18 @@ def test_periodic_ring_bit_identical(nranks, steps, drift):
     assert seam.wrapped > 0, "particles should have crossed the periodic seam"
 
 
+def test_periodic_ring_of_one_slab_bit_identical():
+    """One rank that is its own neighbour on both sides (what tests/test_gpu_zz_periodic_ring.py runs on the GPU): x periodic
+    through the seam exchange alone, y / z through the image entries."""
+    case, first, planes = _ring_case(2.0)
+    g = _single(case, 12, free_surface=0)
+    sr = dec.SlabRank(case, dec.SerialComm(), [first, first + planes], ring=True, free_surface=0)
+    for _ in range(12):
+        sr.step_outer()
+    assert sr.wrapped > 0 and sr.n_ghost[0] > 0 and sr.n_ghost[1] > 0
+    assert _mismatches(g, dec.gather_by_gid([sr.own_state()], case.n_fluid)) == []
+
+
 def test_aligned_periodic_mesh_keeps_neighbour_sets():
     """The aligned mesh (spacing L / floor(L / r_c) >= r_c) changes cells, not neighbours: same sorted rows as the case mesh."""
     case = cases.taylor_green(dim=3, n_side=16)
