@@ -23,6 +23,7 @@ struct TaylorGreenParameters
     int dim = 3;
     double dp = 1.0 / 32.0;   // global_resolution
     double L = 1.0;           // DL = DH (= DW): the periodic box is [0, L]^dim (taylor_green.cpp:14-15)
+    double x_scale = 1.0;     // box [0, x_scale L] x [0, L]^(dim-1): the domain replicated along x for weak scaling
     double rho0_f = 1.0, U_f = 1.0; // :19-20; c_f = 10 U_f
     int sort_interval = 100;
     bool fused_time_step = true;
@@ -40,7 +41,7 @@ class TaylorGreenWaterBlock : public ComplexShape
   public:
     TaylorGreenWaterBlock(const std::string &name, const TaylorGreenParameters &q) : ComplexShape(name)
     {
-        double half[3] = {0.5 * q.L, 0.5 * q.L, q.dim == 3 ? 0.5 * q.L : 0.0};
+        double half[3] = {0.5 * q.L * q.x_scale, 0.5 * q.L, q.dim == 3 ? 0.5 * q.L : 0.0};
         add<GeometricShapeBox>(half, half);
     }
 };
@@ -101,7 +102,7 @@ class TaylorGreenCK
 
     static BoundingBoxd caseBounds(const TaylorGreenParameters &q)
     {
-        return BoundingBoxd(Vecd(0, 0, 0), Vecd(Real(q.L), Real(q.L), q.dim == 3 ? Real(q.L) : Real(0)));
+        return BoundingBoxd(Vecd(0, 0, 0), Vecd(Real(q.L * q.x_scale), Real(q.L), q.dim == 3 ? Real(q.L) : Real(0)));
     }
     // TaylorGreenInitialCondition (taylor_green.cpp:44-57) and its usual 3-D extension
     static Vecd initialVelocity(const Vecd &x, int dim, Real U)
@@ -141,8 +142,15 @@ class TaylorGreenCK
             for (int r = 0; r <= q.nranks; ++r) cuts.push_back(seam_ring.first_plane() + (int)((long)seam_ring.box_planes() * r / q.nranks));
             const int own_planes = cuts[q.rank + 1] - cuts[q.rank];
             const size_t n = positions->size(), per_plane = n / (size_t)own_planes + 1;
+            // images of the other axes: Ghost<PeriodicAlongAxis>::reserveSize with the slab (own + 2 ghost planes) as x extent
             size_t reserve = 0;
-            for (int a = 1; a < q.dim; ++a) reserve += ghost_along_axis[a]->reserveSize(Real(q.dp), q.dim);
+            for (int a = 1; a < q.dim; ++a)
+            {
+                double face = 1.0;
+                for (int d = 0; d < q.dim; ++d)
+                    if (d != a) face *= (d == 0 ? double(own_planes + 2) * double(mesh.spacing) : double(box.upper_[d] - box.lower_[d])) / q.dp + 8.0;
+                reserve += (size_t)std::ceil(2.0 * 4.0 * face);
+            }
             const size_t bound = n + 4 * per_plane + 2 * reserve + 4096;
             water_block.generateParticlesFromPositions(*positions, Real(std::pow(Real(q.dp), Real(q.dim))), bound, reference_ids);
             water_block.getCellLinkedList().resetMesh(mesh, water_block.getBaseParticles().ParticlesBound());

@@ -119,9 +119,17 @@ def aligned_periodic_mesh(case, ghost_planes=2):
     L = R(up - lo)
     planes = int(np.floor(float(L) / float(case.kernel.cutoff)))
     spacing = R(L / R(planes))
-    dim = case.dim
-    cells = [planes + 2 * ghost_planes] * dim + [1] * (3 - dim)
-    lower = [float(R(lo - R(ghost_planes) * spacing))] * dim + [0.0] * (3 - dim)
+    cells, lower = [], []
+    for d in range(3):
+        if d >= case.dim:
+            cells.append(1)
+            lower.append(0.0)
+            continue
+        lo_d = R(R(case.periodic_lower[d]) - R(ghost_planes) * spacing)
+        lower.append(float(lo_d))
+        # x: the box planes exactly; the other axes: cover the box plus the ghost layers (alignedPeriodicMesh, host layer)
+        cells.append(planes + 2 * ghost_planes if d == 0
+                     else int(np.ceil(float(R(case.periodic_upper[d]) - lo_d) / float(spacing))) + ghost_planes)
     return hm.MeshSpec(tuple(lower), float(spacing), tuple(cells)), ghost_planes, planes
 
 

@@ -216,21 +216,25 @@ def random_block(n, seed=1, dp=0.01, dtype=np.float32, particles_per_cell=17.6):
     return case
 
 
-def taylor_green(dim=3, n_side=32, jitter=0.05, seed=2024, dtype=np.float32, L=1.0, U=1.0) -> DamBreakCase:
+def taylor_green(dim=3, n_side=32, jitter=0.05, seed=2024, dtype=np.float32, L=1.0, U=1.0, x_scale=1) -> DamBreakCase:
     """Periodic Taylor-Green vortex (BASELINE config 4): n_side^dim particles on the lattice of the periodic box
     [0, L]^dim with a deterministic jitter of `jitter` dp, no walls, no gravity, c0 = 10 U.
 
     Reference: tests/2d_examples/test_2d_taylor_green/taylor_green.cpp:14-57 (box, material, initial condition; the 3-D
     velocity field is the usual extension v = U (sin 2pi x cos 2pi y cos 2pi z, -cos 2pi x sin 2pi y cos 2pi z, 0)).
-    Returned in the DamBreakCase shape (without wall particles) so the oracle and the host layer both consume it."""
+    Returned in the DamBreakCase shape (without wall particles) so the oracle and the host layer both consume it.
+    `x_scale` (integer) replicates the box along x: [0, x_scale L] x [0, L]^(dim-1), x_scale n_side^dim particles, the
+    weak-scaling shape of config 4; the velocity field keeps its period L."""
     R = dtype
     dp = L / n_side
     h = 1.3 * dp
-    case = DamBreakCase(dim, dp, R, L, L, L if dim == 3 else 0.0, L, L, L if dim == 3 else 0.0, 0.0, 1.0, 0.0, float(U), 10.0 * U, h)
+    Lx = L * int(x_scale)
+    case = DamBreakCase(dim, dp, R, Lx, L, L if dim == 3 else 0.0, Lx, L, L if dim == 3 else 0.0, 0.0, 1.0, 0.0, float(U), 10.0 * U, h)
+    ext = [Lx, L, L][:dim]
     sys_lo = np.array([0.0 - 4 * dp] * dim)
-    sys_up = np.array([L + 4 * dp] * dim)
+    sys_up = np.array([e + 4 * dp for e in ext])
     axes = [_lattice_axis(sys_lo[d], sys_up[d], dp, R) for d in range(dim)]
-    sel = [a[(a >= 0.0) & (a <= L)] for a in axes]
+    sel = [a[(a >= 0.0) & (a <= ext[d])] for d, a in enumerate(axes)]
     grids = np.meshgrid(*sel, indexing="ij")
     pos = np.stack([g_.reshape(-1) for g_ in grids], axis=1).astype(np.float64)
     if jitter:
@@ -258,7 +262,7 @@ def taylor_green(dim=3, n_side=32, jitter=0.05, seed=2024, dtype=np.float32, L=1
     case.sigma0 = hm.lattice_number_density(case.kernel, dp)
     case.periodic_axes = (1 << dim) - 1
     case.periodic_lower = (0.0, 0.0, 0.0)
-    case.periodic_upper = tuple(float(R(L)) if d < dim else 0.0 for d in range(3))
+    case.periodic_upper = tuple(float(R(ext[d])) if d < dim else 0.0 for d in range(3))
     case.system_lower = tuple(float(R(v)) for v in sys_lo) + ((0.0,) if dim == 2 else ())
     case.system_upper = tuple(float(R(v)) for v in sys_up) + ((0.0,) if dim == 2 else ())
     return case

@@ -232,6 +232,7 @@ extern "C"
         int32_t use_system_bounds;
         double mu_f;                 // > 0: viscous (ViscousForceInnerCK)
         int32_t transport_velocity;  // KernelGradientIntegralInner + TransportVelocityCorrectionCK
+        double x_scale;              // box [0, x_scale L] x [0, L]^(dim-1) (0 is read as 1)
     };
     // xyz / vel_xyz may be NULL: lattice and analytic initial condition are generated by the C++ case then
     void *sphck_taylor_green_create(const sphck_taylor_green_options *o, const float *xyz, const float *vel_xyz, uint64_t n)
@@ -241,6 +242,7 @@ extern "C"
             execution_instance().setDevice(o->device);
             TaylorGreenParameters q;
             q.dim = o->dim; q.dp = o->dp; q.L = o->L; q.U_f = o->U_f;
+            q.x_scale = o->x_scale > 0 ? o->x_scale : 1.0;
             q.fused_time_step = o->fused_time_step != 0;
             q.fused_regularization = o->fused_regularization != 0;
             q.sort_interval = o->sort_interval;
@@ -279,6 +281,7 @@ extern "C"
             h->owns_comm = true;
             TaylorGreenParameters q;
             q.dim = o->dim; q.dp = o->dp; q.L = o->L; q.U_f = o->U_f;
+            q.x_scale = o->x_scale > 0 ? o->x_scale : 1.0;
             q.fused_time_step = o->fused_time_step != 0;
             q.fused_regularization = o->fused_regularization != 0;
             q.sort_interval = 0;

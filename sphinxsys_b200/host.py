@@ -38,7 +38,7 @@ class TaylorGreenOptions(C.Structure):
     _fields_ = [("dim", C.c_int32), ("dp", C.c_double), ("L", C.c_double), ("U_f", C.c_double), ("fused_time_step", C.c_int32),
                 ("fused_regularization", C.c_int32), ("sort_interval", C.c_int32), ("device", C.c_int32),
                 ("relation_stride", C.c_int32), ("system_lower", C.c_double * 3), ("system_upper", C.c_double * 3),
-                ("use_system_bounds", C.c_int32), ("mu_f", C.c_double), ("transport_velocity", C.c_int32)]
+                ("use_system_bounds", C.c_int32), ("mu_f", C.c_double), ("transport_velocity", C.c_int32), ("x_scale", C.c_double)]
 
 
 _lib = None
@@ -352,14 +352,17 @@ class TaylorGreenCK(DamBreakCK):
 
     def __init__(self, case=None, device_index=0, fused_time_step=True, sort_interval=100, relation_stride=None,
                  fused_regularization=True, dim=3, n_side=32, generate=False, mu_f=0.0, transport_velocity=False,
-                 ring=False, rank=0, nranks=1, unique_id=None, own=None):
+                 ring=False, rank=0, nranks=1, unique_id=None, own=None, local_ids=None):
         """ring=True: periodic along x through a ring of slabs, one process per GPU (nranks == 1: a ring of one slab).
-        `own` (indices into the case's particle arrays, ascending) are this rank's particles; default all of them."""
+        `own` (indices into the case's particle arrays, ascending) are this rank's particles; default all of them.
+        `local_ids`: the case holds THIS rank's particles only and these are their global numbers (large runs)."""
         self.lib = load()
         o = TaylorGreenOptions()
         o.mu_f, o.transport_velocity = float(mu_f), int(bool(transport_velocity))
+        o.x_scale = 1.0
         if case is not None:
-            o.dim, o.dp, o.L, o.U_f = case.dim, case.dp, case.DL, case.U_ref
+            o.dim, o.dp, o.L, o.U_f = case.dim, case.dp, case.DH, case.U_ref
+            o.x_scale = case.DL / case.DH
         else:
             o.dim, o.dp, o.L, o.U_f = dim, 1.0 / n_side, 1.0, 1.0
         o.fused_time_step, o.fused_regularization = int(fused_time_step), int(fused_regularization)
@@ -370,10 +373,17 @@ class TaylorGreenCK(DamBreakCK):
         if ring:
             if case is None:
                 raise ValueError("a ring run needs the case (this rank's particles are cut out of it)")
-            own = np.arange(case.n_fluid) if own is None else np.asarray(own)
-            fp = np.ascontiguousarray(case.fluid_pos[own], dtype=np.float32)
-            fv = np.ascontiguousarray(case.fluid_vel[own], dtype=np.float32)
-            ids = np.ascontiguousarray(own, dtype=np.uint32)
+            if local_ids is not None:
+                fp = np.ascontiguousarray(case.fluid_pos, dtype=np.float32)
+                fv = np.ascontiguousarray(case.fluid_vel, dtype=np.float32)
+                ids = np.ascontiguousarray(local_ids, dtype=np.uint32)
+                if ids.size != fp.shape[0]:
+                    raise ValueError("local_ids: one global number per particle of the case")
+            else:
+                own = np.arange(case.n_fluid) if own is None else np.asarray(own)
+                fp = np.ascontiguousarray(case.fluid_pos[own], dtype=np.float32)
+                fv = np.ascontiguousarray(case.fluid_vel[own], dtype=np.float32)
+                ids = np.ascontiguousarray(own, dtype=np.uint32)
             uid = bytes(unique_id) if unique_id is not None else bytes(128)
             self._h = self.lib.sphck_taylor_green_create_ring(C.byref(o), fp.ctypes.data, fv.ctypes.data, ids.ctypes.data,
                                                               fp.shape[0], int(rank), int(nranks), uid)

@@ -46,8 +46,8 @@ def _dam_break():
     return case, planes
 
 
-def _ring_case(drift):
-    case = cases.taylor_green(dim=3, n_side=16)
+def _ring_case(drift, x_scale=1, n_side=16):
+    case = cases.taylor_green(dim=3, n_side=n_side, x_scale=x_scale)
     mesh, first, planes = dec.aligned_periodic_mesh(case)
     vel = case.fluid_vel.copy()
     vel[:, 0] += np.float32(drift)  # uniform drift: particles cross the seam between the last and the first rank
@@ -94,6 +94,17 @@ def test_periodic_ring_bit_identical(nranks, steps, drift):
     assert _mismatches(g, dec.gather_by_gid(states, case.n_fluid)) == []
     seam = ranks[-1] if drift > 0 else ranks[0]
     assert seam.wrapped > 0, "particles should have crossed the periodic seam"
+
+
+def test_periodic_ring_replicated_box_bit_identical():
+    """Weak-scaling shape of config 4: the box replicated along x (2 L x L x L), one copy per rank."""
+    case, first, planes = _ring_case(1.5, x_scale=2, n_side=12)
+    assert case.n_fluid == 2 * 12 ** 3 and case.periodic_upper[0] == 2.0
+    cuts = dec.plan_cuts(dec.x_plane(case.fluid_pos, case.mesh), first, first + planes, 2)
+    g = _single(case, 10, free_surface=0)
+    states, ranks = dec.run_threads(case, 2, cuts, 10, ring=True, free_surface=0)
+    assert _mismatches(g, dec.gather_by_gid(states, case.n_fluid)) == []
+    assert ranks[-1].wrapped > 0 and abs(ranks[0].n_own - ranks[1].n_own) < 0.15 * case.n_fluid  # 9 planes: 4 + 5
 
 
 def test_periodic_ring_of_one_slab_bit_identical():
