@@ -342,6 +342,24 @@ class SlabRank:
         self.outer_steps += 1
         self.rebuild()
 
+    def recut(self, plan, limit):
+        """SlabDecomposition::recut: new cuts from the CURRENT particles-per-plane histogram of all ranks
+        (`plan(hist, nranks)`, the host layer's planSlabCuts), every cut moved at most to the far end of an adjacent slab
+        (`limit(old, wanted)`, limitCutMoves), so that the hand-over stays between neighbour ranks — which rebuild()
+        asserts. Returns True if the cuts changed."""
+        if self.ring:
+            raise NotImplementedError("re-cutting on a ring of slabs")
+        planes_total = int(self.case.mesh.cells[0])
+        mine = np.bincount(self._planes(self.sim.real("Position", 3).reshape(-1, 3)[: self.n_own]), minlength=planes_total)
+        hist = np.zeros(planes_total, dtype=np.uint64)
+        for h in self.comm.route({r: mine for r in range(self.size)}).values():
+            hist += h.astype(np.uint64)
+        new = [int(c) for c in limit(np.asarray(self.cuts, dtype=np.int32), plan(hist, self.size))]
+        changed = new != self.cuts
+        self.cuts = new
+        self.rebuild(bound=False)
+        return changed
+
     def own_state(self):
         """{name: values of the own particles} plus "gid" (ascending), as of the last configuration update."""
         out = {nm: self.sim.real(nm, w).reshape(-1, w)[: self.n_own].copy() for nm, w in VARIABLES}

@@ -75,6 +75,45 @@ def test_dam_break_cuts_do_not_matter():
         assert _mismatches(g, dec.gather_by_gid(states, case.n_fluid)) == []
 
 
+def test_dam_break_recut_keeps_bit_identity():
+    """Re-balancing at the sort cadence (SlabDecomposition::recut) with the host layer's own planner: deliberately skewed
+    initial cuts are pulled back over a few re-cuts, every hand-over goes to a neighbour rank (asserted inside rebuild),
+    and the fields stay those of the single-domain run."""
+    import threading
+    from sphinxsys_b200 import host
+    case, planes = _dam_break()
+    nranks, steps = 3, 24
+    balanced = dec.plan_cuts(planes, 0, case.mesh.cells[0], nranks)
+    skewed = [balanced[0], balanced[1] + 3, balanced[2] + 6, balanced[3]]
+    g = _single(case, steps)
+    comms = dec.ThreadComm.make(nranks)
+    ranks, errors, changes = [None] * nranks, [], [0] * nranks
+
+    def work(r):
+        try:
+            sr = dec.SlabRank(case, comms[r], skewed)
+            for k in range(1, steps + 1):
+                sr.step_outer()
+                if k % 4 == 0:
+                    changes[r] += int(sr.recut(host.plan_slab_cuts, host.limit_cut_moves))
+            ranks[r] = sr
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+            comms[r]._s.barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    real = [e for e in errors if not isinstance(e, threading.BrokenBarrierError)]
+    assert not errors, (real or errors)[0]
+    assert changes[0] > 0 and all(r.cuts == ranks[0].cuts for r in ranks)
+    own = [r.n_own for r in ranks]
+    assert max(own) - min(own) < 0.35 * case.n_fluid / nranks, f"slabs not re-balanced: {own}"
+    assert _mismatches(g, dec.gather_by_gid([r.own_state() for r in ranks], case.n_fluid)) == []
+
+
 @pytest.mark.parametrize("stale", ["VolumetricMeasure", "Pressure", "Velocity"])
 def test_every_refresh_is_needed(stale):
     """Each of the three ghost refreshes carries a value the neighbours' own particles read: dropping one breaks parity."""
