@@ -127,7 +127,7 @@ class OracleSim:
     """One fluid body + one wall body + inner/contact relations, advanced by the oracle."""
 
     def __init__(self, case, f64=False, riemann=1, correction=0, free_surface=1, threads=0, contact_depth=1,
-                 surface_indicator=0, observers=None, viscosity=0.0, transport_velocity=0):
+                 surface_indicator=0, observers=None, viscosity=0.0, transport_velocity=0, correction_alpha=0.5):
         self.case = case
         self.f64 = bool(f64)
         self.dtype = np.float64 if f64 else np.float32
@@ -137,7 +137,7 @@ class OracleSim:
         for d in range(3):
             p.gravity[d] = case.gravity[d]
         p.U_ref, p.h_min = case.U_ref, case.kernel.h
-        p.acoustic_cfl, p.advection_cfl, p.correction_alpha = 0.6, 0.25, 0.5
+        p.acoustic_cfl, p.advection_cfl, p.correction_alpha = 0.6, 0.25, float(correction_alpha)
         p.sigma0, p.wall_rho0, p.contact_depth, p.threads = case.sigma0, 1.0, contact_depth, threads
         p.periodic_axes = int(getattr(case, "periodic_axes", 0))
         if p.periodic_axes:

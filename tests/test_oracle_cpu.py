@@ -192,6 +192,43 @@ def test_inner_pressure_force_conserves_momentum(oracle_lib):
 from helpers import dtw_distance  # noqa: E402
 
 
+def test_linear_gradient_reproduction_known_answer(oracle_lib):
+    """The reference's own known-answer test for the B matrix, restated against the oracle
+    (tests/unit_tests_src/shared/particle_dynamics/general_dynamics/unit_test_gradient_ck/2d_gradient.cpp:57-62,166-168,
+    204-207): randomised 2-D particles between walls, LinearCorrectionMatrix<Inner<WithUpdate>, Contact<>> with alpha = 0,
+    then LinearGradient of the Position field (general_gradient.hpp:31-43: grad = -sum_j (B_i gradW_ij V_j) (x) (x_i - x_j))
+    must be the identity to 1e-6 — at EVERY fluid particle here, free surface included, not at one observer."""
+    import dataclasses
+    from sphinxsys_b200 import cases
+    case = cases.dam_break(dim=2, dp=0.025, dtype=np.float64)
+    rng = np.random.default_rng(42)
+    pos = case.fluid_pos.copy()
+    pos[:, :2] += 0.25 * case.dp * rng.uniform(-1.0, 1.0, size=(case.n_fluid, 2))  # RandomizeParticlePosition, exec(0.25)
+    case = dataclasses.replace(case, fluid_pos=pos)
+    sim = oracle_lib.OracleSim(case, f64=True, correction=1, correction_alpha=0.0)
+    for op in ("cell_list_fluid", "cell_list_wall", "relations", "linear_correction"):
+        sim.exec(op)
+    B = sim.real("LinearCorrectionMatrix", 9).reshape(-1, 3, 3)
+    k = case.kernel
+    scale = k.dimension_factor / k.h ** (case.dim + 1)
+    G = np.zeros((case.n_fluid, 3, 3))
+    for off, idx, tpos in ((sim.uint("inner_offset"), sim.uint("inner_index"), pos),
+                           (sim.uint("contact_offset"), sim.uint("contact_index"), case.wall_pos)):
+        counts = np.diff(off.astype(np.int64))
+        i = np.repeat(np.arange(case.n_fluid), counts)
+        j = idx[: off[-1]].astype(np.int64)
+        d = pos[i] - tpos[j]
+        r = np.linalg.norm(d, axis=1)
+        dW = scale * np.array([oracle_lib.kernel_eval(k, 1, q, f64=True) for q in r / k.h])
+        g = (dW * case.vol / r)[:, None] * d                      # gradW_ij V_j = dW e_ij V_j
+        Bg = np.einsum("nab,nb->na", B[i], g)
+        np.add.at(G, i, -Bg[:, :, None] * d[:, None, :])
+    err = np.linalg.norm((G - np.eye(3))[:, :2, :2], axis=(1, 2))
+    assert counts.size and err.max() < 1.0e-6, f"linear gradient of the position field: {err.max():.3e}"
+    # and the matrix is not trivially the identity: the randomised neighbourhoods need a real correction
+    assert np.abs(B[:, :2, :2] - np.eye(2)).max() > 1e-2
+
+
 def test_oracle_energy_series_pass_reference_dtw_thresholds():
     ref = json.load(open(os.path.join(GOLD, "reference_regression.json")))
     ours = json.load(open(os.path.join(GOLD, "oracle_energy_series.json")))
