@@ -46,8 +46,8 @@ def _dam_break():
     return case, planes
 
 
-def _ring_case(drift, x_scale=1, n_side=16):
-    case = cases.taylor_green(dim=3, n_side=n_side, x_scale=x_scale)
+def _ring_case(drift, x_scale=1, n_side=16, dim=3):
+    case = cases.taylor_green(dim=dim, n_side=n_side, x_scale=x_scale)
     mesh, first, planes = dec.aligned_periodic_mesh(case)
     vel = case.fluid_vel.copy()
     vel[:, 0] += np.float32(drift)  # uniform drift: particles cross the seam between the last and the first rank
@@ -144,6 +144,16 @@ def test_periodic_ring_replicated_box_bit_identical():
     states, ranks = dec.run_threads(case, 2, cuts, 10, ring=True, free_surface=0)
     assert _mismatches(g, dec.gather_by_gid(states, case.n_fluid)) == []
     assert ranks[-1].wrapped > 0 and abs(ranks[0].n_own - ranks[1].n_own) < 0.15 * case.n_fluid  # 9 planes: 4 + 5
+
+
+def test_periodic_ring_2d_bit_identical():
+    """The 2-D Taylor-Green case (taylor_green.cpp) on a ring of three slabs."""
+    case, first, planes = _ring_case(1.0, n_side=40, dim=2)
+    cuts = dec.plan_cuts(dec.x_plane(case.fluid_pos, case.mesh), first, first + planes, 3)
+    g = _single(case, 25, free_surface=0)
+    states, ranks = dec.run_threads(case, 3, cuts, 25, ring=True, free_surface=0)
+    assert _mismatches(g, dec.gather_by_gid(states, case.n_fluid)) == []
+    assert ranks[-1].wrapped > 0
 
 
 def test_periodic_ring_of_one_slab_bit_identical():
