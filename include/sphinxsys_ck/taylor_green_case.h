@@ -179,7 +179,9 @@ class TaylorGreenCK
         PeriodicImages &images = periodic_condition[0]->images();
         if (q.ring)
         {
-            if (q.mu_f > 0 || q.transport_velocity) throw SphError("ring decomposition: viscous force / transport velocity are not decomposed yet");
+            // viscous force, kernel gradient integral and transport correction read Position, VolumetricMeasure and Velocity of
+            // the neighbours, all current on ghost planes and images where they run: the three refreshes below suffice
+            // (pinned on the CPU: tests/test_decomposed_oracle_cpu.py::test_periodic_ring_viscous_transport_bit_identical)
             decomposition.reset(new SlabDecomposition(water_block, q.rank, q.nranks, cuts, seam_ring));
             fluid_advection_time_step->setDecomposition(decomposition.get());
             fluid_acoustic_time_step->setDecomposition(decomposition.get());

@@ -17,7 +17,8 @@ Protocol (one rank; same order as DamBreakCK::stepOuter / SlabDecomposition::reb
   * stored order `own | ghosts from the left | ghosts from the right`, each by ascending global id, so the order
     inside a cell — hence every neighbour row and every summation — is the single-domain one;
   * ghost refresh inside a step: VolumetricMeasure after AdvectionStepSetup, Pressure after the initialisation of
-    the 1st half, Velocity after its update; nothing else. Stages also run on the ghosts here (the GPU runs them on
+    the 1st half, Velocity after its update; nothing else (the viscous force, the kernel gradient integral and the
+    transport-velocity correction of the Taylor-Green case run on what is already there). Stages also run on the ghosts here (the GPU runs them on
     the active range only); their results there are meaningless and never read, which makes the check stricter;
   * time steps: raw reductions over the OWN particles, max over the ranks, then the CFL formula.
 Periodic runs along x ("ring"): the box is a whole number of cell planes (aligned mesh, spacing >= cut-off), the
@@ -40,7 +41,9 @@ from . import oracle as orc
 VARIABLES = [("Position", 3), ("Velocity", 3), ("Displacement", 3), ("Force", 3), ("ForcePrior", 3),
              ("PreviousGravityForceCK", 3), ("VolumetricMeasure", 1), ("VolumetricMeasureRef", 1), ("Mass", 1),
              ("Density", 1), ("Pressure", 1), ("Compression", 1), ("CompressionRate", 1), ("CompressionSummation", 1)]
-WIDTH = dict(VARIABLES)
+# carried as well when the case has viscosity (ForcePriorCK keeps the previous viscous force to form the increment)
+VISCOUS_VARIABLES = [("ViscousForce", 3), ("PreviousViscousForce", 3)]
+WIDTH = dict(VARIABLES + VISCOUS_VARIABLES)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -166,6 +169,9 @@ class SlabRank:
         self.skip_refresh = set(skip_refresh)  # negative tests: leave these variables stale on the ghost planes
         self.rank, self.size = comm.rank, comm.size
         self.kw = dict(oracle_kwargs)
+        self.viscous = float(self.kw.get("viscosity", 0.0)) > 0.0
+        self.transport = bool(self.kw.get("transport_velocity", 0))
+        self.variables = VARIABLES + (VISCOUS_VARIABLES if self.viscous else [])
         self.R = np.float64 if self.kw.get("f64") else np.float32
         if len(self.cuts) != self.size + 1 or any(b <= a for a, b in zip(self.cuts, self.cuts[1:])):
             raise ValueError("cuts must be strictly increasing, one slab per rank")
@@ -185,7 +191,7 @@ class SlabRank:
         pos = g.real("Position", 3).reshape(-1, 3)
         mine = self._owner(pos) == self.rank
         self.gid = np.nonzero(mine)[0].astype(np.int64)
-        self.own = {nm: g.real(nm, w).reshape(-1, w)[mine].copy() for nm, w in VARIABLES}
+        self.own = {nm: g.real(nm, w).reshape(-1, w)[mine].copy() for nm, w in self.variables}
         del g
         self.sim = None
         self.rebuild(bound=False)
@@ -211,7 +217,7 @@ class SlabRank:
         R, case = self.R, self.case
         if self.sim is not None:  # take the own particles' state out of the stage arrays
             n = self.gid.size
-            self.own = {nm: self.sim.real(nm, w).reshape(-1, w)[:n].copy() for nm, w in VARIABLES}
+            self.own = {nm: self.sim.real(nm, w).reshape(-1, w)[:n].copy() for nm, w in self.variables}
         pos = self.own["Position"]
         if bound and case.periodic_axes:  # PeriodicBounding, axis by axis (domain_bounding.h:98-108), in Real arithmetic
             for a in range(3):
@@ -234,16 +240,16 @@ class SlabRank:
             if int(dest) not in (left, right):
                 raise AssertionError(f"rank {self.rank}: particle migrates to rank {dest}, not a neighbour (CFL assumption)")
             sel = owner == dest
-            parcels[int(dest)] = {"gid": self.gid[sel], **{nm: self.own[nm][sel] for nm, _ in VARIABLES}}
+            parcels[int(dest)] = {"gid": self.gid[sel], **{nm: self.own[nm][sel] for nm, _ in self.variables}}
         self.migrated += int(away.sum())
         arrived = self.comm.route(parcels)
         keep = ~away
         gid = [self.gid[keep]] + [box["gid"] for box in arrived.values()]
-        vals = {nm: [self.own[nm][keep]] + [box[nm] for box in arrived.values()] for nm, _ in VARIABLES}
+        vals = {nm: [self.own[nm][keep]] + [box[nm] for box in arrived.values()] for nm, _ in self.variables}
         gid = np.concatenate(gid)
         order = np.argsort(gid, kind="stable")
         self.gid = gid[order]
-        self.own = {nm: np.concatenate(vals[nm])[order] for nm, _ in VARIABLES}
+        self.own = {nm: np.concatenate(vals[nm])[order] for nm, _ in self.variables}
         if np.any(np.diff(self.gid) == 0):
             raise AssertionError("a particle has two owners")
         # 2. ghost planes: my first plane -> the left neighbour's right ghosts, my last plane -> the right neighbour's left ghosts
@@ -252,7 +258,7 @@ class SlabRank:
             raise AssertionError("own particle outside the slab after migration")
         self.send_left = np.nonzero(plane == self.cuts[self.rank])[0]
         self.send_right = np.nonzero(plane == self.cuts[self.rank + 1] - 1)[0]
-        recv = self._exchange_planes([nm for nm, _ in VARIABLES], with_gid=True)
+        recv = self._exchange_planes([nm for nm, _ in self.variables], with_gid=True)
         self.ghost_gid = {side: recv[side]["gid"] for side in ("from_left", "from_right")}
         n_own, n_l, n_r = self.gid.size, self.ghost_gid["from_left"].size, self.ghost_gid["from_right"].size
         # 3. stage arrays: own | ghosts from the left | ghosts from the right
@@ -260,7 +266,7 @@ class SlabRank:
         axes = case.periodic_axes & ~1 if self.ring else case.periodic_axes
         local_case = dataclasses.replace(case, fluid_pos=np.ascontiguousarray(local_pos), fluid_vel=None, periodic_axes=axes)
         sim = orc.OracleSim(local_case, **self.kw)
-        for nm, w in VARIABLES:
+        for nm, w in self.variables:
             sim.real(nm, w)[:] = np.concatenate([self.own[nm], recv["from_left"][nm], recv["from_right"][nm]]).reshape(-1)
         sim.exec("set_reduce_count", n_own)
         sim.exec("cell_list_fluid")
@@ -324,6 +330,14 @@ class SlabRank:
         s.exec("density_regularization")
         s.exec("advection_setup")
         self.refresh(["VolumetricMeasure"])
+        # viscous force, kernel gradient integral, transport correction (order of lid_driven_cavity_sycl.cpp:268-276): they
+        # read Position, VolumetricMeasure and Velocity of the neighbours, all current on the ghost planes at this point
+        # (velocities have not changed since the configuration update), so no further refresh is needed
+        if self.viscous:
+            s.exec("viscous_force")
+        if self.transport:
+            s.exec("kernel_gradient_integral")
+            s.exec("transport_velocity_correction", 1, 0)
         adv_dt = s.exec("advection_dt_of", c.allreduce_max(s.exec("advection_dt_reduced")))
         relax = 0.0
         while relax < adv_dt:
@@ -362,7 +376,7 @@ class SlabRank:
 
     def own_state(self):
         """{name: values of the own particles} plus "gid" (ascending), as of the last configuration update."""
-        out = {nm: self.sim.real(nm, w).reshape(-1, w)[: self.n_own].copy() for nm, w in VARIABLES}
+        out = {nm: self.sim.real(nm, w).reshape(-1, w)[: self.n_own].copy() for nm, w in self.variables}
         out["gid"] = self.gid.copy()
         return out
 
@@ -401,7 +415,8 @@ def gather_by_gid(states, n_total):
         seen[st["gid"]] += 1
     if not np.all(seen == 1):
         raise AssertionError(f"ownership is not a partition: {int((seen == 0).sum())} lost, {int((seen > 1).sum())} duplicated")
-    for nm, w in VARIABLES:
+    for nm in [k for k in states[0] if k != "gid"]:
+        w = WIDTH[nm]
         a = np.empty((n_total, w), dtype=states[0][nm].dtype)
         for st in states:
             a[st["gid"]] = st[nm]

@@ -14,6 +14,8 @@ namespace
 {
 thread_local std::string g_error;
 
+int g_ring_handles = 0; // ring runs share the communicator of the (process-wide) context: the last one gives it back
+
 struct Handle
 {
     std::unique_ptr<DamBreakCK> sim;   // dam break (CK or legacy spelling) ...
@@ -25,7 +27,7 @@ struct Handle
         pipeline.reset();
         tg.reset();
         sim.reset();
-        if (owns_comm) sphb200_comm_destroy(execution_instance().ctx());
+        if (owns_comm && --g_ring_handles == 0) sphb200_comm_destroy(execution_instance().ctx());
     }
     SPHBody &body(int which)
     {
@@ -275,9 +277,15 @@ extern "C"
             if (!xyz || !vel_xyz || !global_ids) throw SphError("ring run: positions, velocities and global ids are required");
             execution_instance().setDevice(o->device);
             sphb200_context_t *ctx = execution_instance().ctx();
-            if (nranks > 1) execution_instance().check(sphb200_comm_create(ctx, nranks, rank, unique_id), "sphb200_comm_create");
-            else execution_instance().check(sphb200_comm_create_self(ctx), "sphb200_comm_create_self");
-            execution_instance().check(sphb200_comm_set_ring(ctx, 1), "sphb200_comm_set_ring");
+            if (g_ring_handles == 0)
+            {
+                if (nranks > 1) execution_instance().check(sphb200_comm_create(ctx, nranks, rank, unique_id), "sphb200_comm_create");
+                else execution_instance().check(sphb200_comm_create_self(ctx), "sphb200_comm_create_self");
+                execution_instance().check(sphb200_comm_set_ring(ctx, 1), "sphb200_comm_set_ring");
+            }
+            else if (sphb200_comm_size(ctx) != (nranks > 1 ? nranks : 1))
+                throw SphError("ring run: another ring run of a different size is alive on this context");
+            ++g_ring_handles;
             h->owns_comm = true;
             TaylorGreenParameters q;
             q.dim = o->dim; q.dp = o->dp; q.L = o->L; q.U_f = o->U_f;
@@ -285,6 +293,8 @@ extern "C"
             q.fused_time_step = o->fused_time_step != 0;
             q.fused_regularization = o->fused_regularization != 0;
             q.sort_interval = 0;
+            q.mu_f = o->mu_f;
+            q.transport_velocity = o->transport_velocity != 0;
             q.ring = true; q.rank = rank; q.nranks = nranks;
             std::vector<Vecd> pos = toVecd(xyz, n), vel = toVecd(vel_xyz, n);
             std::vector<UnsignedInt> ids(global_ids, global_ids + n);

@@ -33,7 +33,8 @@ def _single(case, steps, **kw):
 
 def _mismatches(g, glob):
     bad = []
-    for nm, w in dec.VARIABLES:
+    for nm in glob:
+        w = dec.WIDTH[nm]
         ref = g.real(nm, w).reshape(-1, w)
         if not np.array_equal(ref.view(np.uint32), glob[nm].view(np.uint32)):
             bad.append(nm)
@@ -144,6 +145,20 @@ def test_periodic_ring_replicated_box_bit_identical():
     states, ranks = dec.run_threads(case, 2, cuts, 10, ring=True, free_surface=0)
     assert _mismatches(g, dec.gather_by_gid(states, case.n_fluid)) == []
     assert ranks[-1].wrapped > 0 and abs(ranks[0].n_own - ranks[1].n_own) < 0.15 * case.n_fluid  # 9 planes: 4 + 5
+
+
+def test_periodic_ring_viscous_transport_bit_identical():
+    """The Taylor-Green case as the reference runs it — viscous force and transport-velocity correction
+    (taylor_green.cpp:106-116) — on a ring: no refresh beyond the three of the inviscid step is needed."""
+    case, first, planes = _ring_case(1.0)
+    kw = dict(free_surface=0, viscosity=0.01, transport_velocity=1)
+    cuts = dec.plan_cuts(dec.x_plane(case.fluid_pos, case.mesh), first, first + planes, 2)
+    g = _single(case, 12, **kw)
+    states, ranks = dec.run_threads(case, 2, cuts, 12, ring=True, **kw)
+    glob = dec.gather_by_gid(states, case.n_fluid)
+    assert "PreviousViscousForce" in glob and np.abs(glob["ViscousForce"]).max() > 0
+    assert _mismatches(g, glob) == []
+    assert ranks[-1].wrapped > 0
 
 
 def test_periodic_ring_2d_bit_identical():

@@ -132,3 +132,39 @@ def test_ring_of_one_slab_against_single_domain_oracle(n_side, n_outer, drift):
     rep["energy"] = [e_gpu, e_ref]
     assert abs(e_gpu - e_ref) <= 1e-5 * abs(e_ref)
     _report(f"ring_of_one_{n_side}_{drift}", rep)
+
+
+@pytest.mark.xfail(strict=False, reason="written after the GPU budget of round 1 was spent: not yet run on a B200 "
+                                        "(its CPU twin, test_periodic_ring_viscous_transport_bit_identical, is green)")
+def test_ring_of_one_slab_viscous_transport():
+    """Taylor-Green as the reference runs it (viscous force, Re = 100, + transport-velocity correction) on the ring of one
+    slab: bounds of tests/test_gpu_viscous_transport.py (the fp32 oracle's own distance to the fp64 oracle, >= 2e-4)."""
+    from sphinxsys_b200.host import TaylorGreenCK
+    case = _case(16, 1.5)
+    mu, n_outer = 0.01, 8
+    gpu = TaylorGreenCK(case, ring=True, mu_f=mu, transport_velocity=True)
+    gpu.initialize()
+    o32, _ = _oracle_on_gpu_mesh(case, gpu, viscosity=mu, transport_velocity=1)
+    o64, _ = _oracle_on_gpu_mesh(case, gpu, f64=True, viscosity=mu, transport_velocity=1)
+    for o in (o32, o64):
+        o.exec("prepare_ck")
+        o.exec("run_ck", 1e9, n_outer, 1e9, 0)
+    n_ac = gpu.run_outer(n_outer)
+    assert n_ac == int(o32.exec("acoustic_steps"))
+    n, rep = case.n_fluid, {}
+    for nm, w in (("Position", 3), ("Velocity", 3), ("Density", 1)):
+        g = _own(gpu, nm, n).astype(np.float64).reshape(-1)
+        r32, r64 = o32.real(nm, w).astype(np.float64), o64.real(nm, w).astype(np.float64)
+        if nm == "Position":  # compare modulo the box
+            g, r32 = g + np.round(r64 - g), r32 + np.round(r64 - r32)
+        scale = max(np.max(np.abs(r64)), 1e-30)
+        rep[nm] = (float(np.max(np.abs(g - r64)) / scale), float(np.max(np.abs(r32 - r64)) / scale))
+        assert rep[nm][0] < max(4.0 * rep[nm][1], 2e-4), (nm, rep[nm])
+    e_visc = gpu.energy()
+    gpu.close()
+    inviscid = TaylorGreenCK(case, ring=True)
+    inviscid.initialize()
+    inviscid.run_outer(n_outer)
+    rep["energy_viscous_vs_inviscid"] = (e_visc, inviscid.energy())
+    assert e_visc < rep["energy_viscous_vs_inviscid"][1]
+    _report("ring_of_one_viscous_transport", rep)
