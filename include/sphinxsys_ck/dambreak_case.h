@@ -160,7 +160,6 @@ class DamBreakCK
         if (q.nranks > 1)
         {
             // every rank generates the global lattice, keeps the particles of its own cell planes and their global numbers
-            if (q.correction) throw SphError("slab decomposition: LinearCorrectionCK variants are not decomposed yet");
             std::vector<Vecd> all = fluid_positions ? *fluid_positions
                                                     : generateLattice(water_block.getInitialShape(), sph_system.system_domain_bounds_, Real(q.dp), q.dim);
             SPHAdaptation &ad = water_block.getSPHAdaptation();
@@ -460,7 +459,13 @@ class DamBreakCK
         }
         Real advection_dt = fluid_advection_time_step->exec();
         if (fluid_boundary_indicator) fluid_boundary_indicator->exec();
-        if (q_.correction) fluid_linear_correction_matrix->exec();
+        if (q_.correction)
+        {
+            fluid_linear_correction_matrix->exec();
+            // both half steps read B of the neighbours: the one refresh the correction variants add to a decomposed step
+            // (tests/test_decomposed_oracle_cpu.py::test_dam_break_correction_variants_bit_identical)
+            if (decomposition) decomposition->refreshGhosts({"LinearCorrectionMatrix"});
+        }
         Real relaxation_time = 0, acoustic_dt = 0;
         int n_inner = 0;
         while (relaxation_time < advection_dt)

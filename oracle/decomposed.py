@@ -17,7 +17,8 @@ Protocol (one rank; same order as DamBreakCK::stepOuter / SlabDecomposition::reb
   * stored order `own | ghosts from the left | ghosts from the right`, each by ascending global id, so the order
     inside a cell — hence every neighbour row and every summation — is the single-domain one;
   * ghost refresh inside a step: VolumetricMeasure after AdvectionStepSetup, Pressure after the initialisation of
-    the 1st half, Velocity after its update; nothing else (the viscous force, the kernel gradient integral and the
+    the 1st half, Velocity after its update, LinearCorrectionMatrix after it is rebuilt (correction variants only);
+    nothing else (the viscous force, the kernel gradient integral and the
     transport-velocity correction of the Taylor-Green case run on what is already there). Stages also run on the ghosts here (the GPU runs them on
     the active range only); their results there are meaningless and never read, which makes the check stricter;
   * time steps: raw reductions over the OWN particles, max over the ranks, then the CFL formula.
@@ -43,7 +44,9 @@ VARIABLES = [("Position", 3), ("Velocity", 3), ("Displacement", 3), ("Force", 3)
              ("Density", 1), ("Pressure", 1), ("Compression", 1), ("CompressionRate", 1), ("CompressionSummation", 1)]
 # carried as well when the case has viscosity (ForcePriorCK keeps the previous viscous force to form the increment)
 VISCOUS_VARIABLES = [("ViscousForce", 3), ("PreviousViscousForce", 3)]
-WIDTH = dict(VARIABLES + VISCOUS_VARIABLES)
+# LinearCorrectionCK variants: B is rebuilt every advection step, but the viscous force of the NEXT step still reads it
+CORRECTION_VARIABLES = [("LinearCorrectionMatrix", 9)]
+WIDTH = dict(VARIABLES + VISCOUS_VARIABLES + CORRECTION_VARIABLES)
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -171,7 +174,8 @@ class SlabRank:
         self.kw = dict(oracle_kwargs)
         self.viscous = float(self.kw.get("viscosity", 0.0)) > 0.0
         self.transport = bool(self.kw.get("transport_velocity", 0))
-        self.variables = VARIABLES + (VISCOUS_VARIABLES if self.viscous else [])
+        self.correction = bool(self.kw.get("correction", 0))
+        self.variables = VARIABLES + (VISCOUS_VARIABLES if self.viscous else []) + (CORRECTION_VARIABLES if self.correction else [])
         self.R = np.float64 if self.kw.get("f64") else np.float32
         if len(self.cuts) != self.size + 1 or any(b <= a for a, b in zip(self.cuts, self.cuts[1:])):
             raise ValueError("cuts must be strictly increasing, one slab per rank")
@@ -339,6 +343,9 @@ class SlabRank:
             s.exec("kernel_gradient_integral")
             s.exec("transport_velocity_correction", 1, 0)
         adv_dt = s.exec("advection_dt_of", c.allreduce_max(s.exec("advection_dt_reduced")))
+        if self.correction:  # LinearCorrectionMatrix<Inner<WithUpdate>, Contact<>>: both half steps read B of the neighbours
+            s.exec("linear_correction")
+            self.refresh(["LinearCorrectionMatrix"])
         relax = 0.0
         while relax < adv_dt:
             dt = s.exec("acoustic_dt_of", c.allreduce_max(s.exec("acoustic_dt_reduced")))

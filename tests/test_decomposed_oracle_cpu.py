@@ -115,6 +115,22 @@ def test_dam_break_recut_keeps_bit_identity():
     assert _mismatches(g, dec.gather_by_gid([r.own_state() for r in ranks], case.n_fluid)) == []
 
 
+@pytest.mark.parametrize("viscosity", [0.0, 0.02])
+def test_dam_break_correction_variants_bit_identical(viscosity):
+    """The Correction aliases the complete reference case file uses (dambreak.cpp:117-124): one more refresh, of the B
+    matrix right after LinearCorrectionMatrix has rebuilt it, keeps the decomposed run bit-identical; without it, it is not."""
+    case, planes = _dam_break()
+    cuts = dec.plan_cuts(planes, 0, case.mesh.cells[0], 3)
+    kw = dict(correction=1, viscosity=viscosity)
+    g = _single(case, 20, **kw)
+    states, _ = dec.run_threads(case, 3, cuts, 20, **kw)
+    glob = dec.gather_by_gid(states, case.n_fluid)
+    assert "LinearCorrectionMatrix" in glob and _mismatches(g, glob) == []
+    if viscosity == 0.0:
+        states, _ = dec.run_threads(case, 3, cuts, 6, skip_refresh=["LinearCorrectionMatrix"], **kw)
+        assert _mismatches(_single(case, 6, **kw), dec.gather_by_gid(states, case.n_fluid)) != []
+
+
 @pytest.mark.parametrize("stale", ["VolumetricMeasure", "Pressure", "Velocity"])
 def test_every_refresh_is_needed(stale):
     """Each of the three ghost refreshes carries a value the neighbours' own particles read: dropping one breaks parity."""
