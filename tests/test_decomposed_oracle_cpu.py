@@ -68,10 +68,11 @@ def test_dam_break_slabs_bit_identical(nranks, steps):
 
 
 def test_dam_break_cuts_do_not_matter():
-    """Results do not depend on where the slabs are cut (in-cell order is by global id)."""
+    """Results do not depend on where the slabs are cut (in-cell order is by global id), slabs of ONE plane included
+    (its particles are the left and the right boundary plane at once)."""
     case, _ = _dam_break()
     g = _single(case, 8)
-    for cuts in ([0, 7, 52], [0, 16, 52], [0, 5, 9, 52]):
+    for cuts in ([0, 7, 52], [0, 16, 52], [0, 5, 9, 52], [0, 10, 11, 12, 13, 52]):
         states, _ = dec.run_threads(case, len(cuts) - 1, cuts, 8)
         assert _mismatches(g, dec.gather_by_gid(states, case.n_fluid)) == []
 
@@ -141,7 +142,7 @@ def test_every_refresh_is_needed(stale):
     assert _mismatches(g, dec.gather_by_gid(states, case.n_fluid)) != []
 
 
-@pytest.mark.parametrize("nranks,steps,drift", [(2, 10, 1.0), (3, 30, 1.0), (2, 15, -1.5)])
+@pytest.mark.parametrize("nranks,steps,drift", [(2, 10, 1.0), (3, 30, 1.0), (2, 15, -1.5), (6, 10, 1.5)])
 def test_periodic_ring_bit_identical(nranks, steps, drift):
     case, first, planes = _ring_case(drift)
     cuts = dec.plan_cuts(dec.x_plane(case.fluid_pos, case.mesh), first, first + planes, nranks)
