@@ -252,7 +252,7 @@ def run_ours(args, rank, world, local_rank):
                 "achieved": ach_a2, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach_a2 / peak,
                 "traffic": traffic, "algorithmic_bytes_per_launch": A_STEP_2ND * n_own, "launch_ms": ms_a2,
                 "note": "pair arithmetic (~85 neighbours x ~50 instr, one 32-byte gather each) runs at 84 % of the L1 data-pipe and 72 % of the "
-                        "issue peak (profiles/r01_v5_ncu_full.txt): bound by L1 bank wavefronts and FP32 issue, not by HBM; see DESIGN.md §4",
+                        "issue peak (profiles/r01_v8_ncu_full.txt): bound by L1 bank wavefronts and FP32 issue, not by HBM; see DESIGN.md §4",
                 "other_kernels_ms": {"acoustic_1st_half(init+interact)": ms_a1, "density_summation": ms_sum,
                                      "cell_list_build+reorder": ms_cl, "relation_build(inner+contact)": ms_rel}}
 
@@ -394,6 +394,10 @@ def run_ours(args, rank, world, local_rank):
             "roofline": roofline,
             "whole_step_hbm_frac": value / world * alg_bytes / 1e9 / peak,  # per GPU
             "algorithmic_bytes_per_particle_step": alg_bytes,
+            # also the un-amortised kernel-only rate (the two half-step launches of an acoustic step alone,
+            # rank 0's launch times, every rank working on its own shard at once) and advection steps per second
+            "kernel_only_particle_steps_per_s": n_fluid / ((ms_a1 + ms_a2) * 1e-3),
+            "outer_steps_per_s": args.steps / (ms * 1e-3),
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
         }
         print(json.dumps(line), flush=True)
