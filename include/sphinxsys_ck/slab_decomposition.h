@@ -18,6 +18,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <limits>
 #include <utility>
 
@@ -398,6 +399,7 @@ class SlabDecomposition
         migrated_out_ += (uint64_t)send_l + send_r; // boundary-plane particles and leavers handed to the neighbours
         // periodic images of the other axes: made for all stored particles behind them, after this configuration update
         if (PeriodicImages *im = body_.periodicImages()) im->setStoredRange(n_, a0_, a1_);
+        if (checkExchangeEnabled()) verifyGhostPlanes();
         // 5. slot origin: the slot the first stored particle has in the undecomposed run = particles owned by the ranks
         //    below minus the left ghost plane. Relations against bodies that are NOT decomposed (the wall) lay their rows
         //    out relative to it, so that summation order does not depend on the decomposition (sphb200_relation_t::bank_aligned).
@@ -412,6 +414,40 @@ class SlabDecomposition
             for (int r = 0; r < rank_; ++r) below += all[r];
             body_.setSlotOrigin((uint32_t)((below - a0_) & 0xffffffffull));
         }
+    }
+
+    // SPHB200_CHECK_EXCHANGE=1: after every rebuild() the ranks tell each other how many particles their boundary planes
+    // hold and compare with their ghost planes. refreshGhosts() sends and receives whole planes in place, so a mismatch
+    // would leave an NCCL receive waiting for bytes that never come; with the check the run stops with a message instead
+    // (for first runs of a new exchange pattern; one small exchange and one host round trip per advection step).
+    static bool checkExchangeEnabled()
+    {
+        static const bool on = [] {
+            const char *e = std::getenv("SPHB200_CHECK_EXCHANGE");
+            return e && e[0] != '0' && e[0] != 0;
+        }();
+        return on;
+    }
+    void verifyGhostPlanes()
+    {
+        ExecutionInstance &ex = execution_instance();
+        void *st = ex.stream();
+        uint64_t *d = scalars_.get<uint64_t>();
+        uint64_t host[4] = {uint64_t(f1_ - a0_), uint64_t(a1_ - l0_), 0, 0}; // my first plane -> left, my last plane -> right
+        ex.check(sphb200_copy_h2d(d, host, sizeof(host), st), "sphb200_copy_h2d");
+        {
+            const void *sl[1] = {d}, *sr[1] = {d + 1};
+            void *rl[1] = {d + 2}, *rr[1] = {d + 3};
+            size_t b[1] = {sizeof(uint64_t)};
+            SPHCK_CALL(sphb200_comm_exchange, 1, sl, b, rl, b, sr, b, rr, b, st);
+        }
+        ex.check(sphb200_copy_d2h(host, d, sizeof(host), st), "sphb200_copy_d2h");
+        ex.synchronize();
+        const uint64_t left_ghosts = a0_, right_ghosts = uint64_t(n_) - a1_;
+        if ((hasLeft() && host[2] != left_ghosts) || (hasRight() && host[3] != right_ghosts))
+            throw SphError("SlabDecomposition: rank " + std::to_string(rank_) + " holds " + std::to_string(left_ghosts) + " / " +
+                           std::to_string(right_ghosts) + " ghost particles (left / right) but its neighbours' boundary planes hold " +
+                           std::to_string(host[2]) + " / " + std::to_string(host[3]));
     }
 
     // Re-balance: new cuts from the CURRENT particles-per-plane histogram (all ranks), then hand the planes that changed
