@@ -735,6 +735,7 @@ template <class R> struct Sim
     {
         const std::vector<R> &sum = fluid.r("CompressionSummation");
         std::vector<R> &C = fluid.r("Compression"), &rho = fluid.r("Density");
+        #pragma omp parallel for schedule(static)
         for (u32 i = 0; i < fluid.n; ++i)
         {
             C[i] = P.free_surface ? SMAX(sum[i], R(1)) : sum[i];
@@ -919,6 +920,7 @@ template <class R> struct Sim
         std::vector<R> &dpos = fluid.r("Displacement", 3);
         const R h = R(P.h_min), h2 = h * h, scaling = R(P.transport_coefficient) * h2;
         const std::vector<u32> *ind = bulk_only ? &fluid.uint["Indicator"] : nullptr;
+        #pragma omp parallel for schedule(static)
         for (u32 i = 0; i < fluid.n; ++i)
         {
             if (ind && (*ind)[i] != 0u) continue;
@@ -932,6 +934,7 @@ template <class R> struct Sim
     {
         std::vector<R> &Vol = fluid.r("VolumetricMeasure"), &dpos = fluid.r("Displacement", 3);
         const std::vector<R> &m = fluid.r("Mass"), &rho = fluid.r("Density");
+        #pragma omp parallel for schedule(static)
         for (u32 i = 0; i < fluid.n; ++i)
         {
             Vol[i] = m[i] / rho[i];
@@ -942,6 +945,7 @@ template <class R> struct Sim
     {
         std::vector<R> &pos = fluid.r("Position", 3);
         const std::vector<R> &dpos = fluid.r("Displacement", 3);
+        #pragma omp parallel for schedule(static)
         for (size_t k = 0; k < size_t(3) * fluid.n; ++k) pos[k] += dpos[k];
     }
     // ref: fluid_time_step_ck.h:106-109, fluid_time_step_ck.cpp:24-27; TinyReal base_data_type.h:207
@@ -953,7 +957,9 @@ template <class R> struct Sim
     {
         const std::vector<R> &vel = fluid.r("Velocity", 3);
         R red = std::numeric_limits<R>::lowest();
-        for (u32 i = 0; i < reduceCount(); ++i) red = SMAX(red, vec(vel, i).squaredNorm());
+        const u32 n_red = reduceCount();
+#pragma omp parallel for schedule(static) reduction(max : red)
+        for (u32 i = 0; i < n_red; ++i) red = SMAX(red, vec(vel, i).squaredNorm());
         return double(red);
     }
     double advectionDt() { return advectionDtOf(advectionDtReduced()); }
@@ -969,7 +975,9 @@ template <class R> struct Sim
                              &m = fluid.r("Mass");
         R hmin = R(P.h_min);
         R red = std::numeric_limits<R>::lowest();
-        for (u32 i = 0; i < reduceCount(); ++i)
+        const u32 n_red = reduceCount();
+#pragma omp parallel for schedule(static) reduction(max : red)
+        for (u32 i = 0; i < n_red; ++i)
         {
             R fn = (vec(F, i) + vec(Fp, i)).norm();
             R acc = std::sqrt(R(4.0) * hmin * fn / m[i]);
@@ -990,6 +998,7 @@ template <class R> struct Sim
         std::vector<R> &C = fluid.r("Compression"), &rho = fluid.r("Density"), &p = fluid.r("Pressure"),
                        &dpos = fluid.r("Displacement", 3);
         const std::vector<R> &Cd = fluid.r("CompressionRate"), &vel = fluid.r("Velocity", 3);
+        #pragma omp parallel for schedule(static)
         for (u32 i = 0; i < fluid.n; ++i)
         {
             C[i] += R(0.5) * dt * Cd[i];
@@ -1066,6 +1075,7 @@ template <class R> struct Sim
     {
         std::vector<R> &vel = fluid.r("Velocity", 3);
         const std::vector<R> &F = fluid.r("Force", 3), &Fp = fluid.r("ForcePrior", 3), &m = fluid.r("Mass");
+        #pragma omp parallel for schedule(static)
         for (u32 i = 0; i < fluid.n; ++i) setv(vel, i, vec(vel, i) + (vec(Fp, i) + vec(F, i)) / m[i] * dt);
     }
     // ---- 2nd half; ref: fluid_dynamics/acoustic_step_2nd_half.hpp:33-38,53-73,83-89,117-137 ----
@@ -1073,6 +1083,7 @@ template <class R> struct Sim
     {
         std::vector<R> &dpos = fluid.r("Displacement", 3);
         const std::vector<R> &vel = fluid.r("Velocity", 3);
+        #pragma omp parallel for schedule(static)
         for (u32 i = 0; i < fluid.n; ++i) setv(dpos, i, vec(dpos, i) + vec(vel, i) * dt * R(0.5));
     }
     void a2Inner()
@@ -1140,6 +1151,7 @@ template <class R> struct Sim
     {
         std::vector<R> &C = fluid.r("Compression"), &rho = fluid.r("Density");
         const std::vector<R> &Cd = fluid.r("CompressionRate");
+        #pragma omp parallel for schedule(static)
         for (u32 i = 0; i < fluid.n; ++i)
         {
             C[i] += R(0.5) * dt * Cd[i];
@@ -1230,6 +1242,7 @@ template <class R> struct Sim
         if (!P.free_surface)
         {
             std::vector<R> &Vol = fluid.r("VolumetricMeasure");
+            #pragma omp parallel for schedule(static)
             for (u32 i = 0; i < fluid.n; ++i) Vol[i] = m[i] / rho[i];
         }
     }
@@ -1240,6 +1253,7 @@ template <class R> struct Sim
                        &drho = fluid.r("DensityChangeRate"), &F = fluid.r("Force", 3), &vel = fluid.r("Velocity", 3);
         const std::vector<R> &Vol = fluid.r("VolumetricMeasure"), &m = fluid.r("Mass"), &Fp = fluid.r("ForcePrior", 3);
         const std::vector<R> &wVol = wall.r("VolumetricMeasure"), &wacc = wall.r("Acceleration", 3);
+        #pragma omp parallel for schedule(static)
         for (u32 i = 0; i < fluid.n; ++i)
         {
             rho[i] += drho[i] * dt * R(0.5);
@@ -1278,6 +1292,7 @@ template <class R> struct Sim
             setv(F, i, Fi);
             drho[i] = dr;
         }
+        #pragma omp parallel for schedule(static)
         for (u32 i = 0; i < fluid.n; ++i) setv(vel, i, vec(vel, i) + (vec(Fp, i) + vec(F, i)) / m[i] * dt);
     }
     // ref: fluid_integration.hpp:159-231
@@ -1288,6 +1303,7 @@ template <class R> struct Sim
         const std::vector<R> &Vol = fluid.r("VolumetricMeasure"), &vel = fluid.r("Velocity", 3);
         const std::vector<R> &wVol = wall.r("VolumetricMeasure"), &wvel = wall.r("Velocity", 3),
                              &wn = wall.r("NormalDirection", 3);
+        #pragma omp parallel for schedule(static)
         for (u32 i = 0; i < fluid.n; ++i) setv(pos, i, vec(pos, i) + vec(vel, i) * dt * R(0.5));
 #pragma omp parallel for schedule(dynamic, 256)
         for (long i = 0; i < (long)fluid.n; ++i)
@@ -1322,6 +1338,7 @@ template <class R> struct Sim
             drho[i] += dcrw * rho[i];
             setv(F, i, pd * Vol[i] + pdw * Vol[i]);
         }
+        #pragma omp parallel for schedule(static)
         for (u32 i = 0; i < fluid.n; ++i) rho[i] += drho[i] * dt * R(0.5);
     }
     // ref: particle_dynamics/fluid_dynamics/fluid_time_step.cpp:21-59
@@ -1329,6 +1346,7 @@ template <class R> struct Sim
     {
         const std::vector<R> &vel = fluid.r("Velocity", 3);
         R red = std::numeric_limits<R>::lowest();
+        #pragma omp parallel for schedule(static) reduction(max : red)
         for (u32 i = 0; i < fluid.n; ++i) red = SMAX(red, c0 + vec(vel, i).norm());
         return double(R(P.acoustic_cfl) * R(P.h_min) / (red + R(2.71051e-20)));
     }
@@ -1337,6 +1355,7 @@ template <class R> struct Sim
         const std::vector<R> &vel = fluid.r("Velocity", 3), &F = fluid.r("Force", 3), &Fp = fluid.r("ForcePrior", 3),
                              &m = fluid.r("Mass");
         R red = std::numeric_limits<R>::lowest();
+        #pragma omp parallel for schedule(static) reduction(max : red)
         for (u32 i = 0; i < fluid.n; ++i)
         {
             R acc = R(4.0) * R(P.h_min) * (vec(F, i) + vec(Fp, i)).norm() / m[i];
