@@ -17,7 +17,8 @@ Protocol (one rank; same order as DamBreakCK::stepOuter / SlabDecomposition::reb
   * stored order `own | ghosts from the left | ghosts from the right`, each by ascending global id, so the order
     inside a cell — hence every neighbour row and every summation — is the single-domain one;
   * ghost refresh inside a step: VolumetricMeasure after AdvectionStepSetup, Pressure after the initialisation of
-    the 1st half, Velocity after its update, LinearCorrectionMatrix after it is rebuilt (correction variants only);
+    the 1st half, Velocity after its update, LinearCorrectionMatrix after it is rebuilt (correction variants only),
+    PositionDivergence between the two sweeps of the free-surface indication (when the case has it);
     nothing else (the viscous force, the kernel gradient integral and the
     transport-velocity correction of the Taylor-Green case run on what is already there). Stages also run on the ghosts here (the GPU runs them on
     the active range only); their results there are meaningless and never read, which makes the check stricter;
@@ -46,7 +47,10 @@ VARIABLES = [("Position", 3), ("Velocity", 3), ("Displacement", 3), ("Force", 3)
 VISCOUS_VARIABLES = [("ViscousForce", 3), ("PreviousViscousForce", 3)]
 # LinearCorrectionCK variants: B is rebuilt every advection step, but the viscous force of the NEXT step still reads it
 CORRECTION_VARIABLES = [("LinearCorrectionMatrix", 9)]
-WIDTH = dict(VARIABLES + VISCOUS_VARIABLES + CORRECTION_VARIABLES)
+# FreeSurfaceIndicationCK: PositionDivergence lives inside one call (refreshed on the ghost planes between its two sweeps);
+# the indicator of the previous step is an evolving variable (surface_indication_ck.hpp:42-46) and travels with the particle
+INDICATOR_UINTS = ["PreviousSurfaceIndicator", "Indicator"]
+WIDTH = dict(VARIABLES + VISCOUS_VARIABLES + CORRECTION_VARIABLES + [("PositionDivergence", 1)])
 
 
 # ------------------------------------------------------------------------------------------------------------------
@@ -174,6 +178,8 @@ class SlabRank:
         self.kw = dict(oracle_kwargs)
         self.viscous = float(self.kw.get("viscosity", 0.0)) > 0.0
         self.transport = bool(self.kw.get("transport_velocity", 0))
+        self.indicator = bool(self.kw.get("surface_indicator", 0))
+        self.uints = INDICATOR_UINTS if self.indicator else []
         self.correction = bool(self.kw.get("correction", 0))
         self.variables = VARIABLES + (VISCOUS_VARIABLES if self.viscous else []) + (CORRECTION_VARIABLES if self.correction else [])
         self.R = np.float64 if self.kw.get("f64") else np.float32
@@ -196,6 +202,8 @@ class SlabRank:
         mine = self._owner(pos) == self.rank
         self.gid = np.nonzero(mine)[0].astype(np.int64)
         self.own = {nm: g.real(nm, w).reshape(-1, w)[mine].copy() for nm, w in self.variables}
+        for nm in self.uints:  # registerStateVariable<int>("PreviousSurfaceIndicator", 1), "Indicator" 0
+            self.own[nm] = np.full((self.gid.size, 1), 1 if nm == "PreviousSurfaceIndicator" else 0, dtype=np.uint32)
         del g
         self.sim = None
         self.rebuild(bound=False)
@@ -210,6 +218,9 @@ class SlabRank:
     def _owner(self, pos):
         return np.searchsorted(np.asarray(self.cuts), self._planes(pos), side="right") - 1
 
+    def _names(self):
+        return [nm for nm, _ in self.variables] + list(self.uints)
+
     def _neighbours(self):
         left, right = self.rank - 1, self.rank + 1
         if self.ring:
@@ -222,6 +233,8 @@ class SlabRank:
         if self.sim is not None:  # take the own particles' state out of the stage arrays
             n = self.gid.size
             self.own = {nm: self.sim.real(nm, w).reshape(-1, w)[:n].copy() for nm, w in self.variables}
+            for nm in self.uints:
+                self.own[nm] = self.sim.uint(nm)[:n].copy().reshape(-1, 1)
         pos = self.own["Position"]
         if bound and case.periodic_axes:  # PeriodicBounding, axis by axis (domain_bounding.h:98-108), in Real arithmetic
             for a in range(3):
@@ -244,16 +257,16 @@ class SlabRank:
             if int(dest) not in (left, right):
                 raise AssertionError(f"rank {self.rank}: particle migrates to rank {dest}, not a neighbour (CFL assumption)")
             sel = owner == dest
-            parcels[int(dest)] = {"gid": self.gid[sel], **{nm: self.own[nm][sel] for nm, _ in self.variables}}
+            parcels[int(dest)] = {"gid": self.gid[sel], **{nm: self.own[nm][sel] for nm in self._names()}}
         self.migrated += int(away.sum())
         arrived = self.comm.route(parcels)
         keep = ~away
         gid = [self.gid[keep]] + [box["gid"] for box in arrived.values()]
-        vals = {nm: [self.own[nm][keep]] + [box[nm] for box in arrived.values()] for nm, _ in self.variables}
+        vals = {nm: [self.own[nm][keep]] + [box[nm] for box in arrived.values()] for nm in self._names()}
         gid = np.concatenate(gid)
         order = np.argsort(gid, kind="stable")
         self.gid = gid[order]
-        self.own = {nm: np.concatenate(vals[nm])[order] for nm, _ in self.variables}
+        self.own = {nm: np.concatenate(vals[nm])[order] for nm in self._names()}
         if np.any(np.diff(self.gid) == 0):
             raise AssertionError("a particle has two owners")
         # 2. ghost planes: my first plane -> the left neighbour's right ghosts, my last plane -> the right neighbour's left ghosts
@@ -262,7 +275,7 @@ class SlabRank:
             raise AssertionError("own particle outside the slab after migration")
         self.send_left = np.nonzero(plane == self.cuts[self.rank])[0]
         self.send_right = np.nonzero(plane == self.cuts[self.rank + 1] - 1)[0]
-        recv = self._exchange_planes([nm for nm, _ in self.variables], with_gid=True)
+        recv = self._exchange_planes(self._names(), with_gid=True)
         self.ghost_gid = {side: recv[side]["gid"] for side in ("from_left", "from_right")}
         n_own, n_l, n_r = self.gid.size, self.ghost_gid["from_left"].size, self.ghost_gid["from_right"].size
         # 3. stage arrays: own | ghosts from the left | ghosts from the right
@@ -276,6 +289,10 @@ class SlabRank:
         sim.exec("cell_list_fluid")
         sim.exec("cell_list_wall")
         sim.exec("relations")
+        if self.uints:
+            sim.exec("surface_indication")  # sizes the indicator arrays; the values are replaced right away
+            for nm in self.uints:
+                sim.uint(nm)[:] = np.concatenate([self.own[nm], recv["from_left"][nm], recv["from_right"][nm]]).reshape(-1)
         self.sim, self.n_own, self.n_ghost = sim, n_own, (n_l, n_r)
 
     def _exchange_planes(self, names, with_gid=False):
@@ -310,7 +327,7 @@ class SlabRank:
             if boxes:
                 out[key] = boxes[0]
             else:
-                out[key] = {nm: np.zeros((0, WIDTH[nm]), dtype=self.R) for nm in names}
+                out[key] = {nm: np.zeros((0, WIDTH.get(nm, 1)), dtype=np.uint32 if nm in INDICATOR_UINTS else self.R) for nm in names}
                 out[key]["gid"] = np.zeros(0, dtype=np.int64)
         return out
 
@@ -343,6 +360,13 @@ class SlabRank:
             s.exec("kernel_gradient_integral")
             s.exec("transport_velocity_correction", 1, 0)
         adv_dt = s.exec("advection_dt_of", c.allreduce_max(s.exec("advection_dt_reduced")))
+        if self.indicator:  # fluid_boundary_indicator.exec(), dambreak.cpp:192: two sweeps, the second reads the first's result
+            s.exec("surface_interact")
+            # the GPU runs the sweep on the own particles only; ghosts close to the cut would get the right value here by
+            # accident (their neighbourhood is complete), which would hide a missing refresh: wipe what was computed there
+            s.real("PositionDivergence")[self.n_own:] = 0
+            self.refresh(["PositionDivergence"])
+            s.exec("surface_update")
         if self.correction:  # LinearCorrectionMatrix<Inner<WithUpdate>, Contact<>>: both half steps read B of the neighbours
             s.exec("linear_correction")
             self.refresh(["LinearCorrectionMatrix"])
@@ -384,6 +408,8 @@ class SlabRank:
     def own_state(self):
         """{name: values of the own particles} plus "gid" (ascending), as of the last configuration update."""
         out = {nm: self.sim.real(nm, w).reshape(-1, w)[: self.n_own].copy() for nm, w in self.variables}
+        for nm in self.uints:
+            out[nm] = self.sim.uint(nm)[: self.n_own].copy().reshape(-1, 1)
         out["gid"] = self.gid.copy()
         return out
 
@@ -423,7 +449,7 @@ def gather_by_gid(states, n_total):
     if not np.all(seen == 1):
         raise AssertionError(f"ownership is not a partition: {int((seen == 0).sum())} lost, {int((seen > 1).sum())} duplicated")
     for nm in [k for k in states[0] if k != "gid"]:
-        w = WIDTH[nm]
+        w = WIDTH.get(nm, 1)
         a = np.empty((n_total, w), dtype=states[0][nm].dtype)
         for st in states:
             a[st["gid"]] = st[nm]

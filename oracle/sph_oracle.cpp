@@ -747,6 +747,12 @@ template <class R> struct Sim
     // update :98-107, very-near :109-128, contact interact :149-160); sequencing interaction_algorithms_ck.cpp:6-34
     void surfaceIndication()
     {
+        surfaceInteract();
+        surfaceUpdate();
+    }
+    // inner interact (:52-70) + near-previous check (:72-87) + contact interact (:149-160)
+    void surfaceInteract()
+    {
         const u32 n = fluid.n;
         const std::vector<R> &pos = fluid.r("Position", 3), &Vol = fluid.r("VolumetricMeasure");
         const std::vector<R> &wpos = wall.r("Position", 3), &wVol = wall.r("VolumetricMeasure");
@@ -754,7 +760,7 @@ template <class R> struct Sim
         std::vector<u32> &ind = fluid.uint["Indicator"], &prev = fluid.uint["PreviousSurfaceIndicator"];
         if (ind.size() != n) ind.assign(n, 0u);
         if (prev.size() != n) prev.assign(n, 1u); // registerStateVariable<int>("PreviousSurfaceIndicator", 1)
-        const R threshold = R(0.75) * R(P.dim), h = R(P.h_min);
+        const R threshold = R(0.75) * R(P.dim);
 #pragma omp parallel for schedule(dynamic, 256)
         for (long i = 0; i < (long)n; ++i)
         {
@@ -780,6 +786,16 @@ template <class R> struct Sim
             }
             pos_div[i] = pd + pw;
         }
+    }
+    // update (:98-107) + very-near check (:109-128): reads PositionDivergence of the neighbours, i.e. the result of
+    // surfaceInteract() on them (a slab-decomposed run refreshes it on the ghost planes in between)
+    void surfaceUpdate()
+    {
+        const u32 n = fluid.n;
+        const std::vector<R> &pos = fluid.r("Position", 3), &pos_div = fluid.r("PositionDivergence");
+        std::vector<u32> &ind = fluid.uint["Indicator"], &prev = fluid.uint["PreviousSurfaceIndicator"];
+        if (ind.size() != n) ind.assign(n, 0u);
+        const R threshold = R(0.75) * R(P.dim), h = R(P.h_min);
 #pragma omp parallel for schedule(dynamic, 256)
         for (long i = 0; i < (long)n; ++i)
         {
@@ -1522,6 +1538,8 @@ double execOp(Sim<R> &s, const std::string &op, double a0, double a1, double a2,
     else if (op == "acoustic2_update") s.a2Update(R(a0));
     else if (op == "linear_correction") s.linearCorrection();
     else if (op == "surface_indication") s.surfaceIndication();
+    else if (op == "surface_interact") s.surfaceInteract();
+    else if (op == "surface_update") s.surfaceUpdate();
     else if (op == "viscous_force") s.viscousForce();
     else if (op == "kernel_gradient_integral") s.kernelGradientIntegral();
     else if (op == "transport_velocity_correction") s.transportVelocityCorrection((int)a0, a1 != 0.0);
