@@ -376,6 +376,12 @@ int sphb200_linear_correction_matrix(sphb200_context_t *ctx, const sphb200_fluid
 int sphb200_free_surface_indication(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, int32_t *indicator,
                                     float *position_divergence, int32_t *previous_indicator, float threshold,
                                     float smoothing_length, void *stream);
+/* one sweep of the same (sweep 0: interact, writes PositionDivergence; sweep 1: update + very-near check, reads
+ * PositionDivergence of the neighbours; surface_indication_ck.hpp:52-87,149-160 and :98-128): slab-decomposed runs refresh
+ * PositionDivergence on the ghost planes between the two (new; sphb200_free_surface_indication = sweep 0 then sweep 1) */
+int sphb200_free_surface_indication_sweep(sphb200_context_t *ctx, const sphb200_fluid_args_t *fluid, int32_t *indicator,
+                                          float *position_divergence, int32_t *previous_indicator, float threshold,
+                                          float smoothing_length, int sweep, void *stream);
 /* Interpolation<Contact<DataType>>::InteractKernel::interact for an observer body:
  * out[i] = sum_j W_ij V_j data[j] / (sum_j W_ij V_j + TinyReal) over the rows of `rel` (observer -> observed body).
  * width 1: Real data; width 4: Vecd data as stored on the device (float4, all four lanes are interpolated).

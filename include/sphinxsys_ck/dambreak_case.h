@@ -281,7 +281,6 @@ class DamBreakCK
             }
             if (q.surface_indicator)
             {
-                if (q.nranks > 1) throw SphError("slab decomposition: FreeSurfaceIndicationCK is not decomposed yet");
                 fluid_boundary_indicator.reset(new InteractionDynamicsCK<P, FreeSurfaceIndicationComplexSpatialTemporalCK>(*water_block_inner, *water_wall_contact));
             }
             if (q.observers)
@@ -306,6 +305,7 @@ class DamBreakCK
             cuts_adv_->setDecomposition(decomposition.get());
             fluid_acoustic_time_step->setDecomposition(decomposition.get());
             record_water_mechanical_energy->setDecomposition(decomposition.get());
+            if (fluid_boundary_indicator) fluid_boundary_indicator->setDecomposition(decomposition.get());
         }
     }
 

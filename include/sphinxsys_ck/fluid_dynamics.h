@@ -600,12 +600,23 @@ template <> class FreeSurfaceIndicationCK<Inner<WithUpdate>, Contact<>> : public
     }
     std::vector<BaseDynamics<void> *> deviceInteract(Real, const std::vector<BaseDynamics<void> *> &post)
     {
-        if (decomposition_) throw SphError("FreeSurfaceIndicationCK: not available in slab-decomposed runs yet");
         sphb200_fluid_args_t a = fluidArgs();
-        SPHCK_CALL(sphb200_free_surface_indication, &a, (int32_t *)particles_.deviceData<int>("Indicator"),
-                   (float *)particles_.deviceData<Real>("PositionDivergence"),
-                   (int32_t *)particles_.deviceData<int>("PreviousSurfaceIndicator"), threshold_by_dimensions_, smoothing_length_,
-                   execution_instance().stream());
+        int32_t *indicator = (int32_t *)particles_.deviceData<int>("Indicator");
+        float *position_divergence = (float *)particles_.deviceData<Real>("PositionDivergence");
+        int32_t *previous = (int32_t *)particles_.deviceData<int>("PreviousSurfaceIndicator");
+        if (decomposition_)
+        {
+            // the second sweep reads PositionDivergence of the neighbours: on the ghost planes it comes from their owners
+            // (tests/test_decomposed_oracle_cpu.py::test_dam_break_complete_case_dynamics_bit_identical)
+            SPHCK_CALL(sphb200_free_surface_indication_sweep, &a, indicator, position_divergence, previous, threshold_by_dimensions_,
+                       smoothing_length_, 0, execution_instance().stream());
+            decomposition_->refreshGhosts({"PositionDivergence"});
+            SPHCK_CALL(sphb200_free_surface_indication_sweep, &a, indicator, position_divergence, previous, threshold_by_dimensions_,
+                       smoothing_length_, 1, execution_instance().stream());
+            return post;
+        }
+        SPHCK_CALL(sphb200_free_surface_indication, &a, indicator, position_divergence, previous, threshold_by_dimensions_,
+                   smoothing_length_, execution_instance().stream());
         return post;
     }
 };

@@ -1245,9 +1245,31 @@ __global__ void __launch_bounds__(FL_THREADS) k_surface_update(FArgs a, const fl
     previous[i] = ind;
 }
 
+static int surface_indication_sweeps(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, int32_t *indicator, float *position_divergence,
+                                     int32_t *previous_indicator, float threshold, float smoothing_length, bool first, bool second,
+                                     void *stream);
+
 extern "C" int sphb200_free_surface_indication(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, int32_t *indicator,
                                                float *position_divergence, int32_t *previous_indicator, float threshold,
                                                float smoothing_length, void *stream)
+{
+    return surface_indication_sweeps(ctx, s, indicator, position_divergence, previous_indicator, threshold, smoothing_length, true, true, stream);
+}
+
+// One sweep of the indication (sweep 0: interact, writes PositionDivergence; sweep 1: update, reads PositionDivergence of
+// the neighbours): slab-decomposed runs refresh PositionDivergence on the ghost planes between the two.
+extern "C" int sphb200_free_surface_indication_sweep(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, int32_t *indicator,
+                                                     float *position_divergence, int32_t *previous_indicator, float threshold,
+                                                     float smoothing_length, int sweep, void *stream)
+{
+    SPH_CHECK_ARG(ctx, sweep == 0 || sweep == 1, "sweep must be 0 (interact) or 1 (update)");
+    return surface_indication_sweeps(ctx, s, indicator, position_divergence, previous_indicator, threshold, smoothing_length, sweep == 0,
+                                     sweep == 1, stream);
+}
+
+static int surface_indication_sweeps(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, int32_t *indicator, float *position_divergence,
+                                     int32_t *previous_indicator, float threshold, float smoothing_length, bool first, bool second,
+                                     void *stream)
 {
     SPH_CHECK_ARG(ctx, ctx && s && indicator && position_divergence && previous_indicator, "null pointer");
     FArgs a;
@@ -1258,10 +1280,14 @@ extern "C" int sphb200_free_surface_indication(sphb200_context_t *ctx, const sph
     SPH_CHECK_ARG(ctx, a.n_wall == 0 || (a.w_posvol && a.ct_count && a.ct_slice && a.ct_index), "null wall array");
     if (a.end <= a.begin) return 0;
     unsigned g = active_blocks(a, FL_THREADS);
-    if (a.analytic) SPH_LAUNCH(ctx, k_surface_interact<true>, g, FL_THREADS, 0, stream, a, dwtab, previous_indicator, position_divergence, threshold);
-    else SPH_LAUNCH(ctx, k_surface_interact<false>, g, FL_THREADS, 0, stream, a, dwtab, previous_indicator, position_divergence, threshold);
-    SPH_LAUNCH(ctx, k_surface_update, g, FL_THREADS, 0, stream, a, position_divergence, indicator, previous_indicator, threshold,
-               smoothing_length);
+    if (first)
+    {
+        if (a.analytic) SPH_LAUNCH(ctx, k_surface_interact<true>, g, FL_THREADS, 0, stream, a, dwtab, previous_indicator, position_divergence, threshold);
+        else SPH_LAUNCH(ctx, k_surface_interact<false>, g, FL_THREADS, 0, stream, a, dwtab, previous_indicator, position_divergence, threshold);
+    }
+    if (second)
+        SPH_LAUNCH(ctx, k_surface_update, g, FL_THREADS, 0, stream, a, position_divergence, indicator, previous_indicator, threshold,
+                   smoothing_length);
     return 0;
 }
 

@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--tolerance", action="store_true", help="pass if the fields agree within 1e-5 of the field maximum (SURVEY §8e) instead")
     ap.add_argument("--trace", action="store_true", help="compare after EVERY advection step and report where the first difference appears")
     ap.add_argument("--serial-exchange", action="store_true", help="plane exchange in line with the dynamics (no overlap)")
+    ap.add_argument("--surface-indicator", action="store_true", help="FreeSurfaceIndicationCK in the loop (two sweeps around a refresh of PositionDivergence); not yet run on GPUs")
     ap.add_argument("--correction", action="store_true", help="LinearCorrectionCK variants (one more ghost refresh: the B matrix); not yet run on GPUs")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -45,14 +46,14 @@ def main():
     dist.init_process_group("gloo")  # bootstrap and result gathering only; the data path is NCCL inside libsphb200
     uid = [host.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
-    sim = host.DamBreakCK(None, dim=3, dp=args.dp, generate=True, device_index=local, sort_interval=0, correction=args.correction, rank=rank, nranks=world,
+    sim = host.DamBreakCK(None, dim=3, dp=args.dp, generate=True, device_index=local, sort_interval=0, correction=args.correction, surface_indicator=args.surface_indicator, rank=rank, nranks=world,
                           unique_id=uid[0], serial_exchange=args.serial_exchange, recut_interval=args.recut_interval, initial_cut_shift=args.cut_shift)
     sim.initialize()
     cuts0 = sim.cuts().tolist()
     if args.trace:
         ref, prev_owner = None, None
         if rank == 0:
-            ref = host.DamBreakCK(None, dim=3, dp=args.dp, generate=True, device_index=local, sort_interval=0, correction=args.correction)
+            ref = host.DamBreakCK(None, dim=3, dp=args.dp, generate=True, device_index=local, sort_interval=0, correction=args.correction, surface_indicator=args.surface_indicator)
             ref.initialize()
         for step in range(1, args.outer + 1):
             sim.run_outer(1)
@@ -119,7 +120,7 @@ def main():
     dist.gather_object(mine, parts, dst=0)
     ok, report = True, {}
     if rank == 0:
-        ref = host.DamBreakCK(None, dim=3, dp=args.dp, generate=True, device_index=local, sort_interval=0, correction=args.correction)
+        ref = host.DamBreakCK(None, dim=3, dp=args.dp, generate=True, device_index=local, sort_interval=0, correction=args.correction, surface_indicator=args.surface_indicator)
         ref.initialize()
         n_ref = ref.run_outer(args.outer)
         n = ref.n_fluid
