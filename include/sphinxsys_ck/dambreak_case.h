@@ -285,7 +285,6 @@ class DamBreakCK
             }
             if (q.observers)
             {
-                if (q.nranks > 1) throw SphError("slab decomposition: observers are not decomposed yet");
                 registerPressure();
                 fluid_observer.reset(new ObserverBody(sph_system, "FluidObserver"));
                 fluid_observer->generateParticles<ObserverParticles>(createObservationPoints(q));
@@ -306,6 +305,7 @@ class DamBreakCK
             fluid_acoustic_time_step->setDecomposition(decomposition.get());
             record_water_mechanical_energy->setDecomposition(decomposition.get());
             if (fluid_boundary_indicator) fluid_boundary_indicator->setDecomposition(decomposition.get());
+            if (fluid_observer_pressure) fluid_observer_pressure->setDecomposition(decomposition.get());
         }
     }
 

@@ -843,8 +843,29 @@ template <class ExecutionPolicy, class DataType> class ObservedQuantityRecording
     bool header_written_ = false;
     std::vector<Real> times_;
     std::vector<std::vector<DataType>> records_;
+    SlabDecomposition *decomposition_ = nullptr;
+
+    // Slab-decomposed runs: every rank interpolates every probe over the particles it stores; the rank that owns the probe's
+    // cell plane stores its whole neighbourhood (own planes + one ghost plane either side, all variables current right
+    // after the configuration update), so its value is the single-GPU one, bit for bit. One term per probe is non-zero:
+    // the sum over the ranks is exact (tests/test_decomposed_oracle_cpu.py::test_dam_break_observer_probes_bit_identical).
+    void combineOverRanks()
+    {
+        static_assert(sizeof(DataType) % sizeof(Real) == 0, "observed quantities are made of Reals");
+        constexpr size_t width = sizeof(DataType) / sizeof(Real);
+        auto *dv_pos = observer_.getBaseParticles().template getVariableByName<Vecd>("Position");
+        Real *v = reinterpret_cast<Real *>(dv_interpolated_quantities_->Data());
+        std::vector<double> sum(number_of_observe_ * width, 0.0);
+        for (size_t i = 0; i != number_of_observe_; ++i)
+            if (decomposition_->ownsPlane(decomposition_->planeOf(dv_pos->Data()[i].x)))
+                for (size_t c = 0; c != width; ++c) sum[i * width + c] = double(v[i * width + c]);
+        for (size_t first = 0; first < sum.size(); first += 64)
+            decomposition_->allReduceSum(sum.data() + first, (int)std::min<size_t>(64, sum.size() - first));
+        for (size_t k = 0; k != sum.size(); ++k) v[k] = Real(sum[k]);
+    }
 
   public:
+    void setDecomposition(SlabDecomposition *d) { decomposition_ = d; }
     ObservedQuantityRecording(Contact<> &contact_relation, const std::string &variable_name)
         : observer_(contact_relation.getSPHBody()), observation_method_(contact_relation, variable_name),
           dv_interpolated_quantities_(observation_method_.dvInterpolatedQuantities()),
@@ -855,6 +876,7 @@ template <class ExecutionPolicy, class DataType> class ObservedQuantityRecording
     {
         observation_method_.exec();
         dv_interpolated_quantities_->synchronizeWithDevice();
+        if (decomposition_) combineOverRanks();
         const DataType *v = dv_interpolated_quantities_->Data();
         times_.push_back(sv_physical_time_->getValue());
         records_.emplace_back(v, v + number_of_observe_);

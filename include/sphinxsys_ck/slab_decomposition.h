@@ -554,6 +554,25 @@ class SlabDecomposition
     }
     // in place on a device float (the fused acoustic-dt slot)
     void allReduceMaxDevice(float *dev) { SPHCK_CALL(sphb200_comm_allreduce_max_f32, dev, 1, execution_instance().stream()); }
+    // cell plane of an x coordinate on the body's mesh, and whether this rank owns it (observer probes are recorded by the
+    // rank that owns their plane: it stores the probe's whole neighbourhood, own planes + one ghost plane on either side)
+    int planeOf(Real x) const
+    {
+        const sphb200_mesh_t &m = body_.getCellLinkedList().mesh_;
+        return hostCellCoordinate(x, m.lower[0], m.spacing, m.cells[0]);
+    }
+    bool ownsPlane(int plane) const { return plane >= cuts_[rank_] && plane < cuts_[rank_ + 1]; }
+    void allReduceSum(double *values, int count)
+    {
+        if (count <= 0) return;
+        if (count > 64) throw SphError("SlabDecomposition::allReduceSum: at most 64 values per call");
+        ExecutionInstance &ex = execution_instance();
+        double *d = scalars_.get<double>() + 32; // bytes 256..767 of the 1024-byte scratch
+        ex.check(sphb200_copy_h2d(d, values, (size_t)count * sizeof(double), ex.stream()), "sphb200_copy_h2d");
+        SPHCK_CALL(sphb200_comm_allreduce_sum_f64, d, count, ex.stream());
+        ex.check(sphb200_copy_d2h(values, d, (size_t)count * sizeof(double), ex.stream()), "sphb200_copy_d2h");
+        ex.synchronize();
+    }
     double allReduceSum(double v)
     {
         ExecutionInstance &ex = execution_instance();

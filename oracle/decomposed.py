@@ -192,6 +192,12 @@ class SlabRank:
             self.L = self.R(self.up - self.lo)
         elif self.cuts[0] != 0 or self.cuts[-1] != case.mesh.cells[0]:
             raise ValueError("cuts must run from 0 to the number of x planes")
+        # observer probes (ObservedQuantityRecording): every rank evaluates every probe over what it stores; the rank that
+        # owns the probe's cell plane has the whole neighbourhood (own planes + one ghost plane on either side) and its
+        # value is the one recorded
+        obs = self.kw.get("observers")
+        self.observers = None if obs is None else np.asarray(obs, dtype=self.R).reshape(-1, 3)
+        self.probe_series = []
         self.acoustic_steps = self.outer_steps = 0
         self.physical_time = 0.0
         self.migrated = self.wrapped = 0
@@ -294,6 +300,15 @@ class SlabRank:
             for nm in self.uints:
                 sim.uint(nm)[:] = np.concatenate([self.own[nm], recv["from_left"][nm], recv["from_right"][nm]]).reshape(-1)
         self.sim, self.n_own, self.n_ghost = sim, n_own, (n_l, n_r)
+        if self.observers is not None:  # fluid_observer_contact_relation.exec(); fluid_observer_pressure.writeToFile(), dambreak.cpp:223-224
+            sim.exec("observer_relation")
+            sim.exec("observe_pressure")
+            mine = self._owner(self.observers) == self.rank
+            values = np.where(mine, sim.real("Pressure", body=2).copy(), 0).astype(np.float64)
+            total = np.zeros_like(values)
+            for v in self.comm.route({r: values for r in range(self.size)}).values():
+                total += v  # one non-zero term per probe: exact
+            self.probe_series.append(total.astype(self.R))
 
     def _exchange_planes(self, names, with_gid=False):
         """Boundary-plane values of `names` to the neighbours; returns {"from_left": {...}, "from_right": {...}}."""

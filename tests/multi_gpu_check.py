@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--tolerance", action="store_true", help="pass if the fields agree within 1e-5 of the field maximum (SURVEY §8e) instead")
     ap.add_argument("--trace", action="store_true", help="compare after EVERY advection step and report where the first difference appears")
     ap.add_argument("--serial-exchange", action="store_true", help="plane exchange in line with the dynamics (no overlap)")
+    ap.add_argument("--observers", action="store_true", help="the six wall-pressure probes, recorded by the rank that owns each probe's plane; not yet run on GPUs")
     ap.add_argument("--surface-indicator", action="store_true", help="FreeSurfaceIndicationCK in the loop (two sweeps around a refresh of PositionDivergence); not yet run on GPUs")
     ap.add_argument("--correction", action="store_true", help="LinearCorrectionCK variants (one more ghost refresh: the B matrix); not yet run on GPUs")
     args = ap.parse_args()
@@ -46,14 +47,14 @@ def main():
     dist.init_process_group("gloo")  # bootstrap and result gathering only; the data path is NCCL inside libsphb200
     uid = [host.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, src=0)
-    sim = host.DamBreakCK(None, dim=3, dp=args.dp, generate=True, device_index=local, sort_interval=0, correction=args.correction, surface_indicator=args.surface_indicator, rank=rank, nranks=world,
+    sim = host.DamBreakCK(None, dim=3, dp=args.dp, generate=True, device_index=local, sort_interval=0, correction=args.correction, surface_indicator=args.surface_indicator, observers=args.observers, rank=rank, nranks=world,
                           unique_id=uid[0], serial_exchange=args.serial_exchange, recut_interval=args.recut_interval, initial_cut_shift=args.cut_shift)
     sim.initialize()
     cuts0 = sim.cuts().tolist()
     if args.trace:
         ref, prev_owner = None, None
         if rank == 0:
-            ref = host.DamBreakCK(None, dim=3, dp=args.dp, generate=True, device_index=local, sort_interval=0, correction=args.correction, surface_indicator=args.surface_indicator)
+            ref = host.DamBreakCK(None, dim=3, dp=args.dp, generate=True, device_index=local, sort_interval=0, correction=args.correction, surface_indicator=args.surface_indicator, observers=args.observers)
             ref.initialize()
         for step in range(1, args.outer + 1):
             sim.run_outer(1)
@@ -116,11 +117,13 @@ def main():
     mine = {"rid": sim.download_own("ReferenceID"), "pos": sim.download_own("Position"), "vel": sim.download_own("Velocity"),
             "rho": sim.download_own("Density"), "cuts0": cuts0, "n_ac": n_ac, "range": sim.own_range(), "cuts": sim.cuts().tolist(),
             "energy": sim.energy(), "time": sim.physical_time, "recuts": sim.exec("recuts")}
+    if args.observers:
+        mine["probes"] = sim.probe_records()[1]
     parts = [None] * world if rank == 0 else None
     dist.gather_object(mine, parts, dst=0)
     ok, report = True, {}
     if rank == 0:
-        ref = host.DamBreakCK(None, dim=3, dp=args.dp, generate=True, device_index=local, sort_interval=0, correction=args.correction, surface_indicator=args.surface_indicator)
+        ref = host.DamBreakCK(None, dim=3, dp=args.dp, generate=True, device_index=local, sort_interval=0, correction=args.correction, surface_indicator=args.surface_indicator, observers=args.observers)
         ref.initialize()
         n_ref = ref.run_outer(args.outer)
         n = ref.n_fluid
@@ -144,6 +147,11 @@ def main():
             scale = float(np.max(np.abs(single))) if n else 1.0
             report[f"rel_diff_{name}"] = diff / scale if scale else 0.0
             ok &= report[f"rel_diff_{name}"] <= 1e-5 if args.tolerance else report[f"bitwise_equal_{name}"]
+        if args.observers:
+            p_ref = ref.probe_records()[1]
+            same = [bool(p["probes"].shape == p_ref.shape and np.array_equal(p["probes"], p_ref)) for p in parts]
+            report["probe_records"], report["probe_series_equal_per_rank"] = list(p_ref.shape), same
+            ok &= all(same)
         e_ref = ref.energy()
         report["energy"] = [parts[0]["energy"], e_ref]
         ok &= abs(parts[0]["energy"] - e_ref) <= 1e-9 * abs(e_ref)

@@ -153,6 +153,26 @@ def test_dam_break_complete_case_dynamics_bit_identical():
     assert "Indicator" in _mismatches(g, dec.gather_by_gid(states, case.n_fluid))
 
 
+def test_dam_break_observer_probes_bit_identical():
+    """The six wall-pressure probes of the reference case file (dambreak.cpp:54-65,223-224) on three slabs: every probe is
+    taken from the rank that owns its cell plane (it stores the probe's whole neighbourhood); the recorded series equals
+    the single-domain one bit for bit, also for probes placed right at the cuts."""
+    case, planes = _dam_break()
+    cuts = dec.plan_cuts(planes, 0, case.mesh.cells[0], 3)
+    s = case.mesh.spacing
+    at_cuts = [[case.mesh.lower[0] + c * s + dx, 0.3, 0.25] for c in cuts[1:-1] for dx in (-1e-4, 1e-4)]
+    probes = [[case.DL, y, 0.5 * case.DW] for y in (0.01, 0.1, 0.2, 0.24, 0.252, 0.266)] + at_cuts + [[0.3, 0.2, 0.1], [1.7, 0.6, 0.4]]
+    kw = dict(observers=probes)
+    g = _single(case, 20, **kw)
+    ref = g.probe_series()
+    states, ranks = dec.run_threads(case, 3, cuts, 20, **kw)
+    got = np.array(ranks[0].probe_series)
+    assert got.shape == ref.shape == (21, len(probes))
+    assert np.array_equal(got.astype(np.float32).view(np.uint32), ref.astype(np.float32).view(np.uint32))
+    assert np.abs(ref[:, 6:]).max() > 0, "the probes inside the water column should see pressure"
+    assert all(np.array_equal(np.array(r.probe_series), got) for r in ranks)
+
+
 @pytest.mark.parametrize("stale", ["VolumetricMeasure", "Pressure", "Velocity"])
 def test_every_refresh_is_needed(stale):
     """Each of the three ghost refreshes carries a value the neighbours' own particles read: dropping one breaks parity."""
