@@ -311,3 +311,25 @@ def test_world_size_2_gloo_matches_single_domain():
         assert bad == [], f"{name}: variables differ from the single-domain oracle: {bad}"
         assert ac == ac_single
     assert results[0]["ring"][3] > 0
+
+
+def test_protocol_fuzz():
+    """Random slabs (empty and one-plane slabs included), random mixes of the optional dynamics, random drifts through the
+    seam, random lengths: the decomposed run is the single-domain run, bit for bit, every time."""
+    rng = np.random.default_rng(20261018)
+    dam, _ = _dam_break()
+    for _ in range(3):
+        n = int(rng.integers(2, 6))
+        cuts = [0] + np.sort(rng.choice(np.arange(5, 30), size=n - 1, replace=False)).tolist() + [dam.mesh.cells[0]]
+        steps = int(rng.integers(8, 25))
+        kw = dict(correction=int(rng.integers(0, 2)), surface_indicator=int(rng.integers(0, 2)))
+        states, _ranks = dec.run_threads(dam, n, cuts, steps, **kw)
+        assert _mismatches(_single(dam, steps, **kw), dec.gather_by_gid(states, dam.n_fluid)) == [], (cuts, steps, kw)
+    for _ in range(3):
+        case, first, planes = _ring_case(float(rng.uniform(-2.5, 2.5)), x_scale=int(rng.integers(1, 3)), n_side=int(rng.choice([12, 16])))
+        n = int(rng.integers(2, 5))
+        cuts = [first] + np.sort(rng.choice(np.arange(first + 1, first + planes), size=n - 1, replace=False)).tolist() + [first + planes]
+        steps = int(rng.integers(8, 20))
+        kw = dict(free_surface=0, viscosity=float(rng.choice([0.0, 0.01])), transport_velocity=int(rng.integers(0, 2)))
+        states, _ranks = dec.run_threads(case, n, cuts, steps, ring=True, **kw)
+        assert _mismatches(_single(case, steps, **kw), dec.gather_by_gid(states, case.n_fluid)) == [], (cuts, steps, kw)
