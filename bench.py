@@ -24,6 +24,10 @@ import time
 
 import numpy as np
 
+# stdout carries exactly ONE line, the JSON: NCCL's version banner / debug log (printed when the environment sets NCCL_DEBUG)
+# goes to stderr unless the caller chose a file for it
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
