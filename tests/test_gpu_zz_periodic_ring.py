@@ -37,9 +37,9 @@ def _report(key, value):
         pass
 
 
-def _case(n_side, drift, jitter=0.05):
+def _case(n_side, drift, jitter=0.05, dim=3):
     from sphinxsys_b200 import cases
-    case = cases.taylor_green(dim=3, n_side=n_side, jitter=jitter)
+    case = cases.taylor_green(dim=dim, n_side=n_side, jitter=jitter)
     vel = case.fluid_vel.copy()
     vel[:, 0] += np.float32(drift)  # uniform drift: particles cross the seam
     return dataclasses.replace(case, fluid_vel=vel)
@@ -168,3 +168,36 @@ def test_ring_of_one_slab_viscous_transport():
     rep["energy_viscous_vs_inviscid"] = (e_visc, inviscid.energy())
     assert e_visc < rep["energy_viscous_vs_inviscid"][1]
     _report("ring_of_one_viscous_transport", rep)
+
+
+@pytest.mark.xfail(strict=False, reason="written after the GPU budget of round 1 was spent: not yet run on a B200 "
+                                        "(its CPU twin, test_periodic_ring_2d_bit_identical, is green)")
+def test_ring_of_one_slab_2d():
+    """The 2-D Taylor-Green case of the reference (taylor_green.cpp) on the ring of one slab: x through the seam, y by images."""
+    from sphinxsys_b200.host import TaylorGreenCK
+    case = _case(40, 1.5, dim=2)
+    n_outer = 15
+    gpu = TaylorGreenCK(case, ring=True)
+    gpu.initialize()
+    o32, _ = _oracle_on_gpu_mesh(case, gpu)
+    o64, _ = _oracle_on_gpu_mesh(case, gpu, f64=True)
+    for o in (o32, o64):
+        o.exec("prepare_ck")
+        o.exec("run_ck", 1e9, n_outer, 1e9, 0)
+    n_ac = gpu.run_outer(n_outer)
+    assert n_ac == int(o32.exec("acoustic_steps"))
+    same_path = int(o64.exec("acoustic_steps")) == n_ac
+    n, rep = case.n_fluid, {}
+    pos = _own(gpu, "Position", n)
+    d = pos.astype(np.float64) - o32.real("Position", 3).reshape(-1, 3)
+    d -= np.round(d)
+    rep["Position"] = float(np.abs(d).max())
+    assert rep["Position"] < 5e-6
+    assert int((np.abs(pos[:, 0].astype(np.float64) - case.fluid_pos[:, 0]) > 0.5).sum()) > 0
+    for nm, w, tol in (("Velocity", 3, 2e-4), ("Density", 1, 2e-6)):
+        b = o32.real(nm, w).reshape(-1, w) if w > 1 else o32.real(nm, w)
+        b64 = o64.real(nm, w).reshape(-1, w) if w > 1 else o64.real(nm, w)
+        e, noise = rel_err(_own(gpu, nm, n), b), (rel_err(b, b64) if same_path else 0.0)
+        rep[nm] = {"gpu_vs_oracle32": e, "oracle32_vs_oracle64": noise}
+        assert e <= max(tol, 2.0 * noise), f"{nm}: {e:.3e} (fp32 noise {noise:.3e})"
+    _report("ring_of_one_2d", rep)
