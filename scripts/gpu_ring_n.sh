@@ -3,6 +3,8 @@
 # then config 4's weak-scaling point at N GPUs. usage (inside gpurun --gpus N): scripts/gpu_ring_n.sh N [n_side_bench]
 N=${1:-2}; NS=${2:-256}; OUT=gpurun_out/ring_n$N; mkdir -p $OUT
 export SPHB200_CHECK_EXCHANGE=1   # first runs of the ring over NCCL: a plane-size mismatch stops with a message instead of a hang
+# the two single-GPU ring tests that have not been run yet
+SPHB200_RUN_UNVERIFIED=1 timeout 200 python -m pytest tests/test_gpu_zz_periodic_ring.py -m gpu -q > $OUT/pytest_unverified.log 2>&1; tail -3 $OUT/pytest_unverified.log
 RUN="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1"
 timeout 240 $RUN --master-port 29533 tests/multi_gpu_check_ring.py --n-side 32 --outer 12 --drift 2.0 --out $OUT/ring_check.json \
     > $OUT/ring_check.log 2>&1; echo "ring check rc=$?"
