@@ -19,10 +19,16 @@ Protocol (one rank; same order as DamBreakCK::stepOuter / SlabDecomposition::reb
   * ghost refresh inside a step: VolumetricMeasure after AdvectionStepSetup, Pressure after the initialisation of
     the 1st half, Velocity after its update, LinearCorrectionMatrix after it is rebuilt (correction variants only),
     PositionDivergence between the two sweeps of the free-surface indication (when the case has it);
-    nothing else (the viscous force, the kernel gradient integral and the
-    transport-velocity correction of the Taylor-Green case run on what is already there). Stages also run on the ghosts here (the GPU runs them on
-    the active range only); their results there are meaningless and never read, which makes the check stricter;
+    nothing else (the viscous force, the kernel gradient integral and the transport-velocity correction of the
+    Taylor-Green case run on what is already there). Stages also run on the ghosts here (the GPU runs them on the
+    active range only); what they leave there is meaningless and never read — except where a ghost close to the cut
+    would get the RIGHT value by accident (PositionDivergence), which is wiped before the refresh so that a missing
+    refresh cannot hide;
+  * observer probes: recorded by the rank that owns the probe's cell plane (it stores the whole neighbourhood);
   * time steps: raw reductions over the OWN particles, max over the ranks, then the CFL formula.
+The GPU differs from this restatement in one place: on a ring it decides what left the box by cell PLANE and keeps a
+shifted particle inside the plane it belongs to (sphb200_seam_shift), while the wrap below is by position as in the
+reference; the two agree except for particles within rounding of a face (identical modulo L).
 Periodic runs along x ("ring"): the box is a whole number of cell planes (aligned mesh, spacing >= cut-off), the
 first and the last rank are neighbours, ghost planes that cross the seam travel with Position shifted by -/+ L
 (the arithmetic of the reference's ghost list entry, domain_bounding.cpp:26,45); y / z periodicity stays local (the
