@@ -161,3 +161,93 @@ def test_ring_seam_thresholds_follow_the_cell_arithmetic(n_side):
         assert np.all(moved == (P if delta > 0 else -P)), "a shifted particle changed its plane relative to the box"
         free = (y == x + delta)
         assert free.mean() > 0.99, "the clamps act in rounding cases only"
+
+
+@pytest.mark.parametrize("n_side,nranks", [(16, 1), (16, 2), (32, 3), (256, 8)])
+def test_ring_ownership_never_loses_or_duplicates_a_particle(n_side, nranks):
+    """The ownership rules of the GPU ring restated in numpy (SlabDecomposition::rebuild on a ring: leavers and boundary
+    planes selected by cell PLANE, sphb200_seam_shift on what crosses the seam) and driven hard: particles start within a
+    few ulps of the box faces and of the cuts and random-walk by up to a fifth of a plane per step. After every
+    configuration update each particle has exactly one owner, sits in one of its owner's planes, and every rank's ghost
+    planes hold exactly the particles of its neighbours' boundary planes (sizes that do not match would leave an NCCL
+    receive waiting: the invariant refreshGhosts() relies on)."""
+    from oracle import oracle as orc
+    from sphinxsys_b200 import host, hostmath as hm
+    f = np.float32
+    cutoff = f(2.0) * f(1.3) * f(1.0 / n_side)
+    m, sm = host.aligned_periodic_mesh((0, 0, 0), (1, 1, 1), cutoff)
+    mesh = hm.MeshSpec(tuple(m.lower), m.spacing, tuple(m.cells))
+    k0, P, s, L = sm.first_plane, sm.box_planes, f(m.spacing), f(1.0)
+    cuts = [k0 + P * r // nranks for r in range(nranks + 1)]
+
+    def plane(x):
+        if len(x) == 0:
+            return np.zeros(0, dtype=np.int64)
+        pos = np.full((len(x), 3), 0.5, dtype=f)
+        pos[:, 0] = x
+        cell, _ = orc.cell_keys(pos, mesh)
+        return cell.astype(np.int64) // (m.cells[1] * m.cells[2])
+
+    def shift(x, delta):  # k_seam_shift
+        y = (x + delta).astype(f)
+        pl = plane(x)
+        if delta > 0:
+            return np.where(pl < k0, np.minimum(y, f(sm.own_max)), np.minimum(np.maximum(y, f(sm.ghost_high_min)), f(sm.ghost_high_max))).astype(f)
+        return np.where(pl >= k0 + P, np.maximum(y, f(sm.own_min)), np.maximum(np.minimum(y, f(sm.ghost_low_max)), f(sm.ghost_low_min))).astype(f)
+
+    rng = np.random.default_rng(n_side + nranks)
+    faces = np.array([0.0, 1.0] + [float(m.lower[0]) + c * float(s) for c in cuts[1:-1]])
+    n = 4000
+    x0 = (rng.choice(faces, n) + rng.choice([0.0, 1e-9, -1e-9, 6e-8, -6e-8, 1e-4, -1e-4], n) + np.where(rng.random(n) < 0.3, rng.uniform(0, 1, n), 0.0))
+    x0 = np.mod(x0, 1.0).astype(f)
+    x0 = np.clip(x0, f(sm.own_min), f(sm.own_max))
+    pl0 = plane(x0)
+    own = [{"gid": np.flatnonzero((pl0 >= cuts[r]) & (pl0 < cuts[r + 1])), "x": None} for r in range(nranks)]
+    for r in range(nranks):
+        own[r]["x"] = x0[own[r]["gid"]]
+    assert sum(o["gid"].size for o in own) == n
+    for step in range(30):
+        send = []
+        for r in range(nranks):  # move, then sphb200_slab_select: <= first own plane to the left, >= last own plane to the right
+            o = own[r]
+            o["x"] = (o["x"] + rng.uniform(-0.2, 0.2, o["x"].size).astype(f) * s).astype(f)
+            # the rounding cases on purpose: some particles of the seam ranks are put within a few ulps of the box faces,
+            # on either side (just outside: leavers whose shifted position rounds onto the far face; just inside: boundary-
+            # plane particles whose image rounds into the box)
+            pl = plane(o["x"])
+            if r == 0:
+                near = np.flatnonzero(pl == cuts[0])[:24]
+                edge = f(sm.own_min)
+                vals = [edge, np.nextafter(edge, f(9)), np.nextafter(edge, f(-9)), np.nextafter(np.nextafter(edge, f(-9)), f(-9)), f(-2e-8), f(0.0)]
+                o["x"][near] = np.array([vals[k % len(vals)] for k in range(near.size)], dtype=f)
+            if r == nranks - 1:
+                near = np.flatnonzero(pl == cuts[-1] - 1)[-24:]
+                edge = f(sm.own_max)
+                vals = [edge, np.nextafter(edge, f(-9)), f(sm.ghost_high_min), np.nextafter(f(sm.ghost_high_min), f(9)), f(1.0), np.nextafter(f(1.0), f(9))]
+                o["x"][near] = np.array([vals[k % len(vals)] for k in range(near.size)], dtype=f)
+            pl = plane(o["x"])
+            send.append({"left": pl <= cuts[r], "right": pl >= cuts[r + 1] - 1})
+        new = []
+        for r in range(nranks):
+            o, lft, rgt = own[r], (r - 1) % nranks, (r + 1) % nranks
+            from_left = (own[lft]["gid"][send[lft]["right"]], own[lft]["x"][send[lft]["right"]])
+            from_right = (own[rgt]["gid"][send[rgt]["left"]], own[rgt]["x"][send[rgt]["left"]])
+            xl = shift(from_left[1], -L) if r == 0 else from_left[1]                  # over the seam: my left neighbour is the last rank
+            xr = shift(from_right[1], L) if r == nranks - 1 else from_right[1]
+            gid = np.concatenate([o["gid"], from_left[0], from_right[0]])
+            x = np.concatenate([o["x"], xl, xr])
+            pl = plane(x)
+            mine = (pl >= cuts[r]) & (pl < cuts[r + 1])
+            ghosts_l, ghosts_r = pl < cuts[r], pl >= cuts[r + 1]
+            new.append({"gid": gid[mine], "x": x[mine], "gl": np.sort(gid[ghosts_l]), "gr": np.sort(gid[ghosts_r]),
+                        "pl_ok": bool(np.all(pl[ghosts_l] == cuts[r] - 1) and np.all(pl[ghosts_r] == cuts[r + 1]))})
+        own = new
+        owners = np.concatenate([o["gid"] for o in own])
+        assert owners.size == n and np.array_equal(np.sort(owners), np.arange(n)), f"step {step}: a particle was lost or is owned twice"
+        assert all(o["pl_ok"] for o in own), f"step {step}: a ghost outside the ghost planes"
+        if nranks > 1 or True:
+            for r in range(nranks):  # ghost planes = the neighbours' boundary planes after the update
+                lft, rgt = (r - 1) % nranks, (r + 1) % nranks
+                pl_l, pl_r = plane(own[lft]["x"]), plane(own[rgt]["x"])
+                assert np.array_equal(own[r]["gl"], np.sort(own[lft]["gid"][pl_l == cuts[lft + 1] - 1])), f"step {step}: left ghost plane of rank {r}"
+                assert np.array_equal(own[r]["gr"], np.sort(own[rgt]["gid"][pl_r == cuts[rgt]])), f"step {step}: right ghost plane of rank {r}"
