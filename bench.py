@@ -111,8 +111,11 @@ def cpu_baseline_run(dp, max_outer, budget_s, threads=0, warmup=0):
         done += 1
     elapsed = time.perf_counter() - t0
     n_ac = int(sim.exec("acoustic_steps")) - n_ac0
+    # also ns per pair interaction = wall time over (neighbour-list entries x 2 half steps x acoustic steps);
+    # the per-advection work (summation, cell list, relation search) is inside the wall time, as in `value`
+    pairs = int(sim.uint("inner_offset")[-1]) + int(sim.uint("contact_offset")[-1])
     return {"value": case.n_fluid * n_ac / elapsed, "unit": "particle-steps/s", "cores": orc.lib().orc_max_threads(),
-            "kind": "port",
+            "kind": "port", "ns_per_pair_interaction": 1e9 * elapsed / max(2.0 * pairs * n_ac, 1.0),
             "sample": f"3-D dam break dp={dp} ({case.n_fluid} fluid + {case.n_wall} wall), {done} outer / {n_ac} acoustic steps "
                       f"in {elapsed:.1f} s after {warmup} untimed, oracle fp32 + OpenMP (restatement of the reference CK par_host "
                       f"path, not the TBB build)",
