@@ -272,10 +272,13 @@ def _gloo_worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         out = {}
-        for name in ("dam_break", "ring"):
-            if name == "dam_break":
+        for name in ("dam_break", "complete", "ring"):
+            if name in ("dam_break", "complete"):
                 case, planes = _dam_break()
                 cuts, steps, kw, ring = dec.plan_cuts(planes, 0, case.mesh.cells[0], world), 10, {}, False
+                if name == "complete":  # the dynamics of the complete reference case file: correction, indication, probes
+                    kw = dict(correction=1, surface_indicator=1,
+                              observers=[[case.DL, y, 0.5 * case.DW] for y in (0.01, 0.1, 0.2)] + [[0.9, 0.3, 0.25]])
             else:
                 case, first, nplanes = _ring_case(1.0)
                 cuts = dec.plan_cuts(dec.x_plane(case.fluid_pos, case.mesh), first, first + nplanes, world)
@@ -287,8 +290,10 @@ def _gloo_worker(rank, world, port, q):
             dist.all_gather_object(states, sr.own_state())
             if rank == 0:
                 g = _single(case, steps, **kw)
-                out[name] = (_mismatches(g, dec.gather_by_gid(states, case.n_fluid)), sr.acoustic_steps,
-                             int(g.exec("acoustic_steps")), sr.migrated + sr.wrapped)
+                bad = _mismatches(g, dec.gather_by_gid(states, case.n_fluid))
+                if "observers" in kw and not np.array_equal(np.array(sr.probe_series, dtype=np.float32), g.probe_series().astype(np.float32)):
+                    bad.append("probe series")
+                out[name] = (bad, sr.acoustic_steps, int(g.exec("acoustic_steps")), sr.migrated + sr.wrapped)
         q.put((rank, out))
     finally:
         dist.destroy_process_group()
@@ -306,7 +311,7 @@ def test_world_size_2_gloo_matches_single_domain():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    for name in ("dam_break", "ring"):
+    for name in ("dam_break", "complete", "ring"):
         bad, ac, ac_single, moved = results[0][name]
         assert bad == [], f"{name}: variables differ from the single-domain oracle: {bad}"
         assert ac == ac_single
