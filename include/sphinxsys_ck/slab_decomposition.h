@@ -458,7 +458,6 @@ class SlabDecomposition
     // Results do not depend on the cuts (in-cell order is by ReferenceID), so a run with re-cuts stays bit-identical.
     void recut()
     {
-        if (ring_.on) throw SphError("SlabDecomposition::recut: not available on a ring of slabs yet");
         ExecutionInstance &ex = execution_instance();
         CellLinkedList &cl = body_.getCellLinkedList();
         const int planes = cl.mesh_.cells[0];
@@ -484,9 +483,13 @@ class SlabDecomposition
         SPHCK_CALL(sphb200_comm_allreduce_sum_f64, d_hist, planes, st);
         ex.check(sphb200_copy_d2h(hist.data(), d_hist, hist.size() * sizeof(double), st), "sphb200_copy_d2h");
         ex.synchronize();
-        std::vector<uint64_t> per_plane(planes);
-        for (int x = 0; x < planes; ++x) per_plane[x] = (uint64_t)(hist[x] + 0.5);
-        std::vector<int> next = limitCutMoves(cuts_, planSlabCuts(per_plane, nranks_));
+        // a ring is cut over the planes of the periodic box only; its seam (the first and the last cut) stays where it is
+        const int p0 = ring_.on ? ring_.first_plane() : 0, p1 = ring_.on ? p0 + ring_.box_planes() : planes;
+        std::vector<uint64_t> per_plane(p1 - p0);
+        for (int x = p0; x < p1; ++x) per_plane[x - p0] = (uint64_t)(hist[x] + 0.5);
+        std::vector<int> wanted = planSlabCuts(per_plane, nranks_);
+        for (int &c : wanted) c += p0;
+        std::vector<int> next = limitCutMoves(cuts_, wanted);
         ++recuts_;
         if (next == cuts_)
         {

@@ -413,14 +413,15 @@ class SlabRank:
         (`plan(hist, nranks)`, the host layer's planSlabCuts), every cut moved at most to the far end of an adjacent slab
         (`limit(old, wanted)`, limitCutMoves), so that the hand-over stays between neighbour ranks — which rebuild()
         asserts. Returns True if the cuts changed."""
-        if self.ring:
-            raise NotImplementedError("re-cutting on a ring of slabs")
-        planes_total = int(self.case.mesh.cells[0])
-        mine = np.bincount(self._planes(self.sim.real("Position", 3).reshape(-1, 3)[: self.n_own]), minlength=planes_total)
+        # a ring is cut over the planes of the periodic box only; its seam (first and last cut) stays where it is
+        first = self.cuts[0] if self.ring else 0
+        planes_total = (self.cuts[-1] - first) if self.ring else int(self.case.mesh.cells[0])
+        mine = np.bincount(self._planes(self.sim.real("Position", 3).reshape(-1, 3)[: self.n_own]) - first, minlength=planes_total)
         hist = np.zeros(planes_total, dtype=np.uint64)
         for h in self.comm.route({r: mine for r in range(self.size)}).values():
             hist += h.astype(np.uint64)
-        new = [int(c) for c in limit(np.asarray(self.cuts, dtype=np.int32), plan(hist, self.size))]
+        wanted = np.asarray(plan(hist, self.size), dtype=np.int32) + np.int32(first)
+        new = [int(c) for c in limit(np.asarray(self.cuts, dtype=np.int32), wanted)]
         changed = new != self.cuts
         self.cuts = new
         self.rebuild(bound=False)

@@ -120,6 +120,42 @@ def test_dam_break_recut_keeps_bit_identity():
     assert _mismatches(g, dec.gather_by_gid([r.own_state() for r in ranks], case.n_fluid)) == []
 
 
+def test_ring_recut_keeps_bit_identity():
+    """Re-cutting on a ring: the cuts inside the periodic box move (the seam stays), hand-overs go to neighbours only."""
+    import threading
+    from sphinxsys_b200 import host
+    case, first, planes = _ring_case(1.5, x_scale=2, n_side=12)   # 9 box planes
+    skewed = [first, first + 1, first + 2, first + planes]
+    steps, nranks = 12, 3
+    g = _single(case, steps, free_surface=0)
+    comms = dec.ThreadComm.make(nranks)
+    ranks, errors, changes = [None] * nranks, [], [0] * nranks
+
+    def work(r):
+        try:
+            sr = dec.SlabRank(case, comms[r], skewed, ring=True, free_surface=0)
+            for k in range(1, steps + 1):
+                sr.step_outer()
+                if k % 3 == 0:
+                    changes[r] += int(sr.recut(host.plan_slab_cuts, host.limit_cut_moves))
+            ranks[r] = sr
+        except BaseException as e:  # noqa: BLE001
+            errors.append(e)
+            comms[r]._s.barrier.abort()
+
+    threads = [threading.Thread(target=work, args=(r,)) for r in range(nranks)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    real = [e for e in errors if not isinstance(e, threading.BrokenBarrierError)]
+    assert not errors, (real or errors)[0]
+    assert changes[0] > 0 and ranks[0].cuts[0] == first and ranks[0].cuts[-1] == first + planes
+    own = [r.n_own for r in ranks]
+    assert max(own) - min(own) < 0.2 * case.n_fluid, f"slabs not re-balanced: {own} with cuts {ranks[0].cuts}"
+    assert _mismatches(g, dec.gather_by_gid([r.own_state() for r in ranks], case.n_fluid)) == []
+
+
 @pytest.mark.parametrize("viscosity", [0.0, 0.02])
 def test_dam_break_correction_variants_bit_identical(viscosity):
     """The Correction aliases the complete reference case file uses (dambreak.cpp:117-124): one more refresh, of the B
