@@ -245,9 +245,8 @@ def test_ring_ownership_never_loses_or_duplicates_a_particle(n_side, nranks):
         owners = np.concatenate([o["gid"] for o in own])
         assert owners.size == n and np.array_equal(np.sort(owners), np.arange(n)), f"step {step}: a particle was lost or is owned twice"
         assert all(o["pl_ok"] for o in own), f"step {step}: a ghost outside the ghost planes"
-        if nranks > 1 or True:
-            for r in range(nranks):  # ghost planes = the neighbours' boundary planes after the update
-                lft, rgt = (r - 1) % nranks, (r + 1) % nranks
-                pl_l, pl_r = plane(own[lft]["x"]), plane(own[rgt]["x"])
-                assert np.array_equal(own[r]["gl"], np.sort(own[lft]["gid"][pl_l == cuts[lft + 1] - 1])), f"step {step}: left ghost plane of rank {r}"
-                assert np.array_equal(own[r]["gr"], np.sort(own[rgt]["gid"][pl_r == cuts[rgt]])), f"step {step}: right ghost plane of rank {r}"
+        for r in range(nranks):  # ghost planes = the neighbours' boundary planes after the update (a ring of one: its own)
+            lft, rgt = (r - 1) % nranks, (r + 1) % nranks
+            pl_l, pl_r = plane(own[lft]["x"]), plane(own[rgt]["x"])
+            assert np.array_equal(own[r]["gl"], np.sort(own[lft]["gid"][pl_l == cuts[lft + 1] - 1])), f"step {step}: left ghost plane of rank {r}"
+            assert np.array_equal(own[r]["gr"], np.sort(own[rgt]["gid"][pl_r == cuts[rgt]])), f"step {step}: right ghost plane of rank {r}"
