@@ -153,7 +153,8 @@ inline sphb200_mesh_t alignedPeriodicMesh(const BoundingBoxd &box, Real cutoff, 
     f = planeFace(m, k0 + planes);     sm.own_max = f.first;        sm.ghost_high_min = f.second;
     f = planeFace(m, k0 + planes + 1); sm.ghost_high_max = f.first;
     // the faces of the box sit on the plane faces up to rounding
-    const Real tol = Real(1e-5) * spacing;
+    // (lower + k * spacing is rounded per plane: the distance grows with the number of planes, a few ulp of the box length)
+    const Real tol = Real(1e-5) * spacing + Real(16) * std::numeric_limits<Real>::epsilon() * std::max({std::abs(lo), std::abs(up), L});
     if (std::abs(sm.own_min - lo) > tol || std::abs(sm.ghost_high_min - up) > tol)
         throw SphError("alignedPeriodicMesh: the box faces are not on cell-plane faces");
     return m;
@@ -217,7 +218,7 @@ class SlabDecomposition
 
   public:
     SlabDecomposition(SPHBody &body, int rank, int nranks, const std::vector<int> &cuts, const SeamRing &ring = SeamRing())
-        : body_(body), rank_(rank), nranks_(nranks), ring_(ring), cuts_(cuts), scalars_(1024)
+        : body_(body), rank_(rank), nranks_(nranks), ring_(ring), cuts_(cuts), scalars_(1024 + 8 * ((size_t)nranks + 2))
     {
         const sphb200_mesh_t &m = body.getCellLinkedList().mesh_;
         plane_cells_ = (uint32_t)m.cells[1] * (uint32_t)m.cells[2];
@@ -294,8 +295,10 @@ class SlabDecomposition
     uint64_t ghostParticles() const { return ghost_particles_; }
     uint64_t migratedOut() const { return migrated_out_; }
 
-    // once per advection step, instead of UpdateCellLinkedList::exec()
-    void rebuild()
+    // once per advection step, instead of UpdateCellLinkedList::exec(). `check_planes` = false for the first of recut()'s
+    // two rebuilds: between them the former owner still holds whole planes it handed over, so "ghosts" are not one plane
+    // per side yet and the SPHB200_CHECK_EXCHANGE comparison would raise a false alarm (and leave the peers in NCCL).
+    void rebuild(bool check_planes = true)
     {
         ExecutionInstance &ex = execution_instance();
         BaseParticles &p = body_.getBaseParticles();
@@ -399,12 +402,16 @@ class SlabDecomposition
         migrated_out_ += (uint64_t)send_l + send_r; // boundary-plane particles and leavers handed to the neighbours
         // periodic images of the other axes: made for all stored particles behind them, after this configuration update
         if (PeriodicImages *im = body_.periodicImages()) im->setStoredRange(n_, a0_, a1_);
-        if (checkExchangeEnabled()) verifyGhostPlanes();
+        if (check_planes && checkExchangeEnabled()) verifyGhostPlanes();
+        // ring: a particle that left over the seam stays here as a ghost with the x it had on THIS side of the box, while
+        // every later refresh delivers fl(fl(x -/+ L) +/- L) from its new owner. Bring Position on the ghost planes to the
+        // owner's value right away, so that the relation build, the summation and both half steps see ONE position.
+        if (check_planes && ring_.on) refreshGhosts({"Position"});
         // 5. slot origin: the slot the first stored particle has in the undecomposed run = particles owned by the ranks
         //    below minus the left ghost plane. Relations against bodies that are NOT decomposed (the wall) lay their rows
         //    out relative to it, so that summation order does not depend on the decomposition (sphb200_relation_t::bank_aligned).
         {
-            uint64_t own = a1_ - a0_, *d_own = scalars_.get<uint64_t>() + 64, *d_all = d_own + 1;
+            uint64_t own = a1_ - a0_, *d_own = scalars_.get<uint64_t>() + 128, *d_all = d_own + 1; // bytes 1024.. : behind the reduction windows
             std::vector<uint64_t> all(nranks_);
             ex.check(sphb200_copy_h2d(d_own, &own, sizeof(own), st), "sphb200_copy_h2d");
             SPHCK_CALL(sphb200_comm_allgather_u64, d_own, d_all, 1, st);
@@ -497,7 +504,7 @@ class SlabDecomposition
             return;
         }
         cuts_ = next;
-        rebuild();
+        rebuild(false); // hand over: ghosts are not one plane per side until the former owner has dropped its copies
         rebuild();
     }
     uint64_t recuts() const { return recuts_; }

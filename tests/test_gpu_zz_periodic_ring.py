@@ -26,13 +26,6 @@ from helpers import rel_err  # noqa: E402
 
 REPORT = {}
 
-# Written after the GPU budget of round 1 was spent: never run on a B200 so far (their CPU twins in
-# tests/test_decomposed_oracle_cpu.py are green). Kept out of the default GPU suite until they have been run once by hand:
-#   SPHB200_RUN_UNVERIFIED=1 python -m pytest tests/test_gpu_zz_periodic_ring.py -m gpu -q
-NOT_YET_RUN = pytest.mark.skipif(os.environ.get("SPHB200_RUN_UNVERIFIED") != "1",
-                                 reason="not yet run on a GPU (set SPHB200_RUN_UNVERIFIED=1 to run it)")
-
-
 def _report(key, value):
     REPORT[key] = value
     out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
@@ -140,7 +133,6 @@ def test_ring_of_one_slab_against_single_domain_oracle(n_side, n_outer, drift):
     _report(f"ring_of_one_{n_side}_{drift}", rep)
 
 
-@NOT_YET_RUN
 def test_ring_of_one_slab_viscous_transport():
     """Taylor-Green as the reference runs it (viscous force, Re = 100, + transport-velocity correction) on the ring of one
     slab: bounds of tests/test_gpu_viscous_transport.py (the fp32 oracle's own distance to the fp64 oracle, >= 2e-4)."""
@@ -175,7 +167,6 @@ def test_ring_of_one_slab_viscous_transport():
     _report("ring_of_one_viscous_transport", rep)
 
 
-@NOT_YET_RUN
 def test_ring_of_one_slab_2d():
     """The 2-D Taylor-Green case of the reference (taylor_green.cpp) on the ring of one slab: x through the seam, y by images."""
     from sphinxsys_b200.host import TaylorGreenCK
