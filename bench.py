@@ -7,10 +7,18 @@ reduction + 1st half + 2nd half each), position update, particle sort at its nat
 steps), cell-linked-list and relation rebuild.  value = N_fluid x (acoustic sub-steps executed) / seconds, i.e.
 every per-advection cost is amortised into the particle-step rate.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--dp 0.00625] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--dp 0.00625] [--impl ours|reference] [--no-extras]
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the CPU oracle (the reference cannot be built in this
-image) on the box's host cores on a bounded sample of the same workload.
+image) on the box's host cores: the SAME case at the SAME spacing (config 2, dp = 0.00625) at every N, all host cores
+(the thread count comes from the CPU affinity mask, not from OMP_NUM_THREADS, which torchrun sets to 1), bounded in the
+number of advection steps only.
+
+Sub-records of the line (all measured in the run): `parity` (N > 1: particle count, energy and an id-keyed 64-bit digest of
+Position/Velocity after the warm-up, next to the same three from a 1-GPU run of the same spacing on rank 0's GPU),
+`developed` (the same K steps timed again after --developed-steps more advection steps: the flow has left the lattice),
+`config3` (N = 8: ~16 M fluid particles per GPU, dp = 0.002), `config4` (periodic Taylor-Green ring, n_side^3 per GPU),
+`config5` (N = 1: neighbour-search chain at 16.7 M and 268 M random particles).
 """
 from __future__ import annotations
 
@@ -93,16 +101,42 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def cpu_baseline_run(dp, max_outer, budget_s, threads=0, warmup=0):
+def host_threads():
+    """Threads the CPU arm may use: the affinity mask of this process (torchrun exports OMP_NUM_THREADS=1, which would
+    otherwise turn the all-cores baseline into a one-thread run)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except (AttributeError, OSError):
+        return max(1, os.cpu_count() or 1)
+
+
+def cpu_baseline_run(dp, max_outer, budget_s, threads=0, warmup=0, fit_s=None):
     """The oracle (CPU restatement of the reference's CK par_host data flow) on the host cores: bounded sample.
-    `warmup` outer steps run untimed first; then up to `max_outer` timed outer steps (fewer only if budget_s runs out)."""
+    `warmup` outer steps run untimed first; then up to `max_outer` timed outer steps (fewer only if budget_s runs out).
+    fit_s: shrink warm-up and step count (never the case) so that set-up + warm-up + timed steps fit that many seconds;
+    the first warm-up step is the probe."""
     from oracle import oracle as orc
     from sphinxsys_b200 import cases
+    threads = threads or host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(threads)  # before the OpenMP runtime starts (first oracle call)
+    t_setup = time.perf_counter()
     case = cases.dam_break(dim=3, dp=dp)
     sim = orc.OracleSim(case, f64=False, threads=threads)
     sim.exec("prepare_ck")
-    for _ in range(warmup):
+    t_setup = time.perf_counter() - t_setup
+    warm_done = 0
+    if fit_s is not None:
+        t0 = time.perf_counter()
         sim.exec("run_ck", 1e9, 1, 1e9, 100)
+        per_step = max(time.perf_counter() - t0, 1e-3)
+        warm_done = 1
+        fit = max(2, int((fit_s - t_setup - per_step) / per_step))
+        if max_outer + max(warmup - 1, 0) > fit:
+            warmup = 1 + min(max(warmup - 1, 0), fit // 5)
+            max_outer = max(1, fit - (warmup - 1))
+    for _ in range(max(warmup - warm_done, 0)):
+        sim.exec("run_ck", 1e9, 1, 1e9, 100)
+    warmup = max(warmup, warm_done)
     n_ac0 = int(sim.exec("acoustic_steps"))
     t0 = time.perf_counter()
     done = 0
@@ -114,42 +148,39 @@ def cpu_baseline_run(dp, max_outer, budget_s, threads=0, warmup=0):
     # also ns per pair interaction = wall time over (neighbour-list entries x 2 half steps x acoustic steps);
     # the per-advection work (summation, cell list, relation search) is inside the wall time, as in `value`
     pairs = int(sim.uint("inner_offset")[-1]) + int(sim.uint("contact_offset")[-1])
-    return {"value": case.n_fluid * n_ac / elapsed, "unit": "particle-steps/s", "cores": orc.lib().orc_max_threads(),
+    return {"value": case.n_fluid * n_ac / elapsed, "unit": "particle-steps/s", "cores": int(orc.lib().orc_max_threads()),
             "kind": "port", "ns_per_pair_interaction": 1e9 * elapsed / max(2.0 * pairs * n_ac, 1.0),
             "sample": f"3-D dam break dp={dp} ({case.n_fluid} fluid + {case.n_wall} wall), {done} outer / {n_ac} acoustic steps "
-                      f"in {elapsed:.1f} s after {warmup} untimed, oracle fp32 + OpenMP (restatement of the reference CK par_host "
-                      f"path, not the TBB build)",
-            "_elapsed": elapsed, "_steps": done, "_ms_per_step": 1e3 * elapsed / max(done, 1), "_n_fluid": case.n_fluid,
+                      f"in {elapsed:.1f} s after {warmup} untimed (set-up {t_setup:.1f} s), oracle fp32 + OpenMP (restatement of the "
+                      f"reference CK par_host path, not the TBB build)",
+            "_elapsed": elapsed, "_steps": done, "_warmup": warmup, "_ms_per_step": 1e3 * elapsed / max(done, 1), "_n_fluid": case.n_fluid,
             "_n_wall": case.n_wall, "_acoustic_per_outer": n_ac / max(done, 1)}
 
 
-REFERENCE_BUDGET_S = 150.0  # the whole --impl reference run (warm-up included) stays within a few minutes
+REFERENCE_BUDGET_S = 150.0  # the whole --impl reference run (set-up and warm-up included) stays within a few minutes
 
 
 def run_reference(args, rank, world):
     """Reference arm: the reference's CPU implementation of the path on the box's host cores. The reference itself
-    cannot be built in this image, so this is the oracle port with all host threads. W untimed warm-up
-    steps, then exactly K timed outer steps; each step is a bounded sample of config 2 (same case, coarser spacing),
-    the spacing chosen so that K + W steps fit REFERENCE_BUDGET_S."""
+    cannot be built in this image, so this is the oracle port with all host threads, on config 2 at ITS
+    OWN size (dp = 0.00625: 4,096,000 fluid + 3,034,688 wall) whatever N is — particle-steps/s of the CPU path does not
+    depend on how many GPUs the other arm uses. W untimed warm-up steps, then K timed advection steps; the sample is
+    bounded in the NUMBER of steps only (the first warm-up step sizes it so that the run fits REFERENCE_BUDGET_S)."""
     if rank != 0:
         return
     steps, warmup = max(args.steps, 1), max(args.warmup, 0)
-    # one probe step at the finest sample resolution sizes the run: cost per outer step scales with the particle count
     dp = args.ref_dp
-    probe = cpu_baseline_run(dp, 1, 1e9)
-    while probe["_elapsed"] * (steps + warmup) > REFERENCE_BUDGET_S and dp < 0.05:
-        probe["_elapsed"] /= 8.0
-        dp *= 2.0
-    r = cpu_baseline_run(dp, steps, 2.0 * REFERENCE_BUDGET_S, warmup=warmup)
+    r = cpu_baseline_run(dp, steps, 2.0 * REFERENCE_BUDGET_S, threads=host_threads(), warmup=warmup, fit_s=REFERENCE_BUDGET_S)
     line = {
         "metric": "particle-steps/sec (3D WCSPH dam break)", "value": r["value"], "unit": "particle-steps/s",
-        "n_gpus": args.gpus, "steps": r["_steps"], "warmup": warmup, "ms_per_step": r["_ms_per_step"],
+        "n_gpus": args.gpus, "steps": r["_steps"], "warmup": r["_warmup"], "ms_per_step": r["_ms_per_step"],
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "impl": "reference",
-        "config": {"workload": "3-D dam break WCSPH (tests_sycl dambreak geometry), AcousticRiemann + wall, Wendland C2 tabulated; "
-                               f"bounded sample of config 2 (dp=0.00625) at dp={dp}: {r['_n_fluid']} fluid + {r['_n_wall']} wall particles",
+        "config": {"workload": f"3-D dam break WCSPH (tests_sycl dambreak geometry), dp={dp:.6g}: {r['_n_fluid']} fluid + {r['_n_wall']} wall "
+                               "particles, AcousticRiemann + wall, Wendland C2 tabulated (config 2 at its own size at every N; the sample "
+                               f"is bounded in advection steps: {r['_steps']} timed of the {args.steps} asked for)",
                    "n_fluid_global": r["_n_fluid"], "n_wall": r["_n_wall"], "acoustic_steps_per_outer": r["_acoustic_per_outer"],
-                   "parallelism": f"{r['cores']} host threads (OpenMP), rank 0 only"},
+                   "parallelism": f"{r['cores']} host threads (OpenMP, from the affinity mask), rank 0 only"},
         "cpu_baseline": {k: v for k, v in r.items() if not k.startswith("_")},
         "e2e": {"value": r["value"], "unit": "particle-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -170,6 +201,59 @@ def time_kernel(fn, iters, torch):
     return s.elapsed_time(e) / iters  # ms
 
 
+def kernel_counters():
+    """ncu counters of the interaction kernels per fluid particle (profiles/kernel_counters.json, written from the committed
+    ncu --set full captures): DRAM bytes, warp instructions and L1 data-pipe wavefronts of one launch divided by the particles
+    it processed. They turn the launch time measured live into the second roofline (issue slots, L1 data pipe)."""
+    try:
+        return json.load(open(os.path.join(ROOT, "profiles", "kernel_counters.json")))
+    except Exception:
+        return {}
+
+
+def second_roofline(name, n_own, launch_ms, sm_mhz, counters):
+    """Fractions of the two SM-side ceilings that bound the pair-interaction kernels: warp instructions per
+    launch over the issue slots of the launch (148 SMs x 4 schedulers x cycles) and L1 data-pipe wavefronts per SM over its
+    cycles (one wavefront per cycle and SM). Counters per particle come from the committed ncu capture of this kernel;
+    the launch time and the SM clock are measured in this run."""
+    c = counters.get(name)
+    if not c or not sm_mhz or launch_ms <= 0:
+        return None
+    cycles = launch_ms * 1e-3 * sm_mhz * 1e6
+    inst = c["warp_instructions_per_particle"] * n_own
+    wave = c["l1_wavefronts_per_particle"] * n_own
+    return {"bound": "issue slots / L1 data pipe", "issue_frac": inst / (cycles * 148 * 4), "l1_data_pipe_frac": wave / (cycles * 148),
+            "warp_instructions_per_launch": inst, "l1_wavefronts_per_launch": wave, "sm_mhz": sm_mhz, "source": c.get("source")}
+
+
+def time_stream_kernels(solver, torch, n_own, peak, peak_kind, sm_mhz, counters):
+    """Per-kernel launch times on the CURRENT state (CUDA events on the launching stream) and the roofline records."""
+    dt = solver.last_acoustic_dt
+    ms_a2 = time_kernel(lambda: solver.exec("acoustic2", dt * 1e-3), 20, torch)
+    ms_a1 = time_kernel(lambda: solver.exec("acoustic1", dt * 1e-3), 20, torch)
+    ms_sum = time_kernel(lambda: solver.exec("density_summation"), 10, torch)
+    ms_cl = time_kernel(lambda: solver.exec("rebuild"), 10, torch)  # cell list + storage reorder (+ migration/ghosts if decomposed)
+    ms_rel = time_kernel(lambda: solver.exec("relations"), 5, torch)
+    solver.exec("acoustic_dt_unprime")
+    traffic = None
+    c2 = counters.get("k_a2")
+    if c2:
+        traffic = c2["dram_bytes_per_particle"] * n_own
+    ach_a2 = A_STEP_2ND * n_own / (ms_a2 * 1e-3) / 1e9  # per GPU
+    roofline = {"bound": "hbm", "kernel": "k_a2 (AcousticStep2ndHalf: initialize+inner+wall+update+dt-max, one launch)",
+                "achieved": ach_a2, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach_a2 / peak,
+                "traffic": traffic,
+                "traffic_source": (c2 or {}).get("source", None),
+                "algorithmic_bytes_per_launch": A_STEP_2ND * n_own, "launch_ms": ms_a2,
+                "second": second_roofline("k_a2", n_own, ms_a2, sm_mhz, counters),
+                "note": "stored-list gather design: ~85 neighbour rows per particle, one 32-byte per-lane gather and ~50 instructions each; "
+                        "bound by the L1 data pipe and the issue rate (`second`), not by HBM; see DESIGN.md §4",
+                "other_kernels_ms": {"acoustic_1st_half(init+interact)": ms_a1, "density_summation": ms_sum,
+                                     "cell_list_build+reorder": ms_cl, "relation_build(inner+contact)": ms_rel},
+                "other_kernels_second": {"k_a1_interact": second_roofline("k_a1_interact", n_own, ms_a1, sm_mhz, counters)}}
+    return roofline, (ms_a1, ms_a2)
+
+
 def run_ours(args, rank, world, local_rank):
     import ctypes as C
 
@@ -184,84 +268,138 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
-    # The C++ host layer builds the case itself (lattice generator + shape normals, include/sphinxsys_ck/dambreak_case.h)
-    # and runs the case-file loop; Python only times it. Weak scaling: the SAME dam break refined
-    # so that the fluid holds world x 4,096,000 particles (dp = 0.00625 / world^(1/3)), split into x-slabs of equal
-    # particle count, one per GPU, with NCCL halo exchange of contiguous cell-plane ranges.
-    dp = args.dp / (world ** (1.0 / 3.0)) if world > 1 else args.dp
-    uid = None
-    if world > 1:
-        from sphinxsys_b200.host import comm_unique_id
+    def new_unique_id():
+        if world == 1:
+            return None
         buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
         if rank == 0:
-            buf.copy_(torch.frombuffer(bytearray(comm_unique_id()), dtype=torch.uint8))
+            buf.copy_(torch.frombuffer(bytearray(host.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(buf, src=0)
-        uid = bytes(buf.cpu().numpy().tobytes())
-    solver = DamBreakCK(None, dim=3, dp=dp, device_index=local_rank, fused_time_step=True, sort_interval=100, generate=True,
-                        rank=rank, nranks=world, unique_id=uid, serial_exchange=args.serial_exchange)
-    solver.initialize()
-    n_own = solver.own_range()[1]
-    n_wall = solver.n_wall
-    if world > 1:
-        tn = torch.tensor([float(n_own)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tn, op=dist.ReduceOp.SUM)
-        n_fluid = int(tn.item())          # global fluid particles
-    else:
-        n_fluid = solver.n_fluid
+        return bytes(buf.cpu().numpy().tobytes())
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(*vals):
+        t = torch.tensor([float(v) for v in vals], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return [float(x) for x in t]
+
+    def sum_over_ranks(*vals):
+        t = torch.tensor([float(v) for v in vals], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return [float(x) for x in t]
+
+    def timed_outer(solver, k):
+        """K advection steps inside the C++ host loop, CUDA events on the launching stream, barrier + synchronize on both
+        sides, max over ranks. Returns (ms, acoustic steps, launches)."""
+        l0, a0 = solver.launches, solver.acoustic_steps
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        ev0.record()
+        solver.run_outer(k)
+        ev1.record()
+        barrier()
+        ms, = max_over_ranks(ev0.elapsed_time(ev1))
+        return ms, solver.acoustic_steps - a0, solver.launches - l0
+
+    # The C++ host layer builds the case itself (lattice generator + shape normals, include/sphinxsys_ck/dambreak_case.h)
+    # and runs the case-file loop; Python only times it. Weak scaling (SURVEY.md §8d C3): the SAME dam break refined
+    # so that the fluid holds world x 4,096,000 particles (dp = 0.00625 / world^(1/3)), split into x-slabs of equal
+    # particle count, one per GPU, with NCCL halo exchange of contiguous cell-plane ranges (DESIGN.md §6).
+    dp = args.dp / (world ** (1.0 / 3.0)) if world > 1 else args.dp
+    # the particle sort (decomposed: the re-cut of the slabs) runs every 100 advection steps in the case file; a timed window
+    # shorter than that gets exactly ONE inside it (cadence = K), i.e. the sort weighs 100/K times its natural share
+    cadence = min(100, max(args.steps, 2))
+    solver = DamBreakCK(None, dim=3, dp=dp, device_index=local_rank, fused_time_step=True, sort_interval=cadence, generate=True,
+                        rank=rank, nranks=world, unique_id=new_unique_id(), serial_exchange=args.serial_exchange, recut_interval=cadence)
+    solver.initialize()
+    n_wall = solver.n_wall
+    n_fluid = int(sum_over_ranks(solver.own_range()[1])[0]) if world > 1 else solver.n_fluid
+
     solver.run_outer(args.warmup)
     barrier()
+
+    # ---- parity evidence carried by the multi-GPU numbers: the state after the warm-up against ONE GPU ----
+    parity = None
+    if world > 1 and not args.no_parity:
+        cnt, dig = solver.state_digest()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, (cnt, dig))
+        energy = solver.energy()        # all-reduced inside the host layer
+        ac_dec = solver.acoustic_steps
+        one = None
+        if rank == 0:
+            try:
+                single = DamBreakCK(None, dim=3, dp=dp, device_index=local_rank, fused_time_step=True, sort_interval=cadence, generate=True)
+                single.initialize()
+                single.run_outer(args.warmup)
+                c1, d1 = single.state_digest()
+                one = {"particles": c1, "energy": single.energy(), "digest": f"{d1:016x}", "acoustic_steps": single.acoustic_steps}
+                single.close()
+                del single
+                torch.cuda.empty_cache()
+            except Exception as e:  # e.g. the global case does not fit one GPU
+                one = {"error": str(e)[:300]}
+        barrier()
+        if rank == 0:
+            tot = sum(c for c, _ in gathered)
+            dsum = sum(d for _, d in gathered) % (1 << 64)
+            parity = {"after_outer_steps": args.warmup, "decomposed": {"particles": tot, "energy": energy, "digest": f"{dsum:016x}",
+                                                                        "acoustic_steps": ac_dec, "own_per_rank": [c for c, _ in gathered]},
+                      "single_gpu": one,
+                      "bit_identical": bool(one and one.get("digest") == f"{dsum:016x}" and one.get("particles") == tot),
+                      "digest": "sum mod 2^64 over particles of mix64(global id, Position bits, Velocity bits): order- and partition-independent"}
+
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = solver.launches
-    ac0 = solver.acoustic_steps
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record()
-    solver.run_outer(args.steps)  # K outer steps inside the C++ host loop (library work runs on the default stream)
-    ev1.record()
-    barrier()
-    ms = ev0.elapsed_time(ev1)
+    ms, n_ac, launches = timed_outer(solver, args.steps)
     clocks = sampler.stop() if rank == 0 else None
-    n_ac = solver.acoustic_steps - ac0
-    launches = solver.launches - launches0
+    sorts_in_window = sum(1 for it in range(args.warmup + 1, args.warmup + args.steps + 1) if it % cadence == 0 and it != 1)
     n_own = solver.own_range()[1]  # own particles of this rank after the timed steps (migration, re-cuts)
-    t = torch.tensor([ms, float(n_ac)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # every rank takes the same sub-steps (global dt); time = slowest rank
-        ms = float(t[0])
     total_particle_steps = n_fluid * float(n_ac)  # n_fluid is the GLOBAL particle count
     value = total_particle_steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (2nd-half fused launch), timed live on the same state ----
     peak, peak_kind = measured_peak()
-    dt = solver.last_acoustic_dt
-    ms_a2 = time_kernel(lambda: solver.exec("acoustic2", dt * 1e-3), 20, torch)
-    ms_a1 = time_kernel(lambda: solver.exec("acoustic1", dt * 1e-3), 20, torch)
-    ms_sum = time_kernel(lambda: solver.exec("density_summation"), 10, torch)
-    ms_cl = time_kernel(lambda: solver.exec("rebuild"), 10, torch)  # cell list + storage reorder (+ migration/ghosts if decomposed)
-    ms_rel = time_kernel(lambda: solver.exec("relations"), 5, torch)
-    solver.exec("acoustic_dt_unprime")
-    traffic = None
-    try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        traffic = tj.get("k_a2", {}).get(str(n_fluid))
-    except Exception:
-        pass
-    ach_a2 = A_STEP_2ND * n_own / (ms_a2 * 1e-3) / 1e9  # per GPU
-    roofline = {"bound": "hbm", "kernel": "k_a2 (AcousticStep2ndHalf: initialize+inner+wall+update+dt-max, one launch)",
-                "achieved": ach_a2, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s", "frac": ach_a2 / peak,
-                "traffic": traffic, "algorithmic_bytes_per_launch": A_STEP_2ND * n_own, "launch_ms": ms_a2,
-                "note": "pair arithmetic (~85 neighbours x ~50 instr, one 32-byte gather each) runs at 84 % of the L1 data-pipe and 72 % of the "
-                        "issue peak (profiles/r01_v8_ncu_full.txt): bound by L1 bank wavefronts and FP32 issue, not by HBM; see DESIGN.md §4",
-                "other_kernels_ms": {"acoustic_1st_half(init+interact)": ms_a1, "density_summation": ms_sum,
-                                     "cell_list_build+reorder": ms_cl, "relation_build(inner+contact)": ms_rel}}
+    counters = kernel_counters()
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    roofline, (ms_a1, ms_a2) = time_stream_kernels(solver, torch, n_own, peak, peak_kind, sm_mhz, counters)
+    # one ParticleSortCK (keys + radix sort + renumbering) and the configuration update that follows it, timed alone
+    sort_ms = None
+    if world == 1:
+        sort_ms = time_kernel(lambda: solver.exec("sort"), 3, torch)
+        solver.exec("rebuild")
+        solver.exec("relations")
+
+    # ---- developed state (SURVEY §8d): the same K steps after the flow has left the initial lattice ----
+    developed = None
+    if not args.no_extras and args.developed_steps > 0:
+        solver.exec("set_sort_interval", 100)
+        solver.run_outer(args.developed_steps)
+        solver.exec("set_sort_interval", cadence)
+        sampler2 = ClockSampler(local_rank)
+        if rank == 0:
+            sampler2.start()
+        ms_d, n_ac_d, launches_d = timed_outer(solver, args.steps)
+        clocks_d = sampler2.stop() if rank == 0 else None
+        n_own_d = solver.own_range()[1]
+        roof_d, (ms_a1_d, ms_a2_d) = time_stream_kernels(solver, torch, n_own_d, peak, peak_kind, (clocks_d or {}).get("sm_mhz") or sm_mhz, counters)
+        pairs_in, pairs_ct = sum_over_ranks(solver.exec("inner_pairs"), solver.exec("contact_pairs"))
+        own_total, own_max = sum_over_ranks(n_own_d)[0], max_over_ranks(n_own_d)[0]
+        developed = {"after_outer_steps": args.warmup + args.steps + args.developed_steps, "physical_time": solver.physical_time,
+                     "value": n_fluid * float(n_ac_d) / (ms_d * 1e-3), "unit": "particle-steps/s", "ms_per_step": ms_d / max(args.steps, 1),
+                     "acoustic_steps_per_outer": n_ac_d / max(args.steps, 1), "gpu_launches": int(launches_d),
+                     "inner_neighbours_per_particle": pairs_in / max(own_total, 1.0),
+                     "wall_neighbours_per_particle": pairs_ct / max(own_total, 1.0),
+                     "load_imbalance_max_over_mean": own_max / max(own_total / world, 1.0),
+                     "k_a2_ms": ms_a2_d, "k_a1_ms": ms_a1_d, "roofline_frac_k_a2": roof_d["frac"], "second": roof_d["second"],
+                     "other_kernels_ms": roof_d["other_kernels_ms"], "clocks": clocks_d}
 
     # ---- e2e: the same step driven from HOST buffers (pinned), H2D of the evolving state + D2H of the result ----
     in_names = ["Position", "VolumetricMeasure", "Velocity", "Mass", "ForcePrior", "Compression", "CompressionRate",
@@ -292,10 +430,9 @@ def run_ours(args, rank, world, local_rank):
     per = lambda nm, vecw: (vecw if nm in host.VEC_NAMES else 1) * 4
     h2d = sum(per(nm, 4 if decomposed else 3) * (n_own if decomposed else n_fluid) for nm in in_names)
     d2h = sum(per(nm, 4 if decomposed else 3) * (n_own if decomposed else n_fluid) for nm in out_names)
+    h2d_own, d2h_own = h2d, d2h
     if decomposed:
-        th = torch.tensor([float(h2d), float(d2h)], dtype=torch.float64, device="cuda")
-        dist.all_reduce(th, op=dist.ReduceOp.SUM)
-        h2d, d2h = int(th[0]), int(th[1])
+        h2d, d2h = (int(v) for v in sum_over_ranks(h2d, d2h))
 
     def e2e_step():
         if decomposed:
@@ -320,68 +457,76 @@ def run_ours(args, rank, world, local_rank):
     # the state arrives from the host every step: build the cell list and the relations for it at the START of the step
     # (DamBreakCK::ConfigurationUpdate::BeforeDynamics) instead of at its end — the same launches per step as `value`
     solver.exec("configuration_before_dynamics", 1.0)
-    if decomposed:
-        e2e_step()
-        barrier()
-        t0 = time.perf_counter()
-        n_ac_e2e = 0
-        for _ in range(k_e2e):
-            n_ac_e2e += e2e_step()
-        barrier()
-        sec = time.perf_counter() - t0
-        e2e_note = ("per step: H2D of all evolving variables of the rank's own particles from pinned host memory, migration + "
-                    "cell-list + relation rebuild for the uploaded state, the dynamics of one outer step, D2H of Position/Velocity/Density")
-    else:
-        # single GPU: the same host buffers go through the HostTransferPipeline of the host layer — H2D of step s+1 and
-        # D2H of step s-1 run on a side stream while step s computes; every step's copies are inside the timed region
-        solver.pipeline_create(in_names, out_names)
-        ins = [host_in[nm][1] for nm in in_names]
-        outs = [host_out[nm][1] for nm in out_names]
+    solver.exec("set_sort_interval", 0)  # the state is re-uploaded every step: no renumbering / re-cut in between
+    # The host buffers go through the HostTransferPipeline of the host layer — H2D of step s+1 and D2H of step s-1 run on a
+    # side stream while step s computes; every step's copies are inside the timed region. Single GPU: reference particle
+    # order and packed layout; decomposed: this rank's own slots, raw (HostTransferPipeline::setRawOwnSlots).
+    solver.pipeline_create(in_names, out_names)
+    ins = [host_in[nm][1] for nm in in_names]
+    outs = [host_out[nm][1] for nm in out_names]
 
-        def run_pipelined(k):
-            n_ac = 0
-            solver.pipeline_stage_uploads(ins)
-            for s_ in range(k):
-                solver.pipeline_commit_uploads()
-                if s_ + 1 < k:
-                    solver.pipeline_stage_uploads(ins)   # next step's inputs: overlaps this step's dynamics
-                n_ac += solver.step_outer()              # configuration update first (state came from the host), then dynamics
-                solver.pipeline_stage_downloads(outs)    # overlaps the next step's dynamics
-            solver.pipeline_synchronize()
-            return n_ac
+    def run_pipelined(k):
+        n_ac = 0
+        solver.pipeline_stage_uploads(ins)
+        for s_ in range(k):
+            solver.pipeline_commit_uploads()
+            if s_ + 1 < k:
+                solver.pipeline_stage_uploads(ins)   # next step's inputs: overlaps this step's dynamics
+            n_ac += solver.step_outer()              # configuration update first (state came from the host), then dynamics
+            if decomposed:
+                assert solver.own_range()[1] == n_own, "own set changed during an e2e step"
+            solver.pipeline_stage_downloads(outs)    # overlaps the next step's dynamics
+        solver.pipeline_synchronize()
+        return n_ac
 
-        run_pipelined(2)
-        barrier()
-        t0 = time.perf_counter()
-        n_ac_e2e = run_pipelined(k_e2e)
-        barrier()
-        sec = time.perf_counter() - t0
-        pb_in, pb_out = solver.pipeline_bytes()
-        assert (pb_in, pb_out) == (h2d, d2h), (pb_in, h2d, pb_out, d2h)
-        # the synchronous spelling (DiscreteVariable::synchronizeToDevice / synchronizeWithDevice per variable) for comparison
-        e2e_step()
-        torch.cuda.synchronize()
-        t1 = time.perf_counter()
-        n_sync = sum(e2e_step() for _ in range(3))
-        torch.cuda.synchronize()
-        sec_sync = time.perf_counter() - t1
-        e2e_note = ("per step: H2D of all evolving variables from pinned host memory (reference particle order), cell-list + "
-                    "relation rebuild, one outer step, D2H of Position/Velocity/Density; copies run on a side stream and overlap "
-                    "the neighbouring steps' dynamics (HostTransferPipeline); synchronous per-variable spelling: "
-                    f"{n_fluid * float(n_sync) / sec_sync:.4g} particle-steps/s")
-    tt = torch.tensor([sec, float(n_ac_e2e)], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        sec = float(tt[0])
+    run_pipelined(2)
+    barrier()
+    t0 = time.perf_counter()
+    n_ac_e2e = run_pipelined(k_e2e)
+    barrier()
+    sec = time.perf_counter() - t0
+    pb_in, pb_out = solver.pipeline_bytes()
+    assert (pb_in, pb_out) == (h2d_own, d2h_own), (pb_in, h2d_own, pb_out, d2h_own)
+    # the synchronous spelling (one blocking copy per variable: DiscreteVariable::synchronizeToDevice / WithDevice) for comparison
+    e2e_step()
+    barrier()
+    t1 = time.perf_counter()
+    n_sync = sum(e2e_step() for _ in range(3))
+    barrier()
+    sec_sync, = max_over_ranks(time.perf_counter() - t1)
+    sec, = max_over_ranks(sec)
+    e2e_note = ("per step: H2D of all evolving variables from pinned host memory (" +
+                ("this rank's own particles in slot order" if decomposed else "reference particle order") +
+                "), cell-list + relation rebuild" + (" with migration and ghost-plane exchange" if decomposed else "") +
+                ", one outer step, D2H of Position/Velocity/Density; copies run on a side stream and overlap the neighbouring steps' "
+                "dynamics (HostTransferPipeline); synchronous per-variable spelling: "
+                f"{n_fluid * float(n_sync) / sec_sync:.4g} particle-steps/s")
     tot = n_fluid * float(n_ac_e2e)
     e2e = {"value": tot / sec, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "steps": k_e2e, "note": e2e_note}
 
-    # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample ----
+    solver.close()
+    del solver, host_in, host_out, ins, outs
+    torch.cuda.empty_cache()
+
+    # ---- CPU baseline (rank 0, N=1 only): the oracle on the host cores, bounded sample of the SAME case and spacing ----
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        r = cpu_baseline_run(args.ref_dp, 3, 25.0)
+        r = cpu_baseline_run(args.ref_dp, 2, 40.0, threads=host_threads(), warmup=1)
         cpu = {k: v for k, v in r.items() if not k.startswith("_")}
+
+    # ---- the other BASELINE configs, each a small driver-visible record (failures are reported, not fatal) ----
+    extras = {}
+    if not args.no_extras:
+        if world == 8 or args.force_config3:
+            extras["config3"] = guarded_leg(lambda: config3_leg(args, rank, world, local_rank, torch, dist, new_unique_id, timed_outer,
+                                                               sum_over_ranks, max_over_ranks), rank)
+            barrier()
+        extras["config4"] = guarded_leg(lambda: config4_leg(args, rank, world, local_rank, torch, dist, new_unique_id, barrier,
+                                                           max_over_ranks), rank)
+        barrier()
+        if world == 1:
+            extras["config5"] = guarded_leg(lambda: config5_leg(args), rank)
 
     if rank == 0:
         n_ac_per_outer = n_ac / max(args.steps, 1)
@@ -391,9 +536,11 @@ def run_ours(args, rank, world, local_rank):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": f"3-D dam break WCSPH (tests_sycl dambreak geometry), dp={dp:.6g}: {n_fluid} fluid + {n_wall} wall "
-                                   f"particles, AcousticRiemann + wall, Wendland C2 tabulated, sort every 100 outer steps",
+                                   f"particles, AcousticRiemann + wall, Wendland C2 tabulated; " +
+                                   (f"slab re-cut every {cadence}" if world > 1 else f"ParticleSortCK every {cadence}") +
+                                   f" advection steps ({sorts_in_window} inside the timed window; the case file's cadence is 100)",
                        "n_fluid_global": n_fluid, "n_fluid_per_gpu": n_fluid // world, "n_wall": n_wall,
-                       "acoustic_steps_per_outer": n_ac_per_outer,
+                       "acoustic_steps_per_outer": n_ac_per_outer, "sorts_in_timed_window": sorts_in_window, "sort_ms": sort_ms,
                        "l2_policy": "working set (~2 GB per GPU incl. neighbour lists) larger than L2, no flush",
                        "parallelism": "1 GPU" if world == 1 else
                        f"{world} x-slabs of equal particle count on the global mesh, NCCL halo exchange of contiguous cell-plane ranges, "
@@ -406,10 +553,119 @@ def run_ours(args, rank, world, local_rank):
             "kernel_only_particle_steps_per_s": n_fluid / ((ms_a1 + ms_a2) * 1e-3),
             "outer_steps_per_s": args.steps / (ms * 1e-3),
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "parity": parity, "developed": developed,
         }
+        line.update(extras)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def guarded_leg(fn, rank):
+    """A sub-record must never take the headline down: an exception becomes {"error": ...} (every rank runs the leg)."""
+    try:
+        return fn()
+    except Exception as e:  # noqa: BLE001
+        import traceback
+        if rank == 0:
+            traceback.print_exc(file=sys.stderr)
+        return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
+
+def config3_leg(args, rank, world, local_rank, torch, dist, new_unique_id, timed_outer, sum_over_ranks, max_over_ranks):
+    """BASELINE config 3 at its own size: the dam break at dp = 0.002 (125 M fluid + ~29 M wall) over the GPUs of the box,
+    ~16 M fluid particles per GPU."""
+    from sphinxsys_b200.host import DamBreakCK
+    dp3 = args.config3_dp
+    k, w = max(3, min(args.steps, 10)), 3
+    t0 = time.perf_counter()
+    s3 = DamBreakCK(None, dim=3, dp=dp3, device_index=local_rank, fused_time_step=True, sort_interval=100, generate=True,
+                    rank=rank, nranks=world, unique_id=new_unique_id(), recut_interval=100)
+    s3.initialize()
+    setup_s = time.perf_counter() - t0
+    n3, = sum_over_ranks(s3.own_range()[1])
+    stored_max, = max_over_ranks(s3.own_range()[2])
+    s3.run_outer(w)
+    ms3, n_ac3, l3 = timed_outer(s3, k)
+    cnt, dig = s3.state_digest()
+    tot, = sum_over_ranks(cnt)
+    e3 = s3.energy()
+    mem = torch.cuda.max_memory_allocated()  # torch's own share only; the library allocates with cudaMalloc
+    free_b, total_b = torch.cuda.mem_get_info()
+    rec = {"dp": dp3, "n_fluid_global": int(n3), "n_wall": s3.n_wall, "n_fluid_per_gpu": int(n3) // world, "stored_per_gpu_max": int(stored_max),
+           "steps": k, "warmup": w, "ms_per_step": ms3 / k, "acoustic_steps_per_outer": n_ac3 / k,
+           "value": n3 * n_ac3 / (ms3 * 1e-3), "unit": "particle-steps/s", "gpu_launches": int(l3), "setup_s": setup_s,
+           "particles_after": int(tot), "energy": e3, "hbm_used_gb_rank0": (total_b - free_b) / 1e9, "_torch_peak": mem}
+    rec.pop("_torch_peak")
+    s3.close()
+    del s3
+    torch.cuda.empty_cache()
+    return rec
+
+
+def config4_leg(args, rank, world, local_rank, torch, dist, new_unique_id, barrier, max_over_ranks):
+    """BASELINE config 4: periodic Taylor-Green vortex, n_side^3 particles PER GPU, the box replicated along x as a ring of
+    `world` slabs (x through the slab exchange + seam shift, y / z by image particles); one GPU: the ring of one slab."""
+    import dataclasses
+    from sphinxsys_b200 import cases, host
+    n_side = args.config4_side
+    k, w = max(3, min(args.steps, 6)), 2
+    t0 = time.perf_counter()
+    case = cases.taylor_green(dim=3, n_side=n_side, jitter=0.05)
+    n_local = case.n_fluid
+    local_ids = None
+    if world > 1:
+        pos = case.fluid_pos.copy()
+        pos[:, 0] += np.float32(rank)
+        up = list(case.periodic_upper)
+        up[0] = float(world)
+        case = dataclasses.replace(case, fluid_pos=pos, DL=float(world), LL=float(world), periodic_upper=tuple(up))
+        local_ids = np.arange(n_local, dtype=np.uint32) + np.uint32(rank * n_local)
+    gpu = host.TaylorGreenCK(case, device_index=local_rank, ring=True, rank=rank, nranks=world, unique_id=new_unique_id(),
+                             local_ids=local_ids, sort_interval=0)
+    gpu.initialize()
+    setup_s = time.perf_counter() - t0
+    gpu.run_outer(w)
+    gpu.synchronize()
+    l0 = gpu.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    n_ac = gpu.run_outer(k)
+    ev1.record()
+    barrier()
+    ms4, = max_over_ranks(ev0.elapsed_time(ev1))
+    dt4 = gpu.last_acoustic_dt
+    parts = {"acoustic_2nd_half": time_kernel(lambda: gpu.exec("acoustic2", dt4 * 1e-3), 5, torch),
+             "acoustic_1st_half": time_kernel(lambda: gpu.exec("acoustic1", dt4 * 1e-3), 5, torch),
+             "density_summation": time_kernel(lambda: gpu.exec("density_summation"), 3, torch),
+             "cell_list+migration+ghost_planes+images": time_kernel(lambda: gpu.exec("rebuild"), 3, torch),
+             "relation_build": time_kernel(lambda: gpu.exec("relations"), 3, torch),
+             "inner_stride": gpu.exec("inner_stride"), "inner_max_count": gpu.exec("inner_max_count")}
+    rec = {"n_side": n_side, "kernels_ms_rank0": parts, "particles_per_gpu": n_local, "n_fluid_global": n_local * world, "steps": k, "warmup": w,
+           "ms_per_step": ms4 / k, "acoustic_steps_per_outer": n_ac / k, "value": world * n_local * n_ac / (ms4 * 1e-3),
+           "unit": "particle-steps/s", "gpu_launches": gpu.launches - l0, "images_rank0": gpu.ghost_particles,
+           "plane_ghosts_rank0": int(gpu.exec("plane_ghost_particles")), "kinetic_energy": gpu.energy(), "setup_s": setup_s,
+           "parallelism": f"ring of {world} slab(s) along x, NCCL" if world > 1 else "ring of one slab (device copies)"}
+    gpu.close()
+    del gpu
+    torch.cuda.empty_cache()
+    return rec
+
+
+def config5_leg(args):
+    """BASELINE config 5: neighbour-search chain (keys, radix sort, permutation, cell list + reorder, neighbour count) on
+    random particles, through scripts/config5_bench.py in a child process (its own context; bounded by a timeout)."""
+    out = os.path.join(ROOT, "gpurun_out", "config5_bench_leg.json")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "config5_bench.py"), "--sizes", args.config5_sizes, "--reps", "2",
+                        "--out", out], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=240)
+    if p.returncode != 0 and not os.path.exists(out):
+        return {"error": (p.stderr or p.stdout)[-300:]}
+    d = json.load(open(out))
+    rows = [{"particles": r["particles"], "ms_total": r["ms_total"], "particles_per_s": r["particles_per_s"], "ms": r["ms"],
+             "hbm_frac_algorithmic": r["hbm_frac_algorithmic"], "properties_ok": r["properties_ok"]} for r in d["rows"]]
+    return {"algorithmic_bytes_per_particle": d["algorithmic_bytes_per_particle"], "rows": rows}
 
 
 def main():
@@ -418,10 +674,17 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--dp", type=float, default=0.00625, help="particle spacing; 0.00625 = config 2 (4,096,000 fluid)")
-    ap.add_argument("--ref-dp", type=float, default=0.0125, help="resolution of the bounded CPU sample (512,000 fluid)")
+    ap.add_argument("--ref-dp", type=float, default=0.00625, help="spacing of the CPU arm: config 2 at its own size (4,096,000 fluid)")
+    ap.add_argument("--developed-steps", type=int, default=1200, help="advection steps run (untimed) before the developed-state leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the developed / config3 / config4 / config5 sub-records")
+    ap.add_argument("--config4-side", type=int, default=256, help="particles per side and GPU of the config-4 ring leg")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--serial-exchange", action="store_true", help="N > 1: plane exchange in line with the dynamics (no overlap)")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the 1-GPU comparison run of the parity sub-record")
+    ap.add_argument("--config3-dp", type=float, default=0.002, help="spacing of the config-3 leg (0.002: 125 M fluid particles)")
+    ap.add_argument("--force-config3", action="store_true", help="run the config-3 leg at any N (default: N = 8 only)")
+    ap.add_argument("--config5-sizes", default="16,256", help="config-5 leg: millions (2^20) of random particles")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

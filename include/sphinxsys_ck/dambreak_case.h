@@ -20,6 +20,9 @@ struct DamBreakParameters
     double DL = 5.366, DH = 2.0, DW = 0.5, LL = 2.0, LH = 1.0, LW = 0.5; // dambreak.cpp:13-18
     double rho0_f = 1.0, gravity_g = 1.0;                                // :22-23
     bool correction = false;   // LinearCorrectionCK variants (the reference case file uses them; the hot path is without)
+    int riemann = 1;           // 0 NoRiemannSolverCK, 1 AcousticRiemannSolverCK (the case file), 2 DissipativeRiemannSolverCK
+                               // (riemann_solver_ck.h:46-173; aliases acoustic_step_1st_half.h:196-201)
+    int kernel_kind = 0;       // 0 KernelWendlandC2 (default), 1 resetKernel<KernelTabulated<KernelLaguerreGauss>>(20), adaptation.h:96-100
     bool surface_indicator = false; // FreeSurfaceIndicationComplexSpatialTemporalCK in the loop (dambreak.cpp:133-134,192)
     bool observers = false;         // FluidObserver pressure probes of the case file (dambreak.cpp:54-65,87-88,140-141,223-224)
     double mu_f = 0.0;              // > 0: Viscosity closure + ViscousForceWithWallCK after the advection set-up
@@ -65,6 +68,8 @@ class WallBoundary : public ComplexShape
         subtract<GeometricShapeBox>(half_in, half_in);
     }
 };
+
+template <class T> struct TypeTag { using type = T; };
 
 class DamBreakCK
 {
@@ -141,6 +146,13 @@ class DamBreakCK
           wall_boundary(sph_system, makeShared<WallBoundary>("WallBoundary", q)),
           gravity(Vecd(0, Real(-q.gravity_g), 0))
     {
+        if (q.kernel_kind == 1)
+        {
+            if (q.legacy) throw SphError("legacy formulation: only the Wendland C2 kernel");
+            water_block.getSPHAdaptation().resetKernel<KernelLaguerreGauss>();
+            wall_boundary.getSPHAdaptation().resetKernel<KernelLaguerreGauss>();
+        }
+        else if (q.kernel_kind != 0) throw SphError("kernel_kind: 0 (Wendland C2) or 1 (Laguerre-Gauss)");
         {
             // system bounds = case bounds + 4 dp (sph_system.cpp:39), evaluated in double from the case file's double
             // literals and rounded once to Real
@@ -237,6 +249,7 @@ class DamBreakCK
             fluid_acoustic_time_step = ac;
             if (q.correction)
             {
+                if (q.riemann != 1) throw SphError("correction variants: the reference has aliases for the acoustic Riemann solver only");
                 fluid_linear_correction_matrix.reset(new InteractionDynamicsCK<P, LinearCorrectionMatrixComplex>(
                     DynamicsArgs(*water_block_inner, 0.5), *water_wall_contact));
                 fluid_acoustic_step_1st_half.reset(new InteractionDynamicsCK<P, AcousticStep1stHalfWithWallRiemannCorrectionCK>(*water_block_inner, *water_wall_contact));
@@ -246,10 +259,19 @@ class DamBreakCK
             }
             else
             {
-                fluid_acoustic_step_1st_half.reset(new InteractionDynamicsCK<P, AcousticStep1stHalfWithWallRiemannCK>(*water_block_inner, *water_wall_contact));
-                auto *a2 = new InteractionDynamicsCK<P, AcousticStep2ndHalfWithWallRiemannCK>(*water_block_inner, *water_wall_contact);
-                fluid_acoustic_step_2nd_half.reset(a2);
-                if (q.fused_time_step) a2->fuseTimeStepReduction(*ac);
+                // the closed set of Riemann variants of SURVEY §8 a14 (aliases acoustic_step_1st_half.h:196-201, 2nd_half.h)
+                auto make = [&](auto first, auto second) {
+                    using First = typename decltype(first)::type;
+                    using Second = typename decltype(second)::type;
+                    fluid_acoustic_step_1st_half.reset(new InteractionDynamicsCK<P, First>(*water_block_inner, *water_wall_contact));
+                    auto *a2 = new InteractionDynamicsCK<P, Second>(*water_block_inner, *water_wall_contact);
+                    fluid_acoustic_step_2nd_half.reset(a2);
+                    if (q.fused_time_step) a2->fuseTimeStepReduction(*ac);
+                };
+                if (q.riemann == 1) make(TypeTag<AcousticStep1stHalfWithWallRiemannCK>{}, TypeTag<AcousticStep2ndHalfWithWallRiemannCK>{});
+                else if (q.riemann == 0) make(TypeTag<AcousticStep1stHalfWithWallNoRiemannCK>{}, TypeTag<AcousticStep2ndHalfWithWallNoRiemannCK>{});
+                else if (q.riemann == 2) make(TypeTag<AcousticStep1stHalfWithWallDissipativeRiemannCK>{}, TypeTag<AcousticStep2ndHalfWithWallDissipativeRiemannCK>{});
+                else throw SphError("riemann: 0 (NoRiemann), 1 (Acoustic) or 2 (Dissipative)");
             }
             auto *sum = new InteractionDynamicsCK<P, CompressionSummation<Inner<>, Contact<>>>(*water_block_inner, *water_wall_contact);
             fluid_density_summation.reset(sum);

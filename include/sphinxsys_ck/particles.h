@@ -395,6 +395,10 @@ class HostTransferPipeline
     };
     BaseParticles &p_;
     std::vector<std::unique_ptr<Item>> ins_, outs_;
+    // slab-decomposed bodies: the host holds THIS RANK's own particles in storage (slot) order and in the device element
+    // layout (Vecd = 4 floats) — what SlabDecomposition hands out with the ReferenceID array; the copies go straight
+    // between the pinned buffers and the own slot range [activeBegin, activeEnd), no reordering passes
+    bool raw_own_slots_ = false;
     void *copy_stream_ = nullptr, *ev_h2d_ = nullptr, *ev_commit_ = nullptr, *ev_out_ready_ = nullptr, *ev_d2h_ = nullptr;
 
     template <class T> static Item *makeItem(DiscreteVariable<T> *v)
@@ -425,28 +429,33 @@ class HostTransferPipeline
     template <class T> void addOutput(DiscreteVariable<T> *v) { outs_.emplace_back(makeItem(v)); }
     size_t inputs() const { return ins_.size(); }
     size_t outputs() const { return outs_.size(); }
+    void setRawOwnSlots(bool on) { raw_own_slots_ = on; }
+    bool rawOwnSlots() const { return raw_own_slots_; }
+    size_t count() const { return raw_own_slots_ ? p_.activeEnd() - p_.activeBegin() : p_.hostSyncCount(); }
+    size_t hostElementBytes(const Item &it) const { return raw_own_slots_ ? it.v->deviceElementBytes() : it.host_elem_bytes; }
     size_t inputBytes() const
     {
         size_t b = 0;
-        for (auto &it : ins_) b += it->host_elem_bytes * p_.hostSyncCount();
+        for (auto &it : ins_) b += hostElementBytes(*it) * count();
         return b;
     }
     size_t outputBytes() const
     {
         size_t b = 0;
-        for (auto &it : outs_) b += it->host_elem_bytes * p_.hostSyncCount();
+        for (auto &it : outs_) b += hostElementBytes(*it) * count();
         return b;
     }
     void stageUploads(const void *const *pinned_host)
     {
         ExecutionInstance &ex = execution_instance();
-        const size_t n = p_.hostSyncCount();
+        const size_t n = count();
         ex.check(sphb200_stream_wait_event(copy_stream_, ev_commit_), "sphb200_stream_wait_event");
         for (size_t k = 0; k < ins_.size(); ++k)
         {
             Item &it = *ins_[k];
-            it.raw.ensure(it.host_elem_bytes * n + 64);
-            ex.check(sphb200_copy_h2d(it.raw.get(), pinned_host[k], it.host_elem_bytes * n, copy_stream_), "sphb200_copy_h2d");
+            const size_t eb = hostElementBytes(it);
+            it.raw.ensure(eb * n + 64);
+            ex.check(sphb200_copy_h2d(it.raw.get(), pinned_host[k], eb * n, copy_stream_), "sphb200_copy_h2d");
         }
         ex.check(sphb200_event_record(ev_h2d_, copy_stream_), "sphb200_event_record");
     }
@@ -454,8 +463,19 @@ class HostTransferPipeline
     {
         ExecutionInstance &ex = execution_instance();
         void *st = ex.stream();
-        const uint32_t n = (uint32_t)p_.hostSyncCount();
+        const uint32_t n = (uint32_t)count();
         ex.check(sphb200_stream_wait_event(st, ev_h2d_), "sphb200_stream_wait_event");
+        if (raw_own_slots_)
+        {
+            // the staging already is slot order + device layout: one device copy per variable into the own slot range
+            for (auto &ip : ins_)
+            {
+                const size_t eb = ip->v->deviceElementBytes();
+                ex.check(sphb200_copy_d2d((char *)ip->v->deviceAddress() + p_.activeBegin() * eb, ip->raw.get(), eb * n, st), "sphb200_copy_d2d");
+            }
+            ex.check(sphb200_event_record(ev_commit_, st), "sphb200_event_record");
+            return;
+        }
         std::vector<void *> dst;
         std::vector<const void *> src;
         std::vector<uint32_t> bytes;
@@ -483,8 +503,23 @@ class HostTransferPipeline
     {
         ExecutionInstance &ex = execution_instance();
         void *st = ex.stream();
-        const uint32_t n = (uint32_t)p_.hostSyncCount();
+        const uint32_t n = (uint32_t)count();
         ex.check(sphb200_stream_wait_event(st, ev_d2h_), "sphb200_stream_wait_event"); // the previous D2H has left the staging
+        if (raw_own_slots_)
+        {
+            for (auto &op : outs_)
+            {
+                const size_t eb = op->v->deviceElementBytes();
+                op->raw.ensure(eb * n + 64);
+                ex.check(sphb200_copy_d2d(op->raw.get(), (const char *)op->v->deviceAddress() + p_.activeBegin() * eb, eb * n, st), "sphb200_copy_d2d");
+            }
+            ex.check(sphb200_event_record(ev_out_ready_, st), "sphb200_event_record");
+            ex.check(sphb200_stream_wait_event(copy_stream_, ev_out_ready_), "sphb200_stream_wait_event");
+            for (size_t k = 0; k < outs_.size(); ++k)
+                ex.check(sphb200_copy_d2h(pinned_host[k], outs_[k]->raw.get(), outs_[k]->v->deviceElementBytes() * n, copy_stream_), "sphb200_copy_d2h");
+            ex.check(sphb200_event_record(ev_d2h_, copy_stream_), "sphb200_event_record");
+            return;
+        }
         std::vector<void *> dst;
         std::vector<const void *> src;
         std::vector<uint32_t> bytes;

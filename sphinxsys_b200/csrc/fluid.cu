@@ -53,8 +53,9 @@ struct FArgs
     float inv_h, inv_dq, q_scale, W0;
     // closed form of the tabulated Wendland C2 interpolant (see wendland_*): scales and error-term coefficients
     int analytic;
-    float wl_w_scale, wl_w_c4, wl_w_c5, wl_four_dq, wl_dw_a, wl_dw_c;
+    float wl_w_scale, wl_w_c4, wl_w_c5, wl_four_dq, wl_dw_a, wl_dw_ah, wl_dw_c; // wl_dw_ah = wl_dw_a / h
     float rho0, c0, p0, Z, inv_Z_sum, inv_Z_ave, Z_geo, inv_c_ave, limiter;
+    float lim_k; // limiter * inv_c_ave: TruncatedLinear(InvSoundSpeedAve * max(u, 0)) in one multiply
     int free_surface, dim;
     int legacy;               // 1: state is Density/DensityChangeRate (in rho / Cdot), analytic kernel
     float lg_sum_scale;       // legacy DensitySummation: rho0 / sigma0
@@ -153,6 +154,7 @@ static int make_fargs(sphb200_context *ctx, const sphb200_fluid_args_t *s, FArgs
         a->wl_w_c5 = (float)(0.125 * dq4 * w_scale);
         a->wl_four_dq = (float)(4.0 * dq);
         a->wl_dw_a = (float)(0.625 * dw_scale);
+        a->wl_dw_ah = (float)(0.625 * dw_scale * ih);
         a->wl_dw_c = (float)(0.625 * dq4 * dw_scale);
     }
     a->inv_h = inv_h;
@@ -176,6 +178,7 @@ static int make_fargs(sphb200_context *ctx, const sphb200_fluid_args_t *s, FArgs
     a->Z_geo = 2.0f * a->Z * a->Z * a->inv_Z_sum;
     a->inv_c_ave = 0.5f * (m.rho0 + m.rho0) * a->inv_Z_ave;
     a->limiter = m.limiter_coeff;
+    a->lim_k = m.limiter_coeff * a->inv_c_ave;
     a->free_surface = m.free_surface;
     a->dim = k.dim;
     return 0;
@@ -212,14 +215,13 @@ __device__ __forceinline__ float eval_tab(const float4 *tab, float r, float q_sc
 __device__ __forceinline__ float wendland_dw(const FArgs &a, float r)
 {
     const float MAGIC = 12582912.0f;
-    float q = r * a.inv_h;
     float u = fmaf(r, a.q_scale, -0.5f);
     float m = u + MAGIC;
     float s = u - (m - MAGIC);
     float s2 = s * s;
-    float pi = (s2 - 2.25f) * (s2 - 0.25f);
-    float g = q - 2.0f;
-    float poly = (g * g) * (g * (q * a.wl_dw_a));
+    float pi = fmaf(s2, s2 - 2.5f, 0.5625f); // (s2 - 9/4)(s2 - 1/4)
+    float g = fmaf(r, a.inv_h, -2.0f);       // q - 2
+    float poly = (g * g) * (g * (r * a.wl_dw_ah)); // 0.625 scale q (q - 2)^3
     return fmaf(-a.wl_dw_c, pi, poly);
 }
 __device__ __forceinline__ float wendland_w(const FArgs &a, float r)
@@ -323,12 +325,13 @@ __device__ __forceinline__ void for_neighbors(const u32 *__restrict__ idx, u32 c
 constexpr int SUM_U = SPH_SUM_U; // the summation kernel is light on registers (32): deeper batches are affordable there
 constexpr int NB_WALL_U = 2; // wall pairs need up to three records each: smaller batches keep the kernels spill-free
 
-// RiemannSolver<...>::ComputingKernel::DissipativePJump, riemann_solver_ck.hpp:44-49
-template <int RIEMANN> __device__ __forceinline__ float pjump(const FArgs &a, float u)
+// RiemannSolver<...>::ComputingKernel::DissipativePJump, riemann_solver_ck.hpp:44-49, WITHOUT its constant factor
+// ImpedanceGeoAve (Z_geo): the callers multiply the accumulated sums by it once per particle
+template <int RIEMANN> __device__ __forceinline__ float pjump_over_z(const FArgs &a, float u)
 {
     if (RIEMANN == 0) return 0.f;
-    float lim = RIEMANN == 1 ? fminf(a.limiter * (a.inv_c_ave * fmaxf(u, 0.f)), 1.f) : 1.f;
-    return a.Z_geo * u * lim;
+    if (RIEMANN == 2) return u;
+    return u * fminf(a.lim_k * fmaxf(u, 0.f), 1.f);
 }
 
 // =====================================================================================================
@@ -779,7 +782,7 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
                     float c = (p_i + p_j) * dWV * inv_r;
                     fx -= c * dx; fy -= c * dy; fz -= c * dz;
                 }
-                if (RIEMANN) diss += (p_i - p_j) * a.inv_Z_ave * dWV; // DissipativeUJump, :51-56
+                if (RIEMANN) diss += (p_i - p_j) * dWV; // DissipativeUJump, :51-56 (its constant InvImpedanceAve: once per particle below)
             });
     }
     float wx = 0.f, wy = 0.f, wz = 0.f, wdiss = 0.f;
@@ -829,7 +832,7 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
                 {
                     wx -= c * ex; wy -= c * ey; wz -= c * ez;
                 }
-                if (RIEMANN) wdiss += (p_i - p_w) * a.inv_Z_ave * dWV;
+                if (RIEMANN) wdiss += (p_i - p_w) * dWV;
                 });
         }
     }
@@ -838,8 +841,8 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
     F.x += wx * vol_i; F.y += wy * vol_i; F.z += wz * vol_i;
     a.force[i] = F;
     const float C_i = a.legacy ? a.rho[i] : a.C[i];
-    float cd = diss * C_i;
-    cd += wdiss * C_i;
+    float cd = (diss * a.inv_Z_ave) * C_i;
+    cd += (wdiss * a.inv_Z_ave) * C_i;
     a.Cdot[i] = cd;
     if (do_update)
     {
@@ -954,21 +957,22 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a2(FArgs a, KTab 
                 dist(r2, r, inv_r);
                 float dWV = kernel_dw<ANALYTIC>(a, tab, r) * xj.w;
                 dWV = valid ? dWV : 0.f;
-                float ex = dx * inv_r, ey = dy * inv_r, ez = dz * inv_r;
                 // AverageV (riemann_solver_ck.hpp:26-31) with Z_i == Z_j: 2 (v_i - v_ave) = v_i - v_j
                 float ux = vi.x - vj.x, uy = vi.y - vj.y, uz = vi.z - vj.z;
-                float u = ux * ex + uy * ey + uz * ez;
+                // u = (v_i - v_j) . e_ij with e_ij = d / |d| folded into the scalars (one multiply instead of three)
+                float u = (ux * dx + uy * dy + uz * dz) * inv_r;
                 if (CORR)
                 {
-                    float3 ce = mat_vec(Bi, make_float3(ex, ey, ez));
+                    float3 ce = mat_vec(Bi, make_float3(dx * inv_r, dy * inv_r, dz * inv_r));
                     div += (ux * ce.x + uy * ce.y + uz * ce.z) * dWV;
                 }
                 else
                     div += u * dWV;
-                float c = pjump<RIEMANN>(a, u) * dWV;
-                px += c * ex; py += c * ey; pz += c * ez;
+                float c = pjump_over_z<RIEMANN>(a, u) * (dWV * inv_r);
+                px += c * dx; py += c * dy; pz += c * dz;
                 });
         }
+        px *= a.Z_geo; py *= a.Z_geo; pz *= a.Z_geo;
         float wdiv = 0.f, wx = 0.f, wy = 0.f, wz = 0.f;
         if (a.n_wall)
         {
@@ -1005,9 +1009,10 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a2(FArgs a, KTab 
                 float sg = en < 0.f ? -1.f : (en > 0.f ? 1.f : 0.f); // SGN, scalar_functions.h:128-131
                 float nx = sg * nj.x, ny = sg * nj.y, nz = sg * nj.z;
                 float u = vx * nx + vy * ny + vz * nz;
-                float c = pjump<RIEMANN>(a, u) * dWV;
+                float c = pjump_over_z<RIEMANN>(a, u) * dWV;
                 wx += c * nx; wy += c * ny; wz += c * nz;
                 });
+            wx *= a.Z_geo; wy *= a.Z_geo; wz *= a.Z_geo;
         }
         const float vol_i = xi.w;
         float C = a.legacy ? a.rho[i] : a.C[i];

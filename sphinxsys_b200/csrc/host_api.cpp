@@ -94,6 +94,8 @@ extern "C"
         int32_t serial_exchange;         // decomposed runs: 1 = plane exchange in line with the dynamics (no overlap)
         int32_t recut_interval;          // decomposed runs: re-balance the cuts every so many advection steps (< 0: default 100)
         int32_t initial_cut_shift;       // decomposed runs: unbalanced start, interior cuts moved by so many planes (test hook)
+        int32_t riemann;                 // 0 NoRiemannSolverCK, 1 AcousticRiemannSolverCK, 2 DissipativeRiemannSolverCK
+        int32_t kernel_kind;             // 0 Wendland C2, 1 Laguerre-Gauss (tabulated, resetKernel)
     };
 
     const char *sphck_last_error() { return g_error.c_str(); }
@@ -187,6 +189,8 @@ extern "C"
             q.dim = o->dim; q.dp = o->dp;
             q.DL = o->DL; q.DH = o->DH; q.DW = o->DW; q.LL = o->LL; q.LH = o->LH; q.LW = o->LW;
             q.correction = o->correction != 0;
+            q.riemann = o->riemann;
+            q.kernel_kind = o->kernel_kind;
             q.fused_time_step = o->fused_time_step != 0;
             q.fused_regularization = o->fused_regularization != 0;
             q.sort_interval = o->sort_interval;
@@ -201,7 +205,11 @@ extern "C"
             q.initial_cut_shift = o->initial_cut_shift;
             q.nranks = o->nranks > 0 ? o->nranks : 1;
             if (q.nranks > 1)
+            {
+                // one communicator per context: a decomposed case made earlier in this process leaves its own behind
+                if (sphb200_comm_size(execution_instance().ctx()) > 1) sphb200_comm_destroy(execution_instance().ctx());
                 execution_instance().check(sphb200_comm_create(execution_instance().ctx(), q.nranks, q.rank, o->unique_id), "sphb200_comm_create");
+            }
             std::vector<Vecd> fp, wp, wn;
             BoundingBoxd sb;
             if (o->use_system_bounds)
@@ -279,6 +287,8 @@ extern "C"
             sphb200_context_t *ctx = execution_instance().ctx();
             if (g_ring_handles == 0)
             {
+                // a communicator left behind by an earlier decomposed case of this process is not a ring: start afresh
+                if (sphb200_comm_size(ctx) > 1) sphb200_comm_destroy(ctx);
                 if (nranks > 1) execution_instance().check(sphb200_comm_create(ctx, nranks, rank, unique_id), "sphb200_comm_create");
                 else execution_instance().check(sphb200_comm_create_self(ctx), "sphb200_comm_create_self");
                 execution_instance().check(sphb200_comm_set_ring(ctx, 1), "sphb200_comm_set_ring");
@@ -352,6 +362,13 @@ extern "C"
                     r = (double)total;
                 }
                 else if (op == "cell_list_fluid") s.water_cell_linked_list->exec();
+                else if (op == "rebuild")
+                {
+                    // the configuration update without the relation search: cell list (ring: migration + ghost planes) + images
+                    if (s.decomposition) s.decomposition->rebuild();
+                    else s.water_cell_linked_list->exec();
+                    for (auto &pc : s.periodic_condition) pc->ghost_creation_.exec();
+                }
                 else if (op == "periodic_bounding") { for (auto &pc : s.periodic_condition) pc->bounding_.exec(); }
                 else if (op == "ghost_creation") { for (auto &pc : s.periodic_condition) pc->ghost_creation_.exec(); }
                 else if (op == "ghost_update") s.periodic_condition[0]->ghost_update_.exec();
@@ -400,6 +417,7 @@ extern "C"
                 for (long k = 0; k < n; ++k) total += s.stepOuter();
                 r = (double)total;
             }
+            else if (op == "set_sort_interval") { s.q_.sort_interval = (int)a0; s.q_.recut_interval = (int)a0; } // ParticleSortCK / re-cut cadence
             else if (op == "configuration_before_dynamics")
                 s.configuration_update = a0 != 0.0 ? DamBreakCK::ConfigurationUpdate::BeforeDynamics : DamBreakCK::ConfigurationUpdate::AfterDynamics;
             else if (op == "gravity") s.constant_gravity->exec();
@@ -448,6 +466,20 @@ extern "C"
             else if (op == "recuts") r = s.decomposition ? (double)s.decomposition->recuts() : 0.0;
             else if (op == "rebuild") { if (s.decomposition) s.decomposition->rebuild(); else s.water_cell_linked_list->exec(); }
             else if (op == "inner_total") r = (double)s.water_block_inner->total_;
+            else if (op == "inner_pairs" || op == "contact_pairs")
+            {
+                // neighbour-list entries of the own particles (sum of the row counts), read back once
+                RelationBase &rel = op == "inner_pairs" ? (RelationBase &)*s.water_block_inner : (RelationBase &)*s.water_wall_contact;
+                BaseParticles &p = s.water_block.getBaseParticles();
+                const size_t b = p.activeBegin(), e = p.activeEnd();
+                std::vector<uint32_t> c(e - b);
+                ExecutionInstance &ex = execution_instance();
+                if (e > b) ex.check(sphb200_copy_d2h(c.data(), rel.count_.get<uint32_t>() + b, (e - b) * sizeof(uint32_t), ex.stream()), "sphb200_copy_d2h");
+                ex.synchronize();
+                uint64_t tot = 0;
+                for (uint32_t v : c) tot += v;
+                r = (double)tot;
+            }
             else if (op == "inner_stride") r = (double)s.water_block_inner->fixed_stride_;
             else if (op == "inner_max_count") r = (double)s.water_block_inner->max_count_;
             else if (op == "set_relation_stride")
@@ -523,6 +555,8 @@ extern "C"
             Handle *h = (Handle *)hp;
             BaseParticles &p = h->body(0).getBaseParticles();
             h->pipeline.reset(new HostTransferPipeline(p));
+            // decomposed bodies exchange this rank's own slots raw (storage order, device layout)
+            h->pipeline->setRawOwnSlots(h->sim && h->sim->decomposition);
             auto add = [&](const char *list, bool input) {
                 std::string s(list ? list : ""), name;
                 size_t pos = 0;

@@ -31,7 +31,8 @@ class Options(C.Structure):
                 ("device", C.c_int32), ("relation_stride", C.c_int32), ("system_lower", C.c_double * 3),
                 ("system_upper", C.c_double * 3), ("use_system_bounds", C.c_int32), ("legacy", C.c_int32), ("rank", C.c_int32),
                 ("nranks", C.c_int32), ("unique_id", C.c_uint8 * 128), ("surface_indicator", C.c_int32), ("observers", C.c_int32),
-                ("mu_f", C.c_double), ("transport_velocity", C.c_int32), ("serial_exchange", C.c_int32), ("recut_interval", C.c_int32), ("initial_cut_shift", C.c_int32)]
+                ("mu_f", C.c_double), ("transport_velocity", C.c_int32), ("serial_exchange", C.c_int32), ("recut_interval", C.c_int32), ("initial_cut_shift", C.c_int32),
+                ("riemann", C.c_int32), ("kernel_kind", C.c_int32)]
 
 
 class TaylorGreenOptions(C.Structure):
@@ -132,6 +133,20 @@ def limit_cut_moves(old_cuts, wanted):
     return out
 
 
+def particle_digest(ids, pos, vel):
+    """64-bit digest of a particle set that does not depend on storage order or on how the set is split over ranks:
+    the sum (mod 2^64) over the particles of a mix of the particle's global number with the bit patterns of its position and
+    velocity. Equal digests of two runs <=> (up to hash collisions) every particle has bit-identical position and velocity."""
+    h = np.ascontiguousarray(ids, dtype=np.uint32).astype(np.uint64) * np.uint64(0x9E3779B97F4A7C15)
+    for a in (pos, vel):
+        bits = np.ascontiguousarray(a[:, :3], dtype=np.float32).view(np.uint32)
+        for c in range(3):
+            h ^= bits[:, c].astype(np.uint64)
+            h *= np.uint64(0xBF58476D1CE4E5B9)
+            h ^= h >> np.uint64(29)
+    return int(np.add.reduce(h, dtype=np.uint64)) if h.size else 0
+
+
 def _kind(name):
     return 1 if name in VEC_NAMES else (2 if name in UINT_NAMES else (3 if name in MAT_NAMES else (4 if name in INT_NAMES else 0)))
 
@@ -142,9 +157,13 @@ class DamBreakCK:
     def __init__(self, case=None, device_index=0, correction=False, fused_time_step=True, sort_interval=100,
                  relation_stride=None, fused_regularization=True, dim=3, dp=0.05, generate=False, rank=0, nranks=1,
                  unique_id=None, width_scale=1.0, legacy=False, surface_indicator=False, observers=False, mu_f=0.0,
-                 transport_velocity=False, serial_exchange=False, recut_interval=None, initial_cut_shift=0):
+                 transport_velocity=False, serial_exchange=False, recut_interval=None, initial_cut_shift=0, riemann=1,
+                 kernel_kind=None):
         self.lib = load()
         o = Options()
+        o.riemann = int(riemann)
+        # the smoothing kernel follows the case the oracle gets unless stated (0 Wendland C2, 1 Laguerre-Gauss)
+        o.kernel_kind = int(kernel_kind if kernel_kind is not None else (getattr(case.kernel, "kind", 0) if case is not None else 0))
         o.serial_exchange = int(bool(serial_exchange))
         o.recut_interval = -1 if recut_interval is None else int(recut_interval)
         o.initial_cut_shift = int(initial_cut_shift)
@@ -270,6 +289,13 @@ class DamBreakCK:
         out = np.empty(shape, dtype=dt)
         self._check(self.lib.sphck_download_raw(self._h, 0, name.encode(), out.ctypes.data, b, c), f"download_raw {name}")
         return out[:, :3] if k == 1 else out
+
+    def state_digest(self):
+        """(own particle count, particle_digest of (ReferenceID, Position, Velocity)) of this rank's own particles; the sum of
+        the digests over the ranks (mod 2^64) equals the digest of the same state held by one GPU."""
+        ids = self.download_own("ReferenceID")
+        with np.errstate(over="ignore"):
+            return int(ids.size), particle_digest(ids, self.download_own("Position"), self.download_own("Velocity"))
 
     def download_own_into(self, name, out):
         """download_own into a caller buffer (e.g. pinned): device element layout, Vecd = 4 floats per particle."""

@@ -20,11 +20,11 @@ def make_oracle(case, f64=False, correction=0, riemann=1):
     return orc.OracleSim(case, f64=f64, correction=correction, riemann=riemann)
 
 
-def make_gpu(case, correction=False, fused_time_step=True, sort_interval=100, relation_stride=None, legacy=False):
+def make_gpu(case, correction=False, fused_time_step=True, sort_interval=100, relation_stride=None, legacy=False, riemann=1):
     """The C++ host layer (include/sphinxsys_ck) on the same particle arrays the oracle gets."""
     from sphinxsys_b200.host import DamBreakCK
     return DamBreakCK(case, correction=correction, fused_time_step=fused_time_step, sort_interval=sort_interval,
-                      relation_stride=relation_stride, legacy=legacy)
+                      relation_stride=relation_stride, legacy=legacy, riemann=riemann)
 
 
 def oracle_field(sim, name, width=1):

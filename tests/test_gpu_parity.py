@@ -258,8 +258,11 @@ def test_exact_two_phase_build_equals_one_pass(pair3d):
         gpu.exec("relations")
 
 
-def _compare(gpu, o32, o64, names_real, names_vec, tag, tol):
-    """|gpu - oracle64| must be within `tol` (field-norm relative) and comparable to the oracle's own fp32 error."""
+TOL = 1e-5  # BASELINE.json north_star: 1e-5 relative (field max-norm) in fp32 per step, every field, no exceptions
+
+
+def _compare(gpu, o32, o64, names_real, names_vec, tag, tol=TOL):
+    """|gpu - oracle64| <= tol * max|oracle64| for every named field (the fp32 oracle's own distance is reported next to it)."""
     rep = {}
     for nm in names_real + names_vec:
         w = 3 if nm in names_vec else 1
@@ -270,28 +273,22 @@ def _compare(gpu, o32, o64, names_real, names_vec, tag, tol):
         e_o32 = rel_err(r32, r64)
         e_gpu32 = rel_err(g, r32)
         rep[nm] = {"gpu_vs_f64": e_gpu, "oracle32_vs_f64": e_o32, "gpu_vs_oracle32": e_gpu32}
-        bound = max(tol.get(nm, tol["default"]), 4.0 * e_o32)  # never demand more than the CPU fp32 path delivers
-        assert e_gpu <= bound, f"{tag}:{nm}: gpu vs oracle64 {e_gpu:.3e} (oracle32 vs 64 {e_o32:.3e})"
+        assert e_gpu <= tol, f"{tag}:{nm}: gpu vs oracle64 {e_gpu:.3e} > {tol:.1e} (oracle32 vs 64 {e_o32:.3e})"
     _report(tag, rep)
     return rep
 
 
-def test_per_dynamics_parity_3d(pair3d):
-    """Each dynamics of one acoustic step, in the order of dambreak.cpp:188-205, compared field by field.
-    Tolerance: 1e-5 of the field's max norm (fp32, BASELINE.json), except Pressure whose fp32 granularity is
-    p0 * ulp(1) = 400 * 1.2e-7 (p = p0 (rho/rho0 - 1)): 2e-4 of max|p| on this case."""
-    case, gpu, o32, o64 = pair3d
-    tol = {"default": 1e-5, "Pressure": 3e-4, "CompressionRate": 5e-5, "Force": 5e-5}
-    # density summation + regularisation
+def _one_acoustic_step_by_phase(gpu, o32, o64, tag):
+    """Each dynamics of one acoustic step, in the order of dambreak.cpp:188-205, compared field by field."""
     gpu.exec("density_summation")
     for o in (o32, o64):
         o.exec("compression_summation")
         o.exec("density_regularization")
-    _compare(gpu, o32, o64, ["CompressionSummation", "Compression", "Density"], [], "density_summation", tol)
+    _compare(gpu, o32, o64, ["CompressionSummation", "Compression", "Density"], [], tag + "density_summation")
     gpu.exec("advection_setup")
     for o in (o32, o64):
         o.exec("advection_setup")
-    _compare(gpu, o32, o64, ["VolumetricMeasure"], ["Displacement"], "advection_setup", tol)
+    _compare(gpu, o32, o64, ["VolumetricMeasure"], ["Displacement"], tag + "advection_setup")
     # time steps
     adv = gpu.exec("advection_dt")
     ac = gpu.exec("acoustic_dt")
@@ -303,26 +300,140 @@ def test_per_dynamics_parity_3d(pair3d):
     gpu.acoustic1_phase(0, dt)
     for o in (o32, o64):
         o.exec("acoustic1_init", dt)
-    _compare(gpu, o32, o64, ["Compression", "Density", "Pressure"], ["Displacement"], "a1_init", tol)
+    _compare(gpu, o32, o64, ["Compression", "Density", "Pressure"], ["Displacement"], tag + "a1_init")
     gpu.acoustic1_phase(1, dt)
     for o in (o32, o64):
         o.exec("acoustic1_inner")
         o.exec("acoustic1_wall")
         o.exec("acoustic1_update", dt)
-    _compare(gpu, o32, o64, ["CompressionRate"], ["Force", "Velocity"], "a1_interact_update", tol)
+    _compare(gpu, o32, o64, ["CompressionRate"], ["Force", "Velocity"], tag + "a1_interact_update")
     # 2nd half (single fused launch)
     gpu.exec("acoustic2", dt)
     for o in (o32, o64):
         o.exec("acoustic2", dt)
-    _compare(gpu, o32, o64, ["CompressionRate", "Compression", "Density"], ["Force", "Displacement"], "a2", tol)
+    _compare(gpu, o32, o64, ["CompressionRate", "Compression", "Density"], ["Force", "Displacement"], tag + "a2")
     # energy reduction
     e = gpu.energy()
     assert abs(e - o64.exec("energy")) <= 1e-5 * abs(e)
 
 
+def test_per_dynamics_parity_3d(pair3d):
+    """Each dynamics of one acoustic step, field by field within 1e-5 of the field's max norm against the fp64 oracle
+    (case-file variant: AcousticRiemannSolverCK, Wendland C2)."""
+    case, gpu, o32, o64 = pair3d
+    _one_acoustic_step_by_phase(gpu, o32, o64, "")
+
+
+@pytest.mark.parametrize("riemann,kernel", [(0, "wendland"), (2, "wendland"), (1, "laguerre"), (0, "laguerre"), (2, "laguerre")])
+def test_per_dynamics_parity_variants_3d(riemann, kernel):
+    """The rest of SURVEY §8's closed type set on the GPU: NoRiemannSolverCK / DissipativeRiemannSolverCK
+    (riemann_solver_ck.h:46-173, aliases acoustic_step_1st_half.h:196-201) and the Laguerre-Gauss kernel
+    (kernel_laguerre_gauss.cpp:8-50 through resetKernel<KernelTabulated<...>>, adaptation.h:96-100), which takes the
+    generic shared-memory table path of every interaction kernel (eval_tab). Neighbour lists bit-exact, every dynamics
+    of one acoustic step within 1e-5."""
+    from sphinxsys_b200 import cases, hostmath as hm
+    kind = hm.KERNEL_LAGUERRE_GAUSS if kernel == "laguerre" else hm.KERNEL_WENDLAND_C2
+    case = cases.dam_break(dim=3, dp=0.05, kernel_kind=kind)
+    pos, vel = perturb_state(case)
+    case.fluid_pos = pos
+    gpu = make_gpu(case, fused_time_step=False, riemann=riemann)
+    assert int(gpu.kernel().kind) == kind
+    gpu.upload("Velocity", vel)
+    gpu.initialize()
+    o32, o64 = make_oracle(case, f64=False, riemann=riemann), make_oracle(case, f64=True, riemann=riemann)
+    for o in (o32, o64):
+        o.real("Velocity", 3)[:] = vel.reshape(-1)
+        o.exec("prepare_ck")
+    for contact, name in ((False, "inner"), (True, "contact")):
+        off, idx = gpu.export_csr(contact)
+        assert np.array_equal(off, o32.uint(f"{name}_offset")) and np.array_equal(idx, o32.uint(f"{name}_index")[: off[-1]])
+    _one_acoustic_step_by_phase(gpu, o32, o64, f"riemann{riemann}_{kernel}_")
+    if riemann == 0:
+        # NoRiemann: both dissipative jumps vanish, so the 1st half leaves CompressionRate at exactly zero
+        gpu2 = make_gpu(case, fused_time_step=False, riemann=0)
+        gpu2.upload("Velocity", vel)
+        gpu2.initialize()
+        gpu2.exec("density_summation")
+        gpu2.exec("advection_setup")
+        gpu2.exec("acoustic1", 1e-4)
+        assert not np.any(gpu_field(gpu2, "CompressionRate"))
+
+
+@pytest.mark.parametrize("riemann,kernel", [(2, "wendland"), (0, "wendland")])
+def test_multi_step_drift_variants(riemann, kernel):
+    """Six advection steps of the case loop (sort every 5) with a non-default Riemann solver: same acoustic step count,
+    neighbour lists bit-exact afterwards, fields within the fp32 oracle's own distance to the fp64 oracle. (The
+    Laguerre-Gauss kernel is covered dynamics by dynamics above only: with h = 1.3 dp its negative lobe makes the dam-break
+    lattice pair up, and the oracle itself runs into NaN within three advection steps — not a usable multi-step case.)"""
+    from sphinxsys_b200 import cases, hostmath as hm
+    kind = hm.KERNEL_LAGUERRE_GAUSS if kernel == "laguerre" else hm.KERNEL_WENDLAND_C2
+    case = cases.dam_break(dim=3, dp=0.05, kernel_kind=kind)
+    gpu = make_gpu(case, fused_time_step=True, sort_interval=5, riemann=riemann)
+    gpu.initialize()
+    o32, o64 = make_oracle(case, f64=False, riemann=riemann), make_oracle(case, f64=True, riemann=riemann)
+    n_outer = 6
+    n_ac = sum(gpu.step_outer() for _ in range(n_outer))
+    for o in (o32, o64):
+        o.exec("prepare_ck")
+        o.exec("run_ck", 1e9, n_outer, 1e9, 5)
+    assert int(o32.exec("acoustic_steps")) == n_ac
+    same_path = int(o64.exec("acoustic_steps")) == n_ac
+    rep = {}
+    for nm, w, tol in (("Position", 3, 5e-6), ("Velocity", 3, 2e-4), ("Density", 1, 1e-6)):
+        e = rel_err(gpu_field(gpu, nm), oracle_field(o32, nm, w))
+        noise = rel_err(oracle_field(o32, nm, w), oracle_field(o64, nm, w)) if same_path else 0.0
+        rep[nm] = {"gpu_vs_oracle32": e, "oracle32_vs_oracle64": noise}
+        assert e <= max(tol, 2.0 * noise), f"{nm}: {e:.3e} (fp32 noise {noise:.3e})"
+    off, idx = gpu.export_csr()
+    assert np.array_equal(off, o32.uint("inner_offset")) and np.array_equal(idx, o32.uint("inner_index")[: off[-1]])
+    _report(f"drift_riemann{riemann}_{kernel}", rep)
+
+
+def test_config2_full_size_parity():
+    """BASELINE config 2 at ITS OWN size (dp = 0.00625: 4,096,000 fluid + 3,034,688 wall — the benchmarked configuration)
+    against the oracle: cell lists and both neighbour lists bit-exact (sets and order), then one full advection step of the
+    case loop (summation, ~5 acoustic steps, position update, configuration update) with every field within 1e-5 of its
+    max norm against the fp64 oracle, and the neighbour lists of the moved state bit-exact again."""
+    from sphinxsys_b200 import cases
+    case = cases.dam_break(dim=3, dp=0.00625)
+    assert (case.n_fluid, case.n_wall) == (4_096_000, 3_034_688)
+    pos, vel = perturb_state(case)  # not the t = 0 lattice: jittered positions, smooth + random velocity
+    case.fluid_pos = pos
+    gpu = make_gpu(case, fused_time_step=True)
+    gpu.upload("Velocity", vel)
+    gpu.initialize()
+    o32, o64 = make_oracle(case, f64=False), make_oracle(case, f64=True)
+    for o in (o32, o64):
+        o.real("Velocity", 3)[:] = vel.reshape(-1)
+        o.exec("prepare_ck")
+    rep = {}
+    for wall, prefix in ((False, "fluid"), (True, "wall")):
+        assert np.array_equal(gpu.cell_offsets(wall), o32.uint(f"{prefix}_cell_offset"))
+    for contact, name in ((False, "inner"), (True, "contact")):
+        off, idx = gpu.export_csr(contact)
+        ref_off = o32.uint(f"{name}_offset")
+        assert np.array_equal(off, ref_off)
+        assert np.array_equal(idx, o32.uint(f"{name}_index")[: ref_off[-1]])
+        rep[f"{name}_pairs"] = int(ref_off[-1])
+        del off, idx
+    n_ac = gpu.step_outer()
+    for o in (o32, o64):
+        o.exec("run_ck", 1e9, 1, 1e9, 100)
+    assert int(o32.exec("acoustic_steps")) == n_ac and int(o64.exec("acoustic_steps")) == n_ac
+    rep["acoustic_steps"] = n_ac
+    rep["fields"] = _compare(gpu, o32, o64, ["Density", "Compression", "CompressionRate", "Pressure", "VolumetricMeasure"],
+                             ["Position", "Velocity", "Force", "Displacement"], "config2_full_size_fields")
+    e_gpu, e_ref = gpu.energy(), o64.exec("energy")
+    assert abs(e_gpu - e_ref) <= 1e-5 * abs(e_ref)
+    off, idx = gpu.export_csr()
+    ref_off = o32.uint("inner_offset")
+    assert np.array_equal(off, ref_off) and np.array_equal(idx, o32.uint("inner_index")[: ref_off[-1]])
+    _report("config2_full_size", rep)
+
+
 def test_per_dynamics_parity_2d():
     """One acoustic step of the 2-D dam break (dim-2 kernel normalisation, one cell layer in z), field by field
-    within 1e-5 of the field norm against the double oracle (pressure: its fp32 granularity)."""
+    within 1e-5 of the field norm against the double oracle."""
     from sphinxsys_b200 import cases
     case = cases.dam_break(dim=2, dp=0.025)
     pos, vel = perturb_state(case)
@@ -336,13 +447,12 @@ def test_per_dynamics_parity_2d():
         o.exec("prepare_ck")
     off, idx = gpu.export_csr()
     assert np.array_equal(off, o32.uint("inner_offset")) and np.array_equal(idx, o32.uint("inner_index")[: off[-1]])
-    tol = {"default": 1e-5, "Pressure": 3e-4, "CompressionRate": 5e-5, "Force": 5e-5}
     gpu.exec("density_summation")
     gpu.exec("advection_setup")
     for o in (o32, o64):
         for op in ("compression_summation", "density_regularization", "advection_setup"):
             o.exec(op)
-    _compare(gpu, o32, o64, ["CompressionSummation", "Compression", "Density", "VolumetricMeasure"], [], "2d_density", tol)
+    _compare(gpu, o32, o64, ["CompressionSummation", "Compression", "Density", "VolumetricMeasure"], [], "2d_density")
     dt = float(np.float32(gpu.exec("acoustic_dt")))
     assert abs(dt - o32.exec("acoustic_dt")) <= 1e-6 * dt
     gpu.exec("acoustic1", dt)
@@ -350,7 +460,7 @@ def test_per_dynamics_parity_2d():
     for o in (o32, o64):
         o.exec("acoustic1", dt)
         o.exec("acoustic2", dt)
-    _compare(gpu, o32, o64, ["CompressionRate", "Compression", "Density", "Pressure"], ["Force", "Velocity", "Displacement"], "2d_step", tol)
+    _compare(gpu, o32, o64, ["CompressionRate", "Compression", "Density", "Pressure"], ["Force", "Velocity", "Displacement"], "2d_step")
 
 
 @pytest.mark.parametrize("dim,dp", [(2, 0.025), (3, 0.05)])
@@ -374,13 +484,12 @@ def test_legacy_formulation_parity(dim, dp):
     for contact, name in ((False, "inner"), (True, "contact")):
         off, idx = gpu.export_csr(contact)
         assert np.array_equal(off, o32.uint(f"{name}_offset")) and np.array_equal(idx, o32.uint(f"{name}_index")[: off[-1]])
-    tol = {"default": 1e-5, "Pressure": 3e-4, "DensityChangeRate": 5e-5, "Force": 5e-5}
     adv = gpu.exec("advection_dt")
     assert abs(adv - o32.exec("legacy_advection_dt")) <= 1e-6 * adv
     gpu.exec("density_summation")
     for o in (o32, o64):
         o.exec("legacy_density_summation")
-    _compare(gpu, o32, o64, ["DensitySummation", "Density"], [], f"legacy{dim}d_density", tol)
+    _compare(gpu, o32, o64, ["DensitySummation", "Density"], [], f"legacy{dim}d_density")
     for step in range(2):
         ac = gpu.exec("acoustic_dt")
         assert abs(ac - o32.exec("legacy_acoustic_dt")) <= 1e-6 * ac
@@ -388,11 +497,11 @@ def test_legacy_formulation_parity(dim, dp):
         gpu.exec("acoustic1", dt)
         for o in (o32, o64):
             o.exec("legacy1", dt)
-        _compare(gpu, o32, o64, ["Density", "Pressure", "DensityChangeRate"], ["Force", "Velocity", "Position"], f"legacy{dim}d_1st_{step}", tol)
+        _compare(gpu, o32, o64, ["Density", "Pressure", "DensityChangeRate"], ["Force", "Velocity", "Position"], f"legacy{dim}d_1st_{step}")
         gpu.exec("acoustic2", dt)
         for o in (o32, o64):
             o.exec("legacy2", dt)
-        _compare(gpu, o32, o64, ["Density", "DensityChangeRate"], ["Force", "Position"], f"legacy{dim}d_2nd_{step}", tol)
+        _compare(gpu, o32, o64, ["Density", "DensityChangeRate"], ["Force", "Position"], f"legacy{dim}d_2nd_{step}")
 
 
 def test_legacy_case_loop_drift_2d():
