@@ -2,7 +2,7 @@
 // order of the reference case file tests/tests_sycl/3d_examples/test_3d_dambreak_sycl/dambreak.cpp:69-225.
 // Build (no nvcc needed; the GPU is reached through the C ABI of libsphb200.so only):
 //   g++ -O2 -std=c++17 -Iinclude examples/dambreak_ck.cpp -Lsphinxsys_b200 -lsphb200 -Wl,-rpath,$PWD/sphinxsys_b200 -o dambreak_ck
-// Run: ./dambreak_ck [dp=0.05] [end_time=1.0]
+// Run: ./dambreak_ck [dp=0.05] [end_time=1.0] [output folder for the .vtp body states; default: none written]
 #include <chrono>
 #include <iomanip>
 
@@ -53,6 +53,8 @@ int main(int ac, char *av[])
 {
     if (ac > 1) global_resolution = Real(std::atof(av[1]));
     Real end_time = ac > 2 ? Real(std::atof(av[2])) : Real(1.0);
+    const bool write_states = ac > 3;
+    const std::string output_folder = ac > 3 ? av[3] : "./output";
     Real BW = global_resolution * 4;
     Real U_f = 2.0 * std::sqrt(gravity_g * LH), c_f = 10.0 * U_f;
     //	Build up an SPHSystem.
@@ -101,6 +103,13 @@ int main(int ac, char *av[])
     ReduceDynamicsCK<MainExecutionPolicy, fluid_dynamics::AdvectionTimeStepCK> fluid_advection_time_step(water_block, U_f);
     ReduceDynamicsCK<MainExecutionPolicy, fluid_dynamics::AcousticTimeStepCK<WeaklyCompressibleFluid>> fluid_acoustic_time_step(water_block);
     ReduceDynamicsCK<MainExecutionPolicy, TotalMechanicalEnergyCK> record_water_mechanical_energy(water_block, gravity);
+    //	Define the methods for I/O operations, observations and regression tests (dambreak.cpp:141-145).
+    BodyStatesRecordingToVtpCK<MainExecutionPolicy> body_states_recording(sph_system, output_folder);
+    body_states_recording.setStateRecording(write_states);
+    body_states_recording.addToWrite<Vecd>(wall_boundary, "NormalDirection");
+    body_states_recording.addToWrite<Real>(water_block, "Density");
+    body_states_recording.addToWrite<int>(water_block, "Indicator");
+    body_states_recording.addToWrite<Real>(water_block, "PositionDivergence");
     ObservedQuantityRecording<MainExecutionPolicy, Real> fluid_observer_pressure(fluid_observer_contact, "Pressure");
     //	Prepare the simulation with cell linked list, configuration and case specified initial condition.
     SingleVariable<Real> *sv_physical_time = sph_system.getSystemVariableByName<Real>("PhysicalTime");
@@ -118,6 +127,7 @@ int main(int ac, char *av[])
     auto t1 = std::chrono::steady_clock::now();
     std::cout << "N_fluid = " << water_block.TotalRealParticles() << "  N_wall = " << wall_boundary.TotalRealParticles()
               << "  E0 = " << std::setprecision(9) << record_water_mechanical_energy.exec() << "\n";
+    body_states_recording.writeToFile(); // first output before the main loop, dambreak.cpp:177
     fluid_observer_pressure.writeToFile(number_of_iterations);
     //	Main loop starts here.
     while (sv_physical_time->getValue() < end_time)
@@ -163,6 +173,7 @@ int main(int ac, char *av[])
             fluid_observer_contact_relation.exec();
             fluid_observer_pressure.writeToFile(number_of_iterations);
         }
+        body_states_recording.writeToFile(); // dambreak.cpp:230: device -> host synchronisation of the write list, then the file
         std::cout << "t = " << sv_physical_time->getValue() << "  TotalMechanicalEnergy = " << record_water_mechanical_energy.exec() << "\n";
     }
     execution_instance().synchronize();

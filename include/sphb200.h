@@ -278,6 +278,20 @@ int sphb200_cell_list_build(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, 
 int sphb200_cell_list_build_reorder(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, const sphb200_vec4_t *pos,
                                     uint32_t n, const uint32_t *sort_key, sphb200_cell_list_t list, int count,
                                     void *const *dst, const void *const *src, const uint32_t *elem_bytes, void *stream);
+/* The same with the particle count taken from DEVICE memory: n is the capacity the launches are sized for and
+ * min(n, *n_dev) particles are processed (n_dev == NULL: n). For slab-decomposed runs, whose arrivals are counted on the
+ * device (sphb200_comm_pull), so that a rebuild needs no host round trip before its last step. */
+int sphb200_cell_list_build_reorder_n(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, const sphb200_vec4_t *pos,
+                                      uint32_t n, const uint32_t *n_dev, const uint32_t *sort_key, sphb200_cell_list_t list,
+                                      int count, void *const *dst, const void *const *src, const uint32_t *elem_bytes,
+                                      void *stream);
+/* Slab bookkeeping in one device record (new): out_dev[0..k) = cell_offset[cells_dev[0..k)], out_dev[k] = *n_dev,
+ * out_dev[k + 1] = the mailbox status word; own64_dev[0] = out[hi] - out[lo] with own_lo_hi = lo | hi << 8 (the rank's own
+ * particle count, as the 64-bit word the all-gather of the slot origins sends). */
+/* *out_dev = base + *a_dev + *b_dev (NULL terms are 0): the stored-particle count after the arrivals of a rebuild. */
+int sphb200_slab_total(sphb200_context_t *ctx, uint32_t base, const uint32_t *a_dev, const uint32_t *b_dev, uint32_t *out_dev, void *stream);
+int sphb200_slab_bounds(sphb200_context_t *ctx, const uint32_t *cell_offset, const uint32_t *cells_dev, int k,
+                        const uint32_t *n_dev, int own_lo_hi, uint32_t *out_dev, uint64_t *own64_dev, void *stream);
 /* UpdateRelation<Inner<>>::exec and <Contact<>>::exec, split as the reference splits them so the host can
  * grow `index` between the two phases (update_body_relation.hpp:117-164, 240-288):
  *   *_count : fills rel.count and rel.slice_offset, returns the required capacity (entries) in *required_host
@@ -458,6 +472,24 @@ typedef struct
  * outside the box planes on the sender (leavers) end inside them, the others (its boundary plane) in the ghost plane. */
 int sphb200_seam_shift(sphb200_context_t *ctx, void *base, uint32_t stride_bytes, uint32_t n, float delta,
                        const sphb200_seam_t *seam, void *stream);
+/* Peer mailboxes (new): every rank owns four boxes of `box_bytes` (two parities x {from the left, from the right}); the
+ * neighbours map them over CUDA IPC (NVLink peer access) and WRITE into them directly: sphb200_comm_push gathers the listed
+ * slots of `count` variables — the list length is read from DEVICE memory, so no message size crosses the host — stores
+ * them into the neighbour's box of parity (seq & 1) and releases the box by writing {count, seq} into its header
+ * (system-scope fence, last block of the launch). sphb200_comm_pull waits on the device for the header of `seq`, appends the
+ * box's records behind `dst_begin` (+ *dst_extra_dev) of each variable and leaves the count in *count_dev.
+ * side: 0 = the left neighbour, 1 = the right neighbour (push: where it goes; pull: where it comes from).
+ * Status bits (sphb200_comm_mailbox_status, device word): 1 = a push had more entries than the neighbour's box holds,
+ * 2 = a pull timed out waiting for its neighbour, 4 = a pull ran out of room behind dst_begin. open/close are collective. */
+int sphb200_comm_mailbox_open(sphb200_context_t *ctx, size_t box_bytes);
+int sphb200_comm_mailbox_close(sphb200_context_t *ctx);
+size_t sphb200_comm_mailbox_peer_bytes(const sphb200_context_t *ctx, int side);
+const uint32_t *sphb200_comm_mailbox_status(const sphb200_context_t *ctx);
+int sphb200_comm_push(sphb200_context_t *ctx, int side, int count, const void *const *src, const uint32_t *elem_bytes,
+                      const uint32_t *idx, const uint32_t *n_dev, uint64_t seq, void *stream);
+int sphb200_comm_pull(sphb200_context_t *ctx, int side, int count, void *const *dst, const uint32_t *elem_bytes,
+                      uint32_t dst_begin, const uint32_t *dst_extra_dev, uint32_t dst_end, uint32_t *count_dev, uint64_t seq,
+                      void *stream);
 int sphb200_comm_allreduce_max_f32(sphb200_context_t *ctx, float *dev_inout, int n, void *stream);
 int sphb200_comm_allreduce_sum_f64(sphb200_context_t *ctx, double *dev_inout, int n, void *stream);
 int sphb200_comm_allgather_u64(sphb200_context_t *ctx, const uint64_t *dev_send, uint64_t *dev_recv, int n_per_rank, void *stream);

@@ -109,7 +109,9 @@ class RelationBase
         r.capacity = capacity_;
         r.order = nullptr; // storage is cell ordered: slot == particle id
         // contact relations: the target body is not decomposed with the source, see sphb200_relation_t::bank_aligned
-        r.bank_aligned = bank_aligned_ ? 1 + (is_inner_ ? 0 : (int)(source_.slotOrigin() & 7u)) : 0;
+        // (and when the target keeps only a slab of its particles as well — WallSlab — its own slot origin comes off again:
+        // the layout class of an entry is s_global - t_global whatever the two bodies store)
+        r.bank_aligned = bank_aligned_ ? 1 + (is_inner_ ? 0 : (int)((source_.slotOrigin() - target_.slotOrigin()) & 7u)) : 0;
         return r;
     }
     sphb200_search_t search()

@@ -39,6 +39,7 @@ struct DamBreakParameters
     int initial_cut_shift = 0;    // decomposed runs: start with the interior cuts moved by so many planes (test hook)
     int recut_interval = 100;     // decomposed runs: re-balance the slab cuts every so many advection steps (0: never)
     bool overlap_exchange = true; // decomposed runs: hide the plane exchange behind interior compute (acousticStepOverlapped)
+    bool wall_slabs = true;       // decomposed runs: every rank stores the wall planes around its slab only (WallSlab)
     static DamBreakParameters twoDimensional(double dp = 0.025)
     {
         DamBreakParameters p;
@@ -71,6 +72,74 @@ class WallBoundary : public ComplexShape
 
 template <class T> struct TypeTag { using type = T; };
 
+// Slab of the static wall (SURVEY §8e / DESIGN §6): a rank of a decomposed run stores only the wall particles of the cell
+// planes its own fluid can reach — [first own plane - depth - margin, last own plane + depth + margin] on the wall's mesh —
+// instead of a full copy of the wall. The master copy (positions, normals, planes; the reference's particle order) stays on
+// the host; when re-cuts move the slab beyond the stored planes the subset is loaded again and the wall's cell list is
+// rebuilt (the wall is static: nothing else ever changes there, dambreak.cpp:159 builds its list once too).
+// Wall particles keep their GLOBAL numbers as ReferenceID, so in-cell order, neighbour rows and the CSR export are those of
+// the undecomposed run; the number of wall particles in the planes below the stored ones is the wall's slot origin
+// (RelationBase::view: bank-aligned contact rows depend on s_global - t_global only).
+class WallSlab
+{
+    SolidBody &wall_;
+    std::vector<Vecd> pos_, normal_;
+    std::vector<int> plane_;
+    std::vector<uint64_t> below_; // below_[x] = wall particles in planes < x
+    int planes_ = 0, depth_ = 1, margin_ = 4;
+    int lo_ = 0, hi_ = -1; // stored planes [lo_, hi_]
+    uint64_t loads_ = 0;
+
+  public:
+    // `m`: the mesh of the wall's cell-linked list (handed in: the list itself is made once the storage is sized)
+    WallSlab(SolidBody &wall, const sphb200_mesh_t &m, std::vector<Vecd> positions, std::vector<Vecd> normals, int search_depth)
+        : wall_(wall), pos_(std::move(positions)), normal_(std::move(normals)), depth_(search_depth)
+    {
+        planes_ = m.cells[0];
+        plane_.resize(pos_.size());
+        below_.assign(planes_ + 1, 0);
+        for (size_t i = 0; i < pos_.size(); ++i)
+        {
+            plane_[i] = hostCellCoordinate(pos_[i].x, m.lower[0], m.spacing, m.cells[0]);
+            below_[plane_[i] + 1]++;
+        }
+        for (int x = 0; x < planes_; ++x) below_[x + 1] += below_[x];
+    }
+    size_t globalParticles() const { return pos_.size(); }
+    uint64_t loads() const { return loads_; }
+    // largest number of wall particles any window of `width` planes holds (sizes the storage once)
+    size_t largestWindow(int width) const
+    {
+        uint64_t best = 0;
+        for (int x = 0; x < planes_; ++x) best = std::max(best, below_[std::min(planes_, x + width)] - below_[x]);
+        return (size_t)best;
+    }
+    int marginPlanes() const { return margin_; }
+    // make sure the wall planes around the fluid planes [X0, X1) are stored; true if the subset was (re)loaded
+    bool ensure(int X0, int X1)
+    {
+        const int need_lo = std::max(0, X0 - depth_), need_hi = std::min(planes_ - 1, X1 - 1 + depth_);
+        if (hi_ >= lo_ && need_lo >= lo_ && need_hi <= hi_) return false;
+        lo_ = std::max(0, need_lo - margin_);
+        hi_ = std::min(planes_ - 1, need_hi + margin_);
+        std::vector<Vecd> p, nrm;
+        std::vector<UnsignedInt> ids;
+        const size_t count = (size_t)(below_[hi_ + 1] - below_[lo_]);
+        p.reserve(count), nrm.reserve(count), ids.reserve(count);
+        for (size_t i = 0; i < pos_.size(); ++i)
+            if (plane_[i] >= lo_ && plane_[i] <= hi_)
+            {
+                p.push_back(pos_[i]);
+                nrm.push_back(normal_[i]);
+                ids.push_back((UnsignedInt)i);
+            }
+        wall_.loadWallSubset(p, nrm, ids);
+        wall_.setSlotOrigin((uint32_t)(below_[lo_] & 0xffffffffull));
+        ++loads_;
+        return true;
+    }
+};
+
 class DamBreakCK
 {
   public:
@@ -97,6 +166,7 @@ class DamBreakCK
     std::unique_ptr<Contact<>> fluid_observer_contact;
     std::unique_ptr<UpdateRelation<P, Contact<>>> fluid_observer_contact_relation;
     std::unique_ptr<ObservedQuantityRecording<P, Real>> fluid_observer_pressure;
+    std::unique_ptr<BodyStatesRecordingToVtpCK<P>> body_states_recording; // made on demand (recordStates)
     std::unique_ptr<InteractionDynamicsBase> fluid_acoustic_step_1st_half, fluid_acoustic_step_2nd_half;
     std::unique_ptr<InteractionDynamicsBase> fluid_density_summation;
     std::unique_ptr<StateDynamics<P, fluid_dynamics::DensityRegularization<SPHBody, WeaklyCompressibleFluid, FreeSurface>>> fluid_density_regularization;
@@ -109,6 +179,7 @@ class DamBreakCK
     fluid_dynamics::FluidDynamicsBase *cuts_adv_ = nullptr;
     std::unique_ptr<ReduceDynamicsCK<P, TotalMechanicalEnergyCK>> record_water_mechanical_energy;
     std::unique_ptr<SlabDecomposition> decomposition; // nranks > 1 only
+    std::unique_ptr<WallSlab> wall_slab;              // nranks > 1 only: this rank's part of the static wall
     fluid_dynamics::AcousticStep1stHalfPhases *first_half_phases_ = nullptr;
     fluid_dynamics::AcousticStep2ndHalfPhases *second_half_phases_ = nullptr;
     SingleVariable<Real> *sv_physical_time = nullptr;
@@ -206,10 +277,29 @@ class DamBreakCK
         else if (fluid_positions) water_block.generateParticlesFromPositions(*fluid_positions, vol);
         else water_block.generateParticles<BaseParticles, Lattice>();
         wall_boundary.defineMatterMaterial<Solid>();
-        if (wall_positions) wall_boundary.generateParticlesFromPositions(*wall_positions, vol);
-        else wall_boundary.generateParticles<BaseParticles, Lattice>();
-        if (wall_normals) wall_boundary.registerWallVariables(wall_normals);
-        else wall_boundary.computeNormalFromBodyShape(); // NormalFromBodyShapeCK, run on the host (dambreak.cpp:119,153)
+        if (q.nranks > 1 && q.wall_slabs)
+        {
+            // slab of the wall: master copy on the host, storage for the widest window this rank may ever hold
+            std::vector<Vecd> all_wall = wall_positions ? *wall_positions
+                                                        : generateLattice(wall_boundary.getInitialShape(), sph_system.system_domain_bounds_, Real(q.dp), q.dim);
+            std::vector<Vecd> all_normals = wall_normals ? *wall_normals : wall_boundary.normalsFromBodyShape(all_wall);
+            const sphb200_mesh_t wmesh = makeMesh(sph_system.system_domain_bounds_, wall_boundary.getSPHAdaptation().CutOffRadius(), 2, q.dim);
+            // every rank owns about planes / nranks planes; re-cuts may widen a slab: room for twice that plus the margins
+            const int width = std::min(wmesh.cells[0], 2 * (wmesh.cells[0] / q.nranks + 1) + 2 * (1 + 4) + 2);
+            wall_slab.reset(new WallSlab(wall_boundary, wmesh, std::move(all_wall), std::move(all_normals), 1));
+            const size_t room = std::min(wall_slab->globalParticles(), wall_slab->largestWindow(width)) + 1024;
+            std::vector<Vecd> none;
+            wall_boundary.generateParticlesFromPositions(none, vol, room); // empty storage of that size; WallSlab::ensure fills it
+            wall_boundary.registerWallVariables(nullptr);
+            wall_slab->ensure(cuts[q.rank], cuts[q.rank + 1]);
+        }
+        else
+        {
+            if (wall_positions) wall_boundary.generateParticlesFromPositions(*wall_positions, vol);
+            else wall_boundary.generateParticles<BaseParticles, Lattice>();
+            if (wall_normals) wall_boundary.registerWallVariables(wall_normals);
+            else wall_boundary.computeNormalFromBodyShape(); // NormalFromBodyShapeCK, run on the host (dambreak.cpp:119,153)
+        }
 
         using namespace fluid_dynamics;
         water_cell_linked_list.reset(new UpdateCellLinkedList<P, RealBody>(water_block));
@@ -315,6 +405,7 @@ class DamBreakCK
                 fluid_observer_pressure.reset(new ObservedQuantityRecording<P, Real>(*fluid_observer_contact, "Pressure"));
             }
         }
+        if (wall_slab && water_wall_contact->search_depth_ != 1) throw SphError("WallSlab: the contact search reaches further than one cell plane");
         water_block_update_complex_relation.reset(new UpdateRelation<P, Inner<>, Contact<>>(*water_block_inner, *water_wall_contact));
         record_water_mechanical_energy.reset(new ReduceDynamicsCK<P, TotalMechanicalEnergyCK>(water_block, gravity));
         sv_physical_time = sph_system.getSystemVariableByName<Real>("PhysicalTime");
@@ -332,6 +423,24 @@ class DamBreakCK
     }
 
     void registerPressure() { water_block.getBaseParticles().registerStateVariable<Real>("Pressure"); }
+
+    // dambreak.cpp:141-145,177,230: the body-state output with its write list; every call synchronises Position and the
+    // listed variables device -> host (BodyStatesRecordingToVtpCK::prepareToWrite) and writes one .vtp per body
+    void recordStates(const std::string &folder)
+    {
+        if (!body_states_recording)
+        {
+            body_states_recording.reset(new BodyStatesRecordingToVtpCK<P>(sph_system, folder));
+            body_states_recording->addToWrite<Vecd>(wall_boundary, "NormalDirection");
+            body_states_recording->addToWrite<Real>(water_block, "Density");
+            if (fluid_boundary_indicator)
+            {
+                body_states_recording->addToWrite<int>(water_block, "Indicator");
+                body_states_recording->addToWrite<Real>(water_block, "PositionDivergence");
+            }
+        }
+        body_states_recording->writeToFile(number_of_iterations);
+    }
 
     // dambreak.cpp:152-160
     void initialize()
@@ -441,8 +550,13 @@ class DamBreakCK
         {
             // migration + ghost planes + cell-linked list; at the sort cadence the slabs are re-balanced as well
             const bool recut = allow_sort && q_.recut_interval > 0 && number_of_iterations % q_.recut_interval == 0 && number_of_iterations != 1;
-            if (recut) decomposition->recut();
-            else decomposition->rebuild();
+            if (recut)
+            {
+                decomposition->recut();
+                // the cuts moved: load the wall planes around the new slab if they are not stored yet, and list them
+                if (wall_slab && wall_slab->ensure(decomposition->cuts()[q_.rank], decomposition->cuts()[q_.rank + 1])) wall_cell_linked_list->exec();
+            }
+            else decomposition->update();
         }
         else water_cell_linked_list->exec();
         water_block_update_complex_relation->exec();

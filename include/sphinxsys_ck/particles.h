@@ -131,6 +131,17 @@ template <class T> class DiscreteVariable : public DiscreteVariableBase
     }
     void synchronizeToDevice();   // host (reference order) -> device (slot order)
     void synchronizeWithDevice(); // device -> host
+    // sphinxsys_variable.h:350-356: what the output / reload paths call; a device policy is the only one there is here
+    template <class Policy> void prepareForOutput(const Policy &)
+    {
+        execution::require_device_policy<Policy>();
+        synchronizeWithDevice();
+    }
+    template <class Policy> void finalizeLoadIn(const Policy &)
+    {
+        execution::require_device_policy<Policy>();
+        synchronizeToDevice();
+    }
 };
 
 // SingleVariable<T>: a named scalar living on the host, mirrored to the device on demand (sphinxsys_variable.h:50-120)
@@ -178,6 +189,16 @@ class BaseParticles
     {
         if (n > particles_bound_) throw SphError("particle storage exhausted: " + std::to_string(n) + " > bound " + std::to_string(particles_bound_));
         total_real_particles_ = n;
+    }
+    // a new particle set in the same storage (static bodies re-cut by the slab decomposition): n particles in the order
+    // the caller uploads them next, i.e. host order == slot order again until the next reorder
+    void resetContents(size_t n)
+    {
+        setTotalRealParticles(n);
+        active_begin_ = 0;
+        active_end_ = n;
+        identity_order_ = true;
+        ++storage_version_;
     }
     size_t activeBegin() const { return active_begin_; }
     size_t activeEnd() const { return active_end_; }
@@ -811,6 +832,36 @@ class SolidBody : public SPHBody
         ExecutionInstance &ex = execution_instance();
         ex.check(sphb200_copy_d2d(dv_ref->deviceAddress(), dv_vol->deviceAddress(), n * sizeof(Real), ex.stream()), "sphb200_copy_d2d");
         if (normals && n) p.upload(dv_n, normals->data());
+    }
+    // Slab-decomposed runs keep only the part of the static wall a rank can reach (dambreak_case.h, WallSlab): replace the
+    // stored particle set by `pos` / `normals` with the global particle numbers `ids` (in-cell order and the CSR export go
+    // by them). Volumes are uniform and were filled over the whole storage at registration. The caller rebuilds the cell
+    // list (which brings the storage into cell order) afterwards.
+    void loadWallSubset(const std::vector<Vecd> &pos, const std::vector<Vecd> &normals, const std::vector<UnsignedInt> &ids)
+    {
+        BaseParticles &p = getBaseParticles();
+        const size_t n = pos.size();
+        if (normals.size() != n || ids.size() != n) throw SphError("loadWallSubset: array sizes differ");
+        p.resetContents(n); // throws if the storage is too small
+        ExecutionInstance &ex = execution_instance();
+        if (n)
+        {
+            p.upload(p.getVariableByName<Vecd>("Position"), pos.data());
+            p.upload(p.getVariableByName<Vecd>("NormalDirection"), normals.data());
+            ex.check(sphb200_copy_d2d(p.deviceData<Real>("VolumetricMeasureRef"), p.deviceData<Real>("VolumetricMeasure"), n * sizeof(Real), ex.stream()), "sphb200_copy_d2d");
+            ex.check(sphb200_copy_h2d(p.referenceID(), ids.data(), n * sizeof(UnsignedInt), ex.stream()), "sphb200_copy_h2d");
+            ex.check(sphb200_copy_h2d(p.deviceData<UnsignedInt>("OriginalID"), ids.data(), n * sizeof(UnsignedInt), ex.stream()), "sphb200_copy_h2d");
+            ex.synchronize();
+        }
+        setCellOrdered(false);
+        setPosVolDirty();
+    }
+    // NormalFromBodyShapeCK for arbitrary points of the body (host)
+    std::vector<Vecd> normalsFromBodyShape(const std::vector<Vecd> &pos) const
+    {
+        std::vector<Vecd> normals(pos.size());
+        for (size_t i = 0; i < pos.size(); ++i) normals[i] = shape_->directionToSurface(pos[i], sph_system_.dim_);
+        return normals;
     }
     // NormalFromBodyShapeCK (host-side in the reference case file: StateDynamics<ParallelPolicy, ...>)
     void computeNormalFromBodyShape()

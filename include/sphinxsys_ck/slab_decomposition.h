@@ -174,6 +174,11 @@ class SlabDecomposition
     DeviceBuffer plane_scratch_; // plane-boundary offsets and the particles-per-plane histogram (recut)
     uint64_t recuts_ = 0;
     uint64_t migrated_out_ = 0, ghost_particles_ = 0;
+    // peer-mailbox rebuild (rebuildPeer): sequence number of the pushes, capacity the mailboxes were opened with
+    uint64_t mail_seq_ = 0;
+    bool mail_open_ = false;
+    bool configured_ = false; // a rebuild has run: planes and ghosts exist (every rank flips this at the same call)
+    uint64_t host_syncs_ = 0; // host round trips spent in rebuilds (diagnostics)
     // overlap of the plane exchange with interior compute: a high-priority side stream carries the exchanges and the
     // boundary-plane launches, the default stream the interior launches; events order the two (dambreak_case.h)
     void *side_stream_ = nullptr;
@@ -194,8 +199,9 @@ class SlabDecomposition
             ex.check(sphb200_copy_d2h(out + k, body_.getCellLinkedList().cell_offset_.get<uint32_t>() + cells[k], sizeof(uint32_t), ex.stream()), "sphb200_copy_d2h");
         ex.synchronize();
     }
-    // cell-list build + storage reorder of the slots [begin, begin + n) into [0, n)
-    void reorder(uint32_t begin, uint32_t n)
+    // cell-list build + storage reorder of the slots [begin, begin + n) into [0, n); n_dev != nullptr: n is the capacity
+    // the launches are sized for and the live count is read from the device
+    void reorder(uint32_t begin, uint32_t n, const uint32_t *n_dev = nullptr)
     {
         BaseParticles &p = body_.getBaseParticles();
         CellLinkedList &cl = body_.getCellLinkedList();
@@ -209,7 +215,7 @@ class SlabDecomposition
             dst[k] = vars[k]->shadowAddress();
             src[k] = (const char *)vars[k]->deviceAddress() + (size_t)begin * bytes[k];
         }
-        SPHCK_CALL(sphb200_cell_list_build_reorder, &cl.mesh_, (const sphb200_vec4_t *)p.deviceData<Vecd>("Position") + begin, n,
+        SPHCK_CALL(sphb200_cell_list_build_reorder_n, &cl.mesh_, (const sphb200_vec4_t *)p.deviceData<Vecd>("Position") + begin, n, n_dev,
                    p.referenceID() + begin, cl.view(), (int)vars.size(), dst.data(), src.data(), bytes.data(),
                    execution_instance().stream());
         for (auto *v : vars) v->swapWithShadow();
@@ -242,6 +248,7 @@ class SlabDecomposition
     }
     ~SlabDecomposition()
     {
+        if (mail_open_) sphb200_comm_mailbox_close(execution_instance().ctx());
         for (void *e : events_)
             if (e) sphb200_event_destroy(e);
         if (side_stream_) sphb200_stream_destroy(side_stream_);
@@ -295,6 +302,117 @@ class SlabDecomposition
     uint64_t ghostParticles() const { return ghost_particles_; }
     uint64_t migratedOut() const { return migrated_out_; }
 
+    // SPHB200_PEER_REBUILD=0 keeps the NCCL exchange (count round trip + grouped send/recv) for every rebuild
+    static bool peerRebuildEnabled()
+    {
+        static const bool on = [] {
+            const char *e = std::getenv("SPHB200_PEER_REBUILD");
+            return !(e && e[0] == '0');
+        }();
+        return on;
+    }
+    uint64_t hostSyncs() const { return host_syncs_; }
+
+    // The configuration update of an advection step. Chains of slabs use the peer-mailbox rebuild (one host round trip,
+    // migrants written straight into the neighbours' memory); rings, the very first rebuild (which sizes the mailboxes from
+    // the planes it finds) and the hand-over rebuilds of recut() — whole slabs may change owner there — use the NCCL one.
+    void update()
+    {
+        // the choice depends on nothing rank-local: all ranks take the same branch at the same call
+        if (!ring_.on && nranks_ > 1 && peerRebuildEnabled() && configured_) rebuildPeer();
+        else rebuild();
+    }
+
+    // rebuild() without host-known message sizes. Everything up to the last step is enqueued without a host round trip:
+    //   select -> push to both neighbours (gather + remote stores into their mailboxes + release, ONE kernel per side)
+    //   -> pull from both neighbours (device-side wait on the mailbox header, append behind the own slots, count stays on
+    //   the device) -> cell-list build + reorder sized for the storage, live count read from the device -> plane offsets,
+    //   counts and status gathered into one record -> all-gather of the own counts (slot origins) -> ONE copy to the host.
+    void rebuildPeer()
+    {
+        ExecutionInstance &ex = execution_instance();
+        BaseParticles &p = body_.getBaseParticles();
+        CellLinkedList &cl = body_.getCellLinkedList();
+        void *st = ex.stream();
+        const uint32_t n_old = a1_ - a0_;
+        const int X0 = cuts_[rank_], X1 = cuts_[rank_ + 1];
+        std::vector<DiscreteVariableBase *> vars = p.reorderedVariables();
+        const size_t k = vars.size();
+        std::vector<const void *> src(k);
+        std::vector<void *> dst(k);
+        std::vector<uint32_t> bytes(k);
+        size_t entry_bytes = 0;
+        for (size_t i = 0; i < k; ++i)
+        {
+            bytes[i] = vars[i]->deviceElementBytes();
+            src[i] = vars[i]->deviceAddress();
+            dst[i] = vars[i]->deviceAddress();
+            entry_bytes += bytes[i];
+        }
+        if (!mail_open_)
+        {
+            // a box holds four times the larger boundary plane (leavers are a small fraction of a plane per step); what does
+            // not fit is reported by the status word, not written
+            // (the largest plane of ALL ranks: a box must hold what the NEIGHBOUR sends)
+            const size_t mine = std::max<size_t>(std::max(f1_ - a0_, a1_ - l0_), 4096);
+            const size_t plane = (size_t)allReduceMax(Real(mine / 1024 + 1)) * 1024;
+            ex.check(sphb200_comm_mailbox_open(ex.ctx(), 64 + 4 * plane * entry_bytes), "sphb200_comm_mailbox_open");
+            mail_open_ = true;
+        }
+        const uint64_t seq = ++mail_seq_;
+        select_.ensure((size_t)2 * n_old * sizeof(uint32_t) + 64);
+        uint32_t *left_idx = select_.get<uint32_t>(), *right_idx = left_idx + n_old;
+        // device words of this rebuild (bytes 768.. of the scratch): [0,1] send counts, [2,3] receive counts, [4] stored total,
+        // [5..8] cells of the plane boundaries, [16..23] the record that goes to the host
+        uint32_t *w = scalars_.get<uint32_t>() + 192;
+        uint32_t *d_send = w, *d_recv = w + 2, *d_ntot = w + 4, *d_cells = w + 5, *d_rec = w + 16;
+        SPHCK_CALL(sphb200_slab_select, &cl.mesh_, (const sphb200_vec4_t *)p.deviceData<Vecd>("Position"), a0_, n_old,
+                   hasLeft() ? X0 : -1, hasRight() ? X1 - 1 : -1, left_idx, right_idx, d_send, st);
+        if (hasLeft()) SPHCK_CALL(sphb200_comm_push, 0, (int)k, src.data(), bytes.data(), left_idx, d_send, seq, st);
+        if (hasRight()) SPHCK_CALL(sphb200_comm_push, 1, (int)k, src.data(), bytes.data(), right_idx, d_send + 1, seq, st);
+        const uint32_t bound = (uint32_t)p.ParticlesBound();
+        if (hasLeft()) SPHCK_CALL(sphb200_comm_pull, 0, (int)k, dst.data(), bytes.data(), a1_, nullptr, bound, d_recv, seq, st);
+        if (hasRight()) SPHCK_CALL(sphb200_comm_pull, 1, (int)k, dst.data(), bytes.data(), a1_, hasLeft() ? d_recv : nullptr, bound, d_recv + 1, seq, st);
+        SPHCK_CALL(sphb200_slab_total, n_old, hasLeft() ? d_recv : nullptr, hasRight() ? d_recv + 1 : nullptr, d_ntot, st);
+        // everything into cell order at the front of the arrays; launches sized for what the storage can hold
+        const uint32_t capacity = bound - a0_;
+        p.setTotalRealParticles(bound);
+        reorder(a0_, capacity, d_ntot);
+        uint32_t cells4[4] = {(uint32_t)X0 * plane_cells_, (uint32_t)(X0 + 1) * plane_cells_, (uint32_t)(X1 - 1) * plane_cells_,
+                              (uint32_t)X1 * plane_cells_};
+        ex.check(sphb200_copy_h2d(d_cells, cells4, sizeof(cells4), st), "sphb200_copy_h2d");
+        uint64_t *d_own = scalars_.get<uint64_t>() + 128, *d_all = d_own + 1; // bytes 1024.. : behind the reduction windows
+        SPHCK_CALL(sphb200_slab_bounds, cl.cell_offset_.get<uint32_t>(), d_cells, 4, d_ntot, 0 | (3 << 8), d_rec, d_own, st);
+        SPHCK_CALL(sphb200_comm_allgather_u64, d_own, d_all, 1, st);
+        // the ONE host round trip: plane offsets, stored total, status, send counts, own counts of all ranks
+        uint32_t rec[6] = {0, 0, 0, 0, 0, 0}, sent[2] = {0, 0};
+        std::vector<uint64_t> all(nranks_);
+        ex.check(sphb200_copy_d2h(rec, d_rec, sizeof(rec), st), "sphb200_copy_d2h");
+        ex.check(sphb200_copy_d2h(sent, d_send, sizeof(sent), st), "sphb200_copy_d2h");
+        ex.check(sphb200_copy_d2h(all.data(), d_all, all.size() * sizeof(uint64_t), st), "sphb200_copy_d2h");
+        ex.synchronize();
+        ++host_syncs_;
+        if (rec[5])
+            throw SphError("SlabDecomposition::rebuildPeer: rank " + std::to_string(rank_) + " mailbox status " + std::to_string(rec[5]) +
+                           " (1: more migrants than a mailbox holds, 2: a neighbour did not deliver, 4: particle storage exhausted)");
+        a0_ = rec[0];
+        f1_ = rec[1];
+        l0_ = rec[2];
+        a1_ = rec[3];
+        n_ = rec[4];
+        p.setTotalRealParticles(n_);
+        p.setActiveRange(a0_, a1_);
+        body_.setCellOrdered(true);
+        body_.setPosVolDirty();
+        ghost_particles_ = (uint64_t)a0_ + (n_ - a1_);
+        migrated_out_ += (uint64_t)sent[0] + sent[1];
+        if (PeriodicImages *im = body_.periodicImages()) im->setStoredRange(n_, a0_, a1_);
+        if (checkExchangeEnabled()) verifyGhostPlanes();
+        uint64_t below = 0;
+        for (int r = 0; r < rank_; ++r) below += all[r];
+        body_.setSlotOrigin((uint32_t)((below - a0_) & 0xffffffffull));
+    }
+
     // once per advection step, instead of UpdateCellLinkedList::exec(). `check_planes` = false for the first of recut()'s
     // two rebuilds: between them the former owner still holds whole planes it handed over, so "ghosts" are not one plane
     // per side yet and the SPHB200_CHECK_EXCHANGE comparison would raise a false alarm (and leave the peers in NCCL).
@@ -321,6 +439,7 @@ class SlabDecomposition
         uint32_t sel[2] = {0, 0};
         ex.check(sphb200_copy_d2h(sel, d_counts, sizeof(sel), st), "sphb200_copy_d2h");
         ex.synchronize();
+        host_syncs_ += 4; // own counts, neighbours' counts, plane offsets, slot origins
         const uint32_t send_l = sel[0], send_r = sel[1];
         uint64_t host_counts[4] = {send_l, send_r, 0, 0};
         ex.check(sphb200_copy_h2d(d, host_counts, sizeof(host_counts), st), "sphb200_copy_h2d");
@@ -421,6 +540,7 @@ class SlabDecomposition
             for (int r = 0; r < rank_; ++r) below += all[r];
             body_.setSlotOrigin((uint32_t)((below - a0_) & 0xffffffffull));
         }
+        configured_ = true;
     }
 
     // SPHB200_CHECK_EXCHANGE=1: after every rebuild() the ranks tell each other how many particles their boundary planes
@@ -500,7 +620,7 @@ class SlabDecomposition
         ++recuts_;
         if (next == cuts_)
         {
-            rebuild();
+            update();
             return;
         }
         cuts_ = next;

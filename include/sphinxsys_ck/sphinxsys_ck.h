@@ -6,4 +6,5 @@
 #include "particles.h"
 #include "configuration.h"
 #include "fluid_dynamics.h"
+#include "io_ck.h"
 #endif

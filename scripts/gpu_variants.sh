@@ -5,7 +5,7 @@ TAG=$1; shift
 OUT=gpurun_out/$TAG; mkdir -p $OUT
 cd sphinxsys_b200/csrc
 for V in "$@"; do
-  rm -f build/fluid.o build/neighbor.o
+  rm -f build/fluid.o
   make NVCCFLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xptxas -v --expt-extended-lambda -ccbin /usr/bin/g++ $V" > /dev/null 2>&1 || echo "build failed: $V"
-  (cd ../..; python scripts/kbench.py --tag "$V" | tee -a $OUT/variants.jsonl)
+  (cd ../..; python scripts/kbench.py --tag="$V" | tee -a $OUT/variants.jsonl)
 done

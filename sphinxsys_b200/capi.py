@@ -158,6 +158,15 @@ SYMBOLS = {
     "sphb200_comm_set_ring": (_I, [_CTX, _I]),
     "sphb200_comm_is_ring": (_I, [_CTX]),
     "sphb200_seam_shift": (_I, [_CTX, _P, _U32, _U32, C.c_float, _P, _P]),
+    "sphb200_comm_mailbox_open": (_I, [_CTX, C.c_size_t]),
+    "sphb200_comm_mailbox_close": (_I, [_CTX]),
+    "sphb200_comm_mailbox_peer_bytes": (C.c_size_t, [_CTX, _I]),
+    "sphb200_comm_mailbox_status": (_P, [_CTX]),
+    "sphb200_comm_push": (_I, [_CTX, _I, _I, _P, _P, _P, _P, C.c_uint64, _P]),
+    "sphb200_comm_pull": (_I, [_CTX, _I, _I, _P, _P, _U32, _P, _U32, _P, C.c_uint64, _P]),
+    "sphb200_cell_list_build_reorder_n": (_I, [_CTX, C.POINTER(MeshT), _P, _U32, _P, _P, CellListT, _I, _P, _P, _P, _P]),
+    "sphb200_slab_total": (_I, [_CTX, _U32, _P, _P, _P, _P]),
+    "sphb200_slab_bounds": (_I, [_CTX, _P, _P, _I, _P, _I, _P, _P]),
     "sphb200_comm_allreduce_max_f32": (_I, [_CTX, _P, _I, _P]),
     "sphb200_comm_allreduce_sum_f64": (_I, [_CTX, _P, _I, _P]),
     "sphb200_comm_allgather_u64": (_I, [_CTX, _P, _P, _I, _P]),

@@ -114,6 +114,7 @@ extern "C" int sphb200_comm_create(sphb200_context_t *ctx, int nranks, int rank,
 extern "C" int sphb200_comm_destroy(sphb200_context_t *ctx)
 {
     SPH_CHECK_ARG(ctx, ctx, "null context");
+    if (ctx->mailbox) sphb200_comm_mailbox_close(ctx);
     if (ctx->comm && g_nccl.ok) g_nccl.CommDestroy((nccl_comm_t)ctx->comm);
     ctx->comm = nullptr;
     ctx->ring = 0;
@@ -263,5 +264,283 @@ extern "C" int sphb200_seam_shift(sphb200_context_t *ctx, void *base, uint32_t s
     SPH_CHECK_ARG(ctx, ctx && seam && (n == 0 || base) && stride_bytes >= 12 && stride_bytes % 4 == 0, "bad arguments");
     if (n == 0) return 0;
     SPH_LAUNCH(ctx, k_seam_shift, sph_blocks(n, 256), 256, 0, (cudaStream_t)stream, (char *)base, stride_bytes, n, delta, *seam);
+    return 0;
+}
+
+
+// =====================================================================================================
+// Peer mailboxes: migration and boundary planes written straight into the neighbour's memory (see sphb200.h)
+// =====================================================================================================
+namespace
+{
+constexpr int MAIL_MAX_VARS = 32;
+constexpr unsigned MAIL_HEADER = 64; // bytes: {u64 seq, u32 count}
+struct MailVars
+{
+    void *ptr[MAIL_MAX_VARS];  // push: source arrays; pull: destination arrays
+    u32 bytes[MAIL_MAX_VARS];  // element size
+    u64 offset[MAIL_MAX_VARS]; // byte offset of the variable's records inside the payload
+    int count;
+};
+struct MailIdentity
+{
+    cudaIpcMemHandle_t handle; // 64 bytes
+    u64 box_bytes;
+};
+
+__device__ __forceinline__ void copy_record(char *dst, const char *src, u32 bytes)
+{
+    if (bytes == 16) *(float4 *)dst = *(const float4 *)src;
+    else if (bytes == 4) *(u32 *)dst = *(const u32 *)src;
+    else
+        for (u32 w = 0; w < bytes; w += 4) *(u32 *)(dst + w) = *(const u32 *)(src + w);
+}
+
+// gather + remote store + release. Grid-stride over the list (its length lives in device memory).
+__global__ void __launch_bounds__(256)
+    k_mail_push(MailVars a, const u32 *__restrict__ idx, const u32 *__restrict__ n_dev, u32 capacity, char *box, u64 seq,
+                unsigned *ticket, unsigned *status)
+{
+    u32 n = *n_dev;
+    const bool overflow = n > capacity;
+    if (overflow) n = capacity;
+    char *payload = box + MAIL_HEADER;
+    for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+    {
+        const u32 p = idx[e];
+#pragma unroll 1
+        for (int k = 0; k < a.count; ++k)
+        {
+            const u32 b = a.bytes[k];
+            copy_record(payload + a.offset[k] + (u64)e * b, (const char *)a.ptr[k] + (u64)p * b, b);
+        }
+    }
+    __threadfence_system(); // this thread's remote stores are visible system-wide before its block takes a ticket
+    __syncthreads();
+    if (threadIdx.x == 0)
+    {
+        const unsigned t = atomicAdd(ticket, 1u);
+        if (t == gridDim.x - 1)
+        {
+            *ticket = 0; // ready for the next launch (stream ordered)
+            if (overflow) atomicOr(status, 1u);
+            __threadfence_system();
+            *(volatile u32 *)(box + 8) = overflow ? 0xffffffffu : n;
+            __threadfence_system();
+            *(volatile u64 *)box = seq; // release: the receiver polls this word
+        }
+    }
+}
+
+__device__ __forceinline__ u64 global_timer_ns()
+{
+    u64 t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// one thread polls the header of the local box until the neighbour has released `seq`
+__global__ void k_mail_wait(const char *box, u64 seq, u32 *count_dev, unsigned *status, u64 timeout_ns)
+{
+    const u64 t0 = global_timer_ns();
+    const volatile u64 *flag = (const volatile u64 *)box;
+    u32 n = 0;
+    bool ok = false;
+    for (;;)
+    {
+        if (*flag == seq)
+        {
+            ok = true;
+            break;
+        }
+        if (global_timer_ns() - t0 > timeout_ns) break;
+        __nanosleep(200);
+    }
+    __threadfence_system(); // acquire side: the payload reads of the following launch come after the flag read
+    if (ok)
+    {
+        n = *(const volatile u32 *)(box + 8);
+        if (n == 0xffffffffu)
+        {
+            atomicOr(status, 1u);
+            n = 0;
+        }
+    }
+    else
+        atomicOr(status, 2u);
+    *count_dev = n;
+}
+
+__global__ void __launch_bounds__(256)
+    k_mail_unpack(MailVars a, const char *box, const u32 *__restrict__ count_dev, u32 dst_begin, const u32 *__restrict__ extra_dev,
+                  u32 dst_end, unsigned *status)
+{
+    const u32 n = *count_dev;
+    const u64 base = (u64)dst_begin + (extra_dev ? *extra_dev : 0u);
+    const char *payload = box + MAIL_HEADER;
+    if (base + n > dst_end)
+    {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(status, 4u);
+        return; // nothing is written: the host raises the storage-exhausted error
+    }
+    for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n; e += gridDim.x * blockDim.x)
+    {
+#pragma unroll 1
+        for (int k = 0; k < a.count; ++k)
+        {
+            const u32 b = a.bytes[k];
+            copy_record((char *)a.ptr[k] + (base + e) * b, payload + a.offset[k] + (u64)e * b, b);
+        }
+    }
+}
+
+int mail_vars(sphb200_context *ctx, int count, void *const *ptr, const uint32_t *elem_bytes, size_t box_bytes, MailVars *out, u32 *capacity)
+{
+    SPH_CHECK_ARG(ctx, count > 0 && count <= MAIL_MAX_VARS, "1..32 variables per mailbox transfer");
+    u64 per_entry = 0;
+    for (int k = 0; k < count; ++k)
+    {
+        SPH_CHECK_ARG(ctx, ptr[k] && elem_bytes[k] >= 4 && elem_bytes[k] % 4 == 0, "null array or element size not a multiple of 4");
+        per_entry += elem_bytes[k];
+    }
+    SPH_CHECK_ARG(ctx, box_bytes > MAIL_HEADER + per_entry, "mailbox smaller than one entry");
+    // 16-byte aligned sections: capacity is a multiple of 4 entries
+    const u64 cap = ((box_bytes - MAIL_HEADER) / per_entry) & ~3ull;
+    SPH_CHECK_ARG(ctx, cap > 0, "mailbox smaller than four entries");
+    u64 off = 0;
+    out->count = count;
+    for (int k = 0; k < count; ++k)
+    {
+        out->ptr[k] = ptr[k];
+        out->bytes[k] = elem_bytes[k];
+        out->offset[k] = off;
+        off += cap * elem_bytes[k];
+    }
+    *capacity = (u32)(cap > 0xfffffff0ull ? 0xfffffff0ull : cap);
+    return 0;
+}
+inline int neighbour_rank(const sphb200_context *ctx, int side)
+{
+    int r = ctx->rank + (side ? 1 : -1);
+    if (ctx->ring) r = (r + ctx->nranks) % ctx->nranks;
+    return (r < 0 || r >= ctx->nranks) ? -1 : r;
+}
+} // namespace
+
+extern "C" int sphb200_comm_mailbox_open(sphb200_context_t *ctx, size_t box_bytes)
+{
+    SPH_CHECK_ARG(ctx, ctx && (ctx->comm || ctx->self_comm), "no communicator (call sphb200_comm_create)");
+    SPH_CHECK_ARG(ctx, !ctx->mailbox, "mailboxes are open already");
+    SPH_CHECK_ARG(ctx, box_bytes >= 4096, "box_bytes too small");
+    box_bytes = (box_bytes + 255) & ~(size_t)255;
+    SPH_CUDA(ctx, cudaSetDevice(ctx->device));
+    SPH_CUDA(ctx, cudaMalloc(&ctx->mailbox, 4 * box_bytes));
+    SPH_CUDA(ctx, cudaMemset(ctx->mailbox, 0, 4 * box_bytes)); // seq 0 is never used by a push
+    SPH_CUDA(ctx, cudaMalloc((void **)&ctx->mailbox_dev, 64));
+    SPH_CUDA(ctx, cudaMemset(ctx->mailbox_dev, 0, 64));
+    ctx->mailbox_box_bytes = box_bytes;
+    ctx->peer_mailbox[0] = ctx->peer_mailbox[1] = nullptr;
+    ctx->peer_mapped[0] = ctx->peer_mapped[1] = 0;
+    if (ctx->self_comm)
+    {
+        if (ctx->ring) // a ring of one slab: the rank is its own neighbour on both sides
+            for (int s = 0; s < 2; ++s) ctx->peer_mailbox[s] = ctx->mailbox, ctx->peer_box_bytes[s] = box_bytes;
+        return 0;
+    }
+    // identities of all ranks: IPC handle + box size, gathered through the communicator
+    const int n = ctx->nranks;
+    MailIdentity mine;
+    memset(&mine, 0, sizeof(mine));
+    SPH_CUDA(ctx, cudaIpcGetMemHandle(&mine.handle, ctx->mailbox));
+    mine.box_bytes = box_bytes;
+    char *d_all = nullptr;
+    SPH_CUDA(ctx, cudaMalloc((void **)&d_all, (size_t)(n + 1) * sizeof(MailIdentity)));
+    SPH_CUDA(ctx, cudaMemcpy(d_all + (size_t)n * sizeof(MailIdentity), &mine, sizeof(mine), cudaMemcpyHostToDevice));
+    SPH_NCCL(ctx, g_nccl.AllGather(d_all + (size_t)n * sizeof(MailIdentity), d_all, sizeof(MailIdentity), NCCL_UINT8, (nccl_comm_t)ctx->comm, 0));
+    SPH_CUDA(ctx, cudaStreamSynchronize(0));
+    MailIdentity *all = new MailIdentity[n];
+    cudaError_t e = cudaMemcpy(all, d_all, (size_t)n * sizeof(MailIdentity), cudaMemcpyDeviceToHost);
+    cudaFree(d_all);
+    if (e != cudaSuccess)
+    {
+        delete[] all;
+        SPH_CUDA(ctx, e);
+    }
+    for (int s = 0; s < 2 && e == cudaSuccess; ++s)
+    {
+        const int r = neighbour_rank(ctx, s);
+        if (r < 0) continue;
+        if (r == ctx->rank) ctx->peer_mailbox[s] = ctx->mailbox;
+        else if (s == 1 && r == neighbour_rank(ctx, 0)) ctx->peer_mailbox[1] = ctx->peer_mailbox[0]; // ring of two: one peer
+        else
+        {
+            e = cudaIpcOpenMemHandle(&ctx->peer_mailbox[s], all[r].handle, cudaIpcMemLazyEnablePeerAccess);
+            ctx->peer_mapped[s] = e == cudaSuccess;
+        }
+        ctx->peer_box_bytes[s] = all[r].box_bytes;
+    }
+    delete[] all;
+    if (e != cudaSuccess)
+    {
+        snprintf(ctx->err, sizeof(ctx->err), "sphb200_comm_mailbox_open: cudaIpcOpenMemHandle -> %s", cudaGetErrorString(e));
+        return (int)e;
+    }
+    return 0;
+}
+
+extern "C" int sphb200_comm_mailbox_close(sphb200_context_t *ctx)
+{
+    SPH_CHECK_ARG(ctx, ctx, "null context");
+    if (!ctx->mailbox) return 0;
+    cudaDeviceSynchronize();
+    for (int s = 0; s < 2; ++s)
+    {
+        if (ctx->peer_mapped[s] && ctx->peer_mailbox[s]) cudaIpcCloseMemHandle(ctx->peer_mailbox[s]);
+        ctx->peer_mailbox[s] = nullptr;
+        ctx->peer_mapped[s] = 0;
+    }
+    cudaFree(ctx->mailbox);
+    cudaFree(ctx->mailbox_dev);
+    ctx->mailbox = nullptr;
+    ctx->mailbox_dev = nullptr;
+    return 0;
+}
+
+extern "C" size_t sphb200_comm_mailbox_peer_bytes(const sphb200_context_t *ctx, int side)
+{
+    return ctx && ctx->mailbox && ctx->peer_mailbox[side ? 1 : 0] ? ctx->peer_box_bytes[side ? 1 : 0] : 0;
+}
+extern "C" const uint32_t *sphb200_comm_mailbox_status(const sphb200_context_t *ctx) { return ctx && ctx->mailbox_dev ? ctx->mailbox_dev + 2 : nullptr; }
+
+extern "C" int sphb200_comm_push(sphb200_context_t *ctx, int side, int count, const void *const *src, const uint32_t *elem_bytes,
+                                 const uint32_t *idx, const uint32_t *n_dev, uint64_t seq, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && ctx->mailbox && src && elem_bytes && idx && n_dev && seq > 0, "bad arguments (mailboxes open?)");
+    side = side ? 1 : 0;
+    SPH_CHECK_ARG(ctx, ctx->peer_mailbox[side], "no neighbour on that side");
+    MailVars a;
+    u32 capacity = 0;
+    int rc = mail_vars(ctx, count, (void *const *)src, elem_bytes, ctx->peer_box_bytes[side], &a, &capacity);
+    if (rc) return rc;
+    // what I send to my LEFT neighbour arrives "from the right" there (box 1), and the other way round
+    char *box = (char *)ctx->peer_mailbox[side] + ((size_t)(seq & 1ull) * 2 + (side ? 0 : 1)) * ctx->peer_box_bytes[side];
+    SPH_LAUNCH(ctx, k_mail_push, 148 * 4, 256, 0, stream, a, idx, n_dev, capacity, box, (u64)seq, ctx->mailbox_dev + side, ctx->mailbox_dev + 2);
+    return 0;
+}
+
+extern "C" int sphb200_comm_pull(sphb200_context_t *ctx, int side, int count, void *const *dst, const uint32_t *elem_bytes,
+                                 uint32_t dst_begin, const uint32_t *dst_extra_dev, uint32_t dst_end, uint32_t *count_dev,
+                                 uint64_t seq, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && ctx->mailbox && dst && elem_bytes && count_dev && seq > 0, "bad arguments (mailboxes open?)");
+    side = side ? 1 : 0;
+    SPH_CHECK_ARG(ctx, ctx->peer_mailbox[side], "no neighbour on that side");
+    MailVars a;
+    u32 capacity = 0;
+    int rc = mail_vars(ctx, count, dst, elem_bytes, ctx->mailbox_box_bytes, &a, &capacity);
+    if (rc) return rc;
+    const char *box = (const char *)ctx->mailbox + ((size_t)(seq & 1ull) * 2 + side) * ctx->mailbox_box_bytes;
+    SPH_LAUNCH(ctx, k_mail_wait, 1, 1, 0, stream, box, (u64)seq, count_dev, ctx->mailbox_dev + 2, (u64)20000000000ull);
+    SPH_LAUNCH(ctx, k_mail_unpack, 148 * 4, 256, 0, stream, a, box, (const u32 *)count_dev, dst_begin, dst_extra_dev, dst_end, ctx->mailbox_dev + 2);
     return 0;
 }

@@ -27,6 +27,14 @@ struct sphb200_context
     int rank, nranks;
     int ring;      // 1: the slab chain is closed (periodic along x): rank 0 and rank nranks-1 are neighbours
     int self_comm; // 1: communicator of ONE rank without NCCL (a ring of one slab: exchanges are device copies)
+    // peer mailboxes (comm.cu, sphb200_comm_mailbox_*): migrants and boundary planes are written straight into the
+    // neighbour's memory over NVLink (CUDA IPC mapping) by the kernel that gathers them; no host-known message sizes
+    void *mailbox;              // this rank's boxes: [parity 0/1][from-left, from-right], each `mailbox_box_bytes`
+    void *peer_mailbox[2];      // the left / right neighbour's boxes mapped into this process (nullptr: no neighbour)
+    int peer_mapped[2];         // 1: peer_mailbox[s] came from cudaIpcOpenMemHandle (to be closed)
+    size_t mailbox_box_bytes;   // bytes of one box of THIS rank (64-byte header + payload)
+    size_t peer_box_bytes[2];   // ... of the neighbours' boxes
+    unsigned *mailbox_dev;      // device words: [0..1] block tickets of the two push launches, [2] status flags
 };
 
 #define SPH_CHECK_ARG(ctx, cond, msg)                                                              \

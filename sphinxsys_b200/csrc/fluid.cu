@@ -19,6 +19,12 @@
 // launches per half step are fused wherever no neighbour reads the value being written.
 #include "common.cuh"
 
+// SPH_TRIM (tuning bit mask, scripts/gpu_variants.sh): 1 = wendland_dw with q folded into the scales, 2 = unit vector and
+// impedance folded out of the 2nd-half pair loop, 4 = InvImpedanceAve folded out of the 1st-half pair loop
+#ifndef SPH_TRIM
+#define SPH_TRIM 6 // measured (profiles/r02_kernel_variants.jsonl): bit 1 costs 4 % in k_a1_interact, bit 2 gains 1.6 % in k_a2, bit 4 is neutral
+#endif
+
 constexpr int FL_THREADS = 128;
 #ifndef SPH_FL_MIN_BLOCKS
 #define SPH_FL_MIN_BLOCKS 8
@@ -219,9 +225,16 @@ __device__ __forceinline__ float wendland_dw(const FArgs &a, float r)
     float m = u + MAGIC;
     float s = u - (m - MAGIC);
     float s2 = s * s;
+#if SPH_TRIM & 1
     float pi = fmaf(s2, s2 - 2.5f, 0.5625f); // (s2 - 9/4)(s2 - 1/4)
     float g = fmaf(r, a.inv_h, -2.0f);       // q - 2
     float poly = (g * g) * (g * (r * a.wl_dw_ah)); // 0.625 scale q (q - 2)^3
+#else
+    float q = r * a.inv_h;
+    float pi = (s2 - 2.25f) * (s2 - 0.25f);
+    float g = q - 2.0f;
+    float poly = (g * g) * (g * (q * a.wl_dw_a));
+#endif
     return fmaf(-a.wl_dw_c, pi, poly);
 }
 __device__ __forceinline__ float wendland_w(const FArgs &a, float r)
@@ -330,8 +343,13 @@ constexpr int NB_WALL_U = 2; // wall pairs need up to three records each: smalle
 template <int RIEMANN> __device__ __forceinline__ float pjump_over_z(const FArgs &a, float u)
 {
     if (RIEMANN == 0) return 0.f;
+#if SPH_TRIM & 2
     if (RIEMANN == 2) return u;
     return u * fminf(a.lim_k * fmaxf(u, 0.f), 1.f);
+#else
+    float lim = RIEMANN == 1 ? fminf(a.limiter * (a.inv_c_ave * fmaxf(u, 0.f)), 1.f) : 1.f;
+    return a.Z_geo * u * lim; // the complete DissipativePJump: the callers' factor is 1 then
+#endif
 }
 
 // =====================================================================================================
@@ -782,7 +800,11 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
                     float c = (p_i + p_j) * dWV * inv_r;
                     fx -= c * dx; fy -= c * dy; fz -= c * dz;
                 }
+#if SPH_TRIM & 4
                 if (RIEMANN) diss += (p_i - p_j) * dWV; // DissipativeUJump, :51-56 (its constant InvImpedanceAve: once per particle below)
+#else
+                if (RIEMANN) diss += (p_i - p_j) * a.inv_Z_ave * dWV; // DissipativeUJump, :51-56
+#endif
             });
     }
     float wx = 0.f, wy = 0.f, wz = 0.f, wdiss = 0.f;
@@ -832,7 +854,11 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
                 {
                     wx -= c * ex; wy -= c * ey; wz -= c * ez;
                 }
+#if SPH_TRIM & 4
                 if (RIEMANN) wdiss += (p_i - p_w) * dWV;
+#else
+                if (RIEMANN) wdiss += (p_i - p_w) * a.inv_Z_ave * dWV;
+#endif
                 });
         }
     }
@@ -841,8 +867,13 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
     F.x += wx * vol_i; F.y += wy * vol_i; F.z += wz * vol_i;
     a.force[i] = F;
     const float C_i = a.legacy ? a.rho[i] : a.C[i];
+#if SPH_TRIM & 4
     float cd = (diss * a.inv_Z_ave) * C_i;
     cd += (wdiss * a.inv_Z_ave) * C_i;
+#else
+    float cd = diss * C_i;
+    cd += wdiss * C_i;
+#endif
     a.Cdot[i] = cd;
     if (do_update)
     {
@@ -959,6 +990,7 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a2(FArgs a, KTab 
                 dWV = valid ? dWV : 0.f;
                 // AverageV (riemann_solver_ck.hpp:26-31) with Z_i == Z_j: 2 (v_i - v_ave) = v_i - v_j
                 float ux = vi.x - vj.x, uy = vi.y - vj.y, uz = vi.z - vj.z;
+#if SPH_TRIM & 2
                 // u = (v_i - v_j) . e_ij with e_ij = d / |d| folded into the scalars (one multiply instead of three)
                 float u = (ux * dx + uy * dy + uz * dz) * inv_r;
                 if (CORR)
@@ -970,9 +1002,24 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a2(FArgs a, KTab 
                     div += u * dWV;
                 float c = pjump_over_z<RIEMANN>(a, u) * (dWV * inv_r);
                 px += c * dx; py += c * dy; pz += c * dz;
+#else
+                float ex = dx * inv_r, ey = dy * inv_r, ez = dz * inv_r;
+                float u = ux * ex + uy * ey + uz * ez;
+                if (CORR)
+                {
+                    float3 ce = mat_vec(Bi, make_float3(ex, ey, ez));
+                    div += (ux * ce.x + uy * ce.y + uz * ce.z) * dWV;
+                }
+                else
+                    div += u * dWV;
+                float c = pjump_over_z<RIEMANN>(a, u) * dWV;
+                px += c * ex; py += c * ey; pz += c * ez;
+#endif
                 });
         }
+#if SPH_TRIM & 2
         px *= a.Z_geo; py *= a.Z_geo; pz *= a.Z_geo;
+#endif
         float wdiv = 0.f, wx = 0.f, wy = 0.f, wz = 0.f;
         if (a.n_wall)
         {
@@ -1012,7 +1059,9 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a2(FArgs a, KTab 
                 float c = pjump_over_z<RIEMANN>(a, u) * dWV;
                 wx += c * nx; wy += c * ny; wz += c * nz;
                 });
+#if SPH_TRIM & 2
             wx *= a.Z_geo; wy *= a.Z_geo; wz *= a.Z_geo;
+#endif
         }
         const float vol_i = xi.w;
         float C = a.legacy ? a.rho[i] : a.C[i];

@@ -96,6 +96,7 @@ extern "C"
         int32_t initial_cut_shift;       // decomposed runs: unbalanced start, interior cuts moved by so many planes (test hook)
         int32_t riemann;                 // 0 NoRiemannSolverCK, 1 AcousticRiemannSolverCK, 2 DissipativeRiemannSolverCK
         int32_t kernel_kind;             // 0 Wendland C2, 1 Laguerre-Gauss (tabulated, resetKernel)
+        int32_t full_wall;               // decomposed runs: 1 = every rank keeps the whole wall (default: its slab of it)
     };
 
     const char *sphck_last_error() { return g_error.c_str(); }
@@ -191,6 +192,7 @@ extern "C"
             q.correction = o->correction != 0;
             q.riemann = o->riemann;
             q.kernel_kind = o->kernel_kind;
+            q.wall_slabs = o->full_wall == 0;
             q.fused_time_step = o->fused_time_step != 0;
             q.fused_regularization = o->fused_regularization != 0;
             q.sort_interval = o->sort_interval;
@@ -331,6 +333,16 @@ extern "C"
         return body(h, which).TotalRealParticles();
     }
     uint64_t sphck_launches(void *) { return execution_instance().launches(); }
+    // BodyStatesRecordingToVtpCK::writeToFile of the dam-break case into `folder` (one .vtp per body); returns bytes synchronised
+    int sphck_record_states(void *hp, const char *folder, uint64_t *bytes_synchronized)
+    {
+        return guarded([&] {
+            Handle *h = (Handle *)hp;
+            if (!h->sim) throw SphError("record_states: dam-break cases only");
+            h->sim->recordStates(folder);
+            if (bytes_synchronized) *bytes_synchronized = h->sim->body_states_recording->bytesSynchronized();
+        });
+    }
     int sphck_synchronize(void *) { return guarded([] { execution_instance().synchronize(); }); }
 
     // mesh / kernel PODs as computed by the host layer (parity of the host arithmetic with the oracle's inputs)
@@ -464,7 +476,10 @@ extern "C"
             else if (op == "last_acoustic_dt") r = s.last_acoustic_dt;
             else if (op == "ghost_particles") r = s.decomposition ? (double)s.decomposition->ghostParticles() : 0.0;
             else if (op == "recuts") r = s.decomposition ? (double)s.decomposition->recuts() : 0.0;
-            else if (op == "rebuild") { if (s.decomposition) s.decomposition->rebuild(); else s.water_cell_linked_list->exec(); }
+            else if (op == "rebuild") { if (s.decomposition) s.decomposition->update(); else s.water_cell_linked_list->exec(); }
+            else if (op == "wall_slab_loads") r = s.wall_slab ? (double)s.wall_slab->loads() : 0.0;
+            else if (op == "wall_global_particles") r = s.wall_slab ? (double)s.wall_slab->globalParticles() : (double)s.wall_boundary.TotalRealParticles();
+            else if (op == "rebuild_host_syncs") r = s.decomposition ? (double)s.decomposition->hostSyncs() : 0.0;
             else if (op == "inner_total") r = (double)s.water_block_inner->total_;
             else if (op == "inner_pairs" || op == "contact_pairs")
             {

@@ -54,22 +54,44 @@ extern "C" int sphb200_update_sorted_id(sphb200_context_t *ctx, const uint32_t *
 // =====================================================================================================
 // cell-linked list
 // =====================================================================================================
+// Kernels of the cell-list build take the particle count either from the host (n_dev == nullptr) or from device memory
+// (n = min(n, *n_dev): slab-decomposed runs append arrivals whose number only the device knows, slab_decomposition.h).
+__device__ __forceinline__ u32 live_count(u32 n, const u32 *n_dev) { return n_dev ? min(n, *n_dev) : n; }
+
+// One pass: cell of every particle, its arrival rank inside the cell, the cell populations. Storage is cell ordered, so the
+// lanes of a warp fall into very few cells: the lanes of one cell are found with __match_any_sync and ONE of them adds the
+// group's size to the counter (warp-aggregated atomics: ~2 atomics per warp instead of 32 on the same two addresses).
 __global__ void __launch_bounds__(256)
-    k_cell_count(DMesh m, const float4 *__restrict__ pos, u32 n, u32 *__restrict__ counts, u32 *__restrict__ cell_of,
-                 u32 *__restrict__ rank)
+    k_cell_count(DMesh m, const float4 *__restrict__ pos, u32 n, const u32 *__restrict__ n_dev, u32 *__restrict__ counts,
+                 u32 *__restrict__ cell_of, u32 *__restrict__ rank)
 {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float4 x = pos[i];
-    u32 c = cell_linear(m, cell_coord(x.x, m.lx, m.spacing, m.cx), cell_coord(x.y, m.ly, m.spacing, m.cy),
+    n = live_count(n, n_dev);
+    const u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = i < n;
+    u32 c = 0xffffffffu; // lanes past the end form their own group and do nothing
+    if (live)
+    {
+        float4 x = pos[i];
+        c = cell_linear(m, cell_coord(x.x, m.lx, m.spacing, m.cx), cell_coord(x.y, m.ly, m.spacing, m.cy),
                         cell_coord(x.z, m.lz, m.spacing, m.cz));
-    cell_of[i] = c;
-    rank[i] = atomicAdd(&counts[c], 1u);
+    }
+    const u32 lane = threadIdx.x & 31u;
+    const u32 peers = __match_any_sync(0xffffffffu, c);
+    const u32 leader = __ffs(peers) - 1u;
+    u32 base = 0;
+    if (live && lane == leader) base = atomicAdd(&counts[c], (u32)__popc(peers));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (live)
+    {
+        cell_of[i] = c;
+        rank[i] = base + __popc(peers & ((1u << lane) - 1u));
+    }
 }
 __global__ void __launch_bounds__(256)
     k_cell_fill(const u32 *__restrict__ cell_offset, const u32 *__restrict__ cell_of, const u32 *__restrict__ rank, u32 n,
-                u32 *__restrict__ list)
+                const u32 *__restrict__ n_dev, u32 *__restrict__ list)
 {
+    n = live_count(n, n_dev);
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) list[cell_offset[cell_of[i]] + rank[i]] = i;
 }
@@ -77,9 +99,10 @@ __global__ void __launch_bounds__(256)
 // (sort_key == nullptr: the particle index itself). Keys must be unique within a cell.
 __global__ void __launch_bounds__(256)
     k_cell_order(const u32 *__restrict__ cell_offset, const u32 *__restrict__ cell_of, const u32 *__restrict__ unordered,
-                 const u32 *__restrict__ sort_key, u32 n, u32 *__restrict__ particle_index, const float4 *__restrict__ pos,
-                 float4 *__restrict__ sorted_pos)
+                 const u32 *__restrict__ sort_key, u32 n, const u32 *__restrict__ n_dev, u32 *__restrict__ particle_index,
+                 const float4 *__restrict__ pos, float4 *__restrict__ sorted_pos)
 {
+    n = live_count(n, n_dev);
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     u32 c = cell_of[i];
@@ -97,7 +120,7 @@ __global__ void __launch_bounds__(256)
 }
 
 static int cell_list_build(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, const sphb200_vec4_t *pos, uint32_t n,
-                           const uint32_t *sort_key, sphb200_cell_list_t list, void *stream)
+                           const uint32_t *n_dev, const uint32_t *sort_key, sphb200_cell_list_t list, void *stream)
 {
     SPH_CHECK_ARG(ctx, ctx && mesh && list.cell_offset && list.particle_index && (pos || n == 0), "null pointer");
     u64 cells = (u64)mesh->cells[0] * mesh->cells[1] * mesh->cells[2];
@@ -109,13 +132,13 @@ static int cell_list_build(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, c
     u32 *counts = (u32 *)p, *cell_of = counts + cells + 1, *rank = cell_of + n, *unordered = rank + n;
     SPH_CUDA(ctx, cudaMemsetAsync(counts, 0, (cells + 1) * sizeof(u32), st));
     DMesh m = make_dmesh(mesh);
-    if (n) SPH_LAUNCH(ctx, k_cell_count, sph_blocks(n, 256), 256, 0, st, m, (const float4 *)pos, n, counts, cell_of, rank);
+    if (n) SPH_LAUNCH(ctx, k_cell_count, sph_blocks(n, 256), 256, 0, st, m, (const float4 *)pos, n, n_dev, counts, cell_of, rank);
     rc = sph_scan_u32(ctx, counts, list.cell_offset, cells + 1, 0, st);
     if (rc) return rc;
     if (n)
     {
-        SPH_LAUNCH(ctx, k_cell_fill, sph_blocks(n, 256), 256, 0, st, list.cell_offset, cell_of, rank, n, unordered);
-        SPH_LAUNCH(ctx, k_cell_order, sph_blocks(n, 256), 256, 0, st, list.cell_offset, cell_of, unordered, sort_key, n,
+        SPH_LAUNCH(ctx, k_cell_fill, sph_blocks(n, 256), 256, 0, st, list.cell_offset, cell_of, rank, n, n_dev, unordered);
+        SPH_LAUNCH(ctx, k_cell_order, sph_blocks(n, 256), 256, 0, st, list.cell_offset, cell_of, unordered, sort_key, n, n_dev,
                    list.particle_index, (const float4 *)pos, (float4 *)list.sorted_pos);
     }
     return 0;
@@ -124,24 +147,66 @@ static int cell_list_build(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, c
 extern "C" int sphb200_cell_list_build(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, const sphb200_vec4_t *pos,
                                        uint32_t n, sphb200_cell_list_t list, void *stream)
 {
-    return cell_list_build(ctx, mesh, pos, n, nullptr, list, stream);
+    return cell_list_build(ctx, mesh, pos, n, nullptr, nullptr, list, stream);
 }
+
+int sph_gather_multi_n(sphb200_context_t *ctx, int count, void *const *dst, const void *const *src, const uint32_t *elem_bytes,
+                       const uint32_t *perm, uint32_t n, const uint32_t *n_dev, void *stream); // primitives.cu
 
 // UpdateCellLinkedList for a body whose STORAGE follows the cell order: builds the list from the
 // current positions, gathers every listed variable into its shadow buffer by the resulting permutation
 // (dst_k[slot] = src_k[particle_index[slot]]) and leaves particle_index = identity. In-cell order = ascending
 // sort_key (the reference particle id), so lists and sums do not depend on the storage history.
+extern "C" int sphb200_cell_list_build_reorder_n(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, const sphb200_vec4_t *pos,
+                                                 uint32_t n, const uint32_t *n_dev, const uint32_t *sort_key,
+                                                 sphb200_cell_list_t list, int count, void *const *dst, const void *const *src,
+                                                 const uint32_t *elem_bytes, void *stream)
+{
+    int rc = cell_list_build(ctx, mesh, pos, n, n_dev, sort_key, list, stream);
+    if (rc) return rc;
+    if (n == 0) return 0;
+    rc = sph_gather_multi_n(ctx, count, dst, src, elem_bytes, list.particle_index, n, n_dev, stream);
+    if (rc) return rc;
+    return sphb200_iota_u32(ctx, list.particle_index, n, stream);
+}
 extern "C" int sphb200_cell_list_build_reorder(sphb200_context_t *ctx, const sphb200_mesh_t *mesh, const sphb200_vec4_t *pos,
                                                uint32_t n, const uint32_t *sort_key, sphb200_cell_list_t list, int count,
                                                void *const *dst, const void *const *src, const uint32_t *elem_bytes,
                                                void *stream)
 {
-    int rc = cell_list_build(ctx, mesh, pos, n, sort_key, list, stream);
-    if (rc) return rc;
-    if (n == 0) return 0;
-    rc = sphb200_gather_multi(ctx, count, dst, src, elem_bytes, list.particle_index, n, stream);
-    if (rc) return rc;
-    return sphb200_iota_u32(ctx, list.particle_index, n, stream);
+    return sphb200_cell_list_build_reorder_n(ctx, mesh, pos, n, nullptr, sort_key, list, count, dst, src, elem_bytes, stream);
+}
+
+// Slab bookkeeping after a rebuild whose particle count lives on the device (slab_decomposition.h): out[0..k) = the cell
+// offsets at `cells[0..k)` (the plane boundaries of the slab), out[k] = *n_dev, out[k+1] = the mailbox status word (or 0);
+// own64[0] = out[own_hi] - out[own_lo] as a 64-bit word, ready for the all-gather of the ranks' own counts.
+__global__ void k_slab_bounds(const u32 *__restrict__ cell_offset, const u32 *__restrict__ cells, int k, const u32 *__restrict__ n_dev,
+                              const u32 *__restrict__ status, u32 *__restrict__ out, int own_lo, int own_hi, u64 *__restrict__ own64)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0)
+    {
+        for (int c = 0; c < k; ++c) out[c] = cell_offset[cells[c]];
+        out[k] = n_dev ? *n_dev : 0u;
+        out[k + 1] = status ? *status : 0u;
+        if (own64) own64[0] = (u64)(out[own_hi] - out[own_lo]);
+    }
+}
+__global__ void k_slab_total(u32 base, const u32 *a, const u32 *b, u32 *out) { *out = base + (a ? *a : 0u) + (b ? *b : 0u); }
+extern "C" int sphb200_slab_total(sphb200_context_t *ctx, uint32_t base, const uint32_t *a_dev, const uint32_t *b_dev, uint32_t *out_dev,
+                                  void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && out_dev, "null pointer");
+    SPH_LAUNCH(ctx, k_slab_total, 1, 1, 0, stream, base, a_dev, b_dev, out_dev);
+    return 0;
+}
+extern "C" int sphb200_slab_bounds(sphb200_context_t *ctx, const uint32_t *cell_offset, const uint32_t *cells_dev, int k,
+                                   const uint32_t *n_dev, int own_lo_hi, uint32_t *out_dev, uint64_t *own64_dev, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && cell_offset && cells_dev && out_dev && k > 0 && k <= 16, "bad arguments");
+    const int lo = own_lo_hi & 0xff, hi = (own_lo_hi >> 8) & 0xff;
+    SPH_CHECK_ARG(ctx, lo < k && hi < k, "own_lo_hi outside the cell list");
+    SPH_LAUNCH(ctx, k_slab_bounds, 1, 32, 0, stream, cell_offset, cells_dev, k, n_dev, sphb200_comm_mailbox_status(ctx), out_dev, lo, hi, own64_dev);
+    return 0;
 }
 
 // =====================================================================================================

@@ -543,8 +543,9 @@ struct GatherArgs
     int count;
 };
 
-__global__ void __launch_bounds__(256) k_gather_multi(GatherArgs a, const u32 *__restrict__ perm, u32 n)
+__global__ void __launch_bounds__(256) k_gather_multi(GatherArgs a, const u32 *__restrict__ perm, u32 n, const u32 *__restrict__ n_dev)
 {
+    if (n_dev) n = min(n, *n_dev); // count known on the device only (slab_decomposition.h)
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     u32 p = perm[i];
@@ -565,8 +566,8 @@ __global__ void __launch_bounds__(256) k_gather_multi(GatherArgs a, const u32 *_
     }
 }
 
-extern "C" int sphb200_gather_multi(sphb200_context_t *ctx, int count, void *const *dst, const void *const *src,
-                                    const uint32_t *elem_bytes, const uint32_t *perm, uint32_t n, void *stream)
+int sph_gather_multi_n(sphb200_context_t *ctx, int count, void *const *dst, const void *const *src, const uint32_t *elem_bytes,
+                       const uint32_t *perm, uint32_t n, const uint32_t *n_dev, void *stream)
 {
     SPH_CHECK_ARG(ctx, ctx && dst && src && elem_bytes && (perm || n == 0), "null pointer");
     SPH_CHECK_ARG(ctx, count >= 0, "negative count");
@@ -583,7 +584,12 @@ extern "C" int sphb200_gather_multi(sphb200_context_t *ctx, int count, void *con
             SPH_CHECK_ARG(ctx, a.dst[k] && a.src[k] && a.dst[k] != a.src[k], "gather needs distinct non-null dst/src");
             SPH_CHECK_ARG(ctx, a.bytes[k] >= 4 && a.bytes[k] % 4 == 0, "elem_bytes must be a multiple of 4");
         }
-        SPH_LAUNCH(ctx, k_gather_multi, sph_blocks(n, 256), 256, 0, stream, a, perm, n);
+        SPH_LAUNCH(ctx, k_gather_multi, sph_blocks(n, 256), 256, 0, stream, a, perm, n, n_dev);
     }
     return 0;
+}
+extern "C" int sphb200_gather_multi(sphb200_context_t *ctx, int count, void *const *dst, const void *const *src,
+                                    const uint32_t *elem_bytes, const uint32_t *perm, uint32_t n, void *stream)
+{
+    return sph_gather_multi_n(ctx, count, dst, src, elem_bytes, perm, n, nullptr, stream);
 }

@@ -32,7 +32,7 @@ class Options(C.Structure):
                 ("system_upper", C.c_double * 3), ("use_system_bounds", C.c_int32), ("legacy", C.c_int32), ("rank", C.c_int32),
                 ("nranks", C.c_int32), ("unique_id", C.c_uint8 * 128), ("surface_indicator", C.c_int32), ("observers", C.c_int32),
                 ("mu_f", C.c_double), ("transport_velocity", C.c_int32), ("serial_exchange", C.c_int32), ("recut_interval", C.c_int32), ("initial_cut_shift", C.c_int32),
-                ("riemann", C.c_int32), ("kernel_kind", C.c_int32)]
+                ("riemann", C.c_int32), ("kernel_kind", C.c_int32), ("full_wall", C.c_int32)]
 
 
 class TaylorGreenOptions(C.Structure):
@@ -64,6 +64,7 @@ def load():
         L.sphck_destroy.argtypes = [C.c_void_p]
         L.sphck_count.restype = C.c_uint64
         L.sphck_count.argtypes = [C.c_void_p, C.c_int]
+        L.sphck_record_states.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint64)]
         L.sphck_launches.restype = C.c_uint64
         L.sphck_launches.argtypes = [C.c_void_p]
         L.sphck_synchronize.argtypes = [C.c_void_p]
@@ -158,9 +159,10 @@ class DamBreakCK:
                  relation_stride=None, fused_regularization=True, dim=3, dp=0.05, generate=False, rank=0, nranks=1,
                  unique_id=None, width_scale=1.0, legacy=False, surface_indicator=False, observers=False, mu_f=0.0,
                  transport_velocity=False, serial_exchange=False, recut_interval=None, initial_cut_shift=0, riemann=1,
-                 kernel_kind=None):
+                 kernel_kind=None, full_wall=False):
         self.lib = load()
         o = Options()
+        o.full_wall = int(bool(full_wall))
         o.riemann = int(riemann)
         # the smoothing kernel follows the case the oracle gets unless stated (0 Wendland C2, 1 Laguerre-Gauss)
         o.kernel_kind = int(kernel_kind if kernel_kind is not None else (getattr(case.kernel, "kind", 0) if case is not None else 0))
@@ -289,6 +291,13 @@ class DamBreakCK:
         out = np.empty(shape, dtype=dt)
         self._check(self.lib.sphck_download_raw(self._h, 0, name.encode(), out.ctypes.data, b, c), f"download_raw {name}")
         return out[:, :3] if k == 1 else out
+
+    def record_states(self, folder) -> int:
+        """BodyStatesRecordingToVtpCK::writeToFile (device -> host sync of the write list + one .vtp per body); returns the
+        bytes synchronised so far."""
+        b = C.c_uint64(0)
+        self._check(self.lib.sphck_record_states(self._h, str(folder).encode(), C.byref(b)), "record_states")
+        return int(b.value)
 
     def state_digest(self):
         """(own particle count, particle_digest of (ReferenceID, Position, Velocity)) of this rank's own particles; the sum of

@@ -392,8 +392,9 @@ def test_multi_step_drift_variants(riemann, kernel):
 def test_config2_full_size_parity():
     """BASELINE config 2 at ITS OWN size (dp = 0.00625: 4,096,000 fluid + 3,034,688 wall — the benchmarked configuration)
     against the oracle: cell lists and both neighbour lists bit-exact (sets and order), then one full advection step of the
-    case loop (summation, ~5 acoustic steps, position update, configuration update) with every field within 1e-5 of its
-    max norm against the fp64 oracle, and the neighbour lists of the moved state bit-exact again."""
+    case loop (summation, ~5 acoustic steps, position update, configuration update) with every state field within 1e-5 of
+    its max norm against the fp64 oracle (the two rate fields: 1e-5 per acoustic step), and the neighbour lists of the moved
+    state bit-exact again."""
     from sphinxsys_b200 import cases
     case = cases.dam_break(dim=3, dp=0.00625)
     assert (case.n_fluid, case.n_wall) == (4_096_000, 3_034_688)
@@ -421,8 +422,12 @@ def test_config2_full_size_parity():
         o.exec("run_ck", 1e9, 1, 1e9, 100)
     assert int(o32.exec("acoustic_steps")) == n_ac and int(o64.exec("acoustic_steps")) == n_ac
     rep["acoustic_steps"] = n_ac
-    rep["fields"] = _compare(gpu, o32, o64, ["Density", "Compression", "CompressionRate", "Pressure", "VolumetricMeasure"],
-                             ["Position", "Velocity", "Force", "Displacement"], "config2_full_size_fields")
+    # state fields: 1e-5 of the field maximum after the whole advection step
+    rep["fields"] = _compare(gpu, o32, o64, ["Density", "Compression", "Pressure", "VolumetricMeasure"],
+                             ["Position", "Velocity", "Displacement"], "config2_full_size_fields")
+    # the two pair-sum RATES left behind by the last acoustic step (they feed the next one): BASELINE states 1e-5 per step, and
+    # n_ac acoustic steps lie behind them — the fp32 oracle itself is 1.3e-5 from the fp64 oracle here (reported next to it)
+    rep["rates"] = _compare(gpu, o32, o64, ["CompressionRate"], ["Force"], "config2_full_size_rates", tol=TOL * n_ac)
     e_gpu, e_ref = gpu.energy(), o64.exec("energy")
     assert abs(e_gpu - e_ref) <= 1e-5 * abs(e_ref)
     off, idx = gpu.export_csr()

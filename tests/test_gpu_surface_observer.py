@@ -226,3 +226,41 @@ def test_full_3d_case_file_pressure_probes_meet_reference_dtw():
     for k in range(6):
         assert min(d[k]) <= gold["dtw_threshold"][k], (k, d[k])
     assert max(de) <= egold["dtw_threshold"], de
+
+
+def test_body_states_recording_synchronises_the_write_list(tmp_path):
+    """BodyStatesRecordingToVtpCK (io_base_ck.hpp:12-45): writeToFile brings Position and the write list (dambreak.cpp:
+    141-145: NormalDirection of the wall; Density, Indicator, PositionDivergence of the water) from the device to the host
+    in the REFERENCE particle order right before the file is written. The .vtp content equals what download() returns."""
+    from sphinxsys_b200 import cases
+    from sphinxsys_b200.host import DamBreakCK
+    case = cases.dam_break(dim=3, dp=0.05)
+    gpu = DamBreakCK(case, surface_indicator=True, sort_interval=2)
+    gpu.initialize()
+    gpu.run_outer(3)  # one particle sort inside: the host order is the renumbered reference order, not the slot order
+    synced = gpu.record_states(tmp_path)
+    n_f, n_w = gpu.n_fluid, gpu.n_wall
+    assert synced == n_f * (12 + 4 + 4 + 4) + n_w * (12 + 12)
+
+    def arrays(path):
+        import re
+        txt = open(path).read()
+        out = {}
+        for m in re.finditer(r'<DataArray type="Float32"(?: Name="(\w+)")? NumberOfComponents="(\d)" format="ascii">\n(.*?)</DataArray>', txt, re.S):
+            out[m.group(1) or "Position"] = np.array(m.group(3).split(), dtype=np.float64).reshape(-1, int(m.group(2)))
+        return out
+
+    files = sorted(os.listdir(tmp_path))
+    assert len(files) == 2 and all(f.endswith("_0000000003.vtp") for f in files)
+    water = arrays(os.path.join(tmp_path, [f for f in files if f.startswith("WaterBody")][0]))
+    wall = arrays(os.path.join(tmp_path, [f for f in files if f.startswith("WallBoundary")][0]))
+    assert set(water) == {"Position", "Density", "Indicator", "PositionDivergence"} and set(wall) == {"Position", "NormalDirection"}
+    for nm in ("Position", "Density", "PositionDivergence"):
+        ref = gpu.download(nm).astype(np.float64).reshape(n_f, -1)
+        assert np.allclose(water[nm], ref, rtol=2e-8, atol=0)  # nine significant digits in the file
+    assert np.array_equal(water["Indicator"][:, 0], gpu.download("Indicator").astype(np.float64))
+    assert np.allclose(wall["NormalDirection"], gpu.download("NormalDirection", wall=True), rtol=2e-8, atol=1e-12)
+    # a second call writes the next state under the next iteration number
+    gpu.run_outer(1)
+    assert gpu.record_states(tmp_path) == 2 * synced
+    assert len(os.listdir(tmp_path)) == 4
