@@ -319,6 +319,7 @@ def run_ours(args, rank, world, local_rank):
                         rank=rank, nranks=world, unique_id=new_unique_id(), serial_exchange=args.serial_exchange, recut_interval=cadence)
     solver.initialize()
     n_wall = solver.n_wall
+    n_wall_global = int(solver.exec("wall_global_particles"))
     n_fluid = int(sum_over_ranks(solver.own_range()[1])[0]) if world > 1 else solver.n_fluid
 
     solver.run_outer(args.warmup)
@@ -543,8 +544,9 @@ def run_ours(args, rank, world, local_rank):
                        "acoustic_steps_per_outer": n_ac_per_outer, "sorts_in_timed_window": sorts_in_window, "sort_ms": sort_ms,
                        "l2_policy": "working set (~2 GB per GPU incl. neighbour lists) larger than L2, no flush",
                        "parallelism": "1 GPU" if world == 1 else
-                       f"{world} x-slabs of equal particle count on the global mesh, NCCL halo exchange of contiguous cell-plane ranges, "
-                       f"full wall copy per rank"},
+                       f"{world} x-slabs of equal particle count on the global mesh; halo refresh: NCCL send/recv of contiguous cell-plane "
+                       f"ranges; migration: peer-mailbox writes over NVLink (CUDA IPC); every rank stores its slab of the wall "
+                       f"(n_wall = rank 0's share of {n_wall_global})"},
             "roofline": roofline,
             "whole_step_hbm_frac": value / world * alg_bytes / 1e9 / peak,  # per GPU
             "algorithmic_bytes_per_particle_step": alg_bytes,
@@ -592,7 +594,8 @@ def config3_leg(args, rank, world, local_rank, torch, dist, new_unique_id, timed
     e3 = s3.energy()
     mem = torch.cuda.max_memory_allocated()  # torch's own share only; the library allocates with cudaMalloc
     free_b, total_b = torch.cuda.mem_get_info()
-    rec = {"dp": dp3, "n_fluid_global": int(n3), "n_wall": s3.n_wall, "n_fluid_per_gpu": int(n3) // world, "stored_per_gpu_max": int(stored_max),
+    rec = {"dp": dp3, "n_fluid_global": int(n3), "n_wall_global": int(s3.exec("wall_global_particles")), "n_wall_stored_rank0": s3.n_wall,
+           "rebuild_host_round_trips": int(s3.exec("rebuild_host_syncs")), "n_fluid_per_gpu": int(n3) // world, "stored_per_gpu_max": int(stored_max),
            "steps": k, "warmup": w, "ms_per_step": ms3 / k, "acoustic_steps_per_outer": n_ac3 / k,
            "value": n3 * n_ac3 / (ms3 * 1e-3), "unit": "particle-steps/s", "gpu_launches": int(l3), "setup_s": setup_s,
            "particles_after": int(tot), "energy": e3, "hbm_used_gb_rank0": (total_b - free_b) / 1e9, "_torch_peak": mem}
@@ -694,7 +697,18 @@ def main():
     else:
         if args.warmup < 3:
             args.warmup = 3
-        run_ours(args, rank, world, local_rank)
+        try:
+            run_ours(args, rank, world, local_rank)
+        except SystemExit:
+            raise
+        except BaseException:
+            # N > 1: a rank-local failure must not leave the peers waiting in a collective until some outer timeout
+            import traceback
+            traceback.print_exc()
+            sys.stderr.flush()
+            if world > 1:
+                os._exit(1)
+            raise
 
 
 if __name__ == "__main__":

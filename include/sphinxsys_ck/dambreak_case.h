@@ -271,7 +271,9 @@ class DamBreakCK
                     own.push_back(all[i]);
                     ids.push_back((UnsignedInt)i);
                 }
-            size_t bound = own.size() + own.size() / 4 + 8 * (size_t)max_plane + 4096;
+            // room for what re-cuts may bring: a rank that starts small (skewed cuts) ends with its fair share of the fluid
+            const size_t share = std::max(own.size(), all.size() / (size_t)q.nranks + 1);
+            size_t bound = share + share / 4 + 8 * (size_t)max_plane + 4096;
             water_block.generateParticlesFromPositions(own, vol, bound, &ids);
         }
         else if (fluid_positions) water_block.generateParticlesFromPositions(*fluid_positions, vol);

@@ -116,7 +116,9 @@ def main():
     n_ac = sim.run_outer(args.outer)
     mine = {"rid": sim.download_own("ReferenceID"), "pos": sim.download_own("Position"), "vel": sim.download_own("Velocity"),
             "rho": sim.download_own("Density"), "cuts0": cuts0, "n_ac": n_ac, "range": sim.own_range(), "cuts": sim.cuts().tolist(),
-            "energy": sim.energy(), "time": sim.physical_time, "recuts": sim.exec("recuts")}
+            "energy": sim.energy(), "time": sim.physical_time, "recuts": sim.exec("recuts"),
+            "wall_stored": int(sim.lib.sphck_count(sim._h, 1)), "wall_global": int(sim.exec("wall_global_particles")),
+            "wall_loads": int(sim.exec("wall_slab_loads")), "host_syncs": int(sim.exec("rebuild_host_syncs"))}
     if args.observers:
         mine["probes"] = sim.probe_records()[1]
     parts = [None] * world if rank == 0 else None
@@ -134,6 +136,10 @@ def main():
         report["cuts"] = parts[0]["cuts"]
         report["initial_cuts"] = parts[0]["cuts0"]
         report["recuts"] = int(parts[0]["recuts"])
+        # slabs of the wall: what every rank stores of the static wall and how often re-cuts made it reload its planes
+        report["wall_global"], report["wall_stored_per_rank"] = parts[0]["wall_global"], [p["wall_stored"] for p in parts]
+        report["wall_slab_loads_per_rank"] = [p["wall_loads"] for p in parts]
+        report["rebuild_host_round_trips_per_rank"] = [p["host_syncs"] for p in parts]
         report["acoustic_steps"] = [int(p["n_ac"]) for p in parts] + [int(n_ref)]
         ok &= rid.size == n and np.array_equal(np.sort(rid), np.arange(n, dtype=np.uint32))
         ok &= all(p["n_ac"] == n_ref for p in parts)
@@ -168,4 +174,12 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except SystemExit:
+        raise
+    except BaseException:  # a rank-local failure must not leave the peers waiting in a collective: die at once, loudly
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)

@@ -125,4 +125,12 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    try:
+        main()
+    except SystemExit:
+        raise
+    except BaseException:  # a rank-local failure must not leave the peers waiting in a collective: die at once, loudly
+        import traceback
+        traceback.print_exc()
+        sys.stderr.flush()
+        os._exit(1)
