@@ -103,6 +103,9 @@ int main(int ac, char *av[])
     ReduceDynamicsCK<MainExecutionPolicy, fluid_dynamics::AdvectionTimeStepCK> fluid_advection_time_step(water_block, U_f);
     ReduceDynamicsCK<MainExecutionPolicy, fluid_dynamics::AcousticTimeStepCK<WeaklyCompressibleFluid>> fluid_acoustic_time_step(water_block);
     ReduceDynamicsCK<MainExecutionPolicy, TotalMechanicalEnergyCK> record_water_mechanical_energy(water_block, gravity);
+    // NormalFromBodyShapeCK (dambreak.cpp:119,153): a host dynamics in the reference too; it registers NormalDirection,
+    // which the recording below puts on its write list
+    wall_boundary.computeNormalFromBodyShape();
     //	Define the methods for I/O operations, observations and regression tests (dambreak.cpp:141-145).
     BodyStatesRecordingToVtpCK<MainExecutionPolicy> body_states_recording(sph_system, output_folder);
     body_states_recording.setStateRecording(write_states);
@@ -113,7 +116,6 @@ int main(int ac, char *av[])
     ObservedQuantityRecording<MainExecutionPolicy, Real> fluid_observer_pressure(fluid_observer_contact, "Pressure");
     //	Prepare the simulation with cell linked list, configuration and case specified initial condition.
     SingleVariable<Real> *sv_physical_time = sph_system.getSystemVariableByName<Real>("PhysicalTime");
-    wall_boundary.computeNormalFromBodyShape(); // NormalFromBodyShapeCK, a host dynamics in the reference too
     constant_gravity.exec();
 
     water_cell_linked_list.exec();

@@ -13,6 +13,8 @@
 #ifndef SPHINXSYS_CK_BASE_H
 #define SPHINXSYS_CK_BASE_H
 
+#include <chrono>
+#include <map>
 #include <cmath>
 #include <cstdint>
 #include <cstdio>
@@ -138,6 +140,75 @@ class ExecutionInstance
     uint64_t launches() { return ctx_ ? sphb200_launch_count(ctx_) : 0; }
 };
 inline ExecutionInstance &execution_instance() { return ExecutionInstance::get(); }
+
+// SPHB200_STEP_TRACE=1: wall time of every named stage of a case loop, the device drained before and after each one
+// (a diagnosis mode: it serialises host and device, so the totals are not the run's speed). StepTrace::report() prints
+// the table; the case classes wrap their stages in SPHCK_STAGE("name", statement).
+class StepTrace
+{
+    std::map<std::string, std::pair<double, uint64_t>> ms_;
+    std::vector<std::string> order_;
+
+  public:
+    static bool enabled()
+    {
+        static const bool on = [] {
+            const char *e = std::getenv("SPHB200_STEP_TRACE");
+            return e && e[0] != '0' && e[0] != 0;
+        }();
+        return on;
+    }
+    static StepTrace &get()
+    {
+        static StepTrace t;
+        return t;
+    }
+    void add(const std::string &name, double ms)
+    {
+        auto it = ms_.find(name);
+        if (it == ms_.end())
+        {
+            order_.push_back(name);
+            ms_[name] = {ms, 1};
+        }
+        else
+        {
+            it->second.first += ms;
+            it->second.second++;
+        }
+    }
+    void report(std::ostream &out, uint64_t steps)
+    {
+        double total = 0;
+        for (auto &n : order_) total += ms_[n].first;
+        out << "SPHB200_STEP_TRACE over " << steps << " advection steps (device drained around every stage):\n";
+        for (auto &n : order_)
+            out << "  " << n << ": " << ms_[n].first / double(steps ? steps : 1) << " ms per step in " << double(ms_[n].second) / double(steps ? steps : 1)
+                << " calls (" << 100.0 * ms_[n].first / (total > 0 ? total : 1) << " %)\n";
+        out << "  total: " << total / double(steps ? steps : 1) << " ms per step" << std::endl;
+    }
+    void clear()
+    {
+        ms_.clear();
+        order_.clear();
+    }
+};
+#define SPHCK_STAGE(name, statement)                                                                              \
+    do                                                                                                            \
+    {                                                                                                             \
+        if (::SPH::StepTrace::enabled())                                                                          \
+        {                                                                                                         \
+            ::SPH::execution_instance().synchronize();                                                            \
+            auto t0__ = std::chrono::steady_clock::now();                                                         \
+            statement;                                                                                            \
+            ::SPH::execution_instance().synchronize();                                                            \
+            ::SPH::StepTrace::get().add(name, std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0__).count()); \
+        }                                                                                                         \
+        else                                                                                                      \
+        {                                                                                                         \
+            statement;                                                                                            \
+        }                                                                                                         \
+    } while (0)
 
 // Every library call made while the scope lives is issued on `stream` instead of the default stream (ordering against
 // the default stream is then the caller's business: events).

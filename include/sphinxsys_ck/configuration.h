@@ -256,15 +256,16 @@ template <class ExecutionPolicy, class... RelationTypes> class UpdateRelation : 
         ExecutionInstance &ex = execution_instance();
         for (RelationBase *r : relations_)
         {
-            sphb200_search_t s = r->search(); // creates pending periodic images first: they are stored particles too
+            sphb200_search_t s;
+            SPHCK_STAGE("  relation: search arguments (+ pending periodic images)", s = r->search()); // creates pending periodic images first: they are stored particles too
             uint32_t n = s.n_src;
             r->bank_aligned_ = r->fixed_stride_ && s.cell_ordered && bankAlignEnabled();
             if (r->fixed_stride_)
             {
                 uint64_t need = (uint64_t)((n + 31) / 32) * 32ull * r->fixed_stride_;
-                if (need > r->capacity_) r->grow(need);
+                if (need > r->capacity_) SPHCK_STAGE("  relation: grow the index array", r->grow(need));
                 uint32_t mx = 0;
-                SPHCK_CALL(sphb200_relation_build_fixed, &s, r->view(), r->fixed_stride_, &mx, ex.stream());
+                SPHCK_STAGE("  relation: one-pass build", SPHCK_CALL(sphb200_relation_build_fixed, &s, r->view(), r->fixed_stride_, &mx, ex.stream()));
                 r->max_count_ = mx;
                 r->total_ = need;
                 if (mx <= r->fixed_stride_) continue;

@@ -115,6 +115,12 @@ class WallSlab
         return (size_t)best;
     }
     int marginPlanes() const { return margin_; }
+    // wall particles the planes around the fluid planes [X0, X1) hold, margins included
+    size_t particlesAround(int X0, int X1) const
+    {
+        const int lo = std::max(0, X0 - depth_ - margin_), hi = std::min(planes_ - 1, X1 - 1 + depth_ + margin_);
+        return (size_t)(below_[hi + 1] - below_[lo]);
+    }
     // make sure the wall planes around the fluid planes [X0, X1) are stored; true if the subset was (re)loaded
     bool ensure(int X0, int X1)
     {
@@ -122,6 +128,13 @@ class WallSlab
         if (hi_ >= lo_ && need_lo >= lo_ && need_hi <= hi_) return false;
         lo_ = std::max(0, need_lo - margin_);
         hi_ = std::min(planes_ - 1, need_hi + margin_);
+        // the margin only saves reloads: give it up where the storage is too small for it
+        const size_t bound = wall_.getBaseParticles().ParticlesBound();
+        while ((size_t)(below_[hi_ + 1] - below_[lo_]) > bound && (lo_ < need_lo || hi_ > need_hi))
+        {
+            if (lo_ < need_lo) ++lo_;
+            if (hi_ > need_hi) --hi_;
+        }
         std::vector<Vecd> p, nrm;
         std::vector<UnsignedInt> ids;
         const size_t count = (size_t)(below_[hi_ + 1] - below_[lo_]);
@@ -289,7 +302,10 @@ class DamBreakCK
             // every rank owns about planes / nranks planes; re-cuts may widen a slab: room for twice that plus the margins
             const int width = std::min(wmesh.cells[0], 2 * (wmesh.cells[0] / q.nranks + 1) + 2 * (1 + 4) + 2);
             wall_slab.reset(new WallSlab(wall_boundary, wmesh, std::move(all_wall), std::move(all_normals), 1));
-            const size_t room = std::min(wall_slab->globalParticles(), wall_slab->largestWindow(width)) + 1024;
+            // ... and never less than a quarter more than the first slab needs: slabs are cut by particle count, so a rank
+            // downstream of the water column starts with a long, nearly empty range of planes (and most of the wall)
+            const size_t first = wall_slab->particlesAround(cuts[q.rank], cuts[q.rank + 1]);
+            const size_t room = std::min(wall_slab->globalParticles(), std::max(first + first / 4, wall_slab->largestWindow(width))) + 1024;
             std::vector<Vecd> none;
             wall_boundary.generateParticlesFromPositions(none, vol, room); // empty storage of that size; WallSlab::ensure fills it
             wall_boundary.registerWallVariables(nullptr);
@@ -545,7 +561,7 @@ class DamBreakCK
         // decomposed runs keep the initial global numbering (ParticleSortCK only renumbers: storage is cell ordered anyway)
         if (allow_sort && !decomposition && q_.sort_interval > 0 && number_of_iterations % q_.sort_interval == 0 && number_of_iterations != 1)
         {
-            particle_sort->exec();
+            SPHCK_STAGE("particle sort", particle_sort->exec());
             fluid_acoustic_time_step->setPrimed(false); // Force/ForcePrior pairing changed (see ParticleSortCK)
         }
         if (decomposition)
@@ -554,14 +570,14 @@ class DamBreakCK
             const bool recut = allow_sort && q_.recut_interval > 0 && number_of_iterations % q_.recut_interval == 0 && number_of_iterations != 1;
             if (recut)
             {
-                decomposition->recut();
+                SPHCK_STAGE("slab re-cut", decomposition->recut());
                 // the cuts moved: load the wall planes around the new slab if they are not stored yet, and list them
                 if (wall_slab && wall_slab->ensure(decomposition->cuts()[q_.rank], decomposition->cuts()[q_.rank + 1])) wall_cell_linked_list->exec();
             }
-            else decomposition->update();
+            else SPHCK_STAGE("slab rebuild (migration, ghost planes, cell list)", decomposition->update());
         }
-        else water_cell_linked_list->exec();
-        water_block_update_complex_relation->exec();
+        else SPHCK_STAGE("cell list", water_cell_linked_list->exec());
+        SPHCK_STAGE("relations", water_block_update_complex_relation->exec());
         if (fluid_observer_contact_relation)
         {
             fluid_observer_contact_relation->exec();
@@ -585,21 +601,22 @@ class DamBreakCK
             updateConfiguration(false);
             fluid_acoustic_time_step->setPrimed(false); // the state came from outside: no fused reduction to reuse
         }
-        fluid_density_summation->exec();
+        SPHCK_STAGE("density summation", fluid_density_summation->exec());
         if (!q_.fused_regularization) fluid_density_regularization->exec();
-        water_advection_step_setup->exec();
-        if (decomposition) decomposition->refreshGhosts({"VolumetricMeasure"}); // neighbours read V_j of ghost particles
+        SPHCK_STAGE("advection setup", water_advection_step_setup->exec());
+        if (decomposition) SPHCK_STAGE("ghost refresh (volume)", decomposition->refreshGhosts({"VolumetricMeasure"})); // neighbours read V_j of ghost particles
         if (fluid_viscous_force) fluid_viscous_force->exec(); // lid_driven_cavity_sycl.cpp:268-276
         if (kernel_gradient_integral)
         {
             kernel_gradient_integral->exec();
             transport_correction->exec();
         }
-        Real advection_dt = fluid_advection_time_step->exec();
-        if (fluid_boundary_indicator) fluid_boundary_indicator->exec();
+        Real advection_dt = 0;
+        SPHCK_STAGE("advection dt", advection_dt = fluid_advection_time_step->exec());
+        if (fluid_boundary_indicator) SPHCK_STAGE("free-surface indication", fluid_boundary_indicator->exec());
         if (q_.correction)
         {
-            fluid_linear_correction_matrix->exec();
+            SPHCK_STAGE("linear correction matrix", fluid_linear_correction_matrix->exec());
             // both half steps read B of the neighbours: the one refresh the correction variants add to a decomposed step
             // (tests/test_decomposed_oracle_cpu.py::test_dam_break_correction_variants_bit_identical)
             if (decomposition) decomposition->refreshGhosts({"LinearCorrectionMatrix"});
@@ -608,9 +625,9 @@ class DamBreakCK
         int n_inner = 0;
         while (relaxation_time < advection_dt)
         {
-            acoustic_dt = fluid_acoustic_time_step->exec(); // global max when decomposed
+            SPHCK_STAGE("acoustic dt", acoustic_dt = fluid_acoustic_time_step->exec()); // global max when decomposed
             if (decomposition && q_.overlap_exchange)
-                acousticStepOverlapped(acoustic_dt);
+                SPHCK_STAGE("acoustic step (overlapped exchange)", acousticStepOverlapped(acoustic_dt));
             else if (decomposition)
             {
                 // the two neighbour-read variables of the half steps are refreshed on the ghost planes in between
@@ -622,8 +639,8 @@ class DamBreakCK
             }
             else
             {
-                fluid_acoustic_step_1st_half->exec(acoustic_dt);
-                fluid_acoustic_step_2nd_half->exec(acoustic_dt);
+                SPHCK_STAGE("1st half", fluid_acoustic_step_1st_half->exec(acoustic_dt));
+                SPHCK_STAGE("2nd half", fluid_acoustic_step_2nd_half->exec(acoustic_dt));
             }
             relaxation_time += acoustic_dt;
             physical_time += acoustic_dt;
@@ -631,7 +648,7 @@ class DamBreakCK
             ++n_inner;
         }
         acoustic_steps += n_inner;
-        water_update_particle_position->exec();
+        SPHCK_STAGE("update position", water_update_particle_position->exec());
         number_of_iterations++;
         if (configuration_update == ConfigurationUpdate::AfterDynamics) updateConfiguration(true);
         last_acoustic_dt = acoustic_dt;

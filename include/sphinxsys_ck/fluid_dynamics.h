@@ -256,8 +256,8 @@ class FluidDynamicsBase
     {
         sphb200_fluid_args_t a;
         std::memset(&a, 0, sizeof(a));
-        if (sph_body_.periodicImages()) sph_body_.periodicImages()->ensure();
-        sph_body_.refreshPosVol();
+        if (sph_body_.periodicImages()) SPHCK_STAGE("  args: pending periodic images", sph_body_.periodicImages()->ensure());
+        SPHCK_STAGE("  args: gather records", sph_body_.refreshPosVol());
         a.fluid = fluidView();
         a.material = material();
         if (inner_)
@@ -432,7 +432,7 @@ template <> class CompressionSummation<Inner<>, Contact<>> : public FluidDynamic
                 remaining.push_back(d);
         }
         sphb200_fluid_args_t a = fluidArgs();
-        SPHCK_CALL(sphb200_compression_summation, &a, regularize, execution_instance().stream());
+        SPHCK_STAGE("  summation: launch", SPHCK_CALL(sphb200_compression_summation, &a, regularize, execution_instance().stream()));
         return remaining;
     }
 };
@@ -456,7 +456,7 @@ template <> class CompressionSummation<Inner<>> : public FluidDynamicsBase
                 remaining.push_back(d);
         }
         sphb200_fluid_args_t a = fluidArgs();
-        SPHCK_CALL(sphb200_compression_summation, &a, regularize, execution_instance().stream());
+        SPHCK_STAGE("  summation: launch", SPHCK_CALL(sphb200_compression_summation, &a, regularize, execution_instance().stream()));
         return remaining;
     }
 };

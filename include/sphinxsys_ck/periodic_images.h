@@ -155,8 +155,9 @@ class PeriodicImages
         sphb200_periodic_t b = box_;
         b.axes = armed_axes_;
         uint32_t count = 0;
-        int rc = sphb200_periodic_images(ex.ctx(), &b, (const sphb200_vec4_t *)p.deviceData<Vecd>("Position"), n_real_,
-                                         tmp_pos_.get<sphb200_vec4_t>(), tmp_src_.get<uint32_t>(), capacity, &count, ex.stream());
+        int rc = 0;
+        SPHCK_STAGE("    images: enumerate", rc = sphb200_periodic_images(ex.ctx(), &b, (const sphb200_vec4_t *)p.deviceData<Vecd>("Position"), n_real_,
+                                                                        tmp_pos_.get<sphb200_vec4_t>(), tmp_src_.get<uint32_t>(), capacity, &count, ex.stream()));
         if (rc == SPHB200_E_CAPACITY)
             throw SphError("ghost particles exceed the reserve: " + std::to_string(count) + " > " + std::to_string(capacity)); // checkWithinGhostSize
         ex.check(rc, "sphb200_periodic_images");
@@ -170,8 +171,8 @@ class PeriodicImages
             void *dst[2] = {pos_tail, ghost_src_.get()};
             const void *src[2] = {tmp_pos_.get(), tmp_src_.get()};
             uint32_t eb[2] = {16, 4};
-            SPHCK_CALL(sphb200_cell_list_build_reorder, &cl.mesh_, tmp_pos_.get<sphb200_vec4_t>(), n_ghost_, tmp_src_.get<uint32_t>(),
-                       listView(), 2, dst, src, eb, ex.stream());
+            SPHCK_STAGE("    images: cell list", SPHCK_CALL(sphb200_cell_list_build_reorder, &cl.mesh_, tmp_pos_.get<sphb200_vec4_t>(), n_ghost_, tmp_src_.get<uint32_t>(),
+                                                             listView(), 2, dst, src, eb, ex.stream()));
         }
         // every other stored variable: copy of the source particle (BaseParticles::updateGhostParticle)
         if (n_ghost_)

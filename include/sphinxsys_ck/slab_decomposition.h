@@ -525,7 +525,7 @@ class SlabDecomposition
         // ring: a particle that left over the seam stays here as a ghost with the x it had on THIS side of the box, while
         // every later refresh delivers fl(fl(x -/+ L) +/- L) from its new owner. Bring Position on the ghost planes to the
         // owner's value right away, so that the relation build, the summation and both half steps see ONE position.
-        if (check_planes && ring_.on) refreshGhosts({"Position"});
+        if (check_planes && ring_.on && !std::getenv("SPHB200_NO_RING_POSITION_REFRESH")) refreshGhosts({"Position"});
         // 5. slot origin: the slot the first stored particle has in the undecomposed run = particles owned by the ranks
         //    below minus the left ghost plane. Relations against bodies that are NOT decomposed (the wall) lay their rows
         //    out relative to it, so that summation order does not depend on the decomposition (sphb200_relation_t::bank_aligned).

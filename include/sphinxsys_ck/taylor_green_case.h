@@ -229,12 +229,12 @@ class TaylorGreenCK
     void updateConfiguration(bool bounding)
     {
         if (bounding)
-            for (auto &pc : periodic_condition) pc->bounding_.exec();
+            for (auto &pc : periodic_condition) SPHCK_STAGE("periodic bounding", pc->bounding_.exec());
         // ring: x is bounded by migration (what leaves the box over the seam arrives shifted on the other side)
-        if (decomposition) decomposition->rebuild();
-        else water_cell_linked_list->exec();
-        for (auto &pc : periodic_condition) pc->ghost_creation_.exec();
-        water_block_update_inner_relation->exec();
+        if (decomposition) SPHCK_STAGE("slab rebuild (migration, ghost planes, cell list)", decomposition->rebuild());
+        else SPHCK_STAGE("cell list", water_cell_linked_list->exec());
+        for (auto &pc : periodic_condition) SPHCK_STAGE("ghost creation", pc->ghost_creation_.exec());
+        SPHCK_STAGE("relation", water_block_update_inner_relation->exec());
     }
     void initialize()
     {
@@ -245,10 +245,10 @@ class TaylorGreenCK
     // one advection step; returns the number of acoustic sub-steps taken
     int stepOuter()
     {
-        fluid_density_summation->exec();
+        SPHCK_STAGE("density summation", fluid_density_summation->exec());
         if (!q_.fused_regularization) fluid_density_regularization->exec();
-        water_advection_step_setup->exec();
-        volume_ghost_update->exec(); // neighbours read V_j of the images
+        SPHCK_STAGE("advection setup", water_advection_step_setup->exec());
+        SPHCK_STAGE("volume ghost update", volume_ghost_update->exec()); // neighbours read V_j of the images
         // viscous force, kernel gradient integral, transport correction: order of lid_driven_cavity_sycl.cpp:268-276
         if (viscous_force) viscous_force->exec();
         if (kernel_gradient_integral)
@@ -256,21 +256,22 @@ class TaylorGreenCK
             kernel_gradient_integral->exec();
             transport_velocity_correction->exec();
         }
-        Real advection_dt = fluid_advection_time_step->exec();
+        Real advection_dt = 0;
+        SPHCK_STAGE("advection dt", advection_dt = fluid_advection_time_step->exec());
         Real relaxation_time = 0, acoustic_dt = 0;
         int n_inner = 0;
         while (relaxation_time < advection_dt)
         {
-            acoustic_dt = fluid_acoustic_time_step->exec();
-            fluid_acoustic_step_1st_half->exec(acoustic_dt); // initialize -> ghost pressure -> interact + update
-            fluid_acoustic_step_2nd_half->exec(acoustic_dt); // ghost velocity -> one fused launch
+            SPHCK_STAGE("acoustic dt", acoustic_dt = fluid_acoustic_time_step->exec());
+            SPHCK_STAGE("1st half (+ghost pressure)", fluid_acoustic_step_1st_half->exec(acoustic_dt)); // initialize -> ghost pressure -> interact + update
+            SPHCK_STAGE("2nd half (+ghost velocity)", fluid_acoustic_step_2nd_half->exec(acoustic_dt)); // ghost velocity -> one fused launch
             relaxation_time += acoustic_dt;
             physical_time += acoustic_dt;
             sv_physical_time->incrementValue(acoustic_dt);
             ++n_inner;
         }
         acoustic_steps += n_inner;
-        water_update_particle_position->exec();
+        SPHCK_STAGE("update position", water_update_particle_position->exec());
         number_of_iterations++;
         if (!decomposition && q_.sort_interval > 0 && number_of_iterations % q_.sort_interval == 0 && number_of_iterations != 1)
         {

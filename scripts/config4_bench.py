@@ -72,6 +72,8 @@ for mode in modes:
     n_ac = gpu.run_outer(steps)
     gpu.synchronize()
     dt = time.perf_counter() - t1
+    if rank == 0:
+        gpu.step_trace_report(steps + 2)  # SPHB200_STEP_TRACE=1 only
     if dist:
         every = [None] * world
         dist.all_gather_object(every, dt)

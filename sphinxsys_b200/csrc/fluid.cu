@@ -311,8 +311,27 @@ __device__ __forceinline__ void load_mat(const float *B, u32 i, float *out)
 #define SPH_NB_U 4
 #endif
 constexpr int NB_U = SPH_NB_U;
-template <int U = NB_U, class Gather, class Compute>
-__device__ __forceinline__ void for_neighbors(const u32 *__restrict__ idx, u32 cnt, Gather gather, Compute compute)
+// SPH_PREFETCH (tuning, scripts/gpu_variants.sh): 1 = prefetch.global.L2, 2 = prefetch.global.L1 of the NEXT batch's records
+// as soon as its indices have arrived (costs no registers: hides part of the gather latency the 4-deep batches leave)
+#ifndef SPH_PREFETCH
+#define SPH_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_record(const void *p)
+{
+#if SPH_PREFETCH == 1
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#elif SPH_PREFETCH == 2
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
+struct NoPrefetch
+{
+    __device__ __forceinline__ void operator()(u32) const {}
+};
+template <int U = NB_U, class Gather, class Compute, class Prefetch = NoPrefetch>
+__device__ __forceinline__ void for_neighbors(const u32 *__restrict__ idx, u32 cnt, Gather gather, Compute compute, Prefetch prefetch = Prefetch())
 {
     if (cnt == 0) return;
     const u32 last = cnt - 1u;
@@ -326,6 +345,10 @@ __device__ __forceinline__ void for_neighbors(const u32 *__restrict__ idx, u32 c
         for (int u = 0; u < U; ++u) jn[u] = idx[32ull * min(k + U + (u32)u, last)];
 #pragma unroll
         for (int u = 0; u < U; ++u) gather(u, j[u]);
+#if SPH_PREFETCH
+#pragma unroll
+        for (int u = 0; u < U; ++u) prefetch(jn[u]);
+#endif
 #pragma unroll
         for (int u = 0; u < U; ++u) compute(u, k + (u32)u < cnt);
 #pragma unroll
@@ -805,7 +828,8 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
 #else
                 if (RIEMANN) diss += (p_i - p_j) * a.inv_Z_ave * dWV; // DissipativeUJump, :51-56
 #endif
-            });
+            },
+            [&](u32 j) { prefetch_record(a.posvol + j); });
     }
     float wx = 0.f, wy = 0.f, wz = 0.f, wdiss = 0.f;
     const float vol_i = xi.w;
@@ -1015,7 +1039,8 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a2(FArgs a, KTab 
                 float c = pjump_over_z<RIEMANN>(a, u) * dWV;
                 px += c * ex; py += c * ey; pz += c * ez;
 #endif
-                });
+                },
+                [&](u32 j) { prefetch_record(a.rec2 + 2ull * j); });
         }
 #if SPH_TRIM & 2
         px *= a.Z_geo; py *= a.Z_geo; pz *= a.Z_geo;

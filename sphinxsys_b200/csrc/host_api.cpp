@@ -344,6 +344,15 @@ extern "C"
         });
     }
     int sphck_synchronize(void *) { return guarded([] { execution_instance().synchronize(); }); }
+    // SPHB200_STEP_TRACE=1: print the per-stage table gathered so far (over `steps` advection steps) and start afresh
+    int sphck_step_trace_report(uint64_t steps)
+    {
+        return guarded([&] {
+            if (!StepTrace::enabled()) return;
+            StepTrace::get().report(std::cerr, steps);
+            StepTrace::get().clear();
+        });
+    }
 
     // mesh / kernel PODs as computed by the host layer (parity of the host arithmetic with the oracle's inputs)
     int sphck_mesh(void *hp, int which, sphb200_mesh_t *out)

@@ -299,6 +299,11 @@ class DamBreakCK:
         self._check(self.lib.sphck_record_states(self._h, str(folder).encode(), C.byref(b)), "record_states")
         return int(b.value)
 
+    def step_trace_report(self, steps):
+        """SPHB200_STEP_TRACE=1: print the per-stage wall-time table of the case loop to stderr and reset it."""
+        self.lib.sphck_step_trace_report.argtypes = [C.c_uint64]
+        self._check(self.lib.sphck_step_trace_report(int(steps)), "step_trace_report")
+
     def state_digest(self):
         """(own particle count, particle_digest of (ReferenceID, Position, Velocity)) of this rank's own particles; the sum of
         the digests over the ranks (mod 2^64) equals the digest of the same state held by one GPU."""

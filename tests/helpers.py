@@ -66,3 +66,17 @@ def dtw_distance(a, b, window=5):
         for j in range(max(1, i - w), min(lb, i + w)):
             D[i, j] = abs(a[i] - b[j]) + min(D[i - 1, j], D[i, j - 1], D[i - 1, j - 1])
     return float(D[la - 1, lb - 1])
+
+
+def lists_on_oracle_positions(gpu, o32, periodic=False):
+    """Neighbour lists of the END state of a multi-step run, on IDENTICAL inputs: after many steps the two fp32 paths differ
+    by rounding (a few 1e-7 in position), so a pair that sits within that distance of the cut-off may be a neighbour on one
+    side and not on the other — with 10^5..10^8 pairs some always do. The bar is bit-exact sets on the same inputs: hand the
+    oracle's end positions to the GPU path (reference particle order), rebuild cell list + relation there, then compare."""
+    gpu.upload("Position", oracle_field(o32, "Position", 3))
+    if periodic:
+        gpu.exec("update_configuration", 0.0)  # cell list, periodic images, relation (positions are bounded already)
+    else:
+        gpu.exec("cell_list_fluid")
+        gpu.exec("relations")
+    return gpu.export_csr()
