@@ -254,6 +254,28 @@ def time_stream_kernels(solver, torch, n_own, peak, peak_kind, sm_mhz, counters)
     return roofline, (ms_a1, ms_a2)
 
 
+def bind_near_gpu(torch, index):
+    """N > 1: run this rank (and allocate its pinned host buffers: first touch) on the NUMA node its GPU hangs off, so that
+    the host <-> device copies of the e2e path do not cross the socket interconnect. Returns the node or None."""
+    try:
+        p = torch.cuda.get_device_properties(index)
+        path = f"/sys/bus/pci/devices/{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= set(os.sched_getaffinity(0))
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def run_ours(args, rank, world, local_rank):
     import ctypes as C
 
@@ -265,6 +287,7 @@ def run_ours(args, rank, world, local_rank):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — libsphb200 has no CPU path (use --impl reference for the CPU oracle)")
     torch.cuda.set_device(local_rank)
+    numa_node = bind_near_gpu(torch, local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
@@ -417,8 +440,9 @@ def run_ours(args, rank, world, local_rank):
     n_own = solver.own_range()[1]  # the own set as it is NOW (migration and re-cuts during the timed steps changed it)
 
     def pinned_like(name):
-        # single GPU: the reference's packed layout in reference particle order; decomposed: this rank's own slots raw
-        w = (4 if decomposed else 3) if name in host.VEC_NAMES else 1
+        # the reference's packed layout (Vecd = 3 floats). Single GPU: reference particle order; decomposed: this rank's own
+        # particles in slot order (room for a quarter more: the own set may grow)
+        w = 3 if name in host.VEC_NAMES else 1
         rows = n_own + n_own // 4 if decomposed else n_fluid
         tns = torch.empty((rows, w) if w > 1 else (rows,), dtype=torch.float32).pin_memory()
         return tns, tns.numpy()
@@ -429,35 +453,25 @@ def run_ours(args, rank, world, local_rank):
     def fetch_inputs():
         for nm in in_names:
             if decomposed:
-                solver.download_own_into(nm, host_in[nm][1])
+                host_in[nm][1][:n_own] = solver.download_own(nm)
             else:
                 solver.download(nm, out=host_in[nm][1])
 
     fetch_inputs()
-    per = lambda nm, vecw: (vecw if nm in host.VEC_NAMES else 1) * 4
-    h2d = sum(per(nm, 4 if decomposed else 3) * (n_own if decomposed else n_fluid) for nm in in_names)
-    d2h = sum(per(nm, 4 if decomposed else 3) * (n_own if decomposed else n_fluid) for nm in out_names)
+    per = lambda nm: (3 if nm in host.VEC_NAMES else 1) * 4
+    h2d = sum(per(nm) * (n_own if decomposed else n_fluid) for nm in in_names)
+    d2h = sum(per(nm) * (n_own if decomposed else n_fluid) for nm in out_names)
     h2d_own, d2h_own = h2d, d2h
     if decomposed:
         h2d, d2h = (int(v) for v in sum_over_ranks(h2d, d2h))
 
     def e2e_step():
-        if decomposed:
-            for nm in in_names:
-                solver.upload_own(nm, host_in[nm][1])   # own slots, storage order, from pinned memory
-        else:
-            for nm in in_names:
-                solver.upload(nm, host_in[nm][1])       # DiscreteVariable::synchronizeToDevice (reference order)
+        # the synchronous spelling, single GPU only: DiscreteVariable::synchronizeToDevice / synchronizeWithDevice per variable
+        for nm in in_names:
+            solver.upload(nm, host_in[nm][1])
         n = solver.step_outer()                         # configuration update (cell list, relations) FIRST, then the dynamics
-        if decomposed:
-            for nm in out_names:
-                solver.download_own_into(nm, host_out[nm][1])
-            # the configuration update ran at the START of the step on the uploaded state, so the rank still owns exactly
-            # the particles of its host buffers (nothing migrated since): the same buffers are the next step's inputs
-            assert solver.own_range()[1] == n_own, "own set changed during an e2e step"
-        else:
-            for nm in out_names:
-                solver.download(nm, out=host_out[nm][1])  # DiscreteVariable::synchronizeWithDevice
+        for nm in out_names:
+            solver.download(nm, out=host_out[nm][1])
         return n
 
     k_e2e = max(3, min(args.steps, 10))
@@ -508,20 +522,23 @@ def run_ours(args, rank, world, local_rank):
     transfer_only(4)
     barrier()
     sec_copy, = max_over_ranks((time.perf_counter() - t2) / 4)
-    # the synchronous spelling (one blocking copy per variable: DiscreteVariable::synchronizeToDevice / WithDevice) for comparison
-    e2e_step()
-    barrier()
-    t1 = time.perf_counter()
-    n_sync = sum(e2e_step() for _ in range(3))
-    barrier()
-    sec_sync, = max_over_ranks(time.perf_counter() - t1)
     sec, = max_over_ranks(sec)
+    sync_note = ""
+    if not decomposed:
+        # the synchronous spelling (one blocking copy per variable) for comparison
+        e2e_step()
+        barrier()
+        t1 = time.perf_counter()
+        n_sync = sum(e2e_step() for _ in range(3))
+        barrier()
+        sec_sync = time.perf_counter() - t1
+        sync_note = f"; synchronous per-variable spelling: {n_fluid * float(n_sync) / sec_sync:.4g} particle-steps/s"
     e2e_note = ("per step: H2D of all evolving variables from pinned host memory (" +
                 ("this rank's own particles in slot order" if decomposed else "reference particle order") +
-                "), cell-list + relation rebuild" + (" with migration and ghost-plane exchange" if decomposed else "") +
+                ", Vecd packed as 3 floats), cell-list + relation rebuild" + (" with migration and ghost-plane exchange" if decomposed else "") +
                 ", one outer step, D2H of Position/Velocity/Density; copies run on a side stream and overlap the neighbouring steps' "
-                "dynamics (HostTransferPipeline); synchronous per-variable spelling: "
-                f"{n_fluid * float(n_sync) / sec_sync:.4g} particle-steps/s")
+                "dynamics (HostTransferPipeline)" + sync_note +
+                (f"; rank bound to NUMA node {numa_node} of its GPU" if numa_node is not None else ""))
     tot = n_fluid * float(n_ac_e2e)
     e2e = {"value": tot / sec, "unit": "particle-steps/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
            "steps": k_e2e, "ms_per_step": 1e3 * sec / k_e2e,

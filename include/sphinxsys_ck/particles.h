@@ -416,9 +416,10 @@ class HostTransferPipeline
     };
     BaseParticles &p_;
     std::vector<std::unique_ptr<Item>> ins_, outs_;
-    // slab-decomposed bodies: the host holds THIS RANK's own particles in storage (slot) order and in the device element
-    // layout (Vecd = 4 floats) — what SlabDecomposition hands out with the ReferenceID array; the copies go straight
-    // between the pinned buffers and the own slot range [activeBegin, activeEnd), no reordering passes
+    // slab-decomposed bodies: the host holds THIS RANK's own particles in storage (slot) order — what SlabDecomposition
+    // hands out with the ReferenceID array — in the reference's packed layout (Vecd = 3 floats: a quarter fewer bytes over
+    // PCIe than the device's float4); the copies go between the pinned buffers and the own slot range
+    // [activeBegin, activeEnd) with the 3 <-> 4 conversion on the device, no reordering passes
     bool raw_own_slots_ = false;
     void *copy_stream_ = nullptr, *ev_h2d_ = nullptr, *ev_commit_ = nullptr, *ev_out_ready_ = nullptr, *ev_d2h_ = nullptr;
 
@@ -453,7 +454,7 @@ class HostTransferPipeline
     void setRawOwnSlots(bool on) { raw_own_slots_ = on; }
     bool rawOwnSlots() const { return raw_own_slots_; }
     size_t count() const { return raw_own_slots_ ? p_.activeEnd() - p_.activeBegin() : p_.hostSyncCount(); }
-    size_t hostElementBytes(const Item &it) const { return raw_own_slots_ ? it.v->deviceElementBytes() : it.host_elem_bytes; }
+    size_t hostElementBytes(const Item &it) const { return it.host_elem_bytes; }
     size_t inputBytes() const
     {
         size_t b = 0;
@@ -488,11 +489,13 @@ class HostTransferPipeline
         ex.check(sphb200_stream_wait_event(st, ev_h2d_), "sphb200_stream_wait_event");
         if (raw_own_slots_)
         {
-            // the staging already is slot order + device layout: one device copy per variable into the own slot range
+            // the staging already is in slot order: one conversion / device copy per variable into the own slot range
             for (auto &ip : ins_)
             {
                 const size_t eb = ip->v->deviceElementBytes();
-                ex.check(sphb200_copy_d2d((char *)ip->v->deviceAddress() + p_.activeBegin() * eb, ip->raw.get(), eb * n, st), "sphb200_copy_d2d");
+                char *own = (char *)ip->v->deviceAddress() + p_.activeBegin() * eb;
+                if (ip->is_vec) SPHCK_CALL(sphb200_vec3_to_vec4, (sphb200_vec4_t *)own, (const float *)ip->raw.get(), n, st);
+                else ex.check(sphb200_copy_d2d(own, ip->raw.get(), eb * n, st), "sphb200_copy_d2d");
             }
             ex.check(sphb200_event_record(ev_commit_, st), "sphb200_event_record");
             return;
@@ -531,13 +534,15 @@ class HostTransferPipeline
             for (auto &op : outs_)
             {
                 const size_t eb = op->v->deviceElementBytes();
-                op->raw.ensure(eb * n + 64);
-                ex.check(sphb200_copy_d2d(op->raw.get(), (const char *)op->v->deviceAddress() + p_.activeBegin() * eb, eb * n, st), "sphb200_copy_d2d");
+                const char *own = (const char *)op->v->deviceAddress() + p_.activeBegin() * eb;
+                op->raw.ensure(op->host_elem_bytes * n + 64);
+                if (op->is_vec) SPHCK_CALL(sphb200_vec4_to_vec3, (float *)op->raw.get(), (const sphb200_vec4_t *)own, n, st);
+                else ex.check(sphb200_copy_d2d(op->raw.get(), own, eb * n, st), "sphb200_copy_d2d");
             }
             ex.check(sphb200_event_record(ev_out_ready_, st), "sphb200_event_record");
             ex.check(sphb200_stream_wait_event(copy_stream_, ev_out_ready_), "sphb200_stream_wait_event");
             for (size_t k = 0; k < outs_.size(); ++k)
-                ex.check(sphb200_copy_d2h(pinned_host[k], outs_[k]->raw.get(), outs_[k]->v->deviceElementBytes() * n, copy_stream_), "sphb200_copy_d2h");
+                ex.check(sphb200_copy_d2h(pinned_host[k], outs_[k]->raw.get(), outs_[k]->host_elem_bytes * n, copy_stream_), "sphb200_copy_d2h");
             ex.check(sphb200_event_record(ev_d2h_, copy_stream_), "sphb200_event_record");
             return;
         }
