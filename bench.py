@@ -424,6 +424,7 @@ def run_ours(args, rank, world, local_rank):
         own_total, own_max = sum_over_ranks(n_own_d)[0], max_over_ranks(n_own_d)[0]
         developed = {"after_outer_steps": args.warmup + args.steps + args.developed_steps, "physical_time": solver.physical_time,
                      "value": n_fluid * float(n_ac_d) / (ms_d * 1e-3), "unit": "particle-steps/s", "ms_per_step": ms_d / max(args.steps, 1),
+                     "ms_per_acoustic_step": ms_d / max(n_ac_d, 1),
                      "acoustic_steps_per_outer": n_ac_d / max(args.steps, 1), "gpu_launches": int(launches_d),
                      "inner_neighbours_per_particle": pairs_in / max(own_total, 1.0),
                      "wall_neighbours_per_particle": pairs_ct / max(own_total, 1.0),
