@@ -17,6 +17,7 @@ number of advection steps only.
 Sub-records of the line (all measured in the run): `parity` (N > 1: particle count, energy and an id-keyed 64-bit digest of
 Position/Velocity after the warm-up, next to the same three from a 1-GPU run of the same spacing on rank 0's GPU),
 `developed` (the same K steps timed again after --developed-steps more advection steps: the flow has left the lattice),
+`complete_case` (correction variants + free-surface indication + probes: the case file as the reference runs it),
 `config3` (N = 8: ~16 M fluid particles per GPU, dp = 0.002), `config4` (periodic Taylor-Green ring, n_side^3 per GPU),
 `config5` (N = 1: neighbour-search chain at 16.7 M and 268 M random particles).
 """
@@ -561,6 +562,9 @@ def run_ours(args, rank, world, local_rank):
     # ---- the other BASELINE configs, each a small driver-visible record (failures are reported, not fatal) ----
     extras = {}
     if not args.no_extras:
+        extras["complete_case"] = guarded_leg(lambda: complete_case_leg(args, dp, rank, world, local_rank, torch, new_unique_id, timed_outer,
+                                                                       sum_over_ranks), rank)
+        barrier()
         if world == 8 or args.force_config3:
             extras["config3"] = guarded_leg(lambda: config3_leg(args, rank, world, local_rank, torch, dist, new_unique_id, timed_outer,
                                                                sum_over_ranks, max_over_ranks), rank)
@@ -614,6 +618,29 @@ def guarded_leg(fn, rank):
         if rank == 0:
             traceback.print_exc(file=sys.stderr)
         return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
+
+def complete_case_leg(args, dp, rank, world, local_rank, torch, new_unique_id, timed_outer, sum_over_ranks):
+    """The case file as the reference actually runs it (dambreak.cpp:117-134,192-193,223-224): LinearCorrectionMatrix + the
+    Correction aliases of both half steps, FreeSurfaceIndicationComplexSpatialTemporalCK every advection step, the six
+    wall-pressure probes interpolated and recorded every advection step — same particles as `value`."""
+    from sphinxsys_b200.host import DamBreakCK
+    k, w = max(3, min(args.steps, 20)), 3
+    s = DamBreakCK(None, dim=3, dp=dp, device_index=local_rank, fused_time_step=True, sort_interval=100, generate=True, correction=True,
+                   surface_indicator=True, observers=True, rank=rank, nranks=world, unique_id=new_unique_id(), recut_interval=100)
+    s.initialize()
+    n, = sum_over_ranks(s.own_range()[1])
+    s.run_outer(w)
+    ms, n_ac, launches = timed_outer(s, k)
+    rec = {"dynamics": "AcousticStep1st/2ndHalfWithWallRiemannCorrectionCK, LinearCorrectionMatrixComplex, "
+                       "FreeSurfaceIndicationComplexSpatialTemporalCK, 6 pressure probes per advection step",
+           "n_fluid_global": int(n), "steps": k, "warmup": w, "ms_per_step": ms / k, "acoustic_steps_per_outer": n_ac / k,
+           "value": n * n_ac / (ms * 1e-3), "unit": "particle-steps/s", "gpu_launches": int(launches), "energy": s.energy(),
+           "probe_records": int(s.exec("probe_records"))}
+    s.close()
+    del s
+    torch.cuda.empty_cache()
+    return rec
 
 
 def config3_leg(args, rank, world, local_rank, torch, dist, new_unique_id, timed_outer, sum_over_ranks, max_over_ranks):
@@ -676,6 +703,9 @@ def config4_leg(args, rank, world, local_rank, torch, dist, new_unique_id, barri
     # one event per advection step: a fresh process / freshly returned device memory makes the first steps of a large case
     # several times slower than the steady state (seen: 815 -> 43 ms per step at 256^3), so the record carries every step
     evs = [torch.cuda.Event(enable_timing=True) for _ in range(k + 1)]
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     barrier()
     evs[0].record()
     n_ac = 0
@@ -683,8 +713,10 @@ def config4_leg(args, rank, world, local_rank, torch, dist, new_unique_id, barri
         n_ac += gpu.run_outer(1)
         evs[s_ + 1].record()
     barrier()
+    clocks4 = sampler.stop() if rank == 0 else None
     per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(k)]
     ms4, = max_over_ranks(evs[0].elapsed_time(evs[k]))
+    med4, = max_over_ranks(float(np.median(per_step)))
     dt4 = gpu.last_acoustic_dt
     parts = {"acoustic_2nd_half": time_kernel(lambda: gpu.exec("acoustic2", dt4 * 1e-3), 5, torch),
              "acoustic_1st_half": time_kernel(lambda: gpu.exec("acoustic1", dt4 * 1e-3), 5, torch),
@@ -695,6 +727,8 @@ def config4_leg(args, rank, world, local_rank, torch, dist, new_unique_id, barri
     rec = {"n_side": n_side, "kernels_ms_rank0": parts, "particles_per_gpu": n_local, "n_fluid_global": n_local * world, "steps": k, "warmup": w,
            "ms_per_step": ms4 / k, "ms_per_step_rank0": [round(v, 2) for v in per_step], "acoustic_steps_per_outer": n_ac / k,
            "value": world * n_local * n_ac / (ms4 * 1e-3),
+           # the same from the MEDIAN step (slowest rank): single steps of this leg come out 1.5-2.7x slow now and then
+           "ms_per_step_median": med4, "value_median_step": world * n_local * (n_ac / k) / (med4 * 1e-3), "clocks": clocks4,
            "unit": "particle-steps/s", "gpu_launches": gpu.launches - l0, "images_rank0": gpu.ghost_particles,
            "plane_ghosts_rank0": int(gpu.exec("plane_ghost_particles")), "kinetic_energy": gpu.energy(), "setup_s": setup_s,
            "parallelism": f"ring of {world} slab(s) along x, NCCL" if world > 1 else "ring of one slab (device copies)"}
