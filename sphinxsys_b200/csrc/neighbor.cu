@@ -454,13 +454,25 @@ __device__ __forceinline__ unsigned long long fma2(unsigned long long a, unsigne
 // bit into the hit mask) and one FMNMX (ambiguity tracker) — the integer/predicate pipe runs at half the FP32 rate on
 // sm_100 (scripts/microbench/ffma2.cu), which is what bounded the two-threshold FSETP/SEL form used before.
 // -----------------------------------------------------------------------------------------------------
+// tuning (scripts/gpu_variants.sh): chunk masks a lane may hold back, minimum resident blocks (0: the compiler's choice)
+#ifndef SPH_REL_NW
+#define SPH_REL_NW 32
+#endif
+#ifndef SPH_REL_MINB
+#define SPH_REL_MINB 0
+#endif
+#if SPH_REL_MINB > 0
+#define SPH_REL_BOUNDS __launch_bounds__(128, SPH_REL_MINB)
+#else
+#define SPH_REL_BOUNDS __launch_bounds__(128)
+#endif
 template <bool INNER, int MODE, bool TWO>
-__global__ void __launch_bounds__(128)
+__global__ void SPH_REL_BOUNDS
     k_relation_ordered(SearchArgs a, u32 *__restrict__ count, u32 *__restrict__ slice, u32 *__restrict__ index, u64 capacity,
                        u32 stride, u32 *__restrict__ max_count, int align_origin)
 {
     constexpr int CH = 32; // candidates tested per chunk; hits of a chunk are collected in a per-lane bit mask
-    constexpr int NW = 32; // chunk masks a lane may hold back before its hits are written out
+    constexpr int NW = SPH_REL_NW; // chunk masks a lane may hold back before its hits are written out
     __shared__ __align__(16) float rel_tile[4][2][3][CH]; // per warp: two tiles of x[CH], y[CH], z[CH]
     __shared__ u32 rel_mask[4][NW][32];
     __shared__ u32 rel_base[4][NW];
