@@ -322,6 +322,7 @@ def run_ours(args, rank, world, local_rank):
         """K advection steps inside the C++ host loop, CUDA events on the launching stream, barrier + synchronize on both
         sides, max over ranks. Returns (ms, acoustic steps, launches)."""
         l0, a0 = solver.launches, solver.acoustic_steps
+        timed_outer.allocations_before = solver.device_allocations
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         ev0.record()
@@ -329,6 +330,7 @@ def run_ours(args, rank, world, local_rank):
         ev1.record()
         barrier()
         ms, = max_over_ranks(ev0.elapsed_time(ev1))
+        timed_outer.allocations = solver.device_allocations - timed_outer.allocations_before
         return ms, solver.acoustic_steps - a0, solver.launches - l0
 
     # The C++ host layer builds the case itself (lattice generator + shape normals, include/sphinxsys_ck/dambreak_case.h)
@@ -390,6 +392,7 @@ def run_ours(args, rank, world, local_rank):
     if rank == 0:
         sampler.start()
     ms, n_ac, launches = timed_outer(solver, args.steps)
+    allocations_in_window = timed_outer.allocations
     clocks = sampler.stop() if rank == 0 else None
     sorts_in_window = sum(1 for it in range(args.warmup + 1, args.warmup + args.steps + 1) if it % cadence == 0 and it != 1)
     n_own = solver.own_range()[1]  # own particles of this rank after the timed steps (migration, re-cuts)
@@ -601,6 +604,7 @@ def run_ours(args, rank, world, local_rank):
             "kernel_only_particle_steps_per_s": n_fluid / ((ms_a1 + ms_a2) * 1e-3),
             "outer_steps_per_s": args.steps / (ms * 1e-3),
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "device_allocations_in_timed_window_rank0": int(allocations_in_window),
             "parity": parity, "developed": developed,
         }
         line.update(extras)
@@ -709,9 +713,11 @@ def config4_leg(args, rank, world, local_rank, torch, dist, new_unique_id, barri
     barrier()
     evs[0].record()
     n_ac = 0
+    allocs = [gpu.device_allocations]
     for s_ in range(k):
         n_ac += gpu.run_outer(1)
         evs[s_ + 1].record()
+        allocs.append(gpu.device_allocations)
     barrier()
     clocks4 = sampler.stop() if rank == 0 else None
     per_step = [evs[i].elapsed_time(evs[i + 1]) for i in range(k)]
@@ -725,7 +731,8 @@ def config4_leg(args, rank, world, local_rank, torch, dist, new_unique_id, barri
              "relation_build": time_kernel(lambda: gpu.exec("relations"), 3, torch),
              "inner_stride": gpu.exec("inner_stride"), "inner_max_count": gpu.exec("inner_max_count")}
     rec = {"n_side": n_side, "kernels_ms_rank0": parts, "particles_per_gpu": n_local, "n_fluid_global": n_local * world, "steps": k, "warmup": w,
-           "ms_per_step": ms4 / k, "ms_per_step_rank0": [round(v, 2) for v in per_step], "acoustic_steps_per_outer": n_ac / k,
+           "ms_per_step": ms4 / k, "ms_per_step_rank0": [round(v, 2) for v in per_step],
+           "device_allocations_per_step_rank0": [b - a for a, b in zip(allocs[:-1], allocs[1:])], "acoustic_steps_per_outer": n_ac / k,
            "value": world * n_local * n_ac / (ms4 * 1e-3),
            # the same from the MEDIAN step (slowest rank): single steps of this leg come out 1.5-2.7x slow now and then
            "ms_per_step_median": med4, "value_median_step": world * n_local * (n_ac / k) / (med4 * 1e-3), "clocks": clocks4,

@@ -210,6 +210,8 @@ uint64_t sphb200_launch_count(const sphb200_context_t *ctx);
 int sphb200_malloc_device(void **ptr, size_t bytes);                 /* allocateDeviceOnly, implementation_sycl.h:99-105 */
 int sphb200_malloc_host(void **ptr, size_t bytes);                   /* allocateHostStaging (pinned) */
 int sphb200_free_device(void *ptr);
+/* device allocations made so far through the library (arrays + scratch arenas): a steady-state loop must not add any */
+uint64_t sphb200_device_allocation_count(void);
 int sphb200_free_host(void *ptr);
 int sphb200_copy_h2d(void *dst, const void *src, size_t bytes, void *stream); /* copyToDevice   :117-127 */
 int sphb200_copy_d2h(void *dst, const void *src, size_t bytes, void *stream); /* copyFromDevice :129-139 */

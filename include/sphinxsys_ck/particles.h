@@ -64,9 +64,12 @@ class DeviceBuffer
         p_ = deviceAllocate(bytes ? bytes : 4);
         bytes_ = bytes;
     }
-    void ensure(size_t bytes) // grow without copy (DiscreteVariable::reallocateData semantics)
+    // grow without copy (DiscreteVariable::reallocateData semantics). A buffer that has to grow AGAIN gets an eighth of
+    // head-room: sizes that follow a particle count creep up by a few elements per step in decomposed and periodic runs,
+    // and every cudaFree / cudaMalloc pair synchronises the device
+    void ensure(size_t bytes)
     {
-        if (bytes > bytes_) reset(bytes);
+        if (bytes > bytes_) reset(bytes_ ? bytes + bytes / 8 : bytes);
     }
     void swap(DeviceBuffer &o)
     {

@@ -75,6 +75,7 @@ class PeriodicImages
     bool decomposed_ = false;
     uint32_t own_begin_ = 0, own_end_ = 0;
     DeviceBuffer tmp_pos_, tmp_src_, ghost_src_, cell_offset_, particle_index_;
+    size_t work_capacity_ = 0; // images the work arrays hold (grown with head-room: see ensure())
 
   public:
     explicit PeriodicImages(SPHBody &body) : body_(body)
@@ -148,10 +149,18 @@ class PeriodicImages
         CellLinkedList &cl = body_.getCellLinkedList();
         if (!body_.isCellOrdered()) throw SphError("periodic ghost creation needs the body's cell-linked list (UpdateCellLinkedList first)");
         const uint32_t capacity = (uint32_t)(p.ParticlesBound() - n_real_);
-        tmp_pos_.ensure(((size_t)capacity + 1) * 16);
-        tmp_src_.ensure(((size_t)capacity + 1) * 4);
-        ghost_src_.ensure(((size_t)capacity + 1) * 4);
-        particle_index_.ensure((std::max<size_t>(capacity, cl.total_cells_) + 2) * 4);
+        // The room behind the real particles changes by a few slots every step (decomposed runs: the ghost planes do), and
+        // every new maximum used to re-allocate all four work arrays — four cudaFree / cudaMalloc pairs per advection step in
+        // the 256^3 ring, each synchronising the device (bench.py `config4.device_allocations_per_step_rank0`). They are
+        // sized with a quarter of head-room now: allocation stops after the first steps.
+        if (capacity > work_capacity_)
+        {
+            work_capacity_ = (size_t)capacity + capacity / 4 + 4096;
+            tmp_pos_.ensure((work_capacity_ + 1) * 16);
+            tmp_src_.ensure((work_capacity_ + 1) * 4);
+            ghost_src_.ensure((work_capacity_ + 1) * 4);
+            particle_index_.ensure((std::max<size_t>(work_capacity_, cl.total_cells_) + 2) * 4);
+        }
         sphb200_periodic_t b = box_;
         b.axes = armed_axes_;
         uint32_t count = 0;

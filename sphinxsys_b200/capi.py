@@ -158,6 +158,7 @@ SYMBOLS = {
     "sphb200_comm_set_ring": (_I, [_CTX, _I]),
     "sphb200_comm_is_ring": (_I, [_CTX]),
     "sphb200_seam_shift": (_I, [_CTX, _P, _U32, _U32, C.c_float, _P, _P]),
+    "sphb200_device_allocation_count": (C.c_uint64, []),
     "sphb200_comm_mailbox_open": (_I, [_CTX, C.c_size_t]),
     "sphb200_comm_mailbox_close": (_I, [_CTX]),
     "sphb200_comm_mailbox_peer_bytes": (C.c_size_t, [_CTX, _I]),

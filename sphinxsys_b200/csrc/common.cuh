@@ -69,10 +69,12 @@ struct sphb200_context
         SPH_CUDA(ctx, cudaGetLastError());                                                         \
     } while (0)
 
+void sph_count_allocation(); // primitives.cu
 static inline int sph_scratch(sphb200_context *ctx, int slot, size_t bytes, void **out)
 {
     if (ctx->scratch_bytes[slot] < bytes)
     {
+        sph_count_allocation();
         if (ctx->scratch[slot]) SPH_CUDA(ctx, cudaFree(ctx->scratch[slot]));
         ctx->scratch[slot] = nullptr;
         ctx->scratch_bytes[slot] = 0;

@@ -333,6 +333,7 @@ extern "C"
         return body(h, which).TotalRealParticles();
     }
     uint64_t sphck_launches(void *) { return execution_instance().launches(); }
+    uint64_t sphck_device_allocations(void *) { return sphb200_device_allocation_count(); }
     // BodyStatesRecordingToVtpCK::writeToFile of the dam-break case into `folder` (one .vtp per body); returns bytes synchronised
     int sphck_record_states(void *hp, const char *folder, uint64_t *bytes_synchronized)
     {

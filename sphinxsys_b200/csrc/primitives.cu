@@ -48,7 +48,16 @@ extern "C" int sphb200_context_destroy(sphb200_context_t *ctx)
 extern "C" const char *sphb200_last_error_string(const sphb200_context_t *ctx) { return ctx ? ctx->err : "null context"; }
 extern "C" uint64_t sphb200_launch_count(const sphb200_context_t *ctx) { return ctx ? ctx->launches : 0; }
 
-extern "C" int sphb200_malloc_device(void **ptr, size_t bytes) { return (int)cudaMalloc(ptr, bytes ? bytes : 1); }
+// device allocations made so far by this process through the library (arrays of the host layer + scratch arenas): a
+// steady-state loop must not allocate — cudaMalloc / cudaFree synchronise the device and cost milliseconds
+static unsigned long long g_device_allocations = 0;
+void sph_count_allocation() { ++g_device_allocations; }
+extern "C" uint64_t sphb200_device_allocation_count(void) { return g_device_allocations; }
+extern "C" int sphb200_malloc_device(void **ptr, size_t bytes)
+{
+    ++g_device_allocations;
+    return (int)cudaMalloc(ptr, bytes ? bytes : 1);
+}
 extern "C" int sphb200_malloc_host(void **ptr, size_t bytes) { return (int)cudaMallocHost(ptr, bytes ? bytes : 1); }
 extern "C" int sphb200_free_device(void *ptr) { return (int)cudaFree(ptr); }
 extern "C" int sphb200_free_host(void *ptr) { return (int)cudaFreeHost(ptr); }

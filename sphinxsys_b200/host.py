@@ -65,6 +65,8 @@ def load():
         L.sphck_count.restype = C.c_uint64
         L.sphck_count.argtypes = [C.c_void_p, C.c_int]
         L.sphck_record_states.argtypes = [C.c_void_p, C.c_char_p, C.POINTER(C.c_uint64)]
+        L.sphck_device_allocations.restype = C.c_uint64
+        L.sphck_device_allocations.argtypes = [C.c_void_p]
         L.sphck_launches.restype = C.c_uint64
         L.sphck_launches.argtypes = [C.c_void_p]
         L.sphck_synchronize.argtypes = [C.c_void_p]
@@ -244,6 +246,11 @@ class DamBreakCK:
     @property
     def launches(self) -> int:
         return int(self.lib.sphck_launches(self._h))
+
+    @property
+    def device_allocations(self) -> int:
+        """cudaMalloc calls made through the library so far (arrays + scratch arenas)."""
+        return int(self.lib.sphck_device_allocations(self._h))
 
     @property
     def physical_time(self):
