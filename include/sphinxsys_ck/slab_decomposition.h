@@ -366,24 +366,28 @@ class SlabDecomposition
         // [5..8] cells of the plane boundaries, [16..23] the record that goes to the host
         uint32_t *w = scalars_.get<uint32_t>() + 192;
         uint32_t *d_send = w, *d_recv = w + 2, *d_ntot = w + 4, *d_cells = w + 5, *d_rec = w + 16;
-        SPHCK_CALL(sphb200_slab_select, &cl.mesh_, (const sphb200_vec4_t *)p.deviceData<Vecd>("Position"), a0_, n_old,
-                   hasLeft() ? X0 : -1, hasRight() ? X1 - 1 : -1, left_idx, right_idx, d_send, st);
-        if (hasLeft()) SPHCK_CALL(sphb200_comm_push, 0, (int)k, src.data(), bytes.data(), left_idx, d_send, seq, st);
-        if (hasRight()) SPHCK_CALL(sphb200_comm_push, 1, (int)k, src.data(), bytes.data(), right_idx, d_send + 1, seq, st);
+        SPHCK_STAGE("  rebuild: select", SPHCK_CALL(sphb200_slab_select, &cl.mesh_, (const sphb200_vec4_t *)p.deviceData<Vecd>("Position"), a0_, n_old,
+                                                    hasLeft() ? X0 : -1, hasRight() ? X1 - 1 : -1, left_idx, right_idx, d_send, st));
+        if (hasLeft()) SPHCK_STAGE("  rebuild: push left", SPHCK_CALL(sphb200_comm_push, 0, (int)k, src.data(), bytes.data(), left_idx, d_send, seq, st));
+        if (hasRight()) SPHCK_STAGE("  rebuild: push right", SPHCK_CALL(sphb200_comm_push, 1, (int)k, src.data(), bytes.data(), right_idx, d_send + 1, seq, st));
         const uint32_t bound = (uint32_t)p.ParticlesBound();
-        if (hasLeft()) SPHCK_CALL(sphb200_comm_pull, 0, (int)k, dst.data(), bytes.data(), a1_, nullptr, bound, d_recv, seq, st);
-        if (hasRight()) SPHCK_CALL(sphb200_comm_pull, 1, (int)k, dst.data(), bytes.data(), a1_, hasLeft() ? d_recv : nullptr, bound, d_recv + 1, seq, st);
+        if (hasLeft()) SPHCK_STAGE("  rebuild: pull left (wait + unpack)", SPHCK_CALL(sphb200_comm_pull, 0, (int)k, dst.data(), bytes.data(), a1_, nullptr, bound, d_recv, seq, st));
+        if (hasRight())
+            SPHCK_STAGE("  rebuild: pull right (wait + unpack)",
+                        SPHCK_CALL(sphb200_comm_pull, 1, (int)k, dst.data(), bytes.data(), a1_, hasLeft() ? d_recv : nullptr, bound, d_recv + 1, seq, st));
         SPHCK_CALL(sphb200_slab_total, n_old, hasLeft() ? d_recv : nullptr, hasRight() ? d_recv + 1 : nullptr, d_ntot, st);
         // everything into cell order at the front of the arrays; launches sized for what the storage can hold
-        const uint32_t capacity = bound - a0_;
+        // ... which is an eighth above the last stored total (own + ghost planes change by well under a percent per step;
+        // launching for the whole reserve — twice the own count — cost 0.1 ms of empty blocks), never beyond the storage
+        const uint32_t capacity = (uint32_t)std::min<uint64_t>(bound - a0_, (uint64_t)n_ + n_ / 8 + 8192);
         p.setTotalRealParticles(bound);
-        reorder(a0_, capacity, d_ntot);
+        SPHCK_STAGE("  rebuild: cell list + reorder", reorder(a0_, capacity, d_ntot));
         uint32_t cells4[4] = {(uint32_t)X0 * plane_cells_, (uint32_t)(X0 + 1) * plane_cells_, (uint32_t)(X1 - 1) * plane_cells_,
                               (uint32_t)X1 * plane_cells_};
         ex.check(sphb200_copy_h2d(d_cells, cells4, sizeof(cells4), st), "sphb200_copy_h2d");
         uint64_t *d_own = scalars_.get<uint64_t>() + 128, *d_all = d_own + 1; // bytes 1024.. : behind the reduction windows
         SPHCK_CALL(sphb200_slab_bounds, cl.cell_offset_.get<uint32_t>(), d_cells, 4, d_ntot, 0 | (3 << 8), d_rec, d_own, st);
-        SPHCK_CALL(sphb200_comm_allgather_u64, d_own, d_all, 1, st);
+        SPHCK_STAGE("  rebuild: all-gather of the own counts", SPHCK_CALL(sphb200_comm_allgather_u64, d_own, d_all, 1, st));
         // the ONE host round trip: plane offsets, stored total, status, send counts, own counts of all ranks
         uint32_t rec[6] = {0, 0, 0, 0, 0, 0}, sent[2] = {0, 0};
         std::vector<uint64_t> all(nranks_);
@@ -392,6 +396,9 @@ class SlabDecomposition
         ex.check(sphb200_copy_d2h(all.data(), d_all, all.size() * sizeof(uint64_t), st), "sphb200_copy_d2h");
         ex.synchronize();
         ++host_syncs_;
+        if (rec[4] > capacity)
+            throw SphError("SlabDecomposition::rebuildPeer: rank " + std::to_string(rank_) + " received more particles in one step (" +
+                           std::to_string(rec[4]) + " stored) than the cell-list launch was sized for (" + std::to_string(capacity) + ")");
         if (rec[5])
             throw SphError("SlabDecomposition::rebuildPeer: rank " + std::to_string(rank_) + " mailbox status " + std::to_string(rec[5]) +
                            " (1: more migrants than a mailbox holds, 2: a neighbour did not deliver, 4: particle storage exhausted)");

@@ -37,3 +37,5 @@ while done < steps:
         rec["own"] = [r["own"] for r in allr]
     if rank == 0:
         print("PROBE", json.dumps(rec), flush=True)
+if rank == int(os.environ.get("TRACE_RANK", "0")):
+    s.step_trace_report(done)

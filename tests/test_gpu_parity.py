@@ -927,3 +927,98 @@ def test_host_transfer_pipeline_equals_synchronous_transfers():
     for s in range(steps):
         for k, nm in enumerate(out_names):
             assert np.array_equal(outs[s][k][1], sync_out[s][nm]), (s, nm)
+
+
+def test_peer_mailbox_push_pull_on_a_ring_of_one(ctx):
+    """The peer-mailbox primitives of the N-GPU rebuild (sphb200_comm_push / _pull, SlabDecomposition::rebuildPeer) on ONE
+    GPU: a communicator of one rank closed into a ring is its own neighbour on both sides, so what is pushed to the left
+    arrives "from the right". List length and arrival count live in device memory; two parities; records of 16, 4 and 36
+    bytes; the overflow and the out-of-room status bits."""
+    from sphinxsys_b200 import capi
+    c = capi.Context(0)
+    try:
+        c.call("sphb200_comm_create_self")
+        c.call("sphb200_comm_set_ring", 1)
+        n, cap_entries = 50_000, 4_000
+        per_entry = 16 + 4 + 36
+        c.call("sphb200_comm_mailbox_open", C.c_size_t(64 + cap_entries * per_entry))
+        rng = np.random.default_rng(11)
+        a16 = torch.from_numpy(rng.standard_normal((n, 4)).astype(np.float32)).cuda()
+        a4 = torch.from_numpy(rng.integers(0, 1 << 30, size=n).astype(np.int32)).cuda()
+        a36 = torch.from_numpy(rng.standard_normal((n, 9)).astype(np.float32)).cuda()
+        srcs = [a16, a4, a36]
+        eb = (C.c_uint32 * 3)(16, 4, 36)
+        sp = (C.c_void_p * 3)(*[t.data_ptr() for t in srcs])
+        for seq, m in ((1, 1234), (2, 0), (3, 3999)):
+            pick = np.sort(rng.choice(n, size=m, replace=False)).astype(np.int32) if m else np.zeros(0, dtype=np.int32)
+            idx = torch.from_numpy(np.concatenate([pick, np.zeros(8, dtype=np.int32)])).cuda()
+            n_dev = torch.tensor([m], dtype=torch.int32, device="cuda")
+            c.call("sphb200_comm_push", 0, 3, sp, eb, _p(idx), _p(n_dev), C.c_uint64(seq), _s())
+            dsts = [torch.zeros((m + 10, 4), dtype=torch.float32, device="cuda"), torch.zeros(m + 10, dtype=torch.int32, device="cuda"),
+                    torch.zeros((m + 10, 9), dtype=torch.float32, device="cuda")]
+            dp = (C.c_void_p * 3)(*[t.data_ptr() for t in dsts])
+            got = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+            extra = torch.tensor([3], dtype=torch.int32, device="cuda")  # append behind dst_begin + *extra
+            c.call("sphb200_comm_pull", 1, 3, dp, eb, 2, _p(extra), m + 10, _p(got), C.c_uint64(seq), _s())
+            torch.cuda.synchronize()
+            assert int(got[0]) == m
+            for d, s_ in zip(dsts, (a16, a4, a36)):
+                assert torch.equal(d[5:5 + m], s_[torch.from_numpy(pick).long().cuda()]) and not d[:5].any() and not d[5 + m:].any()
+        # more entries than the neighbour's box holds: nothing usable arrives, both sides see status bit 1
+        idx = torch.arange(n, dtype=torch.int32, device="cuda")
+        n_dev = torch.tensor([cap_entries + 500], dtype=torch.int32, device="cuda")
+        c.call("sphb200_comm_push", 1, 3, sp, eb, _p(idx), _p(n_dev), C.c_uint64(4), _s())
+        dsts = [torch.zeros((16, 4), dtype=torch.float32, device="cuda"), torch.zeros(16, dtype=torch.int32, device="cuda"),
+                torch.zeros((16, 9), dtype=torch.float32, device="cuda")]
+        dp = (C.c_void_p * 3)(*[t.data_ptr() for t in dsts])
+        got = torch.full((1,), -1, dtype=torch.int32, device="cuda")
+        c.call("sphb200_comm_pull", 0, 3, dp, eb, 0, None, 16, _p(got), C.c_uint64(4), _s())
+        torch.cuda.synchronize()
+        assert int(got[0]) == 0 and not dsts[0].any()
+        lib = capi.load()
+        word = np.zeros(1, dtype=np.uint32)
+        assert lib.sphb200_copy_d2h(word.ctypes.data, lib.sphb200_comm_mailbox_status(c._ctx), 4, None) == 0
+        assert lib.sphb200_stream_sync(None) == 0
+        assert int(word[0]) & 1
+        # no room behind dst_begin: status bit 4, nothing written
+        n_dev = torch.tensor([100], dtype=torch.int32, device="cuda")
+        c.call("sphb200_comm_push", 0, 3, sp, eb, _p(idx), _p(n_dev), C.c_uint64(5), _s())
+        c.call("sphb200_comm_pull", 1, 3, dp, eb, 0, None, 16, _p(got), C.c_uint64(5), _s())
+        torch.cuda.synchronize()
+        assert lib.sphb200_copy_d2h(word.ctypes.data, lib.sphb200_comm_mailbox_status(c._ctx), 4, None) == 0
+        assert lib.sphb200_stream_sync(None) == 0
+        assert int(word[0]) & 4 and int(got[0]) == 100 and not dsts[1].any()
+        c.call("sphb200_comm_mailbox_close")
+    finally:
+        c.close()
+
+
+def test_cell_list_build_with_device_side_count(ctx, oracle_lib):
+    """sphb200_cell_list_build_reorder_n: launches sized for a capacity, the live particle count read from device memory —
+    identical cell offsets and storage order to the host-count entry point on the first n particles."""
+    from sphinxsys_b200 import capi, cases
+    case = cases.dam_break(dim=3, dp=0.05)
+    n, cap = case.n_fluid, case.n_fluid + 3_000
+    pos = np.concatenate([case.fluid_pos, np.full((cap - n, 3), 1.0e9, dtype=np.float32)])  # junk behind the live range
+    m = capi.mesh_t(case.mesh)
+    cells = case.mesh.total_cells
+    outs = []
+    for n_dev in (None, torch.tensor([n], dtype=torch.int32, device="cuda")):
+        p4 = torch.zeros((cap, 4), dtype=torch.float32, device="cuda")
+        p4[:, :3] = torch.from_numpy(pos).cuda()
+        ids = torch.arange(cap, dtype=torch.int32, device="cuda")
+        off = torch.zeros(cells + 2, dtype=torch.int32, device="cuda")
+        pidx = torch.zeros(max(cap, cells) + 2, dtype=torch.int32, device="cuda")
+        cl = capi.CellListT(_p(off), _p(pidx), None)
+        dst = [torch.zeros_like(p4), torch.zeros_like(ids)]
+        dpp = (C.c_void_p * 2)(dst[0].data_ptr(), dst[1].data_ptr())
+        spp = (C.c_void_p * 2)(p4.data_ptr(), ids.data_ptr())
+        ebb = (C.c_uint32 * 2)(16, 4)
+        ctx.call("sphb200_cell_list_build_reorder_n", C.byref(m), _p(p4), n if n_dev is None else cap, None if n_dev is None else _p(n_dev),
+                 _p(ids), cl, 2, dpp, spp, ebb, _s())
+        torch.cuda.synchronize()
+        outs.append((off[: cells + 1].cpu().numpy(), dst[0][:n].cpu().numpy(), dst[1][:n].cpu().numpy()))
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    ref_cell, _ = oracle_lib.cell_keys(case.fluid_pos, case.mesh)
+    assert np.array_equal(np.diff(outs[0][0].astype(np.int64)), np.bincount(ref_cell, minlength=cells))
