@@ -224,6 +224,8 @@ def second_roofline(name, n_own, launch_ms, sm_mhz, counters):
     inst = c["warp_instructions_per_particle"] * n_own
     wave = c["l1_wavefronts_per_particle"] * n_own
     return {"bound": "issue slots / L1 data pipe", "issue_frac": inst / (cycles * 148 * 4), "l1_data_pipe_frac": wave / (cycles * 148),
+            # the launch time each ceiling alone would allow (ms): what a perfect memory system / a perfect scheduler would leave
+            "issue_floor_ms": 1e3 * inst / (148 * 4 * sm_mhz * 1e6), "l1_data_pipe_floor_ms": 1e3 * wave / (148 * sm_mhz * 1e6),
             "warp_instructions_per_launch": inst, "l1_wavefronts_per_launch": wave, "sm_mhz": sm_mhz, "source": c.get("source")}
 
 
