@@ -121,20 +121,27 @@ class WallSlab
         const int lo = std::max(0, X0 - depth_ - margin_), hi = std::min(planes_ - 1, X1 - 1 + depth_ + margin_);
         return (size_t)(below_[hi + 1] - below_[lo]);
     }
+    // Pure planning (host arithmetic only): the planes to store for the fluid planes [X0, X1) given the planes stored now
+    // ([lo, hi], empty if hi < lo) and the storage `bound`. Returns false if what is stored suffices.
+    bool plan(int X0, int X1, size_t bound, int &lo, int &hi) const
+    {
+        const int need_lo = std::max(0, X0 - depth_), need_hi = std::min(planes_ - 1, X1 - 1 + depth_);
+        if (hi >= lo && need_lo >= lo && need_hi <= hi) return false;
+        lo = std::max(0, need_lo - margin_);
+        hi = std::min(planes_ - 1, need_hi + margin_);
+        // the margin only saves reloads: give it up where the storage is too small for it
+        while ((size_t)(below_[hi + 1] - below_[lo]) > bound && (lo < need_lo || hi > need_hi))
+        {
+            if (lo < need_lo) ++lo;
+            if (hi > need_hi) --hi;
+        }
+        return true;
+    }
+    uint64_t particlesBelow(int plane) const { return below_[std::min(std::max(plane, 0), planes_)]; }
     // make sure the wall planes around the fluid planes [X0, X1) are stored; true if the subset was (re)loaded
     bool ensure(int X0, int X1)
     {
-        const int need_lo = std::max(0, X0 - depth_), need_hi = std::min(planes_ - 1, X1 - 1 + depth_);
-        if (hi_ >= lo_ && need_lo >= lo_ && need_hi <= hi_) return false;
-        lo_ = std::max(0, need_lo - margin_);
-        hi_ = std::min(planes_ - 1, need_hi + margin_);
-        // the margin only saves reloads: give it up where the storage is too small for it
-        const size_t bound = wall_.getBaseParticles().ParticlesBound();
-        while ((size_t)(below_[hi_ + 1] - below_[lo_]) > bound && (lo_ < need_lo || hi_ > need_hi))
-        {
-            if (lo_ < need_lo) ++lo_;
-            if (hi_ > need_hi) --hi_;
-        }
+        if (!plan(X0, X1, wall_.getBaseParticles().ParticlesBound(), lo_, hi_)) return false;
         std::vector<Vecd> p, nrm;
         std::vector<UnsignedInt> ids;
         const size_t count = (size_t)(below_[hi_ + 1] - below_[lo_]);
