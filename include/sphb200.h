@@ -104,6 +104,10 @@ typedef struct
     float *vol_ref;               /* VolumetricMeasureRef */
     float *compression_sum;       /* CompressionSummation */
     float *B;                     /* LinearCorrectionMatrix, 9 floats row-major per particle, or NULL */
+    void *correction_record;      /* 32-byte records (Bxx, Bxy, Bxz, Byy, Byz, Bzz, -, -): the symmetric part of B as ONE
+                                     gather per neighbour for the 1st-half interaction with LinearCorrectionCK (which reads
+                                     B of the neighbour). sphb200_linear_correction_matrix writes it next to B; NULL: the
+                                     interaction gathers the nine entries of B itself (2.2 x slower at 4 M particles) */
     sphb200_vec4_t *posvol;       /* derived gather records, one load per neighbour instead of two; refresh with
                                      sphb200_pack_records whenever their sources changed outside the library:
                                      posvol = (x, y, z, Vol)                         [1st half, correction matrix] */
@@ -382,8 +386,11 @@ int sphb200_acoustic_2nd_half(sphb200_context_t *ctx, const sphb200_fluid_args_t
 int sphb200_acoustic_1st_half_initialize(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, float dt, void *stream);
 int sphb200_acoustic_1st_half_interact(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, float dt, int do_update,
                                        void *stream);
-/* LinearCorrectionMatrix<Inner<WithUpdate>,Contact<>>; ref: general_dynamics/kernel_correction_ck.hpp:40-95 */
+/* LinearCorrectionMatrix<Inner<WithUpdate>,Contact<>>; ref: general_dynamics/kernel_correction_ck.hpp:40-95.
+ * Writes fluid.B and, when given, fluid.correction_record. */
 int sphb200_linear_correction_matrix(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, float alpha, void *stream);
+/* correction_record (see sphb200_fluid_view_t) of n matrices written outside the library (host uploads) */
+int sphb200_pack_correction_records(sphb200_context_t *ctx, uint32_t n, const float *B, void *correction_record, void *stream);
 /* InteractionDynamicsCK<FreeSurfaceIndicationCK<Inner<WithUpdate>, Contact<>>>::exec: inner interact (position
  * divergence, spatial-temporal override next to the previous surface) -> contact interact -> update (Indicator,
  * PreviousSurfaceIndicator). threshold = 0.75 * Dimensions, smoothing_length = ReferenceSmoothingLength().

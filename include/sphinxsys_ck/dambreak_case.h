@@ -626,7 +626,7 @@ class DamBreakCK
             SPHCK_STAGE("linear correction matrix", fluid_linear_correction_matrix->exec());
             // both half steps read B of the neighbours: the one refresh the correction variants add to a decomposed step
             // (tests/test_decomposed_oracle_cpu.py::test_dam_break_correction_variants_bit_identical)
-            if (decomposition) decomposition->refreshGhosts({"LinearCorrectionMatrix"});
+            if (decomposition) decomposition->refreshGhosts({"LinearCorrectionMatrix", "LinearCorrectionRecord"});
         }
         Real relaxation_time = 0, acoustic_dt = 0;
         int n_inner = 0;

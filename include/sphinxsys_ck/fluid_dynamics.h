@@ -26,6 +26,16 @@
 namespace SPH
 {
 // ---- type tags (spelled as in the reference) ----
+// LinearCorrectionRecord: the symmetric part of LinearCorrectionMatrix as one 32-byte gather record (sphb200.h,
+// sphb200_fluid_view_t::correction_record) — what AcousticStep1stHalf<..., LinearCorrectionCK> reads of its neighbours.
+// The identity until LinearCorrectionMatrix has run, like the matrix itself; a registered state variable, so it is
+// reordered, migrated and refreshed on ghost planes with the matrix.
+inline void registerCorrectionRecord(BaseParticles &p)
+{
+    GatherRecord8 identity;
+    identity.v[0] = identity.v[3] = identity.v[5] = Real(1);
+    p.registerStateVariable<GatherRecord8>("LinearCorrectionRecord", identity);
+}
 struct Base {};
 struct WithUpdate {};
 struct WithInitialization {};
@@ -220,6 +230,7 @@ class FluidDynamicsBase
         f.vol_ref = (float *)p.deviceDataOrNull<Real>("VolumetricMeasureRef");
         f.compression_sum = (float *)p.deviceDataOrNull<Real>("CompressionSummation");
         f.B = (float *)p.deviceDataOrNull<Matd>("LinearCorrectionMatrix");
+        f.correction_record = p.deviceDataOrNull<GatherRecord8>("LinearCorrectionRecord");
         f.posvol = (sphb200_vec4_t *)p.deviceDataOrNull<Vecd>("PosVol");
         f.posvolref = (sphb200_vec4_t *)p.deviceDataOrNull<Vecd>("PosVolRef");
         f.posvolvel = p.deviceDataOrNull<GatherRecord8>("PosVolVel");
@@ -480,14 +491,14 @@ class AcousticStep1stHalfWithWall : public FluidDynamicsBase, public AcousticSte
         riemann_ = RiemannType::kind;
         correction_ = CorrectionType::kind;
         registerAcousticVariables();
-        if (correction_) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity());
+        if (correction_) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity()), registerCorrectionRecord(particles_);
     }
     AcousticStep1stHalfWithWall(Inner<> &inner, Contact<> &contact) : FluidDynamicsBase(inner, &contact)
     {
         riemann_ = RiemannType::kind;
         correction_ = CorrectionType::kind;
         registerAcousticVariables();
-        if (correction_) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity());
+        if (correction_) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity()), registerCorrectionRecord(particles_);
     }
     std::vector<BaseDynamics<void> *> deviceInteract(Real dt, const std::vector<BaseDynamics<void> *> &post)
     {
@@ -526,14 +537,14 @@ template <class RiemannType, class CorrectionType> class AcousticStep2ndHalfWith
         riemann_ = RiemannType::kind;
         correction_ = CorrectionType::kind;
         registerAcousticVariables();
-        if (correction_) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity());
+        if (correction_) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity()), registerCorrectionRecord(particles_);
     }
     AcousticStep2ndHalfWithWall(Inner<> &inner, Contact<> &contact) : FluidDynamicsBase(inner, &contact)
     {
         riemann_ = RiemannType::kind;
         correction_ = CorrectionType::kind;
         registerAcousticVariables();
-        if (correction_) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity());
+        if (correction_) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity()), registerCorrectionRecord(particles_);
     }
     // Fold the next AcousticTimeStepCK reduction into this launch (library extension: removes one pass over the
     // particles per acoustic step; the reduced value is bit-identical to the stand-alone reduction).
@@ -642,7 +653,7 @@ class ViscousForceBase : public FluidDynamicsBase
         particles_.registerStateVariable<Vecd>("ForcePrior");
         particles_.addEvolvingVariable<Vecd>("ForcePrior");
         particles_.addEvolvingVariable<Vecd>("PreviousViscousForce");
-        if (correction) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity());
+        if (correction) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity()), registerCorrectionRecord(particles_);
     }
 
   public:
@@ -725,12 +736,12 @@ class LinearCorrectionMatrixComplex : public fluid_dynamics::FluidDynamicsBase
     LinearCorrectionMatrixComplex(DynamicsArgsT<Inner<>, double> args, Contact<> &contact)
         : FluidDynamicsBase(args.identifier_, &contact), alpha_(Real(std::get<0>(args.others_)))
     {
-        particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity());
+        particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity()), registerCorrectionRecord(particles_);
     }
     LinearCorrectionMatrixComplex(Inner<> &inner, Contact<> &contact, Real alpha = Real(0))
         : FluidDynamicsBase(inner, &contact), alpha_(alpha)
     {
-        particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity());
+        particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity()), registerCorrectionRecord(particles_);
     }
     std::vector<BaseDynamics<void> *> deviceInteract(Real, const std::vector<BaseDynamics<void> *> &post)
     {
@@ -749,7 +760,7 @@ class KernelGradientIntegralBase : public fluid_dynamics::FluidDynamicsBase
     {
         correction_ = correction;
         particles_.registerStateVariable<Vecd>("KernelGradientIntegral");
-        if (correction) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity());
+        if (correction) particles_.registerStateVariable<Matd>("LinearCorrectionMatrix", Matd::Identity()), registerCorrectionRecord(particles_);
     }
 
   public:

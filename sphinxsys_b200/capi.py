@@ -48,7 +48,7 @@ _P = C.c_void_p
 class FluidView(C.Structure):
     _fields_ = [("n", C.c_uint32), ("pos", _P), ("vel", _P), ("dpos", _P), ("force", _P), ("force_prior", _P),
                 ("vol", _P), ("mass", _P), ("rho", _P), ("p", _P), ("compression", _P), ("compression_rate", _P),
-                ("vol_ref", _P), ("compression_sum", _P), ("B", _P), ("posvol", _P),
+                ("vol_ref", _P), ("compression_sum", _P), ("B", _P), ("correction_record", _P), ("posvol", _P),
                 ("posvolref", _P), ("posvolvel", _P), ("active_begin", C.c_uint32), ("active_end", C.c_uint32)]
 
 
@@ -134,6 +134,7 @@ SYMBOLS = {
     "sphb200_acoustic_1st_half_initialize": (_I, [_CTX, C.POINTER(FluidArgs), _F, _P]),
     "sphb200_acoustic_1st_half_interact": (_I, [_CTX, C.POINTER(FluidArgs), _F, _I, _P]),
     "sphb200_linear_correction_matrix": (_I, [_CTX, C.POINTER(FluidArgs), _F, _P]),
+    "sphb200_pack_correction_records": (_I, [_CTX, _U32, _P, _P, _P]),
     "sphb200_stream_create": (_I, [C.POINTER(_P)]),
     "sphb200_slab_select": (_I, [_CTX, C.POINTER(MeshT), _P, _U32, _U32, _I, _I, _P, _P, _P, _P]),
     "sphb200_stream_create_with_priority": (_I, [C.POINTER(_P), _I]),

@@ -47,6 +47,7 @@ struct FArgs
     const float4 *posvolref; // (x, y, z, VolRef)
     float4 *rec2;            // 32-byte records (x, y, z, Vol | vx, vy, vz, -)
     float *vol, *mass, *rho, *p, *C, *Cdot, *vol_ref, *Csum, *B;
+    float4 *brec; // LinearCorrectionRecord: (Bxx, Bxy, Bxz, Byy | Byz, Bzz, -, -), the symmetric part of B as one 32-byte gather record, or nullptr
     // wall
     u32 n_wall;
     const float4 *w_pos, *w_posvol, *w_posvolref, *w_vel, *w_acc, *w_n;
@@ -106,7 +107,7 @@ static int make_fargs(sphb200_context *ctx, const sphb200_fluid_args_t *s, FArgs
     a->force = (float4 *)f.force; a->force_prior = (float4 *)f.force_prior; a->posvol = (float4 *)f.posvol;
     a->posvolref = (const float4 *)f.posvolref; a->rec2 = (float4 *)f.posvolvel;
     a->vol = f.vol; a->mass = f.mass; a->rho = f.rho; a->p = f.p; a->C = f.compression; a->Cdot = f.compression_rate;
-    a->vol_ref = f.vol_ref; a->Csum = f.compression_sum; a->B = f.B;
+    a->vol_ref = f.vol_ref; a->Csum = f.compression_sum; a->B = f.B; a->brec = (float4 *)f.correction_record;
     const sphb200_wall_view_t &w = s->wall;
     a->n_wall = w.n;
     a->w_pos = (const float4 *)w.pos; a->w_posvol = (const float4 *)w.posvol; a->w_posvolref = (const float4 *)w.posvolref; a->w_vel = (const float4 *)w.vel_ave;
@@ -788,6 +789,46 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
         const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
         float4 xjs[NB_U];
         float pjs[NB_U];
+        if (CORR && a.brec)
+        {
+            // sum_j dWV (p_i B_j + p_j B_i) e = p_i sum_j dWV B_j e + B_i sum_j p_j dWV e: B_i leaves the pair loop, and B_j
+            // comes as ONE 32-byte record of its six distinct entries (B is the regularised inverse of the symmetric
+            // sum_j r (x) r dW V / |r|: symmetric up to rounding; the record holds (B + B^T) / 2) instead of nine 4-byte gathers
+            float4 bas[NB_U], bbs[NB_U];
+            float ax = 0.f, ay = 0.f, az = 0.f; // sum_j dWV B_j e
+            for_neighbors(
+                idx, cnt,
+                [&](int u, u32 j) {
+                    xjs[u] = a.posvol[j];
+                    pjs[u] = a.p[j];
+                    load_rec2(a.brec, j, bas[u], bbs[u]);
+                },
+                [&](int u, bool valid) {
+                    const float4 xj = xjs[u], ba = bas[u], bb = bbs[u];
+                    const float p_j = pjs[u];
+                    float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                    float r2 = dx * dx + dy * dy + dz * dz;
+                    float r, inv_r;
+                    dist(r2, r, inv_r);
+                    float dWV = kernel_dw<ANALYTIC>(a, tab, r) * xj.w;
+                    dWV = valid ? dWV : 0.f;
+                    const float g = dWV * inv_r; // dWV e = g d
+                    const float gx = g * dx, gy = g * dy, gz = g * dz;
+                    ax += ba.x * gx + ba.y * gy + ba.z * gz;
+                    ay += ba.y * gx + ba.w * gy + bb.x * gz;
+                    az += ba.z * gx + bb.x * gy + bb.y * gz;
+                    fx += p_j * gx; fy += p_j * gy; fz += p_j * gz; // sum_j p_j dWV e (B_i applied below)
+#if SPH_TRIM & 4
+                    if (RIEMANN) diss += (p_i - p_j) * dWV;
+#else
+                    if (RIEMANN) diss += (p_i - p_j) * a.inv_Z_ave * dWV;
+#endif
+                });
+            const float3 bs = mat_vec(Bi, make_float3(fx, fy, fz));
+            fx = -(p_i * ax + bs.x); fy = -(p_i * ay + bs.y); fz = -(p_i * az + bs.z);
+        }
+        else
+        {
         u32 js[NB_U];
         for_neighbors(
             idx, cnt,
@@ -830,6 +871,7 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
 #endif
             },
             [&](u32 j) { prefetch_record(a.posvol + j); });
+        }
     }
     float wx = 0.f, wy = 0.f, wz = 0.f, wdiss = 0.f;
     const float vol_i = xi.w;
@@ -1175,12 +1217,13 @@ __global__ void __launch_bounds__(FL_THREADS) k_linear_correction(FArgs a, KTab 
     float b[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k) b[k] = 0.f;
-    auto accumulate = [&](float4 xj) {
+    auto accumulate = [&](float4 xj, bool valid) {
         float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
         float r2 = dx * dx + dy * dy + dz * dz;
         float r, inv_r;
         dist(r2, r, inv_r);
         float g = eval_tab(tab, r, a.q_scale) * inv_r * xj.w; // dW/r * V_j : nablaW V = g * d
+        g = valid ? g : 0.f;
         float gx = g * dx, gy = g * dy, gz = g * dz;
         b[0] -= dx * gx; b[1] -= dx * gy; b[2] -= dx * gz;
         b[3] -= dy * gx; b[4] -= dy * gy; b[5] -= dy * gz;
@@ -1189,13 +1232,15 @@ __global__ void __launch_bounds__(FL_THREADS) k_linear_correction(FArgs a, KTab 
     {
         u32 cnt = a.in_count[t];
         const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
-        for (u32 k = 0; k < cnt; ++k) accumulate(a.posvol[idx[32ull * k]]);
+        float4 xjs[NB_U];
+        for_neighbors(idx, cnt, [&](int u, u32 j) { xjs[u] = a.posvol[j]; }, [&](int u, bool valid) { accumulate(xjs[u], valid); });
     }
     if (a.n_wall)
     {
         u32 cnt = a.ct_count[t];
         const u32 *idx = a.ct_index + (u64)a.ct_slice[t >> 5] + (t & 31u);
-        for (u32 k = 0; k < cnt; ++k) accumulate(a.w_posvol[idx[32ull * k]]);
+        float4 xjs[NB_U];
+        for_neighbors(idx, cnt, [&](int u, u32 j) { xjs[u] = a.w_posvol[j]; }, [&](int u, bool valid) { accumulate(xjs[u], valid); });
     }
     if (a.dim == 2) b[8] = 1.0f;
     float det = det3(b);
@@ -1220,12 +1265,36 @@ __global__ void __launch_bounds__(FL_THREADS) k_linear_correction(FArgs a, KTab 
         for (int c = 0; c < 3; ++c)
             inv[3 * r + c] = ib[3 * r] * bt[c] + ib[3 * r + 1] * bt[3 + c] + ib[3 * r + 2] * bt[6 + c];
     float wgt = det / (det + det_sqr);
+    float B[9];
 #pragma unroll
     for (int k = 0; k < 9; ++k)
     {
         float id = (k == 0 || k == 4 || k == 8) ? 1.0f : 0.f;
-        a.B[9ull * i + k] = wgt * inv[k] + (1.0f - wgt) * id;
+        B[k] = wgt * inv[k] + (1.0f - wgt) * id;
+        a.B[9ull * i + k] = B[k];
     }
+    if (a.brec) // the gather record of the 1st-half interaction (k_a1_interact): the symmetric part, six entries
+    {
+        a.brec[2ull * i] = make_float4(B[0], 0.5f * (B[1] + B[3]), 0.5f * (B[2] + B[6]), B[4]);
+        a.brec[2ull * i + 1] = make_float4(0.5f * (B[5] + B[7]), B[8], 0.f, 0.f);
+    }
+}
+
+// the gather record of given matrices (matrices written outside the library, e.g. uploaded by the host)
+__global__ void __launch_bounds__(256) k_pack_correction_records(u32 n, const float *__restrict__ B, float4 *__restrict__ rec)
+{
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float b[9];
+    load_mat(B, i, b);
+    rec[2ull * i] = make_float4(b[0], 0.5f * (b[1] + b[3]), 0.5f * (b[2] + b[6]), b[4]);
+    rec[2ull * i + 1] = make_float4(0.5f * (b[5] + b[7]), b[8], 0.f, 0.f);
+}
+extern "C" int sphb200_pack_correction_records(sphb200_context_t *ctx, uint32_t n, const float *B, void *correction_record, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && (n == 0 || (B && correction_record)), "null pointer");
+    if (n) SPH_LAUNCH(ctx, k_pack_correction_records, sph_blocks(n, 256), 256, 0, stream, n, B, (float4 *)correction_record);
+    return 0;
 }
 
 extern "C" int sphb200_linear_correction_matrix(sphb200_context_t *ctx, const sphb200_fluid_args_t *s, float alpha, void *stream)
@@ -1260,14 +1329,18 @@ __global__ void __launch_bounds__(FL_THREADS) k_surface_interact(FArgs a, KTab d
     const u32 cnt = a.in_count[t];
     const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
     float pd = 0.f;
-#pragma unroll 4
-    for (u32 k = 0; k < cnt; ++k)
     {
-        float4 xj = a.posvol[idx[32ull * k]];
-        float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-        float r, inv_r;
-        dist(dx * dx + dy * dy + dz * dz, r, inv_r);
-        pd -= kernel_dw<ANALYTIC>(a, tab, r) * xj.w * r;
+        float4 xjs[SUM_U];
+        for_neighbors<SUM_U>(
+            idx, cnt, [&](int u, u32 j) { xjs[u] = a.posvol[j]; },
+            [&](int u, bool valid) {
+                const float4 xj = xjs[u];
+                float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                float r, inv_r;
+                dist(dx * dx + dy * dy + dz * dz, r, inv_r);
+                const float w = kernel_dw<ANALYTIC>(a, tab, r) * xj.w * r;
+                pd -= valid ? w : 0.f;
+            });
     }
     if (pd < threshold && previous[i] != 1)
     {
@@ -1281,15 +1354,17 @@ __global__ void __launch_bounds__(FL_THREADS) k_surface_interact(FArgs a, KTab d
     {
         u32 wc = a.ct_count[t];
         const u32 *widx = a.ct_index + (u64)a.ct_slice[t >> 5] + (t & 31u);
-#pragma unroll 4
-        for (u32 k = 0; k < wc; ++k)
-        {
-            float4 xj = a.w_posvol[widx[32ull * k]];
-            float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
-            float r, inv_r;
-            dist(dx * dx + dy * dy + dz * dz, r, inv_r);
-            pw -= kernel_dw<ANALYTIC>(a, tab, r) * xj.w * r;
-        }
+        float4 xjs[SUM_U];
+        for_neighbors<SUM_U>(
+            widx, wc, [&](int u, u32 j) { xjs[u] = a.w_posvol[j]; },
+            [&](int u, bool valid) {
+                const float4 xj = xjs[u];
+                float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
+                float r, inv_r;
+                dist(dx * dx + dy * dy + dz * dz, r, inv_r);
+                const float w = kernel_dw<ANALYTIC>(a, tab, r) * xj.w * r;
+                pw -= valid ? w : 0.f;
+            });
     }
     pos_div[i] = pd + pw;
 }
@@ -1307,17 +1382,25 @@ __global__ void __launch_bounds__(FL_THREADS) k_surface_update(FArgs a, const fl
         const float4 xi = a.posvol[i];
         const u32 cnt = a.in_count[t];
         const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
+        // batched like the pair loops (for_neighbors): an interior particle reads PositionDivergence of ALL its neighbours and
+        // finds none below the threshold — a loop with an early exit kept one dependent gather in flight per warp
         bool very_near = false;
-        for (u32 k = 0; k < cnt && !very_near; ++k)
-        {
-            u32 j = idx[32ull * k];
-            if (pos_div[j] < threshold)
-            {
-                float4 xj = a.posvol[j];
-                float dx = __fsub_rn(xi.x, xj.x), dy = __fsub_rn(xi.y, xj.y), dz = __fsub_rn(xi.z, xj.z);
-                very_near = sqrtf(norm2_rn(dx, dy, dz)) < smoothing_length; // same rounding as the CPU evaluation
-            }
-        }
+        float pds[SUM_U];
+        u32 js[SUM_U];
+        for_neighbors<SUM_U>(
+            idx, cnt,
+            [&](int u, u32 j) {
+                pds[u] = pos_div[j];
+                js[u] = j;
+            },
+            [&](int u, bool valid) {
+                if (valid && !very_near && pds[u] < threshold)
+                {
+                    float4 xj = a.posvol[js[u]];
+                    float dx = __fsub_rn(xi.x, xj.x), dy = __fsub_rn(xi.y, xj.y), dz = __fsub_rn(xi.z, xj.z);
+                    very_near = sqrtf(norm2_rn(dx, dy, dz)) < smoothing_length; // same rounding as the CPU evaluation
+                }
+            });
         if (!very_near) ind = 0;
     }
     indicator[i] = ind;

@@ -279,7 +279,7 @@ def _compare(gpu, o32, o64, names_real, names_vec, tag, tol=TOL):
     return rep
 
 
-def _one_acoustic_step_by_phase(gpu, o32, o64, tag):
+def _one_acoustic_step_by_phase(gpu, o32, o64, tag, correction=False):
     """Each dynamics of one acoustic step, in the order of dambreak.cpp:188-205, compared field by field."""
     gpu.exec("density_summation")
     for o in (o32, o64):
@@ -297,6 +297,14 @@ def _one_acoustic_step_by_phase(gpu, o32, o64, tag):
     assert abs(ac - o32.exec("acoustic_dt")) <= 1e-6 * ac
     assert np.float32(gpu.exec("advection_dt_reduced")) == np.float32(o32.exec("advection_dt_reduced"))  # exact max
     dt = float(np.float32(ac))
+    if correction:  # LinearCorrectionMatrix<Inner<WithUpdate>, Contact<>>, dambreak.cpp:192
+        gpu.exec("linear_correction")
+        for o in (o32, o64):
+            o.exec("linear_correction")
+        g, r64 = gpu_field(gpu, "LinearCorrectionMatrix"), oracle_field(o64, "LinearCorrectionMatrix", 9)
+        e = rel_err(g, r64)
+        assert e <= TOL, f"{tag}LinearCorrectionMatrix: gpu vs oracle64 {e:.3e}"
+        _report(tag + "linear_correction", {"LinearCorrectionMatrix": {"gpu_vs_f64": e, "oracle32_vs_f64": rel_err(oracle_field(o32, "LinearCorrectionMatrix", 9), r64)}})
     # 1st half, phase by phase
     gpu.acoustic1_phase(0, dt)
     for o in (o32, o64):
@@ -358,6 +366,34 @@ def test_per_dynamics_parity_variants_3d(riemann, kernel):
         gpu2.exec("advection_setup")
         gpu2.exec("acoustic1", 1e-4)
         assert not np.any(gpu_field(gpu2, "CompressionRate"))
+
+
+def test_per_dynamics_parity_correction_3d():
+    """The LinearCorrectionCK aliases the complete case file runs (dambreak.cpp:117-134: AcousticStep1stHalfWithWallRiemannCorrectionCK,
+    AcousticStep2ndHalfWithWallRiemannCorrectionCK, LinearCorrectionMatrixComplex): the matrix and every dynamics of one acoustic
+    step within 1e-5 of the fp64 oracle. The 1st half reads B of every neighbour (acoustic_step_1st_half.hpp:98-104) — on the
+    device through the 32-byte record of its symmetric part (sphb200_fluid_view_t::correction_record), with B_i factored out of
+    the pair loop."""
+    from sphinxsys_b200 import cases
+    case = cases.dam_break(dim=3, dp=0.05)
+    pos, vel = perturb_state(case)
+    case.fluid_pos = pos
+    gpu = make_gpu(case, correction=True, fused_time_step=False)
+    gpu.upload("Velocity", vel)
+    gpu.initialize()
+    o32, o64 = make_oracle(case, f64=False, correction=1), make_oracle(case, f64=True, correction=1)
+    for o in (o32, o64):
+        o.real("Velocity", 3)[:] = vel.reshape(-1)
+        o.exec("prepare_ck")
+    _one_acoustic_step_by_phase(gpu, o32, o64, "correction_", correction=True)
+    # a second acoustic step on the state the first one left (B unchanged, pressure and velocity no longer the start values)
+    dt = float(np.float32(gpu.exec("acoustic_dt")))
+    gpu.exec("acoustic1", dt)
+    gpu.exec("acoustic2", dt)
+    for o in (o32, o64):
+        o.exec("acoustic1", dt)
+        o.exec("acoustic2", dt)
+    _compare(gpu, o32, o64, ["CompressionRate", "Compression", "Density", "Pressure"], ["Force", "Velocity", "Displacement"], "correction_step2_")
 
 
 @pytest.mark.parametrize("riemann,kernel", [(2, "wendland"), (0, "wendland")])
