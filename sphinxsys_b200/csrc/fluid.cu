@@ -1206,10 +1206,11 @@ __device__ __forceinline__ void inv3(const float *m, float *o)
     o[6] = (m[3] * m[7] - m[4] * m[6]) / d; o[7] = (m[1] * m[6] - m[0] * m[7]) / d; o[8] = (m[0] * m[4] - m[1] * m[3]) / d;
 }
 
+template <bool ANALYTIC>
 __global__ void __launch_bounds__(FL_THREADS) k_linear_correction(FArgs a, KTab dwtab, float alpha)
 {
     __shared__ float4 tab[KT_SLOTS];
-    stage_tab(dwtab, tab);
+    if (!ANALYTIC) stage_tab(dwtab, tab);
     u32 t = active_slot(a);
     if (t < a.begin || t >= a.end) return;
     const u32 i = a.order ? a.order[t] : t;
@@ -1222,7 +1223,7 @@ __global__ void __launch_bounds__(FL_THREADS) k_linear_correction(FArgs a, KTab 
         float r2 = dx * dx + dy * dy + dz * dz;
         float r, inv_r;
         dist(r2, r, inv_r);
-        float g = eval_tab(tab, r, a.q_scale) * inv_r * xj.w; // dW/r * V_j : nablaW V = g * d
+        float g = kernel_dw<ANALYTIC>(a, tab, r) * inv_r * xj.w; // dW/r * V_j : nablaW V = g * d
         g = valid ? g : 0.f;
         float gx = g * dx, gy = g * dy, gz = g * dz;
         b[0] -= dx * gx; b[1] -= dx * gy; b[2] -= dx * gz;
@@ -1306,7 +1307,11 @@ extern "C" int sphb200_linear_correction_matrix(sphb200_context_t *ctx, const sp
     if (rc) return rc;
     SPH_CHECK_ARG(ctx, a.n == 0 || (a.posvol && a.B && a.in_count && a.in_slice && a.in_index), "null fluid array");
     SPH_CHECK_ARG(ctx, a.n_wall == 0 || (a.w_posvol && a.ct_count && a.ct_slice && a.ct_index), "null wall array");
-    if (a.end > a.begin) SPH_LAUNCH(ctx, k_linear_correction, active_blocks(a, FL_THREADS), FL_THREADS, 0, stream, a, dwtab, alpha);
+    if (a.end > a.begin)
+    {
+        if (a.analytic) SPH_LAUNCH(ctx, k_linear_correction<true>, active_blocks(a, FL_THREADS), FL_THREADS, 0, stream, a, dwtab, alpha);
+        else SPH_LAUNCH(ctx, k_linear_correction<false>, active_blocks(a, FL_THREADS), FL_THREADS, 0, stream, a, dwtab, alpha);
+    }
     return 0;
 }
 
