@@ -413,31 +413,10 @@ def run_ours(args, rank, world, local_rank):
         solver.exec("rebuild")
         solver.exec("relations")
 
-    # ---- developed state: the same K steps after the flow has left the initial lattice ----
-    developed = None
-    if not args.no_extras and args.developed_steps > 0:
-        solver.exec("set_sort_interval", 100)
-        solver.run_outer(args.developed_steps)
-        solver.exec("set_sort_interval", cadence)
-        sampler2 = ClockSampler(local_rank)
-        if rank == 0:
-            sampler2.start()
-        ms_d, n_ac_d, launches_d = timed_outer(solver, args.steps)
-        clocks_d = sampler2.stop() if rank == 0 else None
-        n_own_d = solver.own_range()[1]
-        roof_d, (ms_a1_d, ms_a2_d) = time_stream_kernels(solver, torch, n_own_d, peak, peak_kind, (clocks_d or {}).get("sm_mhz") or sm_mhz, counters)
-        pairs_in, pairs_ct = sum_over_ranks(solver.exec("inner_pairs"), solver.exec("contact_pairs"))
-        own_total, own_max = sum_over_ranks(n_own_d)[0], max_over_ranks(n_own_d)[0]
-        developed = {"after_outer_steps": args.warmup + args.steps + args.developed_steps, "physical_time": solver.physical_time,
-                     "value": n_fluid * float(n_ac_d) / (ms_d * 1e-3), "unit": "particle-steps/s", "ms_per_step": ms_d / max(args.steps, 1),
-                     "ms_per_acoustic_step": ms_d / max(n_ac_d, 1),
-                     "acoustic_steps_per_outer": n_ac_d / max(args.steps, 1), "gpu_launches": int(launches_d),
-                     "inner_neighbours_per_particle": pairs_in / max(own_total, 1.0),
-                     "wall_neighbours_per_particle": pairs_ct / max(own_total, 1.0),
-                     "load_imbalance_max_over_mean": own_max / max(own_total / world, 1.0),
-                     "k_a2_ms": ms_a2_d, "k_a1_ms": ms_a1_d, "roofline_frac_k_a2": roof_d["frac"], "second": roof_d["second"],
-                     "other_kernels_ms": roof_d["other_kernels_ms"], "clocks": clocks_d}
-
+    # (the developed-state leg runs on its own solver AFTER the e2e leg — developed_leg() below: the e2e leg takes the state the
+    # timed window left, i.e. the kind of state `value` was measured on, at every N. It used to inherit the developed state,
+    # which at the finer spacings of the N-GPU runs holds 2-3 acoustic steps per advection step instead of 5: an e2e rate in
+    # particle-STEPS per second that could not be compared with the one at N = 1.)
     # ---- e2e: the same step driven from HOST buffers (pinned), H2D of the evolving state + D2H of the result ----
     in_names = ["Position", "VolumetricMeasure", "Velocity", "Mass", "ForcePrior", "Compression", "CompressionRate",
                 "VolumetricMeasureRef", "PreviousGravityForceCK"]
@@ -566,6 +545,11 @@ def run_ours(args, rank, world, local_rank):
 
     # ---- the other BASELINE configs, each a small driver-visible record (failures are reported, not fatal) ----
     extras = {}
+    developed = None
+    if not args.no_extras and args.developed_steps > 0:
+        developed = guarded_leg(lambda: developed_leg(args, dp, cadence, rank, world, local_rank, torch, new_unique_id, timed_outer,
+                                                      sum_over_ranks, max_over_ranks, n_fluid, peak, peak_kind, sm_mhz, counters), rank)
+        barrier()
     if not args.no_extras:
         extras["complete_case"] = guarded_leg(lambda: complete_case_leg(args, dp, rank, world, local_rank, torch, new_unique_id, timed_outer,
                                                                        sum_over_ranks), rank)
@@ -624,6 +608,40 @@ def guarded_leg(fn, rank):
         if rank == 0:
             traceback.print_exc(file=sys.stderr)
         return {"error": f"{type(e).__name__}: {str(e)[:300]}"}
+
+
+def developed_leg(args, dp, cadence, rank, world, local_rank, torch, new_unique_id, timed_outer, sum_over_ranks, max_over_ranks, n_fluid,
+                  peak, peak_kind, sm_mhz, counters):
+    """the same K steps timed after the flow has left the initial lattice (--developed-steps more advection steps:
+    free surface formed, fewer neighbours per particle, re-cuts done) — on a solver of its own, same case and spacing."""
+    from sphinxsys_b200.host import DamBreakCK
+    solver = DamBreakCK(None, dim=3, dp=dp, device_index=local_rank, fused_time_step=True, sort_interval=100, generate=True,
+                        rank=rank, nranks=world, unique_id=new_unique_id(), serial_exchange=args.serial_exchange, recut_interval=100)
+    solver.initialize()
+    solver.run_outer(args.warmup + args.steps + args.developed_steps)
+    solver.exec("set_sort_interval", cadence)
+    sampler2 = ClockSampler(local_rank)
+    if rank == 0:
+        sampler2.start()
+    ms_d, n_ac_d, launches_d = timed_outer(solver, args.steps)
+    clocks_d = sampler2.stop() if rank == 0 else None
+    n_own_d = solver.own_range()[1]
+    roof_d, (ms_a1_d, ms_a2_d) = time_stream_kernels(solver, torch, n_own_d, peak, peak_kind, (clocks_d or {}).get("sm_mhz") or sm_mhz, counters)
+    pairs_in, pairs_ct = sum_over_ranks(solver.exec("inner_pairs"), solver.exec("contact_pairs"))
+    own_total, own_max = sum_over_ranks(n_own_d)[0], max_over_ranks(n_own_d)[0]
+    developed = {"after_outer_steps": args.warmup + args.steps + args.developed_steps, "physical_time": solver.physical_time,
+                 "value": n_fluid * float(n_ac_d) / (ms_d * 1e-3), "unit": "particle-steps/s", "ms_per_step": ms_d / max(args.steps, 1),
+                 "ms_per_acoustic_step": ms_d / max(n_ac_d, 1),
+                 "acoustic_steps_per_outer": n_ac_d / max(args.steps, 1), "gpu_launches": int(launches_d),
+                 "inner_neighbours_per_particle": pairs_in / max(own_total, 1.0),
+                 "wall_neighbours_per_particle": pairs_ct / max(own_total, 1.0),
+                 "load_imbalance_max_over_mean": own_max / max(own_total / world, 1.0),
+                 "k_a2_ms": ms_a2_d, "k_a1_ms": ms_a1_d, "roofline_frac_k_a2": roof_d["frac"], "second": roof_d["second"],
+                 "other_kernels_ms": roof_d["other_kernels_ms"], "clocks": clocks_d}
+    solver.close()
+    del solver
+    torch.cuda.empty_cache()
+    return developed
 
 
 def complete_case_leg(args, dp, rank, world, local_rank, torch, new_unique_id, timed_outer, sum_over_ranks):
