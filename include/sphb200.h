@@ -412,6 +412,13 @@ int sphb200_free_surface_indication_sweep(sphb200_context_t *ctx, const sphb200_
 int sphb200_interpolate(sphb200_context_t *ctx, const sphb200_kernel_t *kernel, const sphb200_vec4_t *src_pos, uint32_t n_src,
                         sphb200_relation_t rel, const sphb200_vec4_t *tar_posvol, const float *tar_data, int width, float *out,
                         void *stream);
+/* Interpolation<Contact<DataType, RestoringCorrection>>::InteractKernel::interact: the first-order consistent interpolation
+ * (constant and linear fields are reproduced on any neighbour set with a regular restoring matrix), same arguments;
+ * out[i] = (restoring_i^-1).row(0) . prediction_i with restoring_i = Eps I + sum_j A_ij, prediction_i = sum_j A_ij.col(0) data[j].
+ * ref: general_dynamics/interpolation_dynamics.hpp:72-100; known answer unit_test_interpolation_ck/2d_interpolation.cpp */
+int sphb200_interpolate_restoring(sphb200_context_t *ctx, const sphb200_kernel_t *kernel, const sphb200_vec4_t *src_pos,
+                                  uint32_t n_src, sphb200_relation_t rel, const sphb200_vec4_t *tar_posvol, const float *tar_data,
+                                  int width, float *out, void *stream);
 /* InteractionDynamicsCK<ViscousForceCK<Inner<WithUpdate, Viscosity, Correction>, Contact<Wall, Viscosity, Correction>>>::exec:
  * inner interact -> wall interact -> ForcePriorCK update (ForcePrior += F - Previous; Previous = F), one launch.
  * Needs fluid.posvolvel (the 32-byte gather record) and fluid.force_prior; material.correction selects the B-matrix form.

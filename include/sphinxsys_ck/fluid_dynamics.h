@@ -812,7 +812,13 @@ class TotalMechanicalEnergyCK : public fluid_dynamics::FluidDynamicsBase
 // ---- observation (general_dynamics/interpolation_dynamics.h:43-150, io_system/io_observation_ck.h:38-107) ----
 // ObservingQuantityCK<P, DataType>(contact, "Name"): Interpolation<Contact<DataType>> of a variable of the observed
 // body at the particles of an observer body; the result lives in the observer's variable of the same name.
-template <class ExecutionPolicy, class DataType> class ObservingQuantityCK : public BaseDynamics<void>
+struct RestoringCorrection {}; // Interpolation<Contact<DataType, RestoringCorrection>>, interpolation_dynamics.hpp:72-100
+template <class... Parameters> struct UsesRestoringCorrection : std::false_type {};
+template <class First, class... Rest>
+struct UsesRestoringCorrection<First, Rest...>
+    : std::integral_constant<bool, std::is_same<First, RestoringCorrection>::value || UsesRestoringCorrection<Rest...>::value> {};
+
+template <class ExecutionPolicy, class DataType, class... Parameters> class ObservingQuantityCK : public BaseDynamics<void>
 {
     Contact<> &contact_;
     std::string variable_name_;
@@ -833,20 +839,29 @@ template <class ExecutionPolicy, class DataType> class ObservingQuantityCK : pub
         SPHBody &observer = contact_.source_, &observed = contact_.target_;
         observed.refreshPosVol();
         BaseParticles &op = observer.getBaseParticles(), &tp = observed.getBaseParticles();
-        SPHCK_CALL(sphb200_interpolate, &contact_.kernel_, (const sphb200_vec4_t *)op.deviceData<Vecd>("Position"),
-                   (uint32_t)op.TotalRealParticles(), contact_.view(), (const sphb200_vec4_t *)tp.deviceData<Vecd>("PosVol"),
-                   (const float *)tp.template deviceData<DataType>(variable_name_), std::is_same<DataType, Vecd>::value ? 4 : 1,
-                   (float *)dv_interpolated_quantities_->deviceAddress(), execution_instance().stream());
+        const sphb200_vec4_t *src = (const sphb200_vec4_t *)op.deviceData<Vecd>("Position"), *tar = (const sphb200_vec4_t *)tp.deviceData<Vecd>("PosVol");
+        const float *data = (const float *)tp.template deviceData<DataType>(variable_name_);
+        float *out = (float *)dv_interpolated_quantities_->deviceAddress();
+        const int width = std::is_same<DataType, Vecd>::value ? 4 : 1;
+        // (observing "Position" writes the observer's own positions — the reference registers the interpolated variable under
+        // the same name, interpolation_dynamics.hpp:20-27; every thread reads and writes its own observer only)
+        if (UsesRestoringCorrection<Parameters...>::value)
+            SPHCK_CALL(sphb200_interpolate_restoring, &contact_.kernel_, src, (uint32_t)op.TotalRealParticles(), contact_.view(), tar, data,
+                       width, out, execution_instance().stream());
+        else
+            SPHCK_CALL(sphb200_interpolate, &contact_.kernel_, src, (uint32_t)op.TotalRealParticles(), contact_.view(), tar, data, width,
+                       out, execution_instance().stream());
     }
+
 };
 
 // ObservedQuantityRecording<P, DataType>(contact, "Name"): writeToFile(iteration) runs the observation, brings the values
 // to the host and appends one record (physical time + one value per observer); records are kept in memory and, when an
 // output path is set, appended to a .dat file in the reference's column layout (io_observation_ck.h:69-94).
-template <class ExecutionPolicy, class DataType> class ObservedQuantityRecording
+template <class ExecutionPolicy, class DataType, class... Parameters> class ObservedQuantityRecording
 {
     SPHBody &observer_;
-    ObservingQuantityCK<ExecutionPolicy, DataType> observation_method_;
+    ObservingQuantityCK<ExecutionPolicy, DataType, Parameters...> observation_method_;
     DiscreteVariable<DataType> *dv_interpolated_quantities_;
     size_t number_of_observe_;
     SingleVariable<Real> *sv_physical_time_;

@@ -842,6 +842,76 @@ template <class R> struct Sim
             out[i] = q / (total + R(2.71051e-20));
         }
     }
+    // Interpolation<Contact<DataType, RestoringCorrection>>::InteractKernel::interact, general_dynamics/interpolation_dynamics.hpp:72-100:
+    // the first-order consistent interpolation (reproduces constant and linear fields on any neighbour set whose restoring
+    // matrix is regular; known answer: unit_test_interpolation_ck/2d_interpolation.cpp interpolates "Position" at a random
+    // point of a randomised lattice and expects the point back to 1e-6). Matrices are (dim + 1) square; Eigen's inverse of
+    // a fixed 3x3 / 4x4 matrix is the cofactor formula, of which only row 0 is needed.
+    //   A(0,0) = W V, A(0,1+b) = -W V r_b, A(1+a,0) = dW V e_a, A(1+a,1+b) = -dW V r_a e_b;   restoring = Eps I + sum_j A_j
+    //   prediction = sum_j A_j.col(0) data_j;   out = (restoring^-1).row(0) . prediction
+    static R minorDet(const R M[4][4], int n, int skip_row, int skip_col)
+    {
+        int rr[3] = {0, 0, 0}, cc[3] = {0, 0, 0}, a = 0, b = 0;
+        for (int k = 0; k < n; ++k)
+        {
+            if (k != skip_row) rr[a++] = k;
+            if (k != skip_col) cc[b++] = k;
+        }
+        if (n == 3) return M[rr[0]][cc[0]] * M[rr[1]][cc[1]] - M[rr[0]][cc[1]] * M[rr[1]][cc[0]];
+        return M[rr[0]][cc[0]] * (M[rr[1]][cc[1]] * M[rr[2]][cc[2]] - M[rr[1]][cc[2]] * M[rr[2]][cc[1]]) -
+               M[rr[0]][cc[1]] * (M[rr[1]][cc[0]] * M[rr[2]][cc[2]] - M[rr[1]][cc[2]] * M[rr[2]][cc[0]]) +
+               M[rr[0]][cc[2]] * (M[rr[1]][cc[0]] * M[rr[2]][cc[1]] - M[rr[1]][cc[1]] * M[rr[2]][cc[0]]);
+    }
+    void observeRestoring(const std::string &name, int width)
+    {
+        if (!observer.n) return;
+        const int dim = P.dim, n = dim + 1;
+        const std::vector<R> &opos = observer.r("Position", 3), &pos = fluid.r("Position", 3), &Vol = fluid.r("VolumetricMeasure");
+        const std::vector<R> &data = fluid.r(name, (size_t)width);
+        std::vector<R> &out = observer.r("Restored" + name, (size_t)width);
+        for (u32 i = 0; i < observer.n; ++i)
+        {
+            R M[4][4], pred[4][3];
+            for (int a = 0; a < 4; ++a)
+            {
+                for (int b = 0; b < 4; ++b) M[a][b] = a == b ? std::numeric_limits<R>::epsilon() : R(0);
+                for (int c = 0; c < 3; ++c) pred[a][c] = R(0);
+            }
+            for (u32 m = observer_contact.offset[i]; m < observer_contact.offset[i + 1]; ++m)
+            {
+                u32 j = observer_contact.index[m];
+                V3<R> r = vec(opos, i) - vec(pos, j);
+                V3<R> e = r.normalized();
+                const R rv[3] = {r.x, r.y, r.z}, ev[3] = {e.x, e.y, e.z};
+                R WV = K.W(r) * Vol[j], dWV = K.dW(r) * Vol[j];
+                R col0[4];
+                col0[0] = WV;
+                M[0][0] += WV;
+                for (int b = 0; b < dim; ++b) M[0][1 + b] += -WV * rv[b];
+                for (int a = 0; a < dim; ++a)
+                {
+                    col0[1 + a] = dWV * ev[a];
+                    M[1 + a][0] += dWV * ev[a];
+                    for (int b = 0; b < dim; ++b) M[1 + a][1 + b] += -dWV * rv[a] * ev[b];
+                }
+                for (int a = 0; a < n; ++a)
+                    for (int c = 0; c < width; ++c) pred[a][c] += col0[a] * data[(size_t)width * j + c];
+            }
+            // row 0 of the inverse: (M^-1)(0,k) = cofactor(k,0) / det
+            R cof[4], det = R(0);
+            for (int k = 0; k < n; ++k)
+            {
+                cof[k] = ((k & 1) ? R(-1) : R(1)) * minorDet(M, n, k, 0);
+                det += M[k][0] * cof[k];
+            }
+            for (int c = 0; c < width; ++c)
+            {
+                R v = R(0);
+                for (int k = 0; k < n; ++k) v += (cof[k] / det) * pred[k][c];
+                out[(size_t)width * i + c] = v;
+            }
+        }
+    }
     void recordProbes()
     {
         if (!observer.n) return;
@@ -1546,6 +1616,8 @@ double execOp(Sim<R> &s, const std::string &op, double a0, double a1, double a2,
     else if (op == "set_observers") { s.observer.n = (u32)a0; s.observer.real.clear(); }
     else if (op == "observer_relation") s.observerRelation();
     else if (op == "observe_pressure") s.observe("Pressure");
+    else if (op == "observe_restoring_pressure") s.observeRestoring("Pressure", 1);
+    else if (op == "observe_restoring_position") s.observeRestoring("Position", 3);
     else if (op == "probe_records") return (double)s.probe_series.size();
     else if (op == "energy") return s.mechanicalEnergy();
     else if (op == "legacy_density_summation") s.legacyDensitySummation();

@@ -149,6 +149,7 @@ SYMBOLS = {
     "sphb200_free_surface_indication": (_I, [_CTX, C.POINTER(FluidArgs), _P, _P, _P, _F, _F, _P]),
     "sphb200_free_surface_indication_sweep": (_I, [_CTX, C.POINTER(FluidArgs), _P, _P, _P, _F, _F, _I, _P]),
     "sphb200_interpolate": (_I, [_CTX, C.POINTER(KernelT), _P, C.c_uint32, RelationT, _P, _P, _I, _P, _P]),
+    "sphb200_interpolate_restoring": (_I, [_CTX, C.POINTER(KernelT), _P, C.c_uint32, RelationT, _P, _P, _I, _P, _P]),
     "sphb200_comm_unique_id": (_I, [_P]),
     "sphb200_comm_create": (_I, [_CTX, _I, _I, _P]),
     "sphb200_comm_destroy": (_I, [_CTX]),

@@ -1529,6 +1529,135 @@ extern "C" int sphb200_interpolate(sphb200_context_t *ctx, const sphb200_kernel_
     return 0;
 }
 
+// Interpolation<Contact<DataType, RestoringCorrection>>::InteractKernel::interact, general_dynamics/interpolation_dynamics.hpp:72-100:
+// the first-order consistent interpolation — reproduces constant and linear fields on ANY neighbour set whose restoring
+// matrix is regular (one-sided neighbourhoods at walls and free surfaces included). Per observer, with n = dim + 1:
+//   A_j(0,0) = W V, A_j(0,1+b) = -W V r_b, A_j(1+a,0) = dW V e_a, A_j(1+a,1+b) = -dW V r_a e_b
+//   restoring = Eps I + sum_j A_j;  prediction = sum_j A_j.col(0) data_j;  out = (restoring^-1).row(0) . prediction
+// Row 0 of the inverse by cofactors (what Eigen's fixed-size inverse evaluates): (M^-1)(0,k) = cofactor(k,0) / det.
+template <int K> __device__ __forceinline__ float minor3_col0(const float (&M)[4][4]) // n == 3: rows != K of {0,1,2}, columns 1,2
+{
+    constexpr int r0 = K == 0 ? 1 : 0, r1 = K == 2 ? 1 : 2;
+    return M[r0][1] * M[r1][2] - M[r0][2] * M[r1][1];
+}
+template <int K> __device__ __forceinline__ float minor4_col0(const float (&M)[4][4]) // n == 4: rows != K of {0,1,2,3}, columns 1,2,3
+{
+    constexpr int r0 = K == 0 ? 1 : 0, r1 = K <= 1 ? 2 : 1, r2 = K == 3 ? 2 : 3;
+    return M[r0][1] * (M[r1][2] * M[r2][3] - M[r1][3] * M[r2][2]) - M[r0][2] * (M[r1][1] * M[r2][3] - M[r1][3] * M[r2][1]) +
+           M[r0][3] * (M[r1][1] * M[r2][2] - M[r1][2] * M[r2][1]);
+}
+template <int WIDTH, bool ANALYTIC>
+__global__ void __launch_bounds__(128) k_interpolate_restoring(FArgs a, KTab wtab, KTab dwtab, const float4 *__restrict__ src_pos, u32 n_src,
+                                                               const u32 *__restrict__ count, const u32 *__restrict__ slice,
+                                                               const u32 *__restrict__ index, const float4 *__restrict__ tar_posvol,
+                                                               const float *__restrict__ tar_data, float *__restrict__ out)
+{
+    __shared__ float4 tab[KT_SLOTS], dtab[KT_SLOTS];
+    if (!ANALYTIC)
+    {
+        stage_tab(wtab, tab);
+        stage_tab(dwtab, dtab);
+    }
+    u32 t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_src) return;
+    const float4 xi = src_pos[t];
+    const u32 cnt = count[t];
+    const u32 *idx = index + (u64)slice[t >> 5] + (t & 31u);
+    const int dim = a.dim;
+    float M[4][4], pred[4][WIDTH];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+    {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) M[r][c] = r == c ? 1.1920929e-07f : 0.f; // Eps, base_data_type.h:205
+#pragma unroll
+        for (int c = 0; c < WIDTH; ++c) pred[r][c] = 0.f;
+    }
+    for (u32 k = 0; k < cnt; ++k)
+    {
+        const u32 j = idx[32ull * k];
+        const float4 xj = tar_posvol[j];
+        const float rv[3] = {xi.x - xj.x, xi.y - xj.y, xi.z - xj.z};
+        float r, inv_r;
+        dist(rv[0] * rv[0] + rv[1] * rv[1] + rv[2] * rv[2], r, inv_r);
+        const float WV = kernel_w<ANALYTIC>(a, tab, r) * xj.w, dWV = kernel_dw<ANALYTIC>(a, dtab, r) * xj.w;
+        float col0[4];
+        col0[0] = WV;
+        M[0][0] += WV;
+#pragma unroll
+        for (int b = 0; b < 3; ++b)
+            if (b < dim) M[0][1 + b] -= WV * rv[b];
+#pragma unroll
+        for (int q = 0; q < 3; ++q)
+        {
+            const float ge = q < dim ? dWV * (rv[q] * inv_r) : 0.f; // dW V e_q
+            col0[1 + q] = ge;
+            M[1 + q][0] += ge;
+#pragma unroll
+            for (int b = 0; b < 3; ++b)
+                if (q < dim && b < dim) M[1 + q][1 + b] -= dWV * rv[q] * (rv[b] * inv_r);
+        }
+#pragma unroll
+        for (int c = 0; c < WIDTH; ++c)
+        {
+            const float d = tar_data[(u64)WIDTH * j + c];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) pred[q][c] += col0[q] * d;
+        }
+    }
+    float cof[4];
+    if (dim == 2)
+    {
+        cof[0] = minor3_col0<0>(M); cof[1] = -minor3_col0<1>(M); cof[2] = minor3_col0<2>(M); cof[3] = 0.f;
+    }
+    else
+    {
+        cof[0] = minor4_col0<0>(M); cof[1] = -minor4_col0<1>(M); cof[2] = minor4_col0<2>(M); cof[3] = -minor4_col0<3>(M);
+    }
+    const float det = M[0][0] * cof[0] + M[1][0] * cof[1] + M[2][0] * cof[2] + (dim == 3 ? M[3][0] * cof[3] : 0.f);
+#pragma unroll
+    for (int c = 0; c < WIDTH; ++c)
+    {
+        float v = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v += (cof[q] / det) * pred[q][c];
+        out[(u64)WIDTH * t + c] = v;
+    }
+}
+
+extern "C" int sphb200_interpolate_restoring(sphb200_context_t *ctx, const sphb200_kernel_t *kernel, const sphb200_vec4_t *src_pos,
+                                             uint32_t n_src, sphb200_relation_t rel, const sphb200_vec4_t *tar_posvol,
+                                             const float *tar_data, int width, float *out, void *stream)
+{
+    SPH_CHECK_ARG(ctx, ctx && kernel, "null pointer");
+    SPH_CHECK_ARG(ctx, width == 1 || width == 4, "width must be 1 (Real) or 4 (Vecd stored as float4)");
+    if (n_src == 0) return 0;
+    SPH_CHECK_ARG(ctx, src_pos && rel.count && rel.slice_offset && rel.index && tar_posvol && tar_data && out, "null pointer");
+    SPH_CHECK_ARG(ctx, rel.order == nullptr, "observer rows must be in plain slot order");
+    sphb200_fluid_args_t s;
+    memset(&s, 0, sizeof(s));
+    s.kernel = *kernel;
+    s.material.rho0 = 1.f;
+    s.material.c0 = 1.f;
+    FArgs a;
+    KTab wtab, dwtab;
+    int rc = make_fargs(ctx, &s, &a, &wtab, &dwtab);
+    if (rc) return rc;
+    unsigned g = sph_blocks(n_src, 128);
+    const float4 *sp = (const float4 *)src_pos, *tp = (const float4 *)tar_posvol;
+    if (width == 1)
+    {
+        if (a.analytic) SPH_LAUNCH(ctx, (k_interpolate_restoring<1, true>), g, 128, 0, stream, a, wtab, dwtab, sp, n_src, rel.count, rel.slice_offset, rel.index, tp, tar_data, out);
+        else SPH_LAUNCH(ctx, (k_interpolate_restoring<1, false>), g, 128, 0, stream, a, wtab, dwtab, sp, n_src, rel.count, rel.slice_offset, rel.index, tp, tar_data, out);
+    }
+    else
+    {
+        if (a.analytic) SPH_LAUNCH(ctx, (k_interpolate_restoring<4, true>), g, 128, 0, stream, a, wtab, dwtab, sp, n_src, rel.count, rel.slice_offset, rel.index, tp, tar_data, out);
+        else SPH_LAUNCH(ctx, (k_interpolate_restoring<4, false>), g, 128, 0, stream, a, wtab, dwtab, sp, n_src, rel.count, rel.slice_offset, rel.index, tp, tar_data, out);
+    }
+    return 0;
+}
+
 // =====================================================================================================
 // viscous force: ViscousForceCK<Inner<WithUpdate, Viscosity, Correction>, Contact<Wall, Viscosity, Correction>> + the
 // ForcePriorCK update it carries; fluid_dynamics/viscous_force.hpp:44-103, general_dynamics/force_prior_ck.h:53-57
@@ -1555,7 +1684,8 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS)
         const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
         float4 xjs[NB_U], vjs[NB_U];
         u32 js[NB_U];
-        for_neighbors(
+        const bool has_rec = CORR && a.brec != nullptr; // B_j as one 32-byte record of its symmetric part (k_a1_interact)
+        for_neighbors<(CORR ? 2 : NB_U)>(
             idx, cnt,
             [&](int q, u32 j) {
                 load_rec2(a.rec2, j, xjs[q], vjs[q]);
@@ -1573,7 +1703,14 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS)
                 if (CORR)
                 {
                     float Bj[9];
-                    load_mat(a.B, js[q], Bj);
+                    if (has_rec)
+                    {
+                        float4 ba, bb;
+                        load_rec2(a.brec, js[q], ba, bb);
+                        Bj[0] = ba.x; Bj[1] = ba.y; Bj[2] = ba.z; Bj[3] = ba.y; Bj[4] = ba.w; Bj[5] = bb.x; Bj[6] = ba.z; Bj[7] = bb.x; Bj[8] = bb.y;
+                    }
+                    else
+                        load_mat(a.B, js[q], Bj);
 #pragma unroll
                     for (int k = 0; k < 9; ++k) Bj[k] += Bi[k];
                     float3 be = mat_vec(Bj, make_float3(dx * inv_r, dy * inv_r, dz * inv_r));

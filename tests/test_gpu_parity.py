@@ -854,6 +854,14 @@ def test_example_case_files_run():
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         energies = [float(l.split("=")[-1]) for l in r.stdout.splitlines() if "TotalMechanicalEnergy" in l]
         assert energies and all(0.9 * e0 < e < 1.1 * e0 for e in energies), r.stdout[-2000:]
+    # the reference's known-answer test of the restoring-correction interpolation (2d_interpolation.cpp), 64 random points
+    path = os.path.join(root, "examples", "interpolation_restoring_2d")
+    if not os.path.exists(path):
+        pytest.skip("interpolation_restoring_2d not built")
+    for seed in ("1", "2"):
+        r = subprocess.run([path, seed, "64"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        assert "InterpolationError" in r.stdout
 
 
 # ------------------------------------------------------------------------------------------------------

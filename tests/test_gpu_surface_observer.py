@@ -188,6 +188,28 @@ def test_interpolation_primitive_against_oracle(tmp_path):
     _report("interpolation_primitive", {"rel_err": err, "max_abs_pressure": float(np.max(np.abs(want))), "probes": int(n)})
     assert err < 2e-5, err
     assert got[1] == 0.0
+    # Interpolation<Contact<DataType, RestoringCorrection>> (interpolation_dynamics.hpp:72-100) on the same rows: against the
+    # oracle, and by the reference's own known answer (unit_test_interpolation_ck/2d_interpolation.cpp: interpolating
+    # "Position" gives the observer's position back — also at the free surface, where the plain interpolation is one-sided)
+    ref.exec("observe_restoring_pressure")
+    ref.exec("observe_restoring_position")
+    want_p = ref.real("RestoredPressure", 1, body=2).copy()
+    want_x = ref.real("RestoredPosition", 3, body=2).reshape(-1, 3).copy()
+    out_p = torch.zeros(n, dtype=torch.float32, device=dev)
+    out_x = torch.zeros((n, 4), dtype=torch.float32, device=dev)
+    ctx.call("sphb200_interpolate_restoring", C.byref(kern), src.data_ptr(), n, rel, posvol, data, 1, out_p.data_ptr(), None)
+    ctx.call("sphb200_interpolate_restoring", C.byref(kern), src.data_ptr(), n, rel, posvol, s.tar_pos, 4, out_x.data_ptr(), None)
+    torch.cuda.synchronize()
+    got_p, got_x = out_p.cpu().numpy().astype(np.float64), out_x.cpu().numpy().astype(np.float64)[:, :3]
+    has = cnt > 0
+    err_p = float(np.max(np.abs(got_p - want_p)[has]) / max(np.max(np.abs(want_p)), 1e-30))
+    err_x = float(np.max(np.abs(got_x - want_x)[has]) / max(np.max(np.abs(want_x)), 1e-30))
+    err_known = float(np.max(np.abs(got_x - probes.astype(np.float64))[has]))
+    _report("interpolation_restoring", {"rel_err_pressure": err_p, "rel_err_position": err_x, "position_reproduction_abs": err_known,
+                                        "oracle_position_reproduction_abs": float(np.max(np.abs(want_x - probes.astype(np.float64))[has]))})
+    assert err_p < 1e-5 and err_x < 1e-5, (err_p, err_x)
+    assert err_known < 1e-5, err_known  # the reference's test: 1e-6 in double; fp32 positions of O(1) carry 1e-7 each
+    assert np.all(got_p[~has] == 0.0)
     ctx.close()
 
 

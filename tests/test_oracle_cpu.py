@@ -270,6 +270,41 @@ def test_ck_energy_series_prefix_3d(oracle_lib):
     assert np.allclose(e, ours["energy"][:2], rtol=1e-6)
 
 
+@pytest.mark.parametrize("dim,dp", [(2, 0.025), (3, 0.05)])
+def test_restoring_correction_interpolation_known_answer(dim, dp):
+    """Interpolation<Contact<DataType, RestoringCorrection>> (interpolation_dynamics.hpp:72-100) pinned by the reference's own
+    known answer, unit_test_interpolation_ck/2d_interpolation.cpp:27-33: on a randomised lattice the interpolated "Position"
+    at a random point is that point to 1e-6 (Real = double there). Also: any linear field is reproduced, at one-sided
+    neighbourhoods (free surface, wall) too, where the plain interpolation is off by percents."""
+    from helpers import perturb_state
+    from oracle import oracle as orc
+    from sphinxsys_b200 import cases
+    case = cases.dam_break(dim=dim, dp=dp)
+    case.fluid_pos, _ = perturb_state(case, jitter=0.25)  # RandomizeParticlePosition(0.5): a quarter spacing per axis
+    rng = np.random.default_rng(11)
+    n = 50
+    probes = np.zeros((n, 3))
+    probes[:, 0], probes[:, 1] = rng.uniform(0.1, 1.9, n), rng.uniform(0.05, 0.95, n)
+    if dim == 3:
+        probes[:, 2] = rng.uniform(0.05, 0.45, n)
+    probes[0, :2] = (1.0, 0.999)   # at the free surface
+    probes[1, :2] = (0.001, 0.5)   # at the wall
+    for f64, tol in ((True, 1.0e-6), (False, 1.0e-5)):
+        o = orc.OracleSim(case, f64=f64, observers=probes)
+        o.exec("cell_list_fluid")
+        o.exec("observer_relation")
+        x = o.real("Position", 3).reshape(-1, 3)
+        o.real("Pressure")[:] = 3.0 + 2.0 * x[:, 0] - x[:, 1] + 0.5 * x[:, 2]
+        for op in ("observe_restoring_position", "observe_restoring_pressure", "observe_pressure"):
+            o.exec(op)
+        at = o.real("Position", 3, body=2).reshape(-1, 3).astype(np.float64)
+        restored = o.real("RestoredPosition", 3, body=2).reshape(-1, 3).astype(np.float64)
+        assert np.max(np.abs(restored[:, :dim] - at[:, :dim])) < tol
+        want = 3.0 + 2.0 * at[:, 0] - at[:, 1] + 0.5 * at[:, 2]
+        assert np.max(np.abs(o.real("RestoredPressure", 1, body=2) - want)) < 10 * tol
+        assert np.max(np.abs(o.real("Pressure", 1, body=2) - want)) > 1e-2  # the plain interpolation is not consistent at the surface
+
+
 # ------------------------------------------------------------------------------------------------------
 # the product library: loads and exports every declared symbol (no compute without a GPU)
 # ------------------------------------------------------------------------------------------------------
