@@ -420,15 +420,17 @@ class DamBreakCK
             {
                 fluid_boundary_indicator.reset(new InteractionDynamicsCK<P, FreeSurfaceIndicationComplexSpatialTemporalCK>(*water_block_inner, *water_wall_contact));
             }
-            if (q.observers)
-            {
-                registerPressure();
-                fluid_observer.reset(new ObserverBody(sph_system, "FluidObserver"));
-                fluid_observer->generateParticles<ObserverParticles>(createObservationPoints(q));
-                fluid_observer_contact.reset(new Contact<>(*fluid_observer, {&water_block}));
-                fluid_observer_contact_relation.reset(new UpdateRelation<P, Contact<>>(*fluid_observer_contact));
-                fluid_observer_pressure.reset(new ObservedQuantityRecording<P, Real>(*fluid_observer_contact, "Pressure"));
-            }
+        }
+        if (q.observers)
+        {
+            // dambreak.cpp:87-88,128,140-141 (CK); Dambreak.cpp:78-79,113 and test_3d_dambreak/dambreak.cpp:84-85,127 (first-generation
+            // API: ObservedQuantityRecording<Real>("Pressure", fluid_observer_contact), the same interpolation)
+            registerPressure();
+            fluid_observer.reset(new ObserverBody(sph_system, "FluidObserver"));
+            fluid_observer->generateParticles<ObserverParticles>(createObservationPoints(q));
+            fluid_observer_contact.reset(new Contact<>(*fluid_observer, {&water_block}));
+            fluid_observer_contact_relation.reset(new UpdateRelation<P, Contact<>>(*fluid_observer_contact));
+            fluid_observer_pressure.reset(new ObservedQuantityRecording<P, Real>(*fluid_observer_contact, "Pressure"));
         }
         if (wall_slab && water_wall_contact->search_depth_ != 1) throw SphError("WallSlab: the contact search reaches further than one cell plane");
         water_block_update_complex_relation.reset(new UpdateRelation<P, Inner<>, Contact<>>(*water_block_inner, *water_wall_contact));
@@ -510,6 +512,13 @@ class DamBreakCK
         }
         water_cell_linked_list->exec();           // water_block.updateCellLinkedList()
         water_wall_complex->updateConfiguration(); // neighbour lists + frozen pair geometry
+        if (fluid_observer_contact_relation)
+        {
+            // fluid_observer_contact.updateConfiguration(); write_recorded_water_pressure.writeToFile(), test_3d_dambreak/dambreak.cpp:193-194
+            // (every iteration; the 2-D case file keeps every 200th of these records, Dambreak.cpp:175-180)
+            fluid_observer_contact_relation->exec();
+            fluid_observer_pressure->writeToFile(number_of_iterations);
+        }
         last_acoustic_dt = acoustic_dt;
         last_advection_dt = advection_dt;
         return n_inner;

@@ -1517,7 +1517,7 @@ template <class R> struct Sim
     // ref: tests/2d_examples/test_2d_dambreak/Dambreak.cpp:118-220 and
     // tests/3d_examples/test_3d_dambreak/dambreak.cpp:108-194 (same sequencing).
     // Energy is recorded at iteration 0 and every `observe_every` outer iterations (2-D case file),
-    // or at every output interval when observe_every == 0 (3-D case file).
+    // or at every output interval when observe_every <= 0 (< 0: the 3-D case file's order, see runLegacy).
     void prepareLegacy()
     {
         ensureFluidState();
@@ -1528,9 +1528,23 @@ template <class R> struct Sim
         energy_series.clear(); time_series.clear();
         energy_series.push_back(mechanicalEnergy()); time_series.push_back(physical_time);
     }
+    // observe_every >= 0: the order of the 2-D case file (Dambreak.cpp:118-220): the acoustic dt is reduced BEFORE the two half steps.
+    //   > 0: energy and the probe are written at iteration 0 and every `observe_every`-th iteration (:137-139,175-180), before
+    //   that iteration's configuration update (the legacy interpolation reads the kernel weights stored at the previous update;
+    //   here it is evaluated on the current positions: one advection step apart, immaterial under the DTW criterion that judges
+    //   it); == 0: energy at every output interval only.
+    // observe_every < 0: the 3-D case file (test_3d_dambreak/dambreak.cpp:160-196): the half steps run with the dt reduced
+    //   AFTER the previous pair (`Real dt = 0.0` before the loop, :151), the probes are written every iteration after the
+    //   configuration update (:193-194), the energy at every output interval (:197).
+    double legacy_dt = 0.0;
     long runLegacy(double end_time, long max_outer, double output_interval, int observe_every, int sort_interval)
     {
         long done = 0;
+        if (observe_every > 0 && outer_steps == 0 && observer.n)
+        {
+            observerRelation();
+            recordProbes();
+        }
         while (physical_time < end_time && done < max_outer)
         {
             double integration_time = 0;
@@ -1541,22 +1555,35 @@ template <class R> struct Sim
                 double relax = 0;
                 while (relax < adv_dt)
                 {
-                    double dt = legacyAcousticDt();
-                    legacy1(R(dt));
-                    legacy2(R(dt));
+                    double dt;
+                    if (observe_every >= 0)
+                    {
+                        dt = legacyAcousticDt();
+                        legacy1(R(dt));
+                        legacy2(R(dt));
+                    }
+                    else
+                    {
+                        legacy1(R(legacy_dt));
+                        legacy2(R(legacy_dt));
+                        dt = legacy_dt = legacyAcousticDt();
+                    }
                     relax += dt; integration_time += dt; physical_time += dt;
                     ++acoustic_steps;
                 }
                 if (observe_every > 0 && outer_steps % 100 == 0 && outer_steps % observe_every == 0 && outer_steps != 0)
                 {
                     energy_series.push_back(mechanicalEnergy()); time_series.push_back(physical_time);
+                    recordProbes();
                 }
                 ++outer_steps; ++done;
                 if (sort_interval > 0 && outer_steps % sort_interval == 0 && outer_steps != 1) sortParticles(true);
                 cellListFluid();
                 relationsLegacy();
+                observerRelation();
+                if (observe_every < 0) recordProbes();
             }
-            if (observe_every == 0 && integration_time >= output_interval)
+            if (observe_every <= 0 && integration_time >= output_interval)
             {
                 energy_series.push_back(mechanicalEnergy()); time_series.push_back(physical_time);
             }

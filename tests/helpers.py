@@ -68,6 +68,15 @@ def dtw_distance(a, b, window=5):
     return float(D[la - 1, lb - 1])
 
 
+def dtw_two_sided(ours, ref_run, window=5):
+    """The reference compares a new run with a stored one as calculateDTWDistance(current, stored) (updateDTWDistance,
+    dynamic_time_warping_method.hpp:86-99). Its band leaves the corner cell at 0 when the first series is SHORTER than the second
+    by exactly the band width (the loop bound `j != min(b_length, i + window)` is exclusive) — the check is then vacuous. Series
+    of different lengths are therefore compared in both argument orders and the larger distance counts: never weaker than the
+    reference's own check, never vacuous."""
+    return max(dtw_distance(ours, ref_run, window), dtw_distance(ref_run, ours, window))
+
+
 def lists_on_oracle_positions(gpu, o32, periodic=False):
     """Neighbour lists of the END state of a multi-step run, on IDENTICAL inputs: after many steps the two fp32 paths differ
     by rounding (a few 1e-7 in position), so a pair that sits within that distance of the cut-off may be a neighbour on one

@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 
 torch = pytest.importorskip("torch")
 
-from helpers import (dtw_distance, gpu_field, lists_on_oracle_positions, make_gpu, make_oracle, oracle_field, perturb_state,  # noqa: E402
+from helpers import (dtw_distance, dtw_two_sided, gpu_field, lists_on_oracle_positions, make_gpu, make_oracle, oracle_field, perturb_state,  # noqa: E402
                      rel_err)
 
 REPORT = {}
@@ -878,11 +878,13 @@ def test_full_2d_dambreak_energy_series_meets_reference_dtw():
     sampled as the case file does (iteration 0 and every 200th advection step, Dambreak.cpp:186-197), against the three
     committed reference runs (23 snapshots, 1.0 -> 0.42; threshold 0.2)."""
     from sphinxsys_b200 import cases
+    from sphinxsys_b200.host import DamBreakCK
     ref = _golden()["2d_dambreak_legacy"]
+    pref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_pressure_probes.json")))["2d_dambreak_legacy"]
     case = cases.dam_break(dim=2, dp=0.025)
-    gpu = make_gpu(case, fused_time_step=True, legacy=True)
+    gpu = DamBreakCK(case, fused_time_step=True, legacy=True, observers=True)
     gpu.initialize()
-    series = [gpu.energy()]
+    series, sampled = [gpu.energy()], [0]  # sampled: probe records kept by the case file (record 0 = before the loop)
     it, t_window, end_time, output_interval = 0, 0.0, 20.0, 0.1
     while gpu.physical_time < end_time:
         t_start = gpu.physical_time
@@ -890,12 +892,19 @@ def test_full_2d_dambreak_energy_series_meets_reference_dtw():
             gpu.step_outer()
             if it % 200 == 0 and it != 0:
                 series.append(gpu.energy())
+                sampled.append(it + 1)  # the record written by this step
             it += 1
     d = [dtw_distance(run, series) for run in ref["runs"].values()]
+    # the wall-pressure probe of the same case file (Dambreak.cpp:27-28,113,137-139,175-180), sampled with the energy
+    _, v = gpu.probe_records()
+    probe = [float(v[k, 0]) for k in sampled]
+    dp_ = [dtw_two_sided(probe, run[0]) for run in pref["runs"].values()]
     _report("full_2d_legacy_energy", {"snapshots": len(series), "outer_steps": it, "dtw_vs_reference_runs": d,
-                                      "threshold": ref["dtw_threshold"], "series": series})
+                                      "threshold": ref["dtw_threshold"], "series": series, "probe_dtw_vs_reference_runs": dp_,
+                                      "probe_threshold": pref["dtw_threshold"][0], "probe_series": probe})
     assert abs(series[0] - 1.0) < 1e-5
     assert max(d) <= ref["dtw_threshold"], f"DTW {d} > {ref['dtw_threshold']}"
+    assert len(probe) == len(series) and max(dp_) <= pref["dtw_threshold"][0], f"probe DTW {dp_} > {pref['dtw_threshold'][0]}"
 
 
 def test_full_3d_dambreak_ck_energy_series_meets_reference_dtw():
@@ -920,6 +929,41 @@ def test_full_3d_dambreak_ck_energy_series_meets_reference_dtw():
                                   "threshold": ref["dtw_threshold"], "series": series})
     assert abs(series[0] - 0.5) < 1e-5
     assert max(d) <= ref["dtw_threshold"], f"DTW {d} > {ref['dtw_threshold']}"
+
+
+def test_full_3d_dambreak_legacy_energy_series_meets_reference_dtw():
+    """tests/3d_examples/test_3d_dambreak — the first-generation API (Integration1stHalf/2ndHalfWithWallRiemann,
+    DensitySummationComplexFreeSurface) in 3-D — to t = 20 on the GPU in fp32, energy at iteration 0 and at every output interval
+    (dambreak.cpp:100-146), against the three committed reference runs (Real = double there; 21 snapshots, threshold 0.03)."""
+    from sphinxsys_b200 import cases
+    from sphinxsys_b200.host import DamBreakCK
+    ref = _golden()["3d_dambreak_legacy"]
+    pref = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_pressure_probes.json")))["3d_dambreak_legacy"]
+    case = cases.dam_break(dim=3, dp=0.05)
+    gpu = DamBreakCK(case, fused_time_step=True, legacy=True, sort_interval=100, observers=True)
+    gpu.initialize()
+    series = [gpu.energy()]
+    end_time, output_interval, it = 20.0, 1.0, 0
+    while gpu.physical_time < end_time:
+        t_start = gpu.physical_time
+        while gpu.physical_time - t_start < output_interval:
+            gpu.step_outer()
+            it += 1
+        series.append(gpu.energy())
+    d = [dtw_distance(run, series) for run in ref["runs"].values()]
+    # the six wall-pressure probes, written every iteration after the configuration update (dambreak.cpp:193-194; the record
+    # made before the loop is ours, not the case file's: dropped), 2,180 records in the reference runs
+    _, v = gpu.probe_records()
+    v = v[1:]
+    dpr = {k: [dtw_two_sided(v[:, k].tolist(), run[k]) for run in pref["runs"].values()] for k in range(6)}
+    _report("full_3d_legacy_energy", {"snapshots": len(series), "outer_steps": it, "dtw_vs_reference_runs": d,
+                                      "threshold": ref["dtw_threshold"], "series": series, "probe_records": int(v.shape[0]),
+                                      "probe_dtw_vs_reference_runs": dpr, "probe_thresholds": pref["dtw_threshold"]})
+    assert abs(series[0] - 0.5) < 1e-5
+    assert max(d) <= ref["dtw_threshold"], f"DTW {d} > {ref['dtw_threshold']}"
+    assert v.shape[0] == it
+    for k in range(6):
+        assert max(dpr[k]) <= pref["dtw_threshold"][k], f"probe {k}: DTW {dpr[k]} > {pref['dtw_threshold'][k]}"
 
 
 def test_host_transfer_pipeline_equals_synchronous_transfers():

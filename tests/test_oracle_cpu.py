@@ -232,7 +232,8 @@ def test_linear_gradient_reproduction_known_answer(oracle_lib):
 def test_oracle_energy_series_pass_reference_dtw_thresholds():
     ref = json.load(open(os.path.join(GOLD, "reference_regression.json")))
     ours = json.load(open(os.path.join(GOLD, "oracle_energy_series.json")))
-    pairs = (("2d_dambreak_legacy", "2d_dambreak_legacy_f64"), ("3d_dambreak_ck_sycl", "3d_dambreak_ck_f32_correction"))
+    pairs = (("2d_dambreak_legacy", "2d_dambreak_legacy_f64"), ("3d_dambreak_ck_sycl", "3d_dambreak_ck_f32_correction"),
+             ("3d_dambreak_legacy", "3d_dambreak_legacy_f64"))
     for ref_key, our_key in pairs:
         thr = ref[ref_key]["dtw_threshold"]
         e = ours[our_key]["energy"]
@@ -256,6 +257,19 @@ def test_oracle_reproduces_committed_series_prefix(oracle_lib):
     assert len(e) >= 3
     assert np.allclose(e[:3], ours["energy"][:3], rtol=1e-12, atol=0)
     assert np.allclose(t[:3], ours["time"][:3], rtol=1e-12, atol=0)
+
+
+def test_legacy_energy_series_prefix_3d(oracle_lib):
+    """tests/3d_examples/test_3d_dambreak (first-generation API in 3-D): the committed oracle series comes from the current oracle."""
+    from sphinxsys_b200 import cases
+    ours = json.load(open(os.path.join(GOLD, "oracle_energy_series.json")))["3d_dambreak_legacy_f64"]
+    case = cases.dam_break(dim=3, dp=0.05, dtype=np.float64)
+    o = make_oracle(case, f64=True)
+    o.exec("prepare_legacy")
+    o.exec("run_legacy", 1.0, 1e9, 1.0, -1)
+    t, e = o.series()
+    assert len(e) == 2
+    assert np.allclose(e, ours["energy"][:2], rtol=1e-9)
 
 
 def test_ck_energy_series_prefix_3d(oracle_lib):

@@ -12,7 +12,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import dtw_distance
+from helpers import dtw_distance, dtw_two_sided
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 GOLD = os.path.join(HERE, "golden")
@@ -159,3 +159,38 @@ def test_oracle_probe_fixture_is_reproducible_prefix():
     assert p.shape == (41, 6)
     want = np.array(mine["pressure"])[:, :41].T
     assert np.allclose(p, want, rtol=2e-5, atol=1e-6)
+
+
+def test_oracle_legacy_probe_series_pass_reference_dtw_thresholds():
+    """The wall-pressure probes of the two first-generation case files the reference holds regression data for — test_2d_dambreak
+    (one probe sampled with the energy: 23 snapshots, threshold 1.078) and test_3d_dambreak (six probes written every iteration:
+    2,180 records, thresholds 1.5 - 4.5) — from the oracle's full runs (oracle/make_golden.py --legacy-pressure), under the
+    reference's criterion in both argument orders."""
+    ref = _gold("reference_pressure_probes.json")
+    ours = _gold("oracle_probe_series.json")
+    g2, o2 = ref["2d_dambreak_legacy"], ours["2d_dambreak_legacy_f64"]["pressure"][0]
+    assert len(o2) == 23
+    for run, series in g2["runs"].items():
+        d = dtw_two_sided(o2, series[0])
+        assert d <= g2["dtw_threshold"][0], f"2-D probe, run {run}: DTW {d:.3f} > {g2['dtw_threshold'][0]}"
+    g3, o3 = ref["3d_dambreak_legacy"], ours["3d_dambreak_legacy_f64"]["pressure"]
+    assert len(o3) == 6 and 0.95 * 2180 < len(o3[0]) < 1.05 * 2180
+    for k in range(6):
+        for run, series in g3["runs"].items():
+            d = dtw_two_sided(o3[k], series[k])
+            assert d <= g3["dtw_threshold"][k], f"3-D legacy probe {k}, run {run}: DTW {d:.3f} > {g3['dtw_threshold'][k]}"
+
+
+def test_oracle_reproduces_committed_2d_probe_prefix():
+    """The committed 2-D probe fixture comes from the current oracle: iteration 0 and every 200th iteration up to t = 4.6."""
+    from oracle import oracle as orc
+    from sphinxsys_b200 import cases
+    ours = _gold("oracle_probe_series.json")["2d_dambreak_legacy_f64"]
+    case = cases.dam_break(dim=2, dp=0.025, dtype=np.float64)
+    o = orc.OracleSim(case, f64=True, observers=ours["args"]["observers"])
+    o.exec("prepare_legacy")
+    o.exec("run_legacy", 4.6, 1e9, 0.1, 200)
+    p = o.probe_series()
+    n = p.shape[0]
+    assert n >= 5 and np.allclose(p[:n, 0], ours["pressure"][0][:n], rtol=1e-5, atol=1e-12)
+    assert np.max(np.abs(p[:n, 0])) > 0.1  # the water has reached the probe within the prefix
