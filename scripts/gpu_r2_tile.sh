@@ -1,4 +1,5 @@
 #!/bin/bash
+# (needs profiles/r02b_tile_order_experiment.patch applied: SPHB200_TILE_ORDER is not in the tree)
 # SM-local tile order A/B: bit-identity of the state, kernel times, full test suite with the order forced on, launch list of the complete case
 OUT=gpurun_out/r2t; mkdir -p $OUT
 for T in 0 1; do SPHB200_TILE_ORDER=$T python scripts/state_hash.py 0.0125 2>&1 | grep STATE_HASH | sed "s/^/tile=$T /" | tee -a $OUT/hash.txt; done
