@@ -106,8 +106,9 @@ typedef struct
     float *B;                     /* LinearCorrectionMatrix, 9 floats row-major per particle, or NULL */
     void *correction_record;      /* 32-byte records (Bxx, Bxy, Bxz, Byy, Byz, Bzz, -, -): the symmetric part of B as ONE
                                      gather per neighbour for the 1st-half interaction with LinearCorrectionCK (which reads
-                                     B of the neighbour). sphb200_linear_correction_matrix writes it next to B; NULL: the
-                                     interaction gathers the nine entries of B itself (2.2 x slower at 4 M particles) */
+                                     B of the neighbour) and for ViscousForceCK with correction. sphb200_linear_correction_matrix
+                                     writes it next to B (sphb200_pack_correction_records for matrices written elsewhere);
+                                     required whenever material.correction is set for those two dynamics */
     sphb200_vec4_t *posvol;       /* derived gather records, one load per neighbour instead of two; refresh with
                                      sphb200_pack_records whenever their sources changed outside the library:
                                      posvol = (x, y, z, Vol)                         [1st half, correction matrix] */

@@ -789,7 +789,7 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
         const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
         float4 xjs[NB_U];
         float pjs[NB_U];
-        if (CORR && a.brec)
+        if (CORR)
         {
             // sum_j dWV (p_i B_j + p_j B_i) e = p_i sum_j dWV B_j e + B_i sum_j p_j dWV e: B_i leaves the pair loop, and B_j
             // comes as ONE 32-byte record of its six distinct entries (B is the regularised inverse of the symmetric
@@ -829,13 +829,11 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
         }
         else
         {
-        u32 js[NB_U];
         for_neighbors(
             idx, cnt,
             [&](int u, u32 j) {
                 xjs[u] = a.posvol[j];
                 pjs[u] = a.p[j];
-                if (CORR) js[u] = j;
             },
             [&](int u, bool valid) {
                 const float4 xj = xjs[u];
@@ -846,24 +844,9 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
                 dist(r2, r, inv_r);
                 float dWV = kernel_dw<ANALYTIC>(a, tab, r) * xj.w;
                 dWV = valid ? dWV : 0.f;
-                if (CORR)
-                {
-                    float Bj[9];
-                    load_mat(a.B, js[u], Bj);
-                    float3 e = make_float3(dx * inv_r, dy * inv_r, dz * inv_r);
-                    float3 bje = mat_vec(Bj, e), bie = mat_vec(Bi, e);
-                    // AverageP(B_j p_i, B_i p_j) * 2 dWV * e
-                    float c = dWV; // 2 dWV * Z / (Z + Z)
-                    fx -= c * (p_i * bje.x + p_j * bie.x);
-                    fy -= c * (p_i * bje.y + p_j * bie.y);
-                    fz -= c * (p_i * bje.z + p_j * bie.z);
-                }
-                else
-                {
-                    // AverageP (riemann_solver_ck.hpp:19-24) with Z_i == Z_j (one fluid): 2 * pave = p_i + p_j
-                    float c = (p_i + p_j) * dWV * inv_r;
-                    fx -= c * dx; fy -= c * dy; fz -= c * dz;
-                }
+                // AverageP (riemann_solver_ck.hpp:19-24) with Z_i == Z_j (one fluid): 2 * pave = p_i + p_j
+                float c = (p_i + p_j) * dWV * inv_r;
+                fx -= c * dx; fy -= c * dy; fz -= c * dz;
 #if SPH_TRIM & 4
                 if (RIEMANN) diss += (p_i - p_j) * dWV; // DissipativeUJump, :51-56 (its constant InvImpedanceAve: once per particle below)
 #else
@@ -1002,7 +985,7 @@ extern "C" int sphb200_acoustic_1st_half_interact(sphb200_context_t *ctx, const 
     if (rc) return rc;
     rc = check_acoustic_args(ctx, a, false);
     if (rc) return rc;
-    SPH_CHECK_ARG(ctx, !s->material.correction || a.B, "LinearCorrectionCK needs fluid.B");
+    SPH_CHECK_ARG(ctx, !s->material.correction || (a.B && a.brec), "LinearCorrectionCK needs fluid.B and fluid.correction_record");
     if (a.end <= a.begin) return 0;
     return s->material.correction ? launch_a1<true>(ctx, a, dwtab, s->material.riemann, dt, do_update, stream)
                                   : launch_a1<false>(ctx, a, dwtab, s->material.riemann, dt, do_update, stream);
@@ -1684,7 +1667,6 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS)
         const u32 *idx = a.in_index + (u64)a.in_slice[t >> 5] + (t & 31u);
         float4 xjs[NB_U], vjs[NB_U];
         u32 js[NB_U];
-        const bool has_rec = CORR && a.brec != nullptr; // B_j as one 32-byte record of its symmetric part (k_a1_interact)
         for_neighbors<(CORR ? 2 : NB_U)>(
             idx, cnt,
             [&](int q, u32 j) {
@@ -1703,14 +1685,9 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS)
                 if (CORR)
                 {
                     float Bj[9];
-                    if (has_rec)
-                    {
-                        float4 ba, bb;
-                        load_rec2(a.brec, js[q], ba, bb);
-                        Bj[0] = ba.x; Bj[1] = ba.y; Bj[2] = ba.z; Bj[3] = ba.y; Bj[4] = ba.w; Bj[5] = bb.x; Bj[6] = ba.z; Bj[7] = bb.x; Bj[8] = bb.y;
-                    }
-                    else
-                        load_mat(a.B, js[q], Bj);
+                    float4 ba, bb; // B_j as one 32-byte record of its symmetric part (see k_a1_interact)
+                    load_rec2(a.brec, js[q], ba, bb);
+                    Bj[0] = ba.x; Bj[1] = ba.y; Bj[2] = ba.z; Bj[3] = ba.y; Bj[4] = ba.w; Bj[5] = bb.x; Bj[6] = ba.z; Bj[7] = bb.x; Bj[8] = bb.y;
 #pragma unroll
                     for (int k = 0; k < 9; ++k) Bj[k] += Bi[k];
                     float3 be = mat_vec(Bj, make_float3(dx * inv_r, dy * inv_r, dz * inv_r));
@@ -1777,7 +1754,7 @@ extern "C" int sphb200_viscous_force(sphb200_context_t *ctx, const sphb200_fluid
     if (rc) return rc;
     SPH_CHECK_ARG(ctx, a.n == 0 || (a.posvol && a.vel && a.rec2 && a.force_prior && a.in_count && a.in_slice && a.in_index), "null fluid array");
     SPH_CHECK_ARG(ctx, a.n_wall == 0 || (a.w_posvol && a.ct_count && a.ct_slice && a.ct_index), "null wall array");
-    SPH_CHECK_ARG(ctx, !s->material.correction || a.B, "LinearCorrectionCK needs fluid.B");
+    SPH_CHECK_ARG(ctx, !s->material.correction || (a.B && a.brec), "LinearCorrectionCK needs fluid.B and fluid.correction_record");
     if (a.end <= a.begin) return 0;
     const float h2_eps = 0.01f * smoothing_length * smoothing_length;
     unsigned g = active_blocks(a, FL_THREADS);
