@@ -104,11 +104,12 @@ typedef struct
     float *vol_ref;               /* VolumetricMeasureRef */
     float *compression_sum;       /* CompressionSummation */
     float *B;                     /* LinearCorrectionMatrix, 9 floats row-major per particle, or NULL */
-    void *correction_record;      /* 32-byte records (Bxx, Bxy, Bxz, Byy, Byz, Bzz, -, -): the symmetric part of B as ONE
-                                     gather per neighbour for the 1st-half interaction with LinearCorrectionCK (which reads
-                                     B of the neighbour) and for ViscousForceCK with correction. sphb200_linear_correction_matrix
-                                     writes it next to B (sphb200_pack_correction_records for matrices written elsewhere);
-                                     required whenever material.correction is set for those two dynamics */
+    void *correction_record;      /* 32-byte records (Bxx, Bxy, Bxz, Byy, Byz, Bzz, p, -): the symmetric part of B and the
+                                     pressure as ONE gather per neighbour for the 1st-half interaction with LinearCorrectionCK
+                                     (which reads B and p of the neighbour); B part also for ViscousForceCK with correction.
+                                     sphb200_linear_correction_matrix writes the B part next to B, the 1st-half initialize
+                                     keeps the pressure slot current (sphb200_pack_correction_records for values written
+                                     elsewhere); required whenever material.correction is set for those dynamics */
     sphb200_vec4_t *posvol;       /* derived gather records, one load per neighbour instead of two; refresh with
                                      sphb200_pack_records whenever their sources changed outside the library:
                                      posvol = (x, y, z, Vol)                         [1st half, correction matrix] */
@@ -390,8 +391,10 @@ int sphb200_acoustic_1st_half_interact(sphb200_context_t *ctx, const sphb200_flu
 /* LinearCorrectionMatrix<Inner<WithUpdate>,Contact<>>; ref: general_dynamics/kernel_correction_ck.hpp:40-95.
  * Writes fluid.B and, when given, fluid.correction_record. */
 int sphb200_linear_correction_matrix(sphb200_context_t *ctx, const sphb200_fluid_args_t *a, float alpha, void *stream);
-/* correction_record (see sphb200_fluid_view_t) of n matrices written outside the library (host uploads) */
-int sphb200_pack_correction_records(sphb200_context_t *ctx, uint32_t n, const float *B, void *correction_record, void *stream);
+/* correction_record (see sphb200_fluid_view_t) of n particles whose matrices (B) and / or pressures were written outside the
+ * library (host uploads); a NULL source leaves its part of the records as it is */
+int sphb200_pack_correction_records(sphb200_context_t *ctx, uint32_t n, const float *B, const float *pressure,
+                                    void *correction_record, void *stream);
 /* InteractionDynamicsCK<FreeSurfaceIndicationCK<Inner<WithUpdate>, Contact<>>>::exec: inner interact (position
  * divergence, spatial-temporal override next to the previous surface) -> contact interact -> update (Indicator,
  * PreviousSurfaceIndicator). threshold = 0.75 * Dimensions, smoothing_length = ReferenceSmoothingLength().

@@ -552,7 +552,8 @@ class DamBreakCK
         {
             StreamScope side(S);
             d.await(0, S);
-            d.refreshGhosts({"Pressure"});
+            if (q_.correction) d.refreshGhosts({"Pressure", "LinearCorrectionRecord"}); // the correction variants read p_j from the record
+            else d.refreshGhosts({"Pressure"});
             for (const SlotRange &r : edge) on(r, [&] { first_half_phases_->deviceInteractAndUpdate(dt); });
             d.signal(1, S);
             d.refreshGhosts({"PosVolVel"}); // the velocity records of the boundary planes are final: send them now
@@ -648,7 +649,8 @@ class DamBreakCK
             {
                 // the two neighbour-read variables of the half steps are refreshed on the ghost planes in between
                 first_half_phases_->deviceInitialize(acoustic_dt);
-                decomposition->refreshGhosts({"Pressure"});
+                if (q_.correction) decomposition->refreshGhosts({"Pressure", "LinearCorrectionRecord"});
+                else decomposition->refreshGhosts({"Pressure"});
                 first_half_phases_->deviceInteractAndUpdate(acoustic_dt);
                 decomposition->refreshGhosts({"PosVolVel"}); // the 2nd half reads neighbour velocities from the gather record
                 fluid_acoustic_step_2nd_half->exec(acoustic_dt);

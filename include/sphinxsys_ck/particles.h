@@ -341,10 +341,16 @@ class BaseParticles
             uint32_t bytes[1] = {eb};
             SPHCK_CALL(sphb200_gather_multi, 1, dst, srcs, bytes, referenceID(), n, ex.stream());
         }
-        // matrices written by the host: their gather record follows (fluid_dynamics.h, registerCorrectionRecord)
-        if (std::is_same<T, Matd>::value && v->Name() == "LinearCorrectionMatrix" && hasVariable("LinearCorrectionRecord"))
-            SPHCK_CALL(sphb200_pack_correction_records, n, (const float *)v->deviceAddress(),
-                       deviceData<GatherRecord8>("LinearCorrectionRecord"), ex.stream());
+        // matrices / pressures written by the host: their gather record follows (fluid_dynamics.h, registerCorrectionRecord)
+        if (hasVariable("LinearCorrectionRecord"))
+        {
+            if (std::is_same<T, Matd>::value && v->Name() == "LinearCorrectionMatrix")
+                SPHCK_CALL(sphb200_pack_correction_records, n, (const float *)v->deviceAddress(), nullptr,
+                           deviceData<GatherRecord8>("LinearCorrectionRecord"), ex.stream());
+            if (std::is_same<T, Real>::value && v->Name() == "Pressure")
+                SPHCK_CALL(sphb200_pack_correction_records, n, nullptr, (const float *)v->deviceAddress(),
+                           deviceData<GatherRecord8>("LinearCorrectionRecord"), ex.stream());
+        }
         ex.synchronize(); // the host buffer may be pageable
     }
     template <class T> void download(DiscreteVariable<T> *v, T *host)

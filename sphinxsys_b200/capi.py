@@ -134,7 +134,7 @@ SYMBOLS = {
     "sphb200_acoustic_1st_half_initialize": (_I, [_CTX, C.POINTER(FluidArgs), _F, _P]),
     "sphb200_acoustic_1st_half_interact": (_I, [_CTX, C.POINTER(FluidArgs), _F, _I, _P]),
     "sphb200_linear_correction_matrix": (_I, [_CTX, C.POINTER(FluidArgs), _F, _P]),
-    "sphb200_pack_correction_records": (_I, [_CTX, _U32, _P, _P, _P]),
+    "sphb200_pack_correction_records": (_I, [_CTX, _U32, _P, _P, _P, _P]),
     "sphb200_stream_create": (_I, [C.POINTER(_P)]),
     "sphb200_slab_select": (_I, [_CTX, C.POINTER(MeshT), _P, _U32, _U32, _I, _I, _P, _P, _P, _P]),
     "sphb200_stream_create_with_priority": (_I, [C.POINTER(_P), _I]),

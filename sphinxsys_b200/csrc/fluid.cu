@@ -47,7 +47,8 @@ struct FArgs
     const float4 *posvolref; // (x, y, z, VolRef)
     float4 *rec2;            // 32-byte records (x, y, z, Vol | vx, vy, vz, -)
     float *vol, *mass, *rho, *p, *C, *Cdot, *vol_ref, *Csum, *B;
-    float4 *brec; // LinearCorrectionRecord: (Bxx, Bxy, Bxz, Byy | Byz, Bzz, -, -), the symmetric part of B as one 32-byte gather record, or nullptr
+    int p_in_brec; // 1: the correction variants run: the 1st-half initialize also keeps the pressure slot of brec current
+    float4 *brec; // LinearCorrectionRecord: (Bxx, Bxy, Bxz, Byy | Byz, Bzz, p, -): the symmetric part of B and the pressure as one 32-byte gather record, or nullptr
     // wall
     u32 n_wall;
     const float4 *w_pos, *w_posvol, *w_posvolref, *w_vel, *w_acc, *w_n;
@@ -188,6 +189,7 @@ static int make_fargs(sphb200_context *ctx, const sphb200_fluid_args_t *s, FArgs
     a->lim_k = m.limiter_coeff * a->inv_c_ave;
     a->free_surface = m.free_surface;
     a->dim = k.dim;
+    a->p_in_brec = m.correction && a->brec;
     return 0;
 }
 
@@ -762,7 +764,9 @@ __global__ void __launch_bounds__(256) k_a1_init(FArgs a, float dt)
         a.C[i] = C;
     }
     a.rho[i] = rho;
-    a.p[i] = a.p0 * (rho / a.rho0 - 1.0f);
+    const float p = a.p0 * (rho / a.rho0 - 1.0f);
+    a.p[i] = p;
+    if (a.p_in_brec) a.brec[2ull * i + 1].z = p; // the neighbours of the correction variants read p here (k_a1_interact)
     float4 d = a.dpos[i], v = a.vel[i];
     d.x += v.x * dt * 0.5f; d.y += v.y * dt * 0.5f; d.z += v.z * dt * 0.5f;
     a.dpos[i] = d;
@@ -793,19 +797,19 @@ __global__ void __launch_bounds__(FL_THREADS, FL_MIN_BLOCKS) k_a1_interact(FArgs
         {
             // sum_j dWV (p_i B_j + p_j B_i) e = p_i sum_j dWV B_j e + B_i sum_j p_j dWV e: B_i leaves the pair loop, and B_j
             // comes as ONE 32-byte record of its six distinct entries (B is the regularised inverse of the symmetric
-            // sum_j r (x) r dW V / |r|: symmetric up to rounding; the record holds (B + B^T) / 2) instead of nine 4-byte gathers
+            // sum_j r (x) r dW V / |r|: symmetric up to rounding; the record holds (B + B^T) / 2) instead of nine 4-byte gathers;
+            // p_j rides in the record's seventh float (k_a1_init keeps it current): two gathers per pair, 48 bytes
             float4 bas[NB_U], bbs[NB_U];
             float ax = 0.f, ay = 0.f, az = 0.f; // sum_j dWV B_j e
             for_neighbors(
                 idx, cnt,
                 [&](int u, u32 j) {
                     xjs[u] = a.posvol[j];
-                    pjs[u] = a.p[j];
                     load_rec2(a.brec, j, bas[u], bbs[u]);
                 },
                 [&](int u, bool valid) {
                     const float4 xj = xjs[u], ba = bas[u], bb = bbs[u];
-                    const float p_j = pjs[u];
+                    const float p_j = bb.z; // written by k_a1_init of this acoustic step (and refreshed on ghost planes with the record)
                     float dx = xi.x - xj.x, dy = xi.y - xj.y, dz = xi.z - xj.z;
                     float r2 = dx * dx + dy * dy + dz * dz;
                     float r, inv_r;
@@ -1260,24 +1264,31 @@ __global__ void __launch_bounds__(FL_THREADS) k_linear_correction(FArgs a, KTab 
     if (a.brec) // the gather record of the 1st-half interaction (k_a1_interact): the symmetric part, six entries
     {
         a.brec[2ull * i] = make_float4(B[0], 0.5f * (B[1] + B[3]), 0.5f * (B[2] + B[6]), B[4]);
-        a.brec[2ull * i + 1] = make_float4(0.5f * (B[5] + B[7]), B[8], 0.f, 0.f);
+        a.brec[2ull * i + 1] = make_float4(0.5f * (B[5] + B[7]), B[8], a.p ? a.p[i] : 0.f, 0.f);
     }
 }
 
 // the gather record of given matrices (matrices written outside the library, e.g. uploaded by the host)
-__global__ void __launch_bounds__(256) k_pack_correction_records(u32 n, const float *__restrict__ B, float4 *__restrict__ rec)
+__global__ void __launch_bounds__(256)
+    k_pack_correction_records(u32 n, const float *__restrict__ B, const float *__restrict__ p, float4 *__restrict__ rec)
 {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float b[9];
-    load_mat(B, i, b);
-    rec[2ull * i] = make_float4(b[0], 0.5f * (b[1] + b[3]), 0.5f * (b[2] + b[6]), b[4]);
-    rec[2ull * i + 1] = make_float4(0.5f * (b[5] + b[7]), b[8], 0.f, 0.f);
+    if (B)
+    {
+        float b[9];
+        load_mat(B, i, b);
+        rec[2ull * i] = make_float4(b[0], 0.5f * (b[1] + b[3]), 0.5f * (b[2] + b[6]), b[4]);
+        rec[2ull * i + 1].x = 0.5f * (b[5] + b[7]);
+        rec[2ull * i + 1].y = b[8];
+    }
+    if (p) rec[2ull * i + 1].z = p[i];
 }
-extern "C" int sphb200_pack_correction_records(sphb200_context_t *ctx, uint32_t n, const float *B, void *correction_record, void *stream)
+extern "C" int sphb200_pack_correction_records(sphb200_context_t *ctx, uint32_t n, const float *B, const float *pressure,
+                                               void *correction_record, void *stream)
 {
-    SPH_CHECK_ARG(ctx, ctx && (n == 0 || (B && correction_record)), "null pointer");
-    if (n) SPH_LAUNCH(ctx, k_pack_correction_records, sph_blocks(n, 256), 256, 0, stream, n, B, (float4 *)correction_record);
+    SPH_CHECK_ARG(ctx, ctx && (n == 0 || ((B || pressure) && correction_record)), "null pointer");
+    if (n) SPH_LAUNCH(ctx, k_pack_correction_records, sph_blocks(n, 256), 256, 0, stream, n, B, pressure, (float4 *)correction_record);
     return 0;
 }
 
