@@ -125,12 +125,17 @@ class WallSlab
     // ([lo, hi], empty if hi < lo) and the storage `bound`. Returns false if what is stored suffices.
     bool plan(int X0, int X1, size_t bound, int &lo, int &hi) const
     {
-        const int need_lo = std::max(0, X0 - depth_), need_hi = std::min(planes_ - 1, X1 - 1 + depth_);
+        return planWallPlanes(below_.data(), planes_, depth_, margin_, X0, X1, bound, lo, hi);
+    }
+    // the same on a plain histogram: below[x] = wall particles in planes < x, x = 0 .. planes (tests/test_host_logic_cpu.py)
+    static bool planWallPlanes(const uint64_t *below, int planes, int depth, int margin, int X0, int X1, size_t bound, int &lo, int &hi)
+    {
+        const int need_lo = std::max(0, X0 - depth), need_hi = std::min(planes - 1, X1 - 1 + depth);
         if (hi >= lo && need_lo >= lo && need_hi <= hi) return false;
-        lo = std::max(0, need_lo - margin_);
-        hi = std::min(planes_ - 1, need_hi + margin_);
+        lo = std::max(0, need_lo - margin);
+        hi = std::min(planes - 1, need_hi + margin);
         // the margin only saves reloads: give it up where the storage is too small for it
-        while ((size_t)(below_[hi + 1] - below_[lo]) > bound && (lo < need_lo || hi > need_hi))
+        while ((size_t)(below[hi + 1] - below[lo]) > bound && (lo < need_lo || hi > need_hi))
         {
             if (lo < need_lo) ++lo;
             if (hi > need_hi) --hi;

@@ -170,6 +170,18 @@ extern "C"
             *seam = ring.seam;
         });
     }
+    // host-only: the wall planes a rank stores for the fluid planes [X0, X1) (WallSlab::plan). below[x] = wall particles in the
+    // planes < x (planes + 1 entries); lo_hi: the planes stored now on entry (hi < lo: none), the planes to store on return;
+    // *reload = 1 if the subset has to be loaded
+    int sphck_wall_slab_plan(const uint64_t *below, int planes, int depth, int margin, int X0, int X1, uint64_t bound, int32_t *lo_hi,
+                             int32_t *reload)
+    {
+        return guarded([&] {
+            int lo = lo_hi[0], hi = lo_hi[1];
+            *reload = WallSlab::planWallPlanes(below, planes, depth, margin, X0, X1, (size_t)bound, lo, hi) ? 1 : 0;
+            lo_hi[0] = lo, lo_hi[1] = hi;
+        });
+    }
     int sphck_limit_cut_moves(const int32_t *old_cuts, const int32_t *wanted, int nranks, int32_t *cuts_out)
     {
         return guarded([&] {

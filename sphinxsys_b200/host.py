@@ -126,6 +126,20 @@ def aligned_periodic_mesh(lower, upper, cutoff, dim=3):
     return mesh, seam
 
 
+def wall_slab_plan(per_plane, depth, margin, X0, X1, bound, stored=(0, -1)):
+    """(lo, hi, reload): the wall planes a rank stores for the fluid planes [X0, X1) given the planes stored now (WallSlab::plan in
+    include/sphinxsys_ck/dambreak_case.h; host arithmetic only)."""
+    h = np.ascontiguousarray(per_plane, dtype=np.uint64)
+    below = np.concatenate([[0], np.cumsum(h)]).astype(np.uint64)
+    lo_hi = np.array(stored, dtype=np.int32)
+    reload = C.c_int32(0)
+    fn = load().sphck_wall_slab_plan
+    fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.POINTER(C.c_int32)]
+    if fn(below.ctypes.data, int(h.size), int(depth), int(margin), int(X0), int(X1), int(bound), lo_hi.ctypes.data, C.byref(reload)) != 0:
+        raise capi.SphB200Error("wall_slab_plan failed: " + load().sphck_last_error().decode())
+    return int(lo_hi[0]), int(lo_hi[1]), bool(reload.value)
+
+
 def limit_cut_moves(old_cuts, wanted):
     """Cuts a re-balancing step may take from `old_cuts` towards `wanted` (SlabDecomposition::recut: neighbour transfers only)."""
     o = np.ascontiguousarray(old_cuts, dtype=np.int32)

@@ -250,3 +250,42 @@ def test_ring_ownership_never_loses_or_duplicates_a_particle(n_side, nranks):
             pl_l, pl_r = plane(own[lft]["x"]), plane(own[rgt]["x"])
             assert np.array_equal(own[r]["gl"], np.sort(own[lft]["gid"][pl_l == cuts[lft + 1] - 1])), f"step {step}: left ghost plane of rank {r}"
             assert np.array_equal(own[r]["gr"], np.sort(own[rgt]["gid"][pl_r == cuts[rgt]])), f"step {step}: right ghost plane of rank {r}"
+
+
+def test_wall_slab_planning_invariants():
+    """WallSlab::plan (include/sphinxsys_ck/dambreak_case.h): the wall planes a rank stores around its fluid planes. Whatever the
+    histogram, the cuts and the storage bound: (i) the planes the contact search can reach are always stored; (ii) the margin is
+    kept in full when the storage allows it and given up only as far as needed; (iii) nothing is reloaded while the stored planes
+    still cover the need (re-cuts inside the margin are free); (iv) if even the needed planes exceed the bound, exactly those are
+    planned (the load then fails loudly in BaseParticles, not silently here)."""
+    from sphinxsys_b200 import host
+    rng = np.random.default_rng(17)
+    for _ in range(300):
+        planes = int(rng.integers(8, 120))
+        h = rng.integers(0, 500, planes).astype(np.uint64)
+        h[rng.random(planes) < 0.2] = 0  # empty planes (no wall there)
+        below = np.concatenate([[0], np.cumsum(h)])
+        depth, margin = int(rng.integers(1, 3)), int(rng.integers(0, 6))
+        X0 = int(rng.integers(0, planes - 1))
+        X1 = int(rng.integers(X0 + 1, planes + 1))
+        need_lo, need_hi = max(0, X0 - depth), min(planes - 1, X1 - 1 + depth)
+        need = int(below[need_hi + 1] - below[need_lo])
+        full_lo, full_hi = max(0, need_lo - margin), min(planes - 1, need_hi + margin)
+        full = int(below[full_hi + 1] - below[full_lo])
+        bound = int(rng.integers(max(need // 2, 1), full + 50))
+        lo, hi, reload = host.wall_slab_plan(h, depth, margin, X0, X1, bound)
+        assert reload and lo <= need_lo and hi >= need_hi                                       # (i)
+        stored = int(below[hi + 1] - below[lo])
+        if bound >= full:
+            assert (lo, hi) == (full_lo, full_hi)                                              # (ii) whole margin
+        elif bound >= need:
+            assert stored <= bound and full_lo <= lo and hi <= full_hi                         # (ii) margin given up as far as needed
+        else:
+            assert (lo, hi) == (need_lo, need_hi)                                              # (iv)
+        # (iii) a re-cut that stays inside the stored planes does not reload and leaves them as they are
+        if lo + depth < hi - depth:
+            Y0 = int(rng.integers(lo + depth, hi - depth + 1)) if lo > 0 else int(rng.integers(0, hi - depth + 1))
+            Y1 = int(rng.integers(Y0 + 1, hi - depth + 2)) if hi < planes - 1 else int(rng.integers(Y0 + 1, planes + 1))
+            if max(0, Y0 - depth) >= lo and min(planes - 1, Y1 - 1 + depth) <= hi:
+                lo2, hi2, reload2 = host.wall_slab_plan(h, depth, margin, Y0, Y1, bound, stored=(lo, hi))
+                assert not reload2 and (lo2, hi2) == (lo, hi)
